@@ -1,0 +1,246 @@
+"""ctypes binding of libgsched.so (include/gsched.h).  No torch types cross this
+boundary: numpy arrays in, numpy arrays out.  There is no CPU fallback -- if the
+shared library or a CUDA device is missing every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .log_manager import JOB_DTYPE, ROW_DTYPE, SPAN_DTYPE
+
+GS_MAX_QUEUES = 8
+SCHEDULES = {"fifo": 0, "sjf": 1, "dlas": 2, "dlas-gpu": 3, "gittins": 4}
+SCHEMES = {"yarn": 0, "count": 1}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsched.so")
+
+
+class GsCluster(C.Structure):
+    _fields_ = [("num_switch", C.c_int32), ("num_node_p_switch", C.c_int32),
+                ("num_gpu_p_node", C.c_int32), ("num_cpu_p_node", C.c_int32),
+                ("mem_p_node", C.c_int32), ("gpu_mem_cap_mib", C.c_int32),
+                ("enable_network_costs", C.c_int32), ("cpu_per_task", C.c_int32),
+                ("mem_per_task", C.c_int32), ("reserved0", C.c_int32),
+                ("bandwidth", C.c_double), ("internode_latency", C.c_double)]
+
+    @property
+    def n_nodes(self):
+        return self.num_switch * self.num_node_p_switch
+
+
+class GsPolicy(C.Structure):
+    _fields_ = [("schedule", C.c_int32), ("scheme", C.c_int32), ("num_queue", C.c_int32),
+                ("gittins_n", C.c_int32), ("queue_limit", C.c_double * GS_MAX_QUEUES),
+                ("gittins_delta", C.c_double), ("gittins_data", C.c_void_p),
+                ("gittins_index", C.c_void_p)]
+
+
+class GsRunStats(C.Structure):
+    _fields_ = [("ticks", C.c_int64), ("events", C.c_int64), ("finished", C.c_int64),
+                ("started", C.c_int64), ("placement_evals", C.c_int64), ("done", C.c_int32),
+                ("status", C.c_int32), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("d2h_ms", C.c_double)]
+
+
+NODE_DTYPE = np.dtype([("busy_mask", "<u8"), ("cpu_used", "<i4"), ("mem_used", "<i4")])
+JOBREQ_DTYPE = np.dtype([("gpus", "<i4"), ("gpu_per_task", "<i4"), ("mem_bytes", "<i8")])
+
+
+def make_cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8, num_cpu_p_node=128,
+                 mem_p_node=512, gpu_memory_capacity=32, enable_network_costs=False,
+                 bandwidth=1250, internode_latency=0.015, cpu_per_task=12, mem_per_task=60):
+    """gs_cluster from the reference's flag values (infrastructure.py:26-43; job.py:105-106)."""
+    return GsCluster(int(num_switch), int(num_node_p_switch), int(num_gpu_p_node),
+                     int(num_cpu_p_node), int(mem_p_node), int(gpu_memory_capacity) * 1024,
+                     1 if enable_network_costs else 0, int(cpu_per_task), int(mem_per_task), 0,
+                     float(bandwidth), float(internode_latency))
+
+
+def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), gittins_delta=3250.0):
+    p = GsPolicy()
+    p.schedule = SCHEDULES[schedule]
+    p.scheme = SCHEMES[scheme]
+    p.num_queue = int(num_queue)
+    for i, v in enumerate(list(queue_limit)[:GS_MAX_QUEUES]):
+        p.queue_limit[i] = float(v)
+    p.gittins_delta = float(gittins_delta)
+    return p
+
+
+class GsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def load_library(path=None):
+    """Load libgsched.so and declare its prototypes; raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise GsError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    i32p, i64p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    lib.gs_abi_version.restype = C.c_int
+    lib.gs_last_error.restype = C.c_char_p
+    lib.gs_last_error.argtypes = [C.c_void_p]
+    lib.gs_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.gs_destroy.argtypes = [C.c_void_p]
+    lib.gs_destroy.restype = None
+    lib.gs_config_sim.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsCluster), C.POINTER(GsPolicy)]
+    lib.gs_load_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64, i32p, i32p, i32p, f64p, i64p,
+                                  f64p, f64p, i32p]
+    lib.gs_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.gs_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsRunStats)]
+    lib.gs_fetch_rows.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    lib.gs_fetch_jobs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, i32p]
+    lib.gs_fetch_spans.argtypes = [C.c_void_p, C.c_int, i64p, C.c_void_p, C.c_int64, i64p]
+    lib.gs_place_batch.argtypes = [C.c_void_p, C.POINTER(GsCluster), C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_int64, i32p, i32p, i64p, i32p, f64p]
+    lib.gs_net_cost.argtypes = [C.c_void_p, C.POINTER(GsCluster), C.c_int64, i64p, i32p,
+                                C.POINTER(C.c_uint8), i32p, f64p, f64p, f64p]
+    for name in ("gs_create", "gs_config_sim", "gs_load_trace", "gs_run", "gs_stats",
+                 "gs_fetch_rows", "gs_fetch_jobs", "gs_fetch_spans", "gs_place_batch",
+                 "gs_net_cost"):
+        getattr(lib, name).restype = C.c_int
+    if lib.gs_abi_version() != 1:
+        raise GsError("libgsched.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class Engine:
+    """One handle == `nsims` independent replicas on one CUDA device."""
+
+    def __init__(self, device=0, nsims=1):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self.nsims = int(nsims)
+        self._n = [0] * self.nsims
+        self._keep = []
+        rc = self.lib.gs_create(int(device), self.nsims, C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.gs_last_error(None)
+            self.h = C.c_void_p()
+            raise GsError(f"gs_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.gs_last_error(self.h)
+            raise GsError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.gs_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def config(self, sim, cluster: GsCluster, policy: GsPolicy | None = None):
+        policy = policy or make_policy()
+        self._check(self.lib.gs_config_sim(self.h, sim, C.byref(cluster), C.byref(policy)), "gs_config_sim")
+
+    def load_trace(self, sim, table):
+        def arr(a, dt):
+            return None if a is None else np.ascontiguousarray(a, dtype=dt)
+        a = arr(table.arrive_tick, np.int32)
+        g = arr(table.gpus, np.int32)
+        c = arr(table.gpu_per_task, np.int32)
+        d = arr(table.duration, np.float64)
+        m = arr(table.mem_bytes, np.int64)
+        mm = arr(table.model_mb, np.float64)
+        it = arr(table.iterations, np.float64)
+        ps = arr(table.ps_count, np.int32)
+        self._n[sim] = int(table.n)
+        self._check(self.lib.gs_load_trace(
+            self.h, sim, int(table.n), _ptr(a, C.c_int32), _ptr(g, C.c_int32), _ptr(c, C.c_int32),
+            _ptr(d, C.c_double), _ptr(m, C.c_int64), _ptr(mm, C.c_double), _ptr(it, C.c_double),
+            _ptr(ps, C.c_int32)), "gs_load_trace")
+
+    def run(self, max_ticks=0, rows_cap=0):
+        self._check(self.lib.gs_run(self.h, int(max_ticks), int(rows_cap)), "gs_run")
+
+    def stats(self, sim=0) -> GsRunStats:
+        st = GsRunStats()
+        self._check(self.lib.gs_stats(self.h, sim, C.byref(st)), "gs_stats")
+        return st
+
+    def fetch_rows(self, sim=0, first=0, count=None):
+        if count is None:
+            count = self.stats(sim).ticks - first
+        rows = np.empty(int(count), dtype=ROW_DTYPE)
+        self._check(self.lib.gs_fetch_rows(self.h, sim, int(first), int(count),
+                                           rows.ctypes.data_as(C.c_void_p)), "gs_fetch_rows")
+        return rows
+
+    def fetch_jobs(self, sim=0):
+        n = self._n[sim]
+        recs = np.empty(n, dtype=JOB_DTYPE)
+        order = np.empty(max(n, 1), dtype=np.int32)
+        self._check(self.lib.gs_fetch_jobs(self.h, sim, recs.ctypes.data_as(C.c_void_p),
+                                           _ptr(order, C.c_int32)), "gs_fetch_jobs")
+        return recs, order[:int(self.stats(sim).finished)]
+
+    def fetch_spans(self, sim=0, cap=None):
+        n = self._n[sim]
+        off = np.zeros(n + 1, dtype=np.int64)
+        used = C.c_int64(0)
+        if cap is None:       # ask for the size first
+            self._check(self.lib.gs_fetch_spans(self.h, sim, _ptr(off, C.c_int64), None, 0,
+                                                C.byref(used)), "gs_fetch_spans")
+            cap = used.value
+        spans = np.empty(int(cap), dtype=SPAN_DTYPE)
+        self._check(self.lib.gs_fetch_spans(self.h, sim, _ptr(off, C.c_int64),
+                                            spans.ctypes.data_as(C.c_void_p), int(cap),
+                                            C.byref(used)), "gs_fetch_spans")
+        return off, spans[:used.value]
+
+    def place_batch(self, cluster: GsCluster, nodes, jobs, task_off=None):
+        nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        jobs = np.ascontiguousarray(jobs, dtype=JOBREQ_DTYPE)
+        b = len(jobs)
+        first = np.empty(b, dtype=np.int32)
+        used = np.empty(b, dtype=np.int32)
+        task_node = None
+        if task_off is not None:
+            task_off = np.ascontiguousarray(task_off, dtype=np.int64)
+            task_node = np.empty(int(task_off[-1]), dtype=np.int32)
+        ms = C.c_double(0.0)
+        self._check(self.lib.gs_place_batch(
+            self.h, C.byref(cluster), nodes.ctypes.data_as(C.c_void_p), len(nodes),
+            jobs.ctypes.data_as(C.c_void_p), b, _ptr(first, C.c_int32), _ptr(used, C.c_int32),
+            _ptr(task_off, C.c_int64), _ptr(task_node, C.c_int32), C.byref(ms)), "gs_place_batch")
+        return first, used, task_node, ms.value
+
+    def net_cost(self, cluster: GsCluster, task_off, task_node, is_ps, ps_count, model_mb, iterations):
+        task_off = np.ascontiguousarray(task_off, dtype=np.int64)
+        task_node = np.ascontiguousarray(task_node, dtype=np.int32)
+        is_ps = None if is_ps is None else np.ascontiguousarray(is_ps, dtype=np.uint8)
+        ps_count = np.ascontiguousarray(ps_count, dtype=np.int32)
+        model_mb = np.ascontiguousarray(model_mb, dtype=np.float64)
+        iterations = np.ascontiguousarray(iterations, dtype=np.float64)
+        b = len(ps_count)
+        out = np.empty(b, dtype=np.float64)
+        self._check(self.lib.gs_net_cost(
+            self.h, C.byref(cluster), b, _ptr(task_off, C.c_int64), _ptr(task_node, C.c_int32),
+            _ptr(is_ps, C.c_uint8), _ptr(ps_count, C.c_int32), _ptr(model_mb, C.c_double),
+            _ptr(iterations, C.c_double), _ptr(out, C.c_double)), "gs_net_cost")
+        return out

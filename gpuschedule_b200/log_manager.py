@@ -1,0 +1,188 @@
+"""Output surface: cluster.csv (one row per tick), job.csv (finish order) and the
+four header-only CSVs, byte-identical to the reference's writer
+(/root/reference/log_manager.py:5-155): same headers, `\\r\\n` line ends (Python
+csv default, quirk Q16), same value types so that str() prints the same text
+(`[0.05556386]` arrays, `nan`, `0` vs `19.0`; quirks Q14, Q15, Q22).
+
+The per-object API (`LogInfo`, `step_cluster`, `jcts`) is kept for drop-in use;
+the engine uses the batch forms (`write_cluster_rows`, `write_job_rows`) that
+format whole runs at once from the integer aggregates the device produced.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+CLUSTER_HEADER = ["delta", "num_idle_nodes", "num_busy_nodes", "num_busy_gpus",
+                  "num_idle_gpus", "avg_gpu_utilization", "avg_gpu_memory_allocated",
+                  "avg_pending_time", "median_pending_time", "max_pending_time",
+                  "num_running_jobs", "num_queuing_jobs", "num_finish_jobs"]
+JOB_HEADER = ["job_id", "num_gpu", "submit_time", "start_time", "end_time",
+              "original_duration", "actual_duration", "jct", "preempt"]
+EOL = "\r\n"
+
+# numpy dtype mirroring include/gsched.h: gs_tick_row / gs_job_rec / gs_span
+ROW_DTYPE = np.dtype([("now", "<i4"), ("idle_nodes", "<i4"), ("busy_nodes", "<i4"),
+                      ("busy_gpus", "<i4"), ("idle_gpus", "<i4"), ("running", "<i4"),
+                      ("queued", "<i4"), ("finished", "<i4"), ("mem_busy_bytes", "<i8"),
+                      ("pend_sum", "<i8"), ("pend_max", "<i4"), ("pend_med_lo", "<i4"),
+                      ("pend_med_hi", "<i4"), ("reserved", "<i4")])
+JOB_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"),
+                      ("preempt", "<i4"), ("duration", "<f8")])
+SPAN_DTYPE = np.dtype([("node", "<i4"), ("ntasks", "<i4"), ("devmask", "<u8")])
+assert ROW_DTYPE.itemsize == 64 and JOB_DTYPE.itemsize == 24 and SPAN_DTYPE.itemsize == 16
+
+
+class LogInfo:
+    """Same fields as the reference record (log_manager.py:5-30)."""
+
+    def __init__(self, num_idle_nodes, num_busy_nodes, num_busy_gpus, num_idle_gpus,
+                 avg_gpu_utilization, avg_gpu_memory_allocated, avg_pending_time,
+                 median_pending_time, max_pending_time, num_running_jobs,
+                 num_queuing_jobs, num_finish_jobs):
+        self.idle_ns = num_idle_nodes
+        self.busy_ns = num_busy_nodes
+        self.busy_gs = num_busy_gpus
+        self.idle_gs = num_idle_gpus
+        self.avg_g_utils = avg_gpu_utilization
+        self.avg_g_mem = avg_gpu_memory_allocated
+        self.avg_pending = avg_pending_time
+        self.median_pending = median_pending_time
+        self.max_pending = max_pending_time
+        self.num_running_jobs = num_running_jobs
+        self.num_queuing_jobs = num_queuing_jobs
+        self.num_finish_jobs = num_finish_jobs
+
+    def fields(self, delta):
+        return [delta, self.idle_ns, self.busy_ns, self.busy_gs, self.idle_gs,
+                self.avg_g_utils, self.avg_g_mem, self.avg_pending, self.median_pending,
+                self.max_pending, self.num_running_jobs, self.num_queuing_jobs,
+                self.num_finish_jobs]
+
+
+def _line(values):
+    return ",".join(v if isinstance(v, str) else str(v) for v in values) + EOL
+
+
+def pending_columns(rows):
+    """avg / median / max pending text from the integer aggregates, using the
+    reference's float expressions (jobs_manager.py:72-87)."""
+    q = rows["queued"]
+    avg = rows["pend_sum"].astype(np.float64) / (q.astype(np.float64) + 1e-9)
+    med = (rows["pend_med_lo"].astype(np.float64) + rows["pend_med_hi"].astype(np.float64)) / 2.0
+    avg_t = [repr(float(x)) for x in avg]
+    med_t = [repr(float(m)) if k > 0 else "nan" for m, k in zip(med, q)]
+    max_t = [repr(float(m)) if k > 0 else "0" for m, k in zip(rows["pend_max"], q)]
+    return avg_t, med_t, max_t
+
+
+def memory_column(rows, total_cap_mib):
+    """sum(min(cap, MiB)) / sum(cap) (schedule.py:115,121; device.py:56-62)."""
+    out = []
+    for b, busy in zip(rows["mem_busy_bytes"], rows["busy_gpus"]):
+        if busy == 0:
+            out.append("0.0")
+        else:
+            out.append(str(np.float64(int(b) / 1048576.0) / total_cap_mib))
+    return out
+
+
+def cluster_lines(rows, util_text, total_cap_mib):
+    avg_t, med_t, max_t = pending_columns(rows)
+    mem_t = memory_column(rows, total_cap_mib)
+    cols = [rows[k].astype(str) for k in ("now", "idle_nodes", "busy_nodes", "busy_gpus", "idle_gpus")]
+    tail = [rows[k].astype(str) for k in ("running", "queued", "finished")]
+    lines = []
+    for i in range(len(rows)):
+        lines.append(",".join((cols[0][i], cols[1][i], cols[2][i], cols[3][i], cols[4][i],
+                               util_text[i], mem_t[i], avg_t[i], med_t[i], max_t[i],
+                               tail[0][i], tail[1][i], tail[2][i])))
+    return lines
+
+
+def job_lines(table, recs, finish_order):
+    """One line per finished job in finish order (log_manager.py:137-153)."""
+    lines = []
+    for j in finish_order:
+        r = recs[j]
+        dur = float(r["duration"])
+        actual = max(float(table.duration[j]), dur)          # Job.get_duration job.py:206-210
+        lines.append(",".join((table.label[j], table.num_gpu_text[j], str(int(table.submit[j])),
+                               str(int(r["start"])), str(int(r["end"])), repr(dur), repr(actual),
+                               str(int(r["jct"])), str(int(r["preempt"])))))
+    return lines
+
+
+class LogManager:
+    def __init__(self, log_path, flags):
+        self.log_path = log_path
+        self.flags = flags
+        self.is_count = getattr(flags, "scheme", "yarn") == "count"
+        self.cluster_stats_header = list(CLUSTER_HEADER)
+        self.job_stats_header = list(JOB_HEADER)
+
+    def init(self, infrastructure):
+        p = self.log_path
+        self.log_cluster = os.path.join(p, "cluster.csv")
+        self.log_job = os.path.join(p, "job.csv")
+        with open(self.log_cluster, "w", newline="") as f:
+            f.write(_line(self.cluster_stats_header))
+        if not self.is_count:
+            n_nodes = len(infrastructure.nodes)
+            self.log_cpu = os.path.join(p, "cpu.csv")
+            self.log_gpu = os.path.join(p, "gpu.csv")
+            self.log_network = os.path.join(p, "network.csv")
+            self.log_mem = os.path.join(p, "memory.csv")
+            with open(self.log_cpu, "w", newline="") as f:
+                f.write(_line(["time"] + ["cpu%d" % i for i in range(n_nodes)]))
+            with open(self.log_gpu, "w", newline="") as f:
+                f.write(_line(["time"] + ["gpu%d" % i for i in range(infrastructure.get_total_gpus())]))
+            with open(self.log_mem, "w", newline="") as f:
+                f.write(_line(["time", "max", "99th", "95th", "med"]))
+            with open(self.log_network, "w", newline="") as f:
+                titles = ["time"]
+                for i in range(n_nodes):
+                    titles += ["in%d" % i, "out%d" % i]
+                f.write(_line(titles))
+        with open(self.log_job, "w", newline="") as f:
+            f.write(_line(self.job_stats_header))
+        assert os.path.exists(self.log_cluster)
+
+    # ---- per-object API (drop-in)
+    def step_cluster(self, loginfo, delta):
+        with open(self.log_cluster, "a", newline="") as f:
+            f.write(_line(loginfo.fields(delta)))
+
+    def jcts(self, finished_jobs):
+        assert len(finished_jobs) > 0, ValueError("No finished jobs")
+        with open(self.log_job, "a", newline="") as f:
+            for _, j in finished_jobs.items():
+                f.write(_line([j.job_id, j.gpus, j.submit_time, j.start_time, j.end_time,
+                               j.duration, j.get_duration(), j.time_processed(), j.migration_count]))
+        time.sleep(1)
+
+    # ---- batch API (engine)
+    def write_cluster_rows(self, rows, util_text, total_cap_mib):
+        lines = cluster_lines(rows, util_text, total_cap_mib)
+        with open(self.log_cluster, "a", newline="") as f:
+            if lines:
+                f.write(EOL.join(lines) + EOL)
+
+    def write_job_rows(self, table, recs, finish_order):
+        assert len(finish_order) > 0, ValueError("No finished jobs")
+        lines = job_lines(table, recs, finish_order)
+        with open(self.log_job, "a", newline="") as f:
+            f.write(EOL.join(lines) + EOL)
+
+
+def render_cluster_csv(rows, util_text, total_cap_mib):
+    """Whole cluster.csv as text (header + rows)."""
+    body = cluster_lines(rows, util_text, total_cap_mib)
+    return _line(CLUSTER_HEADER) + (EOL.join(body) + EOL if body else "")
+
+
+def render_job_csv(table, recs, finish_order):
+    body = job_lines(table, recs, finish_order)
+    return _line(JOB_HEADER) + (EOL.join(body) + EOL if body else "")

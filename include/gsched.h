@@ -1,0 +1,197 @@
+/*
+ * gsched.h -- C ABI of libgsched.so, the sm_100a discrete-event engine that
+ * replaces the per-tick hot path of matthewygf/GPUSchedule.
+ *
+ * The reference has no FFI: its "operator API" is the Python loop object and
+ * three dict registries.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   gs_run            Scheduler.start()            core/scheduling/schedule.py:178-215
+ *                     (gen_jobs jobs_manager.py:228-241, _schedule schedule.py:40-60,
+ *                      schedule_fifo algorithm.py:189-202, ms_yarn_placement :28-32,
+ *                      step jobs_manager.py:143-148, release_finished_jobs
+ *                      schedule.py:141-162, _construct_info schedule.py:95-133)
+ *   gs_place_batch    placement_algorithms['yarn'](infrastructure, job, scheme)
+ *                     core/scheduling/algorithm.py:28-32,301-393,396-417
+ *   gs_net_cost       calculate_network_costs(infrastructure, job)
+ *                     core/network/network_service.py:3-39
+ *   gs_load_trace     JobsManager.gen_jobs' per-row Job(...) construction
+ *                     core/jobs/jobs_manager.py:233-239 (rows arrive pre-sorted by
+ *                     the host ingest, job_generator.py:181-193)
+ *   gs_config_sim     Infrastructure(FLAGS)        infra/infrastructure.py:26-58
+ *
+ * Conventions: every function returns 0 on success and a negative gs_status
+ * on failure (message via gs_last_error); nothing throws or exits across the
+ * boundary.  The caller owns every host buffer and passes sizes explicitly;
+ * the library owns all device memory and its CUDA stream.  One handle is
+ * bound to one CUDA device and must be driven by one host thread at a time;
+ * handles are independent.  There is NO CPU fallback: without a usable CUDA
+ * device gs_create fails with GS_ERR_CUDA.
+ */
+#ifndef GSCHED_H_
+#define GSCHED_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+#define GS_MAX_QUEUES 8
+#define GS_MAX_GPUS_PER_NODE 64
+
+typedef enum {
+  GS_OK = 0,
+  GS_ERR_ARG = -1,      /* bad argument / unsupported configuration          */
+  GS_ERR_CUDA = -2,     /* CUDA runtime or driver error                      */
+  GS_ERR_STATE = -3,    /* call order (e.g. gs_run before gs_load_trace)     */
+  GS_ERR_CAPACITY = -4, /* an output buffer is too small                     */
+  GS_ERR_NCCL = -5      /* NCCL error in the sharded multi-GPU path          */
+} gs_status;
+
+/* scheduling policies (run_sim.py:37-49 names) and placement schemes (:25-36) */
+enum { GS_SCHED_FIFO = 0, GS_SCHED_SJF = 1, GS_SCHED_DLAS = 2,
+       GS_SCHED_DLAS_GPU = 3, GS_SCHED_GITTINS = 4 };
+enum { GS_SCHEME_YARN = 0, GS_SCHEME_COUNT = 1 };
+
+/* Cluster description == the flags Infrastructure reads (infrastructure.py:26-43). */
+typedef struct gs_cluster {
+  int32_t num_switch;
+  int32_t num_node_p_switch;
+  int32_t num_gpu_p_node;        /* G <= GS_MAX_GPUS_PER_NODE                  */
+  int32_t num_cpu_p_node;
+  int32_t mem_p_node;
+  int32_t gpu_mem_cap_mib;       /* gpu_memory_capacity * 1024 (infrastructure.py:36) */
+  int32_t enable_network_costs;  /* schedule.py:49                             */
+  int32_t cpu_per_task;          /* 12 in the reference (job.py:105)           */
+  int32_t mem_per_task;          /* 60 in the reference (job.py:106)           */
+  int32_t reserved0;
+  double bandwidth;              /* MB/s   (run_sim.py:59)                     */
+  double internode_latency;      /* s      (run_sim.py:65)                     */
+} gs_cluster;
+
+typedef struct gs_policy {
+  int32_t schedule;              /* GS_SCHED_*                                 */
+  int32_t scheme;                /* GS_SCHEME_*                                */
+  int32_t num_queue;             /* dlas MLFQ depth (<= GS_MAX_QUEUES)          */
+  int32_t gittins_n;             /* entries in the gittins tables              */
+  double queue_limit[GS_MAX_QUEUES]; /* dlas thresholds (README.md:57-62)      */
+  double gittins_delta;          /* service quantum for the index (3250)       */
+  const double *gittins_data;    /* host ptr, sorted sample + sentinel         */
+  const double *gittins_index;   /* host ptr, index per sample + 0.0           */
+} gs_policy;
+
+/* One row of integer aggregates per simulated tick: everything LogInfo
+ * (log_manager.py:5-30) carries except the RNG column, as integers so that the
+ * host can apply the reference's own float expressions.  64 bytes.            */
+typedef struct gs_tick_row {
+  int32_t now;            /* 'delta' column (already incremented, schedule.py:193) */
+  int32_t idle_nodes;     /* nodes that never hosted a placement (node.py:93-97)  */
+  int32_t busy_nodes;
+  int32_t busy_gpus;
+  int32_t idle_gpus;
+  int32_t running;
+  int32_t queued;
+  int32_t finished;
+  int64_t mem_busy_bytes; /* sum over busy devices of min(cap, task memory_max)   */
+  int64_t pend_sum;       /* sum of pending ticks over the queue                  */
+  int32_t pend_max;       /* 0 when the queue is empty                            */
+  int32_t pend_med_lo;    /* the two middle pending values (equal when odd)       */
+  int32_t pend_med_hi;
+  int32_t reserved;
+} gs_tick_row;
+
+/* Per-job result, 24 bytes: what LogManager.jcts prints (log_manager.py:143-153). */
+typedef struct gs_job_rec {
+  int32_t start;          /* start_time; -1 if the job never started             */
+  int32_t end;            /* end_time;   -1 if it never finished                 */
+  int32_t jct;            /* time_processed() at completion                      */
+  int32_t preempt;        /* migration_count (1 for a never-preempted job)       */
+  double duration;        /* job.duration after network cost (job.py:196-197)    */
+} gs_job_rec;
+
+/* Where a job's tasks ran: one record per (job, node).  16 bytes.               */
+typedef struct gs_span {
+  int32_t node;           /* 0-based node index (reference node_id = node + 1)   */
+  int32_t ntasks;
+  uint64_t devmask;       /* devices of that node held by the job                */
+} gs_span;
+
+typedef struct gs_run_stats {
+  int64_t ticks;          /* rows produced so far                                */
+  int64_t events;         /* arrivals + starts + completions (+preempt/resume)   */
+  int64_t finished;       /* jobs completed                                      */
+  int64_t started;
+  int64_t placement_evals;/* (job,node) candidate evaluations                    */
+  int32_t done;           /* 1 when the loop's exit condition was reached        */
+  int32_t status;         /* 0 or a gs_status raised inside the kernel           */
+  double kernel_ms;       /* CUDA-event time of the engine kernel(s)             */
+  double h2d_ms, d2h_ms;  /* CUDA-event time of the copies of the last calls     */
+} gs_run_stats;
+
+/* cluster state record for the stateless placement entry point. 16 bytes.       */
+typedef struct gs_node {
+  uint64_t busy_mask;     /* bit d set <=> device d has a task                   */
+  int32_t cpu_used;
+  int32_t mem_used;
+} gs_node;
+
+typedef struct gs_jobreq {
+  int32_t gpus;           /* Job.gpus                                            */
+  int32_t gpu_per_task;   /* Job.gpu_per_worker                                  */
+  int64_t mem_bytes;      /* memory_max                                          */
+} gs_jobreq;
+
+typedef struct gs_engine *gs_handle;
+
+int gs_abi_version(void);
+const char *gs_last_error(gs_handle h);  /* h may be NULL: last creation error    */
+
+/* A handle simulates `nsims` independent replicas on CUDA device `device`.      */
+int gs_create(int device, int nsims, gs_handle *out);
+void gs_destroy(gs_handle h);
+
+int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, const gs_policy *policy);
+
+/* Trace of one replica, rows in admission order (arrive_tick non-decreasing).
+ * model_mb / iterations / ps_count may be NULL (no network term).               */
+int gs_load_trace(gs_handle h, int sim, int64_t n,
+                  const int32_t *arrive_tick, const int32_t *gpus,
+                  const int32_t *gpu_per_task, const double *duration,
+                  const int64_t *mem_bytes, const double *model_mb,
+                  const double *iterations, const int32_t *ps_count);
+
+/* Advance every replica by at most max_ticks ticks (<=0: until done).  Row
+ * storage on the device is sized by rows_cap per replica at the first call.    */
+int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap);
+
+int gs_stats(gs_handle h, int sim, gs_run_stats *out);
+
+/* Copy results of one replica to caller-owned host buffers (any may be NULL).  */
+int gs_fetch_rows(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out);
+int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out /* n */,
+                  int32_t *finish_order_out /* n, first `finished` valid */);
+int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out /* n+1 */,
+                   gs_span *spans_out, int64_t spans_cap, int64_t *spans_used);
+
+/* Stateless candidate scoring: evaluate b jobs against ONE cluster state.
+ * first_node[i] = node of a single-node first fit, or the first node of a
+ * cross-node fill, or -1 if the job cannot be placed; task_node (optional)
+ * receives the node of each task at task_off[i] .. task_off[i+1].               */
+int gs_place_batch(gs_handle h, const gs_cluster *cluster, const gs_node *nodes, int32_t m,
+                   const gs_jobreq *jobs, int64_t b, int32_t *first_node,
+                   int32_t *nodes_used, const int64_t *task_off, int32_t *task_node,
+                   double *kernel_ms);
+
+/* PS<->worker transfer time for a batch of placed jobs.  task_node holds the
+ * node of every task (segments given by task_off), is_ps marks PS tasks.        */
+int gs_net_cost(gs_handle h, const gs_cluster *cluster, int64_t b,
+                const int64_t *task_off, const int32_t *task_node, const uint8_t *is_ps,
+                const int32_t *ps_count, const double *model_mb, const double *iterations,
+                double *extra_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSCHED_H_ */

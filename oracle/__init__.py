@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE -- the CPU checker for libgsched.so.
+
+ctypes wrapper around oracle/liboracle.so (oracle/gsched_oracle.c), the plain-C
+restatement of the reference's live fifo+yarn tick loop.  It may be imported
+only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` arm.  The product package never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gpuschedule_b200.capi import JOBREQ_DTYPE, NODE_DTYPE, GsCluster
+from gpuschedule_b200.log_manager import JOB_DTYPE, ROW_DTYPE, SPAN_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "gsched_oracle.c")
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "gsched.h")
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return LIB_PATH
+    subprocess.run(["gcc", "-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-shared",
+                    "-o", LIB_PATH, src, "-lm"], check=True, cwd=_HERE)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.oracle_run_fifo.restype = C.c_int64
+        _lib.oracle_place_one.restype = C.c_int
+        _lib.oracle_net_cost.restype = C.c_double
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleResult:
+    pass
+
+
+def run_fifo(cluster: GsCluster, table, rows_cap=None):
+    """Run the restated Scheduler.start() on a JobTable; returns an OracleResult
+    with the same arrays the engine's fetch_* calls give."""
+    n = table.n
+    if rows_cap is None:
+        rows_cap = int(table.arrive_tick[-1] if n else 0) + int(np.ceil(table.duration).sum() if n else 0) + n + 16
+        rows_cap = min(rows_cap, 1 << 26)
+    rows = np.zeros(rows_cap, dtype=ROW_DTYPE)
+    recs = np.zeros(max(n, 1), dtype=JOB_DTYPE)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    task_off = table.task_offsets()
+    task_node = np.full(max(int(task_off[-1]), 1), -1, dtype=np.int32)
+    task_mask = np.zeros(max(int(task_off[-1]), 1), dtype=np.uint64)
+    nfin = C.c_int64(0)
+    events = C.c_int64(0)
+    evals = C.c_int64(0)
+    arr = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    a, g, c = arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32)
+    d, m = arr(table.duration, np.float64), arr(table.mem_bytes, np.int64)
+    mm, it, ps = arr(table.model_mb, np.float64), arr(table.iterations, np.float64), arr(table.ps_count, np.int32)
+    ticks = lib().oracle_run_fifo(C.byref(cluster), C.c_int64(n), _p(a), _p(g), _p(c), _p(d), _p(m),
+                                  _p(mm), _p(it), _p(ps), _p(rows), C.c_int64(rows_cap), _p(recs),
+                                  _p(order), C.byref(nfin), _p(task_off), _p(task_node), _p(task_mask),
+                                  C.byref(events), C.byref(evals))
+    if ticks < 0:
+        raise RuntimeError(f"oracle_run_fifo failed: {ticks}")
+    r = OracleResult()
+    r.ticks = int(ticks)
+    r.rows = rows[:ticks]
+    r.recs = recs[:n]
+    r.finish_order = order[:nfin.value]
+    r.events = events.value
+    r.evals = evals.value
+    r.task_off, r.task_node, r.task_mask = task_off, task_node, task_mask
+    r.span_off, r.spans = spans_from_tasks(n, task_off, task_node, task_mask)
+    return r
+
+
+def spans_from_tasks(n, task_off, task_node, task_mask):
+    """Collapse the per-task placement log into gs_span records (job, node)."""
+    off = np.zeros(n + 1, dtype=np.int64)
+    out = []
+    for j in range(n):
+        a, b = int(task_off[j]), int(task_off[j + 1])
+        cur = None
+        for t in range(a, b):
+            nd = int(task_node[t])
+            if nd < 0:
+                break
+            if cur is not None and cur[0] == nd:
+                cur[1] += 1
+                cur[2] |= int(task_mask[t])
+            else:
+                cur = [nd, 1, int(task_mask[t])]
+                out.append(cur)
+        off[j + 1] = len(out)
+    spans = np.zeros(len(out), dtype=SPAN_DTYPE)
+    for i, (nd, k, mk) in enumerate(out):
+        spans[i] = (nd, k, mk)
+    return off, spans
+
+
+def place_one(cluster: GsCluster, nodes, job):
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    jr = np.zeros(1, dtype=JOBREQ_DTYPE)
+    jr[0] = job
+    tasks = int(jr[0]["gpus"]) // int(jr[0]["gpu_per_task"])
+    task_node = np.full(max(tasks, 1), -1, dtype=np.int32)
+    first = C.c_int32(-1)
+    used = C.c_int32(0)
+    ok = lib().oracle_place_one(C.byref(cluster), _p(nodes), C.c_int32(len(nodes)), _p(jr),
+                                C.byref(first), C.byref(used), _p(task_node))
+    return bool(ok), first.value, used.value, task_node[:tasks]
+
+
+def net_cost(cluster: GsCluster, task_node, is_ps, ps_count, model_mb, iterations):
+    task_node = np.ascontiguousarray(task_node, dtype=np.int32)
+    is_ps = None if is_ps is None else np.ascontiguousarray(is_ps, dtype=np.uint8)
+    return float(lib().oracle_net_cost(C.byref(cluster), C.c_int32(len(task_node)), _p(task_node),
+                                       _p(is_ps), C.c_int32(int(ps_count)), C.c_double(float(model_mb)),
+                                       C.c_double(float(iterations))))
