@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- simulated events/sec on the BASELINE workload.
+
+Workload (config.workload): R independent replicas per GPU of the 100k-job
+synthetic trace (SURVEY 8d generator, distinct seeds) on the 4x32x8 cluster,
+fifo policy + yarn placement -- the only policy/scheme pair the reference can
+execute and therefore the one with a pinned bit-exact oracle.
+One "step" = one full simulation of every replica (one persistent-kernel
+launch, one warp per replica).  A single replica is latency bound by
+construction (<= 1 placement per simulated tick), so throughput comes from
+replicas -- the sweeps the reference's execute.py runs serially.
+
+  value  : events/s with traces resident in HBM (device-timed with CUDA events
+           around the engine kernel + state reset, max over ranks)
+  e2e    : events/s through the C ABI with HOST buffers: every step re-uploads
+           every trace (pinned staging -> H2D) and reads back every statistics
+           row, job record, finish order and placement span (D2H)
+  impl=reference : the CPU oracle port (oracle/gsched_oracle.c, a restatement of
+           the reference's Python loop) on all host cores, one replica per thread
+
+Launch:  python bench.py --gpus N --steps K --warmup W   (torchrun for N > 1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "simulated events/sec (100k-job trace, 4x32x8 cluster)"
+UNIT = "events/s"
+BASE_SEED = 1
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fast_table(n_jobs, seed, rate=0.5):
+    """Synthetic columns -> JobTable without the pandas round trip (rows are generated in
+    arrival order already; only tie order inside a tick differs from a CSV ingest)."""
+    from gpuschedule_b200 import ingest, tracegen
+    c = tracegen.synth_columns(n_jobs, seed=seed, rate=rate)
+    nt = c["normalized_time"].astype(np.float64) / 10000.0
+    return ingest.JobTable(
+        n=n_jobs, label=None, num_gpu_text=None,
+        arrive_tick=np.ceil(nt).astype(np.int32), submit=nt.astype(np.int32),
+        gpus=c["used_gpus"].astype(np.int32), gpu_per_task=c["gpu_per_container"].astype(np.int32),
+        duration=np.ascontiguousarray(c["minutes"] * 0.5), mem_bytes=c["memory_max"].astype(np.int64),
+        util_avg=c["gpu_utilization_avg"], util_max=c["gpu_utilization_max"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_to_done(eng, rows_cap):
+    while True:
+        eng.run(0, rows_cap)
+        if all(eng.stats(s).done for s in range(eng.nsims)):
+            return
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from gpuschedule_b200 import capi
+    from gpuschedule_b200.log_manager import JOB_DTYPE, ROW_DTYPE, SPAN_DTYPE
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier_sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    R, n = args.replicas, args.jobs
+    cluster = capi.make_cluster(4, 32, 8)
+    t0 = time.time()
+    tables = [fast_table(n, BASE_SEED + rank * R + r) for r in range(R)]
+    log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
+    eng = capi.Engine(device=local, nsims=R)
+    for r in range(R):
+        eng.config(r, cluster)
+        eng.load_trace(r, tables[r])
+
+    # ---- warm-up (also sizes the per-replica row window so one launch completes a run)
+    run_to_done(eng, 0)
+    ticks = [eng.stats(r).ticks for r in range(R)]
+    rows_cap = max(ticks) + 64
+    for _ in range(max(args.warmup - 1, 2)):
+        eng.reset()
+        run_to_done(eng, rows_cap)
+
+    # ---- timed: K steps, traces resident in HBM
+    sampler = ClockSampler(local)
+    launches0 = eng.launch_count()
+    barrier_sync()
+    sampler.start()
+    w0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        eng.reset()
+        run_to_done(eng, rows_cap)
+        dev_ms += eng.stats(0).kernel_ms
+    barrier_sync()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    st = [eng.stats(r) for r in range(R)]
+    events_rank = sum(s.events for s in st)
+    ticks_rank = sum(s.ticks for s in st)
+    evals_rank = sum(s.placement_evals for s in st)
+    spans_rank = 0
+    for r in range(min(R, 4)):
+        spans_rank += len(eng.fetch_spans(r)[1])
+    spans_rank = spans_rank / min(R, 4) * R
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    events_all = sum_over_ranks(events_rank)
+    value = events_all / (dev_ms / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel (gs_tick_kernel), per launch, this rank's GPU
+    # algorithmic bytes: job table in (28 B/job) + job record + finish order out (28 B/job)
+    # + one 16-B span per (job,node) + one 64-B statistics row per tick   
+    alg_bytes = R * n * 56 + spans_rank * 16 + ticks_rank * 64
+    peak, peak_src = peaks()
+    ach = alg_bytes / (dev_ms / args.steps / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "kernel": "gs_tick_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "ticks_per_s": ticks_rank * world / (dev_ms / args.steps / 1e3),
+                "candidate_evals_per_s": evals_rank * world / (dev_ms / args.steps / 1e3)}
+
+    # ---- end to end through the C ABI with host buffers
+    T = max(ticks) + 64
+    pin_rows = capi.PinnedBuffer(T * ROW_DTYPE.itemsize)
+    pin_jobs = capi.PinnedBuffer(n * JOB_DTYPE.itemsize)
+    pin_ord = capi.PinnedBuffer(n * 4)
+    rows_v = pin_rows.view(ROW_DTYPE, T)
+    jobs_v = pin_jobs.view(JOB_DTYPE, n)
+    ord_v = pin_ord.view(np.int32, n)
+    h2d = d2h = 0
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    checksum = 0
+    barrier_sync()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h2d = d2h = 0
+        for r in range(R):
+            eng.load_trace(r, tables[r])
+            h2d += n * 28
+        run_to_done(eng, rows_cap)
+        for r in range(R):
+            s = eng.stats(r)
+            rows = eng.fetch_rows(r, 0, s.ticks, out=rows_v)
+            recs, order = eng.fetch_jobs(r, out_recs=jobs_v, out_order=ord_v)
+            span_off, spans = eng.fetch_spans(r)
+            checksum += int(rows["finished"][-1]) + int(recs["end"][0]) + int(order[-1]) + len(spans)
+            d2h += s.ticks * 64 + n * 24 + s.finished * 4 + len(spans) * 16 + n * 56
+    barrier_sync()
+    e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / e2e_steps
+    e2e = {"value": events_all / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(sum_over_ranks(h2d)), "d2h_bytes_per_step": int(sum_over_ranks(d2h)),
+           "steps": e2e_steps, "timing": "wall clock between barrier+synchronize, max over ranks",
+           "checksum": checksum}
+
+    # ---- CPU baseline: the oracle port, 1 thread, bounded sample (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        t_cpu, ev_cpu, k = 0.0, 0, 0
+        while t_cpu < args.cpu_seconds and k < R:
+            c0 = time.perf_counter()
+            ref = oracle.run_fifo(cluster, tables[k], rows_cap=T + 64, want_spans=False)
+            t_cpu += time.perf_counter() - c0
+            ev_cpu += ref.events
+            assert ref.ticks == ticks[k] and ref.events == st[k].events, "engine/oracle disagree"
+            k += 1
+        cpu = {"value": ev_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{k} replica(s) of the {n}-job trace, full runs, oracle/gsched_oracle.c single thread",
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 (+f64 durations)",
+            "data": "synthetic",
+            "config": {"workload": f"{n}-job synthetic trace x {R} replicas/GPU (distinct seeds), 4x32x8 cluster, fifo+yarn",
+                       "jobs_per_replica": n, "replicas_per_gpu": R, "cluster": "4x32x8", "policy": "fifo",
+                       "scheme": "yarn", "parallelism": f"replicas x{world} GPUs, no data-path collective",
+                       "l2": "inputs+outputs per step (%.1f GB/GPU) exceed the 126 MB L2" % (alg_bytes / 1e9),
+                       "events_per_step": events_all, "ticks_per_step": ticks_rank * world},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    pin_rows.free(); pin_jobs.free(); pin_ord.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference(args):
+    """The reference arm: the CPU port of the reference's loop on all host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import concurrent.futures as cf
+    import oracle
+    from gpuschedule_b200 import capi
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(cores, args.cpu_threads or cores))
+    n = args.jobs
+    cluster = capi.make_cluster(4, 32, 8)
+    tables = [fast_table(n, BASE_SEED + r) for r in range(threads)]
+    oracle.lib()
+
+    def one(t):
+        return oracle.run_fifo(cluster, t, want_spans=False).events          # ctypes releases the GIL
+
+    with cf.ThreadPoolExecutor(threads) as ex:
+        for _ in range(args.warmup):
+            list(ex.map(one, tables))
+        t0 = time.perf_counter()
+        events = 0
+        for _ in range(args.steps):
+            events += sum(ex.map(one, tables))
+        dt = time.perf_counter() - t0
+    value = events / dt
+    sample = f"{threads} replicas of the {n}-job trace per step (one per thread), full runs"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+           "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int32/int64 (+f64 durations)", "data": "synthetic",
+           "config": {"workload": f"{n}-job synthetic trace, 4x32x8 cluster, fifo+yarn", "jobs_per_replica": n,
+                      "cluster": "4x32x8", "policy": "fifo", "scheme": "yarn"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                            "note": "oracle/gsched_oracle.c: C restatement of the reference's Python loop "
+                                    "(the Python reference itself: 186 events/s at N=10k, BASELINE.md)"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--jobs", type=int, default=100000)
+    ap.add_argument("--replicas", type=int, default=1184, help="replicas per GPU (one warp each)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

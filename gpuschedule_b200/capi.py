@@ -75,6 +75,29 @@ class GsError(RuntimeError):
     pass
 
 
+class PinnedBuffer:
+    """Page-locked host memory from gs_host_alloc, viewed as numpy arrays."""
+
+    def __init__(self, nbytes):
+        lib = load_library()
+        self.ptr = C.c_void_p()
+        rc = lib.gs_host_alloc(int(nbytes), C.byref(self.ptr))
+        if rc != 0:
+            raise GsError(f"gs_host_alloc failed ({rc})")
+        self.nbytes = int(nbytes)
+        self._lib = lib
+        self._raw = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value)
+
+    def view(self, dtype, count, offset=0):
+        return np.frombuffer(self._raw, dtype=dtype, count=int(count), offset=int(offset))
+
+    def free(self):
+        if self.ptr and self.ptr.value:
+            self._raw = None
+            self._lib.gs_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
 _lib = None
 
 
@@ -111,7 +134,12 @@ def load_library(path=None):
                                    C.c_void_p, C.c_int64, i32p, i32p, i64p, i32p, f64p]
     lib.gs_net_cost.argtypes = [C.c_void_p, C.POINTER(GsCluster), C.c_int64, i64p, i32p,
                                 C.POINTER(C.c_uint8), i32p, f64p, f64p, f64p]
-    for name in ("gs_create", "gs_config_sim", "gs_load_trace", "gs_run", "gs_stats",
+    lib.gs_reset.argtypes = [C.c_void_p]
+    lib.gs_launch_count.argtypes = [C.c_void_p]
+    lib.gs_launch_count.restype = C.c_int64
+    lib.gs_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.gs_host_free.argtypes = [C.c_void_p]
+    for name in ("gs_reset", "gs_host_alloc", "gs_host_free", "gs_create", "gs_config_sim", "gs_load_trace", "gs_run", "gs_stats",
                  "gs_fetch_rows", "gs_fetch_jobs", "gs_fetch_spans", "gs_place_batch",
                  "gs_net_cost"):
         getattr(lib, name).restype = C.c_int
@@ -175,26 +203,53 @@ class Engine:
             _ptr(d, C.c_double), _ptr(m, C.c_int64), _ptr(mm, C.c_double), _ptr(it, C.c_double),
             _ptr(ps, C.c_int32)), "gs_load_trace")
 
+    def reset(self):
+        self._check(self.lib.gs_reset(self.h), "gs_reset")
+
+    def launch_count(self):
+        return int(self.lib.gs_launch_count(self.h))
+
     def run(self, max_ticks=0, rows_cap=0):
         self._check(self.lib.gs_run(self.h, int(max_ticks), int(rows_cap)), "gs_run")
+
+    def run_all(self, rows_cap=0, collect_rows=True):
+        """Run every replica to its exit condition.  The device keeps a window of
+        `rows_cap` statistics rows per replica; it is drained after every launch.
+        Returns one concatenated row array per replica (or None)."""
+        parts = [[] for _ in range(self.nsims)]
+        seen = [0] * self.nsims
+        while True:
+            self.run(0, rows_cap)
+            pending = 0
+            for s in range(self.nsims):
+                st = self.stats(s)
+                if collect_rows and st.ticks > seen[s]:
+                    parts[s].append(self.fetch_rows(s, seen[s], st.ticks - seen[s]))
+                seen[s] = st.ticks
+                pending += 0 if st.done else 1
+            if pending == 0:
+                break
+        if not collect_rows:
+            return None
+        return [np.concatenate(p) if p else np.empty(0, dtype=ROW_DTYPE) for p in parts]
 
     def stats(self, sim=0) -> GsRunStats:
         st = GsRunStats()
         self._check(self.lib.gs_stats(self.h, sim, C.byref(st)), "gs_stats")
         return st
 
-    def fetch_rows(self, sim=0, first=0, count=None):
+    def fetch_rows(self, sim=0, first=0, count=None, out=None):
         if count is None:
             count = self.stats(sim).ticks - first
-        rows = np.empty(int(count), dtype=ROW_DTYPE)
+        rows = np.empty(int(count), dtype=ROW_DTYPE) if out is None else out[:int(count)]
         self._check(self.lib.gs_fetch_rows(self.h, sim, int(first), int(count),
                                            rows.ctypes.data_as(C.c_void_p)), "gs_fetch_rows")
         return rows
 
-    def fetch_jobs(self, sim=0):
+    def fetch_jobs(self, sim=0, out_recs=None, out_order=None):
         n = self._n[sim]
-        recs = np.empty(n, dtype=JOB_DTYPE)
-        order = np.empty(max(n, 1), dtype=np.int32)
+        recs = np.empty(n, dtype=JOB_DTYPE) if out_recs is None else out_recs[:n]
+        order = np.empty(max(n, 1), dtype=np.int32) if out_order is None else out_order
         self._check(self.lib.gs_fetch_jobs(self.h, sim, recs.ctypes.data_as(C.c_void_p),
                                            _ptr(order, C.c_int32)), "gs_fetch_jobs")
         return recs, order[:int(self.stats(sim).finished)]

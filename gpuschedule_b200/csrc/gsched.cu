@@ -1,0 +1,1006 @@
+// gsched.cu -- sm_100a discrete-event engine + C ABI (include/gsched.h).
+//
+// Execution model (B200-first, not a translation of the Python object graph):
+//   * one WARP owns one simulation replica ("sim").  The cluster's node table
+//     lives in shared memory as (busy-device mask, charged task slots) -- the
+//     reference's cpu_used/mem_used always move together in units of 12/60 per
+//     task (job.py:105-106, node.py:204-205), so both collapse into one slot
+//     counter k with  free_slots = min(cpu/12, mem/60) - k.
+//   * lanes stripe over nodes; single-node first fit is a ballot + ffs (argmin
+//     over node id), cross-node fill is a warp prefix sum over per-node task
+//     capacities with a cut-off -- no per-device objects are ever walked.
+//   * all reference per-tick re-scans (pandas filters, _construct_info,
+//     pending-time aging, time_processed stepping) are replaced by closed
+//     forms and O(1) incremental counters; completions come from a timing
+//     wheel keyed by finish tick, appended in start order.
+//   * every tick emits one 64-byte gs_tick_row of integer aggregates; the job
+//     table is streamed once from HBM (arrival-ordered SoA), results are
+//     written once (24-byte gs_job_rec + 16-byte gs_span per (job,node)).
+//   * thousands of replicas run per launch (one warp each, 148 SMs x many
+//     warps); a single replica is latency bound by construction.
+//
+// Reference semantics followed (paths relative to the reference root):
+//   Scheduler.start            core/scheduling/schedule.py:178-215
+//   Scheduler._schedule        core/scheduling/schedule.py:40-60
+//   schedule_fifo              core/scheduling/algorithm.py:189-202
+//   ms_yarn_placement          core/scheduling/algorithm.py:28-32
+//   try_single_node_alloc_ms   core/scheduling/algorithm.py:396-417
+//   try_cross_node_alloc_ms    core/scheduling/algorithm.py:301-393
+//   Node fit/reserve/release   infra/node.py:71-91,109-127,146-171,200-275
+//   Device.can_fit             infra/device.py:67-77
+//   gen_jobs / step / finish   core/jobs/jobs_manager.py:65-87,143-148,228-250
+//   calculate_network_costs    core/network/network_service.py:3-39
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "gsched.h"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------ device state
+
+struct JobState {   // 32 B, written at start, read once at completion
+  int next;         // next job in the same finish-tick bucket (start order)
+  int node0;        // first span inline (most jobs have exactly one)
+  unsigned long long mask0;
+  int ntasks0;
+  int span_cnt;
+  int span_first;   // index into the span pool
+  int pad;
+};
+
+struct SimDev {
+  // ---- configuration
+  int M, G, K;          // nodes, gpus/node, task slots/node = min(cpu/cpu_pt, mem/mem_pt)
+  int netcost, n, wheel_mask, policy, pad0;
+  long long cap_bytes;  // Device.memory in bytes
+  long long fit_limit;  // a task fits an empty device iff mem_bytes < fit_limit
+  double bandwidth, latency;
+  // ---- trace (read-only)
+  const int *arrive, *gpus, *gpc, *ps;
+  const double *dur, *model_mb, *iters;
+  const long long *memb;
+  // ---- results / scratch
+  gs_job_rec *rec;
+  JobState *jst;
+  int *stack, *fin, *wheel_head, *wheel_tail;
+  gs_span *spans;
+  gs_tick_row *rows;
+  unsigned long long *nbusy;  // persisted node table (between launches)
+  int *nk;                    // bit31 = node ever hosted a placement (node.py:93-97, never cleared)
+  long long span_cap, rows_cap;
+  // ---- loop state (persisted)
+  int delta, p, top, running, finished, ever, busy_gpus, done, status, pad1;
+  long long mem_busy, sum_arr, span_used, events, evals, started, ticks, row_first;
+};
+
+#define EVER_BIT 0x80000000u
+
+__device__ __forceinline__ int lowest_bits(unsigned long long idle, int cnt, unsigned long long *take) {
+  // select the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
+  unsigned long long m = idle, t = 0;
+  for (int i = 0; i < cnt; ++i) { unsigned long long b = m & (~m + 1ull); t |= b; m ^= b; }
+  *take = t;
+  return cnt;
+}
+
+__device__ __forceinline__ int node_cap(unsigned long long busy, int k, int G, int K, int gpc) {
+  int idle = G - __popcll(busy);
+  int slots = K - (int)(k & ~EVER_BIT);
+  int byg = (gpc == 1) ? idle : idle / gpc;
+  int c = min(byg, slots);
+  return c > 0 ? c : 0;
+}
+
+// One warp advances one replica.  Dynamic shared memory: per warp M*(8+4) bytes.
+__global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sim = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (sim >= nsims) return;
+  SimDev &S = sims[sim];
+  if (S.done || S.status != 0) return;
+
+  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)warp * smem_stride);
+  const int M = S.M, G = S.G, K = S.K, n = S.n;
+  int *kk = reinterpret_cast<int *>(busy + M);
+  for (int i = lane; i < M; i += 32) { busy[i] = S.nbusy[i]; kk[i] = S.nk[i]; }
+  __syncwarp();
+
+  const int *__restrict__ g_arrive = S.arrive;
+  const int *__restrict__ g_gpus = S.gpus;
+  const int *__restrict__ g_gpc = S.gpc;
+  const double *__restrict__ g_dur = S.dur;
+  const long long *__restrict__ g_memb = S.memb;
+  gs_job_rec *rec = S.rec;
+  JobState *jst = S.jst;
+  int *stack = S.stack, *fin = S.fin, *wh = S.wheel_head, *wt = S.wheel_tail;
+  gs_span *spans = S.spans;
+  const int wmask = S.wheel_mask;
+  const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
+  const int netcost = S.netcost;
+  const unsigned long long gmask = (G >= 64) ? ~0ull : ((1ull << G) - 1ull);
+
+  int delta = S.delta, p = S.p, top = S.top, running = S.running, finished = S.finished;
+  int ever = S.ever, busy_gpus = S.busy_gpus, status = 0;
+  long long mem_busy = S.mem_busy, sum_arr = S.sum_arr, span_used = S.span_used;
+  long long events = S.events, evals = S.evals, started = S.started, ticks = S.ticks;
+  const long long row_first = ticks;
+  gs_tick_row *rows = S.rows;
+  const long long rows_cap = S.rows_cap;
+  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+
+  // arrival window: lane l holds arrive[wbase + l]
+  int wbase = p & ~31;
+  int arr_w = (wbase + lane < n) ? g_arrive[wbase + lane] : 0x7fffffff;
+
+  // cached queue head
+  int head = -1, hg = 0, hgpc = 1, htasks = 0;
+  long long hmemb = 0;
+  double hdur = 0.0;
+  bool head_valid = false;
+  int bottom_arr = (top > 0) ? g_arrive[stack[0]] : 0;
+
+  bool done = (n - p) + running == 0 && ticks > 0;
+  if (n == 0) done = true;
+
+  while (!done && budget > 0) {
+    if (ticks - row_first >= rows_cap) break;   // row window full: host drains and relaunches
+    // ---------------- A. admit arrivals (gen_jobs + head insert)
+    {
+      int cnt = 0;
+      int q = p;
+      while (q < n) {
+        int idx = wbase + lane;
+        unsigned b = __ballot_sync(FULL, idx >= q && idx < n && arr_w <= delta);
+        int c = __popc(b);
+        cnt += c; q += c;
+        if (q < wbase + 32 || q >= n) break;
+        wbase += 32;
+        arr_w = (wbase + lane < n) ? g_arrive[wbase + lane] : 0x7fffffff;
+      }
+      if (cnt > 0) {
+        // batch [p, p+cnt) lands AHEAD of the queue, first of the batch on top (quirk Q2)
+        for (int i = lane; i < cnt; i += 32) stack[top + i] = p + cnt - 1 - i;
+        if (top == 0) bottom_arr = delta;
+        head = p; head_valid = false;
+        top += cnt; p += cnt;
+        sum_arr += (long long)cnt * delta;
+        events += cnt;
+        __syncwarp();
+      }
+    }
+    // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
+    if (top > 0) {
+      if (!head_valid) {
+        if (head < 0) head = stack[top - 1];
+        hg = g_gpus[head]; hgpc = g_gpc[head]; hmemb = g_memb[head]; hdur = g_dur[head];
+        htasks = hg / hgpc;
+        head_valid = true;
+      }
+      const bool placeable = hmemb < fit_limit;   // Device.can_fit on an empty device
+      bool ok = false;
+      int first_node = -1, nspans = 0, span_first = (int)span_used;
+      unsigned long long mask0 = 0; int ntasks0 = 0;
+      if (hg <= G) {
+        // try_single_node_alloc_ms: first node (id order) that fits the whole job
+        int found = -1;
+        for (int base = 0; base < M; base += 32) {
+          int nd = base + lane;
+          bool fit = false;
+          if (nd < M) {
+            int idle = G - __popcll(busy[nd]);
+            int slots = K - (int)(kk[nd] & ~EVER_BIT);
+            fit = idle >= hg && slots >= htasks;
+          }
+          unsigned b = __ballot_sync(FULL, fit);
+          if (!placeable) {          // quirk Q21: cpu/mem charged for every task, never refunded
+            if (fit) kk[nd] += htasks;
+            continue;
+          }
+          if (b) { found = base + __ffs(b) - 1; break; }
+        }
+        if (found >= 0) {
+          ok = true; first_node = found; nspans = 1; ntasks0 = htasks;
+          bool fresh = false;
+          if (lane == (found & 31)) {
+            unsigned long long idle = ~busy[found] & gmask, take;
+            lowest_bits(idle, hg, &take);
+            busy[found] |= take;
+            unsigned kv = (unsigned)kk[found];
+            kk[found] = (int)((kv + htasks) | EVER_BIT);
+            mask0 = take;
+            fresh = !(kv & EVER_BIT);
+          }
+          mask0 = __shfl_sync(FULL, mask0, found & 31);
+          ever += __popc(__ballot_sync(FULL, fresh));
+          evals += found + 1;
+        } else {
+          evals += M;
+        }
+      } else {
+        // try_cross_node_alloc_ms: walk nodes in id order, each takes what it can hold
+        int cum = 0, last_base = -1;
+        if (placeable) {
+          for (int base = 0; base < M; base += 32) {
+            int nd = base + lane;
+            int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
+            cum += __reduce_add_sync(FULL, c);
+            if (cum >= htasks) { last_base = base; break; }
+          }
+        } else {
+          for (int base = 0; base < M; base += 32) {   // quirk Q21, cross-node flavour: one task charged per node
+            int nd = base + lane;
+            if (nd < M && node_cap(busy[nd], kk[nd], G, K, hgpc) > 0) kk[nd] += 1;
+          }
+        }
+        if (last_base >= 0) {
+          // pass 1 proved the job fits: commit (a failed walk is rolled back exactly by the
+          // reference, algorithm.py:378-387, so no state changes in that case)
+          ok = true;
+          if (span_used + min(htasks, M) > S.span_cap) { status = GS_ERR_CAPACITY; break; }
+          int rem = htasks, last_node = 0;
+          for (int base = 0; base <= last_base; base += 32) {
+            int nd = base + lane;
+            int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
+            int incl = c;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            int take = min(c, max(rem - (incl - c), 0));
+            unsigned tb = __ballot_sync(FULL, take > 0);
+            bool fresh = false;
+            if (take > 0) {
+              unsigned long long idle = ~busy[nd] & gmask, tk;
+              lowest_bits(idle, take * hgpc, &tk);
+              busy[nd] |= tk;
+              unsigned kv = (unsigned)kk[nd];
+              kk[nd] = (int)((kv + take) | EVER_BIT);
+              fresh = !(kv & EVER_BIT);
+              int slot = nspans + __popc(tb & ((1u << lane) - 1u));
+              gs_span sp; sp.node = nd; sp.ntasks = take; sp.devmask = tk;
+              spans[span_first + slot] = sp;
+              if (slot == 0) { mask0 = tk; ntasks0 = take; first_node = nd; }
+            }
+            ever += __popc(__ballot_sync(FULL, fresh));
+            if (tb) last_node = base + 31 - __clz(tb);
+            nspans += __popc(tb);
+            int tot = __shfl_sync(FULL, incl, 31);
+            rem -= min(rem, tot);
+          }
+          {  // first-span fields live in whichever lane owned slot 0
+            int src = __ffs(__ballot_sync(FULL, first_node >= 0)) - 1;
+            mask0 = __shfl_sync(FULL, mask0, src);
+            ntasks0 = __shfl_sync(FULL, ntasks0, src);
+            first_node = __shfl_sync(FULL, first_node, src);
+          }
+          evals += last_node + 1;
+        } else {
+          evals += M;
+        }
+      }
+      __syncwarp();
+      if (ok) {
+        // ---- commit: pop, network cost, start (algorithm.py:198-200, schedule.py:49-54,164-167)
+        const int j = head;
+        double dur2 = hdur;
+        if (netcost && S.ps != nullptr && S.ps[j] > 1) {
+          // (model_size/bandwidth + cross*latency) * (iterations*2.0), network_service.py:34-37
+          double mps = __ddiv_rn(S.model_mb[j], S.bandwidth);
+          double nis = __dmul_rn((double)nspans, S.latency);
+          double rt = __dmul_rn(S.iters[j], 2.0);
+          dur2 = __dadd_rn(hdur, __dmul_rn(__dadd_rn(mps, nis), rt));
+        }
+        double eff = dur2 > hdur ? dur2 : hdur;               // Job.get_duration (job.py:206-210)
+        double cl = ceil(eff);
+        int need = cl < 1.0 ? 1 : (cl > 1.0e9 ? 0x7fffffff : (int)cl);   // quirk Q11
+        if (need > wmask) { status = GS_ERR_ARG; break; }
+        const int endt = delta + need;
+        if (hg <= G) {
+          if (span_used + 1 > S.span_cap) { status = GS_ERR_CAPACITY; break; }
+          if (lane == 0) { gs_span sp; sp.node = first_node; sp.ntasks = ntasks0; sp.devmask = mask0; spans[span_first] = sp; }
+        }
+        span_used += nspans;
+        if (lane == 0) {
+          rec[j].start = delta; rec[j].end = -1; rec[j].jct = need; rec[j].preempt = 1; rec[j].duration = dur2;
+          JobState js; js.next = -1; js.node0 = first_node; js.mask0 = mask0; js.ntasks0 = ntasks0;
+          js.span_cnt = nspans; js.span_first = span_first; js.pad = endt;
+          jst[j] = js;
+          int slot = endt & wmask;
+          int t = wt[slot];
+          if (wh[slot] < 0) wh[slot] = j; else jst[t].next = j;
+          wt[slot] = j;
+        }
+        top -= 1;
+        sum_arr -= g_arrive[j];
+        running += 1; started += 1; events += 1;
+        busy_gpus += hg;
+        mem_busy += (long long)hg * (hmemb < cap_bytes ? hmemb : cap_bytes);
+        head = -1; head_valid = false;
+        __syncwarp();
+      }
+    }
+    // ---------------- D/E. time advances; release jobs whose finish tick is now
+    const int now = delta + 1;
+    {
+      int slot = now & wmask;
+      int h = wh[slot];
+      if (h >= 0) {
+        if (lane == 0) { wh[slot] = -1; wt[slot] = -1; }
+        while (h >= 0) {
+          JobState js = jst[h];
+          int hgp = g_gpus[h];
+          long long mb = g_memb[h];
+          if (js.span_cnt == 1) {
+            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] -= js.ntasks0; }
+          } else {
+            for (int i = lane; i < js.span_cnt; i += 32) {
+              gs_span sp = spans[js.span_first + i];
+              busy[sp.node] &= ~sp.devmask; kk[sp.node] -= sp.ntasks;
+            }
+          }
+          if (lane == 0) { rec[h].end = now; fin[finished] = h; }
+          finished += 1; running -= 1; events += 1;
+          busy_gpus -= hgp;
+          mem_busy -= (long long)hgp * (mb < cap_bytes ? mb : cap_bytes);
+          h = js.next;
+        }
+        __syncwarp();
+      }
+    }
+    // ---------------- H. statistics row (schedule.py:95-133) from O(1) counters
+    {
+      int pmax = 0, mlo = 0, mhi = 0;
+      if (top > 0) {
+        // queue is a stack with non-decreasing arrival ticks bottom->top, so the sorted
+        // pending list is the stack read top->bottom: median/max are index look-ups
+        int ilo = top - 1 - (top - 1) / 2, ihi = top - 1 - top / 2;
+        int a_lo = g_arrive[stack[ilo]], a_hi = g_arrive[stack[ihi]];
+        pmax = now - bottom_arr; mlo = now - a_lo; mhi = now - a_hi;
+      }
+      if (lane == 0) {
+        int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
+        int tg = M * G;
+        dst[0] = make_int4(now, M - ever, ever, busy_gpus);
+        dst[1] = make_int4(tg - busy_gpus, running, top, finished);
+        long long ps = (long long)top * now - sum_arr;
+        dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(ps & 0xffffffffLL), (int)(ps >> 32));
+        dst[3] = make_int4(pmax, mlo, mhi, 0);
+      }
+    }
+    ticks += 1; budget -= 1;
+    delta = now;
+    done = (n - p) + running == 0;      // schedule.py:185 -- the queue is NOT counted (quirk Q4)
+  }
+
+  // ---------------- persist
+  __syncwarp();
+  for (int i = lane; i < M; i += 32) { S.nbusy[i] = busy[i]; S.nk[i] = kk[i]; }
+  if (lane == 0) {
+    S.delta = delta; S.p = p; S.top = top; S.running = running; S.finished = finished;
+    S.ever = ever; S.busy_gpus = busy_gpus; S.mem_busy = mem_busy; S.sum_arr = sum_arr;
+    S.span_used = span_used; S.events = events; S.evals = evals; S.started = started;
+    S.ticks = ticks; S.row_first = row_first; S.done = done ? 1 : 0; S.status = status;
+  }
+}
+
+// never-started jobs report start=end=-1, jct=preempt=0 and their input duration
+__global__ void gs_init_rec_kernel(gs_job_rec *rec, const double *dur, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0; r.duration = dur[i]; rec[i] = r; }
+}
+
+// ------------------------------------------------------------------ stateless candidate scoring
+// gs_place_batch: b independent jobs against ONE cluster state.  A block stages the node
+// table into shared memory with 16-byte loads (one gs_node per load), reduces it to
+// (idle devices, free task slots) per node, then each warp resolves jobs: lanes stripe
+// over nodes, ballot+ffs gives the first fit (argmin node id), a warp prefix sum gives
+// the cross-node fill.  Same decision rules as the tick kernel, no state is modified.
+__global__ void __launch_bounds__(256) gs_place_kernel(const uint4 *__restrict__ nodes, int M, int G, int cpu_cnt,
+                                                       int mem_sz, int cpu_pt, int mem_pt, long long fit_limit,
+                                                       const uint4 *__restrict__ jobs, long long b,
+                                                       int *__restrict__ first_node, int *__restrict__ nodes_used,
+                                                       const long long *__restrict__ task_off, int *__restrict__ task_node) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  short2 *tab = reinterpret_cast<short2 *>(smem_raw);      // (idle, slots) per node
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    uint4 v = nodes[i];                                     // {busy_lo, busy_hi, cpu_used, mem_used}
+    unsigned long long bm = ((unsigned long long)v.y << 32) | v.x;
+    if (G < 64) bm &= (1ull << G) - 1ull;
+    int idle = G - __popcll(bm);
+    int cf = cpu_cnt - (int)v.z, mf = mem_sz - (int)v.w;
+    int slots = min(cf > 0 ? cf / cpu_pt : 0, mf > 0 ? mf / mem_pt : 0);
+    tab[i] = make_short2((short)idle, (short)min(slots, 32767));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < b; j += warps) {
+    uint4 jr = jobs[j];                                     // {gpus, gpc, mem_lo, mem_hi}
+    const int gpus = (int)jr.x, gpc = (int)jr.y;
+    const long long memb = (long long)(((unsigned long long)jr.w << 32) | jr.z);
+    const int tasks = gpus / gpc;
+    const bool placeable = memb < fit_limit;
+    int *tn = task_node ? task_node + task_off[j] : nullptr;
+    int fn = -1, used = 0;
+    if (placeable && gpus <= G) {
+      for (int base = 0; base < M && fn < 0; base += 32) {
+        int nd = base + lane;
+        bool fit = false;
+        if (nd < M) { short2 t = tab[nd]; fit = t.x >= gpus && t.y >= tasks; }
+        unsigned bal = __ballot_sync(FULL, fit);
+        if (bal) fn = base + __ffs(bal) - 1;
+      }
+      if (fn >= 0) { used = 1; if (tn) for (int t = lane; t < tasks; t += 32) tn[t] = fn; }
+    } else if (placeable) {
+      int cum = 0, last_base = -1;
+      for (int base = 0; base < M; base += 32) {
+        int nd = base + lane, c = 0;
+        if (nd < M) { short2 t = tab[nd]; c = max(min(gpc == 1 ? (int)t.x : t.x / gpc, (int)t.y), 0); }
+        cum += __reduce_add_sync(FULL, c);
+        if (cum >= tasks) { last_base = base; break; }
+      }
+      if (last_base >= 0) {
+        int done_tasks = 0;
+        for (int base = 0; base <= last_base; base += 32) {
+          int nd = base + lane, c = 0;
+          if (nd < M) { short2 t = tab[nd]; c = max(min(gpc == 1 ? (int)t.x : t.x / gpc, (int)t.y), 0); }
+          int incl = c;
+          #pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+          int excl = done_tasks + incl - c;
+          int take = min(c, max(tasks - excl, 0));
+          unsigned tb = __ballot_sync(FULL, take > 0);
+          if (fn < 0 && tb) fn = base + __ffs(tb) - 1;
+          used += __popc(tb);
+          if (tn) for (int t = 0; t < take; ++t) tn[excl + t] = nd;
+          done_tasks += __shfl_sync(FULL, incl, 31);
+        }
+      }
+    }
+    if (fn < 0 && tn) for (int t = lane; t < tasks; t += 32) tn[t] = -1;
+    if (lane == 0) { first_node[j] = fn; if (nodes_used) nodes_used[j] = used; }
+  }
+}
+
+// gs_net_cost: one warp per job.  cross = |ps_nodes symmetric-difference wk_nodes|
+// (network_service.py:16-24); extra = (model/bw + cross*lat) * (iters*2.0) with the
+// reference's association and no FMA contraction (:34-37).
+__global__ void gs_netcost_kernel(long long b, const long long *__restrict__ task_off,
+                                  const int *__restrict__ task_node, const unsigned char *__restrict__ is_ps,
+                                  const int *__restrict__ ps_count, const double *__restrict__ model_mb,
+                                  const double *__restrict__ iters, double bandwidth, double latency,
+                                  double *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < b; j += warps) {
+    const long long a = task_off[j], e = task_off[j + 1];
+    int cross = 0;
+    if (ps_count[j] > 1) {
+      for (long long t = a + lane; t < e; t += 32) {
+        int nd = task_node[t];
+        bool first = true;
+        for (long long u = a; u < t && first; ++u) first = task_node[u] != nd;
+        if (!first) continue;
+        bool in_ps = false, in_wk = false;
+        for (long long u = a; u < e; ++u)
+          if (task_node[u] == nd) { if (is_ps && is_ps[u]) in_ps = true; else in_wk = true; }
+        cross += (in_ps != in_wk);
+      }
+      cross = __reduce_add_sync(FULL, cross);
+    }
+    if (lane == 0) {
+      double extra = 0.0;
+      if (cross > 0) {
+        double mps = __ddiv_rn(model_mb[j], bandwidth);
+        double nis = __dmul_rn((double)cross, latency);
+        double rt = __dmul_rn(iters[j], 2.0);
+        extra = __dmul_rn(__dadd_rn(mps, nis), rt);
+      }
+      out[j] = extra;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+
+struct SimHost {
+  gs_cluster cl;
+  gs_policy pol;
+  bool configured = false, loaded = false, prepared = false;
+  int64_t n = 0;
+  void *trace_slab = nullptr;
+  void *state_slab = nullptr;
+  size_t trace_bytes = 0, state_bytes = 0;
+  int64_t span_cap = 0, rows_cap = 0, last_arrive = 0;
+  int max_need = 1;
+  SimDev dev;
+};
+
+struct gs_engine {
+  int device = 0, nsims = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  std::vector<SimHost> sims;
+  SimDev *d_sims = nullptr;
+  void *h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  void *d_scratch = nullptr;
+  size_t d_scratch_bytes = 0;
+  std::string err;
+  double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
+  long long launches = 0;  // kernels launched by this handle
+  bool dirty = true;       // host mirror of SimDev newer than device copy
+};
+
+static std::string g_create_err;
+
+static int fail(gs_handle h, int code, const std::string &msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(h, GS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
+
+extern "C" const char *gs_last_error(gs_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int gs_create(int device, int nsims, gs_handle *out) {
+  gs_handle h = nullptr;
+  if (!out || nsims <= 0) return fail(nullptr, GS_ERR_ARG, "gs_create: bad arguments");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(nullptr, GS_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= count) return fail(nullptr, GS_ERR_ARG, "gs_create: device ordinal out of range");
+  CU(cudaSetDevice(device));
+  h = new gs_engine();
+  h->device = device;
+  h->nsims = nsims;
+  h->sims.resize((size_t)nsims);
+  cudaError_t e1 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaError_t e2 = cudaEventCreate(&h->e0);
+  cudaError_t e3 = cudaEventCreate(&h->e1);
+  cudaError_t e4 = cudaMalloc(&h->d_sims, sizeof(SimDev) * (size_t)nsims);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    delete h;
+    return fail(nullptr, GS_ERR_CUDA, "gs_create: stream/event/alloc failed");
+  }
+  *out = h;
+  return GS_OK;
+}
+
+extern "C" void gs_destroy(gs_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto &s : h->sims) { if (s.trace_slab) cudaFree(s.trace_slab); if (s.state_slab) cudaFree(s.state_slab); }
+  if (h->d_sims) cudaFree(h->d_sims);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->d_scratch) cudaFree(h->d_scratch);
+  if (h->e0) cudaEventDestroy(h->e0);
+  if (h->e1) cudaEventDestroy(h->e1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int check_cluster(gs_handle h, const gs_cluster *c) {
+  if (!c) return fail(h, GS_ERR_ARG, "cluster is NULL");
+  long long m = (long long)c->num_switch * c->num_node_p_switch;
+  if (c->num_switch <= 0 || c->num_node_p_switch <= 0 || m > (1 << 20))
+    return fail(h, GS_ERR_ARG, "cluster: num_switch * num_node_p_switch must be in 1..2^20");
+  if (c->num_gpu_p_node <= 0 || c->num_gpu_p_node > GS_MAX_GPUS_PER_NODE)
+    return fail(h, GS_ERR_ARG, "cluster: num_gpu_p_node must be in 1..64");
+  if (c->cpu_per_task <= 0 || c->mem_per_task <= 0 || c->num_cpu_p_node < 0 || c->mem_p_node < 0)
+    return fail(h, GS_ERR_ARG, "cluster: cpu/mem per task must be positive");
+  if (c->gpu_mem_cap_mib <= 0) return fail(h, GS_ERR_ARG, "cluster: gpu_mem_cap_mib must be positive");
+  return GS_OK;
+}
+
+extern "C" int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, const gs_policy *policy) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_config_sim: sim index out of range");
+  int rc = check_cluster(h, cluster);
+  if (rc) return rc;
+  SimHost &s = h->sims[(size_t)sim];
+  if (s.prepared) return fail(h, GS_ERR_STATE, "gs_config_sim: replica already running");
+  s.cl = *cluster;
+  if (policy) s.pol = *policy; else { memset(&s.pol, 0, sizeof(s.pol)); s.pol.num_queue = 1; }
+  if (s.pol.schedule != GS_SCHED_FIFO || s.pol.scheme != GS_SCHEME_YARN)
+    return fail(h, GS_ERR_ARG, "gs_config_sim: only schedule=fifo, scheme=yarn are implemented in this build");
+  s.configured = true;
+  return GS_OK;
+}
+
+static int ensure_stage(gs_handle h, size_t bytes) {
+  if (h->h_stage_bytes >= bytes) return GS_OK;
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->h_stage = nullptr; h->h_stage_bytes = 0;
+  CU(cudaMallocHost(&h->h_stage, bytes));
+  h->h_stage_bytes = bytes;
+  return GS_OK;
+}
+
+extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arrive_tick, const int32_t *gpus,
+                             const int32_t *gpu_per_task, const double *duration, const int64_t *mem_bytes,
+                             const double *model_mb, const double *iterations, const int32_t *ps_count) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_load_trace: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.configured) return fail(h, GS_ERR_STATE, "gs_load_trace: call gs_config_sim first");
+  if (n < 0 || n >= (1ll << 31) - 64) return fail(h, GS_ERR_ARG, "gs_load_trace: n out of range");
+  if (n > 0 && (!arrive_tick || !gpus || !gpu_per_task || !duration || !mem_bytes))
+    return fail(h, GS_ERR_ARG, "gs_load_trace: NULL column");
+  const bool net = model_mb && iterations && ps_count;
+  const int M = s.cl.num_switch * s.cl.num_node_p_switch;
+  // validate + bounds (host, one pass)
+  int64_t span_cap = 0;
+  double max_need = 1.0;
+  for (int64_t j = 0; j < n; ++j) {
+    if (arrive_tick[j] < 0 || (j > 0 && arrive_tick[j] < arrive_tick[j - 1]))
+      return fail(h, GS_ERR_ARG, "gs_load_trace: arrive_tick must be non-negative and non-decreasing");
+    if (gpu_per_task[j] <= 0 || gpus[j] < gpu_per_task[j] || gpus[j] % gpu_per_task[j] != 0)
+      return fail(h, GS_ERR_ARG, "gs_load_trace: gpus must be a positive multiple of gpu_per_task (job.py:96-100)");
+    if (mem_bytes[j] < 0) return fail(h, GS_ERR_ARG, "gs_load_trace: negative mem_bytes");
+    if (!(duration[j] == duration[j])) return fail(h, GS_ERR_ARG, "gs_load_trace: NaN duration");
+    int64_t tasks = gpus[j] / gpu_per_task[j];
+    span_cap += tasks < M ? tasks : M;
+    double d = duration[j];
+    if (net && s.cl.enable_network_costs && ps_count[j] > 1) {
+      double cross = (double)(tasks < M ? tasks : M);
+      double extra = (model_mb[j] / s.cl.bandwidth + cross * s.cl.internode_latency) * (iterations[j] * 2.0);
+      if (extra > 0) d += extra;
+    }
+    if (d > max_need) max_need = d;
+  }
+  if (max_need > (double)(1 << 26)) return fail(h, GS_ERR_ARG, "gs_load_trace: job duration exceeds 2^26 ticks");
+  CU(cudaSetDevice(h->device));
+  const size_t N = (size_t)(n > 0 ? n : 1);
+  size_t off_arr = 0, off_gpus = align_up(off_arr + 4 * N), off_gpc = align_up(off_gpus + 4 * N);
+  size_t off_ps = align_up(off_gpc + 4 * N), off_dur = align_up(off_ps + 4 * N);
+  size_t off_model = align_up(off_dur + 8 * N), off_iters = align_up(off_model + 8 * N);
+  size_t off_mem = align_up(off_iters + 8 * N), total = align_up(off_mem + 8 * N);
+  int rc = ensure_stage(h, total);
+  if (rc) return rc;
+  unsigned char *st = (unsigned char *)h->h_stage;
+  memset(st, 0, total);
+  if (n > 0) {
+    memcpy(st + off_arr, arrive_tick, 4 * (size_t)n);
+    memcpy(st + off_gpus, gpus, 4 * (size_t)n);
+    memcpy(st + off_gpc, gpu_per_task, 4 * (size_t)n);
+    memcpy(st + off_dur, duration, 8 * (size_t)n);
+    memcpy(st + off_mem, mem_bytes, 8 * (size_t)n);
+    if (net) {
+      memcpy(st + off_ps, ps_count, 4 * (size_t)n);
+      memcpy(st + off_model, model_mb, 8 * (size_t)n);
+      memcpy(st + off_iters, iterations, 8 * (size_t)n);
+    }
+  }
+  if (s.trace_slab && s.trace_bytes < total) { cudaFree(s.trace_slab); s.trace_slab = nullptr; }
+  if (!s.trace_slab) { CU(cudaMalloc(&s.trace_slab, total)); s.trace_bytes = total; }
+  CU(cudaEventRecord(h->e0, h->stream));
+  CU(cudaMemcpyAsync(s.trace_slab, st, total, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->h2d_ms += ms;
+  unsigned char *d = (unsigned char *)s.trace_slab;
+  SimDev &D = s.dev;
+  memset(&D, 0, sizeof(D));
+  D.arrive = (const int *)(d + off_arr); D.gpus = (const int *)(d + off_gpus); D.gpc = (const int *)(d + off_gpc);
+  D.ps = net ? (const int *)(d + off_ps) : nullptr;
+  D.dur = (const double *)(d + off_dur);
+  D.model_mb = net ? (const double *)(d + off_model) : nullptr;
+  D.iters = net ? (const double *)(d + off_iters) : nullptr;
+  D.memb = (const long long *)(d + off_mem);
+  s.n = n; s.span_cap = span_cap > 0 ? span_cap : 1;
+  s.max_need = (int)max_need + 2;
+  s.last_arrive = n > 0 ? arrive_tick[n - 1] : 0;
+  s.loaded = true;
+  s.prepared = false;      // (re)loading a trace restarts the replica; slabs are reused when big enough
+  h->dirty = true;
+  return GS_OK;
+}
+
+static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
+  const gs_cluster &c = s.cl;
+  const int M = c.num_switch * c.num_node_p_switch;
+  const size_t N = (size_t)(s.n > 0 ? s.n : 1);
+  int W = 64; while (W < s.max_need + 1) W <<= 1;
+  if (rows_cap <= 0) rows_cap = s.last_arrive + 2ll * s.max_need + 4096;
+  size_t o_rec = 0, o_jst = align_up(o_rec + sizeof(gs_job_rec) * N), o_stack = align_up(o_jst + sizeof(JobState) * N);
+  size_t o_fin = align_up(o_stack + 4 * N), o_wh = align_up(o_fin + 4 * N), o_wt = align_up(o_wh + 4 * (size_t)W);
+  size_t o_spans = align_up(o_wt + 4 * (size_t)W), o_rows = align_up(o_spans + sizeof(gs_span) * (size_t)s.span_cap);
+  size_t o_nb = align_up(o_rows + sizeof(gs_tick_row) * (size_t)rows_cap), o_nk = align_up(o_nb + 8 * (size_t)M);
+  size_t total = align_up(o_nk + 4 * (size_t)M);
+  if (s.state_slab && s.state_bytes < total) { cudaFree(s.state_slab); s.state_slab = nullptr; }
+  if (!s.state_slab) { CU(cudaMalloc(&s.state_slab, total)); s.state_bytes = total; }
+  unsigned char *d = (unsigned char *)s.state_slab;
+  CU(cudaMemsetAsync(d + o_wh, 0xFF, 4 * (size_t)W, h->stream));
+  CU(cudaMemsetAsync(d + o_wt, 0xFF, 4 * (size_t)W, h->stream));
+  CU(cudaMemsetAsync(d + o_nb, 0, 8 * (size_t)M, h->stream));
+  CU(cudaMemsetAsync(d + o_nk, 0, 4 * (size_t)M, h->stream));
+  SimDev &D = s.dev;
+  D.M = M; D.G = c.num_gpu_p_node;
+  int kc = c.num_cpu_p_node / c.cpu_per_task, km = c.mem_p_node / c.mem_per_task;
+  D.K = kc < km ? kc : km;
+  D.netcost = c.enable_network_costs ? 1 : 0;
+  D.n = (int)s.n; D.wheel_mask = W - 1; D.policy = s.pol.schedule;
+  D.cap_bytes = (long long)c.gpu_mem_cap_mib << 20;
+  D.fit_limit = D.cap_bytes - ((long long)500 << 20);      // cap - mem > 500 MiB  (device.py:75)
+  D.bandwidth = c.bandwidth; D.latency = c.internode_latency;
+  D.rec = (gs_job_rec *)(d + o_rec); D.jst = (JobState *)(d + o_jst);
+  D.stack = (int *)(d + o_stack); D.fin = (int *)(d + o_fin);
+  D.wheel_head = (int *)(d + o_wh); D.wheel_tail = (int *)(d + o_wt);
+  D.spans = (gs_span *)(d + o_spans); D.rows = (gs_tick_row *)(d + o_rows);
+  D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
+  D.span_cap = s.span_cap; D.rows_cap = rows_cap;
+  s.rows_cap = rows_cap;
+  D.delta = D.p = D.top = D.running = D.finished = D.ever = D.busy_gpus = D.done = D.status = 0;
+  D.mem_busy = D.sum_arr = D.span_used = D.events = D.evals = D.started = D.ticks = D.row_first = 0;
+  if (s.n > 0) {
+    gs_init_rec_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(D.rec, D.dur, (int)s.n);
+    h->launches += 1;
+  }
+  CU(cudaGetLastError());
+  s.prepared = true;
+  return GS_OK;
+}
+
+extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
+  if (!h) return GS_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  int maxM = 1;
+  for (auto &s : h->sims) {
+    if (!s.loaded) return fail(h, GS_ERR_STATE, "gs_run: every replica needs gs_config_sim + gs_load_trace");
+    if (!s.prepared) { int rc = prepare_sim(h, s, rows_cap); if (rc) return rc; h->dirty = true; }
+    int M = s.cl.num_switch * s.cl.num_node_p_switch;
+    if (M > maxM) maxM = M;
+  }
+  if (h->dirty) {
+    std::vector<SimDev> tmp((size_t)h->nsims);
+    for (int i = 0; i < h->nsims; ++i) tmp[(size_t)i] = h->sims[(size_t)i].dev;
+    CU(cudaMemcpyAsync(h->d_sims, tmp.data(), sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->dirty = false;
+  }
+  const int stride = (int)align_up((size_t)maxM * 12, 16);
+  if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
+  if (stride > 48 * 1024)
+    CU(cudaFuncSetAttribute(gs_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
+  CU(cudaEventRecord(h->e0, h->stream));
+  gs_tick_kernel<<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaEventRecord(h->e1, h->stream));
+  std::vector<SimDev> back((size_t)h->nsims);
+  CU(cudaMemcpyAsync(back.data(), h->d_sims, sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->kernel_ms += ms;
+  int worst = 0;
+  for (int i = 0; i < h->nsims; ++i) {
+    h->sims[(size_t)i].dev = back[(size_t)i];
+    if (back[(size_t)i].status != 0 && worst == 0) worst = back[(size_t)i].status;
+  }
+  if (worst != 0) return fail(h, worst, "gs_run: a replica stopped with an in-kernel error (see gs_stats.status)");
+  return GS_OK;
+}
+
+extern "C" int gs_stats(gs_handle h, int sim, gs_run_stats *out) {
+  if (!h || !out) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_stats: sim index out of range");
+  const SimDev &D = h->sims[(size_t)sim].dev;
+  memset(out, 0, sizeof(*out));
+  out->ticks = D.ticks; out->events = D.events; out->finished = D.finished; out->started = D.started;
+  out->placement_evals = D.evals; out->done = D.done; out->status = D.status;
+  out->kernel_ms = h->kernel_ms; out->h2d_ms = h->h2d_ms; out->d2h_ms = h->d2h_ms;
+  return GS_OK;
+}
+
+static int timed_d2h(gs_handle h, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return GS_OK;
+  CU(cudaEventRecord(h->e0, h->stream));
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->d2h_ms += ms;
+  return GS_OK;
+}
+
+extern "C" int gs_fetch_rows(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_rows: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_rows: nothing has run yet");
+  const SimDev &D = s.dev;
+  if (count < 0 || first < D.row_first || first + count > D.ticks)
+    return fail(h, GS_ERR_ARG, "gs_fetch_rows: range is outside the rows of the last gs_run window");
+  if (count == 0) return GS_OK;
+  if (!rows_out) return fail(h, GS_ERR_ARG, "gs_fetch_rows: NULL output");
+  CU(cudaSetDevice(h->device));
+  return timed_d2h(h, rows_out, D.rows + (first - D.row_first), sizeof(gs_tick_row) * (size_t)count);
+}
+
+extern "C" int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out, int32_t *finish_order_out) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_jobs: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_jobs: nothing has run yet");
+  CU(cudaSetDevice(h->device));
+  int rc = GS_OK;
+  if (jobs_out && s.n > 0) rc = timed_d2h(h, jobs_out, s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n);
+  if (rc == GS_OK && finish_order_out && s.dev.finished > 0)
+    rc = timed_d2h(h, finish_order_out, s.dev.fin, 4 * (size_t)s.dev.finished);
+  return rc;
+}
+
+extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_span *spans_out, int64_t spans_cap,
+                              int64_t *spans_used) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_spans: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_spans: nothing has run yet");
+  CU(cudaSetDevice(h->device));
+  const int64_t used = s.dev.span_used;
+  if (spans_used) *spans_used = used;
+  if (!spans_out && !span_off_out) return GS_OK;
+  // spans are pooled in start order on the device; hand them back grouped by job (CSR)
+  std::vector<JobState> js((size_t)(s.n > 0 ? s.n : 1));
+  std::vector<gs_job_rec> rec((size_t)(s.n > 0 ? s.n : 1));
+  std::vector<gs_span> pool((size_t)(used > 0 ? used : 1));
+  int rc = GS_OK;
+  if (s.n > 0) rc = timed_d2h(h, js.data(), s.dev.jst, sizeof(JobState) * (size_t)s.n);
+  if (rc == GS_OK && s.n > 0) rc = timed_d2h(h, rec.data(), s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n);
+  if (rc == GS_OK && used > 0) rc = timed_d2h(h, pool.data(), s.dev.spans, sizeof(gs_span) * (size_t)used);
+  if (rc) return rc;
+  int64_t w = 0;
+  for (int64_t j = 0; j < s.n; ++j) {
+    if (span_off_out) span_off_out[j] = w;
+    if (rec[(size_t)j].start < 0) continue;
+    const JobState &st = js[(size_t)j];
+    if (spans_out) {
+      if (w + st.span_cnt > spans_cap) return fail(h, GS_ERR_CAPACITY, "gs_fetch_spans: spans_out too small");
+      memcpy(spans_out + w, pool.data() + st.span_first, sizeof(gs_span) * (size_t)st.span_cnt);
+    }
+    w += st.span_cnt;
+  }
+  if (span_off_out) span_off_out[s.n] = w;
+  return GS_OK;
+}
+
+static int ensure_scratch(gs_handle h, size_t bytes) {
+  if (h->d_scratch_bytes >= bytes) return GS_OK;
+  if (h->d_scratch) cudaFree(h->d_scratch);
+  h->d_scratch = nullptr; h->d_scratch_bytes = 0;
+  CU(cudaMalloc(&h->d_scratch, bytes));
+  h->d_scratch_bytes = bytes;
+  return GS_OK;
+}
+
+extern "C" int gs_place_batch(gs_handle h, const gs_cluster *cluster, const gs_node *nodes, int32_t m,
+                              const gs_jobreq *jobs, int64_t b, int32_t *first_node, int32_t *nodes_used,
+                              const int64_t *task_off, int32_t *task_node, double *kernel_ms) {
+  if (!h) return GS_ERR_ARG;
+  int rc = check_cluster(h, cluster);
+  if (rc) return rc;
+  if (!nodes || m <= 0 || m > 16384 || b < 0 || (b > 0 && (!jobs || !first_node)))
+    return fail(h, GS_ERR_ARG, "gs_place_batch: bad arguments (1 <= m <= 16384)");
+  if ((task_node != nullptr) != (task_off != nullptr))
+    return fail(h, GS_ERR_ARG, "gs_place_batch: task_off and task_node go together");
+  for (int64_t j = 0; j < b; ++j)
+    if (jobs[j].gpu_per_task <= 0 || jobs[j].gpus < jobs[j].gpu_per_task || jobs[j].gpus % jobs[j].gpu_per_task)
+      return fail(h, GS_ERR_ARG, "gs_place_batch: gpus must be a positive multiple of gpu_per_task");
+  if (b == 0) return GS_OK;
+  CU(cudaSetDevice(h->device));
+  const int64_t ntask = task_off ? task_off[b] : 0;
+  size_t o_nodes = 0, o_jobs = align_up(o_nodes + 16 * (size_t)m), o_first = align_up(o_jobs + 16 * (size_t)b);
+  size_t o_used = align_up(o_first + 4 * (size_t)b), o_toff = align_up(o_used + 4 * (size_t)b);
+  size_t o_tn = align_up(o_toff + 8 * (size_t)(b + 1)), total = align_up(o_tn + 4 * (size_t)(ntask > 0 ? ntask : 1));
+  rc = ensure_scratch(h, total);
+  if (rc) return rc;
+  unsigned char *d = (unsigned char *)h->d_scratch;
+  CU(cudaEventRecord(h->e0, h->stream));
+  CU(cudaMemcpyAsync(d + o_nodes, nodes, 16 * (size_t)m, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d + o_jobs, jobs, 16 * (size_t)b, cudaMemcpyHostToDevice, h->stream));
+  if (task_off) CU(cudaMemcpyAsync(d + o_toff, task_off, 8 * (size_t)(b + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1); h->h2d_ms += ms;
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
+  long long want = (b + 7) / 8;
+  int grid = (int)(want < (long long)dev_sms * 8 ? want : (long long)dev_sms * 8);
+  const long long fit_limit = ((long long)cluster->gpu_mem_cap_mib << 20) - ((long long)500 << 20);
+  CU(cudaEventRecord(h->e0, h->stream));
+  gs_place_kernel<<<grid, 256, 4 * (size_t)m, h->stream>>>(
+      (const uint4 *)(d + o_nodes), m, cluster->num_gpu_p_node, cluster->num_cpu_p_node, cluster->mem_p_node,
+      cluster->cpu_per_task, cluster->mem_per_task, fit_limit, (const uint4 *)(d + o_jobs), (long long)b,
+      (int *)(d + o_first), (int *)(d + o_used), task_off ? (const long long *)(d + o_toff) : nullptr,
+      task_node ? (int *)(d + o_tn) : nullptr);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->kernel_ms += ms;
+  if (kernel_ms) *kernel_ms = ms;
+  rc = timed_d2h(h, first_node, d + o_first, 4 * (size_t)b);
+  if (rc == GS_OK && nodes_used) rc = timed_d2h(h, nodes_used, d + o_used, 4 * (size_t)b);
+  if (rc == GS_OK && task_node && ntask > 0) rc = timed_d2h(h, task_node, d + o_tn, 4 * (size_t)ntask);
+  return rc;
+}
+
+extern "C" int gs_net_cost(gs_handle h, const gs_cluster *cluster, int64_t b, const int64_t *task_off,
+                           const int32_t *task_node, const uint8_t *is_ps, const int32_t *ps_count,
+                           const double *model_mb, const double *iterations, double *extra_out) {
+  if (!h) return GS_ERR_ARG;
+  if (!cluster || b < 0 || (b > 0 && (!task_off || !task_node || !ps_count || !model_mb || !iterations || !extra_out)))
+    return fail(h, GS_ERR_ARG, "gs_net_cost: bad arguments");
+  if (b == 0) return GS_OK;
+  CU(cudaSetDevice(h->device));
+  const int64_t nt = task_off[b];
+  size_t o_off = 0, o_tn = align_up(o_off + 8 * (size_t)(b + 1)), o_ps = align_up(o_tn + 4 * (size_t)(nt > 0 ? nt : 1));
+  size_t o_cnt = align_up(o_ps + (size_t)(nt > 0 ? nt : 1)), o_mm = align_up(o_cnt + 4 * (size_t)b);
+  size_t o_it = align_up(o_mm + 8 * (size_t)b), o_out = align_up(o_it + 8 * (size_t)b), total = align_up(o_out + 8 * (size_t)b);
+  int rc = ensure_scratch(h, total);
+  if (rc) return rc;
+  unsigned char *d = (unsigned char *)h->d_scratch;
+  CU(cudaMemcpyAsync(d + o_off, task_off, 8 * (size_t)(b + 1), cudaMemcpyHostToDevice, h->stream));
+  if (nt > 0) CU(cudaMemcpyAsync(d + o_tn, task_node, 4 * (size_t)nt, cudaMemcpyHostToDevice, h->stream));
+  if (is_ps && nt > 0) CU(cudaMemcpyAsync(d + o_ps, is_ps, (size_t)nt, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d + o_cnt, ps_count, 4 * (size_t)b, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d + o_mm, model_mb, 8 * (size_t)b, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d + o_it, iterations, 8 * (size_t)b, cudaMemcpyHostToDevice, h->stream));
+  long long want = (b + 3) / 4;
+  int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  gs_netcost_kernel<<<grid, 128, 0, h->stream>>>((long long)b, (const long long *)(d + o_off), (const int *)(d + o_tn),
+                                                 is_ps ? (const unsigned char *)(d + o_ps) : nullptr,
+                                                 (const int *)(d + o_cnt), (const double *)(d + o_mm),
+                                                 (const double *)(d + o_it), cluster->bandwidth,
+                                                 cluster->internode_latency, (double *)(d + o_out));
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return timed_d2h(h, extra_out, d + o_out, 8 * (size_t)b);
+}
+
+// Restart every replica from tick 0 on the traces already resident in HBM.
+extern "C" int gs_reset(gs_handle h) {
+  if (!h) return GS_ERR_ARG;
+  for (auto &s : h->sims) s.prepared = false;
+  h->dirty = true;
+  h->kernel_ms = h->h2d_ms = h->d2h_ms = 0;
+  return GS_OK;
+}
+
+extern "C" int64_t gs_launch_count(gs_handle h) { return h ? h->launches : 0; }
+
+// Pinned host buffers for callers that want DMA-speed gs_load_trace / gs_fetch_* copies.
+extern "C" int gs_host_alloc(size_t bytes, void **out) {
+  gs_handle h = nullptr;
+  if (!out) return GS_ERR_ARG;
+  *out = nullptr;
+  CU(cudaMallocHost(out, bytes > 0 ? bytes : 1));
+  return GS_OK;
+}
+
+extern "C" int gs_host_free(void *p) {
+  gs_handle h = nullptr;
+  if (p) CU(cudaFreeHost(p));
+  return GS_OK;
+}

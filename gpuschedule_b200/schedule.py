@@ -1,0 +1,42 @@
+"""`Scheduler` -- drop-in for core.scheduling.schedule.Scheduler
+(/root/reference/core/scheduling/schedule.py:12-215): same constructor, same
+`.start()`.  The whole tick loop runs on the GPU behind the C ABI; the host only
+formats the result through LogManager (and replays the RNG column)."""
+from __future__ import annotations
+
+import logging
+import time
+
+from . import capi, rngcol
+
+
+class Scheduler:
+    def __init__(self, infrastructure, jobs_manager, log_manager, enable_migration=False):
+        self.infrastructure = infrastructure
+        self.jobs_manager = jobs_manager
+        self.log_manager = log_manager
+        self.placement = infrastructure.flags.scheme
+        self.schedule = infrastructure.flags.schedule
+        self.enable_migration = enable_migration
+        self.stats = None
+
+    def start(self):
+        t0 = time.time()
+        infra, table = self.infrastructure, self.jobs_manager.table
+        cluster = infra.gs_cluster()
+        policy = capi.make_policy(self.schedule, self.placement, getattr(infra.flags, "num_queue", 1))
+        with capi.Engine(device=getattr(infra.flags, "device", 0), nsims=1) as eng:
+            eng.config(0, cluster, policy)
+            eng.load_trace(0, table)
+            rows = eng.run_all()[0]
+            recs, order = eng.fetch_jobs(0)
+            span_off, spans = eng.fetch_spans(0)
+            self.stats = eng.stats(0)
+        m = cluster.num_switch * cluster.num_node_p_switch
+        g = cluster.num_gpu_p_node
+        util = rngcol.utilization_text(len(rows), m, g, table, recs, span_off, spans)
+        self.log_manager.write_cluster_rows(rows, util, m * g * cluster.gpu_mem_cap_mib)
+        logging.info("Total Time Taken in seconds: %d" % (time.time() - t0))
+        self.log_manager.write_job_rows(table, recs, order)
+        self.rows, self.recs, self.finish_order = rows, recs, order
+        return self.stats

@@ -31,6 +31,7 @@
 #ifndef GSCHED_H_
 #define GSCHED_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -167,6 +168,17 @@ int gs_load_trace(gs_handle h, int sim, int64_t n,
 int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap);
 
 int gs_stats(gs_handle h, int sim, gs_run_stats *out);
+
+/* Restart every replica at tick 0 on the traces already resident in device
+ * memory (sweeps, benchmarking); also clears the accumulated timers.           */
+int gs_reset(gs_handle h);
+
+/* Number of CUDA kernels this handle has launched so far.                       */
+int64_t gs_launch_count(gs_handle h);
+
+/* Page-locked host memory for DMA-speed gs_load_trace / gs_fetch_* transfers.  */
+int gs_host_alloc(size_t bytes, void **out);
+int gs_host_free(void *p);
 
 /* Copy results of one replica to caller-owned host buffers (any may be NULL).  */
 int gs_fetch_rows(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out);

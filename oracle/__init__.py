@@ -51,7 +51,7 @@ class OracleResult:
     pass
 
 
-def run_fifo(cluster: GsCluster, table, rows_cap=None):
+def run_fifo(cluster: GsCluster, table, rows_cap=None, want_spans=True):
     """Run the restated Scheduler.start() on a JobTable; returns an OracleResult
     with the same arrays the engine's fetch_* calls give."""
     n = table.n
@@ -85,7 +85,8 @@ def run_fifo(cluster: GsCluster, table, rows_cap=None):
     r.events = events.value
     r.evals = evals.value
     r.task_off, r.task_node, r.task_mask = task_off, task_node, task_mask
-    r.span_off, r.spans = spans_from_tasks(n, task_off, task_node, task_mask)
+    if want_spans:
+        r.span_off, r.spans = spans_from_tasks(n, task_off, task_node, task_mask)
     return r
 
 

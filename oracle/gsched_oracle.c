@@ -394,6 +394,8 @@ int64_t oracle_run_fifo(const gs_cluster *c, int64_t n, const int32_t *arrive,
           s.running[s.rlen++] = j;
           events += 1;
         }
+      } else {
+        s.evals += s.M;   /* metric only: the engine still scores all M nodes (none can fit) */
       }
     }
     remaining = n - s.next_row;                  /* :191 */

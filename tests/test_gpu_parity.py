@@ -1,0 +1,209 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the reference-generated golden
+fixtures and against the CPU oracle on seeded inputs.  Bit-exact everywhere (integer /
+byte / index work; the one fp64 expression is checked for exact equality too)."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden, render_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine_run(cluster, table, rows_cap=0, nsims=1):
+    from gpuschedule_b200 import capi
+    with capi.Engine(device=0, nsims=nsims) as eng:
+        for s in range(nsims):
+            eng.config(s, cluster)
+            eng.load_trace(s, table)
+        rows = eng.run_all(rows_cap=rows_cap)
+        out = []
+        for s in range(nsims):
+            recs, order = eng.fetch_jobs(s)
+            span_off, spans = eng.fetch_spans(s)
+            out.append((rows[s], recs, order, span_off, spans, eng.stats(s)))
+    return out
+
+
+def _assert_same(ref, got, tag=""):
+    rows, recs, order, span_off, spans, st = got
+    assert st.ticks == ref.ticks, tag
+    assert np.array_equal(order, ref.finish_order), tag
+    if rows.tobytes() != ref.rows.tobytes():
+        for i in range(min(len(rows), len(ref.rows))):
+            assert rows[i].tobytes() == ref.rows[i].tobytes(), f"{tag} row {i}: {rows[i]} != {ref.rows[i]}"
+    assert recs.tobytes() == ref.recs.tobytes(), tag
+    assert np.array_equal(span_off, ref.span_off), tag
+    assert spans.tobytes() == ref.spans.tobytes(), tag
+    assert st.events == ref.events, tag
+    assert st.placement_evals == ref.evals, tag
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_engine_matches_reference_bytes(case):
+    """job.csv + all 13 cluster.csv columns byte-identical to the unmodified reference."""
+    table, cluster, meta, job_csv, cluster_csv = load_golden(case)
+    rows, recs, order, span_off, spans, st = _engine_run(cluster, table)[0]
+    got_job, got_cluster = render_outputs(table, cluster, rows, recs, order, span_off, spans,
+                                          meta["numpy_seed"])
+    assert got_job == job_csv
+    assert got_cluster == cluster_csv
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_engine_matches_oracle_structs(case):
+    import oracle
+    table, cluster, _, _, _ = load_golden(case)
+    _assert_same(oracle.run_fifo(cluster, table), _engine_run(cluster, table)[0], case)
+
+
+SEEDED = [
+    # (jobs, seed, rate, cluster kwargs, tracegen kwargs)
+    (5000, 101, 0.5, dict(num_switch=4, num_node_p_switch=32), {}),
+    (3000, 102, 2.0, dict(num_switch=4, num_node_p_switch=32), {}),                  # saturating
+    (1500, 103, 1.0, dict(num_switch=1, num_node_p_switch=5), {}),                   # M < 32, heavy queue
+    (2000, 104, 0.7, dict(num_switch=3, num_node_p_switch=23, num_gpu_p_node=4), {}),  # M=69, G=4
+    (2000, 105, 0.6, dict(num_switch=16, num_node_p_switch=64), {}),                 # M=1024
+    (2000, 106, 1.0, dict(num_switch=2, num_node_p_switch=20, num_gpu_p_node=16, num_cpu_p_node=100, mem_p_node=400),
+     dict(gpu_per_container=2, gpu_choices=[2, 4, 8, 16, 32, 64], gpu_probs=[.3, .2, .2, .15, .1, .05])),
+    (1500, 107, 0.9, dict(num_switch=2, num_node_p_switch=16, gpu_memory_capacity=16), dict(max_mem_mib=17000)),  # leaks
+]
+
+
+@pytest.mark.parametrize("cfg", SEEDED, ids=[f"seed{c[1]}" for c in SEEDED])
+def test_engine_matches_oracle_seeded(cfg):
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    n, seed, rate, ckw, tkw = cfg
+    cluster = capi.make_cluster(**ckw)
+    table = ingest.table_from_columns(tracegen.synth_columns(n, seed=seed, rate=rate, **tkw))
+    _assert_same(oracle.run_fifo(cluster, table), _engine_run(cluster, table)[0], f"seed{seed}")
+
+
+def test_row_window_resume_is_identical():
+    """A tiny device row window forces many launches; state persists across them."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    cluster = capi.make_cluster(num_switch=2, num_node_p_switch=9)
+    table = ingest.table_from_columns(tracegen.synth_columns(800, seed=7, rate=1.2))
+    ref = oracle.run_fifo(cluster, table)
+    for cap in (1, 7, 64, 1000):
+        _assert_same(ref, _engine_run(cluster, table, rows_cap=cap)[0], f"rows_cap={cap}")
+
+
+def test_replicas_are_independent():
+    """Many replicas in one launch (one warp each), different traces and clusters."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    nsims = 150
+    tables, clusters = [], []
+    for s in range(nsims):
+        clusters.append(capi.make_cluster(num_switch=1 + s % 4, num_node_p_switch=8 + 3 * (s % 7)))
+        tables.append(ingest.table_from_columns(tracegen.synth_columns(200 + 5 * s, seed=1000 + s, rate=0.4 + 0.05 * (s % 9))))
+    with capi.Engine(device=0, nsims=nsims) as eng:
+        for s in range(nsims):
+            eng.config(s, clusters[s])
+            eng.load_trace(s, tables[s])
+        rows = eng.run_all()
+        for s in range(nsims):
+            ref = oracle.run_fifo(clusters[s], tables[s])
+            recs, order = eng.fetch_jobs(s)
+            span_off, spans = eng.fetch_spans(s)
+            _assert_same(ref, (rows[s], recs, order, span_off, spans, eng.stats(s)), f"replica {s}")
+
+
+def test_network_cost_run_matches_oracle():
+    """enable_network_costs: fp64 transfer time fused into the placement commit.  Exact
+    equality of the resulting doubles (same operation order, no FMA contraction)."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    cluster = capi.make_cluster(num_switch=2, num_node_p_switch=16, enable_network_costs=True)
+    table = ingest.table_from_columns(tracegen.synth_columns(1500, seed=55, rate=0.3, with_network=True))
+    assert table.model_mb is not None and table.ps_count is not None
+    ref = oracle.run_fifo(cluster, table)
+    got = _engine_run(cluster, table)[0]
+    assert np.any(ref.recs["duration"] != table.duration)       # the cost term is exercised
+    _assert_same(ref, got, "netcost")
+
+
+def test_place_batch_matches_oracle():
+    import oracle
+    from gpuschedule_b200 import capi
+    rng = np.random.default_rng(17)
+    with capi.Engine(device=0, nsims=1) as eng:
+        for m, g, cpu, mem in [(128, 8, 128, 512), (37, 4, 60, 300), (1024, 8, 128, 512), (5, 16, 400, 2000)]:
+            cluster = capi.make_cluster(1, m, g, cpu, mem)
+            nodes = np.zeros(m, dtype=capi.NODE_DTYPE)
+            for i in range(m):
+                k = int(rng.integers(0, g + 1))
+                devs = rng.choice(g, size=k, replace=False)
+                nodes["busy_mask"][i] = sum(1 << int(d) for d in devs)
+                extra = int(rng.integers(0, 3))
+                nodes["cpu_used"][i] = 12 * (k + extra)
+                nodes["mem_used"][i] = 60 * (k + extra)
+            b = 400
+            jobs = np.zeros(b, dtype=capi.JOBREQ_DTYPE)
+            gpc = rng.choice([1, 1, 1, 2, 4], size=b)
+            jobs["gpu_per_task"] = gpc
+            jobs["gpus"] = gpc * rng.integers(1, 40, size=b)
+            jobs["mem_bytes"] = rng.integers(512, 34000, size=b).astype(np.int64) << 20
+            task_off = np.zeros(b + 1, dtype=np.int64)
+            np.cumsum(jobs["gpus"] // jobs["gpu_per_task"], out=task_off[1:])
+            first, used, task_node, _ = eng.place_batch(cluster, nodes, jobs, task_off)
+            for i in range(b):
+                ok, f, u, tn = oracle.place_one(cluster, nodes, jobs[i])
+                assert (first[i] >= 0) == ok, (m, i)
+                assert first[i] == f and used[i] == u, (m, i, first[i], f, used[i], u)
+                assert np.array_equal(task_node[task_off[i]:task_off[i + 1]], tn), (m, i)
+
+
+def test_net_cost_matches_oracle():
+    import oracle
+    from gpuschedule_b200 import capi
+    rng = np.random.default_rng(23)
+    cluster = capi.make_cluster(4, 32, bandwidth=1250, internode_latency=0.015)
+    b = 300
+    sizes = rng.integers(1, 40, size=b)
+    task_off = np.zeros(b + 1, dtype=np.int64)
+    np.cumsum(sizes, out=task_off[1:])
+    task_node = rng.integers(0, 6, size=int(task_off[-1])).astype(np.int32)
+    is_ps = (rng.random(int(task_off[-1])) < 0.3).astype(np.uint8)
+    ps_count = rng.integers(0, 4, size=b).astype(np.int32)
+    model = rng.choice([15.0, 97.0, 233.0, 1300.0, 549.0], size=b)
+    iters = rng.choice([1.0, 109.0, 521.0, 4861.0], size=b)
+    with capi.Engine(device=0, nsims=1) as eng:
+        for marks in (is_ps, None):
+            got = eng.net_cost(cluster, task_off, task_node, marks, ps_count, model, iters)
+            for i in range(b):
+                seg = slice(task_off[i], task_off[i + 1])
+                exp = oracle.net_cost(cluster, task_node[seg], None if marks is None else marks[seg],
+                                      ps_count[i], model[i], iters[i])
+                assert got[i] == exp, (i, got[i], exp)
+
+
+def test_full_size_properties_100k():
+    """BASELINE size (100k jobs, 4x32x8): size-independent invariants + oracle equality."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    cluster = capi.make_cluster(4, 32, 8)
+    table = ingest.table_from_columns(tracegen.synth_columns(100000, seed=1, rate=0.5))
+    rows, recs, order, span_off, spans, st = _engine_run(cluster, table)[0]
+    n = table.n
+    assert st.done == 1 and st.finished == n and st.events == 3 * n
+    assert np.array_equal(rows["now"], np.arange(1, len(rows) + 1))
+    assert np.all(rows["busy_gpus"] + rows["idle_gpus"] == 1024)
+    assert np.all(rows["idle_nodes"] + rows["busy_nodes"] == 128)
+    assert np.all(np.diff(rows["idle_nodes"]) <= 0) and np.all(np.diff(rows["finished"]) >= 0)
+    assert rows["running"][-1] == 0 and rows["finished"][-1] == n
+    assert np.all(recs["end"] - recs["start"] == recs["jct"])
+    assert np.all(recs["jct"] == np.maximum(1, np.ceil(table.duration)).astype(np.int32))
+    assert np.all(recs["start"] >= table.arrive_tick)
+    assert len(np.unique(recs["start"])) == n                     # at most one start per tick (Q1)
+    assert sorted(order.tolist()) == list(range(n))
+    ends = recs["end"][order]
+    assert np.all(np.diff(ends) >= 0)                              # finish order
+    # per-span device masks are disjoint per node at any time: check total gpu count
+    assert np.all(np.diff(span_off) >= 1)
+    pc = np.array([bin(int(x)).count("1") for x in spans["devmask"]])
+    assert np.array_equal(np.add.reduceat(pc, span_off[:-1]), table.gpus)
+    ref = oracle.run_fifo(cluster, table)
+    _assert_same(ref, (rows, recs, order, span_off, spans, st), "100k")
