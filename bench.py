@@ -160,6 +160,7 @@ def ours(args):
     tables = [fast_table(n, BASE_SEED + rank * R + r) for r in range(R)]
     log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
     eng = capi.Engine(device=local, nsims=R)
+    eng.set_engine(args.engine)
     for r in range(R):
         eng.config(r, cluster)
         eng.load_trace(r, tables[r])
@@ -336,6 +337,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 warp per replica, 2 lane per replica")
     args = ap.parse_args()
     if args.impl == "reference":
         reference(args)

@@ -135,6 +135,8 @@ def load_library(path=None):
     lib.gs_net_cost.argtypes = [C.c_void_p, C.POINTER(GsCluster), C.c_int64, i64p, i32p,
                                 C.POINTER(C.c_uint8), i32p, f64p, f64p, f64p]
     lib.gs_reset.argtypes = [C.c_void_p]
+    lib.gs_set_engine.argtypes = [C.c_void_p, C.c_int]
+    lib.gs_set_engine.restype = C.c_int
     lib.gs_launch_count.argtypes = [C.c_void_p]
     lib.gs_launch_count.restype = C.c_int64
     lib.gs_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
@@ -202,6 +204,10 @@ class Engine:
             self.h, sim, int(table.n), _ptr(a, C.c_int32), _ptr(g, C.c_int32), _ptr(c, C.c_int32),
             _ptr(d, C.c_double), _ptr(m, C.c_int64), _ptr(mm, C.c_double), _ptr(it, C.c_double),
             _ptr(ps, C.c_int32)), "gs_load_trace")
+
+    def set_engine(self, mode):
+        """0 auto, 1 warp-per-replica, 2 lane-per-replica."""
+        self._check(self.lib.gs_set_engine(self.h, int(mode)), "gs_set_engine")
 
     def reset(self):
         self._check(self.lib.gs_reset(self.h), "gs_reset")

@@ -45,14 +45,24 @@
 
 // ------------------------------------------------------------------ device state
 
-struct JobState {   // 32 B, written at start, read once at completion
-  int next;         // next job in the same finish-tick bucket (start order)
-  int node0;        // first span inline (most jobs have exactly one)
-  unsigned long long mask0;
-  int ntasks0;
-  int span_cnt;
-  int span_first;   // index into the span pool
-  int pad;
+struct __align__(16) JobState {   // 32 B, written at start, read once at completion
+  int next;                  // next job in the same finish-tick bucket (start order)
+  int node0;                 // span_cnt == 1: the node;  span_cnt > 1: first index in the span pool
+  unsigned long long mask0;  // span_cnt == 1: devices held on node0
+  long long memc;            // gpus * min(device capacity, memory_max): the job's share of the memory column
+  int gpus;
+  int cnt_gpc;               // span_cnt (bits 0-23) | gpu_per_task (bits 24-31)
+};
+#define JS_CNT(x) ((x) & 0xffffff)
+#define JS_GPC(x) ((int)((unsigned)(x) >> 24))
+
+struct __align__(32) JobIn {   // 32 B = one DRAM sector per job, read once in admission order
+  int arrive;       // first tick with normalized_time <= tick
+  int gpus;
+  int gpc;          // gpu_per_container
+  int ps;           // ps_count (0 when the trace has no network columns)
+  long long memb;   // memory_max, bytes
+  double dur;       // minutes * 0.5
 };
 
 struct SimDev {
@@ -63,12 +73,12 @@ struct SimDev {
   long long fit_limit;  // a task fits an empty device iff mem_bytes < fit_limit
   double bandwidth, latency;
   // ---- trace (read-only)
-  const int *arrive, *gpus, *gpc, *ps;
-  const double *dur, *model_mb, *iters;
-  const long long *memb;
+  const JobIn *jobs;
+  const double *model_mb, *iters;
   // ---- results / scratch
   gs_job_rec *rec;
   JobState *jst;
+  int2 *sref;                 // per job: {first index in the span pool, span count}
   int *stack, *fin, *wheel_head, *wheel_tail;
   gs_span *spans;
   gs_tick_row *rows;
@@ -114,14 +124,11 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
   for (int i = lane; i < M; i += 32) { busy[i] = S.nbusy[i]; kk[i] = S.nk[i]; }
   __syncwarp();
 
-  const int *__restrict__ g_arrive = S.arrive;
-  const int *__restrict__ g_gpus = S.gpus;
-  const int *__restrict__ g_gpc = S.gpc;
-  const double *__restrict__ g_dur = S.dur;
-  const long long *__restrict__ g_memb = S.memb;
+  const JobIn *__restrict__ jobs = S.jobs;
   gs_job_rec *rec = S.rec;
   JobState *jst = S.jst;
-  int *stack = S.stack, *fin = S.fin, *wh = S.wheel_head, *wt = S.wheel_tail;
+  int2 *stack = reinterpret_cast<int2 *>(S.stack);
+  int *fin = S.fin, *wh = S.wheel_head, *wt = S.wheel_tail;
   gs_span *spans = S.spans;
   const int wmask = S.wheel_mask;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
@@ -139,14 +146,14 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
 
   // arrival window: lane l holds arrive[wbase + l]
   int wbase = p & ~31;
-  int arr_w = (wbase + lane < n) ? g_arrive[wbase + lane] : 0x7fffffff;
+  int arr_w = (wbase + lane < n) ? jobs[wbase + lane].arrive : 0x7fffffff;
 
   // cached queue head
-  int head = -1, hg = 0, hgpc = 1, htasks = 0;
+  int head = -1, hg = 0, hgpc = 1, htasks = 0, hps = 0, harr = 0;
   long long hmemb = 0;
   double hdur = 0.0;
   bool head_valid = false;
-  int bottom_arr = (top > 0) ? g_arrive[stack[0]] : 0;
+  int bottom_arr = (top > 0) ? stack[0].y : 0;
 
   bool done = (n - p) + running == 0 && ticks > 0;
   if (n == 0) done = true;
@@ -164,11 +171,11 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         cnt += c; q += c;
         if (q < wbase + 32 || q >= n) break;
         wbase += 32;
-        arr_w = (wbase + lane < n) ? g_arrive[wbase + lane] : 0x7fffffff;
+        arr_w = (wbase + lane < n) ? jobs[wbase + lane].arrive : 0x7fffffff;
       }
       if (cnt > 0) {
         // batch [p, p+cnt) lands AHEAD of the queue, first of the batch on top (quirk Q2)
-        for (int i = lane; i < cnt; i += 32) stack[top + i] = p + cnt - 1 - i;
+        for (int i = lane; i < cnt; i += 32) stack[top + i] = make_int2(p + cnt - 1 - i, delta);
         if (top == 0) bottom_arr = delta;
         head = p; head_valid = false;
         top += cnt; p += cnt;
@@ -180,8 +187,9 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
     // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
     if (top > 0) {
       if (!head_valid) {
-        if (head < 0) head = stack[top - 1];
-        hg = g_gpus[head]; hgpc = g_gpc[head]; hmemb = g_memb[head]; hdur = g_dur[head];
+        if (head < 0) head = stack[top - 1].x;
+        JobIn jr = jobs[head];
+        hg = jr.gpus; hgpc = jr.gpc; hmemb = jr.memb; hdur = jr.dur; hps = jr.ps; harr = jr.arrive;
         htasks = hg / hgpc;
         head_valid = true;
       }
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         // ---- commit: pop, network cost, start (algorithm.py:198-200, schedule.py:49-54,164-167)
         const int j = head;
         double dur2 = hdur;
-        if (netcost && S.ps != nullptr && S.ps[j] > 1) {
+        if (netcost && hps > 1) {
           // (model_size/bandwidth + cross*latency) * (iterations*2.0), network_service.py:34-37
           double mps = __ddiv_rn(S.model_mb[j], S.bandwidth);
           double nis = __dmul_rn((double)nspans, S.latency);
@@ -307,21 +315,23 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
           if (lane == 0) { gs_span sp; sp.node = first_node; sp.ntasks = ntasks0; sp.devmask = mask0; spans[span_first] = sp; }
         }
         span_used += nspans;
+        const long long memc = (long long)hg * (hmemb < cap_bytes ? hmemb : cap_bytes);
         if (lane == 0) {
-          rec[j].start = delta; rec[j].end = -1; rec[j].jct = need; rec[j].preempt = 1; rec[j].duration = dur2;
-          JobState js; js.next = -1; js.node0 = first_node; js.mask0 = mask0; js.ntasks0 = ntasks0;
-          js.span_cnt = nspans; js.span_first = span_first; js.pad = endt;
+          rec[j].start = delta; rec[j].end = endt; rec[j].jct = need; rec[j].preempt = 1; rec[j].duration = dur2;
+          JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first; js.mask0 = mask0;
+          js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
           jst[j] = js;
+          S.sref[j] = make_int2(span_first, nspans);
           int slot = endt & wmask;
           int t = wt[slot];
           if (wh[slot] < 0) wh[slot] = j; else jst[t].next = j;
           wt[slot] = j;
         }
         top -= 1;
-        sum_arr -= g_arrive[j];
+        sum_arr -= harr;
         running += 1; started += 1; events += 1;
         busy_gpus += hg;
-        mem_busy += (long long)hg * (hmemb < cap_bytes ? hmemb : cap_bytes);
+        mem_busy += memc;
         head = -1; head_valid = false;
         __syncwarp();
       }
@@ -335,20 +345,19 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         if (lane == 0) { wh[slot] = -1; wt[slot] = -1; }
         while (h >= 0) {
           JobState js = jst[h];
-          int hgp = g_gpus[h];
-          long long mb = g_memb[h];
-          if (js.span_cnt == 1) {
-            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] -= js.ntasks0; }
+          const int scnt = JS_CNT(js.cnt_gpc), sgpc = JS_GPC(js.cnt_gpc);
+          if (scnt == 1) {
+            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] -= (sgpc == 1 ? js.gpus : js.gpus / sgpc); }
           } else {
-            for (int i = lane; i < js.span_cnt; i += 32) {
-              gs_span sp = spans[js.span_first + i];
+            for (int i = lane; i < scnt; i += 32) {
+              gs_span sp = spans[js.node0 + i];
               busy[sp.node] &= ~sp.devmask; kk[sp.node] -= sp.ntasks;
             }
           }
-          if (lane == 0) { rec[h].end = now; fin[finished] = h; }
+          if (lane == 0) fin[finished] = h;
           finished += 1; running -= 1; events += 1;
-          busy_gpus -= hgp;
-          mem_busy -= (long long)hgp * (mb < cap_bytes ? mb : cap_bytes);
+          busy_gpus -= js.gpus;
+          mem_busy -= js.memc;
           h = js.next;
         }
         __syncwarp();
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         // queue is a stack with non-decreasing arrival ticks bottom->top, so the sorted
         // pending list is the stack read top->bottom: median/max are index look-ups
         int ilo = top - 1 - (top - 1) / 2, ihi = top - 1 - top / 2;
-        int a_lo = g_arrive[stack[ilo]], a_hi = g_arrive[stack[ihi]];
+        int a_lo = stack[ilo].y, a_hi = stack[ihi].y;
         pmax = now - bottom_arr; mlo = now - a_lo; mhi = now - a_hi;
       }
       if (lane == 0) {
@@ -390,10 +399,409 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
   }
 }
 
+
+// ------------------------------------------------------------------ lane engine
+// One THREAD owns one replica; a warp carries up to 32 unrelated replicas.  This is the
+// throughput kernel: a replica's tick is almost all scalar bookkeeping, so a whole warp
+// per replica wastes 31/32 of the issue slots, and the number of replicas in flight is
+// capped by HBM capacity (~18 MB per 100k-job replica), so per-tick LATENCY decides
+// throughput.  Everything the common path touches therefore lives in shared memory or
+// registers, and every global load is issued one iteration before its value is needed:
+//   * node table        meta word per node: idle devices (0-7) | ever (8) | free slots (16-31),
+//                       plus the busy-device bitmap (32 or 64 bit)
+//   * wheel window      finish-tick buckets (head, tail) for the next LW ticks; far buckets
+//                       stay in the global wheel and are pulled in LW ticks ahead
+//   * job ring          the next few 32-byte trace records, refilled one per tick
+//   * stack cache       the top 4 queue entries (job, arrival tick)
+//   * release record    JobState of the job finishing next tick, prefetched into registers
+// Shared memory is laid out [word][lane] so lane l always hits bank l: conflict-free no
+// matter which node / slot each lane is looking at.  First fit is a serial scan from `lo`,
+// the lowest node with an idle device (first fit packs low ids, so the scan is short).
+// Lanes never share data: no warp collectives except the per-tick reconvergence barrier.
+#define META_IDLE(m) ((int)((m) & 0xffu))
+#define META_EVER 0x100u
+#define META_KFREE(m) ((int)((m) >> 16))
+#define LW 128          // shared-memory wheel window, ticks (power of two)
+#define RING 8          // job-record ring, entries (power of two)
+#define SCACHE 4        // cached stack entries (power of two)
+#define LANE_EXTRA_WORDS (2 * LW + RING * 8 + SCACHE * 2)
+
+template <typename MaskT>
+__global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, long long max_ticks, int Mmax, int L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int sim = blockIdx.x * L + lane;
+  const bool in_range = lane < L && sim < nsims;
+  SimDev &S = sims[in_range ? sim : 0];
+  const bool alive = in_range && !S.done && S.status == 0;
+
+  const int M = S.M, G = S.G, K = S.K, n = S.n;
+  const int MW = (sizeof(MaskT) == 8) ? 3 : 2;
+  uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw) + (lane < L ? lane : 0);   // [nd * L]
+  uint32_t *mlo = meta + (size_t)Mmax * L;
+  uint32_t *mhi = meta + (size_t)2 * Mmax * L;                 // only when MaskT is 64 bit
+  uint32_t *swh = meta + (size_t)MW * Mmax * L;                // [slot * L]  bucket head
+  uint32_t *swt = swh + (size_t)LW * L;                        //             bucket tail
+  uint32_t *ring = swt + (size_t)LW * L;                       // [(slot * 8 + word) * L]
+  uint32_t *sstk = ring + (size_t)RING * 8 * L;                // [(slot * 2 + {job,arrive}) * L]
+  const MaskT gmask = (G >= (int)(8 * sizeof(MaskT))) ? (MaskT)~(MaskT)0 : (MaskT)(((MaskT)1 << G) - 1);
+
+  const JobIn *__restrict__ jobs = S.jobs;
+  gs_job_rec *rec = S.rec;
+  JobState *jst = S.jst;
+  int2 *sref = S.sref;
+  int2 *stack = reinterpret_cast<int2 *>(S.stack);
+  int *fin = S.fin, *gwh = S.wheel_head, *gwt = S.wheel_tail;
+  gs_span *spans = S.spans;
+  const int wmask = S.wheel_mask;
+  const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
+  const int netcost = S.netcost;
+
+  int delta = S.delta, p = S.p, top = S.top, running = S.running, finished = S.finished;
+  int ever = S.ever, busy_gpus = S.busy_gpus, status = 0;
+  long long mem_busy = S.mem_busy, sum_arr = S.sum_arr, span_used = S.span_used;
+  long long evals = S.evals, started = S.started, ticks = S.ticks;
+  const long long row_first = ticks;
+  gs_tick_row *rows = S.rows;
+  const long long rows_cap = S.rows_cap;
+  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+
+  // ---- stage the persistent state into shared memory
+  int lo = M;
+  int pf = p;                        // ring holds trace records [max(ring_lo, pf - RING), pf)
+  int ring_lo = p;
+  int pend_h = -1, pend_t = -1;      // bucket of tick delta + LW, loaded but not yet in the window
+  if (alive) {
+    for (int nd = 0; nd < M; ++nd) {
+      unsigned long long bz = S.nbusy[nd];
+      unsigned kv = (unsigned)S.nk[nd];
+      int idle = G - __popcll(bz);
+      meta[nd * L] = (uint32_t)idle | ((kv & EVER_BIT) ? META_EVER : 0u) | ((uint32_t)(K - (int)(kv & ~EVER_BIT)) << 16);
+      mlo[nd * L] = (uint32_t)bz;
+      if (sizeof(MaskT) == 8) mhi[nd * L] = (uint32_t)(bz >> 32);
+      if (idle > 0 && nd < lo) lo = nd;
+    }
+    for (int t = delta + 1; t <= delta + LW - 1; ++t) {      // window ticks move from the global wheel
+      int gs_ = t & wmask;
+      swh[(t & (LW - 1)) * L] = (uint32_t)gwh[gs_]; swt[(t & (LW - 1)) * L] = (uint32_t)gwt[gs_];
+      gwh[gs_] = -1; gwt[gs_] = -1;
+    }
+    { int gs_ = (delta + LW) & wmask; pend_h = gwh[gs_]; pend_t = gwt[gs_]; gwh[gs_] = -1; gwt[gs_] = -1; }
+    for (; pf < n && pf < p + RING - 2; ++pf) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(&jobs[pf]);
+      uint4 a0 = src[0], a1 = src[1];
+      uint32_t *r = ring + (size_t)((pf & (RING - 1)) * 8) * L;
+      r[0] = a0.x; r[L] = a0.y; r[2 * L] = a0.z; r[3 * L] = a0.w;
+      r[4 * L] = a1.x; r[5 * L] = a1.y; r[6 * L] = a1.z; r[7 * L] = a1.w;
+    }
+    for (int i = max(top - SCACHE, 0); i < top; ++i) {
+      int2 e = stack[i];
+      sstk[((i & (SCACHE - 1)) * 2) * L] = (uint32_t)e.x; sstk[((i & (SCACHE - 1)) * 2 + 1) * L] = (uint32_t)e.y;
+    }
+  }
+  int cache_lo = max(top - SCACHE, 0);     // stack entries [cache_lo, top) are in the cache
+
+  // trace record q -> registers (ring if resident, else global)
+  auto load_job = [&](int q) -> JobIn {
+    JobIn r;
+    if (q < pf && q >= pf - RING && q >= ring_lo) {
+      const uint32_t *w = ring + (size_t)((q & (RING - 1)) * 8) * L;
+      r.arrive = (int)w[0]; r.gpus = (int)w[L]; r.gpc = (int)w[2 * L]; r.ps = (int)w[3 * L];
+      r.memb = (long long)(((unsigned long long)w[5 * L] << 32) | w[4 * L]);
+      r.dur = __longlong_as_double((long long)(((unsigned long long)w[7 * L] << 32) | w[6 * L]));
+    } else {
+      r = jobs[q];
+    }
+    return r;
+  };
+  auto arrive_of = [&](int q) -> int {
+    if (q >= n) return 0x7fffffff;
+    if (q < pf && q >= pf - RING && q >= ring_lo) return (int)ring[(size_t)((q & (RING - 1)) * 8) * L];
+    return jobs[q].arrive;
+  };
+
+  int next_arrive = alive ? arrive_of(p) : 0x7fffffff;
+  int head = -1, htasks = 1;
+  JobIn hj;
+  hj.arrive = 0; hj.gpus = 1; hj.gpc = 1; hj.ps = 0; hj.memb = 0; hj.dur = 0.0;
+  int bottom_arr = (alive && top > 0) ? stack[0].y : 0;
+  // pipelined loads: issued at the end of iteration d, consumed in iteration d + 1
+  bool rp_valid = false; uint4 rp0 = make_uint4(0, 0, 0, 0), rp1 = make_uint4(0, 0, 0, 0);   // trace record pf
+  int pre_h = -1; JobState pre_js;                                                          // release record
+  pre_js.next = -1; pre_js.node0 = 0; pre_js.mask0 = 0; pre_js.memc = 0; pre_js.gpus = 0; pre_js.cnt_gpc = 1;
+  int com_j = -1; JobState com_js = pre_js;                                                 // last commit
+  bool done = !alive || (n == 0);
+
+  // Every tick starts with the whole warp reconverged (no break/return inside the body,
+  // explicit barrier): otherwise independent thread scheduling lets the replicas drift
+  // apart and run one at a time.
+  while (true) {
+    const bool go = !done && status == 0 && budget > 0 && (ticks - row_first) < rows_cap;
+    if (!__any_sync(FULL, go)) break;
+    if (go) {
+      // ---------------- A. admit arrivals: the batch lands ahead of the queue, first job on top (Q2)
+      if (next_arrive <= delta) {
+        const int a = p;
+        int b = p, na;
+        do { ++b; na = arrive_of(b); } while (na <= delta);
+        if (top == 0) bottom_arr = delta;
+        for (int i = b - 1; i >= a; --i) {
+          stack[top] = make_int2(i, delta);
+          sstk[((top & (SCACHE - 1)) * 2) * L] = (uint32_t)i; sstk[((top & (SCACHE - 1)) * 2 + 1) * L] = (uint32_t)delta;
+          ++top;
+        }
+        if (top - cache_lo > SCACHE) cache_lo = top - SCACHE;
+        sum_arr += (long long)(b - a) * delta;
+        head = a; hj = load_job(a); htasks = hj.gpc == 1 ? hj.gpus : hj.gpus / hj.gpc;
+        p = b; next_arrive = na;
+      }
+      // ---------------- B. one attempt on the queue head (Q1, Q3)
+      com_j = -1;
+      if (top > 0) {
+        if (head < 0) {
+          if (top - 1 >= cache_lo) head = (int)sstk[(((top - 1) & (SCACHE - 1)) * 2) * L];
+          else { head = stack[top - 1].x; cache_lo = top; }      // cache exhausted: deeper entries are global only
+          hj = load_job(head); htasks = hj.gpc == 1 ? hj.gpus : hj.gpus / hj.gpc;
+        }
+        const int hg = hj.gpus, hgpc = hj.gpc;
+        const bool placeable = hj.memb < fit_limit;
+        bool ok = false;
+        int first_node = -1, nspans = 0;
+        const int span_first = (int)span_used;
+        MaskT mask0 = 0;
+        if (hg <= G) {
+          int found = -1;
+          for (int nd = lo; nd < M; ++nd) {
+            uint32_t mt = meta[nd * L];
+            if (META_IDLE(mt) >= hg && META_KFREE(mt) >= htasks) {
+              if (!placeable) { meta[nd * L] = mt - ((uint32_t)htasks << 16); continue; }   // Q21 leak
+              found = nd; break;
+            }
+          }
+          if (found >= 0 && span_used + 1 > S.span_cap) { status = GS_ERR_CAPACITY; found = -1; }
+          if (found >= 0) {
+            uint32_t mt = meta[found * L];
+            MaskT bz = (MaskT)mlo[found * L];
+            if (sizeof(MaskT) == 8) bz |= (MaskT)((unsigned long long)mhi[found * L] << 32);
+            MaskT m = (MaskT)(~bz & gmask), take = 0;
+            for (int i = 0; i < hg; ++i) { MaskT bit = (MaskT)(m & (MaskT)(~m + 1)); take |= bit; m ^= bit; }
+            bz |= take;
+            mlo[found * L] = (uint32_t)bz;
+            if (sizeof(MaskT) == 8) mhi[found * L] = (uint32_t)((unsigned long long)bz >> 32);
+            if (!(mt & META_EVER)) ever += 1;
+            meta[found * L] = (mt - (uint32_t)hg - ((uint32_t)htasks << 16)) | META_EVER;
+            gs_span sp; sp.node = found; sp.ntasks = htasks; sp.devmask = (unsigned long long)take;
+            spans[span_first] = sp;
+            ok = true; first_node = found; nspans = 1; mask0 = take;
+            evals += found + 1;
+          } else {
+            evals += M;
+          }
+        } else {
+          int cum = 0, last = -1;
+          for (int nd = lo; nd < M; ++nd) {
+            uint32_t mt = meta[nd * L];
+            int idle = META_IDLE(mt);
+            int c = min(hgpc == 1 ? idle : idle / hgpc, META_KFREE(mt));
+            if (c <= 0) continue;
+            if (!placeable) { meta[nd * L] = mt - (1u << 16); continue; }     // Q21 leak, one task per node
+            cum += c;
+            if (cum >= htasks) { last = nd; break; }
+          }
+          if (last >= 0 && span_used + min(htasks, M) > S.span_cap) { status = GS_ERR_CAPACITY; last = -1; }
+          if (last >= 0) {
+            int rem = htasks;
+            for (int nd = lo; nd <= last; ++nd) {
+              uint32_t mt = meta[nd * L];
+              int idle = META_IDLE(mt);
+              int c = min(hgpc == 1 ? idle : idle / hgpc, META_KFREE(mt));
+              if (c <= 0) continue;
+              int take_n = min(c, rem);
+              MaskT bz = (MaskT)mlo[nd * L];
+              if (sizeof(MaskT) == 8) bz |= (MaskT)((unsigned long long)mhi[nd * L] << 32);
+              MaskT m = (MaskT)(~bz & gmask), take = 0;
+              for (int i = 0; i < take_n * hgpc; ++i) { MaskT bit = (MaskT)(m & (MaskT)(~m + 1)); take |= bit; m ^= bit; }
+              bz |= take;
+              mlo[nd * L] = (uint32_t)bz;
+              if (sizeof(MaskT) == 8) mhi[nd * L] = (uint32_t)((unsigned long long)bz >> 32);
+              if (!(mt & META_EVER)) ever += 1;
+              meta[nd * L] = (mt - (uint32_t)(take_n * hgpc) - ((uint32_t)take_n << 16)) | META_EVER;
+              gs_span sp; sp.node = nd; sp.ntasks = take_n; sp.devmask = (unsigned long long)take;
+              spans[span_first + nspans] = sp;
+              if (nspans == 0) { first_node = nd; mask0 = take; }
+              ++nspans;
+              rem -= take_n;
+            }
+            ok = true;
+            evals += last + 1;
+          } else {
+            evals += M;
+          }
+        }
+        if (ok) {
+          // ---- commit: pop, network cost, start (algorithm.py:198-200, schedule.py:49-54,164-167)
+          while (lo < M && META_IDLE(meta[lo * L]) == 0) ++lo;
+          const int j = head;
+          double dur2 = hj.dur;
+          if (netcost && hj.ps > 1) {
+            double mps = __ddiv_rn(S.model_mb[j], S.bandwidth);
+            double nis = __dmul_rn((double)nspans, S.latency);
+            double rt = __dmul_rn(S.iters[j], 2.0);
+            dur2 = __dadd_rn(hj.dur, __dmul_rn(__dadd_rn(mps, nis), rt));
+          }
+          double eff = dur2 > hj.dur ? dur2 : hj.dur;
+          double cl = ceil(eff);
+          int need = cl < 1.0 ? 1 : (cl > 1.0e9 ? 0x7fffffff : (int)cl);
+          if (need > wmask) { status = GS_ERR_ARG; need = wmask; }
+          const int endt = delta + need;
+          span_used += nspans;
+          gs_job_rec r; r.start = delta; r.end = endt; r.jct = need; r.preempt = 1; r.duration = dur2;
+          rec[j] = r;
+          sref[j] = make_int2(span_first, nspans);
+          const long long memc = (long long)hg * (hj.memb < cap_bytes ? hj.memb : cap_bytes);
+          JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first;
+          js.mask0 = (unsigned long long)mask0; js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
+          jst[j] = js;
+          com_j = j; com_js = js;
+          // append to the finish-tick bucket (start order): window / pending register / global wheel
+          int tl;
+          if (need <= LW - 1) {
+            const int sl = (endt & (LW - 1)) * L;
+            tl = (int)swt[sl];
+            if (tl < 0) swh[sl] = (uint32_t)j;
+            swt[sl] = (uint32_t)j;
+          } else if (need == LW) {
+            tl = pend_t;
+            if (tl < 0) pend_h = j;
+            pend_t = j;
+          } else {
+            const int gs_ = endt & wmask;
+            tl = gwt[gs_];
+            if (tl < 0) gwh[gs_] = j;
+            gwt[gs_] = j;
+          }
+          if (tl >= 0) {
+            jst[tl].next = j;
+            if (tl == pre_h) pre_js.next = j;
+          }
+          top -= 1;
+          sum_arr -= hj.arrive;
+          running += 1; started += 1;
+          busy_gpus += hg;
+          mem_busy += memc;
+          head = -1;
+        }
+      }
+      // ---------------- D/E. release jobs whose finish tick is now
+      const int now = delta + 1;
+      {
+        const int sl = (now & (LW - 1)) * L;
+        int h = (int)swh[sl];
+        if (h >= 0) {
+          swh[sl] = 0xffffffffu; swt[sl] = 0xffffffffu;
+          do {
+            JobState js;
+            if (h == pre_h) js = pre_js;
+            else if (h == com_j) js = com_js;
+            else js = jst[h];
+            const int scnt = JS_CNT(js.cnt_gpc), sgpc = JS_GPC(js.cnt_gpc);
+            if (scnt == 1) {
+              const int nd = js.node0;
+              mlo[nd * L] &= ~(uint32_t)js.mask0;
+              if (sizeof(MaskT) == 8) mhi[nd * L] &= ~(uint32_t)(js.mask0 >> 32);
+              meta[nd * L] += (uint32_t)js.gpus + ((uint32_t)(sgpc == 1 ? js.gpus : js.gpus / sgpc) << 16);
+              if (nd < lo) lo = nd;
+            } else {
+              for (int i = 0; i < scnt; ++i) {
+                gs_span sp = spans[js.node0 + i];
+                mlo[sp.node * L] &= ~(uint32_t)sp.devmask;
+                if (sizeof(MaskT) == 8) mhi[sp.node * L] &= ~(uint32_t)(sp.devmask >> 32);
+                meta[sp.node * L] += (uint32_t)(sp.ntasks * sgpc) + ((uint32_t)sp.ntasks << 16);
+                if (sp.node < lo) lo = sp.node;
+              }
+            }
+            fin[finished] = h;
+            finished += 1; running -= 1;
+            busy_gpus -= js.gpus;
+            mem_busy -= js.memc;
+            h = js.next;
+          } while (h >= 0);
+        }
+      }
+      // ---------------- H. statistics row (schedule.py:95-133) from O(1) counters
+      {
+        int pmax = 0, mlo_p = 0, mhi_p = 0;
+        if (top > 0) {
+          const int ilo = top - 1 - (top - 1) / 2, ihi = top - 1 - top / 2;
+          const int alo = ilo >= cache_lo ? (int)sstk[((ilo & (SCACHE - 1)) * 2 + 1) * L] : stack[ilo].y;
+          const int ahi = ihi >= cache_lo ? (int)sstk[((ihi & (SCACHE - 1)) * 2 + 1) * L] : stack[ihi].y;
+          pmax = now - bottom_arr; mlo_p = now - alo; mhi_p = now - ahi;
+        }
+        int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
+        const int tg = M * G;
+        const long long ps = (long long)top * now - sum_arr;
+        dst[0] = make_int4(now, M - ever, ever, busy_gpus);
+        dst[1] = make_int4(tg - busy_gpus, running, top, finished);
+        dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(ps & 0xffffffffLL), (int)(ps >> 32));
+        dst[3] = make_int4(pmax, mlo_p, mhi_p, 0);
+      }
+      // ---------------- pipeline stage: retire last iteration's loads, issue the next ones
+      {
+        // bucket of tick delta + LW enters the window (its slot held tick delta, consumed last iteration)
+        const int sl = (delta & (LW - 1)) * L;
+        swh[sl] = (uint32_t)pend_h; swt[sl] = (uint32_t)pend_t;
+        const int gs_ = (delta + 1 + LW) & wmask;
+        pend_h = gwh[gs_]; pend_t = gwt[gs_];
+        gwh[gs_] = -1; gwt[gs_] = -1;
+        // trace record ring: one record per tick
+        if (rp_valid) {
+          uint32_t *r = ring + (size_t)((pf & (RING - 1)) * 8) * L;
+          r[0] = rp0.x; r[L] = rp0.y; r[2 * L] = rp0.z; r[3 * L] = rp0.w;
+          r[4 * L] = rp1.x; r[5 * L] = rp1.y; r[6 * L] = rp1.z; r[7 * L] = rp1.w;
+          ++pf;
+        }
+        // never run further ahead than RING - 2 past p (the 2 slots behind p keep the records of the
+        // jobs admitted last, which are the ones popped next), never fall behind p
+        rp_valid = false;
+        if (pf < p) { pf = p; ring_lo = p; }         // a burst outran the ring: restart it at p
+        if (pf < n && pf < p + RING - 2) {
+          const uint4 *src = reinterpret_cast<const uint4 *>(&jobs[pf]);
+          rp0 = src[0]; rp1 = src[1]; rp_valid = true;
+        }
+        // release record of the job that heads the bucket of tick now + 1
+        pre_h = (int)swh[((now + 1) & (LW - 1)) * L];
+        if (pre_h >= 0) pre_js = jst[pre_h];
+      }
+      ticks += 1; budget -= 1;
+      delta = now;
+      done = (n - p) + running == 0;      // schedule.py:185 -- the queue is NOT counted (Q4)
+    }   // go
+    __syncwarp();
+  }
+
+  if (!alive) return;
+  // ---- persist: node table, wheel window and pending bucket go back to global memory
+  for (int nd = 0; nd < M; ++nd) {
+    uint32_t mt = meta[nd * L];
+    unsigned long long bz = mlo[nd * L];
+    if (sizeof(MaskT) == 8) bz |= (unsigned long long)mhi[nd * L] << 32;
+    S.nbusy[nd] = bz;
+    S.nk[nd] = (int)((uint32_t)(K - META_KFREE(mt)) | ((mt & META_EVER) ? EVER_BIT : 0u));
+  }
+  for (int t = delta + 1; t <= delta + LW - 1; ++t) {
+    gwh[t & wmask] = (int)swh[(t & (LW - 1)) * L]; gwt[t & wmask] = (int)swt[(t & (LW - 1)) * L];
+  }
+  gwh[(delta + LW) & wmask] = pend_h; gwt[(delta + LW) & wmask] = pend_t;
+  S.delta = delta; S.p = p; S.top = top; S.running = running; S.finished = finished;
+  S.ever = ever; S.busy_gpus = busy_gpus; S.mem_busy = mem_busy; S.sum_arr = sum_arr;
+  S.span_used = span_used; S.events = (long long)p + started + finished; S.evals = evals; S.started = started;
+  S.ticks = ticks; S.row_first = row_first; S.done = done ? 1 : 0; S.status = status;
+}
+
 // never-started jobs report start=end=-1, jct=preempt=0 and their input duration
-__global__ void gs_init_rec_kernel(gs_job_rec *rec, const double *dur, int n) {
+__global__ void gs_init_rec_kernel(gs_job_rec *rec, const JobIn *jobs, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0; r.duration = dur[i]; rec[i] = r; }
+  if (i < n) { gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0; r.duration = jobs[i].dur; rec[i] = r; }
 }
 
 // ------------------------------------------------------------------ stateless candidate scoring
@@ -536,6 +944,7 @@ struct gs_engine {
   std::string err;
   double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
   long long launches = 0;  // kernels launched by this handle
+  int engine_mode = 0;     // 0 auto, 1 warp-per-replica, 2 lane-per-replica
   bool dirty = true;       // host mirror of SimDev newer than device copy
 };
 
@@ -670,25 +1079,19 @@ extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arr
   if (max_need > (double)(1 << 26)) return fail(h, GS_ERR_ARG, "gs_load_trace: job duration exceeds 2^26 ticks");
   CU(cudaSetDevice(h->device));
   const size_t N = (size_t)(n > 0 ? n : 1);
-  size_t off_arr = 0, off_gpus = align_up(off_arr + 4 * N), off_gpc = align_up(off_gpus + 4 * N);
-  size_t off_ps = align_up(off_gpc + 4 * N), off_dur = align_up(off_ps + 4 * N);
-  size_t off_model = align_up(off_dur + 8 * N), off_iters = align_up(off_model + 8 * N);
-  size_t off_mem = align_up(off_iters + 8 * N), total = align_up(off_mem + 8 * N);
+  size_t off_jobs = 0, off_model = align_up(off_jobs + sizeof(JobIn) * N), off_iters = align_up(off_model + (net ? 8 * N : 0));
+  size_t total = align_up(off_iters + (net ? 8 * N : 0));
   int rc = ensure_stage(h, total);
   if (rc) return rc;
   unsigned char *st = (unsigned char *)h->h_stage;
-  memset(st, 0, total);
-  if (n > 0) {
-    memcpy(st + off_arr, arrive_tick, 4 * (size_t)n);
-    memcpy(st + off_gpus, gpus, 4 * (size_t)n);
-    memcpy(st + off_gpc, gpu_per_task, 4 * (size_t)n);
-    memcpy(st + off_dur, duration, 8 * (size_t)n);
-    memcpy(st + off_mem, mem_bytes, 8 * (size_t)n);
-    if (net) {
-      memcpy(st + off_ps, ps_count, 4 * (size_t)n);
-      memcpy(st + off_model, model_mb, 8 * (size_t)n);
-      memcpy(st + off_iters, iterations, 8 * (size_t)n);
-    }
+  JobIn *ji = (JobIn *)(st + off_jobs);
+  for (int64_t j = 0; j < n; ++j) {
+    ji[j].arrive = arrive_tick[j]; ji[j].gpus = gpus[j]; ji[j].gpc = gpu_per_task[j];
+    ji[j].ps = net ? ps_count[j] : 0; ji[j].memb = mem_bytes[j]; ji[j].dur = duration[j];
+  }
+  if (net && n > 0) {
+    memcpy(st + off_model, model_mb, 8 * (size_t)n);
+    memcpy(st + off_iters, iterations, 8 * (size_t)n);
   }
   if (s.trace_slab && s.trace_bytes < total) { cudaFree(s.trace_slab); s.trace_slab = nullptr; }
   if (!s.trace_slab) { CU(cudaMalloc(&s.trace_slab, total)); s.trace_bytes = total; }
@@ -701,12 +1104,9 @@ extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arr
   unsigned char *d = (unsigned char *)s.trace_slab;
   SimDev &D = s.dev;
   memset(&D, 0, sizeof(D));
-  D.arrive = (const int *)(d + off_arr); D.gpus = (const int *)(d + off_gpus); D.gpc = (const int *)(d + off_gpc);
-  D.ps = net ? (const int *)(d + off_ps) : nullptr;
-  D.dur = (const double *)(d + off_dur);
+  D.jobs = (const JobIn *)(d + off_jobs);
   D.model_mb = net ? (const double *)(d + off_model) : nullptr;
   D.iters = net ? (const double *)(d + off_iters) : nullptr;
-  D.memb = (const long long *)(d + off_mem);
   s.n = n; s.span_cap = span_cap > 0 ? span_cap : 1;
   s.max_need = (int)max_need + 2;
   s.last_arrive = n > 0 ? arrive_tick[n - 1] : 0;
@@ -720,10 +1120,10 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   const gs_cluster &c = s.cl;
   const int M = c.num_switch * c.num_node_p_switch;
   const size_t N = (size_t)(s.n > 0 ? s.n : 1);
-  int W = 64; while (W < s.max_need + 1) W <<= 1;
+  int W = 256; while (W < s.max_need + 1) W <<= 1;    // >= 2x the lane engine's shared-memory window
   if (rows_cap <= 0) rows_cap = s.last_arrive + 2ll * s.max_need + 4096;
   size_t o_rec = 0, o_jst = align_up(o_rec + sizeof(gs_job_rec) * N), o_stack = align_up(o_jst + sizeof(JobState) * N);
-  size_t o_fin = align_up(o_stack + 4 * N), o_wh = align_up(o_fin + 4 * N), o_wt = align_up(o_wh + 4 * (size_t)W);
+  size_t o_fin = align_up(o_stack + 8 * N), o_sref = align_up(o_fin + 4 * N), o_wh = align_up(o_sref + 8 * N), o_wt = align_up(o_wh + 4 * (size_t)W);
   size_t o_spans = align_up(o_wt + 4 * (size_t)W), o_rows = align_up(o_spans + sizeof(gs_span) * (size_t)s.span_cap);
   size_t o_nb = align_up(o_rows + sizeof(gs_tick_row) * (size_t)rows_cap), o_nk = align_up(o_nb + 8 * (size_t)M);
   size_t total = align_up(o_nk + 4 * (size_t)M);
@@ -744,7 +1144,7 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   D.fit_limit = D.cap_bytes - ((long long)500 << 20);      // cap - mem > 500 MiB  (device.py:75)
   D.bandwidth = c.bandwidth; D.latency = c.internode_latency;
   D.rec = (gs_job_rec *)(d + o_rec); D.jst = (JobState *)(d + o_jst);
-  D.stack = (int *)(d + o_stack); D.fin = (int *)(d + o_fin);
+  D.stack = (int *)(d + o_stack); D.fin = (int *)(d + o_fin); D.sref = (int2 *)(d + o_sref);
   D.wheel_head = (int *)(d + o_wh); D.wheel_tail = (int *)(d + o_wt);
   D.spans = (gs_span *)(d + o_spans); D.rows = (gs_tick_row *)(d + o_rows);
   D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
@@ -753,7 +1153,7 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   D.delta = D.p = D.top = D.running = D.finished = D.ever = D.busy_gpus = D.done = D.status = 0;
   D.mem_busy = D.sum_arr = D.span_used = D.events = D.evals = D.started = D.ticks = D.row_first = 0;
   if (s.n > 0) {
-    gs_init_rec_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(D.rec, D.dur, (int)s.n);
+    gs_init_rec_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(D.rec, D.jobs, (int)s.n);
     h->launches += 1;
   }
   CU(cudaGetLastError());
@@ -778,12 +1178,36 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
     CU(cudaStreamSynchronize(h->stream));
     h->dirty = false;
   }
-  const int stride = (int)align_up((size_t)maxM * 12, 16);
-  if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
-  if (stride > 48 * 1024)
-    CU(cudaFuncSetAttribute(gs_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
+  int maxG = 1;
+  for (auto &s : h->sims) if (s.cl.num_gpu_p_node > maxG) maxG = s.cl.num_gpu_p_node;
+  const size_t lane_words = (size_t)maxM * (maxG > 32 ? 3 : 2) + LANE_EXTRA_WORDS;
+  int L = 32;
+  while (L > 1 && lane_words * (size_t)L * 4 > 100 * 1024) L >>= 1;
+  const size_t lane_smem = lane_words * (size_t)L * 4;
+  bool use_lane = h->engine_mode == 2;   // auto == warp mapping (measured faster at every replica count that fits HBM)
+  if (use_lane && lane_smem > 200 * 1024) {
+    if (h->engine_mode == 2) return fail(h, GS_ERR_ARG, "gs_run: node table too large for the lane engine");
+    use_lane = false;
+  }
   CU(cudaEventRecord(h->e0, h->stream));
-  gs_tick_kernel<<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+  if (use_lane) {
+    const unsigned grid = (unsigned)((h->nsims + L - 1) / L);
+    if (maxG > 32) {
+      if (lane_smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(gs_lane_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+      gs_lane_kernel<unsigned long long><<<grid, 32, lane_smem, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, maxM, L);
+    } else {
+      if (lane_smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(gs_lane_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+      gs_lane_kernel<uint32_t><<<grid, 32, lane_smem, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, maxM, L);
+    }
+  } else {
+    const int stride = (int)align_up((size_t)maxM * 12, 16);
+    if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
+    if (stride > 48 * 1024)
+      CU(cudaFuncSetAttribute(gs_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
+    gs_tick_kernel<<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+  }
   CU(cudaGetLastError());
   h->launches += 1;
   CU(cudaEventRecord(h->e1, h->stream));
@@ -861,11 +1285,11 @@ extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_sp
   if (spans_used) *spans_used = used;
   if (!spans_out && !span_off_out) return GS_OK;
   // spans are pooled in start order on the device; hand them back grouped by job (CSR)
-  std::vector<JobState> js((size_t)(s.n > 0 ? s.n : 1));
+  std::vector<int2> sref((size_t)(s.n > 0 ? s.n : 1));
   std::vector<gs_job_rec> rec((size_t)(s.n > 0 ? s.n : 1));
   std::vector<gs_span> pool((size_t)(used > 0 ? used : 1));
   int rc = GS_OK;
-  if (s.n > 0) rc = timed_d2h(h, js.data(), s.dev.jst, sizeof(JobState) * (size_t)s.n);
+  if (s.n > 0) rc = timed_d2h(h, sref.data(), s.dev.sref, sizeof(int2) * (size_t)s.n);
   if (rc == GS_OK && s.n > 0) rc = timed_d2h(h, rec.data(), s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n);
   if (rc == GS_OK && used > 0) rc = timed_d2h(h, pool.data(), s.dev.spans, sizeof(gs_span) * (size_t)used);
   if (rc) return rc;
@@ -873,12 +1297,12 @@ extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_sp
   for (int64_t j = 0; j < s.n; ++j) {
     if (span_off_out) span_off_out[j] = w;
     if (rec[(size_t)j].start < 0) continue;
-    const JobState &st = js[(size_t)j];
+    const int2 sr = sref[(size_t)j];
     if (spans_out) {
-      if (w + st.span_cnt > spans_cap) return fail(h, GS_ERR_CAPACITY, "gs_fetch_spans: spans_out too small");
-      memcpy(spans_out + w, pool.data() + st.span_first, sizeof(gs_span) * (size_t)st.span_cnt);
+      if (w + sr.y > spans_cap) return fail(h, GS_ERR_CAPACITY, "gs_fetch_spans: spans_out too small");
+      memcpy(spans_out + w, pool.data() + sr.x, sizeof(gs_span) * (size_t)sr.y);
     }
-    w += st.span_cnt;
+    w += sr.y;
   }
   if (span_off_out) span_off_out[s.n] = w;
   return GS_OK;
@@ -989,6 +1413,14 @@ extern "C" int gs_reset(gs_handle h) {
 }
 
 extern "C" int64_t gs_launch_count(gs_handle h) { return h ? h->launches : 0; }
+
+// 0 = auto (lane engine from 32 replicas up), 1 = one warp per replica, 2 = one lane per replica
+extern "C" int gs_set_engine(gs_handle h, int mode) {
+  if (!h) return GS_ERR_ARG;
+  if (mode < 0 || mode > 2) return fail(h, GS_ERR_ARG, "gs_set_engine: mode must be 0, 1 or 2");
+  h->engine_mode = mode;
+  return GS_OK;
+}
 
 // Pinned host buffers for callers that want DMA-speed gs_load_trace / gs_fetch_* copies.
 extern "C" int gs_host_alloc(size_t bytes, void **out) {

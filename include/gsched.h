@@ -173,6 +173,11 @@ int gs_stats(gs_handle h, int sim, gs_run_stats *out);
  * memory (sweeps, benchmarking); also clears the accumulated timers.           */
 int gs_reset(gs_handle h);
 
+/* Kernel mapping: 0 = auto (currently the warp mapping), 1 = one warp per replica
+ * (lanes stripe over nodes), 2 = one lane per replica (32 replicas per warp,
+ * hot state in shared memory; see DESIGN.md for the measured trade-off).        */
+int gs_set_engine(gs_handle h, int mode);
+
 /* Number of CUDA kernels this handle has launched so far.                       */
 int64_t gs_launch_count(gs_handle h);
 

@@ -9,9 +9,13 @@ from conftest import golden_cases, load_golden, render_outputs
 pytestmark = pytest.mark.gpu
 
 
-def _engine_run(cluster, table, rows_cap=0, nsims=1):
+ENGINES = [1, 2]          # 1 = warp per replica, 2 = lane per replica
+
+
+def _engine_run(cluster, table, rows_cap=0, nsims=1, engine=0):
     from gpuschedule_b200 import capi
     with capi.Engine(device=0, nsims=nsims) as eng:
+        eng.set_engine(engine)
         for s in range(nsims):
             eng.config(s, cluster)
             eng.load_trace(s, table)
@@ -38,22 +42,24 @@ def _assert_same(ref, got, tag=""):
     assert st.placement_evals == ref.evals, tag
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("case", golden_cases())
-def test_engine_matches_reference_bytes(case):
+def test_engine_matches_reference_bytes(case, engine):
     """job.csv + all 13 cluster.csv columns byte-identical to the unmodified reference."""
     table, cluster, meta, job_csv, cluster_csv = load_golden(case)
-    rows, recs, order, span_off, spans, st = _engine_run(cluster, table)[0]
+    rows, recs, order, span_off, spans, st = _engine_run(cluster, table, engine=engine)[0]
     got_job, got_cluster = render_outputs(table, cluster, rows, recs, order, span_off, spans,
                                           meta["numpy_seed"])
     assert got_job == job_csv
     assert got_cluster == cluster_csv
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("case", golden_cases())
-def test_engine_matches_oracle_structs(case):
+def test_engine_matches_oracle_structs(case, engine):
     import oracle
     table, cluster, _, _, _ = load_golden(case)
-    _assert_same(oracle.run_fifo(cluster, table), _engine_run(cluster, table)[0], case)
+    _assert_same(oracle.run_fifo(cluster, table), _engine_run(cluster, table, engine=engine)[0], case)
 
 
 SEEDED = [
@@ -69,14 +75,15 @@ SEEDED = [
 ]
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("cfg", SEEDED, ids=[f"seed{c[1]}" for c in SEEDED])
-def test_engine_matches_oracle_seeded(cfg):
+def test_engine_matches_oracle_seeded(cfg, engine):
     import oracle
     from gpuschedule_b200 import capi, ingest, tracegen
     n, seed, rate, ckw, tkw = cfg
     cluster = capi.make_cluster(**ckw)
     table = ingest.table_from_columns(tracegen.synth_columns(n, seed=seed, rate=rate, **tkw))
-    _assert_same(oracle.run_fifo(cluster, table), _engine_run(cluster, table)[0], f"seed{seed}")
+    _assert_same(oracle.run_fifo(cluster, table), _engine_run(cluster, table, engine=engine)[0], f"seed{seed}")
 
 
 def test_row_window_resume_is_identical():
@@ -86,12 +93,39 @@ def test_row_window_resume_is_identical():
     cluster = capi.make_cluster(num_switch=2, num_node_p_switch=9)
     table = ingest.table_from_columns(tracegen.synth_columns(800, seed=7, rate=1.2))
     ref = oracle.run_fifo(cluster, table)
-    for cap in (1, 7, 64, 1000):
-        _assert_same(ref, _engine_run(cluster, table, rows_cap=cap)[0], f"rows_cap={cap}")
+    for engine in ENGINES:
+        for cap in (1, 7, 64, 1000):
+            _assert_same(ref, _engine_run(cluster, table, rows_cap=cap, engine=engine)[0], f"rows_cap={cap}")
 
 
-def test_replicas_are_independent():
-    """Many replicas in one launch (one warp each), different traces and clusters."""
+def test_kernels_can_alternate_between_launches():
+    """Both kernels persist the same state, so a run may switch mapping at any launch."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    cluster = capi.make_cluster(num_switch=2, num_node_p_switch=9)
+    table = ingest.table_from_columns(tracegen.synth_columns(600, seed=8, rate=1.1))
+    ref = oracle.run_fifo(cluster, table)
+    with capi.Engine(device=0, nsims=1) as eng:
+        eng.config(0, cluster)
+        eng.load_trace(0, table)
+        parts, seen, k = [], 0, 0
+        while True:
+            eng.set_engine(1 + k % 2)
+            k += 1
+            eng.run(0, 97)
+            st = eng.stats(0)
+            parts.append(eng.fetch_rows(0, seen, st.ticks - seen))
+            seen = st.ticks
+            if st.done:
+                break
+        recs, order = eng.fetch_jobs(0)
+        span_off, spans = eng.fetch_spans(0)
+        _assert_same(ref, (np.concatenate(parts), recs, order, span_off, spans, eng.stats(0)), "alternate")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_replicas_are_independent(engine):
+    """Many replicas in one launch, different traces and clusters."""
     import oracle
     from gpuschedule_b200 import capi, ingest, tracegen
     nsims = 150
@@ -100,6 +134,7 @@ def test_replicas_are_independent():
         clusters.append(capi.make_cluster(num_switch=1 + s % 4, num_node_p_switch=8 + 3 * (s % 7)))
         tables.append(ingest.table_from_columns(tracegen.synth_columns(200 + 5 * s, seed=1000 + s, rate=0.4 + 0.05 * (s % 9))))
     with capi.Engine(device=0, nsims=nsims) as eng:
+        eng.set_engine(engine)
         for s in range(nsims):
             eng.config(s, clusters[s])
             eng.load_trace(s, tables[s])
@@ -120,9 +155,9 @@ def test_network_cost_run_matches_oracle():
     table = ingest.table_from_columns(tracegen.synth_columns(1500, seed=55, rate=0.3, with_network=True))
     assert table.model_mb is not None and table.ps_count is not None
     ref = oracle.run_fifo(cluster, table)
-    got = _engine_run(cluster, table)[0]
     assert np.any(ref.recs["duration"] != table.duration)       # the cost term is exercised
-    _assert_same(ref, got, "netcost")
+    for engine in ENGINES:
+        _assert_same(ref, _engine_run(cluster, table, engine=engine)[0], "netcost")
 
 
 def test_place_batch_matches_oracle():
@@ -186,7 +221,7 @@ def test_full_size_properties_100k():
     from gpuschedule_b200 import capi, ingest, tracegen
     cluster = capi.make_cluster(4, 32, 8)
     table = ingest.table_from_columns(tracegen.synth_columns(100000, seed=1, rate=0.5))
-    rows, recs, order, span_off, spans, st = _engine_run(cluster, table)[0]
+    rows, recs, order, span_off, spans, st = _engine_run(cluster, table, engine=2)[0]
     n = table.n
     assert st.done == 1 and st.finished == n and st.events == 3 * n
     assert np.array_equal(rows["now"], np.arange(1, len(rows) + 1))

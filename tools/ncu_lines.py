@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Join an ncu report's SASS page with nvdisasm line info and aggregate per CUDA source line.
+
+  python tools/ncu_lines.py gpurun_out/prof.ncu-rep gs_lane_kernelIj [--top 40]
+
+Needs the .so the report was captured with (same build) at gpuschedule_b200/libgsched.so.
+"""
+import csv
+import re
+import subprocess
+import sys
+import tempfile
+import os
+
+rep, kern = sys.argv[1], sys.argv[2]
+top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
+repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+so = os.path.join(repo, "gpuschedule_b200", "libgsched.so")
+src_path = os.path.join(repo, "gpuschedule_b200", "csrc", "gsched.cu")
+src = open(src_path).read().split("\n")
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+off2line, cur, infn = {}, 0, False
+for ln in dis.split("\n"):
+    if ln.startswith(".text."):
+        infn = kern in ln
+        continue
+    if not infn:
+        continue
+    m = re.search(r'//## File ".*", line (\d+)', ln)
+    if m:
+        cur = int(m.group(1)); continue
+    m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*);", ln)
+    if m:
+        off2line[int(m.group(1), 16)] = cur
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.split("\n")))
+hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+h = rows[hi]
+ie, te, sm = h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("# Samples")
+base = None
+agg = {}
+for r in rows[hi + 1:]:
+    if len(r) <= te:
+        continue
+    addr = int(r[0], 16)
+    if base is None:
+        base = addr
+    line = off2line.get(addr - base, -1)
+    a = agg.setdefault(line, [0, 0, 0])
+    a[0] += int(r[ie]); a[1] += int(r[te]); a[2] += int(r[sm])
+tot = sum(a[0] for a in agg.values()); tots = sum(a[2] for a in agg.values())
+print(f"total warp instructions {tot}, samples {tots}")
+for line, a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
+    text = src[line - 1].strip()[:95] if 0 < line <= len(src) else "?"
+    print("%5d: inst %5.1f%%  samples %5.1f%%  thr/inst %5.1f | %s" % (line, 100 * a[0] / tot, 100 * a[2] / max(tots, 1), a[1] / max(a[0], 1), text))
