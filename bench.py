@@ -157,7 +157,8 @@ def ours(args):
     R, n = args.replicas, args.jobs
     cluster = capi.make_cluster(4, 32, 8)
     t0 = time.time()
-    tables = [fast_table(n, BASE_SEED + rank * R + r) for r in range(R)]
+    from gpuschedule_b200 import dist as gdist
+    tables = [fast_table(n, sd) for sd in gdist.replica_seeds(rank, world, R, base=BASE_SEED)]
     log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
     eng = capi.Engine(device=local, nsims=R)
     eng.set_engine(args.engine)
@@ -218,6 +219,11 @@ def ours(args):
     pin_rows = capi.PinnedBuffer(T * ROW_DTYPE.itemsize)
     pin_jobs = capi.PinnedBuffer(n * JOB_DTYPE.itemsize)
     pin_ord = capi.PinnedBuffer(n * 4)
+    span_cap = int(max(len(eng.fetch_spans(r)[1]) for r in range(min(R, 8))) * 1.25) + 4096
+    pin_off = capi.PinnedBuffer((n + 1) * 8)
+    pin_sp = capi.PinnedBuffer(span_cap * SPAN_DTYPE.itemsize)
+    off_v = pin_off.view(np.int64, n + 1)
+    sp_v = pin_sp.view(SPAN_DTYPE, span_cap)
     rows_v = pin_rows.view(ROW_DTYPE, T)
     jobs_v = pin_jobs.view(JOB_DTYPE, n)
     ord_v = pin_ord.view(np.int32, n)
@@ -236,9 +242,9 @@ def ours(args):
             s = eng.stats(r)
             rows = eng.fetch_rows(r, 0, s.ticks, out=rows_v)
             recs, order = eng.fetch_jobs(r, out_recs=jobs_v, out_order=ord_v)
-            span_off, spans = eng.fetch_spans(r)
+            span_off, spans = eng.fetch_spans(r, out_off=off_v, out_spans=sp_v)
             checksum += int(rows["finished"][-1]) + int(recs["end"][0]) + int(order[-1]) + len(spans)
-            d2h += s.ticks * 64 + n * 24 + s.finished * 4 + len(spans) * 16 + n * 56
+            d2h += s.ticks * 64 + n * 24 + s.finished * 4 + len(spans) * 16 + (n + 1) * 8
     barrier_sync()
     e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / e2e_steps
     e2e = {"value": events_all / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -278,7 +284,7 @@ def ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)
-    pin_rows.free(); pin_jobs.free(); pin_ord.free()
+    pin_rows.free(); pin_jobs.free(); pin_ord.free(); pin_off.free(); pin_sp.free()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -332,7 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--jobs", type=int, default=100000)
-    ap.add_argument("--replicas", type=int, default=1184, help="replicas per GPU (one warp each)")
+    ap.add_argument("--replicas", type=int, default=2368, help="replicas per GPU (one warp each)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)

@@ -60,7 +60,10 @@ def make_cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8, num_cpu_p
                      float(bandwidth), float(internode_latency))
 
 
-def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), gittins_delta=3250.0):
+def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), gittins_delta=3250.0,
+                gittins_table=None):
+    """gs_policy.  `gittins_table` = (data, index) float64 arrays from policies.build_gittins_table;
+    the arrays are kept alive on the returned object."""
     p = GsPolicy()
     p.schedule = SCHEDULES[schedule]
     p.scheme = SCHEMES[scheme]
@@ -68,6 +71,13 @@ def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), git
     for i, v in enumerate(list(queue_limit)[:GS_MAX_QUEUES]):
         p.queue_limit[i] = float(v)
     p.gittins_delta = float(gittins_delta)
+    if gittins_table is not None:
+        data = np.ascontiguousarray(gittins_table[0], dtype=np.float64)
+        idx = np.ascontiguousarray(gittins_table[1], dtype=np.float64)
+        p._keep = (data, idx)
+        p.gittins_n = len(data)
+        p.gittins_data = data.ctypes.data
+        p.gittins_index = idx.ctypes.data
     return p
 
 
@@ -260,19 +270,18 @@ class Engine:
                                            _ptr(order, C.c_int32)), "gs_fetch_jobs")
         return recs, order[:int(self.stats(sim).finished)]
 
-    def fetch_spans(self, sim=0, cap=None):
+    def fetch_spans(self, sim=0, out_off=None, out_spans=None):
+        """(span_off[n+1], spans) grouped by job; optional caller (pinned) buffers."""
         n = self._n[sim]
-        off = np.zeros(n + 1, dtype=np.int64)
+        off = np.zeros(n + 1, dtype=np.int64) if out_off is None else out_off[:n + 1]
         used = C.c_int64(0)
-        if cap is None:       # ask for the size first
-            self._check(self.lib.gs_fetch_spans(self.h, sim, _ptr(off, C.c_int64), None, 0,
-                                                C.byref(used)), "gs_fetch_spans")
-            cap = used.value
-        spans = np.empty(int(cap), dtype=SPAN_DTYPE)
+        if out_spans is None:
+            self._check(self.lib.gs_fetch_spans(self.h, sim, None, None, 0, C.byref(used)), "gs_fetch_spans")
+            out_spans = np.empty(max(int(used.value), 1), dtype=SPAN_DTYPE)
         self._check(self.lib.gs_fetch_spans(self.h, sim, _ptr(off, C.c_int64),
-                                            spans.ctypes.data_as(C.c_void_p), int(cap),
+                                            out_spans.ctypes.data_as(C.c_void_p), len(out_spans),
                                             C.byref(used)), "gs_fetch_spans")
-        return off, spans[:used.value]
+        return off, out_spans[:used.value]
 
     def place_batch(self, cluster: GsCluster, nodes, jobs, task_off=None):
         nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)

@@ -65,6 +65,12 @@ struct __align__(32) JobIn {   // 32 B = one DRAM sector per job, read once in a
   double dur;       // minutes * 0.5
 };
 
+struct PJob {     // 32 B: the fields of the legacy job dict the policies touch (run_sim.py:208-230,730-779)
+  int last_check, total_exec, exec, pending, last_pending, start, resume;
+  unsigned char status, q_id, pad0, pad1;
+};
+enum { PST_NONE = 0, PST_PENDING = 1, PST_RUNNING = 2, PST_END = 3 };
+
 struct SimDev {
   // ---- configuration
   int M, G, K;          // nodes, gpus/node, task slots/node = min(cpu/cpu_pt, mem/mem_pt)
@@ -85,8 +91,15 @@ struct SimDev {
   unsigned long long *nbusy;  // persisted node table (between launches)
   int *nk;                    // bit31 = node ever hosted a placement (node.py:93-97, never cleared)
   long long span_cap, rows_cap;
+  // ---- event-driven policies (sjf / dlas / dlas-gpu / gittins): scratch + parameters
+  struct PJob *pj;            // per-job dynamic state
+  int *runnable, *queues, *endj, *tmpl, *cidle, *ckfree;   // queues: num_queue lists of n entries
+  const double *git_data, *git_index;                      // device copies of the gittins tables
+  double queue_limit[GS_MAX_QUEUES];
+  double gittins_delta, next_gittins_unit;
+  int num_queue, git_n, rn, en, end_time, next_job_jump, qn[GS_MAX_QUEUES];
   // ---- loop state (persisted)
-  int delta, p, top, running, finished, ever, busy_gpus, done, status, pad1;
+  int delta, p, top, running, finished, ever, busy_gpus, done, status, need_init;
   long long mem_busy, sum_arr, span_used, events, evals, started, ticks, row_first;
 };
 
@@ -108,7 +121,32 @@ __device__ __forceinline__ int node_cap(unsigned long long busy, int k, int G, i
   return c > 0 ? c : 0;
 }
 
-// One warp advances one replica.  Dynamic shared memory: per warp M*(8+4) bytes.
+// Shared-memory geometry shared by both tick kernels
+#define LW 128          // finish-tick buckets kept in shared memory (ticks, power of two)
+#define SCACHE 4        // cached top-of-queue entries (power of two)
+#define WARP_EXTRA_BYTES (LW * 8 + SCACHE * 8)
+
+__device__ __forceinline__ unsigned long long take_lowest(unsigned long long idle, int cnt, int G) {
+  // the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
+  if (G <= 32) {
+    unsigned m = (unsigned)idle;
+    if (cnt >= __popc(m)) return idle;
+    for (int i = 0; i < cnt; ++i) m &= m - 1u;
+    return (unsigned long long)((unsigned)idle ^ m);
+  }
+  unsigned long long m = idle;
+  if (cnt >= __popcll(m)) return idle;
+  for (int i = 0; i < cnt; ++i) m &= m - 1ull;
+  return idle ^ m;
+}
+
+// One warp advances one replica.  Lanes stripe over the node table for placement; all other
+// state is warp-uniform.  Per warp in shared memory: node table (busy mask u64 + slot counter
+// i32 per node), a LW-tick window of the finish wheel (head, tail) and the top SCACHE queue
+// entries.  Every global load on the per-tick path is issued one tick before its value is
+// needed (pending wheel bucket, release record of the next tick's first finisher) or comes
+// from a register-resident 32-record window of the trace, so the loop body has no dependent
+// DRAM/L2 round trip in the common case.
 __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -116,19 +154,18 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
   const int sim = blockIdx.x * (blockDim.x >> 5) + warp;
   if (sim >= nsims) return;
   SimDev &S = sims[sim];
-  if (S.done || S.status != 0) return;
+  if (S.done || S.status != 0 || S.policy != GS_SCHED_FIFO) return;
 
-  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)warp * smem_stride);
   const int M = S.M, G = S.G, K = S.K, n = S.n;
+  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)warp * smem_stride);
   int *kk = reinterpret_cast<int *>(busy + M);
-  for (int i = lane; i < M; i += 32) { busy[i] = S.nbusy[i]; kk[i] = S.nk[i]; }
-  __syncwarp();
+  int2 *sstk = reinterpret_cast<int2 *>(kk + M + (M & 1));   // 8-byte aligned
 
   const JobIn *__restrict__ jobs = S.jobs;
   gs_job_rec *rec = S.rec;
   JobState *jst = S.jst;
   int2 *stack = reinterpret_cast<int2 *>(S.stack);
-  int *fin = S.fin, *wh = S.wheel_head, *wt = S.wheel_tail;
+  int *fin = S.fin, *gwh = S.wheel_head, *gwt = S.wheel_tail;
   gs_span *spans = S.spans;
   const int wmask = S.wheel_mask;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
@@ -138,94 +175,130 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
   int delta = S.delta, p = S.p, top = S.top, running = S.running, finished = S.finished;
   int ever = S.ever, busy_gpus = S.busy_gpus, status = 0;
   long long mem_busy = S.mem_busy, sum_arr = S.sum_arr, span_used = S.span_used;
-  long long events = S.events, evals = S.evals, started = S.started, ticks = S.ticks;
+  long long evals = S.evals, started = S.started, ticks = S.ticks;
   const long long row_first = ticks;
   gs_tick_row *rows = S.rows;
   const long long rows_cap = S.rows_cap;
   long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
 
-  // arrival window: lane l holds arrive[wbase + l]
-  int wbase = p & ~31;
-  int arr_w = (wbase + lane < n) ? jobs[wbase + lane].arrive : 0x7fffffff;
+  // ---- stage persistent state: node table, wheel window, queue top
+  for (int i = lane; i < M; i += 32) { busy[i] = S.nbusy[i]; kk[i] = S.nk[i]; }
+  for (int i = max(top - SCACHE, 0) + lane; i < top; i += 32) sstk[i & (SCACHE - 1)] = stack[i];
+  int cache_lo = max(top - SCACHE, 0);           // queue entries [cache_lo, top) are cached
+  __syncwarp();
 
-  // cached queue head
-  int head = -1, hg = 0, hgpc = 1, htasks = 0, hps = 0, harr = 0;
+  // trace window: lane l holds record wbase + l
+  int wbase = p & ~31;
+  JobIn wj;
+  wj.arrive = 0x7fffffff; wj.gpus = 1; wj.gpc = 1; wj.ps = 0; wj.memb = 0; wj.dur = 0.0;
+  if (wbase + lane < n) wj = jobs[wbase + lane];
+
+  // queue head (cached while it stays the head)
+  int head = -1, hg = 1, hgpc = 1, htasks = 1, hps = 0, harr = 0;
   long long hmemb = 0;
   double hdur = 0.0;
   bool head_valid = false;
   int bottom_arr = (top > 0) ? stack[0].y : 0;
 
-  bool done = (n - p) + running == 0 && ticks > 0;
-  if (n == 0) done = true;
+  // release record of the job committed this tick (saves the reload when it finishes at once)
+  int com_j = -1;
+  JobState com_js; com_js.next = -1; com_js.node0 = 0; com_js.mask0 = 0; com_js.memc = 0; com_js.gpus = 0; com_js.cnt_gpc = 1;
 
-  while (!done && budget > 0) {
+  bool done = (n == 0);
+
+  while (!done && budget > 0 && status == 0) {
     if (ticks - row_first >= rows_cap) break;   // row window full: host drains and relaunches
     // ---------------- A. admit arrivals (gen_jobs + head insert)
     {
-      int cnt = 0;
-      int q = p;
+      int cnt = 0, q = p;
       while (q < n) {
-        int idx = wbase + lane;
-        unsigned b = __ballot_sync(FULL, idx >= q && idx < n && arr_w <= delta);
-        int c = __popc(b);
+        const int idx = wbase + lane;
+        const unsigned b = __ballot_sync(FULL, idx >= q && idx < n && wj.arrive <= delta);
+        const int c = __popc(b);
+        if (c > 0 && cnt == 0) {
+          // the batch's first job becomes the queue head: take its record out of the window now
+          const int src = p - wbase;
+          hg = __shfl_sync(FULL, wj.gpus, src); hgpc = __shfl_sync(FULL, wj.gpc, src);
+          hps = __shfl_sync(FULL, wj.ps, src); harr = __shfl_sync(FULL, wj.arrive, src);
+          hmemb = __shfl_sync(FULL, wj.memb, src);
+          hdur = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(wj.dur), src));
+        }
         cnt += c; q += c;
         if (q < wbase + 32 || q >= n) break;
         wbase += 32;
-        arr_w = (wbase + lane < n) ? jobs[wbase + lane].arrive : 0x7fffffff;
+        wj.arrive = 0x7fffffff;
+        if (wbase + lane < n) wj = jobs[wbase + lane];
       }
       if (cnt > 0) {
         // batch [p, p+cnt) lands AHEAD of the queue, first of the batch on top (quirk Q2)
-        for (int i = lane; i < cnt; i += 32) stack[top + i] = make_int2(p + cnt - 1 - i, delta);
+        for (int i = lane; i < cnt; i += 32) {
+          const int2 e = make_int2(p + cnt - 1 - i, delta);
+          stack[top + i] = e;
+          if (i >= cnt - SCACHE) sstk[(top + i) & (SCACHE - 1)] = e;
+        }
         if (top == 0) bottom_arr = delta;
-        head = p; head_valid = false;
+        head = p; head_valid = true; htasks = hgpc == 1 ? hg : hg / hgpc;
         top += cnt; p += cnt;
+        if (top - cache_lo > SCACHE) cache_lo = top - SCACHE;
         sum_arr += (long long)cnt * delta;
-        events += cnt;
         __syncwarp();
       }
     }
     // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
+    com_j = -1;
     if (top > 0) {
       if (!head_valid) {
-        if (head < 0) head = stack[top - 1].x;
-        JobIn jr = jobs[head];
-        hg = jr.gpus; hgpc = jr.gpc; hmemb = jr.memb; hdur = jr.dur; hps = jr.ps; harr = jr.arrive;
-        htasks = hg / hgpc;
+        if (top - 1 >= cache_lo) head = sstk[(top - 1) & (SCACHE - 1)].x;
+        else { head = stack[top - 1].x; cache_lo = top; }
+        if (head >= wbase && head < wbase + 32) {
+          const int src = head - wbase;
+          hg = __shfl_sync(FULL, wj.gpus, src); hgpc = __shfl_sync(FULL, wj.gpc, src);
+          hps = __shfl_sync(FULL, wj.ps, src); harr = __shfl_sync(FULL, wj.arrive, src);
+          hmemb = __shfl_sync(FULL, wj.memb, src);
+          hdur = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(wj.dur), src));
+        } else {
+          const JobIn jr = jobs[head];
+          hg = jr.gpus; hgpc = jr.gpc; hmemb = jr.memb; hdur = jr.dur; hps = jr.ps; harr = jr.arrive;
+        }
+        htasks = hgpc == 1 ? hg : hg / hgpc;
         head_valid = true;
       }
       const bool placeable = hmemb < fit_limit;   // Device.can_fit on an empty device
       bool ok = false;
-      int first_node = -1, nspans = 0, span_first = (int)span_used;
-      unsigned long long mask0 = 0; int ntasks0 = 0;
+      int first_node = -1, nspans = 0;
+      const int span_first = (int)span_used;
+      unsigned long long mask0 = 0;
       if (hg <= G) {
         // try_single_node_alloc_ms: first node (id order) that fits the whole job
         int found = -1;
         for (int base = 0; base < M; base += 32) {
-          int nd = base + lane;
+          const int nd = base + lane;
           bool fit = false;
           if (nd < M) {
-            int idle = G - __popcll(busy[nd]);
-            int slots = K - (int)(kk[nd] & ~EVER_BIT);
+            const int idle = G - __popcll(busy[nd]);
+            const int slots = K - (int)(kk[nd] & ~EVER_BIT);
             fit = idle >= hg && slots >= htasks;
           }
-          unsigned b = __ballot_sync(FULL, fit);
+          const unsigned b = __ballot_sync(FULL, fit);
           if (!placeable) {          // quirk Q21: cpu/mem charged for every task, never refunded
             if (fit) kk[nd] += htasks;
             continue;
           }
           if (b) { found = base + __ffs(b) - 1; break; }
         }
+        if (found >= 0 && span_used + 1 > S.span_cap) { status = GS_ERR_CAPACITY; found = -1; }
         if (found >= 0) {
-          ok = true; first_node = found; nspans = 1; ntasks0 = htasks;
+          ok = true; first_node = found; nspans = 1;
           bool fresh = false;
           if (lane == (found & 31)) {
-            unsigned long long idle = ~busy[found] & gmask, take;
-            lowest_bits(idle, hg, &take);
+            const unsigned long long take = take_lowest(~busy[found] & gmask, hg, G);
             busy[found] |= take;
-            unsigned kv = (unsigned)kk[found];
+            const unsigned kv = (unsigned)kk[found];
             kk[found] = (int)((kv + htasks) | EVER_BIT);
             mask0 = take;
             fresh = !(kv & EVER_BIT);
+            gs_span sp; sp.node = found; sp.ntasks = htasks; sp.devmask = take;
+            spans[span_first] = sp;
           }
           mask0 = __shfl_sync(FULL, mask0, found & 31);
           ever += __popc(__ballot_sync(FULL, fresh));
@@ -238,54 +311,52 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         int cum = 0, last_base = -1;
         if (placeable) {
           for (int base = 0; base < M; base += 32) {
-            int nd = base + lane;
-            int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
+            const int nd = base + lane;
+            const int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
             cum += __reduce_add_sync(FULL, c);
             if (cum >= htasks) { last_base = base; break; }
           }
         } else {
           for (int base = 0; base < M; base += 32) {   // quirk Q21, cross-node flavour: one task charged per node
-            int nd = base + lane;
+            const int nd = base + lane;
             if (nd < M && node_cap(busy[nd], kk[nd], G, K, hgpc) > 0) kk[nd] += 1;
           }
         }
+        if (last_base >= 0 && span_used + min(htasks, M) > S.span_cap) { status = GS_ERR_CAPACITY; last_base = -1; }
         if (last_base >= 0) {
           // pass 1 proved the job fits: commit (a failed walk is rolled back exactly by the
           // reference, algorithm.py:378-387, so no state changes in that case)
           ok = true;
-          if (span_used + min(htasks, M) > S.span_cap) { status = GS_ERR_CAPACITY; break; }
           int rem = htasks, last_node = 0;
           for (int base = 0; base <= last_base; base += 32) {
-            int nd = base + lane;
-            int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
+            const int nd = base + lane;
+            const int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
             int incl = c;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-            int take = min(c, max(rem - (incl - c), 0));
-            unsigned tb = __ballot_sync(FULL, take > 0);
+            const int take = min(c, max(rem - (incl - c), 0));
+            const unsigned tb = __ballot_sync(FULL, take > 0);
             bool fresh = false;
             if (take > 0) {
-              unsigned long long idle = ~busy[nd] & gmask, tk;
-              lowest_bits(idle, take * hgpc, &tk);
+              const unsigned long long tk = take_lowest(~busy[nd] & gmask, take * hgpc, G);
               busy[nd] |= tk;
-              unsigned kv = (unsigned)kk[nd];
+              const unsigned kv = (unsigned)kk[nd];
               kk[nd] = (int)((kv + take) | EVER_BIT);
               fresh = !(kv & EVER_BIT);
-              int slot = nspans + __popc(tb & ((1u << lane) - 1u));
+              const int slot = nspans + __popc(tb & ((1u << lane) - 1u));
               gs_span sp; sp.node = nd; sp.ntasks = take; sp.devmask = tk;
               spans[span_first + slot] = sp;
-              if (slot == 0) { mask0 = tk; ntasks0 = take; first_node = nd; }
+              if (slot == 0) { mask0 = tk; first_node = nd; }
             }
             ever += __popc(__ballot_sync(FULL, fresh));
             if (tb) last_node = base + 31 - __clz(tb);
             nspans += __popc(tb);
-            int tot = __shfl_sync(FULL, incl, 31);
+            const int tot = __shfl_sync(FULL, incl, 31);
             rem -= min(rem, tot);
           }
           {  // first-span fields live in whichever lane owned slot 0
-            int src = __ffs(__ballot_sync(FULL, first_node >= 0)) - 1;
+            const int src = __ffs(__ballot_sync(FULL, first_node >= 0)) - 1;
             mask0 = __shfl_sync(FULL, mask0, src);
-            ntasks0 = __shfl_sync(FULL, ntasks0, src);
             first_node = __shfl_sync(FULL, first_node, src);
           }
           evals += last_node + 1;
@@ -300,36 +371,36 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         double dur2 = hdur;
         if (netcost && hps > 1) {
           // (model_size/bandwidth + cross*latency) * (iterations*2.0), network_service.py:34-37
-          double mps = __ddiv_rn(S.model_mb[j], S.bandwidth);
-          double nis = __dmul_rn((double)nspans, S.latency);
-          double rt = __dmul_rn(S.iters[j], 2.0);
+          const double mps = __ddiv_rn(S.model_mb[j], S.bandwidth);
+          const double nis = __dmul_rn((double)nspans, S.latency);
+          const double rt = __dmul_rn(S.iters[j], 2.0);
           dur2 = __dadd_rn(hdur, __dmul_rn(__dadd_rn(mps, nis), rt));
         }
-        double eff = dur2 > hdur ? dur2 : hdur;               // Job.get_duration (job.py:206-210)
-        double cl = ceil(eff);
+        const double eff = dur2 > hdur ? dur2 : hdur;               // Job.get_duration (job.py:206-210)
+        const double cl = ceil(eff);
         int need = cl < 1.0 ? 1 : (cl > 1.0e9 ? 0x7fffffff : (int)cl);   // quirk Q11
-        if (need > wmask) { status = GS_ERR_ARG; break; }
+        if (need > wmask) { status = GS_ERR_ARG; need = wmask; }
         const int endt = delta + need;
-        if (hg <= G) {
-          if (span_used + 1 > S.span_cap) { status = GS_ERR_CAPACITY; break; }
-          if (lane == 0) { gs_span sp; sp.node = first_node; sp.ntasks = ntasks0; sp.devmask = mask0; spans[span_first] = sp; }
-        }
         span_used += nspans;
         const long long memc = (long long)hg * (hmemb < cap_bytes ? hmemb : cap_bytes);
+        JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first; js.mask0 = mask0;
+        js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
+        com_j = j; com_js = js;
+        // append to the finish-tick bucket of the timing wheel (start order)
+        const int gs_ = endt & wmask;
+        const int tl = gwt[gs_];
         if (lane == 0) {
-          rec[j].start = delta; rec[j].end = endt; rec[j].jct = need; rec[j].preempt = 1; rec[j].duration = dur2;
-          JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first; js.mask0 = mask0;
-          js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
+          if (tl < 0) gwh[gs_] = j;
+          gwt[gs_] = j;
+          gs_job_rec r; r.start = delta; r.end = endt; r.jct = need; r.preempt = 1; r.duration = dur2;
+          rec[j] = r;
           jst[j] = js;
           S.sref[j] = make_int2(span_first, nspans);
-          int slot = endt & wmask;
-          int t = wt[slot];
-          if (wh[slot] < 0) wh[slot] = j; else jst[t].next = j;
-          wt[slot] = j;
+          if (tl >= 0) jst[tl].next = j;
         }
         top -= 1;
         sum_arr -= harr;
-        running += 1; started += 1; events += 1;
+        running += 1; started += 1;
         busy_gpus += hg;
         mem_busy += memc;
         head = -1; head_valid = false;
@@ -339,23 +410,26 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
     // ---------------- D/E. time advances; release jobs whose finish tick is now
     const int now = delta + 1;
     {
-      int slot = now & wmask;
-      int h = wh[slot];
+      const int sl = now & wmask;
+      int h = gwh[sl];
       if (h >= 0) {
-        if (lane == 0) { wh[slot] = -1; wt[slot] = -1; }
+        __syncwarp();
+        if (lane == 0) { gwh[sl] = -1; gwt[sl] = -1; }
         while (h >= 0) {
-          JobState js = jst[h];
+          JobState js;
+          if (h == com_j) js = com_js;
+          else js = jst[h];
           const int scnt = JS_CNT(js.cnt_gpc), sgpc = JS_GPC(js.cnt_gpc);
           if (scnt == 1) {
             if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] -= (sgpc == 1 ? js.gpus : js.gpus / sgpc); }
           } else {
             for (int i = lane; i < scnt; i += 32) {
-              gs_span sp = spans[js.node0 + i];
+              const gs_span sp = spans[js.node0 + i];
               busy[sp.node] &= ~sp.devmask; kk[sp.node] -= sp.ntasks;
             }
           }
           if (lane == 0) fin[finished] = h;
-          finished += 1; running -= 1; events += 1;
+          finished += 1; running -= 1;
           busy_gpus -= js.gpus;
           mem_busy -= js.memc;
           h = js.next;
@@ -369,16 +443,17 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
       if (top > 0) {
         // queue is a stack with non-decreasing arrival ticks bottom->top, so the sorted
         // pending list is the stack read top->bottom: median/max are index look-ups
-        int ilo = top - 1 - (top - 1) / 2, ihi = top - 1 - top / 2;
-        int a_lo = stack[ilo].y, a_hi = stack[ihi].y;
+        const int ilo = top - 1 - ((top - 1) >> 1), ihi = top - 1 - (top >> 1);
+        const int a_lo = ilo >= cache_lo ? sstk[ilo & (SCACHE - 1)].y : stack[ilo].y;
+        const int a_hi = ihi >= cache_lo ? sstk[ihi & (SCACHE - 1)].y : stack[ihi].y;
         pmax = now - bottom_arr; mlo = now - a_lo; mhi = now - a_hi;
       }
       if (lane == 0) {
         int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
-        int tg = M * G;
+        const int tg = M * G;
+        const long long ps = (long long)top * now - sum_arr;
         dst[0] = make_int4(now, M - ever, ever, busy_gpus);
         dst[1] = make_int4(tg - busy_gpus, running, top, finished);
-        long long ps = (long long)top * now - sum_arr;
         dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(ps & 0xffffffffLL), (int)(ps >> 32));
         dst[3] = make_int4(pmax, mlo, mhi, 0);
       }
@@ -388,17 +463,16 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
     done = (n - p) + running == 0;      // schedule.py:185 -- the queue is NOT counted (quirk Q4)
   }
 
-  // ---------------- persist
+  // ---------------- persist: node table, wheel window and pending bucket go back to global memory
   __syncwarp();
   for (int i = lane; i < M; i += 32) { S.nbusy[i] = busy[i]; S.nk[i] = kk[i]; }
   if (lane == 0) {
     S.delta = delta; S.p = p; S.top = top; S.running = running; S.finished = finished;
     S.ever = ever; S.busy_gpus = busy_gpus; S.mem_busy = mem_busy; S.sum_arr = sum_arr;
-    S.span_used = span_used; S.events = events; S.evals = evals; S.started = started;
+    S.span_used = span_used; S.events = (long long)p + started + finished; S.evals = evals; S.started = started;
     S.ticks = ticks; S.row_first = row_first; S.done = done ? 1 : 0; S.status = status;
   }
 }
-
 
 // ------------------------------------------------------------------ lane engine
 // One THREAD owns one replica; a warp carries up to 32 unrelated replicas.  This is the
@@ -421,9 +495,7 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
 #define META_IDLE(m) ((int)((m) & 0xffu))
 #define META_EVER 0x100u
 #define META_KFREE(m) ((int)((m) >> 16))
-#define LW 128          // shared-memory wheel window, ticks (power of two)
 #define RING 8          // job-record ring, entries (power of two)
-#define SCACHE 4        // cached stack entries (power of two)
 #define LANE_EXTRA_WORDS (2 * LW + RING * 8 + SCACHE * 2)
 
 template <typename MaskT>
@@ -433,7 +505,7 @@ __global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, lo
   const int sim = blockIdx.x * L + lane;
   const bool in_range = lane < L && sim < nsims;
   SimDev &S = sims[in_range ? sim : 0];
-  const bool alive = in_range && !S.done && S.status == 0;
+  const bool alive = in_range && !S.done && S.status == 0 && S.policy == GS_SCHED_FIFO;
 
   const int M = S.M, G = S.G, K = S.K, n = S.n;
   const int MW = (sizeof(MaskT) == 8) ? 3 : 2;
@@ -798,10 +870,301 @@ __global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, lo
   S.ticks = ticks; S.row_first = row_first; S.done = done ? 1 : 0; S.status = status;
 }
 
-// never-started jobs report start=end=-1, jct=preempt=0 and their input duration
-__global__ void gs_init_rec_kernel(gs_job_rec *rec, const JobIn *jobs, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0; r.duration = jobs[i].dur; rec[i] = r; }
+// ------------------------------------------------------------------ event-driven policies
+// sjf / dlas / dlas-gpu / gittins: restated from the reference's dead Tiresias-style loops
+// (run_sim.py:162-287, 664-947, 949-1203); the decisions taken where
+// that code is undefined are listed in oracle/policy_oracle.c, which this kernel matches
+// bit for bit.  First version: ONE THREAD per replica (a warp carries 32 replicas); every
+// event re-evaluates all runnable jobs (counter update, ordering, emptied-cluster greedy
+// re-admission), exactly as the specification does.  Lists live in global memory.
+__device__ __forceinline__ double git_lookup(const SimDev &S, double a) {
+  const int n = S.git_n;
+  if (n < 2 || a > S.git_data[n - 2]) return 0.0;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (S.git_data[mid] > a) hi = mid; else lo = mid + 1; }
+  return S.git_index[lo];
+}
+
+__device__ __forceinline__ void plist_remove(int *v, int &n, int x) {
+  int w = 0;
+  for (int i = 0; i < n; ++i) { int e = v[i]; if (e != x) v[w++] = e; }
+  n = w;
+}
+
+__device__ bool pol_yarn_place(const SimDev &S, int gpus, int gpc, bool placeable) {
+  if (!placeable) return false;
+  const int M = S.M, G = S.G, tasks = gpus / gpc;
+  int *idle = S.cidle, *kfree = S.ckfree;
+  if (gpus <= G) {
+    for (int nd = 0; nd < M; ++nd)
+      if (idle[nd] >= gpus && kfree[nd] >= tasks) { idle[nd] -= gpus; kfree[nd] -= tasks; return true; }
+    return false;
+  }
+  int cum = 0, last = -1;
+  for (int nd = 0; nd < M; ++nd) {
+    int cap = min(idle[nd] / gpc, kfree[nd]);
+    if (cap <= 0) continue;
+    cum += cap;
+    if (cum >= tasks) { last = nd; break; }
+  }
+  if (last < 0) return false;
+  int rem = tasks;
+  for (int nd = 0; nd <= last; ++nd) {
+    int cap = min(idle[nd] / gpc, kfree[nd]);
+    if (cap <= 0) continue;
+    int take = min(cap, rem);
+    idle[nd] -= take * gpc; kfree[nd] -= take; rem -= take;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, long long max_ticks) {
+  const int sim = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sim >= nsims) return;
+  SimDev &S = sims[sim];
+  if (S.policy == GS_SCHED_FIFO || S.done || S.status != 0) return;
+  const int policy = S.policy, n = S.n, M = S.M, G = S.G, K = S.K;
+  const bool is_dlas = policy == GS_SCHED_DLAS || policy == GS_SCHED_DLAS_GPU;
+  const bool gputime = policy == GS_SCHED_DLAS_GPU || policy == GS_SCHED_GITTINS;
+  const int nq = is_dlas ? S.num_queue : 1;
+  const JobIn *__restrict__ jobs = S.jobs;
+  PJob *pj = S.pj;
+  int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
+  gs_job_rec *rec = S.rec;
+  const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
+  const int total_gpus = M * G;
+  int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, next_job_jump = S.next_job_jump, nfin = S.finished;
+  double next_git = S.next_gittins_unit;
+  long long events = S.events, ticks = S.ticks;
+  const long long row_first = ticks;
+  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+  int status = 0;
+  bool done = false;
+
+  while (budget > 0 && (ticks - row_first) < S.rows_cap) {
+    if (!((n - p) + rn > 0)) { done = true; break; }
+    if (p >= n && end_time == 0x7fffffff) { done = true; break; }     // "cluster is not large enough"
+    const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
+    int event_time; bool has_start = false, has_end = false;
+    if (end_time < start_time) { event_time = end_time; has_end = true; }
+    else if (end_time > start_time) { event_time = start_time; has_start = true; }
+    else { event_time = start_time; has_start = has_end = true; }
+    if (is_dlas && event_time > next_job_jump) { event_time = next_job_jump; has_start = has_end = false; }
+    if (policy == GS_SCHED_GITTINS && (double)event_time > next_git) { event_time = (int)next_git; has_start = has_end = false; }
+    if (has_end) {
+      for (int i = 0; i < en; ++i) {
+        const int j = endj[i];
+        PJob &r = pj[j];
+        r.status = PST_END;
+        gs_job_rec o; o.start = r.start; o.end = event_time;
+        double cl = ceil(jobs[j].dur); o.jct = cl < 1.0 ? 1 : (int)cl; o.preempt = r.resume; o.duration = jobs[j].dur;
+        rec[j] = o;
+        S.fin[nfin++] = j; ++events;
+        plist_remove(runnable, rn, j);
+        plist_remove(S.queues + (size_t)r.q_id * n, S.qn[r.q_id], j);
+      }
+    }
+    if (has_start) {
+      while (p < n && jobs[p].arrive == event_time) {
+        const int j = p++;
+        PJob r; r.last_check = event_time; r.total_exec = 0; r.exec = 0; r.pending = 0; r.last_pending = 0; r.start = -1;
+        r.resume = 0; r.status = PST_PENDING; r.q_id = 0; r.pad0 = 0; r.pad1 = 0;
+        pj[j] = r;
+        runnable[rn++] = j; S.queues[S.qn[0]++] = j; ++events;
+      }
+    }
+    for (int i = 0; i < rn; ++i) {
+      const int j = runnable[i];
+      PJob &r = pj[j];
+      const int dt = event_time - r.last_check;
+      r.last_check = event_time;
+      if (r.status == PST_RUNNING) {
+        r.total_exec += dt; r.exec += dt;
+        if (is_dlas) {
+          const double j_gt = gputime ? (double)r.exec * jobs[j].gpus : (double)r.exec;
+          if (r.q_id < nq - 1 && j_gt >= S.queue_limit[r.q_id]) {
+            plist_remove(S.queues + (size_t)r.q_id * n, S.qn[r.q_id], j);
+            r.q_id += 1;
+            S.queues[(size_t)r.q_id * n + S.qn[r.q_id]++] = j;
+          }
+        }
+      } else {
+        r.pending += dt;
+        if (r.exec > 0) r.last_pending += dt;
+      }
+    }
+    // ---- order, empty the cluster, greedy re-admission
+    int nrun = 0, npre = 0, busy = 0;
+    long long mem_busy = 0;
+    int *run_jobs = tmpl, *pre_jobs = tmpl + (n > 0 ? n - 1 : 0);
+    if (policy == GS_SCHED_SJF) {
+      for (int i = 1; i < rn; ++i) {          // stable insertion sort by num_gpu (list is nearly sorted)
+        const int x = runnable[i]; const int kx = jobs[x].gpus; int k = i;
+        while (k > 0 && jobs[runnable[k - 1]].gpus > kx) { runnable[k] = runnable[k - 1]; --k; }
+        runnable[k] = x;
+      }
+      for (int nd = 0; nd < M; ++nd) { S.cidle[nd] = G; S.ckfree[nd] = K; }
+      for (int i = 0; i < rn; ++i) {
+        const int j = runnable[i];
+        const JobIn jr = jobs[j];
+        PJob &r = pj[j];
+        if (pol_yarn_place(S, jr.gpus, jr.gpc, jr.memb < fit_limit)) {
+          if (r.start < 0) r.start = event_time;
+          if (r.status == PST_PENDING) run_jobs[nrun++] = j;
+          busy += jr.gpus; mem_busy += (long long)jr.gpus * (jr.memb < cap_bytes ? jr.memb : cap_bytes);
+        } else if (r.status == PST_RUNNING) { pre_jobs[-(npre++)] = j; }
+      }
+    } else {
+      if (policy == GS_SCHED_GITTINS) {       // stable insertion sort by rank, ascending
+        double *rk = reinterpret_cast<double *>(S.queues);     // gittins has no queues: reuse as rank scratch
+        for (int i = 0; i < rn; ++i) {
+          const int j = runnable[i]; const PJob &r = pj[j];
+          rk[i] = git_lookup(S, r.status == PST_RUNNING ? (double)r.exec * jobs[j].gpus : (double)r.exec);
+        }
+        for (int i = 1; i < rn; ++i) {
+          const int x = runnable[i]; const double kx = rk[i]; int k = i;
+          while (k > 0 && rk[k - 1] > kx) { runnable[k] = runnable[k - 1]; rk[k] = rk[k - 1]; --k; }
+          runnable[k] = x; rk[k] = kx;
+        }
+      }
+      int free_gpu = total_gpus;
+      const int nlists = policy == GS_SCHED_GITTINS ? 1 : nq;
+      for (int q = 0; q < nlists; ++q) {
+        const int *lst = policy == GS_SCHED_GITTINS ? runnable : S.queues + (size_t)q * n;
+        const int ln = policy == GS_SCHED_GITTINS ? rn : S.qn[q];
+        for (int i = 0; i < ln; ++i) {
+          const int j = lst[i];
+          const JobIn jr = jobs[j];
+          PJob &r = pj[j];
+          if (free_gpu >= jr.gpus) {
+            if (r.status == PST_PENDING) run_jobs[nrun++] = j;
+            free_gpu -= jr.gpus;
+            busy += jr.gpus; mem_busy += (long long)jr.gpus * (jr.memb < cap_bytes ? jr.memb : cap_bytes);
+          } else if (r.status == PST_RUNNING) { pre_jobs[-(npre++)] = j; }
+        }
+      }
+    }
+    for (int i = 0; i < npre; ++i) { pj[pre_jobs[-i]].status = PST_PENDING; ++events; }
+    for (int i = 0; i < nrun; ++i) {
+      PJob &r = pj[run_jobs[i]];
+      r.status = PST_RUNNING; r.resume += 1; ++events;
+      if (r.start < 0) r.start = event_time;
+    }
+    if (is_dlas) {
+      for (int q = 0; q < nq; ++q) {
+        int *qv = S.queues + (size_t)q * n;
+        int w = 0, pn = 0;
+        for (int i = 0; i < S.qn[q]; ++i) { const int j = qv[i]; if (pj[j].status == PST_PENDING) tmpl[pn++] = j; else qv[w++] = j; }
+        for (int i = 0; i < pn; ++i) qv[w++] = tmpl[i];
+      }
+    }
+    end_time = 0x7fffffff; en = 0;
+    next_job_jump = 0x7fffffff;
+    int running = 0, queued = 0, pmax = 0;
+    long long psum = 0;
+    for (int i = 0; i < rn; ++i) {
+      const int j = runnable[i];
+      const PJob r = pj[j];
+      if (r.status != PST_RUNNING) { ++queued; psum += r.pending; pmax = max(pmax, r.pending); continue; }
+      ++running;
+      const JobIn jr = jobs[j];
+      double cl = ceil(jr.dur);
+      const int D = cl < 1.0 ? 1 : (int)cl;
+      const int e = event_time + (D - r.total_exec);
+      if (e < end_time) { end_time = e; en = 0; endj[en++] = j; }
+      else if (e == end_time) endj[en++] = j;
+      if (is_dlas && r.q_id < nq - 1) {
+        const double lim = S.queue_limit[r.q_id];
+        const double jt = gputime ? ceil((lim - (double)r.exec) / (double)jr.gpus) + event_time : lim - (double)r.exec + event_time;
+        int jti = jt > 2.0e9 ? 0x7fffffff : (int)jt;
+        if (jti <= event_time) jti = event_time + 1;
+        next_job_jump = min(next_job_jump, jti);
+      }
+    }
+    if (policy == GS_SCHED_GITTINS) next_git += (double)event_time;
+    {
+      int busy_nodes = 0;
+      if (policy == GS_SCHED_SJF) for (int nd = 0; nd < M; ++nd) busy_nodes += (S.cidle[nd] < G);
+      int4 *dst = reinterpret_cast<int4 *>(&S.rows[ticks - row_first]);
+      dst[0] = make_int4(event_time, M - busy_nodes, busy_nodes, busy);
+      dst[1] = make_int4(total_gpus - busy, running, queued, nfin);
+      dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(psum & 0xffffffffLL), (int)(psum >> 32));
+      dst[3] = make_int4(pmax, 0, 0, 0);
+    }
+    ticks += 1; budget -= 1;
+  }
+  if (!done && !((n - p) + rn > 0)) done = true;
+  if (!done && p >= n && end_time == 0x7fffffff) done = true;
+  if (done) {   // jobs that started but never completed keep their start and restart count
+    for (int j = 0; j < n; ++j) { const PJob r = pj[j]; if (r.status != PST_END && r.status != PST_NONE && r.start >= 0) { rec[j].start = r.start; rec[j].preempt = r.resume; } }
+  }
+  S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.next_job_jump = next_job_jump; S.finished = nfin;
+  S.next_gittins_unit = next_git; S.events = events; S.ticks = ticks; S.row_first = row_first;
+  S.done = done ? 1 : 0; S.status = status; S.running = 0; S.top = 0; S.started = 0;
+}
+
+// One launch (re)initialises every replica flagged need_init: job records (never-started jobs
+// report start=end=-1, jct=preempt=0 and their input duration), empty wheel, idle node table.
+__global__ void gs_init_kernel(SimDev *sims, int nsims) {
+  const int sim = blockIdx.y;
+  if (sim >= nsims) return;
+  const SimDev &S = sims[sim];
+  if (!S.need_init) return;
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < S.n; i += stride) {
+    gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0; r.duration = S.jobs[i].dur;
+    S.rec[i] = r;
+  }
+  for (int i = t0; i <= S.wheel_mask; i += stride) { S.wheel_head[i] = -1; S.wheel_tail[i] = -1; }
+  for (int i = t0; i < S.M; i += stride) { S.nbusy[i] = 0ull; S.nk[i] = 0; }
+  for (int i = t0; i < S.n; i += stride) S.sref[i] = make_int2(0, 0);
+  if (S.policy != GS_SCHED_FIFO)
+    for (int i = t0; i < S.n; i += stride) { PJob z; memset(&z, 0, sizeof(z)); z.start = -1; S.pj[i] = z; }
+}
+
+// ------------------------------------------------------------------ result regrouping
+// Spans are pooled in START order while the simulation runs; callers want them grouped by
+// job (CSR).  One block scans the per-job span counts, a second kernel gathers.
+__global__ void __launch_bounds__(1024) gs_span_scan_kernel(const gs_job_rec *__restrict__ rec, const int2 *__restrict__ sref,
+                                                            int n, long long *__restrict__ off) {
+  __shared__ long long warp_sum[32], warp_excl[32];
+  __shared__ long long carry_s, tile_tot;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int j = base + tid;
+    const long long v = (j < n && rec[j].start >= 0) ? (long long)sref[j].y : 0;
+    long long incl = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const long long w = warp_sum[lane];
+      long long wi = w;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+      warp_excl[lane] = wi - w;
+      if (lane == 31) tile_tot = wi;
+    }
+    __syncthreads();
+    if (j < n) off[j] = carry_s + warp_excl[wid] + incl - v;
+    __syncthreads();
+    if (tid == 0) carry_s += tile_tot;
+    __syncthreads();
+  }
+  if (tid == 0) off[n] = carry_s;
+}
+
+__global__ void gs_span_gather_kernel(const gs_job_rec *__restrict__ rec, const int2 *__restrict__ sref,
+                                      const gs_span *__restrict__ pool, const long long *__restrict__ off, int n,
+                                      gs_span *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || rec[j].start < 0) return;
+  const int2 sr = sref[j];
+  const long long o = off[j];
+  for (int i = 0; i < sr.y; ++i) out[o + i] = pool[sr.x + i];
 }
 
 // ------------------------------------------------------------------ stateless candidate scoring
@@ -925,6 +1288,7 @@ struct SimHost {
   int64_t n = 0;
   void *trace_slab = nullptr;
   void *state_slab = nullptr;
+  void *git_dev = nullptr;
   size_t trace_bytes = 0, state_bytes = 0;
   int64_t span_cap = 0, rows_cap = 0, last_arrive = 0;
   int max_need = 1;
@@ -997,7 +1361,7 @@ extern "C" int gs_create(int device, int nsims, gs_handle *out) {
 extern "C" void gs_destroy(gs_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  for (auto &s : h->sims) { if (s.trace_slab) cudaFree(s.trace_slab); if (s.state_slab) cudaFree(s.state_slab); }
+  for (auto &s : h->sims) { if (s.trace_slab) cudaFree(s.trace_slab); if (s.state_slab) cudaFree(s.state_slab); if (s.git_dev) cudaFree(s.git_dev); }
   if (h->d_sims) cudaFree(h->d_sims);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->d_scratch) cudaFree(h->d_scratch);
@@ -1029,8 +1393,25 @@ extern "C" int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, co
   if (s.prepared) return fail(h, GS_ERR_STATE, "gs_config_sim: replica already running");
   s.cl = *cluster;
   if (policy) s.pol = *policy; else { memset(&s.pol, 0, sizeof(s.pol)); s.pol.num_queue = 1; }
-  if (s.pol.schedule != GS_SCHED_FIFO || s.pol.scheme != GS_SCHEME_YARN)
-    return fail(h, GS_ERR_ARG, "gs_config_sim: only schedule=fifo, scheme=yarn are implemented in this build");
+  if (s.pol.schedule < GS_SCHED_FIFO || s.pol.schedule > GS_SCHED_GITTINS)
+    return fail(h, GS_ERR_ARG, "gs_config_sim: unknown schedule");
+  if (s.pol.scheme != GS_SCHEME_YARN && s.pol.scheme != GS_SCHEME_COUNT)
+    return fail(h, GS_ERR_ARG, "gs_config_sim: unknown scheme");
+  if (s.pol.schedule == GS_SCHED_FIFO && s.pol.scheme != GS_SCHEME_YARN)
+    return fail(h, GS_ERR_ARG, "gs_config_sim: fifo runs with the yarn scheme only");
+  if ((s.pol.schedule == GS_SCHED_DLAS || s.pol.schedule == GS_SCHED_DLAS_GPU) &&
+      (s.pol.num_queue < 1 || s.pol.num_queue > GS_MAX_QUEUES))
+    return fail(h, GS_ERR_ARG, "gs_config_sim: num_queue must be in 1..8 for dlas");
+  if (s.git_dev) { cudaFree(s.git_dev); s.git_dev = nullptr; }
+  if (s.pol.schedule == GS_SCHED_GITTINS) {
+    if (s.pol.gittins_n < 1 || !s.pol.gittins_data || !s.pol.gittins_index)
+      return fail(h, GS_ERR_ARG, "gs_config_sim: gittins needs the (data, index) tables");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = 8 * (size_t)s.pol.gittins_n;
+    CU(cudaMalloc(&s.git_dev, 2 * bytes));
+    CU(cudaMemcpy(s.git_dev, s.pol.gittins_data, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((unsigned char *)s.git_dev + bytes, s.pol.gittins_index, bytes, cudaMemcpyHostToDevice));
+  }
   s.configured = true;
   return GS_OK;
 }
@@ -1127,13 +1508,17 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   size_t o_spans = align_up(o_wt + 4 * (size_t)W), o_rows = align_up(o_spans + sizeof(gs_span) * (size_t)s.span_cap);
   size_t o_nb = align_up(o_rows + sizeof(gs_tick_row) * (size_t)rows_cap), o_nk = align_up(o_nb + 8 * (size_t)M);
   size_t total = align_up(o_nk + 4 * (size_t)M);
+  const bool evd = s.pol.schedule != GS_SCHED_FIFO;        // event-driven policy: extra scratch
+  const size_t nql = (size_t)(s.pol.num_queue > 2 ? s.pol.num_queue : 2);
+  size_t o_pj = total, o_run = 0, o_q = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0;
+  if (evd) {
+    o_run = align_up(o_pj + sizeof(PJob) * N); o_q = align_up(o_run + 4 * N); o_end = align_up(o_q + 4 * N * nql);
+    o_tmp = align_up(o_end + 4 * N); o_ci = align_up(o_tmp + 4 * N); o_ck = align_up(o_ci + 4 * (size_t)M);
+    total = align_up(o_ck + 4 * (size_t)M);
+  }
   if (s.state_slab && s.state_bytes < total) { cudaFree(s.state_slab); s.state_slab = nullptr; }
   if (!s.state_slab) { CU(cudaMalloc(&s.state_slab, total)); s.state_bytes = total; }
   unsigned char *d = (unsigned char *)s.state_slab;
-  CU(cudaMemsetAsync(d + o_wh, 0xFF, 4 * (size_t)W, h->stream));
-  CU(cudaMemsetAsync(d + o_wt, 0xFF, 4 * (size_t)W, h->stream));
-  CU(cudaMemsetAsync(d + o_nb, 0, 8 * (size_t)M, h->stream));
-  CU(cudaMemsetAsync(d + o_nk, 0, 4 * (size_t)M, h->stream));
   SimDev &D = s.dev;
   D.M = M; D.G = c.num_gpu_p_node;
   int kc = c.num_cpu_p_node / c.cpu_per_task, km = c.mem_p_node / c.mem_per_task;
@@ -1150,13 +1535,20 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
   D.span_cap = s.span_cap; D.rows_cap = rows_cap;
   s.rows_cap = rows_cap;
+  if (evd) {
+    D.pj = (PJob *)(d + o_pj); D.runnable = (int *)(d + o_run); D.queues = (int *)(d + o_q);
+    D.endj = (int *)(d + o_end); D.tmpl = (int *)(d + o_tmp); D.cidle = (int *)(d + o_ci); D.ckfree = (int *)(d + o_ck);
+    D.num_queue = s.pol.num_queue > 0 ? s.pol.num_queue : 1;
+    for (int q = 0; q < GS_MAX_QUEUES; ++q) { D.queue_limit[q] = s.pol.queue_limit[q]; D.qn[q] = 0; }
+    D.gittins_delta = s.pol.gittins_delta; D.next_gittins_unit = s.pol.gittins_delta;
+    D.git_n = s.pol.schedule == GS_SCHED_GITTINS ? s.pol.gittins_n : 0;
+    D.git_data = (const double *)s.git_dev;
+    D.git_index = s.git_dev ? (const double *)((unsigned char *)s.git_dev + 8 * (size_t)s.pol.gittins_n) : nullptr;
+    D.rn = 0; D.en = 0; D.end_time = 0x7fffffff; D.next_job_jump = 0x7fffffff;
+  }
   D.delta = D.p = D.top = D.running = D.finished = D.ever = D.busy_gpus = D.done = D.status = 0;
   D.mem_busy = D.sum_arr = D.span_used = D.events = D.evals = D.started = D.ticks = D.row_first = 0;
-  if (s.n > 0) {
-    gs_init_rec_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(D.rec, D.jobs, (int)s.n);
-    h->launches += 1;
-  }
-  CU(cudaGetLastError());
+  D.need_init = 1;
   s.prepared = true;
   return GS_OK;
 }
@@ -1171,17 +1563,23 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
     int M = s.cl.num_switch * s.cl.num_node_p_switch;
     if (M > maxM) maxM = M;
   }
+  bool any_init = false;
   if (h->dirty) {
     std::vector<SimDev> tmp((size_t)h->nsims);
-    for (int i = 0; i < h->nsims; ++i) tmp[(size_t)i] = h->sims[(size_t)i].dev;
+    for (int i = 0; i < h->nsims; ++i) { tmp[(size_t)i] = h->sims[(size_t)i].dev; any_init |= tmp[(size_t)i].need_init != 0; }
     CU(cudaMemcpyAsync(h->d_sims, tmp.data(), sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->dirty = false;
   }
   int maxG = 1;
-  for (auto &s : h->sims) if (s.cl.num_gpu_p_node > maxG) maxG = s.cl.num_gpu_p_node;
+  bool any_fifo = false, any_evd = false;
+  for (auto &s : h->sims) {
+    if (s.cl.num_gpu_p_node > maxG) maxG = s.cl.num_gpu_p_node;
+    if (s.pol.schedule == GS_SCHED_FIFO) any_fifo = true; else any_evd = true;
+  }
   const size_t lane_words = (size_t)maxM * (maxG > 32 ? 3 : 2) + LANE_EXTRA_WORDS;
   int L = 32;
+  if (const char *e = getenv("GSCHED_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) L = v; }
   while (L > 1 && lane_words * (size_t)L * 4 > 100 * 1024) L >>= 1;
   const size_t lane_smem = lane_words * (size_t)L * 4;
   bool use_lane = h->engine_mode == 2;   // auto == warp mapping (measured faster at every replica count that fits HBM)
@@ -1190,7 +1588,19 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
     use_lane = false;
   }
   CU(cudaEventRecord(h->e0, h->stream));
-  if (use_lane) {
+  if (any_init) {      // state reset is part of the timed engine work
+    gs_init_kernel<<<dim3(16, (unsigned)h->nsims), 256, 0, h->stream>>>(h->d_sims, h->nsims);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (any_evd) {
+    gs_policy_kernel<<<(unsigned)((h->nsims + 31) / 32), 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (!any_fifo) {
+    // nothing for the tick kernels
+  } else if (use_lane) {
     const unsigned grid = (unsigned)((h->nsims + L - 1) / L);
     if (maxG > 32) {
       if (lane_smem > 48 * 1024)
@@ -1202,14 +1612,14 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
       gs_lane_kernel<uint32_t><<<grid, 32, lane_smem, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, maxM, L);
     }
   } else {
-    const int stride = (int)align_up((size_t)maxM * 12, 16);
+    const int stride = (int)align_up((size_t)maxM * 12 + 8 + SCACHE * 8, 16);
     if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
     if (stride > 48 * 1024)
       CU(cudaFuncSetAttribute(gs_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
     gs_tick_kernel<<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
   }
   CU(cudaGetLastError());
-  h->launches += 1;
+  if (any_fifo) h->launches += 1;
   CU(cudaEventRecord(h->e1, h->stream));
   std::vector<SimDev> back((size_t)h->nsims);
   CU(cudaMemcpyAsync(back.data(), h->d_sims, sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyDeviceToHost, h->stream));
@@ -1218,6 +1628,7 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
   h->kernel_ms += ms;
   int worst = 0;
   for (int i = 0; i < h->nsims; ++i) {
+    back[(size_t)i].need_init = 0;
     h->sims[(size_t)i].dev = back[(size_t)i];
     if (back[(size_t)i].status != 0 && worst == 0) worst = back[(size_t)i].status;
   }
@@ -1267,11 +1678,25 @@ extern "C" int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out, int32_t
   SimHost &s = h->sims[(size_t)sim];
   if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_jobs: nothing has run yet");
   CU(cudaSetDevice(h->device));
-  int rc = GS_OK;
-  if (jobs_out && s.n > 0) rc = timed_d2h(h, jobs_out, s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n);
-  if (rc == GS_OK && finish_order_out && s.dev.finished > 0)
-    rc = timed_d2h(h, finish_order_out, s.dev.fin, 4 * (size_t)s.dev.finished);
-  return rc;
+  CU(cudaEventRecord(h->e0, h->stream));
+  if (jobs_out && s.n > 0)
+    CU(cudaMemcpyAsync(jobs_out, s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
+  if (finish_order_out && s.dev.finished > 0)
+    CU(cudaMemcpyAsync(finish_order_out, s.dev.fin, 4 * (size_t)s.dev.finished, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->d2h_ms += ms;
+  return GS_OK;
+}
+
+static int ensure_scratch(gs_handle h, size_t bytes) {
+  if (h->d_scratch_bytes >= bytes) return GS_OK;
+  if (h->d_scratch) cudaFree(h->d_scratch);
+  h->d_scratch = nullptr; h->d_scratch_bytes = 0;
+  CU(cudaMalloc(&h->d_scratch, bytes));
+  h->d_scratch_bytes = bytes;
+  return GS_OK;
 }
 
 extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_span *spans_out, int64_t spans_cap,
@@ -1284,36 +1709,27 @@ extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_sp
   const int64_t used = s.dev.span_used;
   if (spans_used) *spans_used = used;
   if (!spans_out && !span_off_out) return GS_OK;
-  // spans are pooled in start order on the device; hand them back grouped by job (CSR)
-  std::vector<int2> sref((size_t)(s.n > 0 ? s.n : 1));
-  std::vector<gs_job_rec> rec((size_t)(s.n > 0 ? s.n : 1));
-  std::vector<gs_span> pool((size_t)(used > 0 ? used : 1));
-  int rc = GS_OK;
-  if (s.n > 0) rc = timed_d2h(h, sref.data(), s.dev.sref, sizeof(int2) * (size_t)s.n);
-  if (rc == GS_OK && s.n > 0) rc = timed_d2h(h, rec.data(), s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n);
-  if (rc == GS_OK && used > 0) rc = timed_d2h(h, pool.data(), s.dev.spans, sizeof(gs_span) * (size_t)used);
+  if (spans_out && spans_cap < used) return fail(h, GS_ERR_CAPACITY, "gs_fetch_spans: spans_out too small");
+  const size_t N = (size_t)(s.n > 0 ? s.n : 1);
+  const size_t o_off = 0, o_sp = align_up(8 * (N + 1)), total = align_up(o_sp + sizeof(gs_span) * (size_t)(used > 0 ? used : 1));
+  int rc = ensure_scratch(h, total);
   if (rc) return rc;
-  int64_t w = 0;
-  for (int64_t j = 0; j < s.n; ++j) {
-    if (span_off_out) span_off_out[j] = w;
-    if (rec[(size_t)j].start < 0) continue;
-    const int2 sr = sref[(size_t)j];
-    if (spans_out) {
-      if (w + sr.y > spans_cap) return fail(h, GS_ERR_CAPACITY, "gs_fetch_spans: spans_out too small");
-      memcpy(spans_out + w, pool.data() + sr.x, sizeof(gs_span) * (size_t)sr.y);
-    }
-    w += sr.y;
-  }
-  if (span_off_out) span_off_out[s.n] = w;
-  return GS_OK;
-}
-
-static int ensure_scratch(gs_handle h, size_t bytes) {
-  if (h->d_scratch_bytes >= bytes) return GS_OK;
-  if (h->d_scratch) cudaFree(h->d_scratch);
-  h->d_scratch = nullptr; h->d_scratch_bytes = 0;
-  CU(cudaMalloc(&h->d_scratch, bytes));
-  h->d_scratch_bytes = bytes;
+  unsigned char *d = (unsigned char *)h->d_scratch;
+  long long *d_off = (long long *)(d + o_off);
+  gs_span *d_sp = (gs_span *)(d + o_sp);
+  CU(cudaEventRecord(h->e0, h->stream));
+  gs_span_scan_kernel<<<1, 1024, 0, h->stream>>>(s.dev.rec, s.dev.sref, (int)s.n, d_off);
+  if (s.n > 0 && used > 0 && spans_out)
+    gs_span_gather_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(s.dev.rec, s.dev.sref, s.dev.spans, d_off,
+                                                                              (int)s.n, d_sp);
+  CU(cudaGetLastError());
+  h->launches += 2;
+  if (span_off_out) CU(cudaMemcpyAsync(span_off_out, d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, h->stream));
+  if (spans_out && used > 0) CU(cudaMemcpyAsync(spans_out, d_sp, sizeof(gs_span) * (size_t)used, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->d2h_ms += ms;
   return GS_OK;
 }
 

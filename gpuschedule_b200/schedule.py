@@ -7,7 +7,7 @@ from __future__ import annotations
 import logging
 import time
 
-from . import capi, rngcol
+from . import capi, policies, rngcol
 
 
 class Scheduler:
@@ -20,11 +20,24 @@ class Scheduler:
         self.enable_migration = enable_migration
         self.stats = None
 
+    def make_policy(self, table):
+        """gs_policy from the flags (run_sim.py:37-49 names; README.md:57-62 thresholds)."""
+        flags = self.infrastructure.flags
+        kw = {}
+        if self.schedule in ("dlas", "dlas-gpu"):
+            limits = [float(x) for x in str(getattr(flags, "queue_limit", "3600,7200,18000")).split(",") if x]
+            kw = dict(num_queue=max(int(getattr(flags, "num_queue", 1)), 1), queue_limit=limits)
+        elif self.schedule == "gittins":
+            delta = float(getattr(flags, "gittins_delta", 3250.0))
+            kw = dict(gittins_delta=delta,
+                      gittins_table=policies.build_gittins_table(policies.gittins_samples(table), delta))
+        return capi.make_policy(self.schedule, self.placement if self.placement in capi.SCHEMES else "yarn", **kw)
+
     def start(self):
         t0 = time.time()
         infra, table = self.infrastructure, self.jobs_manager.table
         cluster = infra.gs_cluster()
-        policy = capi.make_policy(self.schedule, self.placement, getattr(infra.flags, "num_queue", 1))
+        policy = self.make_policy(table)
         with capi.Engine(device=getattr(infra.flags, "device", 0), nsims=1) as eng:
             eng.config(0, cluster, policy)
             eng.load_trace(0, table)

@@ -22,13 +22,13 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "gsched_oracle.c")
+    srcs = [os.path.join(_HERE, "gsched_oracle.c"), os.path.join(_HERE, "policy_oracle.c")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "gsched.h")
     if (not force and os.path.exists(LIB_PATH)
-            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(x) for x in srcs + [hdr])):
         return LIB_PATH
     subprocess.run(["gcc", "-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-shared",
-                    "-o", LIB_PATH, src, "-lm"], check=True, cwd=_HERE)
+                    "-o", LIB_PATH] + srcs + ["-lm"], check=True, cwd=_HERE)
     return LIB_PATH
 
 
@@ -38,6 +38,7 @@ def lib():
         build()
         _lib = C.CDLL(LIB_PATH)
         _lib.oracle_run_fifo.restype = C.c_int64
+        _lib.oracle_run_policy.restype = C.c_int64
         _lib.oracle_place_one.restype = C.c_int
         _lib.oracle_net_cost.restype = C.c_double
     return _lib
@@ -133,3 +134,29 @@ def net_cost(cluster: GsCluster, task_node, is_ps, ps_count, model_mb, iteration
     return float(lib().oracle_net_cost(C.byref(cluster), C.c_int32(len(task_node)), _p(task_node),
                                        _p(is_ps), C.c_int32(int(ps_count)), C.c_double(float(model_mb)),
                                        C.c_double(float(iterations))))
+
+
+def run_policy(cluster: GsCluster, policy, table, rows_cap=None):
+    """Event-driven policies (sjf / dlas / dlas-gpu / gittins), oracle/policy_oracle.c."""
+    n = table.n
+    if rows_cap is None:
+        rows_cap = 8 * n + 64
+    rows = np.zeros(rows_cap, dtype=ROW_DTYPE)
+    recs = np.zeros(max(n, 1), dtype=JOB_DTYPE)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    nfin = C.c_int64(0)
+    events = C.c_int64(0)
+    arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    a, g, c = arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32)
+    d, m = arr(table.duration, np.float64), arr(table.mem_bytes, np.int64)
+    ticks = lib().oracle_run_policy(C.byref(cluster), C.byref(policy), C.c_int64(n), _p(a), _p(g), _p(c), _p(d), _p(m),
+                                    _p(rows), C.c_int64(rows_cap), _p(recs), _p(order), C.byref(nfin), C.byref(events))
+    if ticks < 0:
+        raise RuntimeError(f"oracle_run_policy failed: {ticks}")
+    r = OracleResult()
+    r.ticks = int(ticks)
+    r.rows = rows[:ticks]
+    r.recs = recs[:n]
+    r.finish_order = order[:nfin.value]
+    r.events = events.value
+    return r

@@ -242,3 +242,27 @@ def test_full_size_properties_100k():
     assert np.array_equal(np.add.reduceat(pc, span_off[:-1]), table.gpus)
     ref = oracle.run_fifo(cluster, table)
     _assert_same(ref, (rows, recs, order, span_off, spans, st), "100k")
+
+
+def test_cli_run_sim_writes_reference_bytes(tmp_path):
+    """run_sim.py end to end: same flags, same files, same bytes as the reference run."""
+    import glob
+    import os
+    import shutil
+    import subprocess
+    import sys
+    from conftest import GOLDEN, REPO
+    case = "n64"
+    shutil.copy(os.path.join(GOLDEN, case, "trace.csv"), tmp_path / "trace.csv")
+    cmd = [sys.executable, os.path.join(REPO, "run_sim.py"), "--num_switch", "4", "--num_node_p_switch", "32",
+           "--num_gpu_p_node", "8", "--scheme", "yarn", "--schedule", "fifo", "--trace_file", "trace.csv",
+           "--log_path", "g", "--enable_network_costs", "False", "--seed", "7"]
+    subprocess.run(cmd, cwd=tmp_path, check=True, capture_output=True)
+    runs = glob.glob(str(tmp_path / "log" / "g" / "*"))
+    assert len(runs) == 1
+    for name in ("job.csv", "cluster.csv"):
+        got = open(os.path.join(runs[0], name), newline="").read()
+        exp = open(os.path.join(GOLDEN, case, name), newline="").read()
+        assert got == exp, name
+    for name in ("cpu.csv", "gpu.csv", "memory.csv", "network.csv", "output.log"):
+        assert os.path.exists(os.path.join(runs[0], name)), name

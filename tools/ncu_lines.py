@@ -15,8 +15,8 @@ import os
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
 repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(repo, "gpuschedule_b200", "libgsched.so")
-src_path = os.path.join(repo, "gpuschedule_b200", "csrc", "gsched.cu")
+so = os.environ.get("NCU_SO", os.path.join(repo, "gpuschedule_b200", "libgsched.so"))
+src_path = os.environ.get("NCU_SRC", os.path.join(repo, "gpuschedule_b200", "csrc", "gsched.cu"))
 src = open(src_path).read().split("\n")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
