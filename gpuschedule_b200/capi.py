@@ -46,6 +46,8 @@ class GsRunStats(C.Structure):
                 ("d2h_ms", C.c_double)]
 
 
+JOBIN_DTYPE = np.dtype([("arrive_tick", "<i4"), ("gpus", "<i4"), ("gpu_per_task", "<i4"), ("ps_count", "<i4"),
+                        ("mem_bytes", "<i8"), ("duration", "<f8")])
 NODE_DTYPE = np.dtype([("busy_mask", "<u8"), ("cpu_used", "<i4"), ("mem_used", "<i4")])
 JOBREQ_DTYPE = np.dtype([("gpus", "<i4"), ("gpu_per_task", "<i4"), ("mem_bytes", "<i8")])
 
@@ -135,6 +137,11 @@ def load_library(path=None):
     lib.gs_config_sim.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsCluster), C.POINTER(GsPolicy)]
     lib.gs_load_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64, i32p, i32p, i32p, f64p, i64p,
                                   f64p, f64p, i32p]
+    lib.gs_load_trace_packed.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, f64p, f64p]
+    lib.gs_load_trace_packed.restype = C.c_int
+    lib.gs_fetch_all.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, i32p, i64p,
+                                 C.c_void_p, C.c_int64, i64p]
+    lib.gs_fetch_all.restype = C.c_int
     lib.gs_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     lib.gs_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsRunStats)]
     lib.gs_fetch_rows.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
@@ -218,6 +225,29 @@ class Engine:
     def set_engine(self, mode):
         """0 auto, 1 warp-per-replica, 2 lane-per-replica."""
         self._check(self.lib.gs_set_engine(self.h, int(mode)), "gs_set_engine")
+
+    def load_trace_packed(self, sim, packed, model_mb=None, iterations=None):
+        """`packed`: JOBIN_DTYPE array (JobTable.packed())."""
+        packed = np.ascontiguousarray(packed, dtype=JOBIN_DTYPE)
+        mm = None if model_mb is None else np.ascontiguousarray(model_mb, dtype=np.float64)
+        it = None if iterations is None else np.ascontiguousarray(iterations, dtype=np.float64)
+        self._n[sim] = len(packed)
+        self._check(self.lib.gs_load_trace_packed(self.h, sim, len(packed), packed.ctypes.data_as(C.c_void_p),
+                                                  _ptr(mm, C.c_double), _ptr(it, C.c_double)), "gs_load_trace_packed")
+
+    def fetch_all(self, sim, rows_out, jobs_out, order_out, off_out, spans_out, first=0, count=None):
+        """One call: rows of the last window, job records, finish order, spans by job (into caller buffers)."""
+        st = self.stats(sim)
+        if count is None:
+            count = st.ticks - first
+        used = C.c_int64(0)
+        self._check(self.lib.gs_fetch_all(self.h, sim, int(first), int(count), rows_out.ctypes.data_as(C.c_void_p),
+                                          jobs_out.ctypes.data_as(C.c_void_p), _ptr(order_out, C.c_int32),
+                                          _ptr(off_out, C.c_int64), spans_out.ctypes.data_as(C.c_void_p),
+                                          len(spans_out), C.byref(used)), "gs_fetch_all")
+        n = self._n[sim]
+        return (rows_out[:int(count)], jobs_out[:n], order_out[:int(st.finished)], off_out[:n + 1],
+                spans_out[:used.value])
 
     def reset(self):
         self._check(self.lib.gs_reset(self.h), "gs_reset")

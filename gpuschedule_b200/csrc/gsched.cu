@@ -113,6 +113,12 @@ __device__ __forceinline__ int lowest_bits(unsigned long long idle, int cnt, uns
   return cnt;
 }
 
+__device__ __forceinline__ int meta_cap(unsigned mt, int gpc) {
+  // tasks a node can still take: min(idle devices / gpus per task, free task slots)
+  const int idle = (int)(mt & 0xffu), kfree = (int)(mt >> 16);
+  return min(gpc == 1 ? idle : idle / gpc, kfree);
+}
+
 __device__ __forceinline__ int node_cap(unsigned long long busy, int k, int G, int K, int gpc) {
   int idle = G - __popcll(busy);
   int slots = K - (int)(k & ~EVER_BIT);
@@ -147,7 +153,7 @@ __device__ __forceinline__ unsigned long long take_lowest(unsigned long long idl
 // needed (pending wheel bucket, release record of the next tick's first finisher) or comes
 // from a register-resident 32-record window of the trace, so the loop body has no dependent
 // DRAM/L2 round trip in the common case.
-__global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
+__global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -179,10 +185,19 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
   const long long row_first = ticks;
   gs_tick_row *rows = S.rows;
   const long long rows_cap = S.rows_cap;
-  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+  long long budget_ll = max_ticks > 0 ? max_ticks : 0x7fffffffLL;
+  if (budget_ll > rows_cap) budget_ll = rows_cap;     // the row window bounds a launch anyway
+  int budget = (int)(budget_ll > 0x7fffffffLL ? 0x7fffffffLL : budget_ll);
+  int4 *rowp = reinterpret_cast<int4 *>(rows);
+  int tick_i = 0;                                     // ticks done in this launch
 
   // ---- stage persistent state: node table, wheel window, queue top
-  for (int i = lane; i < M; i += 32) { busy[i] = S.nbusy[i]; kk[i] = S.nk[i]; }
+  for (int i = lane; i < M; i += 32) {
+    const unsigned long long bz = S.nbusy[i];
+    const unsigned kv = (unsigned)S.nk[i];
+    busy[i] = bz;
+    kk[i] = (int)((unsigned)(G - __popcll(bz)) | ((kv & EVER_BIT) ? 0x100u : 0u) | ((unsigned)(K - (int)(kv & ~EVER_BIT)) << 16));
+  }
   for (int i = max(top - SCACHE, 0) + lane; i < top; i += 32) sstk[i & (SCACHE - 1)] = stack[i];
   int cache_lo = max(top - SCACHE, 0);           // queue entries [cache_lo, top) are cached
   __syncwarp();
@@ -206,8 +221,7 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
 
   bool done = (n == 0);
 
-  while (!done && budget > 0 && status == 0) {
-    if (ticks - row_first >= rows_cap) break;   // row window full: host drains and relaunches
+  while (!done && tick_i < budget && status == 0) {
     // ---------------- A. admit arrivals (gen_jobs + head insert)
     {
       int cnt = 0, q = p;
@@ -219,7 +233,8 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
           // the batch's first job becomes the queue head: take its record out of the window now
           const int src = p - wbase;
           hg = __shfl_sync(FULL, wj.gpus, src); hgpc = __shfl_sync(FULL, wj.gpc, src);
-          hps = __shfl_sync(FULL, wj.ps, src); harr = __shfl_sync(FULL, wj.arrive, src);
+          harr = delta;
+          if (netcost) hps = __shfl_sync(FULL, wj.ps, src);
           hmemb = __shfl_sync(FULL, wj.memb, src);
           hdur = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(wj.dur), src));
         }
@@ -275,13 +290,12 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
           const int nd = base + lane;
           bool fit = false;
           if (nd < M) {
-            const int idle = G - __popcll(busy[nd]);
-            const int slots = K - (int)(kk[nd] & ~EVER_BIT);
-            fit = idle >= hg && slots >= htasks;
+            const unsigned mt = (unsigned)kk[nd];
+            fit = (int)(mt & 0xffu) >= hg && (int)(mt >> 16) >= htasks;
           }
           const unsigned b = __ballot_sync(FULL, fit);
           if (!placeable) {          // quirk Q21: cpu/mem charged for every task, never refunded
-            if (fit) kk[nd] += htasks;
+            if (fit) kk[nd] -= htasks << 16;
             continue;
           }
           if (b) { found = base + __ffs(b) - 1; break; }
@@ -294,9 +308,9 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
             const unsigned long long take = take_lowest(~busy[found] & gmask, hg, G);
             busy[found] |= take;
             const unsigned kv = (unsigned)kk[found];
-            kk[found] = (int)((kv + htasks) | EVER_BIT);
+            kk[found] = (int)((kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u);
             mask0 = take;
-            fresh = !(kv & EVER_BIT);
+            fresh = !(kv & 0x100u);
             gs_span sp; sp.node = found; sp.ntasks = htasks; sp.devmask = take;
             spans[span_first] = sp;
           }
@@ -312,14 +326,14 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         if (placeable) {
           for (int base = 0; base < M; base += 32) {
             const int nd = base + lane;
-            const int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
+            const int c = (nd < M) ? meta_cap((unsigned)kk[nd], hgpc) : 0;
             cum += __reduce_add_sync(FULL, c);
             if (cum >= htasks) { last_base = base; break; }
           }
         } else {
           for (int base = 0; base < M; base += 32) {   // quirk Q21, cross-node flavour: one task charged per node
             const int nd = base + lane;
-            if (nd < M && node_cap(busy[nd], kk[nd], G, K, hgpc) > 0) kk[nd] += 1;
+            if (nd < M && meta_cap((unsigned)kk[nd], hgpc) > 0) kk[nd] -= 1 << 16;
           }
         }
         if (last_base >= 0 && span_used + min(htasks, M) > S.span_cap) { status = GS_ERR_CAPACITY; last_base = -1; }
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
           int rem = htasks, last_node = 0;
           for (int base = 0; base <= last_base; base += 32) {
             const int nd = base + lane;
-            const int c = (nd < M) ? node_cap(busy[nd], kk[nd], G, K, hgpc) : 0;
+            const int c = (nd < M) ? meta_cap((unsigned)kk[nd], hgpc) : 0;
             int incl = c;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
@@ -341,8 +355,8 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
               const unsigned long long tk = take_lowest(~busy[nd] & gmask, take * hgpc, G);
               busy[nd] |= tk;
               const unsigned kv = (unsigned)kk[nd];
-              kk[nd] = (int)((kv + take) | EVER_BIT);
-              fresh = !(kv & EVER_BIT);
+              kk[nd] = (int)((kv - (unsigned)(take * hgpc) - ((unsigned)take << 16)) | 0x100u);
+              fresh = !(kv & 0x100u);
               const int slot = nspans + __popc(tb & ((1u << lane) - 1u));
               gs_span sp; sp.node = nd; sp.ntasks = take; sp.devmask = tk;
               spans[span_first + slot] = sp;
@@ -421,11 +435,11 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
           else js = jst[h];
           const int scnt = JS_CNT(js.cnt_gpc), sgpc = JS_GPC(js.cnt_gpc);
           if (scnt == 1) {
-            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] -= (sgpc == 1 ? js.gpus : js.gpus / sgpc); }
+            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] += js.gpus + ((sgpc == 1 ? js.gpus : js.gpus / sgpc) << 16); }
           } else {
             for (int i = lane; i < scnt; i += 32) {
               const gs_span sp = spans[js.node0 + i];
-              busy[sp.node] &= ~sp.devmask; kk[sp.node] -= sp.ntasks;
+              busy[sp.node] &= ~sp.devmask; kk[sp.node] += sp.ntasks * sgpc + (sp.ntasks << 16);
             }
           }
           if (lane == 0) fin[finished] = h;
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         pmax = now - bottom_arr; mlo = now - a_lo; mhi = now - a_hi;
       }
       if (lane == 0) {
-        int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
+        int4 *dst = rowp;
         const int tg = M * G;
         const long long ps = (long long)top * now - sum_arr;
         dst[0] = make_int4(now, M - ever, ever, busy_gpus);
@@ -458,19 +472,23 @@ __global__ void __launch_bounds__(32) gs_tick_kernel(SimDev *sims, int nsims, lo
         dst[3] = make_int4(pmax, mlo, mhi, 0);
       }
     }
-    ticks += 1; budget -= 1;
+    tick_i += 1; rowp += 4;
     delta = now;
     done = (n - p) + running == 0;      // schedule.py:185 -- the queue is NOT counted (quirk Q4)
   }
 
   // ---------------- persist: node table, wheel window and pending bucket go back to global memory
   __syncwarp();
-  for (int i = lane; i < M; i += 32) { S.nbusy[i] = busy[i]; S.nk[i] = kk[i]; }
+  for (int i = lane; i < M; i += 32) {
+    const unsigned mt = (unsigned)kk[i];
+    S.nbusy[i] = busy[i];
+    S.nk[i] = (int)((unsigned)(K - (int)(mt >> 16)) | ((mt & 0x100u) ? EVER_BIT : 0u));
+  }
   if (lane == 0) {
     S.delta = delta; S.p = p; S.top = top; S.running = running; S.finished = finished;
     S.ever = ever; S.busy_gpus = busy_gpus; S.mem_busy = mem_busy; S.sum_arr = sum_arr;
     S.span_used = span_used; S.events = (long long)p + started + finished; S.evals = evals; S.started = started;
-    S.ticks = ticks; S.row_first = row_first; S.done = done ? 1 : 0; S.status = status;
+    S.ticks = ticks + tick_i; S.row_first = row_first; S.done = done ? 1 : 0; S.status = status;
   }
 }
 
@@ -1127,34 +1145,30 @@ __global__ void gs_init_kernel(SimDev *sims, int nsims) {
 // job (CSR).  One block scans the per-job span counts, a second kernel gathers.
 __global__ void __launch_bounds__(1024) gs_span_scan_kernel(const gs_job_rec *__restrict__ rec, const int2 *__restrict__ sref,
                                                             int n, long long *__restrict__ off) {
-  __shared__ long long warp_sum[32], warp_excl[32];
-  __shared__ long long carry_s, tile_tot;
+  // one block: every thread sums a contiguous chunk, the block scans the 1024 chunk sums,
+  // every thread rewrites its chunk as an exclusive prefix
+  __shared__ long long warp_sum[32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  const int chunk = (n + 1023) / 1024;
+  const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+  long long v = 0;
+  for (int j = lo; j < hi; ++j) v += (rec[j].start >= 0) ? sref[j].y : 0;
+  long long incl = v;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_sum[wid] = incl;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int j = base + tid;
-    const long long v = (j < n && rec[j].start >= 0) ? (long long)sref[j].y : 0;
-    long long incl = v;
+  if (wid == 0) {
+    const long long w = warp_sum[lane];
+    long long wi = w;
     #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) warp_sum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      const long long w = warp_sum[lane];
-      long long wi = w;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
-      warp_excl[lane] = wi - w;
-      if (lane == 31) tile_tot = wi;
-    }
-    __syncthreads();
-    if (j < n) off[j] = carry_s + warp_excl[wid] + incl - v;
-    __syncthreads();
-    if (tid == 0) carry_s += tile_tot;
-    __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+    warp_sum[lane] = wi - w;
   }
-  if (tid == 0) off[n] = carry_s;
+  __syncthreads();
+  long long run = warp_sum[wid] + incl - v;
+  for (int j = lo; j < hi; ++j) { off[j] = run; run += (rec[j].start >= 0) ? sref[j].y : 0; }
+  if (tid == 1023) off[n] = run;
 }
 
 __global__ void gs_span_gather_kernel(const gs_job_rec *__restrict__ rec, const int2 *__restrict__ sref,
@@ -1297,8 +1311,10 @@ struct SimHost {
 
 struct gs_engine {
   int device = 0, nsims = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  void *d_scratch2 = nullptr;
+  size_t d_scratch2_bytes = 0;
   std::vector<SimHost> sims;
   SimDev *d_sims = nullptr;
   void *h_stage = nullptr;
@@ -1347,6 +1363,8 @@ extern "C" int gs_create(int device, int nsims, gs_handle *out) {
   h->nsims = nsims;
   h->sims.resize((size_t)nsims);
   cudaError_t e1 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaError_t e1b = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  (void)e1b;
   cudaError_t e2 = cudaEventCreate(&h->e0);
   cudaError_t e3 = cudaEventCreate(&h->e1);
   cudaError_t e4 = cudaMalloc(&h->d_sims, sizeof(SimDev) * (size_t)nsims);
@@ -1368,6 +1386,8 @@ extern "C" void gs_destroy(gs_handle h) {
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->d_scratch2) cudaFree(h->d_scratch2);
   delete h;
 }
 
@@ -1425,55 +1445,12 @@ static int ensure_stage(gs_handle h, size_t bytes) {
   return GS_OK;
 }
 
-extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arrive_tick, const int32_t *gpus,
-                             const int32_t *gpu_per_task, const double *duration, const int64_t *mem_bytes,
-                             const double *model_mb, const double *iterations, const int32_t *ps_count) {
-  if (!h) return GS_ERR_ARG;
-  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_load_trace: sim index out of range");
-  SimHost &s = h->sims[(size_t)sim];
-  if (!s.configured) return fail(h, GS_ERR_STATE, "gs_load_trace: call gs_config_sim first");
-  if (n < 0 || n >= (1ll << 31) - 64) return fail(h, GS_ERR_ARG, "gs_load_trace: n out of range");
-  if (n > 0 && (!arrive_tick || !gpus || !gpu_per_task || !duration || !mem_bytes))
-    return fail(h, GS_ERR_ARG, "gs_load_trace: NULL column");
-  const bool net = model_mb && iterations && ps_count;
-  const int M = s.cl.num_switch * s.cl.num_node_p_switch;
-  // validate + bounds (host, one pass)
-  int64_t span_cap = 0;
-  double max_need = 1.0;
-  for (int64_t j = 0; j < n; ++j) {
-    if (arrive_tick[j] < 0 || (j > 0 && arrive_tick[j] < arrive_tick[j - 1]))
-      return fail(h, GS_ERR_ARG, "gs_load_trace: arrive_tick must be non-negative and non-decreasing");
-    if (gpu_per_task[j] <= 0 || gpus[j] < gpu_per_task[j] || gpus[j] % gpu_per_task[j] != 0)
-      return fail(h, GS_ERR_ARG, "gs_load_trace: gpus must be a positive multiple of gpu_per_task (job.py:96-100)");
-    if (mem_bytes[j] < 0) return fail(h, GS_ERR_ARG, "gs_load_trace: negative mem_bytes");
-    if (!(duration[j] == duration[j])) return fail(h, GS_ERR_ARG, "gs_load_trace: NaN duration");
-    int64_t tasks = gpus[j] / gpu_per_task[j];
-    span_cap += tasks < M ? tasks : M;
-    double d = duration[j];
-    if (net && s.cl.enable_network_costs && ps_count[j] > 1) {
-      double cross = (double)(tasks < M ? tasks : M);
-      double extra = (model_mb[j] / s.cl.bandwidth + cross * s.cl.internode_latency) * (iterations[j] * 2.0);
-      if (extra > 0) d += extra;
-    }
-    if (d > max_need) max_need = d;
-  }
+// Shared tail of the two loaders: `ji` already holds n validated JobIn records in the pinned
+// staging buffer (plus the optional network columns); bounds are known.
+static int finish_load(gs_handle h, SimHost &s, int64_t n, bool net, size_t off_model, size_t off_iters, size_t total,
+                       int64_t span_cap, double max_need, int64_t last_arrive) {
   if (max_need > (double)(1 << 26)) return fail(h, GS_ERR_ARG, "gs_load_trace: job duration exceeds 2^26 ticks");
-  CU(cudaSetDevice(h->device));
-  const size_t N = (size_t)(n > 0 ? n : 1);
-  size_t off_jobs = 0, off_model = align_up(off_jobs + sizeof(JobIn) * N), off_iters = align_up(off_model + (net ? 8 * N : 0));
-  size_t total = align_up(off_iters + (net ? 8 * N : 0));
-  int rc = ensure_stage(h, total);
-  if (rc) return rc;
   unsigned char *st = (unsigned char *)h->h_stage;
-  JobIn *ji = (JobIn *)(st + off_jobs);
-  for (int64_t j = 0; j < n; ++j) {
-    ji[j].arrive = arrive_tick[j]; ji[j].gpus = gpus[j]; ji[j].gpc = gpu_per_task[j];
-    ji[j].ps = net ? ps_count[j] : 0; ji[j].memb = mem_bytes[j]; ji[j].dur = duration[j];
-  }
-  if (net && n > 0) {
-    memcpy(st + off_model, model_mb, 8 * (size_t)n);
-    memcpy(st + off_iters, iterations, 8 * (size_t)n);
-  }
   if (s.trace_slab && s.trace_bytes < total) { cudaFree(s.trace_slab); s.trace_slab = nullptr; }
   if (!s.trace_slab) { CU(cudaMalloc(&s.trace_slab, total)); s.trace_bytes = total; }
   CU(cudaEventRecord(h->e0, h->stream));
@@ -1485,16 +1462,89 @@ extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arr
   unsigned char *d = (unsigned char *)s.trace_slab;
   SimDev &D = s.dev;
   memset(&D, 0, sizeof(D));
-  D.jobs = (const JobIn *)(d + off_jobs);
+  D.jobs = (const JobIn *)d;
   D.model_mb = net ? (const double *)(d + off_model) : nullptr;
   D.iters = net ? (const double *)(d + off_iters) : nullptr;
   s.n = n; s.span_cap = span_cap > 0 ? span_cap : 1;
   s.max_need = (int)max_need + 2;
-  s.last_arrive = n > 0 ? arrive_tick[n - 1] : 0;
+  s.last_arrive = last_arrive;
   s.loaded = true;
   s.prepared = false;      // (re)loading a trace restarts the replica; slabs are reused when big enough
   h->dirty = true;
   return GS_OK;
+}
+
+static int load_common(gs_handle h, int sim, int64_t n, const JobIn *packed, const int32_t *arrive_tick,
+                       const int32_t *gpus, const int32_t *gpu_per_task, const double *duration,
+                       const int64_t *mem_bytes, const double *model_mb, const double *iterations,
+                       const int32_t *ps_count) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_load_trace: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.configured) return fail(h, GS_ERR_STATE, "gs_load_trace: call gs_config_sim first");
+  if (n < 0 || n >= (1ll << 31) - 64) return fail(h, GS_ERR_ARG, "gs_load_trace: n out of range");
+  if (n > 0 && !packed && (!arrive_tick || !gpus || !gpu_per_task || !duration || !mem_bytes))
+    return fail(h, GS_ERR_ARG, "gs_load_trace: NULL column");
+  const bool net = model_mb && iterations && (packed || ps_count);
+  const int M = s.cl.num_switch * s.cl.num_node_p_switch;
+  CU(cudaSetDevice(h->device));
+  const size_t N = (size_t)(n > 0 ? n : 1);
+  const size_t off_model = align_up(sizeof(JobIn) * N), off_iters = align_up(off_model + (net ? 8 * N : 0));
+  const size_t total = align_up(off_iters + (net ? 8 * N : 0));
+  int rc = ensure_stage(h, total);
+  if (rc) return rc;
+  unsigned char *st = (unsigned char *)h->h_stage;
+  JobIn *ji = (JobIn *)st;
+  if (packed) memcpy(ji, packed, sizeof(JobIn) * (size_t)n);
+  // one pass: (pack,) validate, bounds
+  int64_t span_cap = 0;
+  double max_need = 1.0;
+  int prev = 0;
+  const bool netcost = net && s.cl.enable_network_costs;
+  for (int64_t j = 0; j < n; ++j) {
+    JobIn r;
+    if (packed) r = ji[j];
+    else {
+      r.arrive = arrive_tick[j]; r.gpus = gpus[j]; r.gpc = gpu_per_task[j]; r.ps = net ? ps_count[j] : 0;
+      r.memb = mem_bytes[j]; r.dur = duration[j];
+      ji[j] = r;
+    }
+    if (r.arrive < prev) return fail(h, GS_ERR_ARG, "gs_load_trace: arrive_tick must be non-negative and non-decreasing");
+    prev = r.arrive;
+    if (r.gpc <= 0 || r.gpus < r.gpc || r.gpus % r.gpc != 0)
+      return fail(h, GS_ERR_ARG, "gs_load_trace: gpus must be a positive multiple of gpu_per_task (job.py:96-100)");
+    if (r.memb < 0) return fail(h, GS_ERR_ARG, "gs_load_trace: negative mem_bytes");
+    if (!(r.dur == r.dur)) return fail(h, GS_ERR_ARG, "gs_load_trace: NaN duration");
+    const int64_t tasks = r.gpus / r.gpc;
+    span_cap += tasks < M ? tasks : M;
+    double d = r.dur;
+    if (netcost && r.ps > 1) {
+      const double cross = (double)(tasks < M ? tasks : M);
+      const double extra = (model_mb[j] / s.cl.bandwidth + cross * s.cl.internode_latency) * (iterations[j] * 2.0);
+      if (extra > 0) d += extra;
+    }
+    if (d > max_need) max_need = d;
+  }
+  if (net && n > 0) {
+    memcpy(st + off_model, model_mb, 8 * (size_t)n);
+    memcpy(st + off_iters, iterations, 8 * (size_t)n);
+  }
+  return finish_load(h, s, n, net, off_model, off_iters, total, span_cap, max_need, n > 0 ? ji[n - 1].arrive : 0);
+}
+
+extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arrive_tick, const int32_t *gpus,
+                             const int32_t *gpu_per_task, const double *duration, const int64_t *mem_bytes,
+                             const double *model_mb, const double *iterations, const int32_t *ps_count) {
+  return load_common(h, sim, n, nullptr, arrive_tick, gpus, gpu_per_task, duration, mem_bytes, model_mb, iterations, ps_count);
+}
+
+// Same trace, already packed as 32-byte gs_jobin records (saves the column gather on the host).
+extern "C" int gs_load_trace_packed(gs_handle h, int sim, int64_t n, const gs_jobin *jobs, const double *model_mb,
+                                    const double *iterations) {
+  static_assert(sizeof(gs_jobin) == sizeof(JobIn), "gs_jobin layout");
+  if (n > 0 && !jobs) return fail(h, GS_ERR_ARG, "gs_load_trace_packed: NULL records");
+  return load_common(h, sim, n, reinterpret_cast<const JobIn *>(jobs), nullptr, nullptr, nullptr, nullptr, nullptr,
+                     model_mb, iterations, nullptr);
 }
 
 static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
@@ -1726,6 +1776,56 @@ extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_sp
   h->launches += 2;
   if (span_off_out) CU(cudaMemcpyAsync(span_off_out, d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, h->stream));
   if (spans_out && used > 0) CU(cudaMemcpyAsync(spans_out, d_sp, sizeof(gs_span) * (size_t)used, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->d2h_ms += ms;
+  return GS_OK;
+}
+
+// Everything a caller needs from one finished (or paused) replica in ONE call: the rows of the last
+// window, job records, finish order and the spans grouped by job.  The big row copy runs on the
+// main stream while the regroup kernels and the small copies run on a second stream.
+extern "C" int gs_fetch_all(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out,
+                            gs_job_rec *jobs_out, int32_t *finish_order_out, int64_t *span_off_out,
+                            gs_span *spans_out, int64_t spans_cap, int64_t *spans_used) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_all: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_all: nothing has run yet");
+  const SimDev &D = s.dev;
+  if (rows_out && (count < 0 || first < D.row_first || first + count > D.ticks))
+    return fail(h, GS_ERR_ARG, "gs_fetch_all: row range is outside the last gs_run window");
+  const int64_t used = D.span_used;
+  if (spans_used) *spans_used = used;
+  if (spans_out && spans_cap < used) return fail(h, GS_ERR_CAPACITY, "gs_fetch_all: spans_out too small");
+  CU(cudaSetDevice(h->device));
+  const size_t N = (size_t)(s.n > 0 ? s.n : 1);
+  const size_t o_sp = align_up(8 * (N + 1)), total = align_up(o_sp + sizeof(gs_span) * (size_t)(used > 0 ? used : 1));
+  if (h->d_scratch2_bytes < total) {
+    if (h->d_scratch2) cudaFree(h->d_scratch2);
+    h->d_scratch2 = nullptr; h->d_scratch2_bytes = 0;
+    CU(cudaMalloc(&h->d_scratch2, total));
+    h->d_scratch2_bytes = total;
+  }
+  unsigned char *d = (unsigned char *)h->d_scratch2;
+  long long *d_off = (long long *)d;
+  gs_span *d_sp = (gs_span *)(d + o_sp);
+  CU(cudaEventRecord(h->e0, h->stream));
+  if (rows_out && count > 0)
+    CU(cudaMemcpyAsync(rows_out, D.rows + (first - D.row_first), sizeof(gs_tick_row) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
+  if (span_off_out || spans_out) {
+    gs_span_scan_kernel<<<1, 1024, 0, h->stream2>>>(D.rec, D.sref, (int)s.n, d_off);
+    if (s.n > 0 && used > 0 && spans_out)
+      gs_span_gather_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream2>>>(D.rec, D.sref, D.spans, d_off, (int)s.n, d_sp);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    if (span_off_out) CU(cudaMemcpyAsync(span_off_out, d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, h->stream2));
+    if (spans_out && used > 0) CU(cudaMemcpyAsync(spans_out, d_sp, sizeof(gs_span) * (size_t)used, cudaMemcpyDeviceToHost, h->stream2));
+  }
+  if (jobs_out && s.n > 0) CU(cudaMemcpyAsync(jobs_out, D.rec, sizeof(gs_job_rec) * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream2));
+  if (finish_order_out && D.finished > 0) CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream2));
+  CU(cudaStreamSynchronize(h->stream2));
   CU(cudaEventRecord(h->e1, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);

@@ -48,6 +48,20 @@ class JobTable:
     def tasks(self):
         return self.gpus // self.gpu_per_task
 
+    def packed(self):
+        """The trace as 32-byte gs_jobin records (cached): what gs_load_trace_packed consumes."""
+        if "packed" not in self.extra:
+            from .capi import JOBIN_DTYPE
+            a = np.empty(self.n, dtype=JOBIN_DTYPE)
+            a["arrive_tick"] = self.arrive_tick
+            a["gpus"] = self.gpus
+            a["gpu_per_task"] = self.gpu_per_task
+            a["ps_count"] = 0 if self.ps_count is None else self.ps_count
+            a["mem_bytes"] = self.mem_bytes
+            a["duration"] = self.duration
+            self.extra["packed"] = a
+        return self.extra["packed"]
+
     def task_offsets(self):
         off = np.zeros(self.n + 1, dtype=np.int64)
         np.cumsum(self.tasks, out=off[1:])

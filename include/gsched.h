@@ -144,6 +144,16 @@ typedef struct gs_jobreq {
   int64_t mem_bytes;      /* memory_max                                          */
 } gs_jobreq;
 
+/* One trace row as the device stores it (32 bytes, one DRAM sector).               */
+typedef struct gs_jobin {
+  int32_t arrive_tick;    /* first tick with normalized_time <= tick             */
+  int32_t gpus;
+  int32_t gpu_per_task;
+  int32_t ps_count;       /* 0 when the trace has no network columns             */
+  int64_t mem_bytes;
+  double duration;        /* minutes * scale_factor                              */
+} gs_jobin;
+
 typedef struct gs_engine *gs_handle;
 
 int gs_abi_version(void);
@@ -162,6 +172,10 @@ int gs_load_trace(gs_handle h, int sim, int64_t n,
                   const int32_t *gpu_per_task, const double *duration,
                   const int64_t *mem_bytes, const double *model_mb,
                   const double *iterations, const int32_t *ps_count);
+
+/* The same trace already packed as gs_jobin records (no column gather on the host). */
+int gs_load_trace_packed(gs_handle h, int sim, int64_t n, const gs_jobin *jobs,
+                         const double *model_mb, const double *iterations);
 
 /* Advance every replica by at most max_ticks ticks (<=0: until done).  Row
  * storage on the device is sized by rows_cap per replica at the first call.    */
@@ -191,6 +205,12 @@ int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out /* n */,
                   int32_t *finish_order_out /* n, first `finished` valid */);
 int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out /* n+1 */,
                    gs_span *spans_out, int64_t spans_cap, int64_t *spans_used);
+
+/* All results of one replica in one call (any output may be NULL); rows [first, first+count)
+ * must lie in the last gs_run window.                                           */
+int gs_fetch_all(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out,
+                 gs_job_rec *jobs_out, int32_t *finish_order_out, int64_t *span_off_out,
+                 gs_span *spans_out, int64_t spans_cap, int64_t *spans_used);
 
 /* Stateless candidate scoring: evaluate b jobs against ONE cluster state.
  * first_node[i] = node of a single-node first fit, or the first node of a

@@ -266,3 +266,26 @@ def test_cli_run_sim_writes_reference_bytes(tmp_path):
         assert got == exp, name
     for name in ("cpu.csv", "gpu.csv", "memory.csv", "network.csv", "output.log"):
         assert os.path.exists(os.path.join(runs[0], name)), name
+
+
+def test_packed_loader_and_fetch_all_match_column_api():
+    """gs_load_trace_packed + gs_fetch_all are the same path with fewer host passes / syncs."""
+    from gpuschedule_b200 import capi, ingest, tracegen
+    from gpuschedule_b200.log_manager import JOB_DTYPE, ROW_DTYPE, SPAN_DTYPE
+    cluster = capi.make_cluster(num_switch=2, num_node_p_switch=12)
+    table = ingest.table_from_columns(tracegen.synth_columns(1200, seed=77, rate=0.9))
+    base = _engine_run(cluster, table)[0]
+    with capi.Engine(device=0, nsims=1) as eng:
+        eng.config(0, cluster)
+        eng.load_trace_packed(0, table.packed())
+        eng.run(0, 0)
+        st = eng.stats(0)
+        assert st.done == 1
+        rows = np.empty(st.ticks, dtype=ROW_DTYPE)
+        jobs = np.empty(table.n, dtype=JOB_DTYPE)
+        order = np.empty(table.n, dtype=np.int32)
+        off = np.empty(table.n + 1, dtype=np.int64)
+        spans = np.empty(len(base[4]) + 8, dtype=SPAN_DTYPE)
+        r, j, o, so, sp = eng.fetch_all(0, rows, jobs, order, off, spans)
+    assert r.tobytes() == base[0].tobytes() and j.tobytes() == base[1].tobytes()
+    assert np.array_equal(o, base[2]) and np.array_equal(so, base[3]) and sp.tobytes() == base[4].tobytes()
