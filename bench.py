@@ -158,14 +158,26 @@ def ours(args):
 
     R, n = args.replicas, args.jobs
     cluster = capi.make_cluster(4, 32, 8)
+    from gpuschedule_b200 import policies as gpol
+
+    def policy_for(table):
+        if args.policy == "fifo":
+            return capi.make_policy("fifo")
+        if args.policy == "sjf":
+            return capi.make_policy("sjf")
+        if args.policy in ("dlas", "dlas-gpu"):
+            return capi.make_policy(args.policy, num_queue=4, queue_limit=[3600, 7200, 18000])
+        return capi.make_policy("gittins", gittins_delta=3250.0,
+                                gittins_table=gpol.build_gittins_table(gpol.gittins_samples(table), 3250.0))
     t0 = time.time()
     from gpuschedule_b200 import dist as gdist
     tables = [fast_table(n, sd) for sd in gdist.replica_seeds(rank, world, R, base=BASE_SEED)]
     log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
     eng = capi.Engine(device=local, nsims=R)
     eng.set_engine(args.engine)
+    pols = [policy_for(t) for t in tables]
     for r in range(R):
-        eng.config(r, cluster)
+        eng.config(r, cluster, pols[r])
         eng.load_trace(r, tables[r])
 
     # ---- warm-up (also sizes the per-replica row window so one launch completes a run)
@@ -199,6 +211,32 @@ def ours(args):
     for r in range(min(R, 4)):
         spans_rank += len(eng.fetch_spans(r)[1])
     spans_rank = spans_rank / min(R, 4) * R
+    if args.policy != "fifo":
+        # secondary measurement (event-driven policy kernel): device-timed value only
+        dev_ms = max_over_ranks(dev_ms)
+        events_all = sum_over_ranks(events_rank)
+        if rank == 0:
+            import oracle
+            c0 = time.perf_counter()
+            ref = oracle.run_policy(cluster, pols[0], tables[0])
+            t_cpu = time.perf_counter() - c0
+            assert ref.events == st[0].events and ref.ticks == st[0].ticks, "engine/oracle disagree"
+            print(json.dumps({"metric": METRIC, "value": events_all / (dev_ms / args.steps / 1e3), "unit": UNIT,
+                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                              "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "data": "synthetic", "dtype": "int32/int64",
+                              "config": {"workload": f"{n}-job synthetic trace x {R} replicas/GPU, 4x32x8, {args.policy}",
+                                         "policy": args.policy, "replicas_per_gpu": R, "jobs_per_replica": n,
+                                         "events_per_step": events_all, "rows_per_step": ticks_rank * world},
+                              "kernel": "gs_policy_kernel (thread per replica)", "clocks": clocks,
+                              "gpu_launches": int(launches),
+                              "cpu_baseline": {"value": ref.events / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                                               "sample": "1 replica, oracle/policy_oracle.c (restatement, not reference code)"}}),
+                  flush=True)
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     dev_ms = max_over_ranks(dev_ms)
     wall_ms = max_over_ranks(wall_ms)
     events_all = sum_over_ranks(events_rank)
@@ -210,8 +248,15 @@ def ours(args):
     alg_bytes = R * n * 56 + spans_rank * 16 + ticks_rank * 64
     peak, peak_src = peaks()
     ach = alg_bytes / (dev_ms / args.steps / 1e3) / 1e9
+    traffic = None
+    try:      # DRAM bytes per launch from the committed ncu --set full capture (per replica, scaled to this R)
+        tj = json.load(open(os.path.join(REPO, "profiles", "tick_kernel_traffic.json")))
+        if tj["jobs_per_replica"] == n and args.policy == "fifo" and args.engine in (0, 1):
+            traffic = tj["dram_bytes_per_replica"] * R
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel": "gs_tick_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "gs_tick_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "ticks_per_s": ticks_rank * world / (dev_ms / args.steps / 1e3),
                 "candidate_evals_per_s": evals_rank * world / (dev_ms / args.steps / 1e3)}
@@ -406,6 +451,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],
+                    help="fifo = the headline (pinned) workload; others = secondary, event-driven policy kernel")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 warp per replica, 2 lane per replica")
     args = ap.parse_args()
     if args.impl == "reference":

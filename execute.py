@@ -43,7 +43,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--trace", default=os.path.join("data", "month.csv"))
     ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--batched", action="store_true",
+                    help="run the whole sweep as replicas of one GPU launch (gpuschedule_b200.sweep)")
     a = ap.parse_args()
+    if a.batched:
+        sys.path.insert(0, HERE)
+        from gpuschedule_b200 import sweep
+        return sweep.main(["--trace", a.trace, "--schedule", "fifo", "--repeats", str(a.repeats)])
     schemes = ["yarn"]
     schedules = ["fifo"]
     queues = [1]

@@ -1,0 +1,94 @@
+"""Replica-batched sweeps: what the reference's execute.py runs as N sequential processes
+(/root/reference/execute.py:47-55) becomes ONE engine handle with N replicas advanced by the same
+kernel launches.  Every replica keeps its own flags, trace, policy and output directory, and
+writes the same files a single run_sim.py invocation would."""
+from __future__ import annotations
+
+import argparse
+import datetime
+import os
+import types
+
+import numpy as np
+
+from . import capi, rngcol
+from .infrastructure import Infrastructure
+from .jobs import JobQueueManager, JobsManager
+from .log_manager import LogManager
+from .schedule import Scheduler
+
+DEFAULTS = dict(trace_file="tf_job.csv", log_path="batched", scheme="yarn", schedule="fifo", pack=False,
+                num_switch=1, num_node_p_switch=32, enable_network_costs=False, enable_migration=False,
+                bandwidth=1250, internode_latency=0.015, gpu_memory_capacity=32, num_queue=1, num_buffer=5,
+                num_gpu_p_node=8, num_cpu_p_node=128, mem_p_node=512, cluster_spec=None, device=0,
+                queue_limit="3600,7200,18000", gittins_delta=3250.0, seed=-1)
+
+
+def make_flags(**overrides):
+    """A flags namespace with run_sim.py's defaults (run_sim.py:19-94) plus overrides."""
+    unknown = set(overrides) - set(DEFAULTS)
+    if unknown:
+        raise ValueError(f"unknown flags: {sorted(unknown)}")
+    return types.SimpleNamespace(**{**DEFAULTS, **overrides})
+
+
+def run_batched(flag_sets, device=0, out_root="log"):
+    """Run every configuration of `flag_sets` (list of flags namespaces) as one replica each.
+    Returns [(output_dir, stats)]."""
+    sims = []
+    for fl in flag_sets:
+        infra = Infrastructure(fl)
+        jm = JobsManager(fl, JobQueueManager(fl, fl.trace_file))
+        sched = Scheduler(infra, jm, None)
+        sims.append((fl, infra, jm, sched.make_policy(jm.table)))
+    results = []
+    with capi.Engine(device=device, nsims=len(sims)) as eng:
+        for i, (fl, infra, jm, pol) in enumerate(sims):
+            eng.config(i, infra.gs_cluster(), pol)
+            eng.load_trace(i, jm.table)
+        rows_all = eng.run_all()
+        for i, (fl, infra, jm, pol) in enumerate(sims):
+            recs, order = eng.fetch_jobs(i)
+            span_off, spans = eng.fetch_spans(i)
+            stats = eng.stats(i)
+            stamp = datetime.datetime.now().strftime("%Y-%m-%d-%H-%M-%S-%f")
+            out_dir = os.path.join(out_root, fl.log_path, f"{stamp}-r{i}")
+            os.makedirs(out_dir, exist_ok=True)
+            lm = LogManager(out_dir, fl)
+            lm.init(infra)
+            cl = infra.gs_cluster()
+            m, g = cl.num_switch * cl.num_node_p_switch, cl.num_gpu_p_node
+            if getattr(fl, "seed", -1) >= 0:
+                np.random.seed(fl.seed)
+            util = rngcol.utilization_text(len(rows_all[i]), m, g, jm.table, recs, span_off, spans)
+            lm.write_cluster_rows(rows_all[i], util, m * g * cl.gpu_mem_cap_mib)
+            lm.write_job_rows(jm.table, recs, order)
+            results.append((out_dir, stats))
+    return results
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="run a sweep of simulator configurations as one batched GPU launch")
+    ap.add_argument("--trace", nargs="+", required=True, help="trace CSV file(s)")
+    ap.add_argument("--schedule", nargs="+", default=["fifo"])
+    ap.add_argument("--num_switch", type=int, default=4)
+    ap.add_argument("--num_node_p_switch", type=int, default=32)
+    ap.add_argument("--num_queue", type=int, default=4)
+    ap.add_argument("--repeats", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=-1)
+    a = ap.parse_args(argv)
+    sets = []
+    for tr in a.trace:
+        for sc in a.schedule:
+            for rep in range(a.repeats):
+                tag = os.path.splitext(os.path.basename(tr))[0]
+                sets.append(make_flags(trace_file=tr, schedule=sc, num_switch=a.num_switch,
+                                       num_node_p_switch=a.num_node_p_switch, num_queue=a.num_queue,
+                                       log_path=os.path.join(f"batched_{tag}", f"yarn_{sc}"),
+                                       seed=a.seed if a.seed < 0 else a.seed + rep))
+    for out_dir, st in run_batched(sets):
+        print(f"{out_dir}: ticks={st.ticks} events={st.events} finished={st.finished}")
+
+
+if __name__ == "__main__":
+    main()

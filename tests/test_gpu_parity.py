@@ -289,3 +289,66 @@ def test_packed_loader_and_fetch_all_match_column_api():
         r, j, o, so, sp = eng.fetch_all(0, rows, jobs, order, off, spans)
     assert r.tobytes() == base[0].tobytes() and j.tobytes() == base[1].tobytes()
     assert np.array_equal(o, base[2]) and np.array_equal(so, base[3]) and sp.tobytes() == base[4].tobytes()
+
+
+EDGE = [
+    # (name, cluster kwargs, frame mutation)
+    ("g64_masks", dict(num_switch=1, num_node_p_switch=6, num_gpu_p_node=64, num_cpu_p_node=800, mem_p_node=4000), None),
+    ("never_fits", dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), "huge"),
+    ("single_job", dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8), "one"),
+]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case", EDGE, ids=[c[0] for c in EDGE])
+def test_engine_edge_cases(case, engine):
+    """64-GPU nodes (64-bit device masks), a job larger than the whole cluster (blocks the queue
+    head for ever -> early exit, quirk Q4), and a one-job trace."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    name, ckw, mut = case
+    cluster = capi.make_cluster(**ckw)
+    if name == "g64_masks":
+        cols = tracegen.synth_columns(500, seed=64, rate=0.8, gpu_choices=[1, 8, 48, 64, 128, 200], gpu_probs=[.3, .3, .15, .1, .1, .05])
+    elif mut == "one":
+        cols = tracegen.synth_columns(1, seed=65)
+    else:
+        cols = tracegen.synth_columns(60, seed=66, rate=1.0)
+        cols["used_gpus"][7] = 64                      # 2 nodes x 8 GPUs can never host it
+    table = ingest.table_from_columns(cols)
+    ref = oracle.run_fifo(cluster, table)
+    got = _engine_run(cluster, table, engine=engine)[0]
+    _assert_same(ref, got, name)
+    if mut == "huge":
+        assert got[5].finished < table.n and got[5].done == 1
+
+
+def test_empty_trace_is_rejected_like_the_reference():
+    """No finished job -> the reference asserts in LogManager.jcts (log_manager.py:138)."""
+    from gpuschedule_b200 import capi, ingest, tracegen
+    table = ingest.table_from_columns(tracegen.synth_columns(3, seed=1))
+    table.n = 0
+    for f in ("arrive_tick", "gpus", "gpu_per_task", "duration", "mem_bytes"):
+        setattr(table, f, getattr(table, f)[:0])
+    with capi.Engine(device=0, nsims=1) as eng:
+        eng.config(0, capi.make_cluster(1, 2, 8))
+        eng.load_trace(0, table)
+        eng.run(0, 0)
+        st = eng.stats(0)
+        assert st.done == 1 and st.ticks == 0 and st.finished == 0
+
+
+def test_batched_sweep_writes_reference_bytes(tmp_path):
+    """Several golden cases as replicas of ONE launch; each replica's files equal the reference's."""
+    import os
+    from conftest import GOLDEN
+    from gpuschedule_b200 import sweep
+    cases = [("kat0", dict(num_switch=4, num_node_p_switch=32)), ("n64", dict(num_switch=4, num_node_p_switch=32)),
+             ("sat300", dict(num_switch=1, num_node_p_switch=4)), ("gpc2", dict(num_switch=2, num_node_p_switch=8))]
+    sets = [sweep.make_flags(trace_file=os.path.join(GOLDEN, c, "trace.csv"), log_path=c, seed=7, **kw) for c, kw in cases]
+    res = sweep.run_batched(sets, out_root=str(tmp_path))
+    for (c, _), (out_dir, st) in zip(cases, res):
+        for name in ("job.csv", "cluster.csv"):
+            got = open(os.path.join(out_dir, name), newline="").read()
+            exp = open(os.path.join(GOLDEN, c, name), newline="").read()
+            assert got == exp, (c, name)
