@@ -175,6 +175,8 @@ def ours(args):
     log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
     eng = capi.Engine(device=local, nsims=R)
     eng.set_engine(args.engine)
+    if args.span_budget > 0:
+        eng.set_span_budget(args.span_budget)
     pols = [policy_for(t) for t in tables]
     for r in range(R):
         eng.config(r, cluster, pols[r])
@@ -280,6 +282,8 @@ def ours(args):
             mine = slices[k]
             e = capi.Engine(device=local, nsims=len(mine))
             e.set_engine(args.engine)
+            if args.span_budget > 0:
+                e.set_span_budget(args.span_budget)
             pins = [capi.PinnedBuffer(T * ROW_DTYPE.itemsize), capi.PinnedBuffer(n * JOB_DTYPE.itemsize),
                     capi.PinnedBuffer(n * 4), capi.PinnedBuffer((n + 1) * 8), capi.PinnedBuffer(span_cap * SPAN_DTYPE.itemsize)]
             rows_v, jobs_v = pins[0].view(ROW_DTYPE, T), pins[1].view(JOB_DTYPE, n)
@@ -377,6 +381,41 @@ def ours(args):
         dist.destroy_process_group()
 
 
+def place_mode(args):
+    """Secondary measurement: gs_place_batch, the stateless (job x candidate node) scoring kernel.
+    b job requests against one 128-node cluster state; kernel-only time from the library's CUDA
+    events; algorithmic bytes = 16 B request in + 8 B (first node, nodes used) out per job."""
+    from gpuschedule_b200 import capi
+    rng = np.random.default_rng(5)
+    m, g = 128, 8
+    cluster = capi.make_cluster(4, 32, g)
+    nodes = np.zeros(m, dtype=capi.NODE_DTYPE)
+    for i in range(m):
+        k = int(rng.integers(0, g + 1))
+        nodes["busy_mask"][i] = sum(1 << int(d) for d in rng.choice(g, size=k, replace=False))
+        nodes["cpu_used"][i] = 12 * k
+        nodes["mem_used"][i] = 60 * k
+    b = args.place_jobs
+    jobs = np.zeros(b, dtype=capi.JOBREQ_DTYPE)
+    jobs["gpu_per_task"] = 1
+    jobs["gpus"] = rng.choice([1, 2, 4, 8, 16, 32], size=b, p=[.35, .2, .2, .15, .07, .03])
+    jobs["mem_bytes"] = rng.integers(512, 16384, size=b).astype(np.int64) << 20
+    with capi.Engine(device=0, nsims=1) as eng:
+        best = None
+        for _ in range(args.warmup + args.steps):
+            first, used, _, ms = eng.place_batch(cluster, nodes, jobs)
+            best = ms if best is None else min(best, ms)
+        placed = int((first >= 0).sum())
+    peak, src = peaks()
+    gbs = b * 24 / (best / 1e3) / 1e9
+    print(json.dumps({"metric": "gs_place_batch jobs scored/s (128-node cluster state)", "value": b / (best / 1e3),
+                      "unit": "jobs/s", "kernel_ms": best, "jobs": b, "placeable": placed,
+                      "candidate_evals_per_s": b * m / (best / 1e3),
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                   "algorithmic_bytes_per_launch": b * 24, "peak_source": src,
+                                   "kernel": "gs_place_kernel", "traffic": None}}), flush=True)
+
+
 def reference(args):
     """The reference arm: the CPU port of the reference's loop on all host cores."""
     rank = int(os.environ.get("RANK", 0))
@@ -451,11 +490,17 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--span-budget", type=float, default=0.0,
+                    help="span-pool records per job (0 = worst case); the trace uses ~1.13")
     ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],
                     help="fifo = the headline (pinned) workload; others = secondary, event-driven policy kernel")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 warp per replica, 2 lane per replica")
+    ap.add_argument("--mode", default="sim", choices=["sim", "place"], help="place = gs_place_batch micro-benchmark")
+    ap.add_argument("--place-jobs", type=int, default=64 * 1024 * 1024)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.mode == "place":
+        place_mode(args)
+    elif args.impl == "reference":
         reference(args)
     else:
         ours(args)

@@ -151,6 +151,8 @@ def load_library(path=None):
                                    C.c_void_p, C.c_int64, i32p, i32p, i64p, i32p, f64p]
     lib.gs_net_cost.argtypes = [C.c_void_p, C.POINTER(GsCluster), C.c_int64, i64p, i32p,
                                 C.POINTER(C.c_uint8), i32p, f64p, f64p, f64p]
+    lib.gs_set_span_budget.argtypes = [C.c_void_p, C.c_double]
+    lib.gs_set_span_budget.restype = C.c_int
     lib.gs_reset.argtypes = [C.c_void_p]
     lib.gs_set_engine.argtypes = [C.c_void_p, C.c_int]
     lib.gs_set_engine.restype = C.c_int
@@ -248,6 +250,9 @@ class Engine:
         n = self._n[sim]
         return (rows_out[:int(count)], jobs_out[:n], order_out[:int(st.finished)], off_out[:n + 1],
                 spans_out[:used.value])
+
+    def set_span_budget(self, spans_per_job):
+        self._check(self.lib.gs_set_span_budget(self.h, float(spans_per_job)), "gs_set_span_budget")
 
     def reset(self):
         self._check(self.lib.gs_reset(self.h), "gs_reset")

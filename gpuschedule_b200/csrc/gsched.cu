@@ -42,6 +42,8 @@
 #include "gsched.h"
 
 #define FULL 0xffffffffu
+// ballot over the lanes of one replica group, bit 0 = the group's first lane (needs GM, gbase, SUB in scope)
+#define GBALLOT(pred) ((SUB == 32) ? __ballot_sync(GM, (pred)) : ((__ballot_sync(GM, (pred)) >> gbase) & ((1u << SUB) - 1u)))
 
 // ------------------------------------------------------------------ device state
 
@@ -105,26 +107,10 @@ struct SimDev {
 
 #define EVER_BIT 0x80000000u
 
-__device__ __forceinline__ int lowest_bits(unsigned long long idle, int cnt, unsigned long long *take) {
-  // select the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
-  unsigned long long m = idle, t = 0;
-  for (int i = 0; i < cnt; ++i) { unsigned long long b = m & (~m + 1ull); t |= b; m ^= b; }
-  *take = t;
-  return cnt;
-}
-
 __device__ __forceinline__ int meta_cap(unsigned mt, int gpc) {
   // tasks a node can still take: min(idle devices / gpus per task, free task slots)
   const int idle = (int)(mt & 0xffu), kfree = (int)(mt >> 16);
   return min(gpc == 1 ? idle : idle / gpc, kfree);
-}
-
-__device__ __forceinline__ int node_cap(unsigned long long busy, int k, int G, int K, int gpc) {
-  int idle = G - __popcll(busy);
-  int slots = K - (int)(k & ~EVER_BIT);
-  int byg = (gpc == 1) ? idle : idle / gpc;
-  int c = min(byg, slots);
-  return c > 0 ? c : 0;
 }
 
 // Shared-memory geometry shared by both tick kernels
@@ -153,17 +139,24 @@ __device__ __forceinline__ unsigned long long take_lowest(unsigned long long idl
 // needed (pending wheel bucket, release record of the next tick's first finisher) or comes
 // from a register-resident 32-record window of the trace, so the loop body has no dependent
 // DRAM/L2 round trip in the common case.
+template <int SUB>
 __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
+  // SUB lanes own one replica: 32 = a whole warp, 16 = two replicas per warp sharing the
+  // (mostly warp-uniform) instruction stream.  Every collective uses the group's own lane
+  // mask, so the groups of a warp may diverge freely.
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int sim = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int wl = threadIdx.x & 31;              // lane within the warp
+  const int lane = wl & (SUB - 1);              // lane within the replica's group
+  const int gbase = wl & ~(SUB - 1);            // first warp lane of the group
+  const unsigned GM = (SUB == 32) ? 0xffffffffu : (((1u << SUB) - 1u) << gbase);
+  const int grp = wl / SUB;
+  const int sim = blockIdx.x * (32 / SUB) + grp;
   if (sim >= nsims) return;
   SimDev &S = sims[sim];
   if (S.done || S.status != 0 || S.policy != GS_SCHED_FIFO) return;
 
   const int M = S.M, G = S.G, K = S.K, n = S.n;
-  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)warp * smem_stride);
+  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)grp * smem_stride);
   int *kk = reinterpret_cast<int *>(busy + M);
   int2 *sstk = reinterpret_cast<int2 *>(kk + M + (M & 1));   // 8-byte aligned
 
@@ -192,18 +185,18 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
   int tick_i = 0;                                     // ticks done in this launch
 
   // ---- stage persistent state: node table, wheel window, queue top
-  for (int i = lane; i < M; i += 32) {
+  for (int i = lane; i < M; i += SUB) {
     const unsigned long long bz = S.nbusy[i];
     const unsigned kv = (unsigned)S.nk[i];
     busy[i] = bz;
     kk[i] = (int)((unsigned)(G - __popcll(bz)) | ((kv & EVER_BIT) ? 0x100u : 0u) | ((unsigned)(K - (int)(kv & ~EVER_BIT)) << 16));
   }
-  for (int i = max(top - SCACHE, 0) + lane; i < top; i += 32) sstk[i & (SCACHE - 1)] = stack[i];
+  for (int i = max(top - SCACHE, 0) + lane; i < top; i += SUB) sstk[i & (SCACHE - 1)] = stack[i];
   int cache_lo = max(top - SCACHE, 0);           // queue entries [cache_lo, top) are cached
-  __syncwarp();
+  __syncwarp(GM);
 
   // trace window: lane l holds record wbase + l
-  int wbase = p & ~31;
+  int wbase = p & ~(SUB - 1);
   JobIn wj;
   wj.arrive = 0x7fffffff; wj.gpus = 1; wj.gpc = 1; wj.ps = 0; wj.memb = 0; wj.dur = 0.0;
   if (wbase + lane < n) wj = jobs[wbase + lane];
@@ -227,26 +220,26 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
       int cnt = 0, q = p;
       while (q < n) {
         const int idx = wbase + lane;
-        const unsigned b = __ballot_sync(FULL, idx >= q && idx < n && wj.arrive <= delta);
+        const unsigned b = GBALLOT(idx >= q && idx < n && wj.arrive <= delta);
         const int c = __popc(b);
         if (c > 0 && cnt == 0) {
           // the batch's first job becomes the queue head: take its record out of the window now
           const int src = p - wbase;
-          hg = __shfl_sync(FULL, wj.gpus, src); hgpc = __shfl_sync(FULL, wj.gpc, src);
+          hg = __shfl_sync(GM, wj.gpus, gbase + src); hgpc = __shfl_sync(GM, wj.gpc, gbase + src);
           harr = delta;
-          if (netcost) hps = __shfl_sync(FULL, wj.ps, src);
-          hmemb = __shfl_sync(FULL, wj.memb, src);
-          hdur = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(wj.dur), src));
+          if (netcost) hps = __shfl_sync(GM, wj.ps, gbase + src);
+          hmemb = __shfl_sync(GM, wj.memb, gbase + src);
+          hdur = __longlong_as_double(__shfl_sync(GM, __double_as_longlong(wj.dur), gbase + src));
         }
         cnt += c; q += c;
-        if (q < wbase + 32 || q >= n) break;
-        wbase += 32;
+        if (q < wbase + SUB || q >= n) break;
+        wbase += SUB;
         wj.arrive = 0x7fffffff;
         if (wbase + lane < n) wj = jobs[wbase + lane];
       }
       if (cnt > 0) {
         // batch [p, p+cnt) lands AHEAD of the queue, first of the batch on top (quirk Q2)
-        for (int i = lane; i < cnt; i += 32) {
+        for (int i = lane; i < cnt; i += SUB) {
           const int2 e = make_int2(p + cnt - 1 - i, delta);
           stack[top + i] = e;
           if (i >= cnt - SCACHE) sstk[(top + i) & (SCACHE - 1)] = e;
@@ -256,7 +249,7 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
         top += cnt; p += cnt;
         if (top - cache_lo > SCACHE) cache_lo = top - SCACHE;
         sum_arr += (long long)cnt * delta;
-        __syncwarp();
+        __syncwarp(GM);
       }
     }
     // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
@@ -265,12 +258,12 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
       if (!head_valid) {
         if (top - 1 >= cache_lo) head = sstk[(top - 1) & (SCACHE - 1)].x;
         else { head = stack[top - 1].x; cache_lo = top; }
-        if (head >= wbase && head < wbase + 32) {
+        if (head >= wbase && head < wbase + SUB) {
           const int src = head - wbase;
-          hg = __shfl_sync(FULL, wj.gpus, src); hgpc = __shfl_sync(FULL, wj.gpc, src);
-          hps = __shfl_sync(FULL, wj.ps, src); harr = __shfl_sync(FULL, wj.arrive, src);
-          hmemb = __shfl_sync(FULL, wj.memb, src);
-          hdur = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(wj.dur), src));
+          hg = __shfl_sync(GM, wj.gpus, gbase + src); hgpc = __shfl_sync(GM, wj.gpc, gbase + src);
+          hps = __shfl_sync(GM, wj.ps, gbase + src); harr = __shfl_sync(GM, wj.arrive, gbase + src);
+          hmemb = __shfl_sync(GM, wj.memb, gbase + src);
+          hdur = __longlong_as_double(__shfl_sync(GM, __double_as_longlong(wj.dur), gbase + src));
         } else {
           const JobIn jr = jobs[head];
           hg = jr.gpus; hgpc = jr.gpc; hmemb = jr.memb; hdur = jr.dur; hps = jr.ps; harr = jr.arrive;
@@ -286,14 +279,14 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
       if (hg <= G) {
         // try_single_node_alloc_ms: first node (id order) that fits the whole job
         int found = -1;
-        for (int base = 0; base < M; base += 32) {
+        for (int base = 0; base < M; base += SUB) {
           const int nd = base + lane;
           bool fit = false;
           if (nd < M) {
             const unsigned mt = (unsigned)kk[nd];
             fit = (int)(mt & 0xffu) >= hg && (int)(mt >> 16) >= htasks;
           }
-          const unsigned b = __ballot_sync(FULL, fit);
+          const unsigned b = GBALLOT(fit);
           if (!placeable) {          // quirk Q21: cpu/mem charged for every task, never refunded
             if (fit) kk[nd] -= htasks << 16;
             continue;
@@ -304,7 +297,7 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
         if (found >= 0) {
           ok = true; first_node = found; nspans = 1;
           bool fresh = false;
-          if (lane == (found & 31)) {
+          if (lane == (found & (SUB - 1))) {
             const unsigned long long take = take_lowest(~busy[found] & gmask, hg, G);
             busy[found] |= take;
             const unsigned kv = (unsigned)kk[found];
@@ -314,8 +307,8 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
             gs_span sp; sp.node = found; sp.ntasks = htasks; sp.devmask = take;
             spans[span_first] = sp;
           }
-          mask0 = __shfl_sync(FULL, mask0, found & 31);
-          ever += __popc(__ballot_sync(FULL, fresh));
+          mask0 = __shfl_sync(GM, mask0, gbase + (found & (SUB - 1)));
+          ever += __popc(GBALLOT(fresh));
           evals += found + 1;
         } else {
           evals += M;
@@ -324,14 +317,14 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
         // try_cross_node_alloc_ms: walk nodes in id order, each takes what it can hold
         int cum = 0, last_base = -1;
         if (placeable) {
-          for (int base = 0; base < M; base += 32) {
+          for (int base = 0; base < M; base += SUB) {
             const int nd = base + lane;
             const int c = (nd < M) ? meta_cap((unsigned)kk[nd], hgpc) : 0;
-            cum += __reduce_add_sync(FULL, c);
+            cum += __reduce_add_sync(GM, c);
             if (cum >= htasks) { last_base = base; break; }
           }
         } else {
-          for (int base = 0; base < M; base += 32) {   // quirk Q21, cross-node flavour: one task charged per node
+          for (int base = 0; base < M; base += SUB) {   // quirk Q21, cross-node flavour: one task charged per node
             const int nd = base + lane;
             if (nd < M && meta_cap((unsigned)kk[nd], hgpc) > 0) kk[nd] -= 1 << 16;
           }
@@ -342,14 +335,14 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
           // reference, algorithm.py:378-387, so no state changes in that case)
           ok = true;
           int rem = htasks, last_node = 0;
-          for (int base = 0; base <= last_base; base += 32) {
+          for (int base = 0; base <= last_base; base += SUB) {
             const int nd = base + lane;
             const int c = (nd < M) ? meta_cap((unsigned)kk[nd], hgpc) : 0;
             int incl = c;
             #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            for (int o = 1; o < SUB; o <<= 1) { int v = __shfl_up_sync(GM, incl, o, SUB); if (lane >= o) incl += v; }
             const int take = min(c, max(rem - (incl - c), 0));
-            const unsigned tb = __ballot_sync(FULL, take > 0);
+            const unsigned tb = GBALLOT(take > 0);
             bool fresh = false;
             if (take > 0) {
               const unsigned long long tk = take_lowest(~busy[nd] & gmask, take * hgpc, G);
@@ -362,23 +355,23 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
               spans[span_first + slot] = sp;
               if (slot == 0) { mask0 = tk; first_node = nd; }
             }
-            ever += __popc(__ballot_sync(FULL, fresh));
+            ever += __popc(GBALLOT(fresh));
             if (tb) last_node = base + 31 - __clz(tb);
             nspans += __popc(tb);
-            const int tot = __shfl_sync(FULL, incl, 31);
+            const int tot = __shfl_sync(GM, incl, gbase + SUB - 1);
             rem -= min(rem, tot);
           }
           {  // first-span fields live in whichever lane owned slot 0
-            const int src = __ffs(__ballot_sync(FULL, first_node >= 0)) - 1;
-            mask0 = __shfl_sync(FULL, mask0, src);
-            first_node = __shfl_sync(FULL, first_node, src);
+            const int src = __ffs(GBALLOT(first_node >= 0)) - 1;
+            mask0 = __shfl_sync(GM, mask0, gbase + src);
+            first_node = __shfl_sync(GM, first_node, gbase + src);
           }
           evals += last_node + 1;
         } else {
           evals += M;
         }
       }
-      __syncwarp();
+      __syncwarp(GM);
       if (ok) {
         // ---- commit: pop, network cost, start (algorithm.py:198-200, schedule.py:49-54,164-167)
         const int j = head;
@@ -418,7 +411,7 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
         busy_gpus += hg;
         mem_busy += memc;
         head = -1; head_valid = false;
-        __syncwarp();
+        __syncwarp(GM);
       }
     }
     // ---------------- D/E. time advances; release jobs whose finish tick is now
@@ -427,7 +420,7 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
       const int sl = now & wmask;
       int h = gwh[sl];
       if (h >= 0) {
-        __syncwarp();
+        __syncwarp(GM);
         if (lane == 0) { gwh[sl] = -1; gwt[sl] = -1; }
         while (h >= 0) {
           JobState js;
@@ -437,7 +430,7 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
           if (scnt == 1) {
             if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] += js.gpus + ((sgpc == 1 ? js.gpus : js.gpus / sgpc) << 16); }
           } else {
-            for (int i = lane; i < scnt; i += 32) {
+            for (int i = lane; i < scnt; i += SUB) {
               const gs_span sp = spans[js.node0 + i];
               busy[sp.node] &= ~sp.devmask; kk[sp.node] += sp.ntasks * sgpc + (sp.ntasks << 16);
             }
@@ -448,7 +441,7 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
           mem_busy -= js.memc;
           h = js.next;
         }
-        __syncwarp();
+        __syncwarp(GM);
       }
     }
     // ---------------- H. statistics row (schedule.py:95-133) from O(1) counters
@@ -478,8 +471,8 @@ __global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims
   }
 
   // ---------------- persist: node table, wheel window and pending bucket go back to global memory
-  __syncwarp();
-  for (int i = lane; i < M; i += 32) {
+  __syncwarp(GM);
+  for (int i = lane; i < M; i += SUB) {
     const unsigned mt = (unsigned)kk[i];
     S.nbusy[i] = busy[i];
     S.nk[i] = (int)((unsigned)(K - (int)(mt >> 16)) | ((mt & 0x100u) ? EVER_BIT : 0u));
@@ -1182,75 +1175,150 @@ __global__ void gs_span_gather_kernel(const gs_job_rec *__restrict__ rec, const 
 }
 
 // ------------------------------------------------------------------ stateless candidate scoring
-// gs_place_batch: b independent jobs against ONE cluster state.  A block stages the node
-// table into shared memory with 16-byte loads (one gs_node per load), reduces it to
-// (idle devices, free task slots) per node, then each warp resolves jobs: lanes stripe
-// over nodes, ballot+ffs gives the first fit (argmin node id), a warp prefix sum gives
-// the cross-node fill.  Same decision rules as the tick kernel, no state is modified.
+// gs_place_batch: b independent jobs scored against ONE cluster state (nothing is modified).
+// The block first turns the node table (one 16-byte load per node) into a small capacity
+// index in shared memory:
+//    cap[nd]  = min(idle devices, free task slots)          tasks of a 1-GPU-per-task job the node can take
+//    ff[t]    = first node with cap >= t                    -> single-node first fit is ONE look-up
+//    P[nd]    = inclusive prefix sum of cap,  Q[nd] = inclusive count of nodes with cap > 0
+//                                                           -> cross-node fill is a binary search on P
+// and then streams the job requests through it, ONE THREAD PER JOB: 16 bytes in, 8 bytes out,
+// a handful of instructions -- the kernel is bound by HBM bandwidth, not by the node scan.
+// Jobs with gpu_per_task != 1 (or a requested per-task node list) take the general per-node walk.
+// general walk over the (idle, slots) table: any gpu_per_task, optional per-task node list
+__device__ void place_general(const short2 *tab, int M, int G, int gpus, int gpc, int *tn, int &fn, int &used) {
+  const int tasks = gpus / gpc;
+  if (gpus <= G) {
+    for (int nd = 0; nd < M; ++nd) {
+      const short2 t = tab[nd];
+      if (t.x >= gpus && t.y >= tasks) { fn = nd; used = 1; break; }
+    }
+    if (fn >= 0 && tn) for (int t = 0; t < tasks; ++t) tn[t] = fn;
+    return;
+  }
+  int cum = 0, last = -1;
+  for (int nd = 0; nd < M; ++nd) {
+    const short2 t = tab[nd];
+    cum += max(min((int)t.x / gpc, (int)t.y), 0);
+    if (cum >= tasks) { last = nd; break; }
+  }
+  if (last < 0) return;
+  int done_tasks = 0;
+  for (int nd = 0; nd <= last; ++nd) {
+    const short2 t = tab[nd];
+    const int c = max(min((int)t.x / gpc, (int)t.y), 0);
+    const int take = min(c, tasks - done_tasks);
+    if (take > 0) {
+      if (fn < 0) fn = nd;
+      ++used;
+      if (tn) for (int q = 0; q < take; ++q) tn[done_tasks + q] = nd;
+      done_tasks += take;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gs_place_kernel(const uint4 *__restrict__ nodes, int M, int G, int cpu_cnt,
                                                        int mem_sz, int cpu_pt, int mem_pt, long long fit_limit,
                                                        const uint4 *__restrict__ jobs, long long b,
                                                        int *__restrict__ first_node, int *__restrict__ nodes_used,
                                                        const long long *__restrict__ task_off, int *__restrict__ task_node) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  short2 *tab = reinterpret_cast<short2 *>(smem_raw);      // (idle, slots) per node
+  short2 *tab = reinterpret_cast<short2 *>(smem_raw);          // (idle, slots) per node
+  int *P = reinterpret_cast<int *>(tab + M);                   // prefix of cap (gpc == 1)
+  int *Q = P + M;                                              // prefix count of cap > 0
+  int *ff = Q + M;                                             // [GS_MAX_GPUS_PER_NODE + 1]
+  __shared__ int first_pos_s;
+  for (int i = threadIdx.x; i <= GS_MAX_GPUS_PER_NODE; i += blockDim.x) ff[i] = 0x7fffffff;
+  if (threadIdx.x == 0) first_pos_s = 0x7fffffff;
+  __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    uint4 v = nodes[i];                                     // {busy_lo, busy_hi, cpu_used, mem_used}
+    const uint4 v = nodes[i];                                  // {busy_lo, busy_hi, cpu_used, mem_used}
     unsigned long long bm = ((unsigned long long)v.y << 32) | v.x;
     if (G < 64) bm &= (1ull << G) - 1ull;
-    int idle = G - __popcll(bm);
-    int cf = cpu_cnt - (int)v.z, mf = mem_sz - (int)v.w;
-    int slots = min(cf > 0 ? cf / cpu_pt : 0, mf > 0 ? mf / mem_pt : 0);
-    tab[i] = make_short2((short)idle, (short)min(slots, 32767));
+    const int idle = G - __popcll(bm);
+    const int cf = cpu_cnt - (int)v.z, mf = mem_sz - (int)v.w;
+    const int slots = min(min(cf > 0 ? cf / cpu_pt : 0, mf > 0 ? mf / mem_pt : 0), 32767);
+    tab[i] = make_short2((short)idle, (short)slots);
+    const int cap = min(idle, slots);
+    P[i] = cap;
+    Q[i] = cap > 0 ? 1 : 0;
+    for (int t = 1; t <= cap; ++t) atomicMin(&ff[t], i);
+    if (cap > 0) atomicMin(&first_pos_s, i);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < b; j += warps) {
-    uint4 jr = jobs[j];                                     // {gpus, gpc, mem_lo, mem_hi}
-    const int gpus = (int)jr.x, gpc = (int)jr.y;
-    const long long memb = (long long)(((unsigned long long)jr.w << 32) | jr.z);
-    const int tasks = gpus / gpc;
-    const bool placeable = memb < fit_limit;
-    int *tn = task_node ? task_node + task_off[j] : nullptr;
-    int fn = -1, used = 0;
-    if (placeable && gpus <= G) {
-      for (int base = 0; base < M && fn < 0; base += 32) {
-        int nd = base + lane;
-        bool fit = false;
-        if (nd < M) { short2 t = tab[nd]; fit = t.x >= gpus && t.y >= tasks; }
-        unsigned bal = __ballot_sync(FULL, fit);
-        if (bal) fn = base + __ffs(bal) - 1;
+  if (threadIdx.x < 32) {                                      // warp 0: inclusive scans of P and Q
+    const int lane = threadIdx.x;
+    int cp = 0, cq = 0;
+    for (int base = 0; base < M; base += 32) {
+      const int i = base + lane;
+      int vp = i < M ? P[i] : 0, vq = i < M ? Q[i] : 0;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tp = __shfl_up_sync(FULL, vp, o), tq = __shfl_up_sync(FULL, vq, o);
+        if (lane >= o) { vp += tp; vq += tq; }
       }
-      if (fn >= 0) { used = 1; if (tn) for (int t = lane; t < tasks; t += 32) tn[t] = fn; }
-    } else if (placeable) {
-      int cum = 0, last_base = -1;
-      for (int base = 0; base < M; base += 32) {
-        int nd = base + lane, c = 0;
-        if (nd < M) { short2 t = tab[nd]; c = max(min(gpc == 1 ? (int)t.x : t.x / gpc, (int)t.y), 0); }
-        cum += __reduce_add_sync(FULL, c);
-        if (cum >= tasks) { last_base = base; break; }
-      }
-      if (last_base >= 0) {
-        int done_tasks = 0;
-        for (int base = 0; base <= last_base; base += 32) {
-          int nd = base + lane, c = 0;
-          if (nd < M) { short2 t = tab[nd]; c = max(min(gpc == 1 ? (int)t.x : t.x / gpc, (int)t.y), 0); }
-          int incl = c;
-          #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-          int excl = done_tasks + incl - c;
-          int take = min(c, max(tasks - excl, 0));
-          unsigned tb = __ballot_sync(FULL, take > 0);
-          if (fn < 0 && tb) fn = base + __ffs(tb) - 1;
-          used += __popc(tb);
-          if (tn) for (int t = 0; t < take; ++t) tn[excl + t] = nd;
-          done_tasks += __shfl_sync(FULL, incl, 31);
+      if (i < M) { P[i] = cp + vp; Q[i] = cq + vq; }
+      cp += __shfl_sync(FULL, vp, 31); cq += __shfl_sync(FULL, vq, 31);
+    }
+  }
+  __syncthreads();
+  const int first_pos = first_pos_s;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // fast path: four requests per thread per iteration, all four 16-byte loads in flight together
+  long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (task_node == nullptr) {
+    for (; j0 + 3 * stride < b; j0 += 4 * stride) {
+      uint4 jr[4];
+      #pragma unroll
+      for (int u = 0; u < 4; ++u) jr[u] = __ldcs(&jobs[j0 + u * stride]);
+      #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int gpus = (int)jr[u].x, gpc = (int)jr[u].y;
+        const long long memb = (long long)(((unsigned long long)jr[u].w << 32) | jr[u].z);
+        int fn = -1, used = 0;
+        if (memb < fit_limit) {
+          if (gpc == 1) {
+            if (gpus <= G) {
+              const int f = ff[gpus];
+              if (f != 0x7fffffff) { fn = f; used = 1; }
+            } else if (P[M - 1] >= gpus) {
+              int lo = 0, hi = M - 1;
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] >= gpus) hi = mid; else lo = mid + 1; }
+              fn = first_pos; used = Q[lo];
+            }
+          } else {
+            place_general(tab, M, G, gpus, gpc, nullptr, fn, used);
+          }
         }
+        __stcs(&first_node[j0 + u * stride], fn);
+        if (nodes_used) __stcs(&nodes_used[j0 + u * stride], used);
       }
     }
-    if (fn < 0 && tn) for (int t = lane; t < tasks; t += 32) tn[t] = -1;
-    if (lane == 0) { first_node[j] = fn; if (nodes_used) nodes_used[j] = used; }
+  }
+  for (long long j = j0; j < b; j += stride) {
+    const uint4 jr = jobs[j];                                  // {gpus, gpc, mem_lo, mem_hi}
+    const int gpus = (int)jr.x, gpc = (int)jr.y;
+    const long long memb = (long long)(((unsigned long long)jr.w << 32) | jr.z);
+    const int tasks = gpc == 1 ? gpus : gpus / gpc;
+    int *tn = task_node ? task_node + task_off[j] : nullptr;
+    int fn = -1, used = 0;
+    if (memb < fit_limit) {
+      if (gpc == 1 && tn == nullptr) {
+        if (gpus <= G) {
+          const int f = ff[gpus];
+          if (f != 0x7fffffff) { fn = f; used = 1; }
+        } else if (P[M - 1] >= tasks) {
+          int lo = 0, hi = M - 1;                              // smallest nd with P[nd] >= tasks
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] >= tasks) hi = mid; else lo = mid + 1; }
+          fn = first_pos; used = Q[lo];
+        }
+      } else {
+        place_general(tab, M, G, gpus, gpc, tn, fn, used);
+      }
+    }
+    if (fn < 0 && tn) for (int t = 0; t < tasks; ++t) tn[t] = -1;
+    first_node[j] = fn;
+    if (nodes_used) nodes_used[j] = used;
   }
 }
 
@@ -1324,7 +1392,8 @@ struct gs_engine {
   std::string err;
   double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
   long long launches = 0;  // kernels launched by this handle
-  int engine_mode = 0;     // 0 auto, 1 warp-per-replica, 2 lane-per-replica
+  int engine_mode = 0;     // 0 auto, 1 warp-per-replica, 2 lane-per-replica, 3 half-warp-per-replica
+  double span_budget = 0;  // > 0: span pool = min(worst case, budget * n + 4096) records per replica
   bool dirty = true;       // host mirror of SimDev newer than device copy
 };
 
@@ -1465,6 +1534,10 @@ static int finish_load(gs_handle h, SimHost &s, int64_t n, bool net, size_t off_
   D.jobs = (const JobIn *)d;
   D.model_mb = net ? (const double *)(d + off_model) : nullptr;
   D.iters = net ? (const double *)(d + off_iters) : nullptr;
+  if (h->span_budget > 0) {
+    const int64_t lim = (int64_t)(h->span_budget * (double)n) + 4096;
+    if (span_cap > lim) span_cap = lim;
+  }
   s.n = n; s.span_cap = span_cap > 0 ? span_cap : 1;
   s.max_need = (int)max_need + 2;
   s.last_arrive = last_arrive;
@@ -1664,9 +1737,18 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
   } else {
     const int stride = (int)align_up((size_t)maxM * 12 + 8 + SCACHE * 8, 16);
     if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
-    if (stride > 48 * 1024)
-      CU(cudaFuncSetAttribute(gs_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
-    gs_tick_kernel<<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+    if (2 * stride > 48 * 1024)
+    {
+      CU(cudaFuncSetAttribute(gs_tick_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
+      CU(cudaFuncSetAttribute(gs_tick_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * stride));
+    }
+    int sub = 32;
+    if (const char *e = getenv("GSCHED_SUB")) { if (atoi(e) == 16) sub = 16; }
+    if (h->engine_mode == 3) sub = 16;
+    if (sub == 16)
+      gs_tick_kernel<16><<<(unsigned)((h->nsims + 1) / 2), 32, (size_t)stride * 2, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+    else
+      gs_tick_kernel<32><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
   }
   CU(cudaGetLastError());
   if (any_fifo) h->launches += 1;
@@ -1864,11 +1946,14 @@ extern "C" int gs_place_batch(gs_handle h, const gs_cluster *cluster, const gs_n
   float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1); h->h2d_ms += ms;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
-  long long want = (b + 7) / 8;
+  long long want = (b + 255) / 256;
   int grid = (int)(want < (long long)dev_sms * 8 ? want : (long long)dev_sms * 8);
   const long long fit_limit = ((long long)cluster->gpu_mem_cap_mib << 20) - ((long long)500 << 20);
   CU(cudaEventRecord(h->e0, h->stream));
-  gs_place_kernel<<<grid, 256, 4 * (size_t)m, h->stream>>>(
+  const size_t place_smem = 12 * (size_t)m + 4 * (GS_MAX_GPUS_PER_NODE + 1);
+  if (place_smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(gs_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem));
+  gs_place_kernel<<<grid, 256, place_smem, h->stream>>>(
       (const uint4 *)(d + o_nodes), m, cluster->num_gpu_p_node, cluster->num_cpu_p_node, cluster->mem_p_node,
       cluster->cpu_per_task, cluster->mem_per_task, fit_limit, (const uint4 *)(d + o_jobs), (long long)b,
       (int *)(d + o_first), (int *)(d + o_used), task_off ? (const long long *)(d + o_toff) : nullptr,
@@ -1930,10 +2015,20 @@ extern "C" int gs_reset(gs_handle h) {
 
 extern "C" int64_t gs_launch_count(gs_handle h) { return h ? h->launches : 0; }
 
+// Span-pool sizing.  Default (0): the worst case sum(min(tasks, nodes)) per replica, which can
+// never overflow.  budget > 0: min(worst case, budget * n + 4096) records -- less HBM per replica;
+// a replica that would overflow stops with GS_ERR_CAPACITY instead of writing out of bounds.
+extern "C" int gs_set_span_budget(gs_handle h, double spans_per_job) {
+  if (!h) return GS_ERR_ARG;
+  if (!(spans_per_job >= 0)) return fail(h, GS_ERR_ARG, "gs_set_span_budget: must be >= 0");
+  h->span_budget = spans_per_job;
+  return GS_OK;
+}
+
 // 0 = auto (lane engine from 32 replicas up), 1 = one warp per replica, 2 = one lane per replica
 extern "C" int gs_set_engine(gs_handle h, int mode) {
   if (!h) return GS_ERR_ARG;
-  if (mode < 0 || mode > 2) return fail(h, GS_ERR_ARG, "gs_set_engine: mode must be 0, 1 or 2");
+  if (mode < 0 || mode > 3) return fail(h, GS_ERR_ARG, "gs_set_engine: mode must be 0..3");
   h->engine_mode = mode;
   return GS_OK;
 }

@@ -189,8 +189,13 @@ int gs_reset(gs_handle h);
 
 /* Kernel mapping: 0 = auto (currently the warp mapping), 1 = one warp per replica
  * (lanes stripe over nodes), 2 = one lane per replica (32 replicas per warp,
- * hot state in shared memory; see DESIGN.md for the measured trade-off).        */
+ * hot state in shared memory), 3 = half a warp per replica (two replicas share a
+ * warp's instruction stream); see DESIGN.md for the measured trade-offs.          */
 int gs_set_engine(gs_handle h, int mode);
+
+/* Span-pool sizing for traces loaded afterwards: 0 (default) = worst case, never overflows;
+ * x > 0 = min(worst case, x * n + 4096) records per replica (overflow -> GS_ERR_CAPACITY). */
+int gs_set_span_budget(gs_handle h, double spans_per_job);
 
 /* Number of CUDA kernels this handle has launched so far.                       */
 int64_t gs_launch_count(gs_handle h);

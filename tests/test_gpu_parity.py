@@ -9,7 +9,7 @@ from conftest import golden_cases, load_golden, render_outputs
 pytestmark = pytest.mark.gpu
 
 
-ENGINES = [1, 2]          # 1 = warp per replica, 2 = lane per replica
+ENGINES = [1, 2, 3]       # 1 = warp per replica, 2 = lane per replica, 3 = half-warp per replica
 
 
 def _engine_run(cluster, table, rows_cap=0, nsims=1, engine=0):
