@@ -352,3 +352,29 @@ def test_batched_sweep_writes_reference_bytes(tmp_path):
             got = open(os.path.join(out_dir, name), newline="").read()
             exp = open(os.path.join(GOLDEN, c, name), newline="").read()
             assert got == exp, (c, name)
+
+
+def test_span_budget_overflow_is_reported_not_written():
+    """A span pool sized below the need makes the replica stop with GS_ERR_CAPACITY (no OOB write)."""
+    from gpuschedule_b200 import capi, ingest, tracegen
+    cluster = capi.make_cluster(num_switch=1, num_node_p_switch=16)
+    table = ingest.table_from_columns(tracegen.synth_columns(6000, seed=91, rate=0.3,
+                                                             gpu_choices=[16, 32, 64], gpu_probs=[.4, .4, .2]))
+    base = _engine_run(cluster, table)[0]                  # default pool: worst case, cannot overflow
+    assert len(base[4]) > 60 + 4096                        # more spans than the tiny budget below
+    for engine in ENGINES:
+        with capi.Engine(device=0, nsims=1) as eng:
+            eng.set_engine(engine)
+            eng.set_span_budget(0.01)                      # 60 + 4096 records
+            eng.config(0, cluster)
+            eng.load_trace(0, table)
+            with pytest.raises(capi.GsError, match="in-kernel error"):
+                eng.run_all()
+            assert eng.stats(0).status == -4
+        with capi.Engine(device=0, nsims=1) as eng:        # generous budget == default result
+            eng.set_engine(engine)
+            eng.set_span_budget(8.0)
+            eng.config(0, cluster)
+            eng.load_trace(0, table)
+            rows = eng.run_all()[0]
+            assert eng.stats(0).done == 1 and rows.tobytes() == base[0].tobytes()
