@@ -347,6 +347,7 @@ def ours(args):
 
     # ---- CPU baseline: the oracle port, 1 thread, bounded sample (rank 0, N=1 only)
     cpu = None
+    cpu_tight = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         t_cpu, ev_cpu, k = 0.0, 0, 0
@@ -360,6 +361,17 @@ def ours(args):
         cpu = {"value": ev_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{k} replica(s) of the {n}-job trace, full runs, oracle/gsched_oracle.c single thread",
                "host_cores": os.cpu_count()}
+        # extra yardstick (not the reference's algorithm): the engine's own O(1)-counter algorithm as
+        # tight single-thread C, oracle/tight_cpu.c -- the strongest CPU competitor we could write
+        tr = oracle.TightRunner(cluster, tables[0])
+        tr.run()
+        c0 = time.perf_counter(); reps = 0; ev_t = 0
+        while time.perf_counter() - c0 < 2.0:
+            tk, ev = tr.run(); reps += 1; ev_t += ev
+        assert tk == ticks[0]
+        cpu_tight = {"value": ev_t / (time.perf_counter() - c0), "unit": UNIT, "cores": 1,
+                     "kind": "tight C restatement of the ENGINE's algorithm (oracle/tight_cpu.c), not reference code",
+                     "sample": f"{reps} runs of one {n}-job replica"}
 
     if rank == 0:
         out = {
@@ -374,7 +386,7 @@ def ours(args):
                        "events_per_step": events_all, "ticks_per_step": ticks_rank * world},
             "wall_ms_per_step": wall_ms / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_tight": cpu_tight,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -463,6 +475,13 @@ def reference(args):
             events += sum(ex.map(one, work))
         dt = time.perf_counter() - t0
     value = events / dt
+    runners = [oracle.TightRunner(cluster, t) for t in tables]
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda r: r.run(), runners))
+        t0 = time.perf_counter(); ev_t = 0; reps = 0
+        while time.perf_counter() - t0 < 3.0:
+            ev_t += sum(e for _, e in ex.map(lambda r: r.run(), runners)); reps += 1
+        tight_value = ev_t / (time.perf_counter() - t0)
     sample = f"{threads} replicas of the {n}-job trace per step (one per thread), full runs"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
@@ -473,6 +492,9 @@ def reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                             "note": "oracle/gsched_oracle.c: C restatement of the reference's Python loop "
                                     "(the Python reference itself: 186 events/s at N=10k, BASELINE.md)"},
+           "cpu_tight": {"value": tight_value, "unit": UNIT, "cores": threads,
+                         "kind": "tight C restatement of the ENGINE's algorithm (oracle/tight_cpu.c), not reference code",
+                         "sample": f"{reps} rounds of {threads} replicas, one per thread"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -22,7 +22,8 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "gsched_oracle.c"), os.path.join(_HERE, "policy_oracle.c")]
+    srcs = [os.path.join(_HERE, "gsched_oracle.c"), os.path.join(_HERE, "policy_oracle.c"),
+            os.path.join(_HERE, "tight_cpu.c")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "gsched.h")
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(x) for x in srcs + [hdr])):
@@ -39,6 +40,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.oracle_run_fifo.restype = C.c_int64
         _lib.oracle_run_policy.restype = C.c_int64
+        _lib.tight_run_fifo.restype = C.c_int64
         _lib.oracle_place_one.restype = C.c_int
         _lib.oracle_net_cost.restype = C.c_double
     return _lib
@@ -159,4 +161,67 @@ def run_policy(cluster: GsCluster, policy, table, rows_cap=None):
     r.recs = recs[:n]
     r.finish_order = order[:nfin.value]
     r.events = events.value
+    return r
+
+
+class TightRunner:
+    """Pre-allocated buffers + one bare C call: what bench.py times for the `cpu_tight` yardstick."""
+
+    def __init__(self, cluster: GsCluster, table):
+        n = table.n
+        self.cluster, self.n = cluster, n
+        self.rows_cap = int(table.arrive_tick[-1]) + 2 * int(np.ceil(table.duration.max())) + 4096
+        self.rows = np.zeros(self.rows_cap, dtype=ROW_DTYPE)
+        self.recs = np.zeros(n, dtype=JOB_DTYPE)
+        self.order = np.zeros(n, dtype=np.int32)
+        m = cluster.num_switch * cluster.num_node_p_switch
+        self.cap = int(np.minimum(table.tasks, m).sum()) + 1
+        self.spans = np.zeros(self.cap, dtype=SPAN_DTYPE)
+        self.sfirst = np.zeros(n, dtype=np.int64)
+        self.scnt = np.zeros(n, dtype=np.int32)
+        arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        self.cols = (arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32),
+                     arr(table.duration, np.float64), arr(table.mem_bytes, np.int64))
+        self.fn = lib().tight_run_fifo
+
+    def run(self):
+        nfin, events = C.c_int64(0), C.c_int64(0)
+        a, g, c, d, mm = self.cols
+        ticks = self.fn(C.byref(self.cluster), C.c_int64(self.n), _p(a), _p(g), _p(c), _p(d), _p(mm), _p(self.rows),
+                        C.c_int64(self.rows_cap), _p(self.recs), _p(self.order), C.byref(nfin), _p(self.spans),
+                        C.c_int64(self.cap), _p(self.sfirst), _p(self.scnt), C.byref(events))
+        if ticks < 0:
+            raise RuntimeError(f"tight_run_fifo failed: {ticks}")
+        return int(ticks), int(events.value)
+
+
+def run_tight(cluster: GsCluster, table, rows_cap=None):
+    """oracle/tight_cpu.c: the engine's own algorithm as tight single-thread C (no network cost)."""
+    n = table.n
+    if rows_cap is None:
+        rows_cap = int(table.arrive_tick[-1] if n else 0) + 2 * int(np.ceil(table.duration.max()) if n else 0) + n + 4096
+    rows = np.zeros(rows_cap, dtype=ROW_DTYPE)
+    recs = np.zeros(max(n, 1), dtype=JOB_DTYPE)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    m = cluster.num_switch * cluster.num_node_p_switch
+    cap = int(np.minimum(table.tasks, m).sum()) + 1
+    spans = np.zeros(cap, dtype=SPAN_DTYPE)
+    sfirst = np.zeros(max(n, 1), dtype=np.int64)
+    scnt = np.zeros(max(n, 1), dtype=np.int32)
+    nfin, events = C.c_int64(0), C.c_int64(0)
+    arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    a, g, c = arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32)
+    d, mm = arr(table.duration, np.float64), arr(table.mem_bytes, np.int64)
+    ticks = lib().tight_run_fifo(C.byref(cluster), C.c_int64(n), _p(a), _p(g), _p(c), _p(d), _p(mm), _p(rows),
+                                 C.c_int64(rows_cap), _p(recs), _p(order), C.byref(nfin), _p(spans), C.c_int64(cap),
+                                 _p(sfirst), _p(scnt), C.byref(events))
+    if ticks < 0:
+        raise RuntimeError(f"tight_run_fifo failed: {ticks}")
+    r = OracleResult()
+    r.ticks, r.rows, r.recs = int(ticks), rows[:ticks], recs[:n]
+    r.finish_order, r.events = order[:nfin.value], events.value
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(scnt[:n], out=off[1:])
+    idx = np.concatenate([np.arange(f, f + k) for f, k in zip(sfirst[:n], scnt[:n])]) if n and off[-1] else np.zeros(0, dtype=np.int64)
+    r.span_off, r.spans = off, spans[idx.astype(np.int64)] if len(idx) else spans[:0]
     return r
