@@ -929,11 +929,12 @@ __device__ bool pol_yarn_place(const SimDev &S, int gpus, int gpc, bool placeabl
   return true;
 }
 
-__global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, long long max_ticks) {
+__global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, long long max_ticks, int take_dlas) {
   const int sim = blockIdx.x * blockDim.x + threadIdx.x;
   if (sim >= nsims) return;
   SimDev &S = sims[sim];
   if (S.policy == GS_SCHED_FIFO || S.done || S.status != 0) return;
+  if (!take_dlas && (S.policy == GS_SCHED_DLAS || S.policy == GS_SCHED_DLAS_GPU)) return;   // warp kernel's
   const int policy = S.policy, n = S.n, M = S.M, G = S.G, K = S.K;
   const bool is_dlas = policy == GS_SCHED_DLAS || policy == GS_SCHED_DLAS_GPU;
   const bool gputime = policy == GS_SCHED_DLAS_GPU || policy == GS_SCHED_GITTINS;
@@ -1112,6 +1113,270 @@ __global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, 
   S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.next_job_jump = next_job_jump; S.finished = nfin;
   S.next_gittins_unit = next_git; S.events = events; S.ticks = ticks; S.row_first = row_first;
   S.done = done ? 1 : 0; S.status = status; S.running = 0; S.top = 0; S.started = 0;
+}
+
+// ------------------------------------------------------------------ event-driven policies, warp cooperative
+// dlas / dlas-gpu (MLFQ with GPU counting), one WARP per replica.  Same semantics as
+// gs_policy_kernel / oracle/policy_oracle.c, but every O(runnable) loop of an event runs 32
+// entries at a time: counter update + END compaction (ballot prefix), demotion list in runnable
+// order, greedy admission as a warp prefix sum with skip, RUNNING-before-PENDING stable partition
+// of each queue, min-reduction for the next completion / queue jump.
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
+  return v;
+}
+
+__global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsims, long long max_ticks) {
+  const int sim = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (sim >= nsims) return;
+  SimDev &S = sims[sim];
+  const int policy = S.policy;
+  if (!(policy == GS_SCHED_DLAS || policy == GS_SCHED_DLAS_GPU) || S.done || S.status != 0) return;
+  const int n = S.n, M = S.M, G = S.G;
+  const bool gputime = policy == GS_SCHED_DLAS_GPU;
+  const int nq = S.num_queue;
+  const JobIn *__restrict__ jobs = S.jobs;
+  PJob *pj = S.pj;
+  int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
+  gs_job_rec *rec = S.rec;
+  const long long cap_bytes = S.cap_bytes;
+  const int total_gpus = M * G;
+  const unsigned lt = (1u << lane) - 1u;
+  int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, next_job_jump = S.next_job_jump, nfin = S.finished;
+  int qn[GS_MAX_QUEUES];
+  #pragma unroll
+  for (int q = 0; q < GS_MAX_QUEUES; ++q) qn[q] = S.qn[q];
+  double qlim[GS_MAX_QUEUES];
+  #pragma unroll
+  for (int q = 0; q < GS_MAX_QUEUES; ++q) qlim[q] = S.queue_limit[q];
+  long long events = S.events, ticks = S.ticks;
+  const long long row_first = ticks;
+  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+  bool done = false;
+
+  while (budget > 0 && (ticks - row_first) < S.rows_cap) {
+    if (!((n - p) + rn > 0)) { done = true; break; }
+    if (p >= n && end_time == 0x7fffffff) { done = true; break; }
+    const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
+    int event_time; bool has_start = false, has_end = false;
+    if (end_time < start_time) { event_time = end_time; has_end = true; }
+    else if (end_time > start_time) { event_time = start_time; has_start = true; }
+    else { event_time = start_time; has_start = has_end = true; }
+    if (event_time > next_job_jump) { event_time = next_job_jump; has_start = has_end = false; }
+    // ---- completions (end_jobs is in runnable order)
+    if (has_end) {
+      for (int i = lane; i < en; i += 32) {
+        const int j = endj[i];
+        PJob r = pj[j];
+        r.status = PST_END;
+        pj[j] = r;
+        const double dur = jobs[j].dur;
+        const double cl = ceil(dur);
+        gs_job_rec o; o.start = r.start; o.end = event_time; o.jct = cl < 1.0 ? 1 : (int)cl; o.preempt = r.resume; o.duration = dur;
+        rec[j] = o;
+        S.fin[nfin + i] = j;
+      }
+      nfin += en; events += en;
+    }
+    // ---- arrivals: appended to runnable and to queue 0 in trace order
+    if (has_start) {
+      int cnt = 0;
+      while (true) {
+        const int idx = p + cnt + lane;
+        const unsigned b = __ballot_sync(FULL, idx < n && jobs[idx].arrive == event_time);
+        const int c = (b == FULL) ? 32 : __ffs(~b) - 1;       // run of arrivals from the front
+        cnt += c;
+        if (c < 32) break;
+      }
+      for (int i = lane; i < cnt; i += 32) {
+        const int j = p + i;
+        PJob r; r.last_check = event_time; r.total_exec = 0; r.exec = 0; r.pending = 0; r.last_pending = 0; r.start = -1;
+        r.resume = 0; r.status = PST_PENDING; r.q_id = 0; r.pad0 = 0; r.pad1 = 0;
+        pj[j] = r;
+        runnable[rn + i] = j;
+        S.queues[qn[0] + i] = j;
+      }
+      rn += cnt; qn[0] += cnt; events += cnt; p += cnt;
+    }
+    __syncwarp();
+    // ---- pass 1 over runnable: drop END, age counters, detect demotions (kept in runnable order)
+    int nd = 0;
+    {
+      int w = 0;
+      for (int base = 0; base < rn; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < rn;
+        const int j = valid ? runnable[idx] : 0;
+        PJob r;
+        if (valid) r = pj[j]; else { r.status = PST_END; r.q_id = 0; r.last_check = 0; r.total_exec = 0; r.exec = 0; r.pending = 0; r.last_pending = 0; r.start = -1; r.resume = 0; }
+        const bool keep = valid && r.status != PST_END;
+        bool demote = false;
+        if (keep) {
+          const int dt = event_time - r.last_check;
+          r.last_check = event_time;
+          if (r.status == PST_RUNNING) {
+            r.total_exec += dt; r.exec += dt;
+            const double j_gt = gputime ? (double)r.exec * jobs[j].gpus : (double)r.exec;
+            if (r.q_id < nq - 1 && j_gt >= qlim[r.q_id]) { demote = true; r.q_id += 1; }
+          } else {
+            r.pending += dt;
+            if (r.exec > 0) r.last_pending += dt;
+          }
+          pj[j] = r;
+        }
+        const unsigned kb = __ballot_sync(FULL, keep), db = __ballot_sync(FULL, demote);
+        if (keep) runnable[w + __popc(kb & lt)] = j;
+        if (demote) tmpl[nd + __popc(db & lt)] = j;
+        w += __popc(kb); nd += __popc(db);
+      }
+      rn = w;
+    }
+    __syncwarp();
+    // ---- queues: drop END / demoted-away entries, then append this event's demotions
+    for (int q = 0; q < nq; ++q) {
+      int *qv = S.queues + (size_t)q * n;
+      int w = 0;
+      for (int base = 0; base < qn[q]; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < qn[q];
+        const int j = valid ? qv[idx] : 0;
+        bool keep = false;
+        if (valid) { const PJob r = pj[j]; keep = r.status != PST_END && r.q_id == q; }
+        const unsigned kb = __ballot_sync(FULL, keep);
+        if (keep) qv[w + __popc(kb & lt)] = j;
+        w += __popc(kb);
+      }
+      qn[q] = w;
+      __syncwarp();
+      if (q > 0) {          // jobs demoted into q, in runnable order
+        for (int base = 0; base < nd; base += 32) {
+          const int idx = base + lane;
+          const int j = idx < nd ? tmpl[idx] : 0;
+          const bool mine = idx < nd && pj[j].q_id == q;
+          const unsigned mb = __ballot_sync(FULL, mine);
+          if (mine) qv[qn[q] + __popc(mb & lt)] = j;
+          qn[q] += __popc(mb);
+        }
+      }
+      __syncwarp();
+    }
+    // ---- greedy re-admission on the emptied cluster (GPU counting), queue by queue, and the
+    //      RUNNING-before-PENDING stable partition of each queue
+    int free_gpu = total_gpus, busy = 0;
+    long long mem_busy = 0;
+    for (int q = 0; q < nq; ++q) {
+      int *qv = S.queues + (size_t)q * n;
+      int w = 0, pn = 0;   // RUNNING entries written so far / PENDING entries parked in tmpl
+      for (int base = 0; base < qn[q]; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < qn[q];
+        const int j = valid ? qv[idx] : 0;
+        PJob r; JobIn jr;
+        int g = 0;
+        if (valid) { r = pj[j]; jr = jobs[j]; g = jr.gpus; } else { r.status = PST_NONE; r.start = -1; r.resume = 0; jr.memb = 0; }
+        // sequential greedy over the 32 entries: admit while the prefix fits, skip the first that does not
+        bool admitted = false, decided = !valid;
+        while (true) {
+          const unsigned ub = __ballot_sync(FULL, !decided);
+          if (ub == 0) break;
+          if (free_gpu == 0) { decided = true; continue; }
+          const int inc = warp_incl_scan(decided ? 0 : g, lane);
+          const bool fits = !decided && inc <= free_gpu;
+          const unsigned fb = __ballot_sync(FULL, !decided && !fits);     // undecided entries that do not fit
+          const int first_fail = fb ? __ffs(fb) - 1 : 32;
+          if (!decided && lane < first_fail) { admitted = true; decided = true; }
+          if (!decided && lane == first_fail) decided = true;            // rejected
+          const int last_ok = first_fail - 1;
+          const int used_now = last_ok >= 0 ? __shfl_sync(FULL, inc, last_ok < 0 ? 0 : last_ok) : 0;
+          free_gpu -= used_now;
+        }
+        // status transitions (each one is an event): PENDING->RUNNING = resume, RUNNING->PENDING = preempt
+        const bool flip_run = valid && admitted && r.status == PST_PENDING;
+        const bool flip_pre = valid && !admitted && r.status == PST_RUNNING;
+        if (flip_run) { r.status = PST_RUNNING; r.resume += 1; if (r.start < 0) r.start = event_time; pj[j] = r; }
+        if (flip_pre) { r.status = PST_PENDING; pj[j] = r; }
+        events += __popc(__ballot_sync(FULL, flip_run)) + __popc(__ballot_sync(FULL, flip_pre));
+        busy += __reduce_add_sync(FULL, admitted ? g : 0);
+        {
+          long long mc = admitted ? (long long)g * (jr.memb < cap_bytes ? jr.memb : cap_bytes) : 0;
+          #pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mc += __shfl_xor_sync(FULL, mc, o);
+          mem_busy += mc;
+        }
+        // stable partition: RUNNING entries stay in place order, PENDING go behind
+        const bool is_run = valid && admitted;
+        const bool is_pen = valid && !admitted;
+        const unsigned rb = __ballot_sync(FULL, is_run), pb = __ballot_sync(FULL, is_pen);
+        if (is_run) qv[w + __popc(rb & lt)] = j;
+        if (is_pen) tmpl[pn + __popc(pb & lt)] = j;
+        w += __popc(rb); pn += __popc(pb);
+      }
+      __syncwarp();
+      for (int i = lane; i < pn; i += 32) qv[w + i] = tmpl[i];
+      __syncwarp();
+    }
+    // ---- final pass over runnable: transitions are counted, next completion / jump, statistics
+    end_time = 0x7fffffff; en = 0; next_job_jump = 0x7fffffff;
+    int running = 0, queued = 0, pmax = 0;
+    long long psum = 0;
+    for (int base = 0; base < rn; base += 32) {
+      const int idx = base + lane;
+      const bool valid = idx < rn;
+      const int j = valid ? runnable[idx] : 0;
+      int e = 0x7fffffff, jt = 0x7fffffff, pend = 0;
+      bool isrun = false;
+      if (valid) {
+        const PJob r = pj[j];
+        isrun = r.status == PST_RUNNING;
+        if (isrun) {
+          const JobIn jr = jobs[j];
+          const double cl = ceil(jr.dur);
+          const int D = cl < 1.0 ? 1 : (int)cl;
+          e = event_time + (D - r.total_exec);
+          if (r.q_id < nq - 1) {
+            const double lim = qlim[r.q_id];
+            const double t = gputime ? ceil((lim - (double)r.exec) / (double)jr.gpus) + event_time : lim - (double)r.exec + event_time;
+            jt = t > 2.0e9 ? 0x7fffffff : (int)t;
+            if (jt <= event_time) jt = event_time + 1;
+          }
+        } else pend = r.pending;
+      }
+      const int cmin = __reduce_min_sync(FULL, e);
+      if (cmin < end_time) { end_time = cmin; en = 0; }
+      const unsigned eb = __ballot_sync(FULL, valid && isrun && e == end_time);
+      if (valid && isrun && e == end_time) endj[en + __popc(eb & lt)] = j;
+      en += __popc(eb);
+      next_job_jump = min(next_job_jump, __reduce_min_sync(FULL, jt));
+      running += __popc(__ballot_sync(FULL, valid && isrun));
+      queued += __popc(__ballot_sync(FULL, valid && !isrun));
+      pmax = max(pmax, __reduce_max_sync(FULL, pend));
+      psum += (long long)__reduce_add_sync(FULL, pend);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int4 *dst = reinterpret_cast<int4 *>(&S.rows[ticks - row_first]);
+      dst[0] = make_int4(event_time, M, 0, busy);
+      dst[1] = make_int4(total_gpus - busy, running, queued, nfin);
+      dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(psum & 0xffffffffLL), (int)(psum >> 32));
+      dst[3] = make_int4(pmax, 0, 0, 0);
+    }
+    ticks += 1; budget -= 1;
+  }
+  if (!done && !((n - p) + rn > 0)) done = true;
+  if (!done && p >= n && end_time == 0x7fffffff) done = true;
+  __syncwarp();
+  if (done) {
+    for (int j = lane; j < n; j += 32) { const PJob r = pj[j]; if (r.status != PST_END && r.status != PST_NONE && r.start >= 0) { rec[j].start = r.start; rec[j].preempt = r.resume; } }
+  }
+  if (lane == 0) {
+    S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.next_job_jump = next_job_jump; S.finished = nfin;
+    #pragma unroll
+    for (int q = 0; q < GS_MAX_QUEUES; ++q) S.qn[q] = qn[q];
+    S.events = events; S.ticks = ticks; S.row_first = row_first;
+    S.done = done ? 1 : 0; S.running = 0; S.top = 0; S.started = 0;
+  }
 }
 
 // One launch (re)initialises every replica flagged need_init: job records (never-started jobs
@@ -1717,9 +1982,16 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
     h->launches += 1;
   }
   if (any_evd) {
-    gs_policy_kernel<<<(unsigned)((h->nsims + 31) / 32), 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks);
+    // dlas / dlas-gpu: one warp per replica; sjf / gittins (and everything with engine mode 2): one thread per replica
+    const int thread_dlas = h->engine_mode == 2 ? 1 : 0;
+    gs_policy_kernel<<<(unsigned)((h->nsims + 31) / 32), 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, thread_dlas);
     CU(cudaGetLastError());
     h->launches += 1;
+    if (!thread_dlas) {
+      gs_dlas_warp_kernel<<<(unsigned)h->nsims, 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    }
   }
   if (!any_fifo) {
     // nothing for the tick kernels
