@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, 
   if (sim >= nsims) return;
   SimDev &S = sims[sim];
   if (S.policy == GS_SCHED_FIFO || S.done || S.status != 0) return;
-  if (!take_dlas && (S.policy == GS_SCHED_DLAS || S.policy == GS_SCHED_DLAS_GPU)) return;   // warp kernel's
+  if (!take_dlas) return;   // every event-driven policy has a warp-cooperative kernel; this one is the fallback (engine mode 2)
   const int policy = S.policy, n = S.n, M = S.M, G = S.G, K = S.K;
   const bool is_dlas = policy == GS_SCHED_DLAS || policy == GS_SCHED_DLAS_GPU;
   const bool gputime = policy == GS_SCHED_DLAS_GPU || policy == GS_SCHED_GITTINS;
@@ -1374,6 +1374,311 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
     S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.next_job_jump = next_job_jump; S.finished = nfin;
     #pragma unroll
     for (int q = 0; q < GS_MAX_QUEUES; ++q) S.qn[q] = qn[q];
+    S.events = events; S.ticks = ticks; S.row_first = row_first;
+    S.done = done ? 1 : 0; S.running = 0; S.top = 0; S.started = 0;
+  }
+}
+
+// sjf (stable order by num_gpu + live-yarn placement on the emptied cluster) and gittins (stable
+// order by gittins rank + GPU counting), one WARP per replica.  Same semantics as
+// gs_policy_kernel / oracle/policy_oracle.c.  The runnable list stays sorted between events for
+// sjf (keys never change), so new arrivals are INSERTED (count of keys <= k, warp-parallel shift);
+// gittins ranks move a little every event, so the list is repaired with stable odd-even
+// transposition rounds (adjacent swaps only when strictly greater == the unique stable order).
+__global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int nsims, long long max_ticks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int sim = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (sim >= nsims) return;
+  SimDev &S = sims[sim];
+  const int policy = S.policy;
+  if (!(policy == GS_SCHED_SJF || policy == GS_SCHED_GITTINS) || S.done || S.status != 0) return;
+  const bool sjf = policy == GS_SCHED_SJF;
+  const int n = S.n, M = S.M, G = S.G, K = S.K;
+  int *nidle = reinterpret_cast<int *>(smem_raw);        // sjf: (idle devices, free slots) per node
+  int *nkfree = nidle + M;
+  const JobIn *__restrict__ jobs = S.jobs;
+  PJob *pj = S.pj;
+  int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
+  double *rk = reinterpret_cast<double *>(S.queues);     // gittins: rank of runnable[i] (no queues in these policies)
+  gs_job_rec *rec = S.rec;
+  const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
+  const int total_gpus = M * G;
+  const unsigned lt = (1u << lane) - 1u;
+  int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, nfin = S.finished;
+  double next_git = S.next_gittins_unit;
+  long long events = S.events, ticks = S.ticks;
+  const long long row_first = ticks;
+  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+  bool done = false;
+
+  while (budget > 0 && (ticks - row_first) < S.rows_cap) {
+    if (!((n - p) + rn > 0)) { done = true; break; }
+    if (p >= n && end_time == 0x7fffffff) { done = true; break; }
+    const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
+    int event_time; bool has_start = false, has_end = false;
+    if (end_time < start_time) { event_time = end_time; has_end = true; }
+    else if (end_time > start_time) { event_time = start_time; has_start = true; }
+    else { event_time = start_time; has_start = has_end = true; }
+    if (!sjf && (double)event_time > next_git) { event_time = (int)next_git; has_start = has_end = false; }
+    // ---- completions
+    if (has_end) {
+      for (int i = lane; i < en; i += 32) {
+        const int j = endj[i];
+        PJob r = pj[j];
+        r.status = PST_END;
+        pj[j] = r;
+        const double dur = jobs[j].dur;
+        const double cl = ceil(dur);
+        gs_job_rec o; o.start = r.start; o.end = event_time; o.jct = cl < 1.0 ? 1 : (int)cl; o.preempt = r.resume; o.duration = dur;
+        rec[j] = o;
+        S.fin[nfin + i] = j;
+      }
+      nfin += en; events += en;
+    }
+    __syncwarp();
+    // ---- pass 1: drop END, age counters, (gittins) rank of every survivor at its new position
+    {
+      int w = 0;
+      for (int base = 0; base < rn; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < rn;
+        const int j = valid ? runnable[idx] : 0;
+        PJob r;
+        r.status = PST_END; r.q_id = 0; r.last_check = 0; r.total_exec = 0; r.exec = 0; r.pending = 0; r.last_pending = 0; r.start = -1; r.resume = 0;
+        if (valid) r = pj[j];
+        const bool keep = valid && r.status != PST_END;
+        double rank = 0.0;
+        if (keep) {
+          const int dt = event_time - r.last_check;
+          r.last_check = event_time;
+          if (r.status == PST_RUNNING) { r.total_exec += dt; r.exec += dt; }
+          else { r.pending += dt; if (r.exec > 0) r.last_pending += dt; }
+          pj[j] = r;
+          if (!sjf) rank = git_lookup(S, r.status == PST_RUNNING ? (double)r.exec * jobs[j].gpus : (double)r.exec);
+        }
+        const unsigned kb = __ballot_sync(FULL, keep);
+        if (keep) { const int pos = w + __popc(kb & lt); runnable[pos] = j; if (!sjf) rk[pos] = rank; }
+        w += __popc(kb);
+      }
+      rn = w;
+    }
+    __syncwarp();
+    // ---- arrivals (after the survivors, like the list append of the specification)
+    int cnt = 0;
+    if (has_start) {
+      while (true) {
+        const int idx = p + cnt + lane;
+        const unsigned b = __ballot_sync(FULL, idx < n && jobs[idx].arrive == event_time);
+        const int c = (b == FULL) ? 32 : __ffs(~b) - 1;
+        cnt += c;
+        if (c < 32) break;
+      }
+      for (int i = lane; i < cnt; i += 32) {
+        const int j = p + i;
+        PJob r; r.last_check = event_time; r.total_exec = 0; r.exec = 0; r.pending = 0; r.last_pending = 0; r.start = -1;
+        r.resume = 0; r.status = PST_PENDING; r.q_id = 0; r.pad0 = 0; r.pad1 = 0;
+        pj[j] = r;
+      }
+      events += cnt;
+      if (!sjf) {
+        const double r0 = git_lookup(S, 0.0);              // a new job: executed_time == 0
+        for (int i = lane; i < cnt; i += 32) { runnable[rn + i] = p + i; rk[rn + i] = r0; }
+        rn += cnt;
+      }
+    }
+    __syncwarp();
+    if (sjf) {
+      // stable insertion of each new job: position = number of runnable entries with num_gpu <= its own
+      for (int i = 0; i < cnt; ++i) {
+        const int j = p + i;
+        const int kx = jobs[j].gpus;
+        int pos = 0;
+        for (int base = 0; base < rn; base += 32) {
+          const int idx = base + lane;
+          const bool le = idx < rn && jobs[runnable[idx]].gpus <= kx;
+          pos += __popc(__ballot_sync(FULL, le));
+        }
+        for (int hi = rn; hi > pos; hi -= 32) {              // shift [pos, rn) right by one, from the tail
+          const int idx = hi - 1 - lane;
+          const int v = idx >= pos ? runnable[idx] : 0;
+          __syncwarp();
+          if (idx >= pos) runnable[idx + 1] = v;
+          __syncwarp();
+        }
+        if (lane == 0) runnable[pos] = j;
+        rn += 1;
+        __syncwarp();
+      }
+    } else {
+      // stable odd-even transposition until a full round makes no swap
+      bool again = rn > 1;
+      while (again) {
+        unsigned any = 0;
+        for (int phase = 0; phase < 2; ++phase) {
+          for (int base = phase; base + 1 < rn; base += 64) {
+            const int a = base + 2 * lane;
+            bool sw = false;
+            if (a + 1 < rn) {
+              const double ka = rk[a], kb2 = rk[a + 1];
+              if (ka > kb2) { const int ja = runnable[a], jb = runnable[a + 1]; runnable[a] = jb; runnable[a + 1] = ja; rk[a] = kb2; rk[a + 1] = ka; sw = true; }
+            }
+            any |= __ballot_sync(FULL, sw);
+          }
+          __syncwarp();
+        }
+        again = any != 0;
+      }
+    }
+    p += cnt;
+    __syncwarp();
+    // ---- greedy re-admission on the emptied cluster, in list order
+    int busy = 0;
+    long long mem_busy = 0;
+    if (sjf) {
+      for (int nd = lane; nd < M; nd += 32) { nidle[nd] = G; nkfree[nd] = K; }
+      __syncwarp();
+      for (int i = 0; i < rn; ++i) {
+        const int j = runnable[i];
+        const JobIn jr = jobs[j];
+        PJob r = pj[j];
+        const int hg = jr.gpus, hc = jr.gpc, tasks = hc == 1 ? hg : hg / hc;
+        bool ok = false;
+        if (jr.memb < fit_limit) {
+          if (hg <= G) {
+            int found = -1;
+            for (int base = 0; base < M && found < 0; base += 32) {
+              const int nd = base + lane;
+              const bool fit = nd < M && nidle[nd] >= hg && nkfree[nd] >= tasks;
+              const unsigned b = __ballot_sync(FULL, fit);
+              if (b) found = base + __ffs(b) - 1;
+            }
+            if (found >= 0) { ok = true; if (lane == 0) { nidle[found] -= hg; nkfree[found] -= tasks; } }
+          } else {
+            int cum = 0, last_base = -1;
+            for (int base = 0; base < M; base += 32) {
+              const int nd = base + lane;
+              const int c = nd < M ? max(min(nidle[nd] / hc, nkfree[nd]), 0) : 0;
+              cum += __reduce_add_sync(FULL, c);
+              if (cum >= tasks) { last_base = base; break; }
+            }
+            if (last_base >= 0) {
+              ok = true;
+              int rem = tasks;
+              for (int base = 0; base <= last_base; base += 32) {
+                const int nd = base + lane;
+                const int c = nd < M ? max(min(nidle[nd] / hc, nkfree[nd]), 0) : 0;
+                const int incl = warp_incl_scan(c, lane);
+                const int take = min(c, max(rem - (incl - c), 0));
+                if (take > 0) { nidle[nd] -= take * hc; nkfree[nd] -= take; }
+                rem -= min(rem, __shfl_sync(FULL, incl, 31));
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (ok) {
+          busy += hg;
+          mem_busy += (long long)hg * (jr.memb < cap_bytes ? jr.memb : cap_bytes);
+          if (r.status == PST_PENDING) {
+            r.status = PST_RUNNING; r.resume += 1; if (r.start < 0) r.start = event_time;
+            if (lane == 0) pj[j] = r;
+            events += 1;
+          } else if (r.start < 0) { r.start = event_time; if (lane == 0) pj[j] = r; }
+        } else if (r.status == PST_RUNNING) {
+          r.status = PST_PENDING;
+          if (lane == 0) pj[j] = r;
+          events += 1;
+        }
+        __syncwarp();
+      }
+    } else {
+      int free_gpu = total_gpus;
+      for (int base = 0; base < rn; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < rn;
+        const int j = valid ? runnable[idx] : 0;
+        PJob r; JobIn jr;
+        r.status = PST_NONE; r.start = -1; r.resume = 0; jr.memb = 0; jr.gpus = 0;
+        int g = 0;
+        if (valid) { r = pj[j]; jr = jobs[j]; g = jr.gpus; }
+        bool admitted = false, decided = !valid;
+        while (true) {
+          const unsigned ub = __ballot_sync(FULL, !decided);
+          if (ub == 0) break;
+          if (free_gpu == 0) { decided = true; continue; }
+          const int inc = warp_incl_scan(decided ? 0 : g, lane);
+          const bool fits = !decided && inc <= free_gpu;
+          const unsigned fb = __ballot_sync(FULL, !decided && !fits);
+          const int first_fail = fb ? __ffs(fb) - 1 : 32;
+          if (!decided && lane < first_fail) { admitted = true; decided = true; }
+          if (!decided && lane == first_fail) decided = true;
+          const int used_now = first_fail > 0 ? __shfl_sync(FULL, inc, first_fail - 1) : 0;
+          free_gpu -= used_now;
+        }
+        const bool flip_run = valid && admitted && r.status == PST_PENDING;
+        const bool flip_pre = valid && !admitted && r.status == PST_RUNNING;
+        if (flip_run) { r.status = PST_RUNNING; r.resume += 1; if (r.start < 0) r.start = event_time; pj[j] = r; }
+        if (flip_pre) { r.status = PST_PENDING; pj[j] = r; }
+        events += __popc(__ballot_sync(FULL, flip_run)) + __popc(__ballot_sync(FULL, flip_pre));
+        busy += __reduce_add_sync(FULL, admitted ? g : 0);
+        long long mc = admitted ? (long long)g * (jr.memb < cap_bytes ? jr.memb : cap_bytes) : 0;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mc += __shfl_xor_sync(FULL, mc, o);
+        mem_busy += mc;
+      }
+    }
+    __syncwarp();
+    // ---- final pass: next completion (ties in list order) and statistics
+    end_time = 0x7fffffff; en = 0;
+    int running = 0, queued = 0, pmax = 0;
+    long long psum = 0;
+    for (int base = 0; base < rn; base += 32) {
+      const int idx = base + lane;
+      const bool valid = idx < rn;
+      const int j = valid ? runnable[idx] : 0;
+      int e = 0x7fffffff, pend = 0;
+      bool isrun = false;
+      if (valid) {
+        const PJob r = pj[j];
+        isrun = r.status == PST_RUNNING;
+        if (isrun) {
+          const double cl = ceil(jobs[j].dur);
+          const int D = cl < 1.0 ? 1 : (int)cl;
+          e = event_time + (D - r.total_exec);
+        } else pend = r.pending;
+      }
+      const int cmin = __reduce_min_sync(FULL, e);
+      if (cmin < end_time) { end_time = cmin; en = 0; }
+      const unsigned eb = __ballot_sync(FULL, valid && isrun && e == end_time);
+      if (valid && isrun && e == end_time) endj[en + __popc(eb & lt)] = j;
+      en += __popc(eb);
+      running += __popc(__ballot_sync(FULL, valid && isrun));
+      queued += __popc(__ballot_sync(FULL, valid && !isrun));
+      pmax = max(pmax, __reduce_max_sync(FULL, pend));
+      psum += (long long)__reduce_add_sync(FULL, pend);
+    }
+    if (!sjf) next_git += (double)event_time;
+    int busy_nodes = 0;
+    if (sjf) for (int base = 0; base < M; base += 32) { const int nd = base + lane; busy_nodes += __popc(__ballot_sync(FULL, nd < M && nidle[nd] < G)); }
+    __syncwarp();
+    if (lane == 0) {
+      int4 *dst = reinterpret_cast<int4 *>(&S.rows[ticks - row_first]);
+      dst[0] = make_int4(event_time, M - busy_nodes, busy_nodes, busy);
+      dst[1] = make_int4(total_gpus - busy, running, queued, nfin);
+      dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(psum & 0xffffffffLL), (int)(psum >> 32));
+      dst[3] = make_int4(pmax, 0, 0, 0);
+    }
+    ticks += 1; budget -= 1;
+  }
+  if (!done && !((n - p) + rn > 0)) done = true;
+  if (!done && p >= n && end_time == 0x7fffffff) done = true;
+  __syncwarp();
+  if (done) {
+    for (int j = lane; j < n; j += 32) { const PJob r = pj[j]; if (r.status != PST_END && r.status != PST_NONE && r.start >= 0) { rec[j].start = r.start; rec[j].preempt = r.resume; } }
+  }
+  if (lane == 0) {
+    S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.finished = nfin; S.next_gittins_unit = next_git;
     S.events = events; S.ticks = ticks; S.row_first = row_first;
     S.done = done ? 1 : 0; S.running = 0; S.top = 0; S.started = 0;
   }
@@ -1990,7 +2295,12 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
     if (!thread_dlas) {
       gs_dlas_warp_kernel<<<(unsigned)h->nsims, 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks);
       CU(cudaGetLastError());
-      h->launches += 1;
+      const size_t pol_smem = 8 * (size_t)maxM;
+      if (pol_smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(gs_sortpol_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pol_smem));
+      gs_sortpol_warp_kernel<<<(unsigned)h->nsims, 32, pol_smem, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks);
+      CU(cudaGetLastError());
+      h->launches += 2;
     }
   }
   if (!any_fifo) {

@@ -19,9 +19,10 @@ def _policy(name, table):
                             gittins_table=policies.build_gittins_table(policies.gittins_samples(table), 3250.0))
 
 
-def _run(cluster, policy, table, rows_cap=0):
+def _run(cluster, policy, table, rows_cap=0, engine=0):
     from gpuschedule_b200 import capi
     with capi.Engine(device=0, nsims=1) as eng:
+        eng.set_engine(engine)            # 0: warp-cooperative kernels, 2: thread-per-replica fallback
         eng.config(0, cluster, policy)
         eng.load_trace(0, table)
         rows = eng.run_all(rows_cap=rows_cap)[0]
@@ -54,6 +55,9 @@ def test_policy_engine_matches_oracle(name, cfg):
     # window resume gives the same answer
     rows2, recs2, order2, st2 = _run(cluster, pol, table, rows_cap=53)
     assert rows2.tobytes() == ref.rows.tobytes() and recs2.tobytes() == ref.recs.tobytes()
+    # and so does the thread-per-replica fallback kernel
+    rows3, recs3, order3, st3 = _run(cluster, pol, table, engine=2)
+    assert rows3.tobytes() == ref.rows.tobytes() and recs3.tobytes() == ref.recs.tobytes() and st3.events == ref.events
 
 
 def test_policy_invariants():
