@@ -345,6 +345,47 @@ def ours(args):
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
            "checksum": checksum}
 
+    # ---- secondary measurements (rank 0, N=1): the event-driven policies of BASELINE configs 1-3 on
+    # the same cluster (device-timed, 1 warm-up + 1 timed run each) and the stateless scoring kernel
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = {}
+        rp = min(R, args.policy_replicas)
+        for name, njobs in (("sjf", min(n, 10000)), ("dlas-gpu", n), ("gittins", n)):
+            tabs = tables[:rp] if njobs == n else [fast_table(njobs, sd) for sd in gdist.replica_seeds(0, 1, rp, base=BASE_SEED)]
+            if name == "gittins":
+                tabs = tabs[:max(1, rp // 2)]
+            save = args.policy
+            args.policy = name
+            pl = [policy_for(t) for t in tabs]
+            args.policy = save
+            with capi.Engine(device=local, nsims=len(tabs)) as pe:
+                for i, t in enumerate(tabs):
+                    pe.config(i, cluster, pl[i])
+                    pe.load_trace_packed(i, t.packed())
+                run_to_done(pe, 0)
+                cap = max(pe.stats(i).ticks for i in range(len(tabs))) + 64
+                pe.reset()
+                run_to_done(pe, cap)
+                ms = pe.stats(0).kernel_ms
+                ev = sum(pe.stats(i).events for i in range(len(tabs)))
+            extras[name] = {"value": ev / (ms / 1e3), "unit": UNIT, "ms": ms, "replicas": len(tabs), "jobs_per_replica": njobs,
+                            "kernel": "gs_dlas_warp_kernel" if name == "dlas-gpu" else "gs_sortpol_warp_kernel",
+                            "parity": "engine == oracle/policy_oracle.c; unpinned vs the reference (dead code there)"}
+        try:
+            import contextlib
+            import io
+            buf = io.StringIO()
+            pa = argparse.Namespace(place_jobs=16 * 1024 * 1024, warmup=2, steps=3)
+            with contextlib.redirect_stdout(buf):
+                place_mode(pa)
+            pj = json.loads(buf.getvalue().strip().splitlines()[-1])
+            extras["place_batch"] = {"value": pj["value"], "unit": pj["unit"], "kernel_ms": pj["kernel_ms"], "jobs": pj["jobs"],
+                                     "candidate_evals_per_s": pj["candidate_evals_per_s"], "roofline_frac": pj["roofline"]["frac"],
+                                     "achieved_gbs": pj["roofline"]["achieved"]}
+        except Exception as exc:
+            extras["place_batch"] = {"error": str(exc)}
+
     # ---- CPU baseline: the oracle port, 1 thread, bounded sample (rank 0, N=1 only)
     cpu = None
     cpu_tight = None
@@ -386,7 +427,7 @@ def ours(args):
                        "events_per_step": events_all, "ticks_per_step": ticks_rank * world},
             "wall_ms_per_step": wall_ms / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_tight": cpu_tight,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_tight": cpu_tight, "secondary": extras,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -512,6 +553,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
+    ap.add_argument("--policy-replicas", type=int, default=1024)
     ap.add_argument("--span-budget", type=float, default=0.0,
                     help="span-pool records per job (0 = worst case); the trace uses ~1.13")
     ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],

@@ -99,3 +99,29 @@ def test_mixed_policies_in_one_handle():
             assert rows[i].tobytes() == ref.rows.tobytes(), (i, nm)
             assert recs.tobytes() == ref.recs.tobytes(), (i, nm)
             assert np.array_equal(order, ref.finish_order), (i, nm)
+
+
+def test_cli_runs_an_event_driven_policy(tmp_path):
+    """run_sim.py --schedule dlas-gpu end to end: files written, rows/jobs equal the oracle's."""
+    import glob
+    import os
+    import subprocess
+    import sys
+    import oracle
+    from conftest import REPO
+    from gpuschedule_b200 import capi, ingest, log_manager, tracegen
+    df = tracegen.synth_frame(400, seed=31, rate=0.9, gpu_choices=[1, 2, 4, 8], gpu_probs=[.4, .3, .2, .1])
+    df.to_csv(tmp_path / "trace.csv", index=False)
+    cmd = [sys.executable, os.path.join(REPO, "run_sim.py"), "--num_switch", "1", "--num_node_p_switch", "8",
+           "--scheme", "yarn", "--schedule", "dlas-gpu", "--num_queue", "4", "--queue_limit", "300,900,3000",
+           "--trace_file", "trace.csv", "--log_path", "p"]
+    subprocess.run(cmd, cwd=tmp_path, check=True, capture_output=True)
+    runs = glob.glob(str(tmp_path / "log" / "p" / "*"))
+    assert len(runs) == 1
+    table = ingest.JobTraceReader(str(tmp_path / "trace.csv")).prepare_jobs().table(0.5)
+    cluster = capi.make_cluster(1, 8, 8)
+    ref = oracle.run_policy(cluster, capi.make_policy("dlas-gpu", num_queue=4, queue_limit=[300, 900, 3000]), table)
+    exp_jobs = log_manager.render_job_csv(table, ref.recs, ref.finish_order)
+    assert open(os.path.join(runs[0], "job.csv"), newline="").read() == exp_jobs
+    got_rows = open(os.path.join(runs[0], "cluster.csv"), newline="").read().split("\r\n")
+    assert len(got_rows) == ref.ticks + 2 and got_rows[1].split(",")[0] == str(int(ref.rows["now"][0]))
