@@ -244,6 +244,14 @@ def ours(args):
     events_all = sum_over_ranks(events_rank)
     value = events_all / (dev_ms / args.steps / 1e3)
 
+    if args.value_only:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": dev_ms / args.steps, "replicas_per_gpu": R}), flush=True)
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- roofline of the dominant kernel (gs_tick_kernel), per launch, this rank's GPU
     # algorithmic bytes: job table in (28 B/job) + job record + finish order out (28 B/job)
     # + one 16-B span per (job,node) + one 64-B statistics row per tick   
@@ -547,12 +555,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--jobs", type=int, default=100000)
-    ap.add_argument("--replicas", type=int, default=2960, help="replicas per GPU (one warp each)")
+    ap.add_argument("--replicas", type=int, default=3552, help="replicas per GPU (one warp each)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-threads", type=int, default=16, help="host threads (one engine handle each) in the e2e run")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true", help="kernel experiments: print the device-timed value and stop")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
     ap.add_argument("--policy-replicas", type=int, default=1024)
     ap.add_argument("--span-budget", type=float, default=0.0,

@@ -16,7 +16,7 @@ SCHEDULES = {"fifo": 0, "sjf": 1, "dlas": 2, "dlas-gpu": 3, "gittins": 4}
 SCHEMES = {"yarn": 0, "count": 1}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsched.so")
+LIB_PATH = os.environ.get("GSCHED_LIB", os.path.join(_HERE, "libgsched.so"))   # override: build experiments only
 
 
 class GsCluster(C.Structure):

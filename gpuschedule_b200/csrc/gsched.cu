@@ -41,6 +41,9 @@
 
 #include "gsched.h"
 
+#ifndef GS_TICK_MINBLOCKS
+#define GS_TICK_MINBLOCKS 24
+#endif
 #define FULL 0xffffffffu
 // ballot over the lanes of one replica group, bit 0 = the group's first lane (needs GM, gbase, SUB in scope)
 #define GBALLOT(pred) ((SUB == 32) ? __ballot_sync(GM, (pred)) : ((__ballot_sync(GM, (pred)) >> gbase) & ((1u << SUB) - 1u)))
@@ -140,7 +143,7 @@ __device__ __forceinline__ unsigned long long take_lowest(unsigned long long idl
 // from a register-resident 32-record window of the trace, so the loop body has no dependent
 // DRAM/L2 round trip in the common case.
 template <int SUB>
-__global__ void __launch_bounds__(32, 20) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
+__global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
   // SUB lanes own one replica: 32 = a whole warp, 16 = two replicas per warp sharing the
   // (mostly warp-uniform) instruction stream.  Every collective uses the group's own lane
   // mask, so the groups of a warp may diverge freely.
