@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
   JobIn wj;
   wj.arrive = 0x7fffffff; wj.gpus = 1; wj.gpc = 1; wj.ps = 0; wj.memb = 0; wj.dur = 0.0;
   if (wbase + lane < n) wj = jobs[wbase + lane];
+  // arrival tick of the next trace record: most ticks admit nothing and only compare this scalar
+  int next_arr = 0x7fffffff;
+  if (p < n) next_arr = __shfl_sync(GM, wj.arrive, gbase + (p - wbase));
 
   // queue head (cached while it stays the head)
   int head = -1, hg = 1, hgpc = 1, htasks = 1, hps = 0, harr = 0;
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
 
   while (!done && tick_i < budget && status == 0) {
     // ---------------- A. admit arrivals (gen_jobs + head insert)
-    {
+    if (next_arr <= delta) {
       int cnt = 0, q = p;
       while (q < n) {
         const int idx = wbase + lane;
@@ -254,6 +257,8 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
         sum_arr += (long long)cnt * delta;
         __syncwarp(GM);
       }
+      next_arr = 0x7fffffff;
+      if (p < n) next_arr = __shfl_sync(GM, wj.arrive, gbase + (p - wbase));
     }
     // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
     com_j = -1;
