@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
   const int wmask = S.wheel_mask;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
   const int netcost = S.netcost;
+  const long long span_cap = S.span_cap;      // SimDev lives in global memory: keep loop-invariant fields in registers
+  int2 *sref = S.sref;
   const unsigned long long gmask = (G >= 64) ? ~0ull : ((1ull << G) - 1ull);
 
   int delta = S.delta, p = S.p, top = S.top, running = S.running, finished = S.finished;
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
           }
           if (b) { found = base + __ffs(b) - 1; break; }
         }
-        if (found >= 0 && span_used + 1 > S.span_cap) { status = GS_ERR_CAPACITY; found = -1; }
+        if (found >= 0 && span_used + 1 > span_cap) { status = GS_ERR_CAPACITY; found = -1; }
         if (found >= 0) {
           ok = true; first_node = found; nspans = 1;
           bool fresh = false;
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
             if (nd < M && meta_cap((unsigned)kk[nd], hgpc) > 0) kk[nd] -= 1 << 16;
           }
         }
-        if (last_base >= 0 && span_used + min(htasks, M) > S.span_cap) { status = GS_ERR_CAPACITY; last_base = -1; }
+        if (last_base >= 0 && span_used + min(htasks, M) > span_cap) { status = GS_ERR_CAPACITY; last_base = -1; }
         if (last_base >= 0) {
           // pass 1 proved the job fits: commit (a failed walk is rolled back exactly by the
           // reference, algorithm.py:378-387, so no state changes in that case)
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
           gs_job_rec r; r.start = delta; r.end = endt; r.jct = need; r.preempt = 1; r.duration = dur2;
           rec[j] = r;
           jst[j] = js;
-          S.sref[j] = make_int2(span_first, nspans);
+          sref[j] = make_int2(span_first, nspans);
           if (tl >= 0) jst[tl].next = j;
         }
         top -= 1;
@@ -1149,6 +1151,9 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
   PJob *pj = S.pj;
   int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
   gs_job_rec *rec = S.rec;
+  int *fin = S.fin, *queues = S.queues;
+  gs_tick_row *rows = S.rows;
+  const long long rows_cap = S.rows_cap;
   const long long cap_bytes = S.cap_bytes;
   const int total_gpus = M * G;
   const unsigned lt = (1u << lane) - 1u;
@@ -1164,7 +1169,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
   long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
   bool done = false;
 
-  while (budget > 0 && (ticks - row_first) < S.rows_cap) {
+  while (budget > 0 && (ticks - row_first) < rows_cap) {
     if (!((n - p) + rn > 0)) { done = true; break; }
     if (p >= n && end_time == 0x7fffffff) { done = true; break; }
     const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
@@ -1184,7 +1189,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
         const double cl = ceil(dur);
         gs_job_rec o; o.start = r.start; o.end = event_time; o.jct = cl < 1.0 ? 1 : (int)cl; o.preempt = r.resume; o.duration = dur;
         rec[j] = o;
-        S.fin[nfin + i] = j;
+        fin[nfin + i] = j;
       }
       nfin += en; events += en;
     }
@@ -1204,7 +1209,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
         r.resume = 0; r.status = PST_PENDING; r.q_id = 0; r.pad0 = 0; r.pad1 = 0;
         pj[j] = r;
         runnable[rn + i] = j;
-        S.queues[qn[0] + i] = j;
+        queues[qn[0] + i] = j;
       }
       rn += cnt; qn[0] += cnt; events += cnt; p += cnt;
     }
@@ -1244,7 +1249,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
     __syncwarp();
     // ---- queues: drop END / demoted-away entries, then append this event's demotions
     for (int q = 0; q < nq; ++q) {
-      int *qv = S.queues + (size_t)q * n;
+      int *qv = queues + (size_t)q * n;
       int w = 0;
       for (int base = 0; base < qn[q]; base += 32) {
         const int idx = base + lane;
@@ -1275,7 +1280,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
     int free_gpu = total_gpus, busy = 0;
     long long mem_busy = 0;
     for (int q = 0; q < nq; ++q) {
-      int *qv = S.queues + (size_t)q * n;
+      int *qv = queues + (size_t)q * n;
       int w = 0, pn = 0;   // RUNNING entries written so far / PENDING entries parked in tmpl
       for (int base = 0; base < qn[q]; base += 32) {
         const int idx = base + lane;
@@ -1364,7 +1369,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
     }
     __syncwarp();
     if (lane == 0) {
-      int4 *dst = reinterpret_cast<int4 *>(&S.rows[ticks - row_first]);
+      int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
       dst[0] = make_int4(event_time, M, 0, busy);
       dst[1] = make_int4(total_gpus - busy, running, queued, nfin);
       dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(psum & 0xffffffffLL), (int)(psum >> 32));
@@ -1410,6 +1415,9 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
   double *rk = reinterpret_cast<double *>(S.queues);     // gittins: rank of runnable[i] (no queues in these policies)
   gs_job_rec *rec = S.rec;
+  int *fin = S.fin, *queues = S.queues;
+  gs_tick_row *rows = S.rows;
+  const long long rows_cap = S.rows_cap;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
   const int total_gpus = M * G;
   const unsigned lt = (1u << lane) - 1u;
@@ -1420,7 +1428,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
   bool done = false;
 
-  while (budget > 0 && (ticks - row_first) < S.rows_cap) {
+  while (budget > 0 && (ticks - row_first) < rows_cap) {
     if (!((n - p) + rn > 0)) { done = true; break; }
     if (p >= n && end_time == 0x7fffffff) { done = true; break; }
     const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
@@ -1440,7 +1448,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         const double cl = ceil(dur);
         gs_job_rec o; o.start = r.start; o.end = event_time; o.jct = cl < 1.0 ? 1 : (int)cl; o.preempt = r.resume; o.duration = dur;
         rec[j] = o;
-        S.fin[nfin + i] = j;
+        fin[nfin + i] = j;
       }
       nfin += en; events += en;
     }
@@ -1671,7 +1679,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     if (sjf) for (int base = 0; base < M; base += 32) { const int nd = base + lane; busy_nodes += __popc(__ballot_sync(FULL, nd < M && nidle[nd] < G)); }
     __syncwarp();
     if (lane == 0) {
-      int4 *dst = reinterpret_cast<int4 *>(&S.rows[ticks - row_first]);
+      int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
       dst[0] = make_int4(event_time, M - busy_nodes, busy_nodes, busy);
       dst[1] = make_int4(total_gpus - busy, running, queued, nfin);
       dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(psum & 0xffffffffLL), (int)(psum >> 32));
