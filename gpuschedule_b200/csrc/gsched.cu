@@ -216,9 +216,6 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
   bool head_valid = false;
   int bottom_arr = (top > 0) ? stack[0].y : 0;
 
-  // release record of the job committed this tick (saves the reload when it finishes at once)
-  int com_j = -1;
-  JobState com_js; com_js.next = -1; com_js.node0 = 0; com_js.mask0 = 0; com_js.memc = 0; com_js.gpus = 0; com_js.cnt_gpc = 1;
 
   bool done = (n == 0);
 
@@ -247,10 +244,14 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
       }
       if (cnt > 0) {
         // batch [p, p+cnt) lands AHEAD of the queue, first of the batch on top (quirk Q2)
-        for (int i = lane; i < cnt; i += SUB) {
-          const int2 e = make_int2(p + cnt - 1 - i, delta);
-          stack[top + i] = e;
-          if (i >= cnt - SCACHE) sstk[(top + i) & (SCACHE - 1)] = e;
+        if (cnt == 1) {
+          if (lane == 0) { const int2 e = make_int2(p, delta); stack[top] = e; sstk[top & (SCACHE - 1)] = e; }
+        } else {
+          for (int i = lane; i < cnt; i += SUB) {
+            const int2 e = make_int2(p + cnt - 1 - i, delta);
+            stack[top + i] = e;
+            if (i >= cnt - SCACHE) sstk[(top + i) & (SCACHE - 1)] = e;
+          }
         }
         if (top == 0) bottom_arr = delta;
         head = p; head_valid = true; htasks = hgpc == 1 ? hg : hg / hgpc;
@@ -263,7 +264,6 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
       if (p < n) next_arr = __shfl_sync(GM, wj.arrive, gbase + (p - wbase));
     }
     // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
-    com_j = -1;
     if (top > 0) {
       if (!head_valid) {
         if (top - 1 >= cache_lo) head = sstk[(top - 1) & (SCACHE - 1)].x;
@@ -402,7 +402,6 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
         const long long memc = (long long)hg * (hmemb < cap_bytes ? hmemb : cap_bytes);
         JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first; js.mask0 = mask0;
         js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
-        com_j = j; com_js = js;
         // append to the finish-tick bucket of the timing wheel (start order)
         const int gs_ = endt & wmask;
         const int tl = gwt[gs_];
@@ -433,9 +432,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
         __syncwarp(GM);
         if (lane == 0) { gwh[sl] = -1; gwt[sl] = -1; }
         while (h >= 0) {
-          JobState js;
-          if (h == com_j) js = com_js;
-          else js = jst[h];
+          const JobState js = jst[h];
           const int scnt = JS_CNT(js.cnt_gpc), sgpc = JS_GPC(js.cnt_gpc);
           if (scnt == 1) {
             if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] += js.gpus + ((sgpc == 1 ? js.gpus : js.gpus / sgpc) << 16); }
