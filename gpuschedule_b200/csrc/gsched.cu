@@ -60,6 +60,9 @@ struct __align__(16) JobState {   // 32 B, written at start, read once at comple
 };
 #define JS_CNT(x) ((x) & 0xffffff)
 #define JS_GPC(x) ((int)((unsigned)(x) >> 24))
+// JobState.gpus: gpus (bits 0-23) | tasks of a single-span job (bits 24-31, <= 64 because gpus <= G <= 64 there)
+#define JS_GPUS(x) ((x) & 0xffffff)
+#define JS_NT0(x) ((int)((unsigned)(x) >> 24))
 
 struct __align__(32) JobIn {   // 32 B = one DRAM sector per job, read once in admission order
   int arrive;       // first tick with normalized_time <= tick
@@ -123,6 +126,7 @@ __device__ __forceinline__ int meta_cap(unsigned mt, int gpc) {
 
 __device__ __forceinline__ unsigned long long take_lowest(unsigned long long idle, int cnt, int G) {
   // the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
+  if (cnt == 1) return idle & (~idle + 1ull);
   if (G <= 32) {
     unsigned m = (unsigned)idle;
     if (cnt >= __popc(m)) return idle;
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
         span_used += nspans;
         const long long memc = (long long)hg * (hmemb < cap_bytes ? hmemb : cap_bytes);
         JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first; js.mask0 = mask0;
-        js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
+        js.memc = memc; js.gpus = hg | ((nspans == 1 ? htasks : 0) << 24); js.cnt_gpc = nspans | (hgpc << 24);
         // append to the finish-tick bucket of the timing wheel (start order)
         const int gs_ = endt & wmask;
         const int tl = gwt[gs_];
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
           const JobState js = jst[h];
           const int scnt = JS_CNT(js.cnt_gpc), sgpc = JS_GPC(js.cnt_gpc);
           if (scnt == 1) {
-            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] += js.gpus + ((sgpc == 1 ? js.gpus : js.gpus / sgpc) << 16); }
+            if (lane == 0) { busy[js.node0] &= ~js.mask0; kk[js.node0] += JS_GPUS(js.gpus) + (JS_NT0(js.gpus) << 16); }
           } else {
             for (int i = lane; i < scnt; i += SUB) {
               const gs_span sp = spans[js.node0 + i];
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
           }
           if (lane == 0) fin[finished] = h;
           finished += 1; running -= 1;
-          busy_gpus -= js.gpus;
+          busy_gpus -= JS_GPUS(js.gpus);
           mem_busy -= js.memc;
           h = js.next;
         }
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick_kernel(SimDev *
       if (lane == 0) {
         int4 *dst = rowp;
         const int tg = M * G;
-        const long long ps = (long long)top * now - sum_arr;
+        const long long ps = top > 0 ? (long long)top * now - sum_arr : 0;
         dst[0] = make_int4(now, M - ever, ever, busy_gpus);
         dst[1] = make_int4(tg - busy_gpus, running, top, finished);
         dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(ps & 0xffffffffLL), (int)(ps >> 32));
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, lo
           sref[j] = make_int2(span_first, nspans);
           const long long memc = (long long)hg * (hj.memb < cap_bytes ? hj.memb : cap_bytes);
           JobState js; js.next = -1; js.node0 = nspans == 1 ? first_node : span_first;
-          js.mask0 = (unsigned long long)mask0; js.memc = memc; js.gpus = hg; js.cnt_gpc = nspans | (hgpc << 24);
+          js.mask0 = (unsigned long long)mask0; js.memc = memc; js.gpus = hg | ((nspans == 1 ? htasks : 0) << 24); js.cnt_gpc = nspans | (hgpc << 24);
           jst[j] = js;
           com_j = j; com_js = js;
           // append to the finish-tick bucket (start order): window / pending register / global wheel
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, lo
               const int nd = js.node0;
               mlo[nd * L] &= ~(uint32_t)js.mask0;
               if (sizeof(MaskT) == 8) mhi[nd * L] &= ~(uint32_t)(js.mask0 >> 32);
-              meta[nd * L] += (uint32_t)js.gpus + ((uint32_t)(sgpc == 1 ? js.gpus : js.gpus / sgpc) << 16);
+              meta[nd * L] += (uint32_t)JS_GPUS(js.gpus) + ((uint32_t)JS_NT0(js.gpus) << 16);
               if (nd < lo) lo = nd;
             } else {
               for (int i = 0; i < scnt; ++i) {
@@ -812,7 +816,7 @@ __global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, lo
             }
             fin[finished] = h;
             finished += 1; running -= 1;
-            busy_gpus -= js.gpus;
+            busy_gpus -= JS_GPUS(js.gpus);
             mem_busy -= js.memc;
             h = js.next;
           } while (h >= 0);
@@ -829,7 +833,7 @@ __global__ void __launch_bounds__(32) gs_lane_kernel(SimDev *sims, int nsims, lo
         }
         int4 *dst = reinterpret_cast<int4 *>(&rows[ticks - row_first]);
         const int tg = M * G;
-        const long long ps = (long long)top * now - sum_arr;
+        const long long ps = top > 0 ? (long long)top * now - sum_arr : 0;
         dst[0] = make_int4(now, M - ever, ever, busy_gpus);
         dst[1] = make_int4(tg - busy_gpus, running, top, finished);
         dst[2] = make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), (int)(ps & 0xffffffffLL), (int)(ps >> 32));
@@ -2167,8 +2171,8 @@ static int load_common(gs_handle h, int sim, int64_t n, const JobIn *packed, con
     }
     if (r.arrive < prev) return fail(h, GS_ERR_ARG, "gs_load_trace: arrive_tick must be non-negative and non-decreasing");
     prev = r.arrive;
-    if (r.gpc <= 0 || r.gpus < r.gpc || r.gpus % r.gpc != 0)
-      return fail(h, GS_ERR_ARG, "gs_load_trace: gpus must be a positive multiple of gpu_per_task (job.py:96-100)");
+    if (r.gpc <= 0 || r.gpus < r.gpc || r.gpus % r.gpc != 0 || r.gpus >= (1 << 24) || r.gpc > 255)
+      return fail(h, GS_ERR_ARG, "gs_load_trace: gpus must be a positive multiple of gpu_per_task below 2^24 (job.py:96-100)");
     if (r.memb < 0) return fail(h, GS_ERR_ARG, "gs_load_trace: negative mem_bytes");
     if (!(r.dur == r.dur)) return fail(h, GS_ERR_ARG, "gs_load_trace: NaN duration");
     const int64_t tasks = r.gpus / r.gpc;
