@@ -8,12 +8,29 @@ divides by the GPU count (/root/reference/infra/device.py:48-54,
 numpy's global legacy MT19937 stream, which is sequential by construction, so
 this column stays on the host.  The engine supplies where every
 job ran (gs_span records) and when (start/end); this module rebuilds the
-per-tick ordered device list and replays the stream with ONE vectorised call,
-which consumes the stream exactly like the per-device size=1 calls do.
+per-tick ordered device list and replays the stream with ONE vectorised call
+per chunk of rows, which consumes the stream exactly like the per-device
+size=1 calls do.  Everything is vectorised numpy: a (rows x devices) owner grid
+per chunk is a running sum of +owner / -owner marks at interval starts / stops, the
+sequential per-row accumulation runs column-wise, and the text is produced with
+numpy's own dragon4 formatter.
 """
 from __future__ import annotations
 
 import numpy as np
+
+
+def _holdings(recs, span_off, spans, gpus_per_node):
+    """One entry per (job, device): job index, device key = node * G + dev."""
+    n = len(recs)
+    if len(spans) == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z
+    span_job = np.repeat(np.arange(n, dtype=np.int64), np.diff(span_off))
+    masks = np.ascontiguousarray(spans["devmask"], dtype="<u8")
+    bits = np.unpackbits(masks.view(np.uint8).reshape(-1, 8), axis=1, bitorder="little")   # (spans, 64)
+    si, dev = np.nonzero(bits)
+    return span_job[si], spans["node"][si].astype(np.int64) * gpus_per_node + dev.astype(np.int64)
 
 
 def busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans, chunk_rows=2048):
@@ -22,47 +39,52 @@ def busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans, chunk
     Row r (0-based) is the statistics row written with delta == r + 1; job j is
     counted there iff start_j <= r and (end_j < 0 or end_j > r + 1).
     """
-    G = gpus_per_node
-    width = n_nodes * G
-    start = recs["start"]
-    end = recs["end"]
-    started = np.nonzero(start >= 0)[0]
-    # one entry per (job, device): key = node * G + dev
-    hold_job, hold_key = [], []
-    for j in started:
-        for s in spans[span_off[j]:span_off[j + 1]]:
-            mask = int(s["devmask"])
-            base = int(s["node"]) * G
-            d = 0
-            while mask:
-                if mask & 1:
-                    hold_job.append(j)
-                    hold_key.append(base + d)
-                mask >>= 1
-                d += 1
-    hold_job = np.asarray(hold_job, dtype=np.int64)
-    hold_key = np.asarray(hold_key, dtype=np.int64)
-    first = start[hold_job].astype(np.int64)                       # first row counted
-    last = np.where(end[hold_job] < 0, n_rows - 1, end[hold_job].astype(np.int64) - 2)
+    width = n_nodes * gpus_per_node
+    hold_job, hold_key = _holdings(recs, span_off, spans, gpus_per_node)
+    start = recs["start"][hold_job].astype(np.int64)
+    end = recs["end"][hold_job]
+    keep = start >= 0
+    hold_job, hold_key, start, end = hold_job[keep], hold_key[keep], start[keep], end[keep]
+    first = start                                                   # first row counted
+    last = np.where(end < 0, n_rows - 1, end.astype(np.int64) - 2)  # last row counted
+    live = last >= first
+    hold_job, hold_key, first, last = hold_job[live], hold_key[live], first[live], last[live]
     order = np.argsort(first, kind="stable")
     hold_job, hold_key, first, last = hold_job[order], hold_key[order], first[order], last[order]
     lo_ptr = 0
-    active = np.zeros(0, dtype=np.int64)                           # indices into hold_* still open
+    active = np.zeros(0, dtype=np.int64)                            # holdings still open
     for r0 in range(0, n_rows, chunk_rows):
         r1 = min(n_rows, r0 + chunk_rows)
         hi_ptr = int(np.searchsorted(first, r1, side="left"))
         cand = np.concatenate([active, np.arange(lo_ptr, hi_ptr, dtype=np.int64)])
         lo_ptr = hi_ptr
         cand = cand[last[cand] >= r0]
-        grid = np.full((r1 - r0, width), -1, dtype=np.int64)
-        for h in cand:
-            a = max(int(first[h]), r0) - r0
-            b = min(int(last[h]), r1 - 1) - r0 + 1
-            if b > a:
-                grid[a:b, hold_key[h]] = hold_job[h]
+        rows_n = r1 - r0
+        # +(job+1) where a holding starts (or continues into the chunk), -(job+1) on the first row after it;
+        # devices host one job at a time, so a running sum down each column is the owner (+1), 0 = idle
+        marks = np.zeros((rows_n + 1, width), dtype=np.int32)
+        a = np.maximum(first[cand], r0) - r0
+        b = np.minimum(last[cand], r1 - 1) - r0 + 1                 # first row after the holding (<= rows_n)
+        val = (hold_job[cand] + 1).astype(np.int32)
+        np.add.at(marks, (a, hold_key[cand]), val)
+        np.add.at(marks, (b, hold_key[cand]), -val)
+        filled = np.cumsum(marks[:rows_n], axis=0, dtype=np.int32)
+        busy = filled > 0
         active = cand[last[cand] >= r1]
-        busy = grid >= 0
-        yield busy.sum(axis=1), grid[busy]
+        yield busy.sum(axis=1), filled[busy].astype(np.int64) - 1
+
+
+def _format_bracketed(values):
+    """str(np.array([v])) for every v, fast: numpy prints a 1-element float64 array with the dragon4
+    positional formatter (precision 8, unique, trim '.') unless the value calls for exponent form."""
+    out = []
+    fmt = np.format_float_positional
+    for v in values:
+        if v != 0.0 and (v < 1e-4 or v >= 1e8):
+            out.append(str(np.array([v])))                          # exponent notation: leave it to numpy
+        else:
+            out.append("[" + fmt(v, precision=8, unique=True, fractional=True, trim=".") + "]")
+    return out
 
 
 def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, spans, rng=None):
@@ -70,11 +92,11 @@ def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, span
     normal = np.random.normal if rng is None else rng.normal
     total = n_nodes * gpus_per_node
     out = []
+    loc_all = table.util_avg
+    scale_all = (table.util_max - table.util_avg) / 2
     for counts, jobs in busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans):
         if len(jobs):
-            loc = table.util_avg[jobs]
-            scale = (table.util_max[jobs] - table.util_avg[jobs]) / 2
-            draw = normal(loc=loc, scale=scale)
+            draw = normal(loc=loc_all[jobs], scale=scale_all[jobs])
         else:
             draw = np.zeros(0)
         clipped = draw >= 100.0          # min(100, x) returns the int 100 unless x < 100
@@ -82,17 +104,18 @@ def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, span
         off = np.zeros(len(counts) + 1, dtype=np.int64)
         np.cumsum(counts, out=off[1:])
         acc = np.zeros(len(counts), dtype=np.float64)
-        for k in range(int(counts.max()) if len(counts) else 0):   # sequential per-row accumulation
-            sel = np.nonzero(counts > k)[0]
+        order = np.argsort(-counts, kind="stable")                  # rows with many busy devices first
+        sorted_counts = counts[order]
+        for k in range(int(sorted_counts[0]) if len(counts) else 0):   # sequential per-row accumulation
+            m = int(np.searchsorted(-sorted_counts, -k, side="left"))  # rows with count > k
+            sel = order[:m]
             acc[sel] = acc[sel] + vals[off[sel] + k]
-        n_arr = np.add.reduceat(np.concatenate([~clipped, [False]]).astype(np.int64),
-                                np.minimum(off[:-1], len(clipped)))
-        n_arr = np.where(counts > 0, n_arr, 0)
-        for i in range(len(counts)):
-            if counts[i] == 0:
-                out.append("0.0")                                   # 0 / n  -> float 0.0
-            elif n_arr[i] > 0:
-                out.append(str(np.array([acc[i] / total])))         # numpy 1-element array
-            else:
-                out.append(repr(float(int(acc[i]) / total)))        # every draw clipped: plain ints
+        csum = np.concatenate([[0], np.cumsum(~clipped)])
+        n_arr = csum[off[1:]] - csum[off[:-1]]                      # un-clipped draws per row (numpy arrays)
+        frac = acc / total
+        brack = _format_bracketed(frac)
+        # no busy device: 0 / n -> float 0.0;  some un-clipped draw: numpy 1-element array;
+        # every draw clipped at the int 100: plain Python numbers
+        out.extend("0.0" if c == 0 else (bk if na > 0 else repr(float(int(ac) / total)))
+                   for c, na, bk, ac in zip(counts.tolist(), n_arr.tolist(), brack, acc.tolist()))
     return out
