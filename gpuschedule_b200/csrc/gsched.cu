@@ -1413,10 +1413,10 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   int *nkfree = nidle + M;
   const JobIn *__restrict__ jobs = S.jobs;
   PJob *pj = S.pj;
-  int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
+  int *runnable = S.runnable, *endj = S.endj;
   double *rk = reinterpret_cast<double *>(S.queues);     // gittins: rank of runnable[i] (no queues in these policies)
   gs_job_rec *rec = S.rec;
-  int *fin = S.fin, *queues = S.queues;
+  int *fin = S.fin;
   gs_tick_row *rows = S.rows;
   const long long rows_cap = S.rows_cap;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
