@@ -258,15 +258,17 @@ def ours(args):
     alg_bytes = R * n * 56 + spans_rank * 16 + ticks_rank * 64
     peak, peak_src = peaks()
     ach = alg_bytes / (dev_ms / args.steps / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:      # DRAM bytes per launch from the committed ncu --set full capture (per replica, scaled to this R)
         tj = json.load(open(os.path.join(REPO, "profiles", "tick_kernel_traffic.json")))
         if tj["jobs_per_replica"] == n and args.policy == "fifo" and args.engine in (0, 1):
             traffic = tj["dram_bytes_per_replica"] * R
+            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at %d replicas "
+                           "(profiles/tick_kernel_traffic.json), scaled per replica to %d" % (tj["replicas"], R))
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "kernel": "gs_tick_kernel", "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "gs_tick_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "ticks_per_s": ticks_rank * world / (dev_ms / args.steps / 1e3),
                 "candidate_evals_per_s": evals_rank * world / (dev_ms / args.steps / 1e3)}

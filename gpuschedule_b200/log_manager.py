@@ -68,51 +68,47 @@ def _line(values):
 
 def pending_columns(rows):
     """avg / median / max pending text from the integer aggregates, using the
-    reference's float expressions (jobs_manager.py:72-87)."""
+    reference's float expressions (jobs_manager.py:72-87).  Vectorised: only rows with a
+    non-empty queue need float formatting (str(np.float64) and repr(float) print the same text)."""
     q = rows["queued"]
-    avg = rows["pend_sum"].astype(np.float64) / (q.astype(np.float64) + 1e-9)
-    med = (rows["pend_med_lo"].astype(np.float64) + rows["pend_med_hi"].astype(np.float64)) / 2.0
-    avg_t = [repr(float(x)) for x in avg]
-    med_t = [repr(float(m)) if k > 0 else "nan" for m, k in zip(med, q)]
-    max_t = [repr(float(m)) if k > 0 else "0" for m, k in zip(rows["pend_max"], q)]
+    n = len(rows)
+    avg_t, med_t, max_t = ["0.0"] * n, ["nan"] * n, ["0"] * n
+    nz = np.nonzero(q > 0)[0]
+    if len(nz):
+        avg = rows["pend_sum"][nz].astype(np.float64) / (q[nz].astype(np.float64) + 1e-9)
+        med = (rows["pend_med_lo"][nz].astype(np.float64) + rows["pend_med_hi"][nz].astype(np.float64)) / 2.0
+        mx = rows["pend_max"][nz].astype(np.float64)
+        for i, a, m, x in zip(nz.tolist(), avg.tolist(), med.tolist(), mx.tolist()):
+            avg_t[i] = repr(a); med_t[i] = repr(m); max_t[i] = repr(x)
     return avg_t, med_t, max_t
 
 
 def memory_column(rows, total_cap_mib):
     """sum(min(cap, MiB)) / sum(cap) (schedule.py:115,121; device.py:56-62)."""
-    out = []
-    for b, busy in zip(rows["mem_busy_bytes"], rows["busy_gpus"]):
-        if busy == 0:
-            out.append("0.0")
-        else:
-            out.append(str(np.float64(int(b) / 1048576.0) / total_cap_mib))
-    return out
+    vals = (rows["mem_busy_bytes"].astype(np.float64) / 1048576.0) / total_cap_mib
+    busy = rows["busy_gpus"] > 0
+    return [repr(v) if b else "0.0" for v, b in zip(vals.tolist(), busy.tolist())]
 
 
 def cluster_lines(rows, util_text, total_cap_mib):
     avg_t, med_t, max_t = pending_columns(rows)
     mem_t = memory_column(rows, total_cap_mib)
-    cols = [rows[k].astype(str) for k in ("now", "idle_nodes", "busy_nodes", "busy_gpus", "idle_gpus")]
-    tail = [rows[k].astype(str) for k in ("running", "queued", "finished")]
-    lines = []
-    for i in range(len(rows)):
-        lines.append(",".join((cols[0][i], cols[1][i], cols[2][i], cols[3][i], cols[4][i],
-                               util_text[i], mem_t[i], avg_t[i], med_t[i], max_t[i],
-                               tail[0][i], tail[1][i], tail[2][i])))
-    return lines
+    cols = [rows[k].astype(str).tolist() for k in ("now", "idle_nodes", "busy_nodes", "busy_gpus", "idle_gpus")]
+    tail = [rows[k].astype(str).tolist() for k in ("running", "queued", "finished")]
+    return [",".join(t) for t in zip(cols[0], cols[1], cols[2], cols[3], cols[4], util_text, mem_t, avg_t, med_t, max_t,
+                                     tail[0], tail[1], tail[2])]
 
 
 def job_lines(table, recs, finish_order):
     """One line per finished job in finish order (log_manager.py:137-153)."""
-    lines = []
-    for j in finish_order:
-        r = recs[j]
-        dur = float(r["duration"])
-        actual = max(float(table.duration[j]), dur)          # Job.get_duration job.py:206-210
-        lines.append(",".join((table.label[j], table.num_gpu_text[j], str(int(table.submit[j])),
-                               str(int(r["start"])), str(int(r["end"])), repr(dur), repr(actual),
-                               str(int(r["jct"])), str(int(r["preempt"])))))
-    return lines
+    order = np.asarray(finish_order, dtype=np.int64)
+    dur = recs["duration"][order]
+    actual = np.maximum(table.duration[order], dur)              # Job.get_duration job.py:206-210
+    label, gtext = table.label, table.num_gpu_text
+    return [",".join((label[j], gtext[j], str(sb), str(st), str(en), repr(d), repr(a), str(jc), str(pr)))
+            for j, sb, st, en, d, a, jc, pr in zip(order.tolist(), table.submit[order].tolist(), recs["start"][order].tolist(),
+                                                   recs["end"][order].tolist(), dur.tolist(), actual.tolist(),
+                                                   recs["jct"][order].tolist(), recs["preempt"][order].tolist())]
 
 
 class LogManager:
