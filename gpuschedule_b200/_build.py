@@ -21,7 +21,9 @@ def nvcc_path():
 
 
 def build(force=False, verbose=False):
-    deps = [SRC, os.path.join(REPO, "include", "gsched.h")]
+    csrc = os.path.dirname(SRC)
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    deps.append(os.path.join(REPO, "include", "gsched.h"))
     if (not force and os.path.exists(OUT)
             and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps)):
         return OUT
