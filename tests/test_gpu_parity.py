@@ -378,3 +378,25 @@ def test_span_budget_overflow_is_reported_not_written():
             eng.load_trace(0, table)
             rows = eng.run_all()[0]
             assert eng.stats(0).done == 1 and rows.tobytes() == base[0].tobytes()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_engine_fuzz_matches_oracle(engine):
+    """Differential fuzz: 100 random clusters / traces (the generator of tests/test_cpu_differential.py:
+    1..64 GPUs per node, 1..132 nodes, cpu- or memory-bound nodes, leaks, gpu_per_container up to 4,
+    saturating rates) run as heterogeneous replicas of ONE handle and compared with the oracle."""
+    import oracle
+    from test_cpu_differential import _case
+    from gpuschedule_b200 import capi
+    cases = [_case(seed) for seed in range(300, 400)]
+    with capi.Engine(device=0, nsims=len(cases)) as eng:
+        eng.set_engine(engine)
+        for i, (cluster, table) in enumerate(cases):
+            eng.config(i, cluster)
+            eng.load_trace(i, table)
+        rows = eng.run_all()
+        for i, (cluster, table) in enumerate(cases):
+            ref = oracle.run_fifo(cluster, table)
+            recs, order = eng.fetch_jobs(i)
+            span_off, spans = eng.fetch_spans(i)
+            _assert_same(ref, (rows[i], recs, order, span_off, spans, eng.stats(i)), f"fuzz case {300 + i}")
