@@ -63,10 +63,11 @@ struct SimDev {
   // ---- event-driven policies (sjf / dlas / dlas-gpu / gittins): scratch + parameters
   struct PJob *pj;            // per-job dynamic state
   int *runnable, *queues, *endj, *tmpl, *cidle, *ckfree;   // queues: num_queue lists of n entries
+  int *stalej;                // end list a start event inherited from a tie it lost to a jump (quirk Q25)
   const double *git_data, *git_index;                      // device copies of the gittins tables
   double queue_limit[GS_MAX_QUEUES];
   double gittins_delta, next_gittins_unit;
-  int num_queue, git_n, rn, en, end_time, next_job_jump, qn[GS_MAX_QUEUES];
+  int num_queue, git_n, rn, en, end_time, next_job_jump, stale_n, qn[GS_MAX_QUEUES];
   // ---- loop state (persisted)
   int delta, p, top, running, finished, ever, busy_gpus, done, status, need_init;
   long long mem_busy, sum_arr, span_used, events, evals, started, ticks, row_first;

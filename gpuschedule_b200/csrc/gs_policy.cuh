@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, 
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
   const int total_gpus = M * G;
   int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, next_job_jump = S.next_job_jump, nfin = S.finished;
+  int stale_n = S.stale_n;
   double next_git = S.next_gittins_unit;
   long long events = S.events, ticks = S.ticks;
   const long long row_first = ticks;
@@ -79,14 +80,25 @@ __global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, 
     if (p >= n && end_time == 0x7fffffff) { done = true; break; }     // "cluster is not large enough"
     const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
     int event_time; bool has_start = false, has_end = false;
+    const int *elist = endj; int ecount = en;
     if (end_time < start_time) { event_time = end_time; has_end = true; }
     else if (end_time > start_time) { event_time = start_time; has_start = true; }
-    else { event_time = start_time; has_start = has_end = true; }
-    if (is_dlas && event_time > next_job_jump) { event_time = next_job_jump; has_start = has_end = false; }
-    if (policy == GS_SCHED_GITTINS && (double)event_time > next_git) { event_time = (int)next_git; has_start = has_end = false; }
+    else {                      // tie: the start event inherits this end list (quirk Q25, run_sim.py:708-710)
+      event_time = start_time; has_start = has_end = true;
+      for (int i = 0; i < en; ++i) S.stalej[i] = endj[i];
+      stale_n = en;
+    }
+    bool jumped = false;
+    if (is_dlas && event_time > next_job_jump) { event_time = next_job_jump; jumped = true; }
+    if (policy == GS_SCHED_GITTINS && (double)event_time > next_git) { event_time = (int)next_git; jumped = true; }
+    if (jumped) has_start = has_end = false;       // the start event keeps the inherited list
+    else if (has_start) {                          // the start event is consumed: an inherited list completes here
+      if (stale_n > 0) { elist = S.stalej; ecount = stale_n; has_end = true; }
+      stale_n = 0;
+    }
     if (has_end) {
-      for (int i = 0; i < en; ++i) {
-        const int j = endj[i];
+      for (int i = 0; i < ecount; ++i) {
+        const int j = elist[i];
         PJob &r = pj[j];
         r.status = PST_END;
         gs_job_rec o; o.start = r.start; o.end = event_time;
@@ -210,7 +222,6 @@ __global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, 
         const double lim = S.queue_limit[r.q_id];
         const double jt = gputime ? ceil((lim - (double)r.exec) / (double)jr.gpus) + event_time : lim - (double)r.exec + event_time;
         int jti = jt > 2.0e9 ? 0x7fffffff : (int)jt;
-        if (jti <= event_time) jti = event_time + 1;
         next_job_jump = min(next_job_jump, jti);
       }
     }
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(32) gs_policy_kernel(SimDev *sims, int nsims, 
     for (int j = 0; j < n; ++j) { const PJob r = pj[j]; if (r.status != PST_END && r.status != PST_NONE && r.start >= 0) { rec[j].start = r.start; rec[j].preempt = r.resume; } }
   }
   S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.next_job_jump = next_job_jump; S.finished = nfin;
+  S.stale_n = stale_n;
   S.next_gittins_unit = next_git; S.events = events; S.ticks = ticks; S.row_first = row_first;
   S.done = done ? 1 : 0; S.status = status; S.running = 0; S.top = 0; S.started = 0;
 }
@@ -260,7 +272,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
   const int nq = S.num_queue;
   const JobIn *__restrict__ jobs = S.jobs;
   PJob *pj = S.pj;
-  int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl;
+  int *runnable = S.runnable, *endj = S.endj, *tmpl = S.tmpl, *stalej = S.stalej;
   gs_job_rec *rec = S.rec;
   int *fin = S.fin, *queues = S.queues;
   gs_tick_row *rows = S.rows;
@@ -269,6 +281,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
   const int total_gpus = M * G;
   const unsigned lt = (1u << lane) - 1u;
   int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, next_job_jump = S.next_job_jump, nfin = S.finished;
+  int stale_n = S.stale_n;
   int qn[GS_MAX_QUEUES];
   #pragma unroll
   for (int q = 0; q < GS_MAX_QUEUES; ++q) qn[q] = S.qn[q];
@@ -285,14 +298,24 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
     if (p >= n && end_time == 0x7fffffff) { done = true; break; }
     const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
     int event_time; bool has_start = false, has_end = false;
+    const int *elist = endj; int ecount = en;
     if (end_time < start_time) { event_time = end_time; has_end = true; }
     else if (end_time > start_time) { event_time = start_time; has_start = true; }
-    else { event_time = start_time; has_start = has_end = true; }
-    if (event_time > next_job_jump) { event_time = next_job_jump; has_start = has_end = false; }
-    // ---- completions (end_jobs is in runnable order)
+    else {                      // tie: the start event inherits this end list (quirk Q25, run_sim.py:708-710)
+      event_time = start_time; has_start = has_end = true;
+      for (int i = lane; i < en; i += 32) stalej[i] = endj[i];
+      stale_n = en;
+      __syncwarp();
+    }
+    if (event_time > next_job_jump) { event_time = next_job_jump; has_start = has_end = false; }   // keeps the inherited list
+    else if (has_start) {       // the start event is consumed: an inherited list completes here, whatever the jobs' state
+      if (stale_n > 0) { elist = stalej; ecount = stale_n; has_end = true; }
+      stale_n = 0;
+    }
+    // ---- completions (an end list is in runnable order)
     if (has_end) {
-      for (int i = lane; i < en; i += 32) {
-        const int j = endj[i];
+      for (int i = lane; i < ecount; i += 32) {
+        const int j = elist[i];
         PJob r = pj[j];
         r.status = PST_END;
         pj[j] = r;
@@ -302,7 +325,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
         rec[j] = o;
         fin[nfin + i] = j;
       }
-      nfin += en; events += en;
+      nfin += ecount; events += ecount;
     }
     // ---- arrivals: appended to runnable and to queue 0 in trace order
     if (has_start) {
@@ -463,7 +486,6 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
             const double lim = qlim[r.q_id];
             const double t = gputime ? ceil((lim - (double)r.exec) / (double)jr.gpus) + event_time : lim - (double)r.exec + event_time;
             jt = t > 2.0e9 ? 0x7fffffff : (int)t;
-            if (jt <= event_time) jt = event_time + 1;
           }
         } else pend = r.pending;
       }
@@ -496,6 +518,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
   }
   if (lane == 0) {
     S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.next_job_jump = next_job_jump; S.finished = nfin;
+    S.stale_n = stale_n;
     #pragma unroll
     for (int q = 0; q < GS_MAX_QUEUES; ++q) S.qn[q] = qn[q];
     S.events = events; S.ticks = ticks; S.row_first = row_first;
@@ -523,7 +546,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   int *nkfree = nidle + M;
   const JobIn *__restrict__ jobs = S.jobs;
   PJob *pj = S.pj;
-  int *runnable = S.runnable, *endj = S.endj;
+  int *runnable = S.runnable, *endj = S.endj, *stalej = S.stalej;
   double *rk = reinterpret_cast<double *>(S.queues);     // gittins: rank of runnable[i] (no queues in these policies)
   gs_job_rec *rec = S.rec;
   int *fin = S.fin;
@@ -532,7 +555,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
   const int total_gpus = M * G;
   const unsigned lt = (1u << lane) - 1u;
-  int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, nfin = S.finished;
+  int p = S.p, rn = S.rn, en = S.en, end_time = S.end_time, nfin = S.finished, stale_n = S.stale_n;
   double next_git = S.next_gittins_unit;
   long long events = S.events, ticks = S.ticks;
   const long long row_first = ticks;
@@ -544,14 +567,26 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     if (p >= n && end_time == 0x7fffffff) { done = true; break; }
     const int start_time = p < n ? jobs[p].arrive : 0x7fffffff;
     int event_time; bool has_start = false, has_end = false;
+    const int *elist = endj; int ecount = en;
     if (end_time < start_time) { event_time = end_time; has_end = true; }
     else if (end_time > start_time) { event_time = start_time; has_start = true; }
-    else { event_time = start_time; has_start = has_end = true; }
-    if (!sjf && (double)event_time > next_git) { event_time = (int)next_git; has_start = has_end = false; }
+    else {                      // tie: the start event inherits this end list (quirk Q25, run_sim.py:994-996)
+      event_time = start_time; has_start = has_end = true;
+      if (!sjf) {               // sjf has no jump events, so nothing can come between the tie and the start
+        for (int i = lane; i < en; i += 32) stalej[i] = endj[i];
+        stale_n = en;
+        __syncwarp();
+      }
+    }
+    if (!sjf && (double)event_time > next_git) { event_time = (int)next_git; has_start = has_end = false; }   // keeps the inherited list
+    else if (has_start) {       // the start event is consumed: an inherited list completes here
+      if (stale_n > 0) { elist = stalej; ecount = stale_n; has_end = true; }
+      stale_n = 0;
+    }
     // ---- completions
     if (has_end) {
-      for (int i = lane; i < en; i += 32) {
-        const int j = endj[i];
+      for (int i = lane; i < ecount; i += 32) {
+        const int j = elist[i];
         PJob r = pj[j];
         r.status = PST_END;
         pj[j] = r;
@@ -561,7 +596,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         rec[j] = o;
         fin[nfin + i] = j;
       }
-      nfin += en; events += en;
+      nfin += ecount; events += ecount;
     }
     __syncwarp();
     // ---- pass 1: drop END, age counters, (gittins) rank of every survivor at its new position
@@ -805,7 +840,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     for (int j = lane; j < n; j += 32) { const PJob r = pj[j]; if (r.status != PST_END && r.status != PST_NONE && r.start >= 0) { rec[j].start = r.start; rec[j].preempt = r.resume; } }
   }
   if (lane == 0) {
-    S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.finished = nfin; S.next_gittins_unit = next_git;
+    S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.finished = nfin; S.next_gittins_unit = next_git; S.stale_n = stale_n;
     S.events = events; S.ticks = ticks; S.row_first = row_first;
     S.done = done ? 1 : 0; S.running = 0; S.top = 0; S.started = 0;
   }

@@ -319,11 +319,12 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   size_t total = align_up(o_nk + 4 * (size_t)M);
   const bool evd = s.pol.schedule != GS_SCHED_FIFO;        // event-driven policy: extra scratch
   const size_t nql = (size_t)(s.pol.num_queue > 2 ? s.pol.num_queue : 2);
-  size_t o_pj = total, o_run = 0, o_q = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0;
+  size_t o_pj = total, o_run = 0, o_q = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0, o_stale = 0;
   if (evd) {
     o_run = align_up(o_pj + sizeof(PJob) * N); o_q = align_up(o_run + 4 * N); o_end = align_up(o_q + 4 * N * nql);
     o_tmp = align_up(o_end + 4 * N); o_ci = align_up(o_tmp + 4 * N); o_ck = align_up(o_ci + 4 * (size_t)M);
-    total = align_up(o_ck + 4 * (size_t)M);
+    o_stale = align_up(o_ck + 4 * (size_t)M);
+    total = align_up(o_stale + 4 * N);
   }
   if (s.state_slab && s.state_bytes < total) { cudaFree(s.state_slab); s.state_slab = nullptr; }
   if (!s.state_slab) { CU(cudaMalloc(&s.state_slab, total)); s.state_bytes = total; }
@@ -347,6 +348,7 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   if (evd) {
     D.pj = (PJob *)(d + o_pj); D.runnable = (int *)(d + o_run); D.queues = (int *)(d + o_q);
     D.endj = (int *)(d + o_end); D.tmpl = (int *)(d + o_tmp); D.cidle = (int *)(d + o_ci); D.ckfree = (int *)(d + o_ck);
+    D.stalej = (int *)(d + o_stale); D.stale_n = 0;
     D.num_queue = s.pol.num_queue > 0 ? s.pol.num_queue : 1;
     for (int q = 0; q < GS_MAX_QUEUES; ++q) { D.queue_limit[q] = s.pol.queue_limit[q]; D.qn[q] = 0; }
     D.gittins_delta = s.pol.gittins_delta; D.next_gittins_unit = s.pol.gittins_delta;

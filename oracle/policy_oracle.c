@@ -22,8 +22,9 @@
  *   - solve_starvation = 0 (its default): no promotion.
  * Defects of the spec kept verbatim and flagged: the gputime jump subtracts the un-scaled
  * executed_time (:929); pending jobs rank by executed_time without the GPU factor (:1071);
- * next_gittins_unit += event_time (:1202).  One deviation, for termination: a queue jump
- * that would not lie in the future is moved to event_time + 1.
+ * next_gittins_unit += event_time (:1202); a queue jump may be computed AT or BEFORE the current
+ * event time (:929) -- the loop then handles a zero / negative-dt jump event, exactly as the code does
+ * (each such event demotes at least one job one more level, so the loop still terminates).
  */
 #include <math.h>
 #include <stdint.h>
@@ -116,6 +117,7 @@ int64_t oracle_run_policy(const gs_cluster *c, const gs_policy *pol, int64_t n, 
   for (int q = 0; q < GS_MAX_QUEUES; ++q) { queue[q] = (int32_t *)malloc(N * sizeof(int32_t)); qn[q] = 0; }
   int32_t *end_jobs = (int32_t *)malloc(N * sizeof(int32_t)); int64_t en = 0; int end_time = T_INF;
   int32_t *tmp = (int32_t *)malloc(N * sizeof(int32_t));
+  int32_t *stale_jobs = (int32_t *)malloc(N * sizeof(int32_t)); int64_t stale_n = 0;   /* Q25, see the event selection */
   for (int64_t j = 0; j < n; ++j) {
     double cl_ = ceil(duration[j]); D[j] = cl_ < 1.0 ? 1 : (int32_t)cl_;
     jb[j].start = -1;
@@ -129,19 +131,32 @@ int64_t oracle_run_policy(const gs_cluster *c, const gs_policy *pol, int64_t n, 
     if (next_row >= n && end_time == T_INF) break;               /* "cluster is not large enough" */
     int start_time = next_row < n ? arrive[next_row] : T_INF;
     int event_time, has_start = 0, has_end = 0;
+    const int32_t *elist = end_jobs; int64_t ecount = en;
     if (end_time < start_time) { event_time = end_time; has_end = 1; }
     else if (end_time > start_time) { event_time = start_time; has_start = 1; }
-    else { event_time = start_time; has_start = 1; has_end = 1; }
+    else {                                                        /* tie: the START event dict gets the key */
+      event_time = start_time; has_start = 1; has_end = 1;        /* 'end_jobs' = this end list (:708-710)  */
+      memcpy(stale_jobs, end_jobs, (size_t)en * sizeof(int32_t)); stale_n = en;
+    }
+    int jumped = 0;
     if ((policy == GS_SCHED_DLAS || policy == GS_SCHED_DLAS_GPU) && event_time > next_job_jump) {
-      event_time = next_job_jump; has_start = has_end = 0;       /* :715-717 */
+      event_time = next_job_jump; jumped = 1;                    /* :715-717  event = dict() */
     }
     if (policy == GS_SCHED_GITTINS && (double)event_time > next_gittins_unit) {
-      event_time = (int)next_gittins_unit; has_start = has_end = 0;   /* :1006-1008 */
+      event_time = (int)next_gittins_unit; jumped = 1;           /* :1006-1008 */
+    }
+    if (jumped) { has_start = has_end = 0; }                      /* the start dict KEEPS its 'end_jobs' key */
+    else if (has_start) {
+      /* The start event dict is consumed now.  If an earlier tie left an 'end_jobs' key on it and a jump
+       * was served in between, those jobs complete HERE, whatever their state is by now (quirk Q25;
+       * reference :720-727 looks only at the key).  A fresh tie has just overwritten the key above. */
+      if (stale_n > 0) { elist = stale_jobs; ecount = stale_n; has_end = 1; }
+      stale_n = 0;
     }
     /* completions */
     if (has_end) {
-      for (int64_t i = 0; i < en; ++i) {
-        int32_t j = end_jobs[i];
+      for (int64_t i = 0; i < ecount; ++i) {
+        int32_t j = elist[i];
         jb[j].status = ST_END;
         jobs_out[j].start = jb[j].start; jobs_out[j].end = event_time;
         jobs_out[j].jct = D[j]; jobs_out[j].preempt = jb[j].resume;
@@ -242,7 +257,6 @@ int64_t oracle_run_policy(const gs_cluster *c, const gs_policy *pol, int64_t n, 
         double lim = pol->queue_limit[r->q_id];
         double jt = gputime ? ceil((lim - (double)r->exec) / (double)gpus[j]) + event_time : lim - (double)r->exec + event_time;
         int jti = jt > 2.0e9 ? T_INF : (int)jt;
-        if (jti <= event_time) jti = event_time + 1;              /* deviation: keep time moving */
         if (jti < next_job_jump) next_job_jump = jti;
       }
     }
@@ -268,7 +282,7 @@ int64_t oracle_run_policy(const gs_cluster *c, const gs_policy *pol, int64_t n, 
   if (events_out) *events_out = events;
   for (int64_t j = 0; j < n; ++j)
     if (jb[j].status != ST_END && jb[j].start >= 0) { jobs_out[j].start = jb[j].start; jobs_out[j].preempt = jb[j].resume; }
-  free(cl.idle); free(cl.kfree); free(jb); free(D); free(runnable); free(end_jobs); free(tmp);
+  free(cl.idle); free(cl.kfree); free(jb); free(D); free(runnable); free(end_jobs); free(tmp); free(stale_jobs);
   for (int q = 0; q < GS_MAX_QUEUES; ++q) free(queue[q]);
   return rc < 0 ? rc : ticks;
 }

@@ -1,6 +1,7 @@
 """Event-driven policies (sjf / dlas / dlas-gpu / gittins): CUDA engine vs the CPU restatement
-(oracle/policy_oracle.c).  Parity here is engine <-> oracle only: the reference holds these
-policies as dead code, so nothing executable pins either side."""
+(oracle/policy_oracle.c) and vs tests/golden/policy_*: the reference holds these policies as dead
+code; the fixtures were produced by executing that dead loop code verbatim under
+the stub harness of tests/golden/make_policy_golden.py, which is what pins both sides."""
 import numpy as np
 import pytest
 
@@ -125,3 +126,22 @@ def test_cli_runs_an_event_driven_policy(tmp_path):
     assert open(os.path.join(runs[0], "job.csv"), newline="").read() == exp_jobs
     got_rows = open(os.path.join(runs[0], "cluster.csv"), newline="").read().split("\r\n")
     assert len(got_rows) == ref.ticks + 2 and got_rows[1].split(",")[0] == str(int(ref.rows["now"][0]))
+
+
+def _fixture_cases():
+    import os
+    from conftest import GOLDEN
+    return sorted(d for d in os.listdir(GOLDEN) if d.startswith("policy_") and os.path.isfile(os.path.join(GOLDEN, d, "expected.json")))
+
+
+@pytest.mark.parametrize("engine", [0, 2], ids=["warp", "thread"])
+@pytest.mark.parametrize("case", _fixture_cases())
+def test_policy_engine_matches_reference_loop_fixtures(case, engine):
+    """CUDA engine vs the outputs of the reference's own loop code (completions, checkpoints, event totals);
+    policy_dlas_gpu_8q exercises the inherited-end-list quirk (Q25) and multi-level demotion jumps."""
+    from types import SimpleNamespace
+    from test_policy_golden import _load, check_against_expected
+    table, cluster, pol, exp, kw = _load(case)
+    rows, recs, order, st = _run(cluster, pol, table, engine=engine)
+    assert st.done == 1
+    check_against_expected(table, SimpleNamespace(finish_order=order, recs=recs, rows=rows, ticks=st.ticks, events=st.events), exp)
