@@ -9,8 +9,13 @@
  *     gittins    gittins_sim_jobs            /root/reference/run_sim.py:956-1203
  *                get_gittins_index           /root/reference/run_sim.py:949-954
  *
- * PARITY UNPINNED: nothing in the reference can execute these, so there are no golden
- * vectors; this file is the specification the CUDA kernels are checked against.
+ * PARITY PINNED TO THE REFERENCE'S LOOP CODE (not to a reference run: run_sim.py cannot enter
+ * these loops).  tests/golden/make_policy_golden.py extracts the four functions above plus
+ * cal_r_gittins_index / parse_job_dist from /root/reference/run_sim.py with `ast`, exec()s them
+ * UNCHANGED in a namespace whose JOBS / CLUSTER / LOG / scheduler are the minimal stubs listed
+ * below, and records every LOG.job_complete and every LOG.checkpoint; tests/golden/policy_* hold
+ * 9 such fixtures and tests/golden/fuzz_policy_reference.py compared 460 random cases (all
+ * identical).  What stays an assumption is therefore ONLY the stub completion, not the loop logic.
  * Completion of what the dead code leaves undefined (kept deliberately minimal):
  *   - a job dict = {job_idx, num_gpu, submit_time = admission tick, duration D =
  *     max(1, ceil(minutes * 0.5)) ticks}; move_to_runnable() = status PENDING,
@@ -24,7 +29,10 @@
  * executed_time (:929); pending jobs rank by executed_time without the GPU factor (:1071);
  * next_gittins_unit += event_time (:1202); a queue jump may be computed AT or BEFORE the current
  * event time (:929) -- the loop then handles a zero / negative-dt jump event, exactly as the code does
- * (each such event demotes at least one job one more level, so the loop still terminates).
+ * (each such event demotes at least one job one more level, so the loop still terminates);
+ * Q25: on an end/start tie the START event dict receives the key 'end_jobs' (:708-710, :994-996); if
+ * a jump event is served first, the key survives on the dict and those jobs are completed when the
+ * start event is finally consumed -- even if they were preempted meanwhile and have work left.
  */
 #include <math.h>
 #include <stdint.h>

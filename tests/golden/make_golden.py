@@ -87,6 +87,18 @@ def floatgpu_frame():
     return df
 
 
+def netcost_frame(n, seed, rate):
+    """Wide jobs (many span several nodes) with model_name / iterations / ps_count columns; iterations kept
+    small so that the added seconds stay comparable with the durations."""
+    df = tracegen.synth_frame(n, seed=seed, rate=rate, with_network=True,
+                              gpu_choices=[1, 2, 4, 8, 12, 16, 24], gpu_probs=[.2, .15, .15, .2, .1, .1, .1])
+    df = df.drop(columns=["model"])
+    rng = np.random.default_rng(seed)
+    df["iterations"] = rng.choice([1, 3, 8, 20, 57], size=n)
+    df.loc[rng.choice(n, n // 5, replace=False), "ps_count"] = 1          # not distributed: no cost
+    return df
+
+
 def gpc2_frame():
     df = tracegen.synth_frame(200, seed=41, rate=1.0, gpu_per_container=2,
                               gpu_choices=[2, 4, 8, 16, 24], gpu_probs=[.3, .3, .2, .1, .1])
@@ -108,7 +120,42 @@ CASES = {
     "ragged": (ragged_frame, dict(num_switch=1, num_node_p_switch=8, num_gpu_p_node=8)),
     "leak": (leak_frame, dict(num_switch=1, num_node_p_switch=4, num_gpu_p_node=8)),
     "floatgpu": (floatgpu_frame, dict(num_switch=1, num_node_p_switch=16, num_gpu_p_node=8)),
+    # network-cost branch (schedule.py:48-53): the live Job lacks ps_count / model_size / iterations, so the run
+    # only gets there with those three attributes attached (see _NETCOST_INJECT); everything else is unmodified
+    "netcost": (lambda: netcost_frame(260, 51, 0.6), dict(num_switch=2, num_node_p_switch=8, num_gpu_p_node=8,
+                enable_network_costs=True)),
+    "netcost_lat": (lambda: netcost_frame(200, 52, 1.2), dict(num_switch=1, num_node_p_switch=12, num_gpu_p_node=4,
+                    enable_network_costs=True, bandwidth=800, internode_latency=0.004)),
 }
+
+# Attaches the attributes network_service.calculate_network_costs reads (network_service.py:12,34,36) to every
+# Job the reference builds: ps_count and iterations from the trace's extra columns, model_size from the
+# reference's OWN table (model/model_factory.py:19-55) keyed by the trace's model_name column.
+_NETCOST_INJECT = (
+    "import importlib.abc, importlib.util\n"
+    "import pandas as _pd\n"
+    "from model import model_factory as _mf\n"
+    "_t = _pd.read_csv('trace.csv')\n"
+    "_extra = {str(i): (int(r.ps_count), _mf.model_sizes[r.model_name], r.iterations) for i, r in _t.iterrows()}\n"
+    "def _patch(mod):\n"
+    "    _init = mod.Job.__init__\n"
+    "    def _patched(self, job_id, *a, **k):\n"
+    "        _init(self, job_id, *a, **k)\n"
+    "        self.ps_count, self.model_size, self.iterations = _extra[str(job_id)]\n"
+    "    mod.Job.__init__ = _patched\n"
+    "class _Hook(importlib.abc.MetaPathFinder):\n"        # core.jobs.job can only be imported once run_sim.py
+    "    def find_spec(self, name, path, target=None):\n"  # has initialised base_factory: patch right after
+    "        if name != 'core.jobs.job':\n"
+    "            return None\n"
+    "        sys.meta_path.remove(self)\n"
+    "        spec = importlib.util.find_spec(name)\n"
+    "        run = spec.loader.exec_module\n"
+    "        def exec_module(mod):\n"
+    "            run(mod)\n"
+    "            _patch(mod)\n"
+    "        spec.loader.exec_module = exec_module\n"
+    "        return spec\n"
+    "sys.meta_path.insert(0, _Hook())\n")
 
 
 def run_reference(trace_csv: str, flags: dict, out_dir: str):
@@ -130,6 +177,7 @@ def run_reference(trace_csv: str, flags: dict, out_dir: str):
         "import sys, os, runpy, logging, numpy\n"
         "logging.getLogger().addHandler(logging.NullHandler())\n"
         f"sys.path.insert(0, {REF!r}); os.chdir({scratch!r}); sys.argv = {argv!r}\n"
+        + (_NETCOST_INJECT if flags.get("enable_network_costs") else "") +
         f"numpy.random.seed({SEED})\n"
         "try:\n"
         f"    runpy.run_path({os.path.join(REF, 'run_sim.py')!r}, run_name='__main__')\n"

@@ -215,6 +215,29 @@ def test_net_cost_matches_oracle():
                 assert got[i] == exp, (i, got[i], exp)
 
 
+def test_net_cost_matches_reference_function():
+    """gs_net_cost == the reference's calculate_network_costs on the committed vectors (bit-exact doubles)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from gpuschedule_b200 import capi
+    cases = json.load(open(os.path.join(GOLDEN, "netcost.json")))["cases"]
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["bandwidth"], c["latency"]), []).append(c)
+    with capi.Engine(device=0, nsims=1) as eng:
+        for (bw, lat), cs in groups.items():
+            cluster = capi.make_cluster(4, 32, bandwidth=bw, internode_latency=lat)
+            task_off = np.zeros(len(cs) + 1, dtype=np.int64)
+            np.cumsum([len(c["node"]) for c in cs], out=task_off[1:])
+            task_node = np.concatenate([np.array(c["node"], dtype=np.int32) for c in cs])
+            marks = np.concatenate([np.array(c["is_ps"], dtype=np.uint8) for c in cs])
+            got = eng.net_cost(cluster, task_off, task_node, marks, np.array([c["ps_count"] for c in cs], dtype=np.int32),
+                               np.array([c["model_mb"] for c in cs]), np.array([c["iterations"] for c in cs]))
+            for g, c in zip(got, cs):
+                assert g == float.fromhex(c["expected"]), c
+
+
 def test_full_size_properties_100k():
     """BASELINE size (100k jobs, 4x32x8): size-independent invariants + oracle equality."""
     import oracle

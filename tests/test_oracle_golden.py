@@ -37,3 +37,21 @@ def test_kat0_known_answers():
     j5 = table.label.index("5")
     sp = r.spans[r.span_off[j5]:r.span_off[j5 + 1]]
     assert [(int(s["node"]) + 1, int(s["ntasks"])) for s in sp] == [(1, 7), (5, 8), (6, 1)]
+
+
+def test_net_cost_matches_reference_function():
+    """oracle_net_cost == the reference's calculate_network_costs (network_service.py:3-39), bit for bit, on the
+    400 vectors tests/golden/make_netcost_golden.py produced by calling the unmodified function."""
+    import json
+    import os
+    import numpy as np
+    import oracle
+    from conftest import GOLDEN
+    from gpuschedule_b200 import capi
+    cases = json.load(open(os.path.join(GOLDEN, "netcost.json")))["cases"]
+    assert len(cases) == 400
+    for c in cases:
+        cl = capi.make_cluster(4, 32, bandwidth=c["bandwidth"], internode_latency=c["latency"])
+        got = oracle.net_cost(cl, np.array(c["node"], dtype=np.int32), np.array(c["is_ps"], dtype=np.uint8),
+                              c["ps_count"], c["model_mb"], c["iterations"])
+        assert got == float.fromhex(c["expected"]), c
