@@ -381,7 +381,7 @@ def ours(args):
                 ev = sum(pe.stats(i).events for i in range(len(tabs)))
             extras[name] = {"value": ev / (ms / 1e3), "unit": UNIT, "ms": ms, "replicas": len(tabs), "jobs_per_replica": njobs,
                             "kernel": "gs_dlas_warp_kernel" if name == "dlas-gpu" else "gs_sortpol_warp_kernel",
-                            "parity": "engine == oracle/policy_oracle.c; unpinned vs the reference (dead code there)"}
+                            "parity": "engine == oracle/policy_oracle.c == the reference's loop functions executed under stubs (tests/golden/policy_*)"}
         try:
             import contextlib
             import io

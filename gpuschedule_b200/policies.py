@@ -4,7 +4,8 @@
 (/root/reference/run_sim.py:1650-1708) with binary searches and prefix sums instead of the
 O(n^2) generator scans; the arithmetic (Python round(), association) is kept.  The reference's
 sample file yarn-gput1000.csv is not in the repository, so the sample is the trace's own
-`run length x gpus`.  Parity unpinned (dead code in the reference).
+`run length x gpus`.  Pinned: tests/test_policy_golden.py compares the table with the
+output of the reference's parse_job_dist executed verbatim (tests/golden/make_policy_golden.py).
 """
 from __future__ import annotations
 

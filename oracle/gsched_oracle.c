@@ -12,8 +12,10 @@
  * Parity status: PINNED.  tests/test_oracle_golden.py checks this file against
  * every fixture under tests/golden/, which were produced by running the
  * unmodified reference (tests/golden/make_golden.py).  The network-cost branch
- * (net_cost below) is NOT pinned: the reference cannot execute it
- * (core/jobs/job.py:199-200 reads attributes Job never defines).
+ * (net_cost below) is pinned too: tests/golden/netcost.json holds return values of
+ * the reference's own calculate_network_costs, and the netcost / netcost_lat fixtures
+ * are reference runs with the three attributes core/jobs/job.py:199-200 and
+ * network_service.py:34-36 read (ps_count, model_size, iterations) attached to Job.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
  * arm may load this library.  The product (libgsched.so) never does.
@@ -225,7 +227,7 @@ static int ms_yarn_placement(sim_t *s, int j) {
 /* calculate_network_costs                   core/network/network_service.py:3-39
  * The live Job creates only 'worker*' tasks (job.py:100), so ps_nodes is empty
  * and the symmetric difference is the set of distinct worker nodes.
- * UNPINNED (see header).  Exact operation order of :34-37 is kept.             */
+ * Pinned (see header).  Exact operation order of :34-37 is kept.               */
 static double net_cost(const sim_t *s, const gs_cluster *c, int j) {
   if (!s->ps_count || !(s->ps_count[j] > 1)) return 0.0;      /* is_distributed, job.py:199-200 */
   int tasks = job_tasks(s, j), cross = 0;

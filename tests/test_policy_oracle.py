@@ -1,5 +1,5 @@
 """CPU checks of the event-driven policy restatement (oracle/policy_oracle.c) and the gittins
-table builder: internal consistency only -- parity with the reference is unpinned (dead code)."""
+table builder: internal consistency; parity with the reference's loop code is tests/test_policy_golden.py."""
 import numpy as np
 
 

@@ -10,6 +10,8 @@ from conftest import golden_cases, load_golden
 def test_tight_cpu_matches_pinned_oracle_on_fixtures(case):
     import oracle
     table, cluster, _, _, _ = load_golden(case)
+    if cluster.enable_network_costs:
+        pytest.skip("the yardstick implements the plain fifo + yarn tick only (no network-cost branch)")
     ref = oracle.run_fifo(cluster, table)
     got = oracle.run_tight(cluster, table)
     assert got.ticks == ref.ticks and got.events == ref.events
