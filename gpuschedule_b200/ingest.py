@@ -146,6 +146,8 @@ def table_from_frame(df, scale_factor=0.5) -> JobTable:
         duration=np.ascontiguousarray(duration), mem_bytes=mem.astype(np.int64),
         util_avg=df["gpu_utilization_avg"].to_numpy(dtype=np.float64),
         util_max=df["gpu_utilization_max"].to_numpy(dtype=np.float64))
+    if "memory_avg" in df.columns:      # Job.gpu_mem_avg in MiB (jobs_manager.py:237): a k-means feature (core/jobs/utils.py:4-22)
+        t.extra["mem_avg_mib"] = df["memory_avg"].to_numpy(dtype=np.float64) / 1024 / 1024
     if "model_name" in df.columns or "model_size" in df.columns:
         from .model_factory import model_size_mb
         if "model_size" in df.columns:

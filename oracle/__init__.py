@@ -23,7 +23,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(_HERE, "gsched_oracle.c"), os.path.join(_HERE, "policy_oracle.c"),
-            os.path.join(_HERE, "tight_cpu.c")]
+            os.path.join(_HERE, "tight_cpu.c"), os.path.join(_HERE, "horus_oracle.c")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "gsched.h")
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(x) for x in srcs + [hdr])):
@@ -41,6 +41,7 @@ def lib():
         _lib.oracle_run_fifo.restype = C.c_int64
         _lib.oracle_run_policy.restype = C.c_int64
         _lib.tight_run_fifo.restype = C.c_int64
+        _lib.oracle_run_horus.restype = C.c_int64
         _lib.oracle_place_one.restype = C.c_int
         _lib.oracle_net_cost.restype = C.c_double
     return _lib
@@ -224,4 +225,43 @@ def run_tight(cluster: GsCluster, table, rows_cap=None):
     np.cumsum(scnt[:n], out=off[1:])
     idx = np.concatenate([np.arange(f, f + k) for f, k in zip(sfirst[:n], scnt[:n])]) if n and off[-1] else np.zeros(0, dtype=np.int64)
     r.span_off, r.spans = off, spans[idx.astype(np.int64)] if len(idx) else spans[:0]
+    return r
+
+
+HORUS_REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"), ("preempt", "<i4"),
+                            ("original", "<f8"), ("actual", "<f8")])
+HORUS_SCHEMES = {"horus": 0, "horus+": 0, "gandiva": 1}
+HORUS_SCHEDULES = {"fifo": 0, "horus": 1, "horus+": 2, "gandiva": 3}
+
+
+def run_horus(cluster: GsCluster, table, scheme="horus", schedule="horus", num_buffer=5, num_queue=1, seed=0, rows_cap=None):
+    """The utilisation-aware live paths (horus / horus+ / gandiva), oracle/horus_oracle.c.  `seed` is the value
+    numpy.random.seed() was given before the reference run being checked."""
+    n = table.n
+    if rows_cap is None:
+        rows_cap = min(int(table.arrive_tick[-1] if n else 0) + 2 * int(np.ceil(table.duration).sum() if n else 0) + 8 * n + 64, 1 << 24)
+    rows = np.zeros(rows_cap, dtype=ROW_DTYPE)
+    util = np.zeros(rows_cap, dtype=np.float64)
+    util_arr = np.zeros(rows_cap, dtype=np.uint8)
+    recs = np.zeros(max(n, 1), dtype=HORUS_REC_DTYPE)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    nfin, events, draws = C.c_int64(0), C.c_int64(0), C.c_uint64(0)
+    arr = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    a, g, c = arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32)
+    d, m = arr(table.duration, np.float64), arr(table.mem_bytes, np.int64)
+    ma = arr(table.extra.get("mem_avg_mib"), np.float64)
+    ua, um = arr(table.util_avg, np.float64), arr(table.util_max, np.float64)
+    ticks = lib().oracle_run_horus(C.byref(cluster), C.c_int32(HORUS_SCHEMES[scheme]), C.c_int32(HORUS_SCHEDULES[schedule]),
+                                   C.c_int32(num_buffer), C.c_int32(num_queue), C.c_uint32(seed), C.c_int64(n),
+                                   _p(a), _p(g), _p(c), _p(d), _p(m), _p(ma), _p(ua), _p(um),
+                                   _p(rows), _p(util), _p(util_arr), C.c_int64(rows_cap), _p(recs), _p(order),
+                                   C.byref(nfin), C.byref(events), C.byref(draws))
+    if ticks < 0:
+        raise RuntimeError(f"oracle_run_horus failed: {ticks}")
+    r = OracleResult()
+    r.ticks = int(ticks)
+    r.rows, r.util, r.util_is_array = rows[:ticks], util[:ticks], util_arr[:ticks]
+    r.recs = recs[:n]
+    r.finish_order = order[:nfin.value]
+    r.events, r.draws = events.value, draws.value
     return r

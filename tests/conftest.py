@@ -52,6 +52,47 @@ def render_outputs(table, cluster, rows, recs, finish_order, span_off, spans, se
     return job_csv, cluster_csv
 
 
+def horus_cases():
+    return sorted(d for d in os.listdir(GOLDEN) if os.path.isfile(os.path.join(GOLDEN, d, "horus.json")))
+
+
+def load_horus(case):
+    """(JobTable, GsCluster, run parameters, expected job.csv text, expected cluster.csv text) of a horus_* fixture."""
+    from gpuschedule_b200 import capi, ingest
+    d = os.path.join(GOLDEN, case)
+    with open(os.path.join(d, "horus.json")) as f:
+        meta = json.load(f)
+    flags = dict(meta["flags"])
+    params = dict(scheme=flags.pop("_scheme"), schedule=flags.pop("_schedule"), num_buffer=flags.pop("num_buffer", 5),
+                  num_queue=flags.pop("num_queue", 1), seed=meta["numpy_seed"])
+    cluster = capi.make_cluster(**flags)
+    table = ingest.JobTraceReader(os.path.join(d, "trace.csv")).prepare_jobs().table(0.5)
+    with open(os.path.join(d, "job.csv"), newline="") as f:
+        job_csv = f.read()
+    with open(os.path.join(d, "cluster.csv"), newline="") as f:
+        cluster_csv = f.read()
+    return table, cluster, params, job_csv, cluster_csv
+
+
+def render_horus_outputs(table, cluster, res):
+    """job.csv / cluster.csv text of a horus-family result (rows + utilisation values + 6-field job records)."""
+    import numpy as np
+    from gpuschedule_b200 import log_manager, rngcol
+    m = cluster.num_switch * cluster.num_node_p_switch
+    g = cluster.num_gpu_p_node
+    bracketed = rngcol._format_bracketed(res.util)
+    # a row whose sum saw an un-clipped draw is a 1-element numpy array, otherwise a plain Python number
+    util = [b if a else repr(float(v)) for b, a, v in zip(bracketed, res.util_is_array.tolist(), res.util.tolist())]
+    cluster_csv = log_manager.render_cluster_csv(res.rows, util, m * g * cluster.gpu_mem_cap_mib)
+    rec = res.recs
+    lines = [",".join((table.label[j], table.num_gpu_text[j], str(int(table.submit[j])), str(int(rec["start"][j])),
+                       str(int(rec["end"][j])), repr(float(rec["original"][j])), repr(float(rec["actual"][j])),
+                       str(int(rec["jct"][j])), str(int(rec["preempt"][j]))))
+             for j in np.asarray(res.finish_order, dtype=np.int64).tolist()]
+    job_csv = log_manager._line(log_manager.JOB_HEADER) + (log_manager.EOL.join(lines) + log_manager.EOL if lines else "")
+    return job_csv, cluster_csv
+
+
 @pytest.fixture(scope="session")
 def have_gpu():
     try:

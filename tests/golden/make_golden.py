@@ -161,7 +161,7 @@ _NETCOST_INJECT = (
 def run_reference(trace_csv: str, flags: dict, out_dir: str):
     scratch = tempfile.mkdtemp(prefix="gsref_")
     shutil.copy(trace_csv, os.path.join(scratch, "trace.csv"))
-    argv = [os.path.join(REF, "run_sim.py"), "--scheme", "yarn", "--schedule", "fifo",
+    argv = [os.path.join(REF, "run_sim.py"), "--scheme", flags.get("_scheme", "yarn"), "--schedule", flags.get("_schedule", "fifo"),
             "--trace_file", "trace.csv", "--log_path", "g"]
     for k, v in flags.items():
         if k.startswith("_"):
