@@ -84,7 +84,9 @@ def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), git
 
 
 class GsError(RuntimeError):
-    pass
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code            # gs_status of the failing call, when there was one
 
 
 class PinnedBuffer:
@@ -166,8 +168,122 @@ def load_library(path=None):
         getattr(lib, name).restype = C.c_int
     if lib.gs_abi_version() != 1:
         raise GsError("libgsched.so ABI version mismatch")
+    # ---- include/gsched_horus.h
+    u8p = C.POINTER(C.c_uint8)
+    lib.gs_horus_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.gs_horus_destroy.argtypes = [C.c_void_p]
+    lib.gs_horus_config.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsCluster), C.POINTER(GsHorusParams)]
+    lib.gs_horus_load_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int64, i32p, i32p, i32p, f64p, i64p, f64p, f64p]
+    lib.gs_horus_load_stream.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
+    lib.gs_horus_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.gs_horus_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsHorusRunStats)]
+    lib.gs_horus_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, f64p, u8p, C.c_int64, C.c_void_p, i32p, i64p, i64p]
+    lib.gs_horus_launch_count.argtypes = [C.c_void_p]
+    lib.gs_horus_launch_count.restype = C.c_int64
+    lib.gs_horus_last_error.argtypes = [C.c_void_p]
+    lib.gs_horus_last_error.restype = C.c_char_p
+    for name in ("gs_horus_create", "gs_horus_destroy", "gs_horus_config", "gs_horus_load_trace", "gs_horus_load_stream",
+                 "gs_horus_run", "gs_horus_stats", "gs_horus_fetch"):
+        getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
+
+
+class GsHorusParams(C.Structure):
+    _fields_ = [("score", C.c_int32), ("schedule", C.c_int32), ("num_buffer", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GsHorusRunStats(C.Structure):
+    _fields_ = [("ticks", C.c_int64), ("events", C.c_int64), ("draws", C.c_int64), ("finished", C.c_int32),
+                ("queued", C.c_int32), ("running", C.c_int32), ("done", C.c_int32), ("status", C.c_int32),
+                ("reserved", C.c_int32), ("kernel_ms", C.c_float), ("reserved2", C.c_float)]
+
+
+HORUS_REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"), ("preempt", "<i4"),
+                            ("original", "<f8"), ("actual", "<f8")])
+HORUS_SCORES = {"horus": 0, "gandiva": 1}                 # --scheme  (core/scheduling/algorithm.py:9-13)
+HORUS_SCHEDULES = {"fifo": 0, "horus": 1, "gandiva": 3}   # --schedule (algorithm.py:292-298)
+
+
+def make_horus_params(scheme="horus", schedule="horus", num_buffer=5):
+    if scheme not in HORUS_SCORES or schedule not in HORUS_SCHEDULES:
+        raise NotImplementedError(f"scheme {scheme!r} / schedule {schedule!r}: the utilisation-aware engine serves "
+                                  "horus and gandiva (horus+ is not served yet)")
+    return GsHorusParams(HORUS_SCORES[scheme], HORUS_SCHEDULES[schedule], int(num_buffer), 0)
+
+
+class HorusEngine:
+    """`nsims` independent horus / gandiva simulations on one CUDA device (include/gsched_horus.h)."""
+
+    def __init__(self, device=0, nsims=1):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self.nsims = int(nsims)
+        self._n = [0] * self.nsims
+        rc = self.lib.gs_horus_create(int(device), self.nsims, C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.gs_horus_last_error(None)
+            self.h = C.c_void_p()
+            raise GsError(f"gs_horus_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.gs_horus_last_error(self.h)
+            raise GsError(f"{what} failed ({rc}): {msg.decode() if msg else ''}", rc)
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.gs_horus_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def config(self, sim, cluster: GsCluster, params: GsHorusParams):
+        self._check(self.lib.gs_horus_config(self.h, sim, C.byref(cluster), C.byref(params)), "gs_horus_config")
+
+    def load_trace(self, sim, table):
+        arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        a, g, c = arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32)
+        d, m = arr(table.duration, np.float64), arr(table.mem_bytes, np.int64)
+        ua, um = arr(table.util_avg, np.float64), arr(table.util_max, np.float64)
+        self._check(self.lib.gs_horus_load_trace(self.h, sim, table.n, _ptr(a, C.c_int32), _ptr(g, C.c_int32), _ptr(c, C.c_int32),
+                                                 _ptr(d, C.c_double), _ptr(m, C.c_int64), _ptr(ua, C.c_double),
+                                                 _ptr(um, C.c_double)), "gs_horus_load_trace")
+        self._n[sim] = table.n
+
+    def load_stream(self, sim, standard_normal):
+        g = np.ascontiguousarray(standard_normal, dtype=np.float64)
+        self._check(self.lib.gs_horus_load_stream(self.h, sim, _ptr(g, C.c_double), len(g)), "gs_horus_load_stream")
+
+    def run(self, max_ticks=0, rows_cap=1 << 16):
+        self._check(self.lib.gs_horus_run(self.h, int(max_ticks), int(rows_cap)), "gs_horus_run")
+
+    def stats(self, sim) -> GsHorusRunStats:
+        st = GsHorusRunStats()
+        self._check(self.lib.gs_horus_stats(self.h, sim, C.byref(st)), "gs_horus_stats")
+        return st
+
+    def fetch(self, sim):
+        """(rows, utilisation values, is-array flags, job records, finish order)"""
+        from .log_manager import ROW_DTYPE
+        st = self.stats(sim)
+        n, t = self._n[sim], int(st.ticks)
+        rows = np.zeros(max(t, 1), dtype=ROW_DTYPE)
+        util = np.zeros(max(t, 1), dtype=np.float64)
+        flags = np.zeros(max(t, 1), dtype=np.uint8)
+        recs = np.zeros(max(n, 1), dtype=HORUS_REC_DTYPE)
+        order = np.zeros(max(n, 1), dtype=np.int32)
+        nr, nf = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.gs_horus_fetch(self.h, sim, rows.ctypes.data_as(C.c_void_p), _ptr(util, C.c_double),
+                                            _ptr(flags, C.c_uint8), len(rows), recs.ctypes.data_as(C.c_void_p),
+                                            _ptr(order, C.c_int32), C.byref(nr), C.byref(nf)), "gs_horus_fetch")
+        return rows[:nr.value], util[:nr.value], flags[:nr.value], recs[:n], order[:nf.value]
 
 
 class Engine:

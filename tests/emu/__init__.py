@@ -1,0 +1,54 @@
+"""TEST INFRASTRUCTURE: host build of the engine's __host__ __device__ functions (see horus_emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(os.path.dirname(_HERE))
+_OUT = os.path.join(_HERE, "_build", "libhorus_emu.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "horus_emu.cpp")
+    deps = [src, os.path.join(_REPO, "gpuschedule_b200", "csrc", "gs_horus_core.cuh"),
+            os.path.join(_REPO, "include", "gsched.h"), os.path.join(_REPO, "include", "gsched_horus.h")]
+    if not force and os.path.exists(_OUT) and os.path.getmtime(_OUT) >= max(os.path.getmtime(d) for d in deps):
+        return _OUT
+    os.makedirs(os.path.dirname(_OUT), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-x", "c++",
+                    "-I", os.path.join(_REPO, "include"), "-I", os.path.join(_REPO, "gpuschedule_b200", "csrc"),
+                    "-o", _OUT, src], check=True)
+    return _OUT
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emu_run_horus.restype = C.c_longlong
+    return _lib
+
+
+def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0):
+    from gpuschedule_b200.capi import HORUS_REC_DTYPE
+    from gpuschedule_b200.log_manager import ROW_DTYPE
+    n = table.n
+    rows = np.zeros(rows_cap, dtype=ROW_DTYPE)
+    util = np.zeros(rows_cap, dtype=np.float64)
+    util_arr = np.zeros(rows_cap, dtype=np.uint8)
+    recs = np.zeros(max(n, 1), dtype=HORUS_REC_DTYPE)
+    fin = np.zeros(max(n, 1), dtype=np.int32)
+    nfin, events, draws = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+    arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    cols = [arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32),
+            arr(table.duration, np.float64), arr(table.mem_bytes, np.int64), arr(table.util_avg, np.float64),
+            arr(table.util_max, np.float64)]
+    g = arr(gauss, np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ticks = lib().emu_run_horus(C.byref(cluster), C.byref(params), C.c_longlong(n), *[p(c) for c in cols], p(g),
+                                C.c_longlong(len(g)), p(rows), p(util), p(util_arr), C.c_longlong(rows_cap), p(recs), p(fin),
+                                C.byref(nfin), C.byref(events), C.byref(draws), C.c_longlong(max_ticks_per_call))
+    return ticks, rows[:max(ticks, 0)], util[:max(ticks, 0)], util_arr[:max(ticks, 0)], recs[:n], fin[:nfin.value], events.value, draws.value

@@ -12,9 +12,12 @@ from conftest import REPO
 
 
 def _declared_symbols():
-    src = open(os.path.join(REPO, "include", "gsched.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(gs_[a-z_0-9]+)\s*\(", src)))
+    names = set()
+    for header in ("gsched.h", "gsched_horus.h"):
+        src = open(os.path.join(REPO, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(gs_[a-z_0-9]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -23,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     from gpuschedule_b200 import capi
     lib = ctypes.CDLL(capi.LIB_PATH)
     names = _declared_symbols()
-    assert "gs_run" in names and "gs_place_batch" in names and len(names) >= 12
+    assert "gs_run" in names and "gs_place_batch" in names and "gs_horus_run" in names and len(names) >= 22
     for name in names:
         assert hasattr(lib, name), name
     assert lib.gs_abi_version() == 1

@@ -1,0 +1,114 @@
+"""CUDA engine for the utilisation-aware paths (include/gsched_horus.h) vs the reference fixtures
+(tests/golden/horus_* / gandiva_*, bytes of job.csv and cluster.csv incl. the sampled utilisation column)
+and vs the pinned oracle (oracle/horus_oracle.c) on seeded cases; several replicas per launch, resumed runs,
+and the too-short-stream error."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from conftest import horus_cases, load_horus, render_horus_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream(seed, count=1 << 21):
+    np.random.seed(seed)
+    return np.random.standard_normal(count)
+
+
+def _collect(eng, i):
+    rows, util, flags, recs, order = eng.fetch(i)
+    st = eng.stats(i)
+    return SimpleNamespace(rows=rows, util=util, util_is_array=flags, recs=recs, finish_order=order,
+                           events=int(st.events), draws=int(st.draws), ticks=int(st.ticks), done=int(st.done))
+
+
+def _run(jobs, max_ticks=0):
+    """jobs: list of (cluster, table, params); one replica each, one handle."""
+    from gpuschedule_b200 import capi
+    with capi.HorusEngine(device=0, nsims=len(jobs)) as eng:
+        for i, (cluster, table, params) in enumerate(jobs):
+            eng.config(i, cluster, capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"]))
+            eng.load_trace(i, table)
+            eng.load_stream(i, _stream(params["seed"]))
+        launches = 0
+        while True:
+            eng.run(max_ticks=max_ticks, rows_cap=1 << 15)
+            launches += 1
+            if all(eng.stats(i).done for i in range(len(jobs))):
+                break
+            assert launches < 10000
+        return [_collect(eng, i) for i in range(len(jobs))], launches
+
+
+def _served():
+    return [c for c in horus_cases() if load_horus(c)[2]["schedule"] in ("horus", "gandiva", "fifo")]
+
+
+def test_engine_matches_reference_bytes_all_fixtures_one_launch():
+    cases = _served()
+    loaded = [load_horus(c) for c in cases]
+    results, launches = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded])
+    assert launches == 1
+    for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
+        got_job, got_cluster = render_horus_outputs(table, cluster, res)
+        assert got_job == job_csv, case
+        assert got_cluster == cluster_csv, case
+
+
+def test_engine_resumed_every_50_ticks_is_identical():
+    table, cluster, params, job_csv, cluster_csv = load_horus("gandiva_slice")
+    (res,), launches = _run([(cluster, table, params)], max_ticks=50)
+    assert launches > 5
+    got_job, got_cluster = render_horus_outputs(table, cluster, res)
+    assert got_job == job_csv and got_cluster == cluster_csv
+
+
+def _seeded_case(seed):
+    from gpuschedule_b200 import capi, ingest, tracegen
+    rng = np.random.default_rng(300 + seed)
+    kind = ["horus", "gandiva"][seed % 2]
+    G = int(rng.choice([2, 4, 8]))
+    gpc = 2 if seed % 5 == 4 else 1
+    cluster = capi.make_cluster(num_switch=int(rng.integers(1, 4)), num_node_p_switch=int(rng.integers(1, 5)), num_gpu_p_node=G,
+                                num_cpu_p_node=int(rng.choice([36, 60, 128])), mem_p_node=int(rng.choice([180, 300, 512])),
+                                gpu_memory_capacity=int(rng.choice([16, 32])))
+    choices = sorted(set(int(x) * gpc for x in rng.choice([1, 1, 2, 3, 4, 6, 8], size=4)))
+    table = ingest.table_from_columns(tracegen.synth_columns(int(rng.integers(20, 150)), seed=700 + seed, rate=float(rng.choice([1.0, 2.0, 4.0])),
+                                                             gpu_per_container=gpc, gpu_choices=choices, gpu_probs=rng.dirichlet(np.ones(len(choices))),
+                                                             max_mem_mib=int(rng.choice([8000, 16384, 33500]))))
+    return cluster, table, dict(scheme=kind, schedule=kind, num_buffer=int(rng.choice([1, 3, 5])), num_queue=1, seed=2000 + seed)
+
+
+def test_engine_matches_oracle_on_40_heterogeneous_replicas():
+    import oracle
+    jobs = [_seeded_case(s) for s in range(40)]
+    results, _ = _run(jobs)
+    for s, ((cluster, table, params), res) in enumerate(zip(jobs, results)):
+        ref = oracle.run_horus(cluster, table, **params)
+        assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events, s
+        assert res.rows.tobytes() == ref.rows.tobytes(), s
+        assert res.util.tobytes() == ref.util.tobytes() and res.util_is_array.tobytes() == ref.util_is_array.tobytes(), s
+        assert res.recs.tobytes() == ref.recs.tobytes(), s
+        assert np.array_equal(res.finish_order, ref.finish_order), s
+
+
+def test_short_stream_and_unserved_schedule_fail_loudly():
+    from gpuschedule_b200 import capi
+    table, cluster, params, _, _ = load_horus("horus_small")
+    with capi.HorusEngine(device=0, nsims=1) as eng:
+        eng.config(0, cluster, capi.make_horus_params("horus", "horus", 5))
+        eng.load_trace(0, table)
+        eng.load_stream(0, _stream(params["seed"], 1000))
+        with pytest.raises(capi.GsError) as e:
+            eng.run(rows_cap=1 << 15)
+        assert e.value.code == -4
+        eng.load_stream(0, _stream(params["seed"]))          # a longer stream: the run starts over and completes
+        eng.run(rows_cap=1 << 15)
+        assert eng.stats(0).done == 1
+        bad = capi.GsHorusParams(0, 2, 5, 0)                  # horus+ (credit queues) is not served
+        with pytest.raises(capi.GsError):
+            eng.config(0, cluster, bad)
+    with pytest.raises(NotImplementedError):
+        capi.make_horus_params("horus+", "horus+", 15)

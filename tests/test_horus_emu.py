@@ -1,0 +1,103 @@
+"""CPU check of the logic the horus / gandiva CUDA kernel runs.
+
+gpuschedule_b200/csrc/gs_horus_core.cuh is scalar __host__ __device__ code; tests/emu/ compiles that very
+header with g++ and this file compares it, fed with numpy's own standard-normal stream, against
+  * the reference fixtures (tests/golden/horus_* / gandiva_*: job.csv and all 13 cluster.csv columns), and
+  * the pinned oracle (oracle/horus_oracle.c, which carries its own MT19937) on seeded random cases.
+It also proves the stream contract of include/gsched_horus.h: numpy.random.normal(loc, scale, size=1)
+number k equals loc + scale * standard_normal()[k].  The device build of the same functions is checked
+on the GPU by tests/test_gpu_horus.py."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from conftest import horus_cases, load_horus, render_horus_outputs
+
+
+def _served(params):
+    return params["schedule"] in ("horus", "gandiva", "fifo")
+
+
+def _stream(seed, count):
+    np.random.seed(seed)
+    return np.random.standard_normal(count)
+
+
+def _emu(table, cluster, params, count=1 << 21, step=0):
+    from gpuschedule_b200 import capi
+    from tests_emu import run_horus
+    hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"])
+    ticks, rows, util, flags, recs, order, events, draws = run_horus(cluster, hp, table, _stream(params["seed"], count), 1 << 15, step)
+    assert ticks >= 0, ticks
+    return SimpleNamespace(rows=rows, util=util, util_is_array=flags, recs=recs, finish_order=order, events=events, draws=draws, ticks=ticks)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _emu_module():
+    import importlib.util
+    import os
+    import sys
+    from conftest import REPO
+    spec = importlib.util.spec_from_file_location("tests_emu", os.path.join(REPO, "tests", "emu", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["tests_emu"] = mod
+    spec.loader.exec_module(mod)
+    mod.build()
+    yield
+
+
+def test_numpy_stream_contract():
+    np.random.seed(11)
+    g = np.random.standard_normal(2000)
+    np.random.seed(11)
+    rng = np.random.default_rng(5)
+    for k in range(2000):
+        loc, scale = float(rng.uniform(0, 100)), float(rng.uniform(0, 20))
+        assert np.random.normal(loc=loc, scale=scale, size=1)[0] == loc + scale * g[k]
+
+
+@pytest.mark.parametrize("case", [c for c in horus_cases()])
+def test_kernel_logic_matches_reference_bytes(case):
+    table, cluster, params, job_csv, cluster_csv = load_horus(case)
+    if not _served(params):
+        pytest.skip("horus+ is not served by the engine yet (oracle only)")
+    res = _emu(table, cluster, params)
+    got_job, got_cluster = render_horus_outputs(table, cluster, res)
+    assert got_job == job_csv
+    assert got_cluster == cluster_csv
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_kernel_logic_matches_oracle_seeded(seed):
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    rng = np.random.default_rng(100 + seed)
+    kind = ["horus", "gandiva"][seed % 2]
+    G = int(rng.choice([2, 4, 8]))
+    gpc = 2 if seed % 5 == 4 else 1
+    cluster = capi.make_cluster(num_switch=int(rng.integers(1, 4)), num_node_p_switch=int(rng.integers(1, 5)), num_gpu_p_node=G,
+                                num_cpu_p_node=int(rng.choice([36, 60, 128])), mem_p_node=int(rng.choice([180, 300, 512])),
+                                gpu_memory_capacity=int(rng.choice([16, 32])))
+    choices = sorted(set(int(x) * gpc for x in rng.choice([1, 1, 2, 3, 4, 6, 8], size=4)))
+    table = ingest.table_from_columns(tracegen.synth_columns(int(rng.integers(20, 120)), seed=500 + seed, rate=float(rng.choice([1.0, 2.0, 4.0])),
+                                                             gpu_per_container=gpc, gpu_choices=choices, gpu_probs=rng.dirichlet(np.ones(len(choices))),
+                                                             max_mem_mib=int(rng.choice([8000, 16384, 33500]))))
+    params = dict(scheme=kind, schedule=kind, num_buffer=int(rng.choice([1, 3, 5])), num_queue=1, seed=1000 + seed)
+    ref = oracle.run_horus(cluster, table, **params)
+    for step in (0, 37):                                   # one call / resumed every 37 ticks
+        res = _emu(table, cluster, params, step=step)
+        assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events
+        assert res.rows.tobytes() == ref.rows.tobytes()
+        assert res.util.tobytes() == ref.util.tobytes() and res.util_is_array.tobytes() == ref.util_is_array.tobytes()
+        assert res.recs.tobytes() == ref.recs.tobytes()
+        assert np.array_equal(res.finish_order, ref.finish_order)
+
+
+def test_short_stream_is_reported():
+    from gpuschedule_b200 import capi
+    from tests_emu import run_horus
+    table, cluster, params, _, _ = load_horus("horus_small")
+    hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"])
+    ticks = run_horus(cluster, hp, table, _stream(params["seed"], 1000), 1 << 15)[0]
+    assert ticks == -4                                     # GS_ERR_CAPACITY: load a longer stream
