@@ -479,6 +479,50 @@ def place_mode(args):
                                    "kernel": "gs_place_kernel", "traffic": None}}), flush=True)
 
 
+def horus_mode(args):
+    """Secondary measurement (widening row f1): the utilisation-aware engine, `--horus-replicas` independent
+    horus simulations (one thread each, gs_horus_kernel) of `--horus-jobs`-job traces on a 2x4x8 cluster.
+    Replicas have distinct traces and read one common numpy stream (seed 0).  value = events / kernel time
+    (library CUDA events); cpu_baseline = oracle/horus_oracle.c on one host core over a sample of replicas."""
+    import oracle
+    from gpuschedule_b200 import capi
+    R, n = args.horus_replicas, args.horus_jobs
+    cluster = capi.make_cluster(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)
+    tables = [fast_table(n, BASE_SEED + 1000 + r, rate=1.0) for r in range(R)]
+    np.random.seed(0)
+    stream = np.random.standard_normal(args.horus_stream)          # one numpy stream, shared by all replicas
+    hp = capi.make_horus_params("horus", "horus", 5)
+    with capi.HorusEngine(device=0, nsims=R) as eng:
+        for r in range(R):
+            eng.config(r, cluster, hp)
+            eng.load_trace(r, tables[r])
+        by_lanes = {}
+        for lanes in (32, 1):                              # both kernel mappings; the faster one is reported
+            eng.set_lanes(lanes)
+            eng.load_stream(-1, stream)                    # (re)loading the stream starts the replicas over
+            eng.run(rows_cap=args.horus_rows)
+            by_lanes[lanes] = float(eng.stats(0).kernel_ms)
+        st = [eng.stats(r) for r in range(R)]
+        ms = min(by_lanes.values())
+        events = sum(int(x.events) for x in st)
+        ticks = sum(int(x.ticks) for x in st)
+        draws = sum(int(x.draws) for x in st)
+        assert all(x.done for x in st)
+        rows0, util0, flags0, recs0, order0 = eng.fetch(0)
+    ref = oracle.run_horus(cluster, tables[0], scheme="horus", schedule="horus", num_buffer=5, seed=0)
+    assert rows0.tobytes() == ref.rows.tobytes() and util0.tobytes() == ref.util.tobytes(), "replica 0 differs from the oracle"
+    sample = min(R, 64)
+    t0 = time.perf_counter()
+    cpu_ev = sum(oracle.run_horus(cluster, tables[r], scheme="horus", schedule="horus", num_buffer=5, seed=0).events for r in range(sample))
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"metric": "horus simulated events/s (replica batch)", "value": events / (ms / 1e3), "unit": UNIT,
+                      "kernel_ms": ms, "replicas": R, "jobs_per_replica": n, "ticks": ticks, "samples_drawn": draws,
+                      "samples_per_s": draws / (ms / 1e3), "kernel": "gs_horus_kernel (one simulation per thread)", "kernel_ms_by_lanes_per_warp": by_lanes,
+                      "parity": "replica 0 == oracle/horus_oracle.c == reference (tests/golden/horus_*)",
+                      "cpu_baseline": {"value": cpu_ev / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                                       "sample": f"{sample} of the {R} replicas, oracle/horus_oracle.c, one thread"}}), flush=True)
+
+
 def reference(args):
     """The reference arm: the CPU port of the reference's loop on all host cores."""
     rank = int(os.environ.get("RANK", 0))
@@ -571,11 +615,17 @@ def main():
     ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],
                     help="fifo = the headline (pinned) workload; others = secondary, event-driven policy kernel")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 warp per replica, 2 lane per replica")
-    ap.add_argument("--mode", default="sim", choices=["sim", "place"], help="place = gs_place_batch micro-benchmark")
+    ap.add_argument("--mode", default="sim", choices=["sim", "place", "horus"], help="place = gs_place_batch micro-benchmark; horus = utilisation-aware engine")
+    ap.add_argument("--horus-replicas", type=int, default=2368)
+    ap.add_argument("--horus-jobs", type=int, default=60)
+    ap.add_argument("--horus-stream", type=int, default=4000000, help="standard-normal samples loaded per replica")
+    ap.add_argument("--horus-rows", type=int, default=8192)
     ap.add_argument("--place-jobs", type=int, default=64 * 1024 * 1024)
     args = ap.parse_args()
     if args.mode == "place":
         place_mode(args)
+    elif args.mode == "horus":
+        horus_mode(args)
     elif args.impl == "reference":
         reference(args)
     else:

@@ -178,6 +178,8 @@ def load_library(path=None):
     lib.gs_horus_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     lib.gs_horus_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsHorusRunStats)]
     lib.gs_horus_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, f64p, u8p, C.c_int64, C.c_void_p, i32p, i64p, i64p]
+    lib.gs_horus_set_lanes.argtypes = [C.c_void_p, C.c_int]
+    lib.gs_horus_set_lanes.restype = C.c_int
     lib.gs_horus_launch_count.argtypes = [C.c_void_p]
     lib.gs_horus_launch_count.restype = C.c_int64
     lib.gs_horus_last_error.argtypes = [C.c_void_p]
@@ -256,6 +258,10 @@ class HorusEngine:
                                                  _ptr(d, C.c_double), _ptr(m, C.c_int64), _ptr(ua, C.c_double),
                                                  _ptr(um, C.c_double)), "gs_horus_load_trace")
         self._n[sim] = table.n
+
+    def set_lanes(self, lanes):
+        """simulations per warp: 1 (lane 0 of every warp) or 32"""
+        self._check(self.lib.gs_horus_set_lanes(self.h, int(lanes)), "gs_horus_set_lanes")
 
     def load_stream(self, sim, standard_normal):
         g = np.ascontiguousarray(standard_normal, dtype=np.float64)

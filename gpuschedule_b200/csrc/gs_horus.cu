@@ -9,8 +9,10 @@
 #define GS_HD __host__ __device__ __forceinline__
 #include "gs_horus_core.cuh"
 
-__global__ void __launch_bounds__(32) gs_horus_kernel(HSim *sims, int nsims, long long max_ticks) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// lanes = simulations per warp: 32 (every lane drives one) or 1 (lane 0 only: no divergence inside the warp,
+// more warps in flight for the same number of replicas).
+__global__ void __launch_bounds__(32) gs_horus_kernel(HSim *sims, int nsims, long long max_ticks, int lanes) {
+  const int i = lanes == 32 ? blockIdx.x * 32 + threadIdx.x : (threadIdx.x == 0 ? (int)blockIdx.x : nsims);
   if (i >= nsims) return;
   HSim s = sims[i];                 // pointers + scalars in registers / local memory
   if (s.n < 0 || s.done || s.status != 0) return;
@@ -29,6 +31,7 @@ struct HorusSimHost {
   double *d_stream = nullptr; size_t stream_cap = 0;
   HSim dev{};                       // host mirror of the device struct
   long long rows_cap = 0;
+  bool use_shared = false;          // consume the handle-wide stream (gs_horus_load_stream with sim = -1)
 };
 }  // namespace
 
@@ -41,6 +44,9 @@ struct gs_horus_handle_s {
   float last_ms = 0.f;
   long long launches = 0;
   std::string err;
+  std::vector<double> shared;       // one stream consumed by every replica that did not get its own
+  double *d_shared = nullptr; size_t shared_cap = 0; bool shared_dirty = false;
+  int lanes = 1;                    // simulations per warp (gs_horus_set_lanes)
 };
 
 static std::string g_horus_create_err;
@@ -77,6 +83,7 @@ extern "C" int gs_horus_destroy(gs_horus_handle h) {
   if (!h) return GS_ERR_ARG;
   cudaSetDevice(h->device);
   for (auto &s : h->sims) { if (s.slab) cudaFree(s.slab); if (s.d_stream) cudaFree(s.d_stream); }
+  if (h->d_shared) cudaFree(h->d_shared);
   if (h->d_sims) cudaFree(h->d_sims);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -87,6 +94,11 @@ extern "C" int gs_horus_destroy(gs_horus_handle h) {
 
 extern "C" const char *gs_horus_last_error(gs_horus_handle h) { return h ? h->err.c_str() : g_horus_create_err.c_str(); }
 extern "C" int64_t gs_horus_launch_count(gs_horus_handle h) { return h ? h->launches : 0; }
+extern "C" int gs_horus_set_lanes(gs_horus_handle h, int lanes) {
+  if (!h || (lanes != 1 && lanes != 32)) return hfail(h, GS_ERR_ARG, "gs_horus_set_lanes: 1 or 32");
+  h->lanes = lanes;
+  return GS_OK;
+}
 
 extern "C" int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster *c, const gs_horus_params *p) {
   if (!h || !c || !p || sim < 0 || sim >= (int)h->sims.size()) return hfail(h, GS_ERR_ARG, "gs_horus_config: bad arguments");
@@ -124,10 +136,15 @@ extern "C" int gs_horus_load_trace(gs_horus_handle h, int32_t sim, int64_t n, co
 }
 
 extern "C" int gs_horus_load_stream(gs_horus_handle h, int32_t sim, const double *g, int64_t count) {
-  if (!h || sim < 0 || sim >= (int)h->sims.size() || count < 0 || (count > 0 && !g)) return hfail(h, GS_ERR_ARG, "gs_horus_load_stream: bad arguments");
+  if (!h || sim < -1 || sim >= (int)h->sims.size() || count < 0 || (count > 0 && !g)) return hfail(h, GS_ERR_ARG, "gs_horus_load_stream: bad arguments");
+  if (sim == -1) {                  // every replica reads the same samples (each from position 0)
+    h->shared.assign(g, g + count); h->shared_dirty = true;
+    for (auto &s : h->sims) { s.use_shared = true; s.stream.clear(); s.prepared = false; }
+    return GS_OK;
+  }
   auto &s = h->sims[(size_t)sim];
   s.stream.assign(g, g + count);
-  s.prepared = false;
+  s.use_shared = false; s.prepared = false;
   return GS_OK;
 }
 
@@ -186,7 +203,8 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   D.look = (int *)(d + o_look); D.work = (int *)(d + o_work); D.res_nodes = (int *)(d + o_res);
   D.map_node = (int *)(d + o_mn); D.map_order = (int *)(d + o_mo); D.map_n = (int *)(d + o_mc); D.ok = (int *)(d + o_ok); D.distinct = (int *)(d + o_di);
   D.heap = (HCand *)(d + o_heap);
-  D.gauss = s.d_stream; D.gauss_n = (long long)s.stream.size(); D.gauss_pos = 0;
+  D.gauss = s.use_shared ? h->d_shared : s.d_stream;
+  D.gauss_n = (long long)(s.use_shared ? h->shared.size() : s.stream.size()); D.gauss_pos = 0;
   D.rows = (gs_tick_row *)(d + o_rows); D.util = (double *)(d + o_util); D.util_arr = d + o_ua; D.recs = (gs_horus_job_rec *)(d + o_recs);
   D.rows_cap = rows_cap;
   D.current_remaining = (long long)n; D.running_jobs = 0;
@@ -200,6 +218,18 @@ extern "C" int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_c
   HCU(cudaSetDevice(h->device));
   const int nsims = (int)h->sims.size();
   std::vector<HSim> host((size_t)nsims);
+  if (h->shared_dirty) {
+    if (h->shared.size() > h->shared_cap) {
+      if (h->d_shared) cudaFree(h->d_shared);
+      h->d_shared = nullptr;
+      HCU(cudaMalloc(&h->d_shared, 8 * h->shared.size()));
+      h->shared_cap = h->shared.size();
+    }
+    if (!h->shared.empty()) HCU(cudaMemcpyAsync(h->d_shared, h->shared.data(), 8 * h->shared.size(), cudaMemcpyHostToDevice, h->stream));
+    HCU(cudaStreamSynchronize(h->stream));
+    h->shared_dirty = false;
+    for (auto &s : h->sims) if (s.use_shared) s.prepared = false;          // the buffer may have moved
+  }
   for (int i = 0; i < nsims; ++i) {
     auto &s = h->sims[(size_t)i];
     if (!s.configured || !s.loaded) return hfail(h, GS_ERR_STATE, "gs_horus_run: every replica needs gs_horus_config + gs_horus_load_trace");
@@ -208,7 +238,8 @@ extern "C" int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_c
   }
   HCU(cudaMemcpyAsync(h->d_sims, host.data(), sizeof(HSim) * (size_t)nsims, cudaMemcpyHostToDevice, h->stream));
   HCU(cudaEventRecord(h->ev0, h->stream));
-  gs_horus_kernel<<<(nsims + 31) / 32, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks);
+  if (h->lanes == 32) gs_horus_kernel<<<(nsims + 31) / 32, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 32);
+  else gs_horus_kernel<<<nsims, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 1);
   h->launches += 1;
   HCU(cudaGetLastError());
   HCU(cudaEventRecord(h->ev1, h->stream));

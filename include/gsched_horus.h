@@ -70,7 +70,8 @@ int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster *cluster, c
 int gs_horus_load_trace(gs_horus_handle h, int32_t sim, int64_t n, const int32_t *arrive, const int32_t *gpus,
                         const int32_t *gpu_per_task, const double *duration, const int64_t *mem_bytes,
                         const double *util_avg, const double *util_max);
-/* The numpy stream the run consumes (see the header comment). */
+/* The numpy stream the run consumes (see the header comment).  sim = -1: one stream shared by every replica
+ * of the handle, each reading it from position 0 (replicas that differ in trace or parameters only). */
 int gs_horus_load_stream(gs_horus_handle h, int32_t sim, const double *standard_normal, int64_t count);
 /* Scheduler.start() for every configured replica: runs to completion, or max_ticks ticks (0 = no limit). */
 int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_cap);
@@ -79,6 +80,8 @@ int gs_horus_stats(gs_horus_handle h, int32_t sim, gs_horus_run_stats *out);
  * array" flag (how str() prints it), and the job records in finish order. */
 int gs_horus_fetch(gs_horus_handle h, int32_t sim, gs_tick_row *rows, double *util, uint8_t *util_is_array,
                    int64_t rows_cap, gs_horus_job_rec *recs, int32_t *finish_order, int64_t *n_rows, int64_t *n_finished);
+/* Kernel mapping (no reference counterpart): simulations per warp, 1 (default, lane 0 of each warp) or 32. */
+int gs_horus_set_lanes(gs_horus_handle h, int lanes_per_warp);
 int64_t gs_horus_launch_count(gs_horus_handle h);
 const char *gs_horus_last_error(gs_horus_handle h);
 

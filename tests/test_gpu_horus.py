@@ -24,10 +24,11 @@ def _collect(eng, i):
                            events=int(st.events), draws=int(st.draws), ticks=int(st.ticks), done=int(st.done))
 
 
-def _run(jobs, max_ticks=0):
+def _run(jobs, max_ticks=0, lanes=1):
     """jobs: list of (cluster, table, params); one replica each, one handle."""
     from gpuschedule_b200 import capi
     with capi.HorusEngine(device=0, nsims=len(jobs)) as eng:
+        eng.set_lanes(lanes)
         for i, (cluster, table, params) in enumerate(jobs):
             eng.config(i, cluster, capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"]))
             eng.load_trace(i, table)
@@ -49,7 +50,7 @@ def _served():
 def test_engine_matches_reference_bytes_all_fixtures_one_launch():
     cases = _served()
     loaded = [load_horus(c) for c in cases]
-    results, launches = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded])
+    results, launches = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded], lanes=32)
     assert launches == 1
     for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
         got_job, got_cluster = render_horus_outputs(table, cluster, res)
@@ -81,10 +82,11 @@ def _seeded_case(seed):
     return cluster, table, dict(scheme=kind, schedule=kind, num_buffer=int(rng.choice([1, 3, 5])), num_queue=1, seed=2000 + seed)
 
 
-def test_engine_matches_oracle_on_40_heterogeneous_replicas():
+@pytest.mark.parametrize("lanes", [1, 32])
+def test_engine_matches_oracle_on_40_heterogeneous_replicas(lanes):
     import oracle
     jobs = [_seeded_case(s) for s in range(40)]
-    results, _ = _run(jobs)
+    results, _ = _run(jobs, lanes=lanes)
     for s, ((cluster, table, params), res) in enumerate(zip(jobs, results)):
         ref = oracle.run_horus(cluster, table, **params)
         assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events, s
