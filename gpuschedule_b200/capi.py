@@ -83,6 +83,9 @@ def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), git
     return p
 
 
+GS_OK, GS_ERR_ARG, GS_ERR_CUDA, GS_ERR_STATE, GS_ERR_CAPACITY = 0, -1, -2, -3, -4      # enum gs_status
+
+
 class GsError(RuntimeError):
     def __init__(self, msg, code=None):
         super().__init__(msg)

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 from . import ingest
 
-SUPPORTED_SCHEDULES = ("fifo", "sjf", "dlas", "dlas-gpu", "gittins")
+SUPPORTED_SCHEDULES = ("fifo", "sjf", "dlas", "dlas-gpu", "gittins", "horus", "gandiva")   # horus+: oracle only so far
 
 
 class JobQueueManager:

@@ -111,6 +111,18 @@ def job_lines(table, recs, finish_order):
                                                    recs["jct"][order].tolist(), recs["preempt"][order].tolist())]
 
 
+def horus_job_lines(table, recs, finish_order):
+    """job.csv lines from gs_horus_job_rec records: Job.duration and Job.get_duration() differ once a task has
+    carried an interference penalty (jobs_manager.py:189-201), so both come from the engine."""
+    order = np.asarray(finish_order, dtype=np.int64)
+    label, gtext = table.label, table.num_gpu_text
+    return [",".join((label[j], gtext[j], str(sb), str(st), str(en), repr(o), repr(a), str(jc), str(pr)))
+            for j, sb, st, en, o, a, jc, pr in zip(order.tolist(), table.submit[order].tolist(), recs["start"][order].tolist(),
+                                                   recs["end"][order].tolist(), recs["original"][order].tolist(),
+                                                   recs["actual"][order].tolist(), recs["jct"][order].tolist(),
+                                                   recs["preempt"][order].tolist())]
+
+
 class LogManager:
     def __init__(self, log_path, flags):
         self.log_path = log_path
@@ -166,11 +178,21 @@ class LogManager:
             if lines:
                 f.write(EOL.join(lines) + EOL)
 
+    def write_horus_job_rows(self, table, recs, finish_order):
+        assert len(finish_order) > 0, ValueError("No finished jobs")
+        with open(self.log_job, "a", newline="") as f:
+            f.write(EOL.join(horus_job_lines(table, recs, finish_order)) + EOL)
+
     def write_job_rows(self, table, recs, finish_order):
         assert len(finish_order) > 0, ValueError("No finished jobs")
         lines = job_lines(table, recs, finish_order)
         with open(self.log_job, "a", newline="") as f:
             f.write(EOL.join(lines) + EOL)
+
+
+def render_horus_job_csv(table, recs, finish_order):
+    body = horus_job_lines(table, recs, finish_order)
+    return _line(JOB_HEADER) + (EOL.join(body) + EOL if body else "")
 
 
 def render_cluster_csv(rows, util_text, total_cap_mib):

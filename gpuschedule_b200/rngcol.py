@@ -119,3 +119,11 @@ def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, span
         out.extend("0.0" if c == 0 else (bk if na > 0 else repr(float(int(ac) / total)))
                    for c, na, bk, ac in zip(counts.tolist(), n_arr.tolist(), brack, acc.tolist()))
     return out
+
+
+def sampled_utilization_text(values, is_array):
+    """Text of avg_gpu_utilization when the ENGINE sampled it (horus / gandiva: the samples are part of the
+    scheduling decisions, so the column cannot be replayed afterwards).  A row whose sum saw an un-clipped
+    sample is a 1-element numpy array in the reference and prints bracketed; otherwise it is a plain float."""
+    bracketed = _format_bracketed(values)
+    return [b if a else repr(float(v)) for b, a, v in zip(bracketed, np.asarray(is_array).tolist(), np.asarray(values).tolist())]

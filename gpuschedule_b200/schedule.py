@@ -33,7 +33,49 @@ class Scheduler:
                       gittins_table=policies.build_gittins_table(policies.gittins_samples(table), delta))
         return capi.make_policy(self.schedule, self.placement if self.placement in capi.SCHEMES else "yarn", **kw)
 
+    UTILISATION_AWARE = ("horus", "gandiva")
+
+    def _start_utilisation_aware(self):
+        """--scheme horus|gandiva: score-based placement with look-ahead / time slicing (include/gsched_horus.h).
+        The reference samples numpy's global stream inside these decisions; the engine gets the same stream as
+        standard-normal values drawn HERE from numpy's global generator, so `numpy.random.seed(s)` before
+        start() reproduces a seeded reference run bit for bit (and an unseeded run is random, as there)."""
+        import numpy as np
+        t0 = time.time()
+        infra, table = self.infrastructure, self.jobs_manager.table
+        flags = infra.flags
+        cluster = infra.gs_cluster()
+        params = capi.make_horus_params(self.placement, self.schedule, int(getattr(flags, "num_buffer", 5)))
+        stream = np.random.standard_normal(1 << 21)
+        rows_cap = 1 << 16
+        with capi.HorusEngine(device=getattr(flags, "device", 0), nsims=1) as eng:
+            eng.config(0, cluster, params)
+            eng.load_trace(0, table)
+            while True:
+                eng.load_stream(0, stream)
+                try:
+                    eng.run(rows_cap=rows_cap)
+                    break
+                except capi.GsError as e:
+                    if e.code != capi.GS_ERR_CAPACITY:
+                        raise
+                    if eng.stats(0).draws >= len(stream):        # ran out of samples: continue numpy's stream
+                        stream = np.concatenate([stream, np.random.standard_normal(len(stream))])
+                    else:                                         # ran out of rows
+                        rows_cap *= 2
+            rows, util, flags_arr, recs, order = eng.fetch(0)
+            self.stats = eng.stats(0)
+        m = cluster.num_switch * cluster.num_node_p_switch
+        g = cluster.num_gpu_p_node
+        self.log_manager.write_cluster_rows(rows, rngcol.sampled_utilization_text(util, flags_arr), m * g * cluster.gpu_mem_cap_mib)
+        logging.info("Total Time Taken in seconds: %d" % (time.time() - t0))
+        self.log_manager.write_horus_job_rows(table, recs, order)
+        self.rows, self.recs, self.finish_order = rows, recs, order
+        return self.stats
+
     def start(self):
+        if self.placement in self.UTILISATION_AWARE or self.schedule in self.UTILISATION_AWARE:
+            return self._start_utilisation_aware()
         t0 = time.time()
         infra, table = self.infrastructure, self.jobs_manager.table
         cluster = infra.gs_cluster()

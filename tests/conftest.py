@@ -75,22 +75,13 @@ def load_horus(case):
 
 
 def render_horus_outputs(table, cluster, res):
-    """job.csv / cluster.csv text of a horus-family result (rows + utilisation values + 6-field job records)."""
-    import numpy as np
+    """job.csv / cluster.csv text of a horus-family result, through the package's own formatters."""
     from gpuschedule_b200 import log_manager, rngcol
     m = cluster.num_switch * cluster.num_node_p_switch
     g = cluster.num_gpu_p_node
-    bracketed = rngcol._format_bracketed(res.util)
-    # a row whose sum saw an un-clipped draw is a 1-element numpy array, otherwise a plain Python number
-    util = [b if a else repr(float(v)) for b, a, v in zip(bracketed, res.util_is_array.tolist(), res.util.tolist())]
+    util = rngcol.sampled_utilization_text(res.util, res.util_is_array)
     cluster_csv = log_manager.render_cluster_csv(res.rows, util, m * g * cluster.gpu_mem_cap_mib)
-    rec = res.recs
-    lines = [",".join((table.label[j], table.num_gpu_text[j], str(int(table.submit[j])), str(int(rec["start"][j])),
-                       str(int(rec["end"][j])), repr(float(rec["original"][j])), repr(float(rec["actual"][j])),
-                       str(int(rec["jct"][j])), str(int(rec["preempt"][j]))))
-             for j in np.asarray(res.finish_order, dtype=np.int64).tolist()]
-    job_csv = log_manager._line(log_manager.JOB_HEADER) + (log_manager.EOL.join(lines) + log_manager.EOL if lines else "")
-    return job_csv, cluster_csv
+    return log_manager.render_horus_job_csv(table, res.recs, res.finish_order), cluster_csv
 
 
 @pytest.fixture(scope="session")

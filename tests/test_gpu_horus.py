@@ -114,3 +114,30 @@ def test_short_stream_and_unserved_schedule_fail_loudly():
             eng.config(0, cluster, bad)
     with pytest.raises(NotImplementedError):
         capi.make_horus_params("horus+", "horus+", 15)
+
+
+@pytest.mark.parametrize("case", ["horus_racks", "gandiva_small"])
+def test_cli_run_sim_horus_writes_reference_bytes(case, tmp_path):
+    """run_sim.py --scheme horus|gandiva end to end: same flags as the reference, same files, same bytes."""
+    import glob
+    import json
+    import os
+    import shutil
+    import subprocess
+    import sys
+    from conftest import GOLDEN, REPO
+    f = json.load(open(os.path.join(GOLDEN, case, "horus.json")))
+    fl = f["flags"]
+    shutil.copy(os.path.join(GOLDEN, case, "trace.csv"), tmp_path / "trace.csv")
+    cmd = [sys.executable, os.path.join(REPO, "run_sim.py"), "--scheme", fl["_scheme"], "--schedule", fl["_schedule"],
+           "--trace_file", "trace.csv", "--log_path", "g", "--seed", str(f["numpy_seed"])]
+    for k, v in fl.items():
+        if not k.startswith("_"):
+            cmd += ["--" + k, str(v)]
+    subprocess.run(cmd, cwd=tmp_path, check=True, capture_output=True)
+    runs = glob.glob(str(tmp_path / "log" / "g" / "*"))
+    assert len(runs) == 1
+    for name in ("job.csv", "cluster.csv"):
+        got = open(os.path.join(runs[0], name), newline="").read()
+        exp = open(os.path.join(GOLDEN, case, name), newline="").read()
+        assert got == exp, name

@@ -101,3 +101,69 @@ def test_short_stream_is_reported():
     hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"])
     ticks = run_horus(cluster, hp, table, _stream(params["seed"], 1000), 1 << 15)[0]
     assert ticks == -4                                     # GS_ERR_CAPACITY: load a longer stream
+
+
+class _EmuHorusEngine:
+    """Same interface as capi.HorusEngine, backed by the host build of the device functions: lets the host-side
+    mirror (Scheduler.start -> stream chunks, retry on GS_ERR_CAPACITY, formatting, file writing) run on CPU."""
+
+    def __init__(self, device=0, nsims=1):
+        assert nsims == 1
+        self.res = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        pass
+
+    def config(self, sim, cluster, params):
+        self.cluster, self.params = cluster, params
+
+    def load_trace(self, sim, table):
+        self.table = table
+
+    def load_stream(self, sim, g):
+        self.g = np.array(g)
+
+    def run(self, max_ticks=0, rows_cap=1 << 16):
+        from gpuschedule_b200 import capi
+        from tests_emu import run_horus
+        out = run_horus(self.cluster, self.params, self.table, self.g, rows_cap)
+        self.res = out
+        self.draws = out[7]
+        if out[0] < 0:
+            raise capi.GsError("emulated gs_horus_run failed", out[0])
+
+    def stats(self, sim):
+        return SimpleNamespace(ticks=max(self.res[0], 0), events=self.res[6], draws=self.draws, finished=len(self.res[5]), done=1, kernel_ms=0.0)
+
+    def fetch(self, sim):
+        return self.res[1], self.res[2], self.res[3], self.res[4], self.res[5]
+
+
+@pytest.mark.parametrize("case", ["horus_small", "gandiva_slice"])
+def test_host_mirror_writes_reference_bytes(case, tmp_path, monkeypatch):
+    """Scheduler.start() for --scheme horus|gandiva: numpy's global stream is handed to the engine in chunks (a
+    first chunk that is too short makes the run start over with a longer one) and the files equal the reference's."""
+    import os
+    import shutil
+    from conftest import GOLDEN
+    from gpuschedule_b200 import capi, infrastructure, jobs, log_manager, schedule, sweep
+    table, cluster, params, job_csv, cluster_csv = load_horus(case)
+    shutil.copy(os.path.join(GOLDEN, case, "trace.csv"), tmp_path / "trace.csv")
+    fl = sweep.make_flags(trace_file=str(tmp_path / "trace.csv"), scheme=params["scheme"], schedule=params["schedule"],
+                          num_buffer=params["num_buffer"], num_switch=cluster.num_switch,
+                          num_node_p_switch=cluster.num_node_p_switch, num_gpu_p_node=cluster.num_gpu_p_node)
+    monkeypatch.setattr(capi, "HorusEngine", _EmuHorusEngine)
+    real = np.random.standard_normal
+    monkeypatch.setattr(np.random, "standard_normal", lambda n: real(min(n, 20000)))    # force the "stream too short" retries
+    infra = infrastructure.Infrastructure(fl)
+    jm = jobs.JobsManager(fl, jobs.JobQueueManager(fl, fl.trace_file))
+    lm = log_manager.LogManager(str(tmp_path), fl)
+    lm.init(infra)
+    np.random.seed(params["seed"])
+    stats = schedule.Scheduler(infra, jm, lm).start()
+    assert stats.draws > 20000
+    assert open(tmp_path / "job.csv", newline="").read() == job_csv
+    assert open(tmp_path / "cluster.csv", newline="").read() == cluster_csv
