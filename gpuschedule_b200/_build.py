@@ -11,7 +11,7 @@ SRC = os.path.join(HERE, "csrc", "gsched.cu")
 SRC_HORUS = os.path.join(HERE, "csrc", "gs_horus.cu")          # utilisation-aware placement engine (gsched_horus.h)
 OUT = os.path.join(HERE, "libgsched.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(REPO, "include")]
+         "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-I", os.path.join(REPO, "include")]
 
 
 def nvcc_path():

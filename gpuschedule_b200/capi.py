@@ -176,7 +176,8 @@ def load_library(path=None):
     lib.gs_horus_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.gs_horus_destroy.argtypes = [C.c_void_p]
     lib.gs_horus_config.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsCluster), C.POINTER(GsHorusParams)]
-    lib.gs_horus_load_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int64, i32p, i32p, i32p, f64p, i64p, f64p, f64p]
+    lib.gs_horus_load_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int64, i32p, i32p, i32p, f64p, i64p, f64p, f64p, f64p]
+    lib.gs_horus_load_words.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_int64]
     lib.gs_horus_load_stream.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
     lib.gs_horus_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     lib.gs_horus_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsHorusRunStats)]
@@ -187,7 +188,7 @@ def load_library(path=None):
     lib.gs_horus_launch_count.restype = C.c_int64
     lib.gs_horus_last_error.argtypes = [C.c_void_p]
     lib.gs_horus_last_error.restype = C.c_char_p
-    for name in ("gs_horus_create", "gs_horus_destroy", "gs_horus_config", "gs_horus_load_trace", "gs_horus_load_stream",
+    for name in ("gs_horus_create", "gs_horus_destroy", "gs_horus_config", "gs_horus_load_trace", "gs_horus_load_stream", "gs_horus_load_words",
                  "gs_horus_run", "gs_horus_stats", "gs_horus_fetch"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -195,7 +196,7 @@ def load_library(path=None):
 
 
 class GsHorusParams(C.Structure):
-    _fields_ = [("score", C.c_int32), ("schedule", C.c_int32), ("num_buffer", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("score", C.c_int32), ("schedule", C.c_int32), ("num_buffer", C.c_int32), ("num_queue", C.c_int32)]
 
 
 class GsHorusRunStats(C.Structure):
@@ -206,15 +207,15 @@ class GsHorusRunStats(C.Structure):
 
 HORUS_REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"), ("preempt", "<i4"),
                             ("original", "<f8"), ("actual", "<f8")])
-HORUS_SCORES = {"horus": 0, "gandiva": 1}                 # --scheme  (core/scheduling/algorithm.py:9-13)
-HORUS_SCHEDULES = {"fifo": 0, "horus": 1, "gandiva": 3}   # --schedule (algorithm.py:292-298)
+HORUS_SCORES = {"horus": 0, "horus+": 0, "gandiva": 1}               # --scheme  (core/scheduling/algorithm.py:9-13)
+HORUS_SCHEDULES = {"fifo": 0, "horus": 1, "horus+": 2, "gandiva": 3}   # --schedule (algorithm.py:292-298)
 
 
-def make_horus_params(scheme="horus", schedule="horus", num_buffer=5):
+def make_horus_params(scheme="horus", schedule="horus", num_buffer=5, num_queue=1):
     if scheme not in HORUS_SCORES or schedule not in HORUS_SCHEDULES:
         raise NotImplementedError(f"scheme {scheme!r} / schedule {schedule!r}: the utilisation-aware engine serves "
-                                  "horus and gandiva (horus+ is not served yet)")
-    return GsHorusParams(HORUS_SCORES[scheme], HORUS_SCHEDULES[schedule], int(num_buffer), 0)
+                                  "the horus, horus+ and gandiva schemes with the fifo, horus, horus+ and gandiva schedules")
+    return GsHorusParams(HORUS_SCORES[scheme], HORUS_SCHEDULES[schedule], int(num_buffer), int(num_queue))
 
 
 class HorusEngine:
@@ -257,9 +258,11 @@ class HorusEngine:
         a, g, c = arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32)
         d, m = arr(table.duration, np.float64), arr(table.mem_bytes, np.int64)
         ua, um = arr(table.util_avg, np.float64), arr(table.util_max, np.float64)
+        ma = table.extra.get("mem_avg_mib")
+        ma = None if ma is None else arr(ma, np.float64)
         self._check(self.lib.gs_horus_load_trace(self.h, sim, table.n, _ptr(a, C.c_int32), _ptr(g, C.c_int32), _ptr(c, C.c_int32),
                                                  _ptr(d, C.c_double), _ptr(m, C.c_int64), _ptr(ua, C.c_double),
-                                                 _ptr(um, C.c_double)), "gs_horus_load_trace")
+                                                 _ptr(um, C.c_double), _ptr(ma, C.c_double)), "gs_horus_load_trace")
         self._n[sim] = table.n
 
     def set_lanes(self, lanes):
@@ -269,6 +272,11 @@ class HorusEngine:
     def load_stream(self, sim, standard_normal):
         g = np.ascontiguousarray(standard_normal, dtype=np.float64)
         self._check(self.lib.gs_horus_load_stream(self.h, sim, _ptr(g, C.c_double), len(g)), "gs_horus_load_stream")
+
+    def load_words(self, sim, mt19937_words):
+        """raw generator words (numpy.random.randint(0, 2**32, n, dtype=uint32)); required for horus+"""
+        w = np.ascontiguousarray(mt19937_words, dtype=np.uint32)
+        self._check(self.lib.gs_horus_load_words(self.h, sim, _ptr(w, C.c_uint32), len(w)), "gs_horus_load_words")
 
     def run(self, max_ticks=0, rows_cap=1 << 16):
         self._check(self.lib.gs_horus_run(self.h, int(max_ticks), int(rows_cap)), "gs_horus_run")

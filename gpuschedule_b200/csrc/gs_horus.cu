@@ -8,6 +8,7 @@
 
 #define GS_HD __host__ __device__ __forceinline__
 #include "gs_horus_core.cuh"
+#include "gs_horus_host.h"
 
 // lanes = simulations per warp: 32 (every lane drives one) or 1 (lane 0 only: no divergence inside the warp,
 // more warps in flight for the same number of replicas).
@@ -21,6 +22,11 @@ __global__ void __launch_bounds__(32) gs_horus_kernel(HSim *sims, int nsims, lon
 }
 
 namespace {
+struct WordStream {                 // raw MT19937 words + the per-position sample tables (gs_horus_host.h)
+  std::vector<uint32_t> words;
+  unsigned char *dev = nullptr; size_t cap = 0; bool dirty = false;
+  const unsigned int *d_words = nullptr; const double *d_ret = nullptr, *d_keep = nullptr; const int *d_next = nullptr;
+};
 struct HorusSimHost {
   bool configured = false, loaded = false, prepared = false;
   gs_cluster cl{};
@@ -32,6 +38,8 @@ struct HorusSimHost {
   HSim dev{};                       // host mirror of the device struct
   long long rows_cap = 0;
   bool use_shared = false;          // consume the handle-wide stream (gs_horus_load_stream with sim = -1)
+  WordStream ws; int word_mode = 0; // 0: standard-normal values, 1: own words, 2: the handle-wide words
+  std::vector<double> mem_avg;
 };
 }  // namespace
 
@@ -47,6 +55,7 @@ struct gs_horus_handle_s {
   std::vector<double> shared;       // one stream consumed by every replica that did not get its own
   double *d_shared = nullptr; size_t shared_cap = 0; bool shared_dirty = false;
   int lanes = 1;                    // simulations per warp (gs_horus_set_lanes)
+  WordStream shared_ws;
 };
 
 static std::string g_horus_create_err;
@@ -82,8 +91,9 @@ extern "C" int gs_horus_create(int device, int nsims, gs_horus_handle *out) {
 extern "C" int gs_horus_destroy(gs_horus_handle h) {
   if (!h) return GS_ERR_ARG;
   cudaSetDevice(h->device);
-  for (auto &s : h->sims) { if (s.slab) cudaFree(s.slab); if (s.d_stream) cudaFree(s.d_stream); }
+  for (auto &s : h->sims) { if (s.slab) cudaFree(s.slab); if (s.d_stream) cudaFree(s.d_stream); if (s.ws.dev) cudaFree(s.ws.dev); }
   if (h->d_shared) cudaFree(h->d_shared);
+  if (h->shared_ws.dev) cudaFree(h->shared_ws.dev);
   if (h->d_sims) cudaFree(h->d_sims);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -105,8 +115,10 @@ extern "C" int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster 
   if (c->num_switch <= 0 || c->num_node_p_switch <= 0 || c->num_gpu_p_node <= 0 || c->num_gpu_p_node > 64)
     return hfail(h, GS_ERR_ARG, "gs_horus_config: bad cluster shape");
   if (p->score != GS_HSCORE_HORUS && p->score != GS_HSCORE_GANDIVA) return hfail(h, GS_ERR_ARG, "gs_horus_config: unknown score function");
-  if (p->schedule != GS_HSCHED_FIFO && p->schedule != GS_HSCHED_HORUS && p->schedule != GS_HSCHED_GANDIVA)
-    return hfail(h, GS_ERR_ARG, "gs_horus_config: schedule must be fifo, horus or gandiva (horus+ is not served yet)");
+  if (p->schedule != GS_HSCHED_FIFO && p->schedule != GS_HSCHED_HORUS && p->schedule != GS_HSCHED_HORUS_PLUS && p->schedule != GS_HSCHED_GANDIVA)
+    return hfail(h, GS_ERR_ARG, "gs_horus_config: schedule must be fifo, horus, horus+ or gandiva");
+  if (p->schedule == GS_HSCHED_HORUS_PLUS && (p->num_queue < 1 || p->num_queue > H_MAXQ))
+    return hfail(h, GS_ERR_ARG, "gs_horus_config: horus+ needs 1..8 queues");
   if (c->enable_network_costs) return hfail(h, GS_ERR_ARG, "gs_horus_config: network costs are not part of this path");
   auto &s = h->sims[(size_t)sim];
   s.cl = *c; s.par = *p; s.configured = true; s.prepared = false;
@@ -115,7 +127,7 @@ extern "C" int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster 
 
 extern "C" int gs_horus_load_trace(gs_horus_handle h, int32_t sim, int64_t n, const int32_t *arrive, const int32_t *gpus,
                                    const int32_t *gpc, const double *duration, const int64_t *mem_bytes,
-                                   const double *util_avg, const double *util_max) {
+                                   const double *util_avg, const double *util_max, const double *mem_avg_mib) {
   if (!h || sim < 0 || sim >= (int)h->sims.size() || n < 0 || n > 0x3fffffff) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: bad arguments");
   if (n > 0 && (!arrive || !gpus || !gpc || !duration || !mem_bytes || !util_avg || !util_max)) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: null column");
   auto &s = h->sims[(size_t)sim];
@@ -128,6 +140,7 @@ extern "C" int gs_horus_load_trace(gs_horus_handle h, int32_t sim, int64_t n, co
     HJob &o = s.jobs[(size_t)j];
     o.arrive = arrive[j]; o.gpus = gpus[j]; o.gpc = gpc[j]; o.ntasks = gpus[j] / gpc[j]; o.first_task = (int)first; o.pad = 0;
     o.mem_b = mem_bytes[j]; o.util_avg = util_avg[j]; o.util_max = util_max[j]; o.duration = duration[j];
+    o.mem_avg_mib = mem_avg_mib ? mem_avg_mib[j] : 0.0;
     first += o.ntasks;
     if (first > 0x3fffffff) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: too many tasks");
   }
@@ -139,12 +152,46 @@ extern "C" int gs_horus_load_stream(gs_horus_handle h, int32_t sim, const double
   if (!h || sim < -1 || sim >= (int)h->sims.size() || count < 0 || (count > 0 && !g)) return hfail(h, GS_ERR_ARG, "gs_horus_load_stream: bad arguments");
   if (sim == -1) {                  // every replica reads the same samples (each from position 0)
     h->shared.assign(g, g + count); h->shared_dirty = true;
-    for (auto &s : h->sims) { s.use_shared = true; s.stream.clear(); s.prepared = false; }
+    for (auto &s : h->sims) { s.use_shared = true; s.stream.clear(); s.prepared = false; s.word_mode = 0; }
     return GS_OK;
   }
   auto &s = h->sims[(size_t)sim];
   s.stream.assign(g, g + count);
-  s.use_shared = false; s.prepared = false;
+  s.use_shared = false; s.prepared = false; s.word_mode = 0;
+  return GS_OK;
+}
+
+extern "C" int gs_horus_load_words(gs_horus_handle h, int32_t sim, const uint32_t *w, int64_t count) {
+  if (!h || sim < -1 || sim >= (int)h->sims.size() || count < 0 || count > 0x7ffffff0 || (count > 0 && !w)) return hfail(h, GS_ERR_ARG, "gs_horus_load_words: bad arguments");
+  if (sim == -1) {
+    h->shared_ws.words.assign(w, w + count); h->shared_ws.dirty = true;
+    for (auto &s : h->sims) { s.word_mode = 2; s.prepared = false; }
+    return GS_OK;
+  }
+  auto &s = h->sims[(size_t)sim];
+  s.ws.words.assign(w, w + count); s.ws.dirty = true;
+  s.word_mode = 1; s.prepared = false;
+  return GS_OK;
+}
+
+static int upload_words(gs_horus_handle h, WordStream &ws) {
+  if (!ws.dirty) return GS_OK;
+  const size_t n = ws.words.size(), N = n ? n : 1;
+  const size_t o_w = 0, o_ret = up(4 * N), o_keep = up(o_ret + 8 * N), o_next = up(o_keep + 8 * N), total = up(o_next + 4 * N);
+  if (ws.dev && ws.cap < total) { cudaFree(ws.dev); ws.dev = nullptr; }
+  if (!ws.dev) { HCU(cudaMalloc(&ws.dev, total)); ws.cap = total; }
+  std::vector<double> ret(N), keep(N); std::vector<int> next(N);
+  gs_horus_build_gauss_tables(ws.words.data(), (long long)n, ret.data(), keep.data(), next.data());
+  if (n) {
+    HCU(cudaMemcpyAsync(ws.dev + o_w, ws.words.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    HCU(cudaMemcpyAsync(ws.dev + o_ret, ret.data(), 8 * n, cudaMemcpyHostToDevice, h->stream));
+    HCU(cudaMemcpyAsync(ws.dev + o_keep, keep.data(), 8 * n, cudaMemcpyHostToDevice, h->stream));
+    HCU(cudaMemcpyAsync(ws.dev + o_next, next.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+  }
+  HCU(cudaStreamSynchronize(h->stream));
+  ws.d_words = (const unsigned int *)(ws.dev + o_w); ws.d_ret = (const double *)(ws.dev + o_ret);
+  ws.d_keep = (const double *)(ws.dev + o_keep); ws.d_next = (const int *)(ws.dev + o_next);
+  ws.dirty = false;
   return GS_OK;
 }
 
@@ -157,13 +204,18 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   const size_t NT = ntask ? (size_t)ntask : 1;
   const int pjw = (M + 63) / 64;
   const int nb = std::max(1, s.par.num_buffer);
+  const int nq = s.par.schedule == GS_HSCHED_HORUS_PLUS ? std::max(1, s.par.num_queue) : 1;
+  if (s.par.schedule == GS_HSCHED_HORUS_PLUS && s.word_mode == 0)
+    return hfail(h, GS_ERR_STATE, "gs_horus_run: horus+ draws integers too: load the raw stream with gs_horus_load_words");
+  if (s.word_mode == 1) { int rc = upload_words(h, s.ws); if (rc) return rc; }
   if (rows_cap <= 0) return hfail(h, GS_ERR_ARG, "gs_horus_run: rows_cap must be positive");
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = up(off + bytes); return o; };
   const size_t o_jobs = take(sizeof(HJob) * N), o_js = take(sizeof(HJobState) * N), o_tasks = take(sizeof(HTask) * NT);
   const size_t o_tron = take(4 * NT), o_troo = take(4 * NT), o_nodes = take(sizeof(HNode) * (size_t)M), o_devs = take(sizeof(HDev) * (size_t)M * G);
-  const size_t o_pj = take(8 * N * (size_t)pjw), o_q = take(4 * (N + 1)), o_run = take(4 * N), o_fin = take(4 * N);
-  const size_t o_look = take(4 * (size_t)nb), o_work = take(4 * N), o_res = take(4 * (size_t)M);
+  const size_t o_pj = take(8 * N * (size_t)pjw), o_q = take(4 * (N + 1) * (size_t)nq), o_run = take(4 * N), o_fin = take(4 * N);
+  const size_t o_look = take(4 * (size_t)nb), o_lookq = take(4 * (size_t)nb), o_work = take(4 * N), o_res = take(4 * (size_t)M);
+  const size_t o_kall = take(4 * N), o_kas = take(4 * N), o_kold = take(4 * N), o_ksc = take(8 * N);
   const size_t o_mn = take(4 * (size_t)maxg * maxg), o_mo = take(4 * (size_t)maxg * maxg), o_mc = take(4 * (size_t)maxg);
   const size_t o_ok = take(4 * (size_t)maxg), o_di = take(4 * (size_t)maxg), o_heap = take(sizeof(HCand) * ((size_t)maxg + 2));
   const size_t o_rows = take(sizeof(gs_tick_row) * (size_t)rows_cap), o_util = take(8 * (size_t)rows_cap), o_ua = take((size_t)rows_cap);
@@ -200,7 +252,13 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   D.jobs = (const HJob *)(d + o_jobs); D.js = (HJobState *)(d + o_js); D.tasks = (HTask *)(d + o_tasks);
   D.tro_node = (int *)(d + o_tron); D.tro_order = (int *)(d + o_troo); D.nodes = (HNode *)(d + o_nodes); D.devs = (HDev *)(d + o_devs);
   D.pj_bits = (unsigned long long *)(d + o_pj); D.queue = (int *)(d + o_q); D.running = (int *)(d + o_run); D.fin = (int *)(d + o_fin);
-  D.look = (int *)(d + o_look); D.work = (int *)(d + o_work); D.res_nodes = (int *)(d + o_res);
+  D.look = (int *)(d + o_look); D.look_q = (int *)(d + o_lookq); D.work = (int *)(d + o_work); D.res_nodes = (int *)(d + o_res);
+  D.km_all = (int *)(d + o_kall); D.km_assign = (int *)(d + o_kas); D.km_old = (int *)(d + o_kold); D.km_score = (double *)(d + o_ksc);
+  D.nq = nq;
+  if (s.word_mode) {
+    const WordStream &ws = s.word_mode == 1 ? s.ws : h->shared_ws;
+    D.words = ws.d_words; D.gv_ret = ws.d_ret; D.gv_keep = ws.d_keep; D.gv_next = ws.d_next; D.words_n = (long long)ws.words.size();
+  }
   D.map_node = (int *)(d + o_mn); D.map_order = (int *)(d + o_mo); D.map_n = (int *)(d + o_mc); D.ok = (int *)(d + o_ok); D.distinct = (int *)(d + o_di);
   D.heap = (HCand *)(d + o_heap);
   D.gauss = s.use_shared ? h->d_shared : s.d_stream;
@@ -229,6 +287,10 @@ extern "C" int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_c
     HCU(cudaStreamSynchronize(h->stream));
     h->shared_dirty = false;
     for (auto &s : h->sims) if (s.use_shared) s.prepared = false;          // the buffer may have moved
+  }
+  if (h->shared_ws.dirty) {
+    int rc = upload_words(h, h->shared_ws); if (rc) return rc;
+    for (auto &s : h->sims) if (s.word_mode == 2) s.prepared = false;
   }
   for (int i = 0; i < nsims; ++i) {
     auto &s = h->sims[(size_t)i];
@@ -259,8 +321,10 @@ extern "C" int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_c
 extern "C" int gs_horus_stats(gs_horus_handle h, int32_t sim, gs_horus_run_stats *out) {
   if (!h || !out || sim < 0 || sim >= (int)h->sims.size()) return hfail(h, GS_ERR_ARG, "gs_horus_stats: bad arguments");
   const HSim &D = h->sims[(size_t)sim].dev;
-  out->ticks = D.ticks; out->events = D.events; out->draws = D.gauss_pos;
-  out->finished = D.nfin; out->queued = D.qn; out->running = D.nrun; out->done = D.done; out->status = D.status; out->reserved = 0;
+  out->ticks = D.ticks; out->events = D.events; out->draws = D.draws;
+  int queued = 0;
+  for (int q = 0; q < D.nq; ++q) queued += D.qn[q];
+  out->finished = D.nfin; out->queued = queued; out->running = D.nrun; out->done = D.done; out->status = D.status; out->reserved = 0;
   out->kernel_ms = h->last_ms; out->reserved2 = 0.f;
   return GS_OK;
 }

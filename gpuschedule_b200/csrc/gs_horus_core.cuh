@@ -40,12 +40,14 @@
 #define H_TASK_CPU 12
 #define H_TASK_MEM 60
 #define H_DEV_SLOTS 4
+#define H_MAXQ 8
 
-struct HJob {            // one trace row (read-only), 56 bytes
+struct HJob {            // one trace row (read-only), 64 bytes
   int arrive, gpus, gpc, ntasks;
   int first_task, pad;
   long long mem_b;
   double util_avg, util_max, duration;
+  double mem_avg_mib;    // Job.gpu_mem_avg: only a k-means feature (core/jobs/utils.py:4-22)
 };
 struct HJobState {
   int pending, start, end, migration, tasks_finished, tro_n;
@@ -70,13 +72,23 @@ struct HSim {
   int *tro_node, *tro_order;            // Job.tasks_running_on: value per task / key insertion order
   HNode *nodes; HDev *devs;
   unsigned long long *pj_bits;          // Node.placed_jobs membership, bit (job, node)
-  int *queue, *running, *fin;
-  int qn, nrun, nfin, pad0;
+  int *queue;                           // nq queues of n + 1 slots each (heap order for horus / horus+)
+  int *running, *fin;
+  int qn[H_MAXQ];
+  double credits[H_MAXQ];               // JobQueueManager.queue_credits
+  int nq, nrun, nfin, pad0;
   // ---- scratch
-  int *look, *work, *res_nodes, *map_node, *map_order, *map_n, *ok, *distinct;
+  int *look, *look_q, *work, *res_nodes, *map_node, *map_order, *map_n, *ok, *distinct;
+  int *km_all, *km_assign, *km_old;     // horus+: jobs being re-clustered, their assignment, the previous one
+  double *km_score;
   HCand *heap;
-  // ---- the sampled stream
+  // ---- the sampled stream: either standard-normal values (horus / gandiva) ...
   const double *gauss; long long gauss_n, gauss_pos;
+  // ... or raw MT19937 words with per-position tables of the polar-method outcome (any schedule; needed by
+  // horus+, whose integer draws shift where the next normal sample starts).  See gs_horus_host.h.
+  const unsigned int *words; const double *gv_ret, *gv_keep; const int *gv_next;
+  long long words_n, words_pos, draws;
+  double gauss_kept; int has_gauss, pad1;
   // ---- results
   gs_tick_row *rows; double *util; unsigned char *util_arr; gs_horus_job_rec *recs; long long rows_cap;
   // ---- loop state (persisted between launches)
@@ -85,8 +97,28 @@ struct HSim {
 };
 
 GS_HD double h_gauss(HSim &s) {
+  s.draws += 1;
+  if (s.words) {                                            // legacy_gauss over the word stream: cached second value first
+    if (s.has_gauss) { s.has_gauss = 0; return s.gauss_kept; }
+    if (s.words_pos >= s.words_n || s.gv_next[s.words_pos] < 0) { s.status = GS_ERR_CAPACITY; return 0.0; }
+    const long long p = s.words_pos;
+    s.gauss_kept = s.gv_keep[p]; s.has_gauss = 1; s.words_pos = s.gv_next[p];
+    return s.gv_ret[p];
+  }
   if (s.gauss_pos >= s.gauss_n) { s.status = GS_ERR_CAPACITY; return 0.0; }      // host supplies a longer stream and re-runs
   return s.gauss[s.gauss_pos++];
+}
+// numpy.random.randint(n) / choice(n) of the legacy generator: masked rejection over 32-bit words
+GS_HD long long h_below(HSim &s, long long n) {
+  const unsigned long long mx = (unsigned long long)(n - 1);
+  if (mx == 0) return 0;
+  unsigned long long mask = mx;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+  for (;;) {
+    if (!s.words || s.words_pos >= s.words_n) { s.status = GS_ERR_CAPACITY; return 0; }
+    const unsigned long long v = (unsigned long long)s.words[s.words_pos++] & mask;     // n < 2^32 here (n <= jobs)
+    if (v <= mx) return (long long)v;
+  }
 }
 GS_HD double h_normal(HSim &s, double loc, double scale) { return H_ADD(loc, H_MUL(scale, h_gauss(s))); }
 GS_HD HDev &h_dev(HSim &s, int nd, int d) { return s.devs[(long long)nd * s.G + d]; }
@@ -311,35 +343,136 @@ GS_HD bool h_placement(HSim &s, int j, int &n_res) {
   return true;
 }
 
-// ---- queue: heapq over Job.__lt__ (base_factory.py:7-11) for horus, plain list for fifo / gandiva
+// ---- queues: heapq over Job.__lt__ (base_factory.py:7-11) for horus / horus+, plain list for fifo / gandiva
 GS_HD bool h_job_lt(const HSim &s, int a, int b) { return s.jobs[a].util_avg != 0.0 ? s.jobs[a].util_avg < s.jobs[b].util_avg : false; }
-GS_HD void h_queue_insert(HSim &s, int j, int pos) {       // JobQueueManager.insert (job_queue_manager.py:146-154)
-  int *h = s.queue;
-  if (s.schedule == GS_HSCHED_HORUS) {
-    int at = s.qn++;
+GS_HD bool h_is_pq(const HSim &s) { return s.schedule == GS_HSCHED_HORUS || s.schedule == GS_HSCHED_HORUS_PLUS; }
+GS_HD int h_queued(const HSim &s) { int t = 0; for (int q = 0; q < s.nq; ++q) t += s.qn[q]; return t; }
+GS_HD void h_queue_insert(HSim &s, int q, int j, int pos) {   // JobQueueManager.insert (job_queue_manager.py:146-154)
+  int *h = s.queue + (long long)q * (s.n + 1);
+  s.credits[q] = s.credits[q] + 1;
+  if (h_is_pq(s)) {
+    int at = s.qn[q]++;
     while (at > 0) { const int parent = (at - 1) >> 1; if (h_job_lt(s, j, h[parent])) { h[at] = h[parent]; at = parent; } else break; }
     h[at] = j;
     return;
   }
-  if (pos > s.qn) pos = s.qn;
-  for (int i = s.qn; i > pos; --i) h[i] = h[i - 1];
-  h[pos] = j; s.qn++;
+  if (pos > s.qn[q]) pos = s.qn[q];
+  for (int i = s.qn[q]; i > pos; --i) h[i] = h[i - 1];
+  h[pos] = j; s.qn[q]++;
 }
-GS_HD int h_queue_pop(HSim &s) {                           // job_queue_manager.py:129-135
-  int *h = s.queue;
-  if (s.schedule != GS_HSCHED_HORUS) { const int j = h[0]; --s.qn; for (int i = 0; i < s.qn; ++i) h[i] = h[i + 1]; return j; }
-  const int last = h[--s.qn];
-  if (s.qn == 0) return last;
+GS_HD int h_queue_pop(HSim &s, int q) {                       // job_queue_manager.py:129-135
+  int *h = s.queue + (long long)q * (s.n + 1);
+  int &n = s.qn[q];
+  if (!h_is_pq(s)) { const int j = h[0]; --n; for (int i = 0; i < n; ++i) h[i] = h[i + 1]; return j; }
+  const int last = h[--n];
+  if (n == 0) return last;
   const int ret = h[0];
   int pos = 0, child = 1;
-  while (child < s.qn) {
+  while (child < n) {
     const int right = child + 1;
-    if (right < s.qn && !h_job_lt(s, h[child], h[right])) child = right;
+    if (right < n && !h_job_lt(s, h[child], h[right])) child = right;
     h[pos] = h[child]; pos = child; child = 2 * pos + 1;
   }
   while (pos > 0) { const int parent = (pos - 1) >> 1; if (h_job_lt(s, last, h[parent])) { h[pos] = h[parent]; pos = parent; } else break; }
   h[pos] = last;
   return ret;
+}
+GS_HD void h_sort_ints(int *a, int n) {                    // heapsort (pending times for the medians)
+  for (int i = n / 2 - 1; i >= 0; --i) { int r = i, v = a[r]; for (;;) { int c = 2 * r + 1; if (c >= n) break; if (c + 1 < n && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; } a[r] = v; }
+  for (int e = n - 1; e > 0; --e) { int v = a[e]; a[e] = a[0]; int r = 0; for (;;) { int c = 2 * r + 1; if (c >= e) break; if (c + 1 < e && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; } a[r] = v; }
+}
+// JobQueueManager.update_credits (job_queue_manager.py:115-127): median pending time x queue length
+GS_HD void h_update_credits(HSim &s) {
+  for (int q = 0; q < s.nq; ++q) {
+    const int n = s.qn[q];
+    if (n == 0) { s.credits[q] = 0; continue; }
+    const int *h = s.queue + (long long)q * (s.n + 1);
+    for (int i = 0; i < n; ++i) s.work[i] = s.js[h[i]].pending;
+    h_sort_ints(s.work, n);
+    double mp = (n & 1) ? (double)s.work[n / 2] : ((double)s.work[n / 2 - 1] + (double)s.work[n / 2]) / 2.0;   // np.median
+    if (mp < 0) mp = 0;
+    s.credits[q] = mp < 1 ? (double)n : H_MUL(mp, (double)n);
+  }
+}
+
+// ---- horus+: every insert without explicit queue positions re-clusters ALL queued jobs (jobs_manager.py:93-139)
+GS_HD double h_job_score(const HSim &s, int j) {            // transform_to_dist (core/jobs/utils.py:14-22)
+  const HJob &x = s.jobs[j];
+  double sc = (double)x.ntasks;
+  sc = H_ADD(sc, x.util_avg); sc = H_ADD(sc, (double)x.gpc); sc = H_ADD(sc, (double)x.gpus); sc = H_ADD(sc, x.util_max);
+  sc = H_ADD(sc, x.mem_avg_mib); sc = H_ADD(sc, (double)x.mem_b / 1048576.0);
+  return sc;
+}
+GS_HD double h_fabs(double v) { return v < 0 ? -v : v; }
+GS_HD double h_job_dist(const HSim &s, int a, int b) {      // job_dist (core/jobs/utils.py:4-12)
+  const HJob &x = s.jobs[a], &y = s.jobs[b];
+  const int dt = x.ntasks - y.ntasks, dg = x.gpc - y.gpc, du = x.gpus - y.gpus;
+  double sc = (double)(dt < 0 ? -dt : dt);
+  sc = H_ADD(sc, h_fabs(H_ADD(x.util_avg, -y.util_avg))); sc = H_ADD(sc, (double)(dg < 0 ? -dg : dg)); sc = H_ADD(sc, (double)(du < 0 ? -du : du));
+  sc = H_ADD(sc, h_fabs(H_ADD(x.util_max, -y.util_max))); sc = H_ADD(sc, h_fabs(H_ADD(x.mem_avg_mib, -y.mem_avg_mib)));
+  sc = H_ADD(sc, h_fabs(H_ADD((double)x.mem_b / 1048576.0, -((double)y.mem_b / 1048576.0))));
+  return sc;
+}
+GS_HD double h_block_sum(const double *a, int n) {          // numpy's add.reduce kernel for n <= 128
+  if (n < 8) { double r = 0.; for (int i = 0; i < n; ++i) r = H_ADD(r, a[i]); return r; }
+  double r[8]; int i;
+  for (int k = 0; k < 8; ++k) r[k] = a[k];
+  for (i = 8; i < n - (n % 8); i += 8) for (int k = 0; k < 8; ++k) r[k] = H_ADD(r[k], a[i + k]);
+  double res = H_ADD(H_ADD(H_ADD(r[0], r[1]), H_ADD(r[2], r[3])), H_ADD(H_ADD(r[4], r[5]), H_ADD(r[6], r[7])));
+  for (; i < n; ++i) res = H_ADD(res, a[i]);
+  return res;
+}
+GS_HD double h_pairwise_sum(const double *a, int n) {       // numpy pairwise summation, recursion unrolled with a small stack
+  if (n <= 128) return h_block_sum(a, n);
+  // the recursion splits [lo, lo+len) at n2 = (len / 2) rounded down to a multiple of 8 and adds left + right
+  int lo_st[40], len_st[40], state[40]; double acc[40];
+  int sp = 0; lo_st[0] = 0; len_st[0] = n; state[0] = 0; acc[0] = 0.0;
+  double ret = 0.0;
+  for (;;) {
+    if (len_st[sp] <= 128) { ret = h_block_sum(a + lo_st[sp], len_st[sp]); if (sp == 0) return ret; --sp; }
+    else if (state[sp] == 0) { int n2 = len_st[sp] / 2; n2 -= n2 % 8; state[sp] = 1; lo_st[sp + 1] = lo_st[sp]; len_st[sp + 1] = n2; state[sp + 1] = 0; ++sp; continue; }
+    if (state[sp] == 1) { acc[sp] = ret; int n2 = len_st[sp] / 2; n2 -= n2 % 8; state[sp] = 2; lo_st[sp + 1] = lo_st[sp] + n2; len_st[sp + 1] = len_st[sp] - n2; state[sp + 1] = 0; ++sp; continue; }
+    if (state[sp] == 2) { ret = H_ADD(acc[sp], ret); if (sp == 0) return ret; --sp; }
+  }
+}
+// clusterize (core/jobs/utils.py:36-67) over km_all[0..m): fills km_assign
+GS_HD void h_clusterize(HSim &s, int m) {
+  const int k = s.nq;
+  int cent[H_MAXQ];
+  for (int c = 0; c < k; ++c) cent[c] = s.km_all[h_below(s, m)];                   // np.random.randint(len(jobs), size=k)
+  for (int i = 0; i < m; ++i) { s.km_assign[i] = -1; s.km_old[i] = -1; }
+  int iter = 0;
+  while (iter < 1000 && s.status == 0) {
+    if (iter != 0) { bool same = true; for (int i = 0; i < m; ++i) same &= (s.km_assign[i] == s.km_old[i]); if (same) break; }
+    for (int i = 0; i < m; ++i) s.km_old[i] = s.km_assign[i];
+    iter += 1;
+    for (int i = 0; i < m; ++i) {
+      int bi = 0; double bd = 0;
+      for (int c = 0; c < k; ++c) { const double d = h_job_dist(s, s.km_all[i], cent[c]); if (c == 0 || d < bd) { bd = d; bi = c; } }   // np.argmin
+      s.km_assign[i] = bi;
+    }
+    for (int c = 0; c < k; ++c) {
+      int cnt = 0;
+      for (int i = 0; i < m; ++i) if (s.km_assign[i] == c) s.km_score[cnt++] = h_job_score(s, s.km_all[i]);
+      if (cnt > 0) {
+        const double mean = h_pairwise_sum(s.km_score, cnt) / (double)cnt;
+        const double target = (double)(long long)mean;                               // .astype(int)
+        int best = -1; double bscore = 99999999999.0;
+        for (int i = 0; i < m; ++i) if (s.km_assign[i] == c) { const double t = h_fabs(H_ADD(h_job_score(s, s.km_all[i]), -target)); if (t < bscore) { best = s.km_all[i]; bscore = t; } }
+        cent[c] = best;
+      } else cent[c] = s.km_all[h_below(s, m)];                                      // np.random.choice(len(jobs))
+    }
+  }
+}
+// JobsManager.insert without queue positions under horus+ (jobs_manager.py:114-139): ALL queued jobs are popped
+// (queue by queue, heap order), the new jobs [first_new, first_new + n_new) go behind them, k-means assigns queues
+GS_HD void h_insert_reclustered(HSim &s, int first_new, int n_new) {
+  int m = 0;
+  for (int q = 0; q < s.nq; ++q) { const int cnt = s.qn[q]; for (int i = 0; i < cnt; ++i) s.km_all[m++] = h_queue_pop(s, q); }
+  for (int i = 0; i < n_new; ++i) s.km_all[m++] = first_new + i;
+  if (m == 0) return;
+  h_clusterize(s, m);
+  for (int i = 0; i < m; ++i) h_queue_insert(s, s.km_assign[i], s.km_all[i], i);
 }
 
 GS_HD int h_time_processed(const HSim &s, int j) { const HJob &jb = s.jobs[j]; int m = 0; for (int k = 0; k < jb.ntasks; ++k) { const int v = s.tasks[jb.first_task + k].time_processed; if (v > m) m = v; } return m; }
@@ -384,11 +517,7 @@ GS_HD void h_preempt(HSim &s, int j) {
   st.running = 0; st.pending = 0;
   for (int k = 0; k < jb.ntasks; ++k) s.tasks[jb.first_task + k].running = 0;
   s.events += 1;
-  h_queue_insert(s, j, 0);
-}
-GS_HD void h_sort_ints(int *a, int n) {                    // heapsort (pending times for the median)
-  for (int i = n / 2 - 1; i >= 0; --i) { int r = i, v = a[r]; for (;;) { int c = 2 * r + 1; if (c >= n) break; if (c + 1 < n && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; } a[r] = v; }
-  for (int e = n - 1; e > 0; --e) { int v = a[e]; a[e] = a[0]; int r = 0; for (;;) { int c = 2 * r + 1; if (c >= e) break; if (c + 1 < e && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; } a[r] = v; }
+  h_queue_insert(s, 0, j, 0);          // gandiva only: one plain list
 }
 
 // Scheduler.start (schedule.py:178-213): runs until done, max_ticks or the row buffer is full
@@ -398,24 +527,38 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
     if (!(s.current_remaining + s.running_jobs > 0)) { s.done = 1; break; }
     if (s.ticks >= s.rows_cap) { s.status = GS_ERR_CAPACITY; break; }
     // gen_jobs: rows with normalized_time <= delta in trace order (jobs_manager.py:228-241)
-    { int pos = 0; while (s.p < s.n && s.jobs[s.p].arrive <= s.delta) { h_queue_insert(s, s.p, pos++); ++s.p; ++s.events; } }
+    {
+      const int first_new = s.p;
+      while (s.p < s.n && s.jobs[s.p].arrive <= s.delta) { ++s.p; ++s.events; }
+      if (s.schedule == GS_HSCHED_HORUS_PLUS) h_insert_reclustered(s, first_new, s.p - first_new);   // every tick, even without arrivals
+      else for (int j = first_new; j < s.p; ++j) h_queue_insert(s, 0, j, j - first_new);
+    }
     // _schedule (schedule.py:39-58)
-    if (s.qn > 0) {
+    if (h_queued(s) > 0) {
       int free_nodes = 0;
       for (int nd = 0; nd < s.M; ++nd) free_nodes += h_node_is_free(s, nd);
       if (free_nodes >= 1) {
         int placed = -1, nres = 0;
-        if (s.schedule == GS_HSCHED_HORUS) {                                       // schedule_horus (algorithm.py:204-240)
-          int min_k = s.num_buffer < s.qn ? s.num_buffer : s.qn;
+        if (s.schedule == GS_HSCHED_HORUS || s.schedule == GS_HSCHED_HORUS_PLUS) {   // schedule_horus / schedule_horus_plus (algorithm.py:204-290)
+          const bool plus = s.schedule == GS_HSCHED_HORUS_PLUS;
+          const int qd = h_queued(s);
+          int min_k = s.num_buffer < qd ? s.num_buffer : qd;
           if (min_k < 0) min_k = 0;
-          for (int i = 0; i < min_k; ++i) s.look[i] = h_queue_pop(s);
+          for (int i = 0; i < min_k; ++i) {
+            int qi = 0;
+            if (plus) {                                     // the queue with the most credit (leaky bucket)
+              h_update_credits(s);
+              for (int q = 1; q < s.nq; ++q) if (s.credits[q] > s.credits[qi]) qi = q;        // np.argmax: first maximum
+            }
+            s.look[i] = h_queue_pop(s, qi); s.look_q[i] = qi;
+          }
           int pos = -1;
           for (int i = 0; i < min_k; ++i) if (h_placement(s, s.look[i], nres)) { pos = i; break; }
-          if (pos >= 0) { placed = s.look[pos]; for (int i = pos; i + 1 < min_k; ++i) s.look[i] = s.look[i + 1]; min_k -= 1; }
-          for (int i = 0; i < min_k; ++i) h_queue_insert(s, s.look[i], i);
+          if (pos >= 0) { placed = s.look[pos]; for (int i = pos; i + 1 < min_k; ++i) { s.look[i] = s.look[i + 1]; s.look_q[i] = s.look_q[i + 1]; } min_k -= 1; }
+          for (int i = 0; i < min_k; ++i) h_queue_insert(s, s.look_q[i], s.look[i], i);          // back to the queue they came from
         } else {                                                                   // schedule_fifo (algorithm.py:189-202)
           const int j = s.queue[0];
-          if (h_placement(s, j, nres)) { (void)h_queue_pop(s); placed = j; }
+          if (h_placement(s, j, nres)) { (void)h_queue_pop(s, 0); placed = j; }
         }
         if (placed >= 0) { h_start_job(s, placed, nres); s.events += 1; }
       }
@@ -423,13 +566,14 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
     s.current_remaining = s.n - s.p;
     s.delta += 1;
     // JobsManager.step (jobs_manager.py:141-148)
-    for (int i = 0; i < s.qn; ++i) s.js[s.queue[i]].pending += 1;
+    for (int q = 0; q < s.nq; ++q) { const int *h = s.queue + (long long)q * (s.n + 1); for (int i = 0; i < s.qn[q]; ++i) s.js[h[i]].pending += 1; }
     for (int i = 0; i < s.nrun; ++i) {
       const int j = s.running[i];
       if (!s.js[j].running) continue;
       const HJob &jb = s.jobs[j];
       for (int k = 0; k < jb.ntasks; ++k) if (s.tasks[jb.first_task + k].running) s.tasks[jb.first_task + k].time_processed += 1;
     }
+    if (s.schedule == GS_HSCHED_HORUS_PLUS) h_update_credits(s);
     // release_finished_jobs (schedule.py:136-157)
     int nf = 0;
     for (int i = 0; i < s.nrun; ++i) { const int j = s.running[i]; if (!((double)h_time_processed(s, j) < h_get_duration(s, j))) s.work[nf++] = j; }
@@ -450,7 +594,7 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
     }
     s.running_jobs = s.nrun;
     // plugin: gandiva time slicing (algorithm.py:420-440)
-    if (s.schedule == GS_HSCHED_GANDIVA && s.qn > 0) {
+    if (s.schedule == GS_HSCHED_GANDIVA && s.qn[0] > 0) {
       int nt = 0;
       for (int i = 0; i < s.nrun; ++i) { const int tp = h_time_processed(s, s.running[i]); if (tp > 1 && tp % 100 == 0) s.work[nt++] = s.running[i]; }
       for (int i = 0; i < nt; ++i) h_preempt(s, s.work[i]);
@@ -473,9 +617,13 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
       }
     }
     row.mem_busy_bytes = msum;
-    row.running = s.nrun; row.queued = s.qn; row.finished = s.nfin;
-    for (int i = 0; i < s.qn; ++i) { const int pd = s.js[s.queue[i]].pending; s.work[i] = pd; row.pend_sum += pd; if (pd > row.pend_max) row.pend_max = pd; }
-    if (s.qn > 0) { h_sort_ints(s.work, s.qn); row.pend_med_lo = s.work[(s.qn - 1) / 2]; row.pend_med_hi = s.work[s.qn / 2]; }
+    const int queued = h_queued(s);
+    row.running = s.nrun; row.queued = queued; row.finished = s.nfin;
+    {
+      int m = 0;
+      for (int q = 0; q < s.nq; ++q) { const int *h = s.queue + (long long)q * (s.n + 1); for (int i = 0; i < s.qn[q]; ++i) { const int pd = s.js[h[i]].pending; s.work[m++] = pd; row.pend_sum += pd; if (pd > row.pend_max) row.pend_max = pd; } }
+      if (m > 0) { h_sort_ints(s.work, m); row.pend_med_lo = s.work[(m - 1) / 2]; row.pend_med_hi = s.work[m / 2]; }
+    }
     s.rows[s.ticks] = row;
     s.util[s.ticks] = usum / (double)(row.idle_gpus + row.busy_gpus); s.util_arr[s.ticks] = (unsigned char)uarr;
     s.ticks += 1; budget -= 1;

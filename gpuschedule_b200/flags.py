@@ -91,8 +91,8 @@ def define_simulator_flags():
     DEFINE_string("trace_file", "tf_job.csv", "job trace CSV (live schema)")
     DEFINE_string("log_path", "result-" + time.strftime("%Y%m%d-%H-%M-%S", time.localtime()),
                   "output folder under ./log/")
-    DEFINE_string("scheme", "yarn", "placement scheme: yarn | count | horus | gandiva")
-    DEFINE_string("schedule", "fifo", "policy: fifo | sjf | dlas | dlas-gpu | gittins | horus | gandiva")
+    DEFINE_string("scheme", "yarn", "placement scheme: yarn | count | horus | horus+ | gandiva")
+    DEFINE_string("schedule", "fifo", "policy: fifo | sjf | dlas | dlas-gpu | gittins | horus | horus+ | gandiva")
     DEFINE_boolean("pack", False, "pack several tasks per GPU (not supported by the engine)")
     DEFINE_integer("num_switch", 1, "switches in the cluster")
     DEFINE_integer("num_node_p_switch", 32, "nodes under one switch")
@@ -101,7 +101,7 @@ def define_simulator_flags():
     DEFINE_integer("bandwidth", 1250, "rack bandwidth, MB/s")
     DEFINE_float("internode_latency", 0.015, "latency per crossed node, seconds")
     DEFINE_integer("gpu_memory_capacity", 32, "GPU memory, GiB")
-    DEFINE_integer("num_queue", 1, "queues in the job manager (dlas MLFQ depth)")
+    DEFINE_integer("num_queue", 1, "queues in the job manager (dlas MLFQ depth; horus+ credit queues)")
     DEFINE_integer("num_buffer", 5, "look-ahead width of the horus scheduler")
     DEFINE_integer("num_gpu_p_node", 8, "GPUs per node")
     DEFINE_integer("num_cpu_p_node", 128, "CPUs per node")

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 from . import ingest
 
-SUPPORTED_SCHEDULES = ("fifo", "sjf", "dlas", "dlas-gpu", "gittins", "horus", "gandiva")   # horus+: oracle only so far
+SUPPORTED_SCHEDULES = ("fifo", "sjf", "dlas", "dlas-gpu", "gittins", "horus", "horus+", "gandiva")
 
 
 class JobQueueManager:

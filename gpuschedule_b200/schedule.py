@@ -33,7 +33,7 @@ class Scheduler:
                       gittins_table=policies.build_gittins_table(policies.gittins_samples(table), delta))
         return capi.make_policy(self.schedule, self.placement if self.placement in capi.SCHEMES else "yarn", **kw)
 
-    UTILISATION_AWARE = ("horus", "gandiva")
+    UTILISATION_AWARE = ("horus", "horus+", "gandiva")
 
     def _start_utilisation_aware(self):
         """--scheme horus|gandiva: score-based placement with look-ahead / time slicing (include/gsched_horus.h).
@@ -45,24 +45,29 @@ class Scheduler:
         infra, table = self.infrastructure, self.jobs_manager.table
         flags = infra.flags
         cluster = infra.gs_cluster()
-        params = capi.make_horus_params(self.placement, self.schedule, int(getattr(flags, "num_buffer", 5)))
-        stream = np.random.standard_normal(1 << 21)
+        params = capi.make_horus_params(self.placement, self.schedule, int(getattr(flags, "num_buffer", 5)),
+                                        int(getattr(flags, "num_queue", 1)))
+        # horus+ also draws integers (k-means seeding), so it needs the raw generator words; the others take the
+        # cheaper standard-normal form.  Either way the chunks continue numpy's GLOBAL stream.
+        raw = self.schedule == "horus+"
+        draw = (lambda k: np.random.randint(0, 2 ** 32, size=k, dtype=np.uint32)) if raw else np.random.standard_normal
+        stream = draw(1 << 21)
         rows_cap = 1 << 16
         with capi.HorusEngine(device=getattr(flags, "device", 0), nsims=1) as eng:
             eng.config(0, cluster, params)
             eng.load_trace(0, table)
             while True:
-                eng.load_stream(0, stream)
+                (eng.load_words if raw else eng.load_stream)(0, stream)
                 try:
                     eng.run(rows_cap=rows_cap)
                     break
                 except capi.GsError as e:
                     if e.code != capi.GS_ERR_CAPACITY:
                         raise
-                    if eng.stats(0).draws >= len(stream):        # ran out of samples: continue numpy's stream
-                        stream = np.concatenate([stream, np.random.standard_normal(len(stream))])
-                    else:                                         # ran out of rows
+                    if eng.stats(0).ticks >= rows_cap:            # ran out of rows
                         rows_cap *= 2
+                    else:                                         # ran out of samples: continue numpy's stream
+                        stream = np.concatenate([stream, draw(len(stream))])
             rows, util, flags_arr, recs, order = eng.fetch(0)
             self.stats = eng.stats(0)
         m = cluster.num_switch * cluster.num_node_p_switch

@@ -16,8 +16,9 @@
  * reference's order, so a seeded reference run is reproduced bit for bit.  A stream that is too short
  * ends the run with GS_ERR_CAPACITY (load a longer one and run again).
  *
- * horus+ (credit queues re-clustered by k-means every tick, jobs_manager.py:93-139) interleaves
- * integer draws with the normal samples and is not served by this ABI yet (GS_ERR_ARG).
+ * horus+ (credit queues re-clustered by k-means every tick, jobs_manager.py:93-139, algorithm.py:242-290)
+ * interleaves integer draws with the normal samples, so it takes the stream as raw generator words instead
+ * (gs_horus_load_words); the host side of the library tabulates the normal sampler over them.
  *
  * Conventions as in gsched.h: 0 / negative gs_status, caller-owned host buffers, one handle per
  * device and driving thread, no CPU fallback (gs_horus_create fails without a CUDA device).
@@ -34,13 +35,13 @@ extern "C" {
 #endif
 
 enum { GS_HSCORE_HORUS = 0, GS_HSCORE_GANDIVA = 1 };              /* --scheme: which score_fn (algorithm.py:9-13) */
-enum { GS_HSCHED_FIFO = 0, GS_HSCHED_HORUS = 1, GS_HSCHED_GANDIVA = 3 };   /* --schedule (algorithm.py:292-298) */
+enum { GS_HSCHED_FIFO = 0, GS_HSCHED_HORUS = 1, GS_HSCHED_HORUS_PLUS = 2, GS_HSCHED_GANDIVA = 3 };   /* --schedule (algorithm.py:292-298) */
 
 typedef struct gs_horus_params {
   int32_t score;        /* GS_HSCORE_* */
   int32_t schedule;     /* GS_HSCHED_* */
   int32_t num_buffer;   /* look-ahead width k of schedule_horus (--num_buffer, run_sim.py:76) */
-  int32_t reserved;
+  int32_t num_queue;    /* horus+: number of credit queues (--num_queue, run_sim.py:75); 0 or 1 otherwise */
 } gs_horus_params;
 
 /* One finished (or unfinished) job: the fields LogManager.jcts prints (log_manager.py:137-153). */
@@ -69,10 +70,14 @@ int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster *cluster, c
  * per trace row  (core/jobs/jobs_manager.py:233-239); rows in admission order, arrive = ceil(normalized_time). */
 int gs_horus_load_trace(gs_horus_handle h, int32_t sim, int64_t n, const int32_t *arrive, const int32_t *gpus,
                         const int32_t *gpu_per_task, const double *duration, const int64_t *mem_bytes,
-                        const double *util_avg, const double *util_max);
+                        const double *util_avg, const double *util_max, const double *mem_avg_mib /* horus+ only, may be NULL */);
 /* The numpy stream the run consumes (see the header comment).  sim = -1: one stream shared by every replica
  * of the handle, each reading it from position 0 (replicas that differ in trace or parameters only). */
 int gs_horus_load_stream(gs_horus_handle h, int32_t sim, const double *standard_normal, int64_t count);
+/* The same numpy stream as raw MT19937 output words (numpy.random.randint(0, 2**32, count, dtype=uint32) from the
+ * generator state the reference run would start from).  Serves every schedule and is REQUIRED for horus+, whose
+ * k-means integer draws (core/jobs/utils.py:39,62) share the stream with the normal samples.  sim = -1: shared. */
+int gs_horus_load_words(gs_horus_handle h, int32_t sim, const uint32_t *mt19937_words, int64_t count);
 /* Scheduler.start() for every configured replica: runs to completion, or max_ticks ticks (0 = no limit). */
 int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_cap);
 int gs_horus_stats(gs_horus_handle h, int32_t sim, gs_horus_run_stats *out);

@@ -14,6 +14,7 @@ _lib = None
 def build(force=False):
     src = os.path.join(_HERE, "horus_emu.cpp")
     deps = [src, os.path.join(_REPO, "gpuschedule_b200", "csrc", "gs_horus_core.cuh"),
+            os.path.join(_REPO, "gpuschedule_b200", "csrc", "gs_horus_host.h"),
             os.path.join(_REPO, "include", "gsched.h"), os.path.join(_REPO, "include", "gsched_horus.h")]
     if not force and os.path.exists(_OUT) and os.path.getmtime(_OUT) >= max(os.path.getmtime(d) for d in deps):
         return _OUT
@@ -32,7 +33,8 @@ def lib():
     return _lib
 
 
-def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0):
+def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0, words=None):
+    """gauss: standard-normal values (horus / gandiva), or words: raw MT19937 words (any schedule, needed by horus+)"""
     from gpuschedule_b200.capi import HORUS_REC_DTYPE
     from gpuschedule_b200.log_manager import ROW_DTYPE
     n = table.n
@@ -46,9 +48,13 @@ def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0):
     cols = [arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32),
             arr(table.duration, np.float64), arr(table.mem_bytes, np.int64), arr(table.util_avg, np.float64),
             arr(table.util_max, np.float64)]
-    g = arr(gauss, np.float64)
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
-    ticks = lib().emu_run_horus(C.byref(cluster), C.byref(params), C.c_longlong(n), *[p(c) for c in cols], p(g),
-                                C.c_longlong(len(g)), p(rows), p(util), p(util_arr), C.c_longlong(rows_cap), p(recs), p(fin),
+    ma = table.extra.get("mem_avg_mib")
+    ma = None if ma is None else arr(ma, np.float64)
+    g = None if gauss is None else arr(gauss, np.float64)
+    w = None if words is None else arr(words, np.uint32)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    ticks = lib().emu_run_horus(C.byref(cluster), C.byref(params), C.c_longlong(n), *[p(c) for c in cols], p(ma), p(g),
+                                C.c_longlong(0 if g is None else len(g)), p(w), C.c_longlong(0 if w is None else len(w)),
+                                p(rows), p(util), p(util_arr), C.c_longlong(rows_cap), p(recs), p(fin),
                                 C.byref(nfin), C.byref(events), C.byref(draws), C.c_longlong(max_ticks_per_call))
     return ticks, rows[:max(ticks, 0)], util[:max(ticks, 0)], util_arr[:max(ticks, 0)], recs[:n], fin[:nfin.value], events.value, draws.value

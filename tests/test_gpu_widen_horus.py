@@ -1,7 +1,12 @@
 """CUDA engine for the utilisation-aware paths (include/gsched_horus.h) vs the reference fixtures
-(tests/golden/horus_* / gandiva_*, bytes of job.csv and cluster.csv incl. the sampled utilisation column)
-and vs the pinned oracle (oracle/horus_oracle.c) on seeded cases; several replicas per launch, resumed runs,
-and the too-short-stream error."""
+(tests/golden/horus_* / gandiva_* / horusplus_*, bytes of job.csv and cluster.csv incl. the sampled utilisation
+column) and vs the pinned oracle (oracle/horus_oracle.c) on seeded cases; several replicas per launch, resumed
+runs, both stream forms, and the too-short-stream error.  (The file name sorts after the main-path GPU tests on
+purpose: the widening row must never keep `pytest -x` from reaching them.)
+
+The horus / gandiva tests ran green on a B200 in round 1.  The horus+ device path (k-means, credit queues,
+word-stream tables) was finished after the round's GPU budget was spent: the same functions pass on the CPU
+through tests/emu (tests/test_horus_emu.py), their device build has not run yet -- hence NOT_RUN_YET below."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -10,11 +15,18 @@ import pytest
 from conftest import horus_cases, load_horus, render_horus_outputs
 
 pytestmark = pytest.mark.gpu
+NOT_RUN_YET = pytest.mark.xfail(strict=False, reason="device build of the horus+ functions has not run on a GPU yet "
+                                "(logic verified through tests/emu); a pass shows up as XPASS")
 
 
 def _stream(seed, count=1 << 21):
     np.random.seed(seed)
     return np.random.standard_normal(count)
+
+
+def _words(seed, count=6 << 20):
+    np.random.seed(seed)
+    return np.random.randint(0, 2 ** 32, size=count, dtype=np.uint32)        # raw MT19937 output words
 
 
 def _collect(eng, i):
@@ -24,15 +36,18 @@ def _collect(eng, i):
                            events=int(st.events), draws=int(st.draws), ticks=int(st.ticks), done=int(st.done))
 
 
-def _run(jobs, max_ticks=0, lanes=1):
+def _run(jobs, max_ticks=0, lanes=1, words=False):
     """jobs: list of (cluster, table, params); one replica each, one handle."""
     from gpuschedule_b200 import capi
     with capi.HorusEngine(device=0, nsims=len(jobs)) as eng:
         eng.set_lanes(lanes)
         for i, (cluster, table, params) in enumerate(jobs):
-            eng.config(i, cluster, capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"]))
+            eng.config(i, cluster, capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"], params.get("num_queue", 1)))
             eng.load_trace(i, table)
-            eng.load_stream(i, _stream(params["seed"]))
+            if words or params["schedule"] == "horus+":
+                eng.load_words(i, _words(params["seed"]))
+            else:
+                eng.load_stream(i, _stream(params["seed"]))
         launches = 0
         while True:
             eng.run(max_ticks=max_ticks, rows_cap=1 << 15)
@@ -43,8 +58,8 @@ def _run(jobs, max_ticks=0, lanes=1):
         return [_collect(eng, i) for i in range(len(jobs))], launches
 
 
-def _served():
-    return [c for c in horus_cases() if load_horus(c)[2]["schedule"] in ("horus", "gandiva", "fifo")]
+def _served(plus=False):
+    return [c for c in horus_cases() if (load_horus(c)[2]["schedule"] == "horus+") == plus]
 
 
 def test_engine_matches_reference_bytes_all_fixtures_one_launch():
@@ -109,11 +124,16 @@ def test_short_stream_and_unserved_schedule_fail_loudly():
         eng.load_stream(0, _stream(params["seed"]))          # a longer stream: the run starts over and completes
         eng.run(rows_cap=1 << 15)
         assert eng.stats(0).done == 1
-        bad = capi.GsHorusParams(0, 2, 5, 0)                  # horus+ (credit queues) is not served
         with pytest.raises(capi.GsError):
-            eng.config(0, cluster, bad)
+            eng.config(0, cluster, capi.GsHorusParams(0, 7, 5, 0))       # unknown schedule
+        with pytest.raises(capi.GsError):
+            eng.config(0, cluster, capi.GsHorusParams(0, 2, 5, 0))       # horus+ without queues
+        eng.config(0, cluster, capi.make_horus_params("horus+", "horus+", 15, 3))
+        with pytest.raises(capi.GsError) as e:                           # horus+ needs the raw word stream
+            eng.run(rows_cap=1 << 15)
+        assert e.value.code == -3
     with pytest.raises(NotImplementedError):
-        capi.make_horus_params("horus+", "horus+", 15)
+        capi.make_horus_params("yarn", "horus", 5)
 
 
 @pytest.mark.parametrize("case", ["horus_racks", "gandiva_small"])
@@ -141,3 +161,25 @@ def test_cli_run_sim_horus_writes_reference_bytes(case, tmp_path):
         got = open(os.path.join(runs[0], name), newline="").read()
         exp = open(os.path.join(GOLDEN, case, name), newline="").read()
         assert got == exp, name
+
+
+@NOT_RUN_YET
+def test_horus_plus_matches_reference_bytes():
+    cases = _served(plus=True)
+    assert len(cases) >= 2
+    loaded = [load_horus(c) for c in cases]
+    results, _ = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded])
+    for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
+        got_job, got_cluster = render_horus_outputs(table, cluster, res)
+        assert got_job == job_csv, case
+        assert got_cluster == cluster_csv, case
+
+
+@NOT_RUN_YET
+def test_word_stream_serves_horus_and_gandiva_too():
+    cases = _served()
+    loaded = [load_horus(c) for c in cases]
+    results, _ = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded], words=True)
+    for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
+        got_job, got_cluster = render_horus_outputs(table, cluster, res)
+        assert got_job == job_csv and got_cluster == cluster_csv, case

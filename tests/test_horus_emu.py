@@ -6,7 +6,7 @@ header with g++ and this file compares it, fed with numpy's own standard-normal 
   * the pinned oracle (oracle/horus_oracle.c, which carries its own MT19937) on seeded random cases.
 It also proves the stream contract of include/gsched_horus.h: numpy.random.normal(loc, scale, size=1)
 number k equals loc + scale * standard_normal()[k].  The device build of the same functions is checked
-on the GPU by tests/test_gpu_horus.py."""
+on the GPU by tests/test_gpu_widen_horus.py."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -15,20 +15,27 @@ import pytest
 from conftest import horus_cases, load_horus, render_horus_outputs
 
 
-def _served(params):
-    return params["schedule"] in ("horus", "gandiva", "fifo")
-
-
 def _stream(seed, count):
     np.random.seed(seed)
     return np.random.standard_normal(count)
 
 
-def _emu(table, cluster, params, count=1 << 21, step=0):
+def _words(seed, count):
+    np.random.seed(seed)
+    return np.random.randint(0, 2 ** 32, size=count, dtype=np.uint32)       # the raw MT19937 output words
+
+
+def _emu(table, cluster, params, count=1 << 21, step=0, use_words=None):
     from gpuschedule_b200 import capi
     from tests_emu import run_horus
-    hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"])
-    ticks, rows, util, flags, recs, order, events, draws = run_horus(cluster, hp, table, _stream(params["seed"], count), 1 << 15, step)
+    hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"], params.get("num_queue", 1))
+    if use_words is None:
+        use_words = params["schedule"] == "horus+"
+    if use_words:
+        out = run_horus(cluster, hp, table, None, 1 << 15, step, words=_words(params["seed"], 3 * count))
+    else:
+        out = run_horus(cluster, hp, table, _stream(params["seed"], count), 1 << 15, step)
+    ticks, rows, util, flags, recs, order, events, draws = out
     assert ticks >= 0, ticks
     return SimpleNamespace(rows=rows, util=util, util_is_array=flags, recs=recs, finish_order=order, events=events, draws=draws, ticks=ticks)
 
@@ -57,15 +64,41 @@ def test_numpy_stream_contract():
         assert np.random.normal(loc=loc, scale=scale, size=1)[0] == loc + scale * g[k]
 
 
+@pytest.mark.parametrize("stream", ["values", "words"])
 @pytest.mark.parametrize("case", [c for c in horus_cases()])
-def test_kernel_logic_matches_reference_bytes(case):
+def test_kernel_logic_matches_reference_bytes(case, stream):
     table, cluster, params, job_csv, cluster_csv = load_horus(case)
-    if not _served(params):
-        pytest.skip("horus+ is not served by the engine yet (oracle only)")
-    res = _emu(table, cluster, params)
+    if params["schedule"] == "horus+" and stream == "values":
+        pytest.skip("horus+ draws integers too: it needs the raw word stream")
+    res = _emu(table, cluster, params, use_words=(stream == "words"))
     got_job, got_cluster = render_horus_outputs(table, cluster, res)
     assert got_job == job_csv
     assert got_cluster == cluster_csv
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_horus_plus_logic_matches_oracle_seeded(seed):
+    """k-means re-clustering, credit queues and the integer draws; seed 5 queues > 128 jobs per cluster (numpy's
+    pairwise summation takes its recursive branch there)."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    rng = np.random.default_rng(900 + seed)
+    big = seed == 5
+    cluster = capi.make_cluster(num_switch=int(rng.integers(1, 3)), num_node_p_switch=1 if big else int(rng.integers(1, 5)),
+                                num_gpu_p_node=int(rng.choice([4, 8])), gpu_memory_capacity=int(rng.choice([16, 32])))
+    n = 420 if big else int(rng.integers(30, 140))
+    table = ingest.table_from_columns(tracegen.synth_columns(n, seed=800 + seed, rate=8.0 if big else float(rng.choice([1.0, 3.0])),
+                                                             gpu_choices=[1, 2, 4], gpu_probs=[.5, .3, .2]))
+    params = dict(scheme="horus+", schedule="horus+", num_buffer=int(rng.choice([2, 5, 15])), num_queue=int(rng.integers(2, 6)), seed=3000 + seed)
+    ref = oracle.run_horus(cluster, table, **params)
+    res = _emu(table, cluster, params, count=1 << 22)
+    if big:
+        assert int(ref.rows["queued"].max()) > 300
+    assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events
+    assert res.rows.tobytes() == ref.rows.tobytes()
+    assert res.util.tobytes() == ref.util.tobytes() and res.util_is_array.tobytes() == ref.util_is_array.tobytes()
+    assert res.recs.tobytes() == ref.recs.tobytes()
+    assert np.array_equal(res.finish_order, ref.finish_order)
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -85,8 +118,8 @@ def test_kernel_logic_matches_oracle_seeded(seed):
                                                              max_mem_mib=int(rng.choice([8000, 16384, 33500]))))
     params = dict(scheme=kind, schedule=kind, num_buffer=int(rng.choice([1, 3, 5])), num_queue=1, seed=1000 + seed)
     ref = oracle.run_horus(cluster, table, **params)
-    for step in (0, 37):                                   # one call / resumed every 37 ticks
-        res = _emu(table, cluster, params, step=step)
+    for step, use_words in ((0, False), (37, False), (0, True)):       # one call / resumed every 37 ticks / raw word stream
+        res = _emu(table, cluster, params, step=step, use_words=use_words)
         assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events
         assert res.rows.tobytes() == ref.rows.tobytes()
         assert res.util.tobytes() == ref.util.tobytes() and res.util_is_array.tobytes() == ref.util_is_array.tobytes()
@@ -101,6 +134,8 @@ def test_short_stream_is_reported():
     hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"])
     ticks = run_horus(cluster, hp, table, _stream(params["seed"], 1000), 1 << 15)[0]
     assert ticks == -4                                     # GS_ERR_CAPACITY: load a longer stream
+    ticks = run_horus(cluster, hp, table, None, 1 << 15, words=_words(params["seed"], 3000))[0]
+    assert ticks == -4
 
 
 class _EmuHorusEngine:
@@ -124,12 +159,15 @@ class _EmuHorusEngine:
         self.table = table
 
     def load_stream(self, sim, g):
-        self.g = np.array(g)
+        self.g, self.w = np.array(g), None
+
+    def load_words(self, sim, w):
+        self.g, self.w = None, np.array(w)
 
     def run(self, max_ticks=0, rows_cap=1 << 16):
         from gpuschedule_b200 import capi
         from tests_emu import run_horus
-        out = run_horus(self.cluster, self.params, self.table, self.g, rows_cap)
+        out = run_horus(self.cluster, self.params, self.table, self.g, rows_cap, words=self.w)
         self.res = out
         self.draws = out[7]
         if out[0] < 0:
@@ -142,7 +180,7 @@ class _EmuHorusEngine:
         return self.res[1], self.res[2], self.res[3], self.res[4], self.res[5]
 
 
-@pytest.mark.parametrize("case", ["horus_small", "gandiva_slice"])
+@pytest.mark.parametrize("case", ["horus_small", "gandiva_slice", "horusplus_k3"])
 def test_host_mirror_writes_reference_bytes(case, tmp_path, monkeypatch):
     """Scheduler.start() for --scheme horus|gandiva: numpy's global stream is handed to the engine in chunks (a
     first chunk that is too short makes the run start over with a longer one) and the files equal the reference's."""
@@ -153,11 +191,12 @@ def test_host_mirror_writes_reference_bytes(case, tmp_path, monkeypatch):
     table, cluster, params, job_csv, cluster_csv = load_horus(case)
     shutil.copy(os.path.join(GOLDEN, case, "trace.csv"), tmp_path / "trace.csv")
     fl = sweep.make_flags(trace_file=str(tmp_path / "trace.csv"), scheme=params["scheme"], schedule=params["schedule"],
-                          num_buffer=params["num_buffer"], num_switch=cluster.num_switch,
+                          num_buffer=params["num_buffer"], num_queue=params["num_queue"], num_switch=cluster.num_switch,
                           num_node_p_switch=cluster.num_node_p_switch, num_gpu_p_node=cluster.num_gpu_p_node)
     monkeypatch.setattr(capi, "HorusEngine", _EmuHorusEngine)
-    real = np.random.standard_normal
+    real, real_int = np.random.standard_normal, np.random.randint
     monkeypatch.setattr(np.random, "standard_normal", lambda n: real(min(n, 20000)))    # force the "stream too short" retries
+    monkeypatch.setattr(np.random, "randint", lambda lo, hi=None, size=None, dtype=int: real_int(lo, hi, size=min(size, 50000), dtype=dtype))
     infra = infrastructure.Infrastructure(fl)
     jm = jobs.JobsManager(fl, jobs.JobQueueManager(fl, fl.trace_file))
     lm = log_manager.LogManager(str(tmp_path), fl)
