@@ -395,6 +395,16 @@ def ours(args):
                                      "achieved_gbs": pj["roofline"]["achieved"]}
         except Exception as exc:
             extras["place_batch"] = {"error": str(exc)}
+        # widening row f1 (horus / gandiva / horus+ engine): its own process with a time limit, so that nothing it
+        # does can cost the main measurement
+        try:
+            import subprocess
+            hp = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "horus", "--horus-replicas", "1184"],
+                                capture_output=True, text=True, timeout=240)
+            line = [ln for ln in hp.stdout.splitlines() if ln.startswith("{")]
+            extras["horus"] = json.loads(line[-1]) if line else {"error": (hp.stderr or "no output")[-400:]}
+        except Exception as exc:
+            extras["horus"] = {"error": repr(exc)}
 
     # ---- CPU baseline: the oracle port, 1 thread, bounded sample (rank 0, N=1 only)
     cpu = None
@@ -497,7 +507,7 @@ def horus_mode(args):
             eng.config(r, cluster, hp)
             eng.load_trace(r, tables[r])
         by_lanes = {}
-        for lanes in (32, 1):                              # both kernel mappings; the faster one is reported
+        for lanes in ((32, 1) if args.horus_both_mappings else (1,)):   # 1 simulation per warp won round 1 (2.8x)
             eng.set_lanes(lanes)
             eng.load_stream(-1, stream)                    # (re)loading the stream starts the replicas over
             eng.run(rows_cap=args.horus_rows)
@@ -511,6 +521,29 @@ def horus_mode(args):
         rows0, util0, flags0, recs0, order0 = eng.fetch(0)
     ref = oracle.run_horus(cluster, tables[0], scheme="horus", schedule="horus", num_buffer=5, seed=0)
     assert rows0.tobytes() == ref.rows.tobytes() and util0.tobytes() == ref.util.tobytes(), "replica 0 differs from the oracle"
+    # horus+ (credit queues + k-means, raw word stream): a few replicas against the oracle, replica by replica
+    plus = None
+    try:
+        k = 6
+        np.random.seed(1)
+        words = np.random.randint(0, 2 ** 32, size=args.horus_words, dtype=np.uint32)
+        pp = capi.make_horus_params("horus+", "horus+", 15, 3)
+        with capi.HorusEngine(device=0, nsims=k) as eng:
+            for r in range(k):
+                eng.config(r, cluster, pp)
+                eng.load_trace(r, tables[r])
+            eng.load_words(-1, words)
+            eng.run(rows_cap=args.horus_rows)
+            plus_ms = float(eng.stats(0).kernel_ms)
+            same = 0
+            for r in range(k):
+                prow, putil, pflag, precs, porder = eng.fetch(r)
+                pref = oracle.run_horus(cluster, tables[r], scheme="horus+", schedule="horus+", num_buffer=15, num_queue=3, seed=1)
+                same += int(prow.tobytes() == pref.rows.tobytes() and putil.tobytes() == pref.util.tobytes()
+                            and precs.tobytes() == pref.recs.tobytes() and np.array_equal(porder, pref.finish_order))
+        plus = {"replicas": k, "identical_to_oracle": same, "kernel_ms": plus_ms}
+    except Exception as exc:                                # noqa: BLE001 - reported, never fatal for the horus line
+        plus = {"error": repr(exc)}
     sample = min(R, 64)
     t0 = time.perf_counter()
     cpu_ev = sum(oracle.run_horus(cluster, tables[r], scheme="horus", schedule="horus", num_buffer=5, seed=0).events for r in range(sample))
@@ -519,6 +552,7 @@ def horus_mode(args):
                       "kernel_ms": ms, "replicas": R, "jobs_per_replica": n, "ticks": ticks, "samples_drawn": draws,
                       "samples_per_s": draws / (ms / 1e3), "kernel": "gs_horus_kernel (one simulation per thread)", "kernel_ms_by_lanes_per_warp": by_lanes,
                       "parity": "replica 0 == oracle/horus_oracle.c == reference (tests/golden/horus_*)",
+                      "horus_plus_device_check": plus,
                       "cpu_baseline": {"value": cpu_ev / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
                                        "sample": f"{sample} of the {R} replicas, oracle/horus_oracle.c, one thread"}}), flush=True)
 
@@ -620,6 +654,8 @@ def main():
     ap.add_argument("--horus-jobs", type=int, default=60)
     ap.add_argument("--horus-stream", type=int, default=4000000, help="standard-normal samples loaded per replica")
     ap.add_argument("--horus-rows", type=int, default=8192)
+    ap.add_argument("--horus-both-mappings", action="store_true", help="also time 32 simulations per warp")
+    ap.add_argument("--horus-words", type=int, default=6 << 20, help="raw generator words for the horus+ device check")
     ap.add_argument("--place-jobs", type=int, default=64 * 1024 * 1024)
     args = ap.parse_args()
     if args.mode == "place":
