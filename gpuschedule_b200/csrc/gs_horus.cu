@@ -228,12 +228,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   if (n) HCU(cudaMemcpyAsync(d + o_jobs, s.jobs.data(), sizeof(HJob) * n, cudaMemcpyHostToDevice, h->stream));
   std::vector<HTask> tasks(NT);
   std::vector<int> tron(NT, -1);
-  for (size_t j = 0; j < n; ++j)
-    for (int k = 0; k < s.jobs[j].ntasks; ++k) {
-      HTask &t = tasks[(size_t)s.jobs[j].first_task + k];
-      t.duration = t.original = s.jobs[j].duration; t.job = (int)j; t.time_processed = 0; t.placed_node = -1; t.run_node = -1;
-      t.interfered = t.running = t.finished = t.pad = 0;
-    }
+  gs_horus_init_tasks(s.jobs.data(), (long long)n, (long long)c.gpu_mem_cap_mib << 20, tasks.data());
   HCU(cudaMemcpyAsync(d + o_tasks, tasks.data(), sizeof(HTask) * NT, cudaMemcpyHostToDevice, h->stream));
   HCU(cudaMemcpyAsync(d + o_tron, tron.data(), 4 * NT, cudaMemcpyHostToDevice, h->stream));
   if (s.stream.size() > s.stream_cap) {

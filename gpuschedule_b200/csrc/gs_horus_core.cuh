@@ -53,13 +53,19 @@ struct HJobState {
   int pending, start, end, migration, tasks_finished, tro_n;
   unsigned char running, finished, in_running, pad;
 };
-struct HTask {
+struct HTask {           // 72 bytes; the constants are copied from the job so that the sampling loops touch one record
   double duration, original;           // Task.duration / original_duration (job.py:33-34)
+  double util_avg, half_spread;        // loc and scale of the utilisation sample: avg, (max - avg) / 2 (device.py:52)
+  double quarter_spread;               // scale of the interference sample: (max - avg) / 4 (device.py:31)
+  long long mem_clamped;               // min(device memory, gpu_memory_max) in bytes (device.py:59)
   int job, time_processed;
   int placed_node, run_node;           // membership in Node.placed_tasks / Node.running_tasks
   unsigned char interfered, running, finished, pad;
+  int pad2;
 };
-struct HDev { int nt; int t[H_DEV_SLOTS]; };        // Device.running_tasks in insertion order
+// Device.running_tasks in insertion order + the sum of the clamped task memories (get_current_memory is
+// min(capacity, that sum): clamping after every term or once gives the same value for non-negative terms)
+struct HDev { int nt; int t[H_DEV_SLOTS]; int pad; long long mem_sum; };
 struct HNode { int cpu_used, mem_used, n_running, n_placed_tasks, n_placed_jobs; };
 struct HCand { double min_score; int node, pad; };
 
@@ -126,11 +132,7 @@ GS_HD long long h_task_mem(const HSim &s, int t) { return s.jobs[s.tasks[t].job]
 GS_HD bool h_node_is_free(const HSim &s, int nd) { return s.cpu_cap - s.nodes[nd].cpu_used > 0 || s.mem_cap - s.nodes[nd].mem_used > 0; }   // node.py:57-58
 
 // Device.get_current_memory (device.py:56-62) in bytes: every term is an exact binary fraction of a MiB
-GS_HD long long h_dev_mem(const HSim &s, const HDev &d) {
-  long long m = 0;
-  for (int i = 0; i < d.nt; ++i) { long long x = h_task_mem(s, d.t[i]); if (x > s.cap_b) x = s.cap_b; m += x; if (m > s.cap_b) m = s.cap_b; }
-  return m;
-}
+GS_HD long long h_dev_mem(const HSim &s, const HDev &d) { return d.mem_sum > s.cap_b ? s.cap_b : d.mem_sum; }
 // Device.can_fit (device.py:67-76): at most 4 tasks, 500 MiB margin
 GS_HD bool h_dev_can_fit(const HSim &s, const HDev &d, int t) {
   const long long cur = h_dev_mem(s, d);
@@ -141,8 +143,8 @@ GS_HD bool h_dev_can_fit(const HSim &s, const HDev &d, int t) {
 GS_HD double h_dev_util(HSim &s, const HDev &d, int *is_arr) {
   double u = 0.0; int arr = 0;
   for (int i = 0; i < d.nt; ++i) {
-    const HJob &j = s.jobs[s.tasks[d.t[i]].job];
-    const double x = h_normal(s, j.util_avg, (j.util_max - j.util_avg) / 2);
+    const HTask &o = s.tasks[d.t[i]];
+    const double x = h_normal(s, o.util_avg, o.half_spread);
     if (x < 100.0) { u = H_ADD(u, x); arr = 1; } else { u = H_ADD(u, 100.0); }    // min(100, sample)
     if (100.0 < u) { u = 100.0; arr = 0; }                                        // min(util, 100)
   }
@@ -156,14 +158,14 @@ GS_HD bool h_dev_add_task(HSim &s, HDev &d, int t, bool pack) {
   HTask &tk = s.tasks[t];
   if (d.nt >= 2) {
     for (int i = 0; i < d.nt; ++i) {      // interference samples are drawn; the slowed duration is only logged (:35-37)
-      const HJob &j = s.jobs[s.tasks[d.t[i]].job];
-      (void)h_normal(s, j.util_avg, (j.util_max - j.util_avg) / 4);
+      const HTask &o = s.tasks[d.t[i]];
+      (void)h_normal(s, o.util_avg, o.quarter_spread);
     }
     tk.interfered = 1;
   } else { tk.interfered = 0; tk.duration = tk.original; }
   for (int i = 0; i < d.nt; ++i) if (d.t[i] == t) return true;                   // key already present: position kept
   if (d.nt >= H_DEV_SLOTS) { s.status = GS_ERR_STATE; return true; }
-  d.t[d.nt++] = t;
+  d.t[d.nt++] = t; d.mem_sum += tk.mem_clamped;
   return true;
 }
 // Node.can_fit (node.py:136-162)
@@ -213,7 +215,7 @@ GS_HD void h_node_release(HSim &s, int nd, int t, bool lift) {
   s.nodes[nd].cpu_used -= H_TASK_CPU; s.nodes[nd].mem_used -= H_TASK_MEM;
   for (int d = 0; d < s.G; ++d) {
     HDev &dv = h_dev(s, nd, d);
-    for (int i = 0; i < dv.nt; ++i) if (dv.t[i] == t) { for (int k = i; k + 1 < dv.nt; ++k) dv.t[k] = dv.t[k + 1]; dv.nt--; break; }
+    for (int i = 0; i < dv.nt; ++i) if (dv.t[i] == t) { for (int k = i; k + 1 < dv.nt; ++k) dv.t[k] = dv.t[k + 1]; dv.nt--; dv.mem_sum -= s.tasks[t].mem_clamped; break; }
   }
   if (!lift) return;
   for (int d = 0; d < s.G; ++d) {          // the set is built over ALL devices first, then applied: same outcome, marks are per task

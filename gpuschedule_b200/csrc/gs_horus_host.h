@@ -27,3 +27,20 @@ static inline void gs_horus_build_gauss_tables(const uint32_t *w, long long n, d
     keep[p] = f * x1; ret[p] = f * x2; next[p] = (int)(p + 4);
   }
 }
+
+// Task records of a freshly loaded trace (one per (job, worker)); shared by the library and by the host build of the
+// device functions in tests/emu, so that both start from the same bytes.
+template <class Job, class Task>
+static inline void gs_horus_init_tasks(const Job *jobs, long long n, long long cap_b, Task *tasks) {
+  for (long long j = 0; j < n; ++j)
+    for (int k = 0; k < jobs[j].ntasks; ++k) {
+      Task &t = tasks[jobs[j].first_task + k];
+      t.duration = t.original = jobs[j].duration;
+      t.util_avg = jobs[j].util_avg;
+      t.half_spread = (jobs[j].util_max - jobs[j].util_avg) / 2;
+      t.quarter_spread = (jobs[j].util_max - jobs[j].util_avg) / 4;
+      t.mem_clamped = jobs[j].mem_b < cap_b ? jobs[j].mem_b : cap_b;
+      t.job = (int)j; t.time_processed = 0; t.placed_node = -1; t.run_node = -1;
+      t.interfered = t.running = t.finished = t.pad = 0; t.pad2 = 0;
+    }
+}

@@ -49,12 +49,8 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   std::vector<int> mn((size_t)maxg * maxg), mo((size_t)maxg * maxg), mc((size_t)maxg), ok((size_t)maxg), di((size_t)maxg);
   std::vector<HCand> heap((size_t)maxg + 2);
   memset(js.data(), 0, sizeof(HJobState) * N); memset(nodes.data(), 0, sizeof(HNode) * (size_t)M); memset(devs.data(), 0, sizeof(HDev) * (size_t)M * G);
-  for (long long j = 0; j < n; ++j)
-    for (int k = 0; k < jobs[(size_t)j].ntasks; ++k) {
-      HTask &t = tasks[(size_t)jobs[(size_t)j].first_task + k];
-      memset(&t, 0, sizeof(t));
-      t.duration = t.original = duration[j]; t.job = (int)j; t.placed_node = -1; t.run_node = -1;
-    }
+  memset(tasks.data(), 0, sizeof(HTask) * NT);
+  gs_horus_init_tasks(jobs.data(), n, (long long)c->gpu_mem_cap_mib << 20, tasks.data());
   HSim s; memset(&s, 0, sizeof(s));
   s.M = M; s.G = G; s.S = c->num_switch; s.P = c->num_node_p_switch; s.cpu_cap = c->num_cpu_p_node; s.mem_cap = c->mem_p_node;
   s.scheme = par->score; s.schedule = par->schedule; s.num_buffer = par->num_buffer; s.n = (int)n; s.maxg = maxg; s.pjw = pjw;
