@@ -64,8 +64,10 @@ class Infrastructure:
         self.num_gpu_p_node = flags.num_gpu_p_node
         self.mem_p_node = flags.mem_p_node
         self.cluster_spec = getattr(flags, "cluster_spec", None)
-        if getattr(flags, "pack", False):
-            raise NotImplementedError("--pack is outside the engine's scope (RNG-driven interference, device.py:26-39)")
+        # --pack: the reference stores it on every Node / Device (infrastructure.py:55, node.py:22, device.py:12) and
+        # never reads it again -- packing is decided by the placement scheme (pack=True inside horus_placement) -- so
+        # the flag is accepted and, as there, changes nothing.
+        self.enable_pack = bool(getattr(flags, "pack", False))
         if self.cluster_spec and os.path.exists(self.cluster_spec):
             self._init_from_spec_file()
         self._init_nodes()
