@@ -32,9 +32,79 @@ def make_flags(**overrides):
     return types.SimpleNamespace(**{**DEFAULTS, **overrides})
 
 
+def _is_utilisation_aware(fl):
+    return fl.scheme in Scheduler.UTILISATION_AWARE or fl.schedule in Scheduler.UTILISATION_AWARE
+
+
+def run_batched_horus(flag_sets, device=0, out_root="log", chunk=1 << 21, rows_cap=1 << 16):
+    """The horus / horus+ / gandiva configurations of a sweep as replicas of ONE gs_horus launch.  Every replica
+    owns a numpy RandomState (seeded with flags.seed when >= 0, fresh entropy otherwise -- the reference's repeats
+    are unseeded) whose stream it consumes exactly like the single-run path does with numpy's global one, so a
+    seeded replica writes the same bytes as `run_sim.py --seed s`.  Returns [(output_dir, stats)]."""
+    sims = []
+    for fl in flag_sets:
+        infra = Infrastructure(fl)
+        jm = JobsManager(fl, JobQueueManager(fl, fl.trace_file))
+        rs = np.random.RandomState(fl.seed if getattr(fl, "seed", -1) >= 0 else None)
+        raw = fl.schedule == "horus+"
+        draw = (lambda k, rs=rs: rs.randint(0, 2 ** 32, size=k, dtype=np.uint32)) if raw else (lambda k, rs=rs: rs.standard_normal(k))
+        sims.append(dict(fl=fl, infra=infra, jm=jm, raw=raw, draw=draw, stream=draw(chunk), rows_cap=rows_cap))
+    results = []
+    with capi.HorusEngine(device=device, nsims=len(sims)) as eng:
+        for i, sm in enumerate(sims):
+            fl = sm["fl"]
+            eng.config(i, sm["infra"].gs_cluster(), capi.make_horus_params(fl.scheme, fl.schedule, int(fl.num_buffer), int(fl.num_queue)))
+            eng.load_trace(i, sm["jm"].table)
+            (eng.load_words if sm["raw"] else eng.load_stream)(i, sm["stream"])
+        cap = rows_cap
+        while True:
+            try:
+                eng.run(rows_cap=cap)
+                break
+            except capi.GsError as e:
+                if e.code != capi.GS_ERR_CAPACITY:
+                    raise
+                for i, sm in enumerate(sims):             # finished replicas keep their results; the short ones start over
+                    st = eng.stats(i)
+                    if st.status != capi.GS_ERR_CAPACITY:
+                        continue
+                    if st.ticks < sm["rows_cap"]:         # ran out of samples: continue this replica's stream
+                        sm["stream"] = np.concatenate([sm["stream"], sm["draw"](len(sm["stream"]))])
+                    else:
+                        sm["rows_cap"] *= 2
+                    (eng.load_words if sm["raw"] else eng.load_stream)(i, sm["stream"])
+                cap = max(sm["rows_cap"] for sm in sims)
+        for i, sm in enumerate(sims):
+            fl, infra, jm = sm["fl"], sm["infra"], sm["jm"]
+            rows, util, flags_arr, recs, order = eng.fetch(i)
+            stats = eng.stats(i)
+            stamp = datetime.datetime.now().strftime("%Y-%m-%d-%H-%M-%S-%f")
+            out_dir = os.path.join(out_root, fl.log_path, f"{stamp}-r{i}")
+            os.makedirs(out_dir, exist_ok=True)
+            lm = LogManager(out_dir, fl)
+            lm.init(infra)
+            cl = infra.gs_cluster()
+            m, g = cl.num_switch * cl.num_node_p_switch, cl.num_gpu_p_node
+            lm.write_cluster_rows(rows, rngcol.sampled_utilization_text(util, flags_arr), m * g * cl.gpu_mem_cap_mib)
+            lm.write_horus_job_rows(jm.table, recs, order)
+            results.append((out_dir, stats))
+    return results
+
+
 def run_batched(flag_sets, device=0, out_root="log"):
     """Run every configuration of `flag_sets` (list of flags namespaces) as one replica each.
-    Returns [(output_dir, stats)]."""
+    Returns [(output_dir, stats)] in the order of `flag_sets`; the utilisation-aware configurations go through
+    run_batched_horus (their own engine handle), the others through one gs_run batch."""
+    aware = [i for i, fl in enumerate(flag_sets) if _is_utilisation_aware(fl)]
+    if aware:
+        plain = [i for i in range(len(flag_sets)) if i not in set(aware)]
+        out = [None] * len(flag_sets)
+        for idx, res in zip(aware, run_batched_horus([flag_sets[i] for i in aware], device, out_root)):
+            out[idx] = res
+        if plain:
+            for idx, res in zip(plain, run_batched([flag_sets[i] for i in plain], device, out_root)):
+                out[idx] = res
+        return out
     sims = []
     for fl in flag_sets:
         infra = Infrastructure(fl)
@@ -71,6 +141,8 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="run a sweep of simulator configurations as one batched GPU launch")
     ap.add_argument("--trace", nargs="+", required=True, help="trace CSV file(s)")
     ap.add_argument("--schedule", nargs="+", default=["fifo"])
+    ap.add_argument("--scheme", default=None, help="placement scheme; default: the schedule's own (yarn for fifo / sjf / dlas / gittins)")
+    ap.add_argument("--num_buffer", type=int, default=5)
     ap.add_argument("--num_switch", type=int, default=4)
     ap.add_argument("--num_node_p_switch", type=int, default=32)
     ap.add_argument("--num_queue", type=int, default=4)
@@ -82,9 +154,10 @@ def main(argv=None):
         for sc in a.schedule:
             for rep in range(a.repeats):
                 tag = os.path.splitext(os.path.basename(tr))[0]
-                sets.append(make_flags(trace_file=tr, schedule=sc, num_switch=a.num_switch,
-                                       num_node_p_switch=a.num_node_p_switch, num_queue=a.num_queue,
-                                       log_path=os.path.join(f"batched_{tag}", f"yarn_{sc}"),
+                scheme = a.scheme or (sc if sc in Scheduler.UTILISATION_AWARE else "yarn")
+                sets.append(make_flags(trace_file=tr, schedule=sc, scheme=scheme, num_switch=a.num_switch,
+                                       num_node_p_switch=a.num_node_p_switch, num_queue=a.num_queue, num_buffer=a.num_buffer,
+                                       log_path=os.path.join(f"batched_{tag}", f"{scheme}_{sc}"),
                                        seed=a.seed if a.seed < 0 else a.seed + rep))
     for out_dir, st in run_batched(sets):
         print(f"{out_dir}: ticks={st.ticks} events={st.events} finished={st.finished}")

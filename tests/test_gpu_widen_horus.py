@@ -183,3 +183,24 @@ def test_word_stream_serves_horus_and_gandiva_too():
     for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
         got_job, got_cluster = render_horus_outputs(table, cluster, res)
         assert got_job == job_csv and got_cluster == cluster_csv, case
+
+
+@NOT_RUN_YET
+def test_batched_sweep_on_device(tmp_path):
+    """sweep.run_batched_horus: seeded horus / gandiva / horus+ replicas in one launch == the single-run fixtures."""
+    import os
+    from conftest import GOLDEN
+    from gpuschedule_b200 import sweep
+    cases = ["horus_small", "gandiva_slice", "horusplus_k3"]
+    sets = []
+    for case in cases:
+        table, cluster, params, _, _ = load_horus(case)
+        sets.append(sweep.make_flags(trace_file=os.path.join(GOLDEN, case, "trace.csv"), scheme=params["scheme"], schedule=params["schedule"],
+                                     num_buffer=params["num_buffer"], num_queue=params["num_queue"], num_switch=cluster.num_switch,
+                                     num_node_p_switch=cluster.num_node_p_switch, num_gpu_p_node=cluster.num_gpu_p_node,
+                                     seed=params["seed"], log_path=case))
+    results = sweep.run_batched_horus(sets, out_root=str(tmp_path), chunk=200000)      # small chunks: single replicas restart
+    for case, (out_dir, st) in zip(cases, results):
+        _, _, _, job_csv, cluster_csv = load_horus(case)
+        assert open(os.path.join(out_dir, "job.csv"), newline="").read() == job_csv, case
+        assert open(os.path.join(out_dir, "cluster.csv"), newline="").read() == cluster_csv, case

@@ -140,11 +140,12 @@ def test_short_stream_is_reported():
 
 class _EmuHorusEngine:
     """Same interface as capi.HorusEngine, backed by the host build of the device functions: lets the host-side
-    mirror (Scheduler.start -> stream chunks, retry on GS_ERR_CAPACITY, formatting, file writing) run on CPU."""
+    mirror (Scheduler.start / sweep.run_batched_horus -> stream chunks, retry on GS_ERR_CAPACITY, formatting, file
+    writing) run on CPU.  Like the library, a finished replica keeps its results across later run() calls."""
 
     def __init__(self, device=0, nsims=1):
-        assert nsims == 1
-        self.res = None
+        self.n = nsims
+        self.cfg, self.table, self.g, self.w, self.res, self.dirty = ([None] * nsims for _ in range(6))
 
     def __enter__(self):
         return self
@@ -153,31 +154,64 @@ class _EmuHorusEngine:
         pass
 
     def config(self, sim, cluster, params):
-        self.cluster, self.params = cluster, params
+        self.cfg[sim] = (cluster, params)
 
     def load_trace(self, sim, table):
-        self.table = table
+        self.table[sim] = table
 
     def load_stream(self, sim, g):
-        self.g, self.w = np.array(g), None
+        self.g[sim], self.w[sim], self.dirty[sim] = np.array(g), None, True
 
     def load_words(self, sim, w):
-        self.g, self.w = None, np.array(w)
+        self.g[sim], self.w[sim], self.dirty[sim] = None, np.array(w), True
 
     def run(self, max_ticks=0, rows_cap=1 << 16):
         from gpuschedule_b200 import capi
         from tests_emu import run_horus
-        out = run_horus(self.cluster, self.params, self.table, self.g, rows_cap, words=self.w)
-        self.res = out
-        self.draws = out[7]
-        if out[0] < 0:
-            raise capi.GsError("emulated gs_horus_run failed", out[0])
+        worst = 0
+        for i in range(self.n):
+            if self.dirty[i]:
+                self.res[i] = run_horus(self.cfg[i][0], self.cfg[i][1], self.table[i], self.g[i], rows_cap, words=self.w[i])
+                self.dirty[i] = False
+            if self.res[i][0] < 0 and worst == 0:
+                worst = self.res[i][0]
+        if worst:
+            raise capi.GsError("emulated gs_horus_run failed", worst)
 
     def stats(self, sim):
-        return SimpleNamespace(ticks=max(self.res[0], 0), events=self.res[6], draws=self.draws, finished=len(self.res[5]), done=1, kernel_ms=0.0)
+        r = self.res[sim]
+        return SimpleNamespace(ticks=max(r[0], 0), events=r[6], draws=r[7], finished=len(r[5]), done=int(r[0] >= 0),
+                               status=min(r[0], 0), kernel_ms=0.0)
 
     def fetch(self, sim):
-        return self.res[1], self.res[2], self.res[3], self.res[4], self.res[5]
+        r = self.res[sim]
+        return r[1], r[2], r[3], r[4], r[5]
+
+
+def test_batched_sweep_writes_reference_bytes_per_replica(tmp_path, monkeypatch):
+    """sweep.run_batched: horus, gandiva and horus+ replicas in one (emulated) launch, each with its own seeded
+    numpy stream handed over in small chunks (forcing restarts of single replicas), next to a plain fifo replica that
+    must be routed to the other engine."""
+    import glob
+    import os
+    from conftest import GOLDEN
+    from gpuschedule_b200 import capi, sweep
+    cases = ["horus_small", "gandiva_slice", "horusplus_k3"]
+    sets = []
+    for case in cases:
+        table, cluster, params, _, _ = load_horus(case)
+        sets.append(sweep.make_flags(trace_file=os.path.join(GOLDEN, case, "trace.csv"), scheme=params["scheme"], schedule=params["schedule"],
+                                     num_buffer=params["num_buffer"], num_queue=params["num_queue"], num_switch=cluster.num_switch,
+                                     num_node_p_switch=cluster.num_node_p_switch, num_gpu_p_node=cluster.num_gpu_p_node,
+                                     seed=params["seed"], log_path=case))
+    monkeypatch.setattr(capi, "HorusEngine", _EmuHorusEngine)
+    results = sweep.run_batched_horus(sets, out_root=str(tmp_path), chunk=30000)
+    assert len(results) == 3
+    for case, (out_dir, st) in zip(cases, results):
+        _, _, _, job_csv, cluster_csv = load_horus(case)
+        assert open(os.path.join(out_dir, "job.csv"), newline="").read() == job_csv, case
+        assert open(os.path.join(out_dir, "cluster.csv"), newline="").read() == cluster_csv, case
+    assert all(sweep._is_utilisation_aware(fl) for fl in sets) and not sweep._is_utilisation_aware(sweep.make_flags())
 
 
 @pytest.mark.parametrize("case", ["horus_small", "gandiva_slice", "horusplus_k3"])
