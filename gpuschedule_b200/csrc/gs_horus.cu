@@ -115,8 +115,10 @@ extern "C" int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster 
   if (c->num_switch <= 0 || c->num_node_p_switch <= 0 || c->num_gpu_p_node <= 0 || c->num_gpu_p_node > 64)
     return hfail(h, GS_ERR_ARG, "gs_horus_config: bad cluster shape");
   if (p->score != GS_HSCORE_HORUS && p->score != GS_HSCORE_GANDIVA) return hfail(h, GS_ERR_ARG, "gs_horus_config: unknown score function");
-  if (p->schedule != GS_HSCHED_FIFO && p->schedule != GS_HSCHED_HORUS && p->schedule != GS_HSCHED_HORUS_PLUS && p->schedule != GS_HSCHED_GANDIVA)
-    return hfail(h, GS_ERR_ARG, "gs_horus_config: schedule must be fifo, horus, horus+ or gandiva");
+  if (p->schedule != GS_HSCHED_HORUS && p->schedule != GS_HSCHED_HORUS_PLUS && p->schedule != GS_HSCHED_GANDIVA)
+    return hfail(h, GS_ERR_ARG, "gs_horus_config: schedule must be horus, horus+ or gandiva (with fifo the reference raises KeyError in score_fn, algorithm.py:58)");
+  if ((p->schedule == GS_HSCHED_GANDIVA) != (p->score == GS_HSCORE_GANDIVA))
+    return hfail(h, GS_ERR_ARG, "gs_horus_config: the score function follows the schedule name (gandiva_score <=> schedule gandiva)");
   if (p->schedule == GS_HSCHED_HORUS_PLUS && (p->num_queue < 1 || p->num_queue > H_MAXQ))
     return hfail(h, GS_ERR_ARG, "gs_horus_config: horus+ needs 1..8 queues");
   if (c->enable_network_costs) return hfail(h, GS_ERR_ARG, "gs_horus_config: network costs are not part of this path");

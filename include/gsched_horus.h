@@ -34,7 +34,10 @@
 extern "C" {
 #endif
 
-enum { GS_HSCORE_HORUS = 0, GS_HSCORE_GANDIVA = 1 };              /* --scheme: which score_fn (algorithm.py:9-13) */
+/* Which score_fn runs (algorithm.py:9-13).  NOTE: the reference indexes score_fn with the SCHEDULE name
+ * (schedule.py:47 passes self.schedule down as `scheme`; algorithm.py:58,196): horus and horus+ -> horus_score,
+ * gandiva -> gandiva_score, fifo -> KeyError.  --scheme horus|horus+|gandiva only selects horus_placement. */
+enum { GS_HSCORE_HORUS = 0, GS_HSCORE_GANDIVA = 1 };
 enum { GS_HSCHED_FIFO = 0, GS_HSCHED_HORUS = 1, GS_HSCHED_HORUS_PLUS = 2, GS_HSCHED_GANDIVA = 3 };   /* --schedule (algorithm.py:292-298) */
 
 typedef struct gs_horus_params {

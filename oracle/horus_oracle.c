@@ -19,8 +19,9 @@
  * stream draw for draw: results are compared BYTE FOR BYTE with runs of the unmodified reference under
  * numpy.random.seed(S) (tests/golden/make_horus_golden.py -> tests/golden/horus_*).
  *
- * Parity status: PINNED by those fixtures (tests/test_horus_oracle.py).  No CUDA kernel implements
- * this path yet; the file exists so that the next kernel starts from a pinned checker.
+ * Parity status: PINNED by those fixtures (tests/test_horus_oracle.py) and by tests/golden/fuzz_horus_reference.py
+ * (random clusters / traces / score x scheduler combinations against the unmodified reference).  It checks
+ * gs_horus_kernel (include/gsched_horus.h) and the host build of the same device functions (tests/emu).
  */
 #include <math.h>
 #include <stdint.h>
@@ -540,6 +541,8 @@ static void preempt_job(hsim_t *s, int j, int32_t *scratch, double *dscratch) {
 
 typedef struct { int32_t start, end, jct, preempt; double original, actual; } horus_job_rec;
 
+/* `scheme` = which score function (0 horus_score, 1 gandiva_score).  The reference picks it by the SCHEDULE name
+ * (schedule.py:47 -> algorithm.py:196 -> :58 score_fn[scheme] with scheme == self.schedule); the Python wrapper maps. */
 int64_t oracle_run_horus(const gs_cluster *c, int32_t scheme, int32_t schedule, int32_t num_buffer, int32_t num_queue,
                          uint32_t seed, int64_t n, const int32_t *arrive, const int32_t *gpus, const int32_t *gpc,
                          const double *duration, const int64_t *mem_bytes, const double *mem_avg_mib,

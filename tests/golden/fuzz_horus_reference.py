@@ -31,12 +31,15 @@ import oracle  # noqa: E402
 def random_case(seed):
     rng = np.random.default_rng(7000 + seed)
     kind = str(rng.choice(["horus", "horus", "gandiva", "horus+"]))
+    sched = kind
+    if seed >= 1000:                                   # cross combinations of score function and scheduler
+        sched = str(rng.choice(["fifo", "horus", "gandiva", "horus+"]))
     G = int(rng.choice([2, 4, 8, 8]))
     flags = dict(num_switch=int(rng.integers(1, 4)), num_node_p_switch=int(rng.integers(1, 6)), num_gpu_p_node=G,
                  num_cpu_p_node=int(rng.choice([36, 60, 128, 128])), mem_p_node=int(rng.choice([180, 300, 512, 512])),
-                 gpu_memory_capacity=int(rng.choice([16, 32, 32])), _scheme=kind, _schedule=kind,
+                 gpu_memory_capacity=int(rng.choice([16, 32, 32])), _scheme=kind, _schedule=sched,
                  num_buffer=int(rng.choice([1, 2, 5, 15])))
-    if kind == "horus+":
+    if sched == "horus+":
         flags["num_queue"] = int(rng.integers(2, 6))
     gpc = int(rng.choice([1, 1, 1, 2])) if G >= 2 else 1
     choices = sorted(set(int(x) * gpc for x in rng.choice([1, 1, 2, 2, 3, 4, 6, 8, 12], size=4)))

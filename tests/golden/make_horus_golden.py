@@ -37,6 +37,12 @@ CASES = {
                       dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=8, _scheme="gandiva", _schedule="gandiva", num_buffer=1)),
     "horusplus_k3": (lambda: frame(80, 66, 1.0), dict(num_switch=1, num_node_p_switch=4, num_gpu_p_node=8,
                      _scheme="horus+", _schedule="horus+", num_queue=3, num_buffer=15)),
+    # score function and scheduler follow the --schedule name, the placement routine the --scheme name (see
+    # oracle/__init__.py): the two crossed combinations
+    "cross_gandiva_sched_horus": (lambda: frame(70, 68, 1.5), dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=8,
+                                  _scheme="gandiva", _schedule="horus", num_buffer=3)),
+    "cross_horus_sched_gandiva": (lambda: frame(70, 69, 1.5), dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=8,
+                                  _scheme="horus", _schedule="gandiva", num_buffer=1)),
     "horusplus_k5": (lambda: frame(120, 67, 2.0, gpu_choices=[1, 2, 4, 8, 16], gpu_probs=[.3, .3, .2, .1, .1]),
                      dict(num_switch=2, num_node_p_switch=3, num_gpu_p_node=8, _scheme="horus+", _schedule="horus+", num_queue=5, num_buffer=4)),
 }
