@@ -196,7 +196,8 @@ def load_library(path=None):
 
 
 class GsHorusParams(C.Structure):
-    _fields_ = [("score", C.c_int32), ("schedule", C.c_int32), ("num_buffer", C.c_int32), ("num_queue", C.c_int32)]
+    _fields_ = [("score", C.c_int32), ("schedule", C.c_int32), ("num_buffer", C.c_int32), ("num_queue", C.c_int32),
+                ("placement", C.c_int32), ("reserved", C.c_int32)]
 
 
 class GsHorusRunStats(C.Structure):
@@ -207,22 +208,24 @@ class GsHorusRunStats(C.Structure):
 
 HORUS_REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"), ("preempt", "<i4"),
                             ("original", "<f8"), ("actual", "<f8")])
-# --scheme horus | horus+ | gandiva all select horus_placement (core/scheduling/algorithm.py:182-187); WHICH score
+# --scheme horus | horus+ | gandiva all select horus_placement, yarn selects ms_yarn_placement
+# (core/scheduling/algorithm.py:182-187); WHICH score
 # function it uses is decided by the --schedule name, because Scheduler._schedule passes self.schedule down as the
 # `scheme` argument that indexes score_fn (schedule.py:47, algorithm.py:9-13,58,196).  With --schedule fifo that
 # lookup raises KeyError in the reference, so the combination is rejected here as well.
-HORUS_SCHEMES = ("horus", "horus+", "gandiva")
+HORUS_SCHEMES = {"horus": 0, "horus+": 0, "gandiva": 0, "yarn": 1}  # placement routine: horus_placement / ms_yarn_placement
 HORUS_SCHEDULES = {"horus": 1, "horus+": 2, "gandiva": 3}          # --schedule (algorithm.py:292-298)
 HORUS_SCORE_OF_SCHEDULE = {"horus": 0, "horus+": 0, "gandiva": 1}  # score_fn[schedule] (algorithm.py:9-13)
 
 
 def make_horus_params(scheme="horus", schedule="horus", num_buffer=5, num_queue=1):
     if scheme not in HORUS_SCHEMES:
-        raise NotImplementedError(f"scheme {scheme!r}: the utilisation-aware engine serves the horus, horus+ and gandiva schemes")
+        raise NotImplementedError(f"scheme {scheme!r}: the utilisation-aware engine serves the horus, horus+, gandiva and yarn schemes")
     if schedule not in HORUS_SCHEDULES:
         raise NotImplementedError(f"schedule {schedule!r} with scheme {scheme!r}: the reference raises KeyError in "
                                   "score_fn[schedule] (core/scheduling/algorithm.py:58); use horus, horus+ or gandiva")
-    return GsHorusParams(HORUS_SCORE_OF_SCHEDULE[schedule], HORUS_SCHEDULES[schedule], int(num_buffer), int(num_queue))
+    return GsHorusParams(HORUS_SCORE_OF_SCHEDULE[schedule], HORUS_SCHEDULES[schedule], int(num_buffer), int(num_queue),
+                         HORUS_SCHEMES[scheme], 0)
 
 
 class HorusEngine:

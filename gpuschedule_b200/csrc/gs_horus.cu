@@ -121,6 +121,7 @@ extern "C" int gs_horus_config(gs_horus_handle h, int32_t sim, const gs_cluster 
     return hfail(h, GS_ERR_ARG, "gs_horus_config: the score function follows the schedule name (gandiva_score <=> schedule gandiva)");
   if (p->schedule == GS_HSCHED_HORUS_PLUS && (p->num_queue < 1 || p->num_queue > H_MAXQ))
     return hfail(h, GS_ERR_ARG, "gs_horus_config: horus+ needs 1..8 queues");
+  if (p->placement != GS_HPLACE_HORUS && p->placement != GS_HPLACE_YARN) return hfail(h, GS_ERR_ARG, "gs_horus_config: unknown placement");
   if (c->enable_network_costs) return hfail(h, GS_ERR_ARG, "gs_horus_config: network costs are not part of this path");
   auto &s = h->sims[(size_t)sim];
   s.cl = *c; s.par = *p; s.configured = true; s.prepared = false;
@@ -244,6 +245,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   HSim &D = s.dev;
   D = HSim{};
   D.M = M; D.G = G; D.S = c.num_switch; D.P = c.num_node_p_switch; D.cpu_cap = c.num_cpu_p_node; D.mem_cap = c.mem_p_node;
+  D.placement = s.par.placement;
   D.scheme = s.par.score; D.schedule = s.par.schedule; D.num_buffer = s.par.num_buffer; D.n = (int)n; D.maxg = maxg; D.pjw = pjw;
   D.cap_b = (long long)c.gpu_mem_cap_mib << 20;
   D.jobs = (const HJob *)(d + o_jobs); D.js = (HJobState *)(d + o_js); D.tasks = (HTask *)(d + o_tasks);

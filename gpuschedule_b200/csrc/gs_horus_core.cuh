@@ -72,6 +72,7 @@ struct HCand { double min_score; int node, pad; };
 struct HSim {
   // ---- configuration
   int M, G, S, P, cpu_cap, mem_cap, scheme, schedule, num_buffer, n, maxg, pjw;
+  int placement, pad_cfg;               // GS_HPLACE_*: horus_placement or ms_yarn_placement
   long long cap_b;
   // ---- trace and simulation state
   const HJob *jobs; HJobState *js; HTask *tasks;
@@ -345,6 +346,73 @@ GS_HD bool h_placement(HSim &s, int j, int &n_res) {
   return true;
 }
 
+// ---- --scheme yarn under these schedulers: ms_yarn_placement (algorithm.py:28-32,301-417), no packing
+GS_HD int h_node_idle_devices(const HSim &s, int nd) { int c = 0; const HDev *dv = s.devs + (long long)nd * s.G; for (int d = 0; d < s.G; ++d) c += (dv[d].nt == 0); return c; }
+GS_HD int h_can_fit_num_task(const HSim &s, int nd, int gpc, int remaining) {              // node.py:109-127
+  const int g = h_node_idle_devices(s, nd) / gpc - remaining;
+  const int c = (s.cpu_cap - s.nodes[nd].cpu_used) / H_TASK_CPU - remaining, m = (s.mem_cap - s.nodes[nd].mem_used) / H_TASK_MEM - remaining;
+  const int ng = g >= 0 ? remaining : remaining + g, nc = c >= 0 ? remaining : remaining + c, nm = m >= 0 ? remaining : remaining + m;
+  const int r = nc < nm ? nc : nm;
+  return r < ng ? r : ng;
+}
+GS_HD void h_tro_set(HSim &s, int j, int k, int nd) {          // job.tasks_running_on[task] = node (a known key keeps its position)
+  const int t0 = s.jobs[j].first_task; HJobState &st = s.js[j];
+  if (s.tro_node[t0 + k] < 0) {
+    bool known = false;
+    for (int q = 0; q < st.tro_n; ++q) known |= (s.tro_order[t0 + q] == k);
+    if (!known) s.tro_order[t0 + st.tro_n++] = k;
+  }
+  s.tro_node[t0 + k] = nd;
+}
+GS_HD bool h_yarn_placement(HSim &s, int j, int &n_res) {
+  const HJob &jb = s.jobs[j];
+  const int T = jb.ntasks, t0 = jb.first_task, gpc = jb.gpc;
+  n_res = 0;
+  if (jb.gpus <= s.G) {                                         // try_single_node_alloc_ms (algorithm.py:396-417)
+    for (int nd = 0; nd < s.M; ++nd) {
+      if (!h_node_is_free(s, nd)) continue;
+      if (!(h_node_idle_devices(s, nd) >= jb.gpus && s.cpu_cap - s.nodes[nd].cpu_used >= H_TASK_CPU * T && s.mem_cap - s.nodes[nd].mem_used >= H_TASK_MEM * T)) continue;
+      if (h_can_fit_num_task(s, nd, gpc, T) < T) continue;      // Node.try_alloc_job (node.py:234-263)
+      int placed = 0;
+      for (int k = 0; k < T; ++k) if (h_node_reserve_task(s, nd, t0 + k, false)) { h_tro_set(s, j, k, nd); ++placed; }
+      if (placed == 0) continue;                                // devices refused every task: what was charged stays (Q21)
+      h_node_place_job(s, nd, j);
+      s.res_nodes[n_res++] = nd;
+      return true;
+    }
+    return false;
+  }
+  int assigned = 0; const int least = (jb.gpus + s.G - 1) / s.G;   // try_cross_node_alloc_ms (algorithm.py:301-393)
+  for (int nd = 0; nd < s.M; ++nd) {
+    if (!h_node_is_free(s, nd)) continue;
+    if (assigned == T) break;
+    const int can = h_can_fit_num_task(s, nd, gpc, T - assigned);
+    if (can == 0) continue;
+    int worker_count = 0; bool check_next = false;
+    for (int k = assigned; k < T; ++k) {
+      if (!(worker_count <= can)) continue;                     // the `<=` over-try (:341)
+      ++worker_count;
+      if (!h_node_reserve_task(s, nd, t0 + k, false)) { --worker_count; check_next = true; break; }
+      h_tro_set(s, j, k, nd);
+    }
+    if (worker_count > 0) { assigned += worker_count; h_node_place_job(s, nd, j); s.res_nodes[n_res++] = nd; }
+    if (check_next) continue;
+    if (n_res >= least && assigned == T) break;
+  }
+  if (assigned == T && n_res >= least) return true;
+  for (int a = 0; a < n_res; ++a) {                             // not enough: clear everything (:378-387)
+    const int nd = s.res_nodes[a];
+    h_node_pop_job(s, nd, j);
+    for (int k = 0; k < T; ++k)
+      if (s.tasks[t0 + k].placed_node == nd) { s.tasks[t0 + k].placed_node = -1; s.nodes[nd].n_placed_tasks -= 1; h_node_release(s, nd, t0 + k, false); }
+  }
+  n_res = 0;
+  return false;
+}
+GS_HD bool h_place(HSim &s, int j, int &n_res) {               // placement_algorithms[--scheme] (algorithm.py:182-187)
+  return s.placement == GS_HPLACE_YARN ? h_yarn_placement(s, j, n_res) : h_placement(s, j, n_res);
+}
+
 // ---- queues: heapq over Job.__lt__ (base_factory.py:7-11) for horus / horus+, plain list for fifo / gandiva
 GS_HD bool h_job_lt(const HSim &s, int a, int b) { return s.jobs[a].util_avg != 0.0 ? s.jobs[a].util_avg < s.jobs[b].util_avg : false; }
 GS_HD bool h_is_pq(const HSim &s) { return s.schedule == GS_HSCHED_HORUS || s.schedule == GS_HSCHED_HORUS_PLUS; }
@@ -555,12 +623,12 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
             s.look[i] = h_queue_pop(s, qi); s.look_q[i] = qi;
           }
           int pos = -1;
-          for (int i = 0; i < min_k; ++i) if (h_placement(s, s.look[i], nres)) { pos = i; break; }
+          for (int i = 0; i < min_k; ++i) if (h_place(s, s.look[i], nres)) { pos = i; break; }
           if (pos >= 0) { placed = s.look[pos]; for (int i = pos; i + 1 < min_k; ++i) { s.look[i] = s.look[i + 1]; s.look_q[i] = s.look_q[i + 1]; } min_k -= 1; }
           for (int i = 0; i < min_k; ++i) h_queue_insert(s, s.look_q[i], s.look[i], i);          // back to the queue they came from
         } else {                                                                   // schedule_fifo (algorithm.py:189-202)
           const int j = s.queue[0];
-          if (h_placement(s, j, nres)) { (void)h_queue_pop(s, 0); placed = j; }
+          if (h_place(s, j, nres)) { (void)h_queue_pop(s, 0); placed = j; }
         }
         if (placed >= 0) { h_start_job(s, placed, nres); s.events += 1; }
       }

@@ -79,11 +79,10 @@ class Scheduler:
         return self.stats
 
     def start(self):
-        if self.placement in self.UTILISATION_AWARE:       # --scheme picks the placement routine (algorithm.py:182-187)
+        # horus / horus+ / gandiva as scheme (placement routine) or as schedule (scheduler + score function): the
+        # utilisation-aware engine; --scheme yarn with such a schedule runs ms_yarn_placement under that scheduler
+        if self.placement in self.UTILISATION_AWARE or self.schedule in self.UTILISATION_AWARE:
             return self._start_utilisation_aware()
-        if self.schedule in self.UTILISATION_AWARE:
-            raise NotImplementedError(f"--scheme {self.placement} with --schedule {self.schedule}: yarn placement under the "
-                                      "look-ahead / credit / time-slice schedulers is not served")
         t0 = time.time()
         infra, table = self.infrastructure, self.jobs_manager.table
         cluster = infra.gs_cluster()

@@ -33,7 +33,7 @@ def make_flags(**overrides):
 
 
 def _is_utilisation_aware(fl):
-    return fl.scheme in Scheduler.UTILISATION_AWARE
+    return fl.scheme in Scheduler.UTILISATION_AWARE or fl.schedule in Scheduler.UTILISATION_AWARE
 
 
 def run_batched_horus(flag_sets, device=0, out_root="log", chunk=1 << 21, rows_cap=1 << 16):

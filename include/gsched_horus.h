@@ -5,6 +5,7 @@
  * with the reference's score-based placement and its two schedulers in place of yarn + fifo:
  *
  *   placement_algorithms['horus' | 'gandiva'] = horus_placement     core/scheduling/algorithm.py:34-180,182-187
+ *   placement_algorithms['yarn'] under the same schedulers          core/scheduling/algorithm.py:28-32,301-417
  *   score_fn['horus' | 'gandiva']                                    core/scheduling/horus.py:6-56, algorithm.py:9-13
  *   scheduling_algorithms['horus'] = schedule_horus (look-ahead)     core/scheduling/algorithm.py:204-240,292-298
  *   scheduling_algorithms['gandiva'] = schedule_fifo + time slicing  core/scheduling/algorithm.py:189-202,420-444
@@ -40,11 +41,15 @@ extern "C" {
 enum { GS_HSCORE_HORUS = 0, GS_HSCORE_GANDIVA = 1 };
 enum { GS_HSCHED_FIFO = 0, GS_HSCHED_HORUS = 1, GS_HSCHED_HORUS_PLUS = 2, GS_HSCHED_GANDIVA = 3 };   /* --schedule (algorithm.py:292-298) */
 
+enum { GS_HPLACE_HORUS = 0, GS_HPLACE_YARN = 1 };   /* --scheme: horus | horus+ | gandiva -> horus_placement, yarn -> ms_yarn_placement (algorithm.py:182-187) */
+
 typedef struct gs_horus_params {
   int32_t score;        /* GS_HSCORE_* */
   int32_t schedule;     /* GS_HSCHED_* */
   int32_t num_buffer;   /* look-ahead width k of schedule_horus (--num_buffer, run_sim.py:76) */
   int32_t num_queue;    /* horus+: number of credit queues (--num_queue, run_sim.py:75); 0 or 1 otherwise */
+  int32_t placement;    /* GS_HPLACE_* */
+  int32_t reserved;
 } gs_horus_params;
 
 /* One finished (or unfinished) job: the fields LogManager.jcts prints (log_manager.py:137-153). */

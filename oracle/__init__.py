@@ -234,7 +234,7 @@ HORUS_REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"), ("
 # argument of the scheduling algorithm, which hands it to horus_placement, which indexes score_fn with it
 # (schedule.py:47, algorithm.py:9-13,58,196).  --scheme only selects the placement routine, and horus / horus+ /
 # gandiva all map to horus_placement (algorithm.py:182-187).  schedule "fifo" with such a scheme raises KeyError there.
-HORUS_SCHEMES = ("horus", "horus+", "gandiva")
+HORUS_SCHEMES = ("horus", "horus+", "gandiva", "yarn")       # yarn: ms_yarn_placement under the same schedulers
 HORUS_SCORE_OF_SCHEDULE = {"horus": 0, "horus+": 0, "gandiva": 1}
 HORUS_SCHEDULES = {"fifo": 0, "horus": 1, "horus+": 2, "gandiva": 3}
 
@@ -258,7 +258,7 @@ def run_horus(cluster: GsCluster, table, scheme="horus", schedule="horus", num_b
     ua, um = arr(table.util_avg, np.float64), arr(table.util_max, np.float64)
     if scheme not in HORUS_SCHEMES or schedule not in HORUS_SCORE_OF_SCHEDULE:
         raise KeyError(f"scheme {scheme!r} / schedule {schedule!r}: the reference raises here too (score_fn[schedule])")
-    ticks = lib().oracle_run_horus(C.byref(cluster), C.c_int32(HORUS_SCORE_OF_SCHEDULE[schedule]), C.c_int32(HORUS_SCHEDULES[schedule]),
+    ticks = lib().oracle_run_horus(C.byref(cluster), C.c_int32(HORUS_SCORE_OF_SCHEDULE[schedule] | (256 if scheme == "yarn" else 0)), C.c_int32(HORUS_SCHEDULES[schedule]),
                                    C.c_int32(num_buffer), C.c_int32(num_queue), C.c_uint32(seed), C.c_int64(n),
                                    _p(a), _p(g), _p(c), _p(d), _p(m), _p(ma), _p(ua), _p(um),
                                    _p(rows), _p(util), _p(util_arr), C.c_int64(rows_cap), _p(recs), _p(order),

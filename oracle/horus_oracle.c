@@ -97,7 +97,7 @@ typedef struct {
 } hjob_t;
 
 typedef struct {
-  int M, G, S, P, cpu_cap, mem_cap, scheme, schedule, num_buffer, nq;
+  int M, G, S, P, cpu_cap, mem_cap, scheme, schedule, num_buffer, nq, yarn;
   int64_t cap_b, n;
   hnode_t *nodes; hdev_t *devs; hjob_t *jobs; htask_t *tasks;
   int32_t *tro_node, *tro_order;              /* Job.tasks_running_on: value per task, key insertion order */
@@ -348,6 +348,72 @@ racks_done:
   return success;
 }
 
+/* ------------------------------------------------------------------ yarn placement under these schedulers
+ * --scheme yarn with --schedule horus | horus+ | gandiva: ms_yarn_placement (algorithm.py:28-32,301-417) on the same
+ * node / device state.  No packing (pack=False), so every device holds at most one task. */
+static int node_idle_devices(const hsim_t *s, int nd) { int c = 0; for (int d = 0; d < s->G; ++d) c += (s->devs[(size_t)nd * s->G + d].nt == 0); return c; }
+static int node_can_fit_num_task(const hsim_t *s, int nd, int gpc, int remaining) {          /* node.py:109-127 */
+  int g = node_idle_devices(s, nd) / gpc - remaining, c = cpu_free(s, nd) / TASK_CPU - remaining, m = mem_free(s, nd) / TASK_MEM - remaining;
+  int ng = g >= 0 ? remaining : remaining + g, nc = c >= 0 ? remaining : remaining + c, nm = m >= 0 ? remaining : remaining + m;
+  int r = nc < nm ? nc : nm;
+  return r < ng ? r : ng;
+}
+static void tro_set(hsim_t *s, int j, int k, int nd) {            /* job.tasks_running_on[task] = node (dict semantics) */
+  hjob_t *jb = &s->jobs[j];
+  if (s->tro_node[jb->first_task + k] < 0) {
+    int known = 0;
+    for (int q = 0; q < jb->tro_n; ++q) known |= (s->tro_order[jb->first_task + q] == k);
+    if (!known) s->tro_order[jb->first_task + jb->tro_n++] = k;
+  }
+  s->tro_node[jb->first_task + k] = nd;
+}
+static int yarn_placement(hsim_t *s, int j, int32_t *res_nodes, int *n_res) {
+  hjob_t *jb = &s->jobs[j];
+  const int T = jb->ntasks, t0 = jb->first_task, gpc = jb->gpc;
+  *n_res = 0;
+  if (jb->gpus <= s->G) {                                         /* try_single_node_alloc_ms  algorithm.py:396-417 */
+    for (int nd = 0; nd < s->M; ++nd) {
+      if (!node_is_free(s, nd)) continue;
+      if (!(node_idle_devices(s, nd) >= jb->gpus && cpu_free(s, nd) >= TASK_CPU * T && mem_free(s, nd) >= TASK_MEM * T)) continue;
+      if (node_can_fit_num_task(s, nd, gpc, T) < T) continue;     /* Node.try_alloc_job  node.py:234-263 */
+      int placed = 0;
+      for (int k = 0; k < T; ++k) if (node_reserve_task(s, nd, t0 + k, 0)) { tro_set(s, j, k, nd); ++placed; }
+      if (placed == 0) continue;                                  /* devices refused every task: what was charged stays */
+      node_place_job(s, nd, j);
+      res_nodes[(*n_res)++] = nd;
+      return 1;
+    }
+    return 0;
+  }
+  int assigned = 0, least = (jb->gpus + s->G - 1) / s->G;         /* try_cross_node_alloc_ms  algorithm.py:301-393 */
+  for (int nd = 0; nd < s->M; ++nd) {
+    if (!node_is_free(s, nd)) continue;
+    if (assigned == T) break;
+    int can = node_can_fit_num_task(s, nd, gpc, T - assigned);
+    if (can == 0) continue;
+    int worker_count = 0, check_next = 0;
+    for (int k = assigned; k < T; ++k) {
+      if (!(worker_count <= can)) continue;                       /* the `<=` over-try (:341) */
+      ++worker_count;
+      if (!node_reserve_task(s, nd, t0 + k, 0)) { --worker_count; check_next = 1; break; }
+      tro_set(s, j, k, nd);
+    }
+    if (worker_count > 0) { assigned += worker_count; node_place_job(s, nd, j); res_nodes[(*n_res)++] = nd; }
+    if (check_next) continue;
+    if (*n_res >= least && assigned == T) break;
+  }
+  if (assigned == T && *n_res >= least) return 1;
+  for (int a = 0; a < *n_res; ++a) {                              /* not enough: clear everything (:378-387) */
+    const int nd = res_nodes[a];
+    node_pop_job(s, nd, j);
+    for (int k = 0; k < T; ++k)
+      if (s->tasks[t0 + k].placed_node == nd) { s->tasks[t0 + k].placed_node = -1; s->nodes[nd].n_placed_tasks -= 1; (void)node_release(s, nd, t0 + k, NULL, 0); }
+  }
+  *n_res = 0;
+  return 0;
+}
+static int place_job(hsim_t *s, int j, int32_t *res_nodes, int *n_res);
+
 /* ------------------------------------------------------------------ queues (heapq over Job.__lt__) */
 static inline int job_lt(const hsim_t *s, int a, int b) {         /* base_factory.py:7-11 CompareAbleByUtilization */
   if (s->jobs[a].util_avg != 0.0) return s->jobs[a].util_avg < s->jobs[b].util_avg;
@@ -488,6 +554,10 @@ static void jm_insert(hsim_t *s, const int32_t *jobs_in, int64_t n_in, const int
   for (int64_t i = 0; i < n_in; ++i) q_insert(s, jobs_in[i], qpos ? qpos[i] : 0, i);
 }
 
+static int place_job(hsim_t *s, int j, int32_t *res_nodes, int *n_res) {   /* placement_algorithms[--scheme]  algorithm.py:182-187 */
+  return s->yarn ? yarn_placement(s, j, res_nodes, n_res) : horus_placement(s, j, res_nodes, n_res);
+}
+
 /* ------------------------------------------------------------------ start / finish / preempt */
 static void start_job(hsim_t *s, int j, const int32_t *nodes, int nn, int delta) {   /* schedule.py:159-162, node.py:164-188, job.py:153-169 */
   hjob_t *jb = &s->jobs[j];
@@ -554,6 +624,8 @@ int64_t oracle_run_horus(const gs_cluster *c, int32_t scheme, int32_t schedule, 
   hsim_t *s = &S;
   s->S = c->num_switch; s->P = c->num_node_p_switch; s->M = s->S * s->P; s->G = c->num_gpu_p_node;
   s->cpu_cap = c->num_cpu_p_node; s->mem_cap = c->mem_p_node; s->cap_b = (int64_t)c->gpu_mem_cap_mib << 20;
+  s->yarn = (scheme >> 8) & 1;                /* bit 8 of `scheme`: --scheme yarn (ms_yarn_placement) */
+  scheme &= 0xff;
   s->scheme = scheme; s->schedule = schedule; s->num_buffer = num_buffer; s->n = n;
   s->nq = num_queue > 0 ? num_queue : 1;
   if (s->nq > MAXQ || s->G > 64) return GS_ERR_ARG;
@@ -606,13 +678,13 @@ int64_t oracle_run_horus(const gs_cluster *c, int32_t scheme, int32_t schedule, 
         int placed = -1, nres = 0;
         if (s->schedule == HS_SCHED_FIFO || s->schedule == HS_SCHED_GANDIVA) {          /* schedule_fifo */
           int j = s->queue[0][0];
-          if (horus_placement(s, j, res_nodes, &nres)) { (void)q_pop(s, 0); placed = j; }
+          if (place_job(s, j, res_nodes, &nres)) { (void)q_pop(s, 0); placed = j; }
         } else if (s->schedule == HS_SCHED_HORUS) {                                      /* schedule_horus */
           int64_t qd = q_total(s), min_k = num_buffer < qd ? num_buffer : qd;
           if (min_k < 0) min_k = 0;
           for (int64_t i = 0; i < min_k; ++i) look[i] = q_pop(s, 0);
           int pos = -1;
-          for (int64_t i = 0; i < min_k; ++i) if (horus_placement(s, look[i], res_nodes, &nres)) { pos = (int)i; break; }
+          for (int64_t i = 0; i < min_k; ++i) if (place_job(s, look[i], res_nodes, &nres)) { pos = (int)i; break; }
           if (pos >= 0) { placed = look[pos]; for (int64_t i = pos; i + 1 < min_k; ++i) look[i] = look[i + 1]; min_k -= 1; }
           jm_insert(s, look, min_k, NULL, scratch, dscratch);
         } else {                                                                          /* schedule_horus_plus */
@@ -625,7 +697,7 @@ int64_t oracle_run_horus(const gs_cluster *c, int32_t scheme, int32_t schedule, 
               look[i] = q_pop(s, qi); look_q[i] = qi;
             }
             int pos = -1;
-            for (int64_t i = 0; i < min_k; ++i) if (horus_placement(s, look[i], res_nodes, &nres)) { pos = (int)i; break; }
+            for (int64_t i = 0; i < min_k; ++i) if (place_job(s, look[i], res_nodes, &nres)) { pos = (int)i; break; }
             if (pos >= 0) { placed = look[pos]; for (int64_t i = pos; i + 1 < min_k; ++i) { look[i] = look[i + 1]; look_q[i] = look_q[i + 1]; } min_k -= 1; }
             jm_insert(s, look, min_k, look_q, scratch, dscratch);
           }

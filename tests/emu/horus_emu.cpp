@@ -53,6 +53,7 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   gs_horus_init_tasks(jobs.data(), n, (long long)c->gpu_mem_cap_mib << 20, tasks.data());
   HSim s; memset(&s, 0, sizeof(s));
   s.M = M; s.G = G; s.S = c->num_switch; s.P = c->num_node_p_switch; s.cpu_cap = c->num_cpu_p_node; s.mem_cap = c->mem_p_node;
+  s.placement = par->placement;
   s.scheme = par->score; s.schedule = par->schedule; s.num_buffer = par->num_buffer; s.n = (int)n; s.maxg = maxg; s.pjw = pjw;
   s.cap_b = (long long)c->gpu_mem_cap_mib << 20;
   s.jobs = jobs.data(); s.js = js.data(); s.tasks = tasks.data(); s.tro_node = tron.data(); s.tro_order = troo.data();

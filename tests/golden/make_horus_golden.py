@@ -43,6 +43,13 @@ CASES = {
                                   _scheme="gandiva", _schedule="horus", num_buffer=3)),
     "cross_horus_sched_gandiva": (lambda: frame(70, 69, 1.5), dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=8,
                                   _scheme="horus", _schedule="gandiva", num_buffer=1)),
+    # --scheme yarn (no packing) under the look-ahead / time-slice / credit schedulers
+    "yarn_sched_horus": (lambda: frame(90, 70, 1.5, gpu_choices=[1, 2, 4, 8, 12, 16], gpu_probs=[.3, .2, .2, .15, .1, .05]),
+                         dict(num_switch=2, num_node_p_switch=3, num_gpu_p_node=8, _scheme="yarn", _schedule="horus", num_buffer=4)),
+    "yarn_sched_gandiva": (lambda: frame(80, 71, 2.0, gpu_choices=[1, 2, 4, 8, 12], gpu_probs=[.3, .3, .2, .1, .1]),
+                           dict(num_switch=1, num_node_p_switch=4, num_gpu_p_node=8, _scheme="yarn", _schedule="gandiva", num_buffer=1)),
+    "yarn_sched_horusplus": (lambda: frame(80, 72, 1.5), dict(num_switch=1, num_node_p_switch=4, num_gpu_p_node=8,
+                             _scheme="yarn", _schedule="horus+", num_queue=3, num_buffer=5)),
     "horusplus_k5": (lambda: frame(120, 67, 2.0, gpu_choices=[1, 2, 4, 8, 16], gpu_probs=[.3, .3, .2, .1, .1]),
                      dict(num_switch=2, num_node_p_switch=3, num_gpu_p_node=8, _scheme="horus+", _schedule="horus+", num_queue=5, num_buffer=4)),
 }
