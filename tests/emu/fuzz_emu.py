@@ -14,15 +14,16 @@ bad=0; t0=time.time()
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     rng=np.random.default_rng(50000+seed)
     kind=str(rng.choice(["horus","gandiva","horus+"]))
+    scheme=str(rng.choice(["horus","gandiva","horus+","yarn"]))      # placement routine; the score follows the schedule
     G=int(rng.choice([2,4,8])); gpc=int(rng.choice([1,1,2]))
     cluster=capi.make_cluster(num_switch=int(rng.integers(1,4)),num_node_p_switch=int(rng.integers(1,6)),num_gpu_p_node=G,
         num_cpu_p_node=int(rng.choice([36,60,128])),mem_p_node=int(rng.choice([180,300,512])),gpu_memory_capacity=int(rng.choice([16,32])))
     choices=sorted(set(int(x)*gpc for x in rng.choice([1,1,2,3,4,6,8,12],size=4)))
     table=ingest.table_from_columns(tracegen.synth_columns(int(rng.integers(10,160)),seed=60000+seed,rate=float(rng.choice([0.5,1,2,4])),
         gpu_per_container=gpc,gpu_choices=choices,gpu_probs=rng.dirichlet(np.ones(len(choices))),max_mem_mib=int(rng.choice([6000,16384,33500]))))
-    params=dict(scheme=kind,schedule=kind,num_buffer=int(rng.choice([1,2,5,15])),num_queue=int(rng.integers(1,7)) if kind=="horus+" else 1,seed=int(rng.integers(0,2**31-1)))
+    params=dict(scheme=scheme,schedule=kind,num_buffer=int(rng.choice([1,2,5,15])),num_queue=int(rng.integers(1,7)) if kind=="horus+" else 1,seed=int(rng.integers(0,2**31-1)))
     ref=oracle.run_horus(cluster,table,**params)
-    hp=capi.make_horus_params(kind,kind,params["num_buffer"],params["num_queue"])
+    hp=capi.make_horus_params(scheme,kind,params["num_buffer"],params["num_queue"])
     np.random.seed(params["seed"])
     need_words=int(ref.draws*3+200000+ref.ticks*50)
     if kind=="horus+" or seed%2:

@@ -34,6 +34,8 @@ def random_case(seed):
     sched = kind
     if seed >= 1000:                                   # cross combinations of score function and scheduler
         sched = str(rng.choice(["fifo", "horus", "gandiva", "horus+"]))
+    if seed >= 2000:                                   # --scheme yarn (no packing) under these schedulers
+        kind, sched = "yarn", str(rng.choice(["horus", "gandiva", "horus+"]))
     G = int(rng.choice([2, 4, 8, 8]))
     flags = dict(num_switch=int(rng.integers(1, 4)), num_node_p_switch=int(rng.integers(1, 6)), num_gpu_p_node=G,
                  num_cpu_p_node=int(rng.choice([36, 60, 128, 128])), mem_p_node=int(rng.choice([180, 300, 512, 512])),
