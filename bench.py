@@ -548,11 +548,31 @@ def horus_mode(args):
     t0 = time.perf_counter()
     cpu_ev = sum(oracle.run_horus(cluster, tables[r], scheme="horus", schedule="horus", num_buffer=5, seed=0).events for r in range(sample))
     cpu_s = time.perf_counter() - t0
+    # the warp-cooperative mapping (one simulation per warp, all lanes score together): LAST, in its own handle, so
+    # that whatever it does cannot touch the numbers above
+    coop = None
+    try:
+        with capi.HorusEngine(device=0, nsims=R) as eng:
+            eng.set_lanes(0)
+            for r in range(R):
+                eng.config(r, cluster, hp)
+                eng.load_trace(r, tables[r])
+            eng.load_stream(-1, stream)
+            eng.run(rows_cap=args.horus_rows)
+            cst = [eng.stats(r) for r in range(R)]
+            crow, cutil, cflag, crecs, corder = eng.fetch(0)
+            coop = {"kernel_ms": float(cst[0].kernel_ms), "events": sum(int(x.events) for x in cst),
+                    "events_per_s": sum(int(x.events) for x in cst) / (float(cst[0].kernel_ms) / 1e3),
+                    "replica0_identical_to_oracle": bool(crow.tobytes() == ref.rows.tobytes() and cutil.tobytes() == ref.util.tobytes()
+                                                         and crecs.tobytes() == ref.recs.tobytes()),
+                    "same_event_total_as_scalar_mapping": sum(int(x.events) for x in cst) == events}
+    except Exception as exc:                                # noqa: BLE001
+        coop = {"error": repr(exc)}
     print(json.dumps({"metric": "horus simulated events/s (replica batch)", "value": events / (ms / 1e3), "unit": UNIT,
                       "kernel_ms": ms, "replicas": R, "jobs_per_replica": n, "ticks": ticks, "samples_drawn": draws,
                       "samples_per_s": draws / (ms / 1e3), "kernel": "gs_horus_kernel (one simulation per thread)", "kernel_ms_by_lanes_per_warp": by_lanes,
                       "parity": "replica 0 == oracle/horus_oracle.c == reference (tests/golden/horus_*)",
-                      "horus_plus_device_check": plus,
+                      "horus_plus_device_check": plus, "cooperative_warp_mapping": coop,
                       "cpu_baseline": {"value": cpu_ev / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
                                        "sample": f"{sample} of the {R} replicas, oracle/horus_oracle.c, one thread"}}), flush=True)
 

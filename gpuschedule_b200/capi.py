@@ -276,7 +276,7 @@ class HorusEngine:
         self._n[sim] = table.n
 
     def set_lanes(self, lanes):
-        """simulations per warp: 1 (lane 0 of every warp) or 32"""
+        """simulations per warp: 1 (lane 0 of every warp) or 32; 0 = one per warp, all lanes cooperate in the scoring"""
         self._check(self.lib.gs_horus_set_lanes(self.h, int(lanes)), "gs_horus_set_lanes")
 
     def load_stream(self, sim, standard_normal):

@@ -21,6 +21,27 @@ __global__ void __launch_bounds__(32) gs_horus_kernel(HSim *sims, int nsims, lon
   sims[i] = s;
 }
 
+// One simulation per WARP: lane 0 runs the simulation, all lanes score a candidate job's devices together
+// (see "Warp-cooperative driver" in gs_horus_core.cuh).  The per-warp copy of the state lives in shared memory.
+__global__ void __launch_bounds__(32) gs_horus_coop_kernel(HSim *sims, int nsims, long long max_ticks) {
+  __shared__ HSim s;
+  __shared__ int req;
+  const int b = blockIdx.x, lane = threadIdx.x;
+  if (b >= nsims) return;
+  if (lane == 0) { s = sims[b]; s.budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL; }
+  __syncwarp();
+  if (s.n < 0 || s.done || s.status != 0) return;          // uniform: every lane reads the same shared words
+  for (;;) {
+    if (lane == 0) req = h_coop_advance(s);
+    __syncwarp();                                           // lane 0's state (shared and global) is visible to the warp
+    const int r = req;
+    if (r == H_REQ_DONE) break;
+    if (r == H_REQ_PREP) h_coop_prep(s); else h_coop_score(s);
+    __syncwarp();                                           // the lanes' counts / costs are visible to lane 0
+  }
+  if (lane == 0) { h_write_records(s); sims[b] = s; }
+}
+
 namespace {
 struct WordStream {                 // raw MT19937 words + the per-position sample tables (gs_horus_host.h)
   std::vector<uint32_t> words;
@@ -105,7 +126,7 @@ extern "C" int gs_horus_destroy(gs_horus_handle h) {
 extern "C" const char *gs_horus_last_error(gs_horus_handle h) { return h ? h->err.c_str() : g_horus_create_err.c_str(); }
 extern "C" int64_t gs_horus_launch_count(gs_horus_handle h) { return h ? h->launches : 0; }
 extern "C" int gs_horus_set_lanes(gs_horus_handle h, int lanes) {
-  if (!h || (lanes != 1 && lanes != 32)) return hfail(h, GS_ERR_ARG, "gs_horus_set_lanes: 1 or 32");
+  if (!h || (lanes != 0 && lanes != 1 && lanes != 32)) return hfail(h, GS_ERR_ARG, "gs_horus_set_lanes: 0 (cooperative warp), 1 or 32");
   h->lanes = lanes;
   return GS_OK;
 }
@@ -219,6 +240,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   const size_t o_pj = take(8 * N * (size_t)pjw), o_q = take(4 * (N + 1) * (size_t)nq), o_run = take(4 * N), o_fin = take(4 * N);
   const size_t o_look = take(4 * (size_t)nb), o_lookq = take(4 * (size_t)nb), o_work = take(4 * N), o_res = take(4 * (size_t)M);
   const size_t o_kall = take(4 * N), o_kas = take(4 * N), o_kold = take(4 * N), o_ksc = take(8 * N);
+  const size_t o_sccnt = take(4 * (size_t)M * G), o_scoff = take(4 * (size_t)M * G), o_sccost = take(8 * (size_t)M * G);
   const size_t o_mn = take(4 * (size_t)maxg * maxg), o_mo = take(4 * (size_t)maxg * maxg), o_mc = take(4 * (size_t)maxg);
   const size_t o_ok = take(4 * (size_t)maxg), o_di = take(4 * (size_t)maxg), o_heap = take(sizeof(HCand) * ((size_t)maxg + 2));
   const size_t o_rows = take(sizeof(gs_tick_row) * (size_t)rows_cap), o_util = take(8 * (size_t)rows_cap), o_ua = take((size_t)rows_cap);
@@ -254,6 +276,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   D.look = (int *)(d + o_look); D.look_q = (int *)(d + o_lookq); D.work = (int *)(d + o_work); D.res_nodes = (int *)(d + o_res);
   D.km_all = (int *)(d + o_kall); D.km_assign = (int *)(d + o_kas); D.km_old = (int *)(d + o_kold); D.km_score = (double *)(d + o_ksc);
   D.nq = nq;
+  D.sc_cnt = (int *)(d + o_sccnt); D.sc_off = (int *)(d + o_scoff); D.sc_cost = (double *)(d + o_sccost);
   if (s.word_mode) {
     const WordStream &ws = s.word_mode == 1 ? s.ws : h->shared_ws;
     D.words = ws.d_words; D.gv_ret = ws.d_ret; D.gv_keep = ws.d_keep; D.gv_next = ws.d_next; D.words_n = (long long)ws.words.size();
@@ -300,7 +323,8 @@ extern "C" int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_c
   HCU(cudaMemcpyAsync(h->d_sims, host.data(), sizeof(HSim) * (size_t)nsims, cudaMemcpyHostToDevice, h->stream));
   HCU(cudaEventRecord(h->ev0, h->stream));
   if (h->lanes == 32) gs_horus_kernel<<<(nsims + 31) / 32, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 32);
-  else gs_horus_kernel<<<nsims, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 1);
+  else if (h->lanes == 1) gs_horus_kernel<<<nsims, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 1);
+  else gs_horus_coop_kernel<<<nsims, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks);
   h->launches += 1;
   HCU(cudaGetLastError());
   HCU(cudaEventRecord(h->ev1, h->stream));

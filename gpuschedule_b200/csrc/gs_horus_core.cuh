@@ -98,6 +98,11 @@ struct HSim {
   double gauss_kept; int has_gauss, pad1;
   // ---- results
   gs_tick_row *rows; double *util; unsigned char *util_arr; gs_horus_job_rec *recs; long long rows_cap;
+  // ---- scheduling step in flight (candidates of this tick) and the cooperative scoring request
+  int la_n, la_i, la_pos, la_nres;
+  int phase, req, sc_job, sc_k, sc_total, sc_hn;
+  long long sc_base, budget;
+  int *sc_cnt, *sc_off; double *sc_cost;   // per device: samples it consumes, their offset, its cost (cooperative scoring)
   // ---- loop state (persisted between launches)
   int delta, p, status, done;
   long long ticks, events, current_remaining, running_jobs;
@@ -272,19 +277,12 @@ GS_HD void h_heap_pop(HCand *h, int &n) {
 }
 
 // horus_placement (algorithm.py:34-180): true on success, res_nodes = distinct nodes in first-use order
-GS_HD bool h_placement(HSim &s, int j, int &n_res) {
+// second half of horus_placement: the candidates are in s.heap[0..hn) (heap order); sort, try, commit
+GS_HD bool h_placement_finish(HSim &s, int j, int hn, int &n_res) {
   const HJob &jb = s.jobs[j];
   HJobState &st = s.js[j];
-  const int T = jb.ntasks, demand = jb.gpus, t0 = jb.first_task;
+  const int T = jb.ntasks, t0 = jb.first_task;
   HCand *heap = s.heap;
-  int hn = 0;
-  for (int k = 0; k < T; ++k)
-    for (int nd = 0; nd < s.M; ++nd) {
-      if (!h_node_is_free(s, nd) || !h_node_can_fit(s, nd, t0 + k, true)) continue;
-      HCand x; x.node = nd; x.pad = 0; x.min_score = h_score_node(s, nd, t0 + k);
-      h_heap_push(heap, hn, x);
-      if (hn > demand) h_heap_pop(heap, hn);
-    }
   for (int i = 1; i < hn; ++i) {                          // sorted(nodes_stack, key=min_score): stable
     const HCand x = heap[i]; int k = i - 1;
     while (k >= 0 && heap[k].min_score > x.min_score) { heap[k + 1] = heap[k]; --k; }
@@ -344,6 +342,20 @@ GS_HD bool h_placement(HSim &s, int j, int &n_res) {
     h_node_place_job(s, nd, j);
   }
   return true;
+}
+GS_HD bool h_placement(HSim &s, int j, int &n_res) {
+  const HJob &jb = s.jobs[j];
+  const int T = jb.ntasks, demand = jb.gpus, t0 = jb.first_task;
+  HCand *heap = s.heap;
+  int hn = 0;
+  for (int k = 0; k < T; ++k)
+    for (int nd = 0; nd < s.M; ++nd) {
+      if (!h_node_is_free(s, nd) || !h_node_can_fit(s, nd, t0 + k, true)) continue;
+      HCand x; x.node = nd; x.pad = 0; x.min_score = h_score_node(s, nd, t0 + k);
+      h_heap_push(heap, hn, x);
+      if (hn > demand) h_heap_pop(heap, hn);
+    }
+  return h_placement_finish(s, j, hn, n_res);
 }
 
 // ---- --scheme yarn under these schedulers: ms_yarn_placement (algorithm.py:28-32,301-417), no packing
@@ -590,49 +602,53 @@ GS_HD void h_preempt(HSim &s, int j) {
   h_queue_insert(s, 0, j, 0);          // gandiva only: one plain list
 }
 
-// Scheduler.start (schedule.py:178-213): runs until done, max_ticks or the row buffer is full
-GS_HD void h_run(HSim &s, long long max_ticks) {
-  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
-  while (!s.done && s.status == 0 && budget > 0) {
-    if (!(s.current_remaining + s.running_jobs > 0)) { s.done = 1; break; }
-    if (s.ticks >= s.rows_cap) { s.status = GS_ERR_CAPACITY; break; }
-    // gen_jobs: rows with normalized_time <= delta in trace order (jobs_manager.py:228-241)
-    {
-      const int first_new = s.p;
-      while (s.p < s.n && s.jobs[s.p].arrive <= s.delta) { ++s.p; ++s.events; }
-      if (s.schedule == GS_HSCHED_HORUS_PLUS) h_insert_reclustered(s, first_new, s.p - first_new);   // every tick, even without arrivals
-      else for (int j = first_new; j < s.p; ++j) h_queue_insert(s, 0, j, j - first_new);
-    }
-    // _schedule (schedule.py:39-58)
-    if (h_queued(s) > 0) {
-      int free_nodes = 0;
-      for (int nd = 0; nd < s.M; ++nd) free_nodes += h_node_is_free(s, nd);
-      if (free_nodes >= 1) {
-        int placed = -1, nres = 0;
-        if (s.schedule == GS_HSCHED_HORUS || s.schedule == GS_HSCHED_HORUS_PLUS) {   // schedule_horus / schedule_horus_plus (algorithm.py:204-290)
-          const bool plus = s.schedule == GS_HSCHED_HORUS_PLUS;
-          const int qd = h_queued(s);
-          int min_k = s.num_buffer < qd ? s.num_buffer : qd;
-          if (min_k < 0) min_k = 0;
-          for (int i = 0; i < min_k; ++i) {
-            int qi = 0;
-            if (plus) {                                     // the queue with the most credit (leaky bucket)
-              h_update_credits(s);
-              for (int q = 1; q < s.nq; ++q) if (s.credits[q] > s.credits[qi]) qi = q;        // np.argmax: first maximum
-            }
-            s.look[i] = h_queue_pop(s, qi); s.look_q[i] = qi;
-          }
-          int pos = -1;
-          for (int i = 0; i < min_k; ++i) if (h_place(s, s.look[i], nres)) { pos = i; break; }
-          if (pos >= 0) { placed = s.look[pos]; for (int i = pos; i + 1 < min_k; ++i) { s.look[i] = s.look[i + 1]; s.look_q[i] = s.look_q[i + 1]; } min_k -= 1; }
-          for (int i = 0; i < min_k; ++i) h_queue_insert(s, s.look_q[i], s.look[i], i);          // back to the queue they came from
-        } else {                                                                   // schedule_fifo (algorithm.py:189-202)
-          const int j = s.queue[0];
-          if (h_place(s, j, nres)) { (void)h_queue_pop(s, 0); placed = j; }
-        }
-        if (placed >= 0) { h_start_job(s, placed, nres); s.events += 1; }
+// ---- Scheduler.start (schedule.py:178-213) in pieces, shared by the scalar driver (h_run) and the warp-cooperative one
+// gen_jobs; false = the loop is over (done, or out of rows)
+GS_HD bool h_tick_begin(HSim &s) {
+  if (!(s.current_remaining + s.running_jobs > 0)) { s.done = 1; return false; }
+  if (s.ticks >= s.rows_cap) { s.status = GS_ERR_CAPACITY; return false; }
+  const int first_new = s.p;                               // rows with normalized_time <= delta (jobs_manager.py:228-241)
+  while (s.p < s.n && s.jobs[s.p].arrive <= s.delta) { ++s.p; ++s.events; }
+  if (s.schedule == GS_HSCHED_HORUS_PLUS) h_insert_reclustered(s, first_new, s.p - first_new);   // every tick, even without arrivals
+  else for (int j = first_new; j < s.p; ++j) h_queue_insert(s, 0, j, j - first_new);
+  return true;
+}
+// _schedule (schedule.py:39-58) up to the placement attempts: the candidate jobs are s.look[0..la_n)
+GS_HD bool h_sched_setup(HSim &s) {
+  s.la_n = 0; s.la_i = 0; s.la_pos = -1; s.la_nres = 0;
+  if (h_queued(s) <= 0) return false;
+  int free_nodes = 0;
+  for (int nd = 0; nd < s.M; ++nd) free_nodes += h_node_is_free(s, nd);
+  if (free_nodes < 1) return false;
+  if (s.schedule == GS_HSCHED_HORUS || s.schedule == GS_HSCHED_HORUS_PLUS) {       // schedule_horus / schedule_horus_plus (algorithm.py:204-290)
+    const bool plus = s.schedule == GS_HSCHED_HORUS_PLUS;
+    const int qd = h_queued(s);
+    int min_k = s.num_buffer < qd ? s.num_buffer : qd;
+    if (min_k < 0) min_k = 0;
+    for (int i = 0; i < min_k; ++i) {
+      int qi = 0;
+      if (plus) {                                           // the queue with the most credit (leaky bucket)
+        h_update_credits(s);
+        for (int q = 1; q < s.nq; ++q) if (s.credits[q] > s.credits[qi]) qi = q;              // np.argmax: first maximum
       }
+      s.look[i] = h_queue_pop(s, qi); s.look_q[i] = qi;
     }
+    s.la_n = min_k;
+  } else { s.look[0] = s.queue[0]; s.look_q[0] = 0; s.la_n = 1; }                   // schedule_fifo: the head, popped on success
+  return true;
+}
+// after the attempts: la_pos = index of the job that was placed (or -1), la_nres = its node count
+GS_HD void h_sched_finish(HSim &s) {
+  int placed = -1;
+  if (s.schedule == GS_HSCHED_HORUS || s.schedule == GS_HSCHED_HORUS_PLUS) {
+    int min_k = s.la_n;
+    if (s.la_pos >= 0) { placed = s.look[s.la_pos]; for (int i = s.la_pos; i + 1 < min_k; ++i) { s.look[i] = s.look[i + 1]; s.look_q[i] = s.look_q[i + 1]; } min_k -= 1; }
+    for (int i = 0; i < min_k; ++i) h_queue_insert(s, s.look_q[i], s.look[i], i);               // back to the queue they came from
+  } else if (s.la_pos >= 0) { placed = s.look[0]; (void)h_queue_pop(s, 0); }
+  if (placed >= 0) { h_start_job(s, placed, s.la_nres); s.events += 1; }
+}
+// the rest of the tick: aging, completions, time slicing, statistics row
+GS_HD void h_tick_end(HSim &s) {
     s.current_remaining = s.n - s.p;
     s.delta += 1;
     // JobsManager.step (jobs_manager.py:141-148)
@@ -696,9 +712,10 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
     }
     s.rows[s.ticks] = row;
     s.util[s.ticks] = usum / (double)(row.idle_gpus + row.busy_gpus); s.util_arr[s.ticks] = (unsigned char)uarr;
-    s.ticks += 1; budget -= 1;
+    s.ticks += 1;
     if (!(s.current_remaining + s.running_jobs > 0)) s.done = 1;
-  }
+}
+GS_HD void h_write_records(HSim &s) {
   if (s.done && s.status == 0)
     for (int j = 0; j < s.n; ++j) {
       gs_horus_job_rec r; const HJobState &st = s.js[j];
@@ -706,4 +723,145 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
       r.original = s.jobs[j].duration; r.actual = h_get_duration(s, j);
       s.recs[j] = r;
     }
+}
+
+// scalar driver: one simulation per thread
+GS_HD void h_run(HSim &s, long long max_ticks) {
+  long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+  while (!s.done && s.status == 0 && budget > 0) {
+    if (!h_tick_begin(s)) break;
+    if (h_sched_setup(s)) {
+      for (int i = 0; i < s.la_n; ++i) { int nres = 0; if (h_place(s, s.look[i], nres)) { s.la_pos = i; s.la_nres = nres; break; } }
+      h_sched_finish(s);
+    }
+    h_tick_end(s);
+    budget -= 1;
+  }
+  h_write_records(s);
+}
+
+// ======================================================================================================================
+// Warp-cooperative driver (one simulation per WARP).  Over 90 % of the samples are drawn while scoring
+// (task x node x device x tasks-on-device, for up to num_buffer candidate jobs every tick), so that loop is spread
+// over the lanes: lane 0 runs the scalar simulation (h_coop_advance) until a candidate job needs scoring, posts a
+// request, and all 32 lanes execute it.  Nothing moves while a job is scored, so what each device consumes is known
+// up front: PREP computes per device whether it fits and how many samples it draws; lane 0 turns the counts into
+// offsets (one prefix sum) and, per task k, SCORE lets every lane read ITS devices' samples at
+// base + k * total + offset -- the stream order of the sequential code -- and compute their cost.  Lane 0 then
+// reduces per node and feeds the heap exactly as h_placement does.  Only the standard-normal form of the stream is
+// indexable like this; with the raw-word form (horus+) the scalar scoring is used.
+//
+// The phases are written with H_FOR_LANE_ITEMS / H_SYNC so that the host build (tests/emu) executes the same
+// statements with the lane loop run sequentially: the index arithmetic is checked on the CPU against the oracle.
+#ifdef __CUDA_ARCH__
+#define H_FOR_LANE_ITEMS(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+#define H_SYNC() __syncwarp()
+#else
+#define H_FOR_LANE_ITEMS(i, n) for (int i = 0; i < (n); ++i)
+#define H_SYNC()
+#endif
+enum { H_REQ_DONE = 0, H_REQ_PREP = 1, H_REQ_SCORE = 2 };
+enum { H_PH_TICK = 0, H_PH_JOB = 1, H_PH_PREPPED = 2, H_PH_SCORED = 3 };
+
+// PREP: per device, does the task fit and how many samples does scoring it draw (its running tasks)
+GS_HD void h_coop_prep(HSim &s) {
+  const int t = s.jobs[s.sc_job].first_task;               // all tasks of a job are alike for these predicates
+  H_FOR_LANE_ITEMS(i, s.M * s.G) {
+    const int nd = i / s.G;
+    const bool node_ok = h_node_is_free(s, nd) && s.cpu_cap - s.nodes[nd].cpu_used - H_TASK_CPU >= 0 && s.mem_cap - s.nodes[nd].mem_used - H_TASK_MEM >= 0;
+    const HDev &dv = s.devs[i];
+    s.sc_cnt[i] = (node_ok && h_dev_can_fit(s, dv, t)) ? dv.nt : -1;          // -1: not scored
+  }
+}
+// Device.get_current_utilization with the samples at a known position of the stream
+GS_HD double h_dev_util_at(const HSim &s, const HDev &d, long long pos) {
+  double u = 0.0;
+  for (int i = 0; i < d.nt; ++i) {
+    const HTask &o = s.tasks[d.t[i]];
+    const double x = H_ADD(o.util_avg, H_MUL(o.half_spread, s.gauss[pos + i]));
+    if (x < 100.0) u = H_ADD(u, x); else u = H_ADD(u, 100.0);
+    if (100.0 < u) u = 100.0;
+  }
+  return u;
+}
+// SCORE: the cost of every scored device for task sc_k (horus.py:6-56)
+GS_HD void h_coop_score(HSim &s) {
+  const HJob &jb = s.jobs[s.sc_job];
+  const double cap_mib = (double)(s.cap_b >> 20), tm = (double)jb.mem_b / 1048576.0;
+  const long long base = s.sc_base + (long long)s.sc_k * s.sc_total;
+  H_FOR_LANE_ITEMS(i, s.M * s.G) {
+    if (s.sc_cnt[i] < 0) continue;
+    const HDev &dv = s.devs[i];
+    const double cur = (double)h_dev_mem(s, dv) / 1048576.0;
+    const double util = h_dev_util_at(s, dv, base + s.sc_off[i]);
+    double cost;
+    if (s.scheme == GS_HSCORE_HORUS) {
+      const double mem_cost = (cur + tm) / cap_mib;
+      const double util_cost = h_polyval(H_ADD(util, jb.util_avg));
+      cost = H_ADD(H_ADD(H_MUL(mem_cost, 0.5), H_MUL(util_cost, 0.5)), (double)dv.nt);
+    } else {
+      const double mem_cost = cur + tm / cap_mib;
+      cost = H_ADD(H_ADD(H_MUL(mem_cost, 0.5), util / 100), (double)dv.nt);
+    }
+    s.sc_cost[i] = cost;
+  }
+}
+// lane 0: run the simulation up to the next cooperative request (or the end of this launch)
+GS_HD int h_coop_advance(HSim &s) {
+  for (;;) {
+    if (s.phase == H_PH_TICK) {
+      if (s.done || s.status != 0 || s.budget <= 0) return H_REQ_DONE;
+      if (!h_tick_begin(s)) return H_REQ_DONE;
+      if (h_sched_setup(s)) { s.phase = H_PH_JOB; continue; }
+      h_tick_end(s); s.budget -= 1;
+      continue;
+    }
+    if (s.phase == H_PH_JOB) {
+      if (s.la_pos >= 0 || s.la_i >= s.la_n) { h_sched_finish(s); h_tick_end(s); s.budget -= 1; s.phase = H_PH_TICK; continue; }
+      const int j = s.look[s.la_i];
+      if (s.placement == GS_HPLACE_YARN || s.words) {        // nothing to score / stream not indexable: scalar placement
+        int nres = 0;
+        if (h_place(s, j, nres)) { s.la_pos = s.la_i; s.la_nres = nres; } else s.la_i += 1;
+        continue;
+      }
+      s.sc_job = j; s.sc_k = 0; s.sc_hn = 0; s.phase = H_PH_PREPPED;
+      return H_REQ_PREP;
+    }
+    if (s.phase == H_PH_PREPPED) {                           // counts -> offsets; the samples of one task span sc_total
+      int total = 0;
+      for (int i = 0; i < s.M * s.G; ++i) { s.sc_off[i] = total; if (s.sc_cnt[i] > 0) total += s.sc_cnt[i]; }
+      s.sc_total = total; s.sc_base = s.gauss_pos;
+      const long long need = (long long)total * s.jobs[s.sc_job].ntasks;
+      if (s.gauss_pos + need > s.gauss_n) { s.status = GS_ERR_CAPACITY; s.phase = H_PH_TICK; return H_REQ_DONE; }
+      s.phase = H_PH_SCORED;
+      return H_REQ_SCORE;
+    }
+    // H_PH_SCORED: per node the cheapest scored device -> heap (algorithm.py:50-66), then the next task or the trials
+    const HJob &jb = s.jobs[s.sc_job];
+    for (int nd = 0; nd < s.M; ++nd) {
+      double min_cost = 999.0; bool any = false;
+      for (int d = 0; d < s.G; ++d) { const int i = nd * s.G + d; if (s.sc_cnt[i] < 0) continue; any = true; if (s.sc_cost[i] < min_cost) min_cost = s.sc_cost[i]; }
+      if (!any) continue;                                    // node.can_fit(t, pack=True) is false
+      HCand x; x.node = nd; x.pad = 0; x.min_score = min_cost;
+      h_heap_push(s.heap, s.sc_hn, x);
+      if (s.sc_hn > jb.gpus) h_heap_pop(s.heap, s.sc_hn);
+    }
+    s.sc_k += 1;
+    if (s.sc_k < jb.ntasks) return H_REQ_SCORE;
+    s.gauss_pos = s.sc_base + (long long)s.sc_total * jb.ntasks;
+    s.draws += (long long)s.sc_total * jb.ntasks;
+    int nres = 0;
+    if (h_placement_finish(s, s.sc_job, s.sc_hn, nres)) { s.la_pos = s.la_i; s.la_nres = nres; } else s.la_i += 1;
+    s.phase = H_PH_JOB;
+  }
+}
+// host form of the cooperative driver (the kernel interleaves the same calls with __syncwarp)
+GS_HD void h_run_coop(HSim &s, long long max_ticks) {
+  s.budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
+  for (;;) {
+    const int req = h_coop_advance(s);
+    if (req == H_REQ_DONE) break;
+    if (req == H_REQ_PREP) h_coop_prep(s); else h_coop_score(s);
+  }
+  h_write_records(s);
 }

@@ -93,7 +93,8 @@ int gs_horus_stats(gs_horus_handle h, int32_t sim, gs_horus_run_stats *out);
  * array" flag (how str() prints it), and the job records in finish order. */
 int gs_horus_fetch(gs_horus_handle h, int32_t sim, gs_tick_row *rows, double *util, uint8_t *util_is_array,
                    int64_t rows_cap, gs_horus_job_rec *recs, int32_t *finish_order, int64_t *n_rows, int64_t *n_finished);
-/* Kernel mapping (no reference counterpart): simulations per warp, 1 (default, lane 0 of each warp) or 32. */
+/* Kernel mapping (no reference counterpart): simulations per warp, 1 (default: lane 0 of each warp) or 32; 0 = one
+ * simulation per warp with all 32 lanes scoring a candidate job's devices together (gs_horus_coop_kernel). */
 int gs_horus_set_lanes(gs_horus_handle h, int lanes_per_warp);
 int64_t gs_horus_launch_count(gs_horus_handle h);
 const char *gs_horus_last_error(gs_horus_handle h);

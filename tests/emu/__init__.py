@@ -33,7 +33,7 @@ def lib():
     return _lib
 
 
-def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0, words=None):
+def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0, words=None, cooperative=False):
     """gauss: standard-normal values (horus / gandiva), or words: raw MT19937 words (any schedule, needed by horus+)"""
     from gpuschedule_b200.capi import HORUS_REC_DTYPE
     from gpuschedule_b200.log_manager import ROW_DTYPE
@@ -56,5 +56,5 @@ def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0, wor
     ticks = lib().emu_run_horus(C.byref(cluster), C.byref(params), C.c_longlong(n), *[p(c) for c in cols], p(ma), p(g),
                                 C.c_longlong(0 if g is None else len(g)), p(w), C.c_longlong(0 if w is None else len(w)),
                                 p(rows), p(util), p(util_arr), C.c_longlong(rows_cap), p(recs), p(fin),
-                                C.byref(nfin), C.byref(events), C.byref(draws), C.c_longlong(max_ticks_per_call))
+                                C.byref(nfin), C.byref(events), C.byref(draws), C.c_longlong(max_ticks_per_call), C.c_int(int(cooperative)))
     return ticks, rows[:max(ticks, 0)], util[:max(ticks, 0)], util_arr[:max(ticks, 0)], recs[:n], fin[:nfin.value], events.value, draws.value

@@ -19,7 +19,7 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
                                    const double *gauss, long long gauss_n, const unsigned int *words, long long words_n,
                                    gs_tick_row *rows, double *util, unsigned char *util_arr, long long rows_cap,
                                    gs_horus_job_rec *recs, int *fin, long long *nfin, long long *events, long long *draws,
-                                   long long max_ticks_per_call) {
+                                   long long max_ticks_per_call, int cooperative) {
   const int M = c->num_switch * c->num_node_p_switch, G = c->num_gpu_p_node;
   const size_t N = n ? (size_t)n : 1;
   std::vector<HJob> jobs(N);
@@ -40,6 +40,7 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   const size_t nb = (size_t)(par->num_buffer > 0 ? par->num_buffer : 1);
   std::vector<int> queue((N + 1) * (size_t)nq), running(N), finv(N), look(nb), lookq(nb), work(N), res((size_t)M);
   std::vector<int> kall(N), kas(N), kold(N); std::vector<double> ksc(N);
+  std::vector<int> sccnt((size_t)M * G), scoff((size_t)M * G); std::vector<double> sccost((size_t)M * G);
   std::vector<double> gret, gkeep; std::vector<int> gnext;
   if (words) {                        // what gs_horus_load_words does on the host side of the library
     const size_t W = words_n ? (size_t)words_n : 1;
@@ -60,12 +61,15 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   s.nodes = nodes.data(); s.devs = devs.data(); s.pj_bits = pj.data(); s.queue = queue.data(); s.running = running.data(); s.fin = finv.data();
   s.nq = nq; s.look_q = lookq.data(); s.km_all = kall.data(); s.km_assign = kas.data(); s.km_old = kold.data(); s.km_score = ksc.data();
   if (words) { s.words = words; s.words_n = words_n; s.gv_ret = gret.data(); s.gv_keep = gkeep.data(); s.gv_next = gnext.data(); }
+  s.sc_cnt = sccnt.data(); s.sc_off = scoff.data(); s.sc_cost = sccost.data();
   s.look = look.data(); s.work = work.data(); s.res_nodes = res.data(); s.map_node = mn.data(); s.map_order = mo.data(); s.map_n = mc.data();
   s.ok = ok.data(); s.distinct = di.data(); s.heap = heap.data();
   s.gauss = gauss; s.gauss_n = gauss_n; s.gauss_pos = 0;
   s.rows = rows; s.util = util; s.util_arr = util_arr; s.recs = recs; s.rows_cap = rows_cap;
   s.current_remaining = n; s.running_jobs = 0;
-  while (!s.done && s.status == 0) h_run(s, max_ticks_per_call);        // > 0: exercises the resume-between-launches path
+  while (!s.done && s.status == 0) {                                    // > 0: exercises the resume-between-launches path
+    if (cooperative) h_run_coop(s, max_ticks_per_call); else h_run(s, max_ticks_per_call);
+  }
   for (int i = 0; i < s.nfin; ++i) fin[i] = finv[(size_t)i];
   *nfin = s.nfin; *events = s.events; *draws = s.draws;
   return s.status < 0 ? s.status : s.ticks;

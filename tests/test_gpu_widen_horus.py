@@ -219,3 +219,21 @@ def test_crossed_and_yarn_fixtures_match_reference_bytes():
     for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
         got_job, got_cluster = render_horus_outputs(table, cluster, res)
         assert got_job == job_csv and got_cluster == cluster_csv, case
+
+
+@NOT_RUN_YET
+def test_cooperative_warp_mapping_matches_oracle_and_fixtures():
+    """gs_horus_set_lanes(0): one simulation per warp, all lanes score a candidate job's devices together."""
+    import oracle
+    jobs = [_seeded_case(s) for s in range(24)]
+    results, _ = _run(jobs, lanes=0)
+    for s, ((cluster, table, params), res) in enumerate(zip(jobs, results)):
+        ref = oracle.run_horus(cluster, table, **params)
+        assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events, s
+        assert res.rows.tobytes() == ref.rows.tobytes() and res.util.tobytes() == ref.util.tobytes(), s
+        assert res.recs.tobytes() == ref.recs.tobytes() and np.array_equal(res.finish_order, ref.finish_order), s
+    loaded = [load_horus(c) for c in RAN_GREEN_IN_ROUND_1]
+    results, _ = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded], lanes=0, max_ticks=64)      # resumed every 64 ticks
+    for case, (table, cluster, params, job_csv, cluster_csv), res in zip(RAN_GREEN_IN_ROUND_1, loaded, results):
+        got_job, got_cluster = render_horus_outputs(table, cluster, res)
+        assert got_job == job_csv and got_cluster == cluster_csv, case

@@ -25,16 +25,16 @@ def _words(seed, count):
     return np.random.randint(0, 2 ** 32, size=count, dtype=np.uint32)       # the raw MT19937 output words
 
 
-def _emu(table, cluster, params, count=1 << 21, step=0, use_words=None):
+def _emu(table, cluster, params, count=1 << 21, step=0, use_words=None, cooperative=False):
     from gpuschedule_b200 import capi
     from tests_emu import run_horus
     hp = capi.make_horus_params(params["scheme"], params["schedule"], params["num_buffer"], params.get("num_queue", 1))
     if use_words is None:
         use_words = params["schedule"] == "horus+"
     if use_words:
-        out = run_horus(cluster, hp, table, None, 1 << 15, step, words=_words(params["seed"], 3 * count))
+        out = run_horus(cluster, hp, table, None, 1 << 15, step, words=_words(params["seed"], 3 * count), cooperative=cooperative)
     else:
-        out = run_horus(cluster, hp, table, _stream(params["seed"], count), 1 << 15, step)
+        out = run_horus(cluster, hp, table, _stream(params["seed"], count), 1 << 15, step, cooperative=cooperative)
     ticks, rows, util, flags, recs, order, events, draws = out
     assert ticks >= 0, ticks
     return SimpleNamespace(rows=rows, util=util, util_is_array=flags, recs=recs, finish_order=order, events=events, draws=draws, ticks=ticks)
@@ -64,13 +64,15 @@ def test_numpy_stream_contract():
         assert np.random.normal(loc=loc, scale=scale, size=1)[0] == loc + scale * g[k]
 
 
-@pytest.mark.parametrize("stream", ["values", "words"])
+@pytest.mark.parametrize("stream", ["values", "words", "values-cooperative"])
 @pytest.mark.parametrize("case", [c for c in horus_cases()])
 def test_kernel_logic_matches_reference_bytes(case, stream):
+    """values / words: the scalar driver with either stream form; values-cooperative: the warp-cooperative driver
+    (scoring by sample index, lane loop run sequentially on the host)."""
     table, cluster, params, job_csv, cluster_csv = load_horus(case)
-    if params["schedule"] == "horus+" and stream == "values":
+    if params["schedule"] == "horus+" and stream != "words":
         pytest.skip("horus+ draws integers too: it needs the raw word stream")
-    res = _emu(table, cluster, params, use_words=(stream == "words"))
+    res = _emu(table, cluster, params, use_words=(stream == "words"), cooperative=stream.endswith("cooperative"))
     got_job, got_cluster = render_horus_outputs(table, cluster, res)
     assert got_job == job_csv
     assert got_cluster == cluster_csv
@@ -118,8 +120,8 @@ def test_kernel_logic_matches_oracle_seeded(seed):
                                                              max_mem_mib=int(rng.choice([8000, 16384, 33500]))))
     params = dict(scheme=kind, schedule=kind, num_buffer=int(rng.choice([1, 3, 5])), num_queue=1, seed=1000 + seed)
     ref = oracle.run_horus(cluster, table, **params)
-    for step, use_words in ((0, False), (37, False), (0, True)):       # one call / resumed every 37 ticks / raw word stream
-        res = _emu(table, cluster, params, step=step, use_words=use_words)
+    for step, use_words, coop in ((0, False, False), (37, False, False), (0, True, False), (0, False, True), (37, False, True)):
+        res = _emu(table, cluster, params, step=step, use_words=use_words, cooperative=coop)   # scalar / resumed / words / cooperative
         assert res.ticks == ref.ticks and res.draws == ref.draws and res.events == ref.events
         assert res.rows.tobytes() == ref.rows.tobytes()
         assert res.util.tobytes() == ref.util.tobytes() and res.util_is_array.tobytes() == ref.util_is_array.tobytes()

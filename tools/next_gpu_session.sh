@@ -3,7 +3,7 @@
 #   gpurun --timeout 900 -- 'bash tools/next_gpu_session.sh'
 # 1. the whole GPU suite -- the horus+ / word-stream / batched-sweep / CLI tests of tests/test_gpu_widen_horus.py have
 #    never run on a device (XPASS = they work; then drop the NOT_RUN_YET marks)
-# 2. the utilisation-aware engine: both kernel mappings + the horus+ device check, then a launch list and one
+# 2. the utilisation-aware engine: all three kernel mappings (scalar x1 / x32 lanes, cooperative warp) + the horus+ device check, then a launch list and one
 #    full ncu capture of gs_horus_kernel (where do the ~50 dependent loads per sample go?)
 # 3. the main line again (nothing on that path changed since profiles/r01_bench_final.json)
 set -u
