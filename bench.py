@@ -568,6 +568,24 @@ def horus_mode(args):
                     "same_event_total_as_scalar_mapping": sum(int(x.events) for x in cst) == events}
     except Exception as exc:                                # noqa: BLE001
         coop = {"error": repr(exc)}
+    if isinstance(plus, dict) and "error" not in plus and "error" not in coop:
+        try:                                                # horus+ under the cooperative mapping (indexed word stream)
+            k = plus["replicas"]
+            with capi.HorusEngine(device=0, nsims=k) as eng:
+                eng.set_lanes(0)
+                for r in range(k):
+                    eng.config(r, cluster, pp)
+                    eng.load_trace(r, tables[r])
+                eng.load_words(-1, words)
+                eng.run(rows_cap=args.horus_rows)
+                same = 0
+                for r in range(k):
+                    prow, putil, pflag, precs, porder = eng.fetch(r)
+                    pref = oracle.run_horus(cluster, tables[r], scheme="horus+", schedule="horus+", num_buffer=15, num_queue=3, seed=1)
+                    same += int(prow.tobytes() == pref.rows.tobytes() and putil.tobytes() == pref.util.tobytes() and precs.tobytes() == pref.recs.tobytes())
+                coop["horus_plus"] = {"replicas": k, "identical_to_oracle": same, "kernel_ms": float(eng.stats(0).kernel_ms)}
+        except Exception as exc:                            # noqa: BLE001
+            coop["horus_plus"] = {"error": repr(exc)}
     print(json.dumps({"metric": "horus simulated events/s (replica batch)", "value": events / (ms / 1e3), "unit": UNIT,
                       "kernel_ms": ms, "replicas": R, "jobs_per_replica": n, "ticks": ticks, "samples_drawn": draws,
                       "samples_per_s": draws / (ms / 1e3), "kernel": "gs_horus_kernel (one simulation per thread)", "kernel_ms_by_lanes_per_warp": by_lanes,

@@ -47,6 +47,7 @@ struct WordStream {                 // raw MT19937 words + the per-position samp
   std::vector<uint32_t> words;
   unsigned char *dev = nullptr; size_t cap = 0; bool dirty = false;
   const unsigned int *d_words = nullptr; const double *d_ret = nullptr, *d_keep = nullptr; const int *d_next = nullptr;
+  const int *d_acc = nullptr, *d_rank = nullptr; int cls_off[5] = {0, 0, 0, 0, 0};
 };
 struct HorusSimHost {
   bool configured = false, loaded = false, prepared = false;
@@ -201,12 +202,17 @@ extern "C" int gs_horus_load_words(gs_horus_handle h, int32_t sim, const uint32_
 static int upload_words(gs_horus_handle h, WordStream &ws) {
   if (!ws.dirty) return GS_OK;
   const size_t n = ws.words.size(), N = n ? n : 1;
-  const size_t o_w = 0, o_ret = up(4 * N), o_keep = up(o_ret + 8 * N), o_next = up(o_keep + 8 * N), total = up(o_next + 4 * N);
+  const size_t o_w = 0, o_ret = up(4 * N), o_keep = up(o_ret + 8 * N), o_next = up(o_keep + 8 * N), o_acc = up(o_next + 4 * N);
+  const size_t o_rank = up(o_acc + 4 * N), total = up(o_rank + 4 * N);
   if (ws.dev && ws.cap < total) { cudaFree(ws.dev); ws.dev = nullptr; }
   if (!ws.dev) { HCU(cudaMalloc(&ws.dev, total)); ws.cap = total; }
   std::vector<double> ret(N), keep(N); std::vector<int> next(N);
+  std::vector<int> acc(N), rank(N);
   gs_horus_build_gauss_tables(ws.words.data(), (long long)n, ret.data(), keep.data(), next.data());
+  gs_horus_build_gauss_index(next.data(), (long long)n, acc.data(), rank.data(), ws.cls_off);
   if (n) {
+    HCU(cudaMemcpyAsync(ws.dev + o_acc, acc.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
+    HCU(cudaMemcpyAsync(ws.dev + o_rank, rank.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
     HCU(cudaMemcpyAsync(ws.dev + o_w, ws.words.data(), 4 * n, cudaMemcpyHostToDevice, h->stream));
     HCU(cudaMemcpyAsync(ws.dev + o_ret, ret.data(), 8 * n, cudaMemcpyHostToDevice, h->stream));
     HCU(cudaMemcpyAsync(ws.dev + o_keep, keep.data(), 8 * n, cudaMemcpyHostToDevice, h->stream));
@@ -215,6 +221,7 @@ static int upload_words(gs_horus_handle h, WordStream &ws) {
   HCU(cudaStreamSynchronize(h->stream));
   ws.d_words = (const unsigned int *)(ws.dev + o_w); ws.d_ret = (const double *)(ws.dev + o_ret);
   ws.d_keep = (const double *)(ws.dev + o_keep); ws.d_next = (const int *)(ws.dev + o_next);
+  ws.d_acc = (const int *)(ws.dev + o_acc); ws.d_rank = (const int *)(ws.dev + o_rank);
   ws.dirty = false;
   return GS_OK;
 }
@@ -280,6 +287,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   if (s.word_mode) {
     const WordStream &ws = s.word_mode == 1 ? s.ws : h->shared_ws;
     D.words = ws.d_words; D.gv_ret = ws.d_ret; D.gv_keep = ws.d_keep; D.gv_next = ws.d_next; D.words_n = (long long)ws.words.size();
+    D.gv_acc = ws.d_acc; D.gv_rank = ws.d_rank; for (int c = 0; c < 5; ++c) D.gv_cls_off[c] = ws.cls_off[c];
   }
   D.map_node = (int *)(d + o_mn); D.map_order = (int *)(d + o_mo); D.map_n = (int *)(d + o_mc); D.ok = (int *)(d + o_ok); D.distinct = (int *)(d + o_di);
   D.heap = (HCand *)(d + o_heap);

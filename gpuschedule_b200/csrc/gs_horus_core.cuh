@@ -94,6 +94,7 @@ struct HSim {
   // ... or raw MT19937 words with per-position tables of the polar-method outcome (any schedule; needed by
   // horus+, whose integer draws shift where the next normal sample starts).  See gs_horus_host.h.
   const unsigned int *words; const double *gv_ret, *gv_keep; const int *gv_next;
+  const int *gv_acc, *gv_rank; int gv_cls_off[5], pad_idx;   // accepted start positions per residue class + rank (gs_horus_host.h)
   long long words_n, words_pos, draws;
   double gauss_kept; int has_gauss, pad1;
   // ---- results
@@ -748,8 +749,8 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
 // up front: PREP computes per device whether it fits and how many samples it draws; lane 0 turns the counts into
 // offsets (one prefix sum) and, per task k, SCORE lets every lane read ITS devices' samples at
 // base + k * total + offset -- the stream order of the sequential code -- and compute their cost.  Lane 0 then
-// reduces per node and feeds the heap exactly as h_placement does.  Only the standard-normal form of the stream is
-// indexable like this; with the raw-word form (horus+) the scalar scoring is used.
+// reduces per node and feeds the heap exactly as h_placement does.  Both stream forms are indexable (h_sample_at): the
+// standard-normal values by offset, the raw words through the per-class index of accepted positions.
 //
 // The phases are written with H_FOR_LANE_ITEMS / H_SYNC so that the host build (tests/emu) executes the same
 // statements with the lane loop run sequentially: the index arithmetic is checked on the CPU against the oracle.
@@ -773,12 +774,42 @@ GS_HD void h_coop_prep(HSim &s) {
     s.sc_cnt[i] = (node_ok && h_dev_can_fit(s, dv, t)) ? dv.nt : -1;          // -1: not scored
   }
 }
-// Device.get_current_utilization with the samples at a known position of the stream
+// Sample number idx (0-based) counted from the CURRENT state of the stream, without consuming anything.
+// Values form: a plain offset.  Word form: the kept second value first (if any), then pairs along one residue class.
+GS_HD double h_sample_at(const HSim &s, long long idx) {
+  if (!s.words) return s.gauss[s.gauss_pos + idx];
+  if (s.has_gauss) { if (idx == 0) return s.gauss_kept; idx -= 1; }
+  const long long p = s.words_pos;
+  const int at = s.gv_acc[s.gv_cls_off[p & 3] + s.gv_rank[p] + (int)(idx >> 1)];
+  return (idx & 1) ? s.gv_keep[at] : s.gv_ret[at];
+}
+// are `count` more samples available from the current state?
+GS_HD bool h_samples_available(const HSim &s, long long count) {
+  if (!s.words) return s.gauss_pos + count <= s.gauss_n;
+  if (s.has_gauss) count -= 1;
+  if (count <= 0) return true;
+  const long long p = s.words_pos;
+  if (p >= s.words_n) return false;
+  const long long pairs = (count + 1) >> 1, c = p & 3;
+  return s.gv_rank[p] + pairs <= (long long)(s.gv_cls_off[c + 1] - s.gv_cls_off[c]);
+}
+// consume `count` samples (what `count` calls of h_gauss would have done to the state)
+GS_HD void h_skip_samples(HSim &s, long long count) {
+  s.draws += count;
+  if (!s.words) { s.gauss_pos += count; return; }
+  if (count <= 0) return;
+  if (s.has_gauss) { s.has_gauss = 0; count -= 1; if (count == 0) return; }
+  const long long p = s.words_pos, pairs = (count + 1) >> 1;
+  const int last = s.gv_acc[s.gv_cls_off[p & 3] + s.gv_rank[p] + (int)(pairs - 1)];
+  s.words_pos = (long long)last + 4;
+  if (count & 1) { s.has_gauss = 1; s.gauss_kept = s.gv_keep[last]; }
+}
+// Device.get_current_utilization with the samples at a known index of the stream
 GS_HD double h_dev_util_at(const HSim &s, const HDev &d, long long pos) {
   double u = 0.0;
   for (int i = 0; i < d.nt; ++i) {
     const HTask &o = s.tasks[d.t[i]];
-    const double x = H_ADD(o.util_avg, H_MUL(o.half_spread, s.gauss[pos + i]));
+    const double x = H_ADD(o.util_avg, H_MUL(o.half_spread, h_sample_at(s, pos + i)));
     if (x < 100.0) u = H_ADD(u, x); else u = H_ADD(u, 100.0);
     if (100.0 < u) u = 100.0;
   }
@@ -788,7 +819,7 @@ GS_HD double h_dev_util_at(const HSim &s, const HDev &d, long long pos) {
 GS_HD void h_coop_score(HSim &s) {
   const HJob &jb = s.jobs[s.sc_job];
   const double cap_mib = (double)(s.cap_b >> 20), tm = (double)jb.mem_b / 1048576.0;
-  const long long base = s.sc_base + (long long)s.sc_k * s.sc_total;
+  const long long base = (long long)s.sc_k * s.sc_total;        // sample index relative to the (unchanged) stream state
   H_FOR_LANE_ITEMS(i, s.M * s.G) {
     if (s.sc_cnt[i] < 0) continue;
     const HDev &dv = s.devs[i];
@@ -819,7 +850,7 @@ GS_HD int h_coop_advance(HSim &s) {
     if (s.phase == H_PH_JOB) {
       if (s.la_pos >= 0 || s.la_i >= s.la_n) { h_sched_finish(s); h_tick_end(s); s.budget -= 1; s.phase = H_PH_TICK; continue; }
       const int j = s.look[s.la_i];
-      if (s.placement == GS_HPLACE_YARN || s.words) {        // nothing to score / stream not indexable: scalar placement
+      if (s.placement == GS_HPLACE_YARN) {                   // nothing to score: the scalar placement
         int nres = 0;
         if (h_place(s, j, nres)) { s.la_pos = s.la_i; s.la_nres = nres; } else s.la_i += 1;
         continue;
@@ -830,9 +861,8 @@ GS_HD int h_coop_advance(HSim &s) {
     if (s.phase == H_PH_PREPPED) {                           // counts -> offsets; the samples of one task span sc_total
       int total = 0;
       for (int i = 0; i < s.M * s.G; ++i) { s.sc_off[i] = total; if (s.sc_cnt[i] > 0) total += s.sc_cnt[i]; }
-      s.sc_total = total; s.sc_base = s.gauss_pos;
-      const long long need = (long long)total * s.jobs[s.sc_job].ntasks;
-      if (s.gauss_pos + need > s.gauss_n) { s.status = GS_ERR_CAPACITY; s.phase = H_PH_TICK; return H_REQ_DONE; }
+      s.sc_total = total;
+      if (!h_samples_available(s, (long long)total * s.jobs[s.sc_job].ntasks)) { s.status = GS_ERR_CAPACITY; s.phase = H_PH_TICK; return H_REQ_DONE; }
       s.phase = H_PH_SCORED;
       return H_REQ_SCORE;
     }
@@ -848,8 +878,7 @@ GS_HD int h_coop_advance(HSim &s) {
     }
     s.sc_k += 1;
     if (s.sc_k < jb.ntasks) return H_REQ_SCORE;
-    s.gauss_pos = s.sc_base + (long long)s.sc_total * jb.ntasks;
-    s.draws += (long long)s.sc_total * jb.ntasks;
+    h_skip_samples(s, (long long)s.sc_total * jb.ntasks);
     int nres = 0;
     if (h_placement_finish(s, s.sc_job, s.sc_hn, nres)) { s.la_pos = s.la_i; s.la_nres = nres; } else s.la_i += 1;
     s.phase = H_PH_JOB;

@@ -28,6 +28,24 @@ static inline void gs_horus_build_gauss_tables(const uint32_t *w, long long n, d
   }
 }
 
+// Index over the same tables for the warp-cooperative scoring.  An attempt advances four words, so from any start
+// position the polar method only ever visits positions of one residue class mod 4.  acc lists, class by class
+// (cls_off[c] .. cls_off[c + 1]), the accepted start positions in increasing order; rank[p] = how many accepted
+// positions of p's class lie before p.  "The m-th pair drawn from start position p" is then acc[cls_off[p & 3] +
+// rank[p] + m]: one indexed load instead of a walk along next[].
+static inline void gs_horus_build_gauss_index(const int *next, long long n, int *acc, int *rank, int cls_off[5]) {
+  long long w = 0;
+  for (int c = 0; c < 4; ++c) {
+    cls_off[c] = (int)w;
+    int seen = 0;
+    for (long long p = c; p < n; p += 4) {
+      rank[p] = seen;
+      if (next[p] == (int)(p + 4)) { acc[w++] = (int)p; ++seen; }     // accepted exactly here (not inherited from p + 4)
+    }
+  }
+  cls_off[4] = (int)w;
+}
+
 // Task records of a freshly loaded trace (one per (job, worker)); shared by the library and by the host build of the
 // device functions in tests/emu, so that both start from the same bytes.
 template <class Job, class Task>

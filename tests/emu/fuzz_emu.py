@@ -27,7 +27,7 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     np.random.seed(params["seed"])
     need_words=int(ref.draws*3+200000+ref.ticks*50)
     if kind=="horus+" or seed%2:
-        out=run_horus(cluster,hp,table,None,1<<16,int(rng.choice([0,23])),words=np.random.randint(0,2**32,size=need_words,dtype=np.uint32),cooperative=bool(seed%3==0))
+        out=run_horus(cluster,hp,table,None,1<<16,int(rng.choice([0,23])),words=np.random.randint(0,2**32,size=need_words,dtype=np.uint32),cooperative=bool(seed%3!=1))
     else:
         out=run_horus(cluster,hp,table,np.random.standard_normal(ref.draws+10),1<<16,int(rng.choice([0,23])),cooperative=bool(seed%4<2))
     ok = out[0]==ref.ticks and out[1].tobytes()==ref.rows.tobytes() and out[2].tobytes()==ref.util.tobytes() and out[3].tobytes()==ref.util_is_array.tobytes() and out[4].tobytes()==ref.recs.tobytes() and np.array_equal(out[5],ref.finish_order) and out[7]==ref.draws

@@ -41,11 +41,13 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   std::vector<int> queue((N + 1) * (size_t)nq), running(N), finv(N), look(nb), lookq(nb), work(N), res((size_t)M);
   std::vector<int> kall(N), kas(N), kold(N); std::vector<double> ksc(N);
   std::vector<int> sccnt((size_t)M * G), scoff((size_t)M * G); std::vector<double> sccost((size_t)M * G);
-  std::vector<double> gret, gkeep; std::vector<int> gnext;
+  std::vector<double> gret, gkeep; std::vector<int> gnext, gacc, grank; int cls_off[5] = {0, 0, 0, 0, 0};
   if (words) {                        // what gs_horus_load_words does on the host side of the library
     const size_t W = words_n ? (size_t)words_n : 1;
     gret.resize(W); gkeep.resize(W); gnext.resize(W);
     gs_horus_build_gauss_tables(words, words_n, gret.data(), gkeep.data(), gnext.data());
+    gacc.resize(W); grank.resize(W);
+    gs_horus_build_gauss_index(gnext.data(), words_n, gacc.data(), grank.data(), cls_off);
   }
   std::vector<int> mn((size_t)maxg * maxg), mo((size_t)maxg * maxg), mc((size_t)maxg), ok((size_t)maxg), di((size_t)maxg);
   std::vector<HCand> heap((size_t)maxg + 2);
@@ -60,7 +62,10 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   s.jobs = jobs.data(); s.js = js.data(); s.tasks = tasks.data(); s.tro_node = tron.data(); s.tro_order = troo.data();
   s.nodes = nodes.data(); s.devs = devs.data(); s.pj_bits = pj.data(); s.queue = queue.data(); s.running = running.data(); s.fin = finv.data();
   s.nq = nq; s.look_q = lookq.data(); s.km_all = kall.data(); s.km_assign = kas.data(); s.km_old = kold.data(); s.km_score = ksc.data();
-  if (words) { s.words = words; s.words_n = words_n; s.gv_ret = gret.data(); s.gv_keep = gkeep.data(); s.gv_next = gnext.data(); }
+  if (words) {
+    s.words = words; s.words_n = words_n; s.gv_ret = gret.data(); s.gv_keep = gkeep.data(); s.gv_next = gnext.data();
+    s.gv_acc = gacc.data(); s.gv_rank = grank.data(); for (int c = 0; c < 5; ++c) s.gv_cls_off[c] = cls_off[c];
+  }
   s.sc_cnt = sccnt.data(); s.sc_off = scoff.data(); s.sc_cost = sccost.data();
   s.look = look.data(); s.work = work.data(); s.res_nodes = res.data(); s.map_node = mn.data(); s.map_order = mo.data(); s.map_n = mc.data();
   s.ok = ok.data(); s.distinct = di.data(); s.heap = heap.data();

@@ -237,3 +237,13 @@ def test_cooperative_warp_mapping_matches_oracle_and_fixtures():
     for case, (table, cluster, params, job_csv, cluster_csv), res in zip(RAN_GREEN_IN_ROUND_1, loaded, results):
         got_job, got_cluster = render_horus_outputs(table, cluster, res)
         assert got_job == job_csv and got_cluster == cluster_csv, case
+
+
+@NOT_RUN_YET
+def test_cooperative_warp_mapping_horus_plus():
+    cases = _served(plus=True)
+    loaded = [load_horus(c) for c in cases]
+    results, _ = _run([(cl, tb, pr) for tb, cl, pr, _, _ in loaded], lanes=0)
+    for case, (table, cluster, params, job_csv, cluster_csv), res in zip(cases, loaded, results):
+        got_job, got_cluster = render_horus_outputs(table, cluster, res)
+        assert got_job == job_csv and got_cluster == cluster_csv, case

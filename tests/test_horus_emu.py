@@ -64,15 +64,15 @@ def test_numpy_stream_contract():
         assert np.random.normal(loc=loc, scale=scale, size=1)[0] == loc + scale * g[k]
 
 
-@pytest.mark.parametrize("stream", ["values", "words", "values-cooperative"])
+@pytest.mark.parametrize("stream", ["values", "words", "values-cooperative", "words-cooperative"])
 @pytest.mark.parametrize("case", [c for c in horus_cases()])
 def test_kernel_logic_matches_reference_bytes(case, stream):
     """values / words: the scalar driver with either stream form; values-cooperative: the warp-cooperative driver
     (scoring by sample index, lane loop run sequentially on the host)."""
     table, cluster, params, job_csv, cluster_csv = load_horus(case)
-    if params["schedule"] == "horus+" and stream != "words":
+    if params["schedule"] == "horus+" and not stream.startswith("words"):
         pytest.skip("horus+ draws integers too: it needs the raw word stream")
-    res = _emu(table, cluster, params, use_words=(stream == "words"), cooperative=stream.endswith("cooperative"))
+    res = _emu(table, cluster, params, use_words=stream.startswith("words"), cooperative=stream.endswith("cooperative"))
     got_job, got_cluster = render_horus_outputs(table, cluster, res)
     assert got_job == job_csv
     assert got_cluster == cluster_csv
