@@ -106,6 +106,8 @@ extern "C" int gs_horus_create(int device, int nsims, gs_horus_handle *out) {
     delete h;
     return hfail(nullptr, GS_ERR_CUDA, "gs_horus_create: CUDA initialisation failed");
   }
+  size_t stack = 0;                 // the scalar kernel keeps ~1.5 KB of per-thread state on its stack frame
+  if (cudaDeviceGetLimit(&stack, cudaLimitStackSize) == cudaSuccess && stack < 4096) (void)cudaDeviceSetLimit(cudaLimitStackSize, 4096);
   *out = h;
   return GS_OK;
 }
