@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(32) gs_horus_coop_kernel(HSim *sims, int nsims
     __syncwarp();                                           // lane 0's state (shared and global) is visible to the warp
     const int r = req;
     if (r == H_REQ_DONE) break;
-    if (r == H_REQ_PREP) h_coop_prep(s); else h_coop_score(s);
+    if (r == H_REQ_PREP) h_coop_prep(s); else if (r == H_REQ_SCORE) h_coop_score(s); else h_coop_stats(s);
     __syncwarp();                                           // the lanes' counts / costs are visible to lane 0
   }
   if (lane == 0) { h_write_records(s); sims[b] = s; }

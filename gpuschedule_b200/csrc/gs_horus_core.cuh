@@ -648,8 +648,8 @@ GS_HD void h_sched_finish(HSim &s) {
   } else if (s.la_pos >= 0) { placed = s.look[0]; (void)h_queue_pop(s, 0); }
   if (placed >= 0) { h_start_job(s, placed, s.la_nres); s.events += 1; }
 }
-// the rest of the tick: aging, completions, time slicing, statistics row
-GS_HD void h_tick_end(HSim &s) {
+// the rest of the tick before the statistics row: aging, completions, time slicing
+GS_HD void h_tick_mid(HSim &s) {
     s.current_remaining = s.n - s.p;
     s.delta += 1;
     // JobsManager.step (jobs_manager.py:141-148)
@@ -686,7 +686,10 @@ GS_HD void h_tick_end(HSim &s) {
       for (int i = 0; i < s.nrun; ++i) { const int tp = h_time_processed(s, s.running[i]); if (tp > 1 && tp % 100 == 0) s.work[nt++] = s.running[i]; }
       for (int i = 0; i < nt; ++i) h_preempt(s, s.work[i]);
     }
-    // _construct_info (schedule.py:95-133)
+}
+// _construct_info (schedule.py:95-133).  from_arrays: the per-device utilisation (sc_cost) and "is a numpy array" flag
+// (sc_off) were computed by the lanes (h_coop_stats); otherwise they are sampled here, device by device.
+GS_HD void h_stats_row(HSim &s, bool from_arrays) {
     gs_tick_row row;
     row.now = s.delta; row.idle_nodes = 0; row.busy_nodes = 0; row.busy_gpus = 0; row.idle_gpus = 0;
     row.pend_sum = 0; row.pend_max = 0; row.pend_med_lo = 0; row.pend_med_hi = 0; row.reserved = 0;
@@ -698,8 +701,9 @@ GS_HD void h_tick_end(HSim &s) {
         const HDev &dv = h_dev(s, nd, d);
         if (dv.nt == 0) { row.idle_gpus += 1; continue; }
         row.busy_gpus += 1;
-        int a = 0; const double u = h_dev_util(s, dv, &a);
-        usum = H_ADD(usum, u); uarr |= a;
+        int a = 0; double u;
+        if (from_arrays) { u = s.sc_cost[nd * s.G + d]; a = s.sc_off[nd * s.G + d]; } else u = h_dev_util(s, dv, &a);
+        usum = H_ADD(usum, u); uarr |= a;                    // summed in device order: the order is part of the result
         msum += h_dev_mem(s, dv);
       }
     }
@@ -716,6 +720,7 @@ GS_HD void h_tick_end(HSim &s) {
     s.ticks += 1;
     if (!(s.current_remaining + s.running_jobs > 0)) s.done = 1;
 }
+GS_HD void h_tick_end(HSim &s) { h_tick_mid(s); h_stats_row(s, false); }
 GS_HD void h_write_records(HSim &s) {
   if (s.done && s.status == 0)
     for (int j = 0; j < s.n; ++j) {
@@ -761,8 +766,8 @@ GS_HD void h_run(HSim &s, long long max_ticks) {
 #define H_FOR_LANE_ITEMS(i, n) for (int i = 0; i < (n); ++i)
 #define H_SYNC()
 #endif
-enum { H_REQ_DONE = 0, H_REQ_PREP = 1, H_REQ_SCORE = 2 };
-enum { H_PH_TICK = 0, H_PH_JOB = 1, H_PH_PREPPED = 2, H_PH_SCORED = 3 };
+enum { H_REQ_DONE = 0, H_REQ_PREP = 1, H_REQ_SCORE = 2, H_REQ_STATS = 3 };
+enum { H_PH_TICK = 0, H_PH_JOB = 1, H_PH_PREPPED = 2, H_PH_SCORED = 3, H_PH_STATS = 4 };
 
 // PREP: per device, does the task fit and how many samples does scoring it draw (its running tasks)
 GS_HD void h_coop_prep(HSim &s) {
@@ -837,6 +842,33 @@ GS_HD void h_coop_score(HSim &s) {
     s.sc_cost[i] = cost;
   }
 }
+// STATS: Device.get_current_utilization of every busy device for the statistics row (offsets in sc_off, from lane 0);
+// leaves the value in sc_cost and the "is a numpy array" flag in sc_off
+GS_HD void h_coop_stats(HSim &s) {
+  H_FOR_LANE_ITEMS(i, s.M * s.G) {
+    const HDev &d = s.devs[i];
+    if (d.nt == 0) continue;
+    const long long pos = s.sc_off[i];
+    double u = 0.0; int arr = 0;
+    for (int t = 0; t < d.nt; ++t) {
+      const HTask &o = s.tasks[d.t[t]];
+      const double x = H_ADD(o.util_avg, H_MUL(o.half_spread, h_sample_at(s, pos + t)));
+      if (x < 100.0) { u = H_ADD(u, x); arr = 1; } else { u = H_ADD(u, 100.0); }
+      if (100.0 < u) { u = 100.0; arr = 0; }
+    }
+    s.sc_cost[i] = u; s.sc_off[i] = arr;
+  }
+}
+// lane 0, end of a tick in the cooperative driver: everything before the row, then the sample offsets of the row
+GS_HD int h_coop_tick_end(HSim &s) {
+  h_tick_mid(s);
+  int total = 0;
+  for (int i = 0; i < s.M * s.G; ++i) { s.sc_off[i] = total; total += s.devs[i].nt; }
+  s.sc_total = total;
+  if (!h_samples_available(s, total)) { s.status = GS_ERR_CAPACITY; s.phase = H_PH_TICK; return H_REQ_DONE; }
+  s.phase = H_PH_STATS;
+  return H_REQ_STATS;
+}
 // lane 0: run the simulation up to the next cooperative request (or the end of this launch)
 GS_HD int h_coop_advance(HSim &s) {
   for (;;) {
@@ -844,11 +876,16 @@ GS_HD int h_coop_advance(HSim &s) {
       if (s.done || s.status != 0 || s.budget <= 0) return H_REQ_DONE;
       if (!h_tick_begin(s)) return H_REQ_DONE;
       if (h_sched_setup(s)) { s.phase = H_PH_JOB; continue; }
-      h_tick_end(s); s.budget -= 1;
+      return h_coop_tick_end(s);
+    }
+    if (s.phase == H_PH_STATS) {                             // the lanes have sampled the busy devices
+      h_stats_row(s, true);
+      h_skip_samples(s, s.sc_total);
+      s.budget -= 1; s.phase = H_PH_TICK;
       continue;
     }
     if (s.phase == H_PH_JOB) {
-      if (s.la_pos >= 0 || s.la_i >= s.la_n) { h_sched_finish(s); h_tick_end(s); s.budget -= 1; s.phase = H_PH_TICK; continue; }
+      if (s.la_pos >= 0 || s.la_i >= s.la_n) { h_sched_finish(s); return h_coop_tick_end(s); }
       const int j = s.look[s.la_i];
       if (s.placement == GS_HPLACE_YARN) {                   // nothing to score: the scalar placement
         int nres = 0;
@@ -890,7 +927,7 @@ GS_HD void h_run_coop(HSim &s, long long max_ticks) {
   for (;;) {
     const int req = h_coop_advance(s);
     if (req == H_REQ_DONE) break;
-    if (req == H_REQ_PREP) h_coop_prep(s); else h_coop_score(s);
+    if (req == H_REQ_PREP) h_coop_prep(s); else if (req == H_REQ_SCORE) h_coop_score(s); else h_coop_stats(s);
   }
   h_write_records(s);
 }
