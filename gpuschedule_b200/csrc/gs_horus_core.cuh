@@ -133,6 +133,36 @@ GS_HD long long h_below(HSim &s, long long n) {
     if (v <= mx) return (long long)v;
   }
 }
+// Sample number idx (0-based) counted from the CURRENT state of the stream, without consuming anything.
+// Values form: a plain offset.  Word form: the kept second value first (if any), then pairs along one residue class.
+GS_HD double h_sample_at(const HSim &s, long long idx) {
+  if (!s.words) return s.gauss[s.gauss_pos + idx];
+  if (s.has_gauss) { if (idx == 0) return s.gauss_kept; idx -= 1; }
+  const long long p = s.words_pos;
+  const int at = s.gv_acc[s.gv_cls_off[p & 3] + s.gv_rank[p] + (int)(idx >> 1)];
+  return (idx & 1) ? s.gv_keep[at] : s.gv_ret[at];
+}
+// are `count` more samples available from the current state?
+GS_HD bool h_samples_available(const HSim &s, long long count) {
+  if (!s.words) return s.gauss_pos + count <= s.gauss_n;
+  if (s.has_gauss) count -= 1;
+  if (count <= 0) return true;
+  const long long p = s.words_pos;
+  if (p >= s.words_n) return false;
+  const long long pairs = (count + 1) >> 1, c = p & 3;
+  return s.gv_rank[p] + pairs <= (long long)(s.gv_cls_off[c + 1] - s.gv_cls_off[c]);
+}
+// consume `count` samples (what `count` calls of h_gauss would have done to the state)
+GS_HD void h_skip_samples(HSim &s, long long count) {
+  s.draws += count;
+  if (!s.words) { s.gauss_pos += count; return; }
+  if (count <= 0) return;
+  if (s.has_gauss) { s.has_gauss = 0; count -= 1; if (count == 0) return; }
+  const long long p = s.words_pos, pairs = (count + 1) >> 1;
+  const int last = s.gv_acc[s.gv_cls_off[p & 3] + s.gv_rank[p] + (int)(pairs - 1)];
+  s.words_pos = (long long)last + 4;
+  if (count & 1) { s.has_gauss = 1; s.gauss_kept = s.gv_keep[last]; }
+}
 GS_HD double h_normal(HSim &s, double loc, double scale) { return H_ADD(loc, H_MUL(scale, h_gauss(s))); }
 GS_HD HDev &h_dev(HSim &s, int nd, int d) { return s.devs[(long long)nd * s.G + d]; }
 GS_HD long long h_task_mem(const HSim &s, int t) { return s.jobs[s.tasks[t].job].mem_b; }
@@ -164,10 +194,9 @@ GS_HD bool h_dev_add_task(HSim &s, HDev &d, int t, bool pack) {
   if (!pack && d.nt > 0) return false;
   HTask &tk = s.tasks[t];
   if (d.nt >= 2) {
-    for (int i = 0; i < d.nt; ++i) {      // interference samples are drawn; the slowed duration is only logged (:35-37)
-      const HTask &o = s.tasks[d.t[i]];
-      (void)h_normal(s, o.util_avg, o.quarter_spread);
-    }
+    // one interference sample per resident task is drawn, but the slowed duration they feed is only logged
+    // (device.py:28-37): the values are never used, so the stream is simply advanced
+    if (h_samples_available(s, d.nt)) h_skip_samples(s, d.nt); else s.status = GS_ERR_CAPACITY;
     tk.interfered = 1;
   } else { tk.interfered = 0; tk.duration = tk.original; }
   for (int i = 0; i < d.nt; ++i) if (d.t[i] == t) return true;                   // key already present: position kept
@@ -778,36 +807,6 @@ GS_HD void h_coop_prep(HSim &s) {
     const HDev &dv = s.devs[i];
     s.sc_cnt[i] = (node_ok && h_dev_can_fit(s, dv, t)) ? dv.nt : -1;          // -1: not scored
   }
-}
-// Sample number idx (0-based) counted from the CURRENT state of the stream, without consuming anything.
-// Values form: a plain offset.  Word form: the kept second value first (if any), then pairs along one residue class.
-GS_HD double h_sample_at(const HSim &s, long long idx) {
-  if (!s.words) return s.gauss[s.gauss_pos + idx];
-  if (s.has_gauss) { if (idx == 0) return s.gauss_kept; idx -= 1; }
-  const long long p = s.words_pos;
-  const int at = s.gv_acc[s.gv_cls_off[p & 3] + s.gv_rank[p] + (int)(idx >> 1)];
-  return (idx & 1) ? s.gv_keep[at] : s.gv_ret[at];
-}
-// are `count` more samples available from the current state?
-GS_HD bool h_samples_available(const HSim &s, long long count) {
-  if (!s.words) return s.gauss_pos + count <= s.gauss_n;
-  if (s.has_gauss) count -= 1;
-  if (count <= 0) return true;
-  const long long p = s.words_pos;
-  if (p >= s.words_n) return false;
-  const long long pairs = (count + 1) >> 1, c = p & 3;
-  return s.gv_rank[p] + pairs <= (long long)(s.gv_cls_off[c + 1] - s.gv_cls_off[c]);
-}
-// consume `count` samples (what `count` calls of h_gauss would have done to the state)
-GS_HD void h_skip_samples(HSim &s, long long count) {
-  s.draws += count;
-  if (!s.words) { s.gauss_pos += count; return; }
-  if (count <= 0) return;
-  if (s.has_gauss) { s.has_gauss = 0; count -= 1; if (count == 0) return; }
-  const long long p = s.words_pos, pairs = (count + 1) >> 1;
-  const int last = s.gv_acc[s.gv_cls_off[p & 3] + s.gv_rank[p] + (int)(pairs - 1)];
-  s.words_pos = (long long)last + 4;
-  if (count & 1) { s.has_gauss = 1; s.gauss_kept = s.gv_keep[last]; }
 }
 // Device.get_current_utilization with the samples at a known index of the stream
 GS_HD double h_dev_util_at(const HSim &s, const HDev &d, long long pos) {
