@@ -252,6 +252,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
   const size_t o_sccnt = take(4 * (size_t)M * G), o_scoff = take(4 * (size_t)M * G), o_sccost = take(8 * (size_t)M * G);
   const size_t o_mn = take(4 * (size_t)maxg * maxg), o_mo = take(4 * (size_t)maxg * maxg), o_mc = take(4 * (size_t)maxg);
   const size_t o_ok = take(4 * (size_t)maxg), o_di = take(4 * (size_t)maxg), o_heap = take(sizeof(HCand) * ((size_t)maxg + 2));
+  const size_t o_mskip = take(8 * (size_t)maxg);
   const size_t o_rows = take(sizeof(gs_tick_row) * (size_t)rows_cap), o_util = take(8 * (size_t)rows_cap), o_ua = take((size_t)rows_cap);
   const size_t o_recs = take(sizeof(gs_horus_job_rec) * N);
   const size_t total = off;
@@ -292,7 +293,7 @@ static int prepare(gs_horus_handle h, HorusSimHost &s, long long rows_cap) {
     D.gv_acc = ws.d_acc; D.gv_rank = ws.d_rank; for (int c = 0; c < 5; ++c) D.gv_cls_off[c] = ws.cls_off[c];
   }
   D.map_node = (int *)(d + o_mn); D.map_order = (int *)(d + o_mo); D.map_n = (int *)(d + o_mc); D.ok = (int *)(d + o_ok); D.distinct = (int *)(d + o_di);
-  D.heap = (HCand *)(d + o_heap);
+  D.heap = (HCand *)(d + o_heap); D.map_skip = (long long *)(d + o_mskip);
   D.gauss = s.use_shared ? h->d_shared : s.d_stream;
   D.gauss_n = (long long)(s.use_shared ? h->shared.size() : s.stream.size()); D.gauss_pos = 0;
   D.rows = (gs_tick_row *)(d + o_rows); D.util = (double *)(d + o_util); D.util_arr = d + o_ua; D.recs = (gs_horus_job_rec *)(d + o_recs);

@@ -86,6 +86,7 @@ struct HSim {
   int nq, nrun, nfin, pad0;
   // ---- scratch
   int *look, *look_q, *work, *res_nodes, *map_node, *map_order, *map_n, *ok, *distinct;
+  long long *map_skip;                  // samples a candidate's trial consumed
   int *km_all, *km_assign, *km_old;     // horus+: jobs being re-clustered, their assignment, the previous one
   double *km_score;
   HCand *heap;
@@ -217,8 +218,13 @@ GS_HD bool h_node_can_fit(const HSim &s, int nd, int t, bool pack) {
   return false;
 }
 // Node.try_reserve_and_placed_task (node.py:190-211); a partial placement keeps what it took
+GS_HD bool h_node_reserve_fitting(HSim &s, int nd, int t, bool pack);
 GS_HD bool h_node_reserve_task(HSim &s, int nd, int t, bool pack) {
   if (!h_node_can_fit(s, nd, t, pack)) return false;
+  return h_node_reserve_fitting(s, nd, t, pack);
+}
+// the part after Node.can_fit said yes
+GS_HD bool h_node_reserve_fitting(HSim &s, int nd, int t, bool pack) {
   s.nodes[nd].cpu_used += H_TASK_CPU; s.nodes[nd].mem_used += H_TASK_MEM;
   int need = s.jobs[s.tasks[t].job].gpc;
   for (int d = 0; d < s.G; ++d) {
@@ -319,13 +325,38 @@ GS_HD bool h_placement_finish(HSim &s, int j, int hn, int &n_res) {
     heap[k + 1] = x;
   }
   const int C = hn;
+  // Two shortcuts that leave every outcome as it is.  (a) The tasks of a job are alike, and a Node.can_fit refusal
+  // changes nothing: once a node refuses one task it refuses the rest, so the task loop stops there.  (b) A node
+  // sits in the candidate list once per task; with one device per task (no partial placements) a trial is undone
+  // completely (but for the placed_jobs marks, which are re-applied), so trying the same node again gives the same
+  // plan and advances the stream by the same number of (unused) interference samples -- the plan is copied and the
+  // stream skipped instead.
+  const bool replay = jb.gpc == 1;
   for (int i = 0; i < C; ++i) {
     int *mn = s.map_node + (long long)i * T, *mo = s.map_order + (long long)i * T;
     int mapped = 0;
-    for (int k = 0; k < T; ++k) mn[k] = -1;
     const int cand = heap[i].node;
-    for (int k = 0; k < T; ++k)
-      if (h_node_reserve_task(s, cand, t0 + k, true)) { h_node_place_job(s, cand, j); mn[k] = cand; mo[mapped++] = k; }
+    if (replay) {
+      int same = -1;
+      for (int e = 0; e < i; ++e) if (heap[e].node == cand) { same = e; break; }
+      if (same >= 0) {
+        const int *pn = s.map_node + (long long)same * T, *po = s.map_order + (long long)same * T;
+        for (int k = 0; k < T; ++k) { mn[k] = pn[k]; mo[k] = po[k]; }
+        s.map_n[i] = s.map_n[same]; s.ok[i] = s.ok[same]; s.distinct[i] = s.distinct[same]; s.map_skip[i] = s.map_skip[same];
+        if (h_samples_available(s, s.map_skip[i])) h_skip_samples(s, s.map_skip[i]); else { s.status = GS_ERR_CAPACITY; return false; }
+        // what a trial leaves behind even after its undo: placed_jobs[job] on every node it used except the first
+        // (algorithm.py:127-137) -- another candidate's undo may have popped one of them in between
+        for (int q = 0; q < s.map_n[i]; ++q) h_node_place_job(s, mn[mo[q]], j);
+        if (s.map_n[i] > 0) h_node_pop_job(s, mn[mo[0]], j);
+        continue;
+      }
+    }
+    const long long draws_before = s.draws;
+    for (int k = 0; k < T; ++k) mn[k] = -1;
+    for (int k = 0; k < T; ++k) {
+      if (!h_node_can_fit(s, cand, t0 + k, true)) break;                       // (a)
+      if (h_node_reserve_fitting(s, cand, t0 + k, true)) { h_node_place_job(s, cand, j); mn[k] = cand; mo[mapped++] = k; }
+    }
     const int home = cand / s.P;
     bool stop = false;
     for (int dist = 0; dist < s.S && !stop; ++dist)      // get_racks_by_dist: stable sort of the racks by |rack - home|
@@ -338,7 +369,8 @@ GS_HD bool h_placement_finish(HSim &s, int j, int hn, int &n_res) {
           if (mapped >= T) break;
           for (int k = 0; k < T; ++k) {
             if (mn[k] >= 0) continue;
-            if (h_node_reserve_task(s, nd, t0 + k, true)) { h_node_place_job(s, nd, j); mn[k] = nd; mo[mapped++] = k; }
+            if (!h_node_can_fit(s, nd, t0 + k, true)) break;                   // (a)
+            if (h_node_reserve_fitting(s, nd, t0 + k, true)) { h_node_place_job(s, nd, j); mn[k] = nd; mo[mapped++] = k; }
             if (mapped >= T) break;
           }
         }
@@ -351,7 +383,7 @@ GS_HD bool h_placement_finish(HSim &s, int j, int hn, int &n_res) {
         h_node_release(s, nd, t0 + k, false);
       }
     }
-    s.map_n[i] = mapped; s.ok[i] = mapped >= T;
+    s.map_n[i] = mapped; s.ok[i] = mapped >= T; s.map_skip[i] = s.draws - draws_before;
     int dn = 0;
     for (int q = 0; q < mapped; ++q) { bool seen = false; for (int p2 = 0; p2 < q; ++p2) seen |= (mn[mo[p2]] == mn[mo[q]]); dn += !seen; }
     s.distinct[i] = dn;

@@ -50,7 +50,7 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
     gs_horus_build_gauss_index(gnext.data(), words_n, gacc.data(), grank.data(), cls_off);
   }
   std::vector<int> mn((size_t)maxg * maxg), mo((size_t)maxg * maxg), mc((size_t)maxg), ok((size_t)maxg), di((size_t)maxg);
-  std::vector<HCand> heap((size_t)maxg + 2);
+  std::vector<HCand> heap((size_t)maxg + 2); std::vector<long long> mskip((size_t)maxg);
   memset(js.data(), 0, sizeof(HJobState) * N); memset(nodes.data(), 0, sizeof(HNode) * (size_t)M); memset(devs.data(), 0, sizeof(HDev) * (size_t)M * G);
   memset(tasks.data(), 0, sizeof(HTask) * NT);
   gs_horus_init_tasks(jobs.data(), n, (long long)c->gpu_mem_cap_mib << 20, tasks.data());
@@ -68,7 +68,7 @@ extern "C" long long emu_run_horus(const gs_cluster *c, const gs_horus_params *p
   }
   s.sc_cnt = sccnt.data(); s.sc_off = scoff.data(); s.sc_cost = sccost.data();
   s.look = look.data(); s.work = work.data(); s.res_nodes = res.data(); s.map_node = mn.data(); s.map_order = mo.data(); s.map_n = mc.data();
-  s.ok = ok.data(); s.distinct = di.data(); s.heap = heap.data();
+  s.ok = ok.data(); s.distinct = di.data(); s.heap = heap.data(); s.map_skip = mskip.data();
   s.gauss = gauss; s.gauss_n = gauss_n; s.gauss_pos = 0;
   s.rows = rows; s.util = util; s.util_arr = util_arr; s.recs = recs; s.rows_cap = rows_cap;
   s.current_remaining = n; s.running_jobs = 0;
