@@ -20,17 +20,12 @@ def do_once(scheme, schedule, num_queue, num_buffer, trace_file="data/month.csv"
     log_path = os.path.join(log_sub_dir, f"{scheme}_{schedule}")
     if schedule == "horus+":
         log_path = os.path.join(log_path, "k" + str(num_queue))
-    cmd = [sys.executable, os.path.join(HERE, "run_sim.py"),
-           "--num_node_p_switch", str(num_nodes_p_switch),
-           "--num_switch", str(num_switch),
-           "--scheme", scheme,
-           "--trace_file", trace_file,
-           "--num_queue", str(num_queue),
-           "--num_buffer", str(num_buffer),
-           "--schedule", schedule,
-           "--enable_network_costs", "False",
-           "--enable_migration", str(migrate),
-           "--log_path", log_path]
+    options = dict(num_node_p_switch=num_nodes_p_switch, num_switch=num_switch, scheme=scheme, trace_file=trace_file,
+                   num_queue=num_queue, num_buffer=num_buffer, schedule=schedule, enable_network_costs=False,
+                   enable_migration=migrate, log_path=log_path)          # the argument list of execute.py:19-33
+    cmd = [sys.executable, os.path.join(HERE, "run_sim.py")]
+    for name, value in options.items():
+        cmd += ["--" + name, str(value)]
     p = Popen(cmd)
     print("process pid %d: " % p.pid)
     if wait:
