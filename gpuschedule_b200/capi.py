@@ -122,6 +122,32 @@ def _ptr(a, ctype):
     return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
 
 
+def declare_horus_prototypes(lib):
+    """ctypes prototypes of include/gsched_horus.h on `lib` (libgsched.so; tests/emu also builds the library's host side
+    against a stand-in CUDA runtime and declares the same prototypes on it)"""
+    i32p, i64p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    u8p = C.POINTER(C.c_uint8)
+    lib.gs_horus_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.gs_horus_destroy.argtypes = [C.c_void_p]
+    lib.gs_horus_config.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsCluster), C.POINTER(GsHorusParams)]
+    lib.gs_horus_load_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int64, i32p, i32p, i32p, f64p, i64p, f64p, f64p, f64p]
+    lib.gs_horus_load_words.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_int64]
+    lib.gs_horus_load_stream.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
+    lib.gs_horus_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.gs_horus_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsHorusRunStats)]
+    lib.gs_horus_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, f64p, u8p, C.c_int64, C.c_void_p, i32p, i64p, i64p]
+    lib.gs_horus_set_lanes.argtypes = [C.c_void_p, C.c_int]
+    lib.gs_horus_set_lanes.restype = C.c_int
+    lib.gs_horus_launch_count.argtypes = [C.c_void_p]
+    lib.gs_horus_launch_count.restype = C.c_int64
+    lib.gs_horus_last_error.argtypes = [C.c_void_p]
+    lib.gs_horus_last_error.restype = C.c_char_p
+    for name in ("gs_horus_create", "gs_horus_destroy", "gs_horus_config", "gs_horus_load_trace", "gs_horus_load_stream", "gs_horus_load_words",
+                 "gs_horus_run", "gs_horus_stats", "gs_horus_fetch"):
+        getattr(lib, name).restype = C.c_int
+    return lib
+
+
 def load_library(path=None):
     """Load libgsched.so and declare its prototypes; raises if it is not built."""
     global _lib
@@ -171,26 +197,7 @@ def load_library(path=None):
         getattr(lib, name).restype = C.c_int
     if lib.gs_abi_version() != 1:
         raise GsError("libgsched.so ABI version mismatch")
-    # ---- include/gsched_horus.h
-    u8p = C.POINTER(C.c_uint8)
-    lib.gs_horus_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    lib.gs_horus_destroy.argtypes = [C.c_void_p]
-    lib.gs_horus_config.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsCluster), C.POINTER(GsHorusParams)]
-    lib.gs_horus_load_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int64, i32p, i32p, i32p, f64p, i64p, f64p, f64p, f64p]
-    lib.gs_horus_load_words.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint32), C.c_int64]
-    lib.gs_horus_load_stream.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
-    lib.gs_horus_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
-    lib.gs_horus_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(GsHorusRunStats)]
-    lib.gs_horus_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, f64p, u8p, C.c_int64, C.c_void_p, i32p, i64p, i64p]
-    lib.gs_horus_set_lanes.argtypes = [C.c_void_p, C.c_int]
-    lib.gs_horus_set_lanes.restype = C.c_int
-    lib.gs_horus_launch_count.argtypes = [C.c_void_p]
-    lib.gs_horus_launch_count.restype = C.c_int64
-    lib.gs_horus_last_error.argtypes = [C.c_void_p]
-    lib.gs_horus_last_error.restype = C.c_char_p
-    for name in ("gs_horus_create", "gs_horus_destroy", "gs_horus_config", "gs_horus_load_trace", "gs_horus_load_stream", "gs_horus_load_words",
-                 "gs_horus_run", "gs_horus_stats", "gs_horus_fetch"):
-        getattr(lib, name).restype = C.c_int
+    declare_horus_prototypes(lib)
     _lib = lib
     return lib
 
@@ -231,8 +238,8 @@ def make_horus_params(scheme="horus", schedule="horus", num_buffer=5, num_queue=
 class HorusEngine:
     """`nsims` independent horus / gandiva simulations on one CUDA device (include/gsched_horus.h)."""
 
-    def __init__(self, device=0, nsims=1):
-        self.lib = load_library()
+    def __init__(self, device=0, nsims=1, lib=None):
+        self.lib = lib if lib is not None else load_library()
         self.h = C.c_void_p()
         self.nsims = int(nsims)
         self._n = [0] * self.nsims

@@ -10,6 +10,7 @@
 #include "gs_horus_core.cuh"
 #include "gs_horus_host.h"
 
+#ifdef __CUDACC__
 // lanes = simulations per warp: 32 (every lane drives one) or 1 (lane 0 only: no divergence inside the warp,
 // more warps in flight for the same number of replicas).
 __global__ void __launch_bounds__(32) gs_horus_kernel(HSim *sims, int nsims, long long max_ticks, int lanes) {
@@ -41,6 +42,8 @@ __global__ void __launch_bounds__(32) gs_horus_coop_kernel(HSim *sims, int nsims
   }
   if (lane == 0) { h_write_records(s); sims[b] = s; }
 }
+
+#endif  // __CUDACC__
 
 namespace {
 struct WordStream {                 // raw MT19937 words + the per-position sample tables (gs_horus_host.h)
@@ -333,9 +336,17 @@ extern "C" int gs_horus_run(gs_horus_handle h, int64_t max_ticks, int64_t rows_c
   }
   HCU(cudaMemcpyAsync(h->d_sims, host.data(), sizeof(HSim) * (size_t)nsims, cudaMemcpyHostToDevice, h->stream));
   HCU(cudaEventRecord(h->ev0, h->stream));
+#ifdef __CUDACC__
   if (h->lanes == 32) gs_horus_kernel<<<(nsims + 31) / 32, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 32);
   else if (h->lanes == 1) gs_horus_kernel<<<nsims, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks, 1);
   else gs_horus_coop_kernel<<<nsims, 32, 0, h->stream>>>(h->d_sims, nsims, (long long)max_ticks);
+#else   // host build for tests/emu (fake_cuda/cuda_runtime.h): what the kernels do, one simulation after the other
+  for (int i = 0; i < nsims; ++i) {
+    HSim &sm = h->d_sims[i];
+    if (sm.n < 0 || sm.done || sm.status != 0) continue;
+    if (h->lanes == 0) h_run_coop(sm, (long long)max_ticks); else h_run(sm, (long long)max_ticks);
+  }
+#endif
   h->launches += 1;
   HCU(cudaGetLastError());
   HCU(cudaEventRecord(h->ev1, h->stream));

@@ -58,3 +58,33 @@ def run_horus(cluster, params, table, gauss, rows_cap, max_ticks_per_call=0, wor
                                 p(rows), p(util), p(util_arr), C.c_longlong(rows_cap), p(recs), p(fin),
                                 C.byref(nfin), C.byref(events), C.byref(draws), C.c_longlong(max_ticks_per_call), C.c_int(int(cooperative)))
     return ticks, rows[:max(ticks, 0)], util[:max(ticks, 0)], util_arr[:max(ticks, 0)], recs[:n], fin[:nfin.value], events.value, draws.value
+
+
+_ABI_OUT = os.path.join(_HERE, "_build", "libhorus_abi_emu.so")
+_abi_lib = None
+
+
+def build_abi(force=False):
+    """gs_horus.cu itself -- the library's host side, every extern "C" entry point -- compiled with g++ against
+    fake_cuda/cuda_runtime.h (device memory = host memory, kernels = the source's own host loop)."""
+    src = os.path.join(_REPO, "gpuschedule_b200", "csrc", "gs_horus.cu")
+    deps = [src, os.path.join(_HERE, "fake_cuda", "cuda_runtime.h"),
+            os.path.join(_REPO, "gpuschedule_b200", "csrc", "gs_horus_core.cuh"),
+            os.path.join(_REPO, "gpuschedule_b200", "csrc", "gs_horus_host.h"),
+            os.path.join(_REPO, "include", "gsched.h"), os.path.join(_REPO, "include", "gsched_horus.h")]
+    if not force and os.path.exists(_ABI_OUT) and os.path.getmtime(_ABI_OUT) >= max(os.path.getmtime(d) for d in deps):
+        return _ABI_OUT
+    os.makedirs(os.path.dirname(_ABI_OUT), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-x", "c++",
+                    "-I", os.path.join(_HERE, "fake_cuda"), "-I", os.path.join(_REPO, "include"),
+                    "-I", os.path.join(_REPO, "gpuschedule_b200", "csrc"), "-o", _ABI_OUT, src], check=True)
+    return _ABI_OUT
+
+
+def abi_lib():
+    """the host build of the horus C ABI with the package's own ctypes prototypes on it"""
+    global _abi_lib
+    if _abi_lib is None:
+        from gpuschedule_b200 import capi
+        _abi_lib = capi.declare_horus_prototypes(C.CDLL(build_abi()))
+    return _abi_lib

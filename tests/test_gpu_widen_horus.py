@@ -15,8 +15,9 @@ import pytest
 from conftest import horus_cases, load_horus, render_horus_outputs
 
 pytestmark = pytest.mark.gpu
-NOT_RUN_YET = pytest.mark.xfail(strict=False, reason="device build of the horus+ functions has not run on a GPU yet "
-                                "(logic verified through tests/emu); a pass shows up as XPASS")
+NOT_RUN_YET = pytest.mark.xfail(strict=False, reason="this part of the device build has not run on a GPU yet (the same functions and "
+                                "the library's host side pass on the CPU: tests/test_horus_emu.py, tests/test_horus_abi_emu.py); "
+                                "a pass shows up as XPASS")
 
 
 def _stream(seed, count=1 << 21):
