@@ -29,11 +29,13 @@ def engine_cls():
     return functools.partial(capi.HorusEngine, lib=mod.abi_lib())
 
 
+@functools.lru_cache(maxsize=4)
 def _stream(seed, count=1 << 21):
     np.random.seed(seed)
     return np.random.standard_normal(count)
 
 
+@functools.lru_cache(maxsize=4)
 def _words(seed, count=6 << 20):
     np.random.seed(seed)
     return np.random.randint(0, 2 ** 32, size=count, dtype=np.uint32)
