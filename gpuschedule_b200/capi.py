@@ -16,7 +16,8 @@ SCHEDULES = {"fifo": 0, "sjf": 1, "dlas": 2, "dlas-gpu": 3, "gittins": 4}
 SCHEMES = {"yarn": 0, "count": 1}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("GSCHED_LIB", os.path.join(_HERE, "libgsched.so"))   # override: build experiments only
+LIB_PATH = os.path.join(_HERE, "libgsched.so")     # the in-tree nvcc build; there is no override
+CUDA_BUILD_TAG = b"cuda:sm_100a"
 
 
 class GsCluster(C.Structure):
@@ -142,18 +143,19 @@ def declare_horus_prototypes(lib):
     lib.gs_horus_launch_count.restype = C.c_int64
     lib.gs_horus_last_error.argtypes = [C.c_void_p]
     lib.gs_horus_last_error.restype = C.c_char_p
+    lib.gs_horus_build_tag.restype = C.c_char_p
     for name in ("gs_horus_create", "gs_horus_destroy", "gs_horus_config", "gs_horus_load_trace", "gs_horus_load_stream", "gs_horus_load_words",
                  "gs_horus_run", "gs_horus_stats", "gs_horus_fetch"):
         getattr(lib, name).restype = C.c_int
     return lib
 
 
-def load_library(path=None):
-    """Load libgsched.so and declare its prototypes; raises if it is not built."""
+def load_library():
+    """Load libgsched.so and declare its prototypes; raises if it is not built or is not the CUDA build."""
     global _lib
-    if _lib is not None and path is None:
+    if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = LIB_PATH
     if not os.path.exists(path):
         raise GsError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(there is no CPU fallback)")
@@ -198,6 +200,9 @@ def load_library(path=None):
     if lib.gs_abi_version() != 1:
         raise GsError("libgsched.so ABI version mismatch")
     declare_horus_prototypes(lib)
+    lib.gs_build_tag.restype = C.c_char_p
+    if lib.gs_build_tag() != CUDA_BUILD_TAG or lib.gs_horus_build_tag() != CUDA_BUILD_TAG:
+        raise GsError(f"{path} is not the nvcc sm_100a build (there is no CPU path)")
     _lib = lib
     return lib
 
@@ -238,8 +243,8 @@ def make_horus_params(scheme="horus", schedule="horus", num_buffer=5, num_queue=
 class HorusEngine:
     """`nsims` independent horus / gandiva simulations on one CUDA device (include/gsched_horus.h)."""
 
-    def __init__(self, device=0, nsims=1, lib=None):
-        self.lib = lib if lib is not None else load_library()
+    def __init__(self, device=0, nsims=1):
+        self.lib = self._library()
         self.h = C.c_void_p()
         self.nsims = int(nsims)
         self._n = [0] * self.nsims
@@ -248,6 +253,10 @@ class HorusEngine:
             msg = self.lib.gs_horus_last_error(None)
             self.h = C.c_void_p()
             raise GsError(f"gs_horus_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    @staticmethod
+    def _library():
+        return load_library()       # always the CUDA build (load_library checks the build tag)
 
     def _check(self, rc, what):
         if rc != 0:

@@ -129,6 +129,13 @@ extern "C" int gs_horus_destroy(gs_horus_handle h) {
   return GS_OK;
 }
 
+extern "C" const char *gs_horus_build_tag(void) {
+#ifdef __CUDACC__
+  return "cuda:sm_100a";
+#else
+  return "host-emulation";
+#endif
+}
 extern "C" const char *gs_horus_last_error(gs_horus_handle h) { return h ? h->err.c_str() : g_horus_create_err.c_str(); }
 extern "C" int64_t gs_horus_launch_count(gs_horus_handle h) { return h ? h->launches : 0; }
 extern "C" int gs_horus_set_lanes(gs_horus_handle h, int lanes) {
@@ -161,19 +168,20 @@ extern "C" int gs_horus_load_trace(gs_horus_handle h, int32_t sim, int64_t n, co
   if (!h || sim < 0 || sim >= (int)h->sims.size() || n < 0 || n > 0x3fffffff) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: bad arguments");
   if (n > 0 && (!arrive || !gpus || !gpc || !duration || !mem_bytes || !util_avg || !util_max)) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: null column");
   auto &s = h->sims[(size_t)sim];
-  s.jobs.resize((size_t)n);
+  std::vector<HJob> jobs((size_t)n);     // validated into a temporary: a rejected trace leaves the replica as it was
   long long first = 0;
   for (int64_t j = 0; j < n; ++j) {
     if (gpc[j] <= 0 || gpus[j] < gpc[j] || gpus[j] % gpc[j] != 0) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: used_gpus must be a positive multiple of gpu_per_container");
     if (j > 0 && arrive[j] < arrive[j - 1]) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: rows must be in admission order");
     if (util_max[j] < util_avg[j]) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: gpu_utilization_max < avg (numpy raises on a negative scale)");
-    HJob &o = s.jobs[(size_t)j];
+    HJob &o = jobs[(size_t)j];
     o.arrive = arrive[j]; o.gpus = gpus[j]; o.gpc = gpc[j]; o.ntasks = gpus[j] / gpc[j]; o.first_task = (int)first; o.pad = 0;
     o.mem_b = mem_bytes[j]; o.util_avg = util_avg[j]; o.util_max = util_max[j]; o.duration = duration[j];
     o.mem_avg_mib = mem_avg_mib ? mem_avg_mib[j] : 0.0;
     first += o.ntasks;
     if (first > 0x3fffffff) return hfail(h, GS_ERR_ARG, "gs_horus_load_trace: too many tasks");
   }
+  s.jobs.swap(jobs);
   s.loaded = true; s.prepared = false;
   return GS_OK;
 }

@@ -99,6 +99,13 @@ static int fail(gs_handle h, int code, const std::string &msg) {
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
+extern "C" const char *gs_build_tag(void) {
+#ifdef __CUDACC__
+  return "cuda:sm_100a";
+#else
+  return "host-emulation";
+#endif
+}
 
 extern "C" const char *gs_last_error(gs_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
@@ -166,27 +173,36 @@ extern "C" int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, co
   if (rc) return rc;
   SimHost &s = h->sims[(size_t)sim];
   if (s.prepared) return fail(h, GS_ERR_STATE, "gs_config_sim: replica already running");
-  s.cl = *cluster;
-  if (policy) s.pol = *policy; else { memset(&s.pol, 0, sizeof(s.pol)); s.pol.num_queue = 1; }
-  if (s.pol.schedule < GS_SCHED_FIFO || s.pol.schedule > GS_SCHED_GITTINS)
+  // validate into locals, commit only on success (a rejected call leaves the replica as it was)
+  gs_policy pol;
+  if (policy) pol = *policy; else { memset(&pol, 0, sizeof(pol)); pol.num_queue = 1; }
+  if (pol.schedule < GS_SCHED_FIFO || pol.schedule > GS_SCHED_GITTINS)
     return fail(h, GS_ERR_ARG, "gs_config_sim: unknown schedule");
-  if (s.pol.scheme != GS_SCHEME_YARN && s.pol.scheme != GS_SCHEME_COUNT)
+  if (pol.scheme != GS_SCHEME_YARN && pol.scheme != GS_SCHEME_COUNT)
     return fail(h, GS_ERR_ARG, "gs_config_sim: unknown scheme");
-  if (s.pol.schedule == GS_SCHED_FIFO && s.pol.scheme != GS_SCHEME_YARN)
+  if (pol.schedule == GS_SCHED_FIFO && pol.scheme != GS_SCHEME_YARN)
     return fail(h, GS_ERR_ARG, "gs_config_sim: fifo runs with the yarn scheme only");
-  if ((s.pol.schedule == GS_SCHED_DLAS || s.pol.schedule == GS_SCHED_DLAS_GPU) &&
-      (s.pol.num_queue < 1 || s.pol.num_queue > GS_MAX_QUEUES))
+  if ((pol.schedule == GS_SCHED_DLAS || pol.schedule == GS_SCHED_DLAS_GPU) &&
+      (pol.num_queue < 1 || pol.num_queue > GS_MAX_QUEUES))
     return fail(h, GS_ERR_ARG, "gs_config_sim: num_queue must be in 1..8 for dlas");
-  if (s.git_dev) { cudaFree(s.git_dev); s.git_dev = nullptr; }
-  if (s.pol.schedule == GS_SCHED_GITTINS) {
-    if (s.pol.gittins_n < 1 || !s.pol.gittins_data || !s.pol.gittins_index)
+  void *git_dev = nullptr;
+  if (pol.schedule == GS_SCHED_GITTINS) {
+    if (pol.gittins_n < 1 || !pol.gittins_data || !pol.gittins_index)
       return fail(h, GS_ERR_ARG, "gs_config_sim: gittins needs the (data, index) tables");
     CU(cudaSetDevice(h->device));
-    const size_t bytes = 8 * (size_t)s.pol.gittins_n;
-    CU(cudaMalloc(&s.git_dev, 2 * bytes));
-    CU(cudaMemcpy(s.git_dev, s.pol.gittins_data, bytes, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy((unsigned char *)s.git_dev + bytes, s.pol.gittins_index, bytes, cudaMemcpyHostToDevice));
+    const size_t bytes = 8 * (size_t)pol.gittins_n;
+    CU(cudaMalloc(&git_dev, 2 * bytes));
+    cudaError_t e1 = cudaMemcpy(git_dev, pol.gittins_data, bytes, cudaMemcpyHostToDevice);
+    cudaError_t e2 = cudaMemcpy((unsigned char *)git_dev + bytes, pol.gittins_index, bytes, cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(git_dev); return fail(h, GS_ERR_CUDA, "gs_config_sim: gittins table upload failed"); }
   }
+  if (s.git_dev) cudaFree(s.git_dev);
+  s.git_dev = git_dev;
+  s.cl = *cluster;
+  s.pol = pol;
+  s.pol.gittins_data = s.pol.gittins_index = nullptr;   // host pointers are not retained past this call
+  s.loaded = false;       // load-time bounds (max_need, span_cap) depend on the cluster: a reconfigured replica needs its trace again
+  h->dirty = true;
   s.configured = true;
   return GS_OK;
 }
@@ -390,7 +406,6 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
   }
   const size_t lane_words = (size_t)maxM * (maxG > 32 ? 3 : 2) + LANE_EXTRA_WORDS;
   int L = 32;
-  if (const char *e = getenv("GSCHED_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) L = v; }
   while (L > 1 && lane_words * (size_t)L * 4 > 100 * 1024) L >>= 1;
   const size_t lane_smem = lane_words * (size_t)L * 4;
   bool use_lane = h->engine_mode == 2;   // auto == warp mapping (measured faster at every replica count that fits HBM)
@@ -443,7 +458,6 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
       CU(cudaFuncSetAttribute(gs_tick_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * stride));
     }
     int sub = 32;
-    if (const char *e = getenv("GSCHED_SUB")) { if (atoi(e) == 16) sub = 16; }
     if (h->engine_mode == 3) sub = 16;
     if (sub == 16)
       gs_tick_kernel<16><<<(unsigned)((h->nsims + 1) / 2), 32, (size_t)stride * 2, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);

@@ -58,6 +58,8 @@ def run_batched_horus(flag_sets, device=0, out_root="log", chunk=1 << 21, rows_c
             (eng.load_words if sm["raw"] else eng.load_stream)(i, sm["stream"])
         cap = rows_cap
         while True:
+            for sm in sims:
+                sm["ran_cap"] = cap                       # the row window this launch really gives every replica
             try:
                 eng.run(rows_cap=cap)
                 break
@@ -68,10 +70,10 @@ def run_batched_horus(flag_sets, device=0, out_root="log", chunk=1 << 21, rows_c
                     st = eng.stats(i)
                     if st.status != capi.GS_ERR_CAPACITY:
                         continue
-                    if st.ticks < sm["rows_cap"]:         # ran out of samples: continue this replica's stream
+                    if st.ticks < sm["ran_cap"]:          # ran out of samples: continue this replica's stream
                         sm["stream"] = np.concatenate([sm["stream"], sm["draw"](len(sm["stream"]))])
-                    else:
-                        sm["rows_cap"] *= 2
+                    else:                                 # ran out of rows
+                        sm["rows_cap"] = 2 * sm["ran_cap"]
                     (eng.load_words if sm["raw"] else eng.load_stream)(i, sm["stream"])
                 cap = max(sm["rows_cap"] for sm in sims)
         for i, sm in enumerate(sims):

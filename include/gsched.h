@@ -157,6 +157,7 @@ typedef struct gs_jobin {
 typedef struct gs_engine *gs_handle;
 
 int gs_abi_version(void);
+const char *gs_build_tag(void);          /* "cuda:sm_100a": the package refuses any other build of these entry points */
 const char *gs_last_error(gs_handle h);  /* h may be NULL: last creation error    */
 
 /* A handle simulates `nsims` independent replicas on CUDA device `device`.      */

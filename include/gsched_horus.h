@@ -98,6 +98,9 @@ int gs_horus_fetch(gs_horus_handle h, int32_t sim, gs_tick_row *rows, double *ut
 int gs_horus_set_lanes(gs_horus_handle h, int lanes_per_warp);
 int64_t gs_horus_launch_count(gs_horus_handle h);
 const char *gs_horus_last_error(gs_horus_handle h);
+/* "cuda:sm_100a" for the shipped library.  The test suite also compiles this file's host side with g++ against a
+ * stand-in CUDA runtime (tests/emu); that build answers "host-emulation" and the package refuses to load it. */
+const char *gs_horus_build_tag(void);
 
 #ifdef __cplusplus
 }

@@ -88,3 +88,18 @@ def abi_lib():
         from gpuschedule_b200 import capi
         _abi_lib = capi.declare_horus_prototypes(C.CDLL(build_abi()))
     return _abi_lib
+
+
+def emu_engine_class():
+    """TEST INFRASTRUCTURE: capi.HorusEngine bound to the host-emulation build of gs_horus.cu.  The package itself has
+    no way to select a library (capi.load_library only accepts the nvcc build); the substitution lives here, in tests/."""
+    from gpuschedule_b200 import capi
+
+    class EmuHorusEngine(capi.HorusEngine):
+        @staticmethod
+        def _library():
+            lib = abi_lib()
+            assert lib.gs_horus_build_tag() == b"host-emulation"
+            return lib
+
+    return EmuHorusEngine

@@ -8,7 +8,10 @@ import numpy as np
 from gpuschedule_b200 import capi
 lib = capi.declare_horus_prototypes(C.CDLL(sys.argv[1]))
 import test_horus_abi_emu as T
-cls = functools.partial(capi.HorusEngine, lib=lib)
+class cls(capi.HorusEngine):           # test infrastructure: the sanitizer build of the host-emulation library
+    @staticmethod
+    def _library():
+        return lib
 from conftest import horus_cases, load_horus, render_horus_outputs
 for lanes, words, mt in ((1,False,0),(0,False,0),(0,True,64),(32,False,50)):
     cases = horus_cases(); loaded=[load_horus(c) for c in cases]

@@ -4,9 +4,8 @@ column) and vs the pinned oracle (oracle/horus_oracle.c) on seeded cases; severa
 runs, both stream forms, and the too-short-stream error.  (The file name sorts after the main-path GPU tests on
 purpose: the widening row must never keep `pytest -x` from reaching them.)
 
-The horus / gandiva tests ran green on a B200 in round 1.  The horus+ device path (k-means, credit queues,
-word-stream tables) was finished after the round's GPU budget was spent: the same functions pass on the CPU
-through tests/emu (tests/test_horus_emu.py), their device build has not run yet -- hence NOT_RUN_YET below."""
+Every test here is a hard assertion: nothing is marked xfail.  The same device functions also run on the CPU
+through tests/emu (tests/test_horus_emu.py, tests/test_horus_abi_emu.py)."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -15,9 +14,6 @@ import pytest
 from conftest import horus_cases, load_horus, render_horus_outputs
 
 pytestmark = pytest.mark.gpu
-NOT_RUN_YET = pytest.mark.xfail(strict=False, reason="this part of the device build has not run on a GPU yet (the same functions and "
-                                "the library's host side pass on the CPU: tests/test_horus_emu.py, tests/test_horus_abi_emu.py); "
-                                "a pass shows up as XPASS")
 
 
 def _stream(seed, count=1 << 21):
@@ -136,8 +132,15 @@ def test_short_stream_and_unserved_schedule_fail_loudly():
         with pytest.raises(capi.GsError) as e:                           # horus+ needs the raw word stream
             eng.run(rows_cap=1 << 15)
         assert e.value.code == -3
+    # scheme x schedule matrix of the utilisation-aware engine (algorithm.py:182-187,292-298): yarn is served
+    # (ms_yarn_placement under the look-ahead schedulers); fifo is not (KeyError in score_fn[schedule], algorithm.py:58)
+    yp = capi.make_horus_params("yarn", "horus", 5)
+    assert (yp.placement, yp.schedule, yp.score) == (1, 1, 0)
+    assert capi.make_horus_params("horus", "gandiva", 5).placement == 0
     with pytest.raises(NotImplementedError):
-        capi.make_horus_params("yarn", "horus", 5)
+        capi.make_horus_params("yarn", "fifo", 5)
+    with pytest.raises(NotImplementedError):
+        capi.make_horus_params("random", "horus", 5)
 
 
 @pytest.mark.parametrize("case", ["horus_racks", "gandiva_small"])
@@ -167,7 +170,6 @@ def test_cli_run_sim_horus_writes_reference_bytes(case, tmp_path):
         assert got == exp, name
 
 
-@NOT_RUN_YET
 def test_horus_plus_matches_reference_bytes():
     cases = _served(plus=True)
     assert len(cases) >= 2
@@ -179,7 +181,6 @@ def test_horus_plus_matches_reference_bytes():
         assert got_cluster == cluster_csv, case
 
 
-@NOT_RUN_YET
 def test_word_stream_serves_horus_and_gandiva_too():
     cases = _served()
     loaded = [load_horus(c) for c in cases]
@@ -189,7 +190,6 @@ def test_word_stream_serves_horus_and_gandiva_too():
         assert got_job == job_csv and got_cluster == cluster_csv, case
 
 
-@NOT_RUN_YET
 def test_batched_sweep_on_device(tmp_path):
     """sweep.run_batched_horus: seeded horus / gandiva / horus+ replicas in one launch == the single-run fixtures."""
     import os
@@ -210,7 +210,6 @@ def test_batched_sweep_on_device(tmp_path):
         assert open(os.path.join(out_dir, "cluster.csv"), newline="").read() == cluster_csv, case
 
 
-@NOT_RUN_YET
 def test_crossed_and_yarn_fixtures_match_reference_bytes():
     """score function by schedule name (cross_*) and --scheme yarn under these schedulers (yarn_sched_*)"""
     cases = [c for c in _served() if c not in RAN_GREEN_IN_ROUND_1]
@@ -222,7 +221,6 @@ def test_crossed_and_yarn_fixtures_match_reference_bytes():
         assert got_job == job_csv and got_cluster == cluster_csv, case
 
 
-@NOT_RUN_YET
 def test_cooperative_warp_mapping_matches_oracle_and_fixtures():
     """gs_horus_set_lanes(0): one simulation per warp, all lanes score a candidate job's devices together."""
     import oracle
@@ -240,7 +238,6 @@ def test_cooperative_warp_mapping_matches_oracle_and_fixtures():
         assert got_job == job_csv and got_cluster == cluster_csv, case
 
 
-@NOT_RUN_YET
 def test_cooperative_warp_mapping_horus_plus():
     cases = _served(plus=True)
     loaded = [load_horus(c) for c in cases]

@@ -25,8 +25,7 @@ def engine_cls():
     mod = importlib.util.module_from_spec(spec)
     sys.modules["tests_emu"] = mod
     spec.loader.exec_module(mod)
-    from gpuschedule_b200 import capi
-    return functools.partial(capi.HorusEngine, lib=mod.abi_lib())
+    return mod.emu_engine_class()
 
 
 @functools.lru_cache(maxsize=4)
