@@ -120,11 +120,102 @@ def run_to_done(eng, rows_cap):
             return
 
 
+def numa_cpus_of_gpu(index):
+    """CPUs of the NUMA node the GPU hangs off (pinned buffers allocated by a thread bound there are node-local);
+    None when the topology cannot be read."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return sorted(cpus) or None
+    except Exception:
+        return None
+
+
+def config_block(n, R):
+    """The `config` both arms print (the reference arm runs a bounded sample of the same workload)."""
+    return {"workload": f"{n}-job synthetic trace x {R} replicas/GPU (distinct seeds), 4x32x8 cluster, fifo+yarn",
+            "jobs_per_replica": n, "replicas_per_gpu": R, "cluster": "4x32x8", "policy": "fifo", "scheme": "yarn",
+            "l2": "inputs + outputs of a step (GBs per GPU) exceed the 126 MB L2"}
+
+
+POLICY_SETUP = {"sjf": dict(), "dlas": dict(num_queue=4, queue_limit=[3600, 7200, 18000]),
+                "dlas-gpu": dict(num_queue=4, queue_limit=[3600, 7200, 18000])}
+
+
+def make_policy(name, table):
+    from gpuschedule_b200 import capi
+    from gpuschedule_b200 import policies as gpol
+    if name == "fifo":
+        return capi.make_policy("fifo")
+    if name == "gittins":
+        return capi.make_policy("gittins", gittins_delta=3250.0,
+                                gittins_table=gpol.build_gittins_table(gpol.gittins_samples(table), 3250.0))
+    return capi.make_policy(name, **POLICY_SETUP[name])
+
+
+def policy_measure(name, cluster, tabs, device, steps=1, check=True):
+    """Event-driven policy kernels (BASELINE configs C2-C4 on one GPU): device-timed events/s over `tabs` replicas, the
+    algorithmic bytes of SURVEY 8(d) -- per event (runnable jobs)*32 + M*16 + 64 -- from the rows of a sample of the
+    replicas, one replica compared field by field with oracle/policy_oracle.c, which is also the timed CPU leg."""
+    from gpuschedule_b200 import capi
+    pols = [make_policy(name, t) for t in tabs]
+    m = cluster.num_switch * cluster.num_node_p_switch
+    with capi.Engine(device=device, nsims=len(tabs)) as pe:
+        for i, t in enumerate(tabs):
+            pe.config(i, cluster, pols[i])
+            pe.load_trace_packed(i, t.packed())
+        run_to_done(pe, 0)
+        cap = max(pe.stats(i).ticks for i in range(len(tabs))) + 64
+        ms = 0.0
+        for _ in range(steps):
+            pe.reset()
+            run_to_done(pe, cap)
+            ms += pe.stats(0).kernel_ms
+        ms /= steps
+        ev = sum(pe.stats(i).events for i in range(len(tabs)))
+        sample = list(range(min(4, len(tabs))))
+        alg = 0
+        for i in sample:
+            rows = pe.fetch_rows(i)
+            alg += int((rows["running"].astype(np.int64) + rows["queued"]).sum()) * 32 + len(rows) * (m * 16 + 64)
+        alg = alg / len(sample) * len(tabs)
+        rows0, (recs0, order0), st0 = pe.fetch_rows(0), pe.fetch_jobs(0), pe.stats(0)
+    out = {"value": ev / (ms / 1e3), "unit": UNIT, "ms": ms, "replicas": len(tabs), "jobs_per_replica": tabs[0].n,
+           "kernel": "gs_dlas_warp_kernel" if name.startswith("dlas") else "gs_sortpol_warp_kernel"}
+    peak, src = peaks()
+    ach = alg / (ms / 1e3) / 1e9
+    out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                       "algorithmic_bytes_per_launch": alg, "peak_source": src,
+                       "bytes_model": "SURVEY 8(d): per event (runnable jobs)*32 + M*16 + 64, summed over the events of a 4-replica sample, scaled"}
+    if check:
+        import oracle
+        c0 = time.perf_counter()
+        ref = oracle.run_policy(cluster, pols[0], tabs[0])
+        t_cpu = time.perf_counter() - c0
+        same = (rows0.tobytes() == ref.rows.tobytes() and recs0.tobytes() == ref.recs.tobytes()
+                and np.array_equal(order0, ref.finish_order) and st0.events == ref.events)
+        assert same, f"{name}: engine and oracle/policy_oracle.c disagree on replica 0"
+        out["parity"] = "replica 0 == oracle/policy_oracle.c on every row, record and the finish order (asserted in this run)"
+        out["cpu_baseline"] = {"value": ref.events / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"1 replica of {tabs[0].n} jobs, oracle/policy_oracle.c (restatement of the dead loop code, not reference code)"}
+    return out
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
     from gpuschedule_b200 import capi
-    from gpuschedule_b200.log_manager import JOB_DTYPE, ROW_DTYPE, SPAN_DTYPE
+    from gpuschedule_b200 import log_manager as lm
 
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -142,55 +233,49 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    from gpuschedule_b200 import dist as gdist
+    red = gdist.Reducer(world, dev)
 
     R, n = args.replicas, args.jobs
     cluster = capi.make_cluster(4, 32, 8)
-    from gpuschedule_b200 import policies as gpol
-
-    def policy_for(table):
-        if args.policy == "fifo":
-            return capi.make_policy("fifo")
-        if args.policy == "sjf":
-            return capi.make_policy("sjf")
-        if args.policy in ("dlas", "dlas-gpu"):
-            return capi.make_policy(args.policy, num_queue=4, queue_limit=[3600, 7200, 18000])
-        return capi.make_policy("gittins", gittins_delta=3250.0,
-                                gittins_table=gpol.build_gittins_table(gpol.gittins_samples(table), 3250.0))
+    M, G = 128, 8
     t0 = time.time()
-    from gpuschedule_b200 import dist as gdist
     tables = [fast_table(n, sd) for sd in gdist.replica_seeds(rank, world, R, base=BASE_SEED)]
     log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
-    eng = capi.Engine(device=local, nsims=R)
-    eng.set_engine(args.engine)
-    if args.span_budget > 0:
-        eng.set_span_budget(args.span_budget)
-    pols = [policy_for(t) for t in tables]
-    for r in range(R):
-        eng.config(r, cluster, pols[r])
-        eng.load_trace(r, tables[r])
 
-    # ---- warm-up (also sizes the per-replica row window so one launch completes a run)
+    if args.policy != "fifo":
+        # secondary mode: one event-driven policy alone (device-timed value, roofline, oracle check of replica 0)
+        out = policy_measure(args.policy, cluster, tables, local, steps=args.steps, check=(rank == 0))
+        ev_all = red.sum(out["value"] * out["ms"] / 1e3)
+        ms = red.max(out["ms"])
+        if rank == 0:
+            out.update({"metric": METRIC, "value": ev_all / (ms / 1e3), "n_gpus": world, "steps": args.steps,
+                        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                        "vs_baseline": None, "data": "synthetic", "dtype": "int32/int64 (+f64 ranks)",
+                        "config": {"workload": f"{n}-job synthetic trace x {R} replicas/GPU, 4x32x8, {args.policy}"}})
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    eng = capi.Engine(device=local, nsims=R)
+    eng.set_span_budget(args.span_budget)
+    for r in range(R):
+        eng.config(r, cluster)
+        eng.load_trace_packed(r, tables[r].packed())
+
+    # ---- warm-up (also sizes the per-replica record windows so that one launch completes a run)
     run_to_done(eng, 0)
-    ticks = [eng.stats(r).ticks for r in range(R)]
-    rows_cap = max(ticks) + 64
+    wins = [eng.window(r) for r in range(R)]
+    ticks = [int(w.ticks) for w in wins]
+    rows_cap = max(int(w.ev_rows) for w in wins) + 256
+    qrows_cap = max(int(w.q_rows) for w in wins) + 256
+    eng.set_queue_rows_cap(qrows_cap)
     for _ in range(max(args.warmup - 1, 2)):
         eng.reset()
         run_to_done(eng, rows_cap)
 
-    # ---- timed: K steps, traces resident in HBM
+    # ---- timed: K steps, traces resident in HBM; a step = reset + one full simulation of every replica
     sampler = ClockSampler(local)
     launches0 = eng.launch_count()
     barrier_sync()
@@ -206,124 +291,137 @@ def ours(args):
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
     st = [eng.stats(r) for r in range(R)]
+    wins = [eng.window(r) for r in range(R)]
     events_rank = sum(s.events for s in st)
     ticks_rank = sum(s.ticks for s in st)
     evals_rank = sum(s.placement_evals for s in st)
-    spans_rank = 0
-    for r in range(min(R, 4)):
-        spans_rank += len(eng.fetch_spans(r)[1])
-    spans_rank = spans_rank / min(R, 4) * R
-    if args.policy != "fifo":
-        # secondary measurement (event-driven policy kernel): device-timed value only
-        dev_ms = max_over_ranks(dev_ms)
-        events_all = sum_over_ranks(events_rank)
-        if rank == 0:
-            import oracle
-            c0 = time.perf_counter()
-            ref = oracle.run_policy(cluster, pols[0], tables[0])
-            t_cpu = time.perf_counter() - c0
-            assert ref.events == st[0].events and ref.ticks == st[0].ticks, "engine/oracle disagree"
-            print(json.dumps({"metric": METRIC, "value": events_all / (dev_ms / args.steps / 1e3), "unit": UNIT,
-                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                              "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                              "vs_baseline": None, "data": "synthetic", "dtype": "int32/int64",
-                              "config": {"workload": f"{n}-job synthetic trace x {R} replicas/GPU, 4x32x8, {args.policy}",
-                                         "policy": args.policy, "replicas_per_gpu": R, "jobs_per_replica": n,
-                                         "events_per_step": events_all, "rows_per_step": ticks_rank * world},
-                              "kernel": "gs_policy_kernel (thread per replica)", "clocks": clocks,
-                              "gpu_launches": int(launches),
-                              "cpu_baseline": {"value": ref.events / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                                               "sample": "1 replica, oracle/policy_oracle.c (restatement, not reference code)"}}),
-                  flush=True)
-        eng.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    dev_ms = max_over_ranks(dev_ms)
-    wall_ms = max_over_ranks(wall_ms)
-    events_all = sum_over_ranks(events_rank)
+    spans_rank = sum(int(w.spans_used) for w in wins)
+    recs_rank = sum(int(w.ev_rows) + int(w.q_rows) for w in wins)
+    dev_ms = red.max(dev_ms)
+    wall_ms = red.max(wall_ms)
+    events_all = red.sum(events_rank)
     value = events_all / (dev_ms / args.steps / 1e3)
 
     if args.value_only:
         if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": dev_ms / args.steps, "replicas_per_gpu": R}), flush=True)
+            print(json.dumps({"value": value, "ms_per_step": dev_ms / args.steps, "replicas_per_gpu": R,
+                              "records_per_tick": recs_rank / ticks_rank}), flush=True)
         eng.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (gs_tick_kernel), per launch, this rank's GPU
-    # algorithmic bytes: job table in (28 B/job) + job record + finish order out (28 B/job)
-    # + one 16-B span per (job,node) + one 64-B statistics row per tick   
+    # ---- single replica (the headline configuration itself: ONE 100k-job simulation on one GPU)
+    single = None
+    if rank == 0:
+        with capi.Engine(device=local, nsims=1) as e1:
+            e1.config(0, cluster)
+            e1.load_trace_packed(0, tables[0].packed())
+            run_to_done(e1, 0)
+            best = None
+            for _ in range(3):
+                e1.reset()
+                run_to_done(e1, rows_cap)
+                ms1 = e1.stats(0).kernel_ms
+                best = ms1 if best is None else min(best, ms1)
+            single = {"value": e1.stats(0).events / (best / 1e3), "unit": UNIT, "ms": best,
+                      "note": "one 100k-job simulation alone on the GPU: one warp, latency bound by construction"}
+
+    # ---- roofline of the dominant kernel (gs_tick2_kernel), per launch, this rank's GPU.  Algorithmic bytes are
+    # SURVEY 8(d)'s: job table in + job record out (56 B/job), one 16-B span per (job, node), one 64-B statistics
+    # row per simulated tick -- the information the launch produces, whatever encoding the engine writes it in.
     alg_bytes = R * n * 56 + spans_rank * 16 + ticks_rank * 64
+    written = R * n * (32 + 8 + 4) + spans_rank * 16 + recs_rank * 32
     peak, peak_src = peaks()
     ach = alg_bytes / (dev_ms / args.steps / 1e3) / 1e9
     traffic, traffic_src = None, None
-    try:      # DRAM bytes per launch from the committed ncu --set full capture (per replica, scaled to this R)
-        tj = json.load(open(os.path.join(REPO, "profiles", "tick_kernel_traffic.json")))
-        if tj["jobs_per_replica"] == n and args.policy == "fifo" and args.engine in (0, 1):
+    try:      # DRAM bytes per launch from the committed ncu --set full capture of THIS kernel at THIS replica count
+        tj = json.load(open(os.path.join(REPO, "profiles", "r02_tick2_kernel_traffic.json")))
+        if tj["jobs_per_replica"] == n:
             traffic = tj["dram_bytes_per_replica"] * R
             traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at %d replicas "
-                           "(profiles/tick_kernel_traffic.json), scaled per replica to %d" % (tj["replicas"], R))
+                           "(profiles/r02_tick2_kernel_traffic.json)%s" % (tj["replicas"], "" if tj["replicas"] == R else ", scaled per replica to %d" % R))
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "gs_tick_kernel", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "gs_tick2_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "bytes_read_or_written_once_by_design": written,
+                "records_per_tick": recs_rank / ticks_rank,
                 "ticks_per_s": ticks_rank * world / (dev_ms / args.steps / 1e3),
                 "candidate_evals_per_s": evals_rank * world / (dev_ms / args.steps / 1e3)}
 
-    # ---- end to end through the C ABI with host buffers: K host threads, each driving its own
-    # engine handle (own stream + pinned staging) over a slice of the replicas; every step re-uploads
-    # every trace from host memory and reads back every row, record, finish order and span.
-    T = max(ticks) + 64
-    span_cap = int(max(len(eng.fetch_spans(r)[1]) for r in range(min(R, 8))) * 1.25) + 4096
+    # ---- end to end through the C ABI with HOST buffers.  K host threads, each with its own engine handle (own
+    # stream) over a slice of the replicas; every step each thread uploads its traces from page-locked host memory
+    # (gs_load_trace_packed, asynchronous), runs them, and reads back every record of every replica into page-locked
+    # host memory (gs_fetch_compact + gs_sync): statistics records, queue records, per-job results, finish order, spans.
     eng.close()                                          # free the HBM of the value run first
-    packed = [t.packed() for t in tables]                # host-resident 32-byte records (built at ingest time)
     K = max(1, min(args.e2e_threads, R))
     slices = [list(range(k, R, K)) for k in range(K)]
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps)
     results = [None] * K
     errors = []
     start_evt = threading.Barrier(K + 1)
+    numa = numa_cpus_of_gpu(local)
+    span_max = max(int(w.spans_used) for w in wins) + 64
+    out_bytes = 32 * rows_cap + 32 * qrows_cap + 8 * n + 4 * n + 16 * span_max
 
     def worker(k):
         try:
+            if numa:
+                os.sched_setaffinity(0, numa)            # this thread only: its pinned allocations are node-local
             mine = slices[k]
             e = capi.Engine(device=local, nsims=len(mine))
-            e.set_engine(args.engine)
-            if args.span_budget > 0:
-                e.set_span_budget(args.span_budget)
-            pins = [capi.PinnedBuffer(T * ROW_DTYPE.itemsize), capi.PinnedBuffer(n * JOB_DTYPE.itemsize),
-                    capi.PinnedBuffer(n * 4), capi.PinnedBuffer((n + 1) * 8), capi.PinnedBuffer(span_cap * SPAN_DTYPE.itemsize)]
-            rows_v, jobs_v = pins[0].view(ROW_DTYPE, T), pins[1].view(JOB_DTYPE, n)
-            ord_v, off_v, sp_v = pins[2].view(np.int32, n), pins[3].view(np.int64, n + 1), pins[4].view(SPAN_DTYPE, span_cap)
-            for i in range(len(mine)):
+            e.set_async(True)
+            e.set_span_budget(args.span_budget)
+            e.set_queue_rows_cap(qrows_cap)
+            pin_in = capi.PinnedBuffer(len(mine) * n * 32)
+            pin_out = capi.PinnedBuffer(len(mine) * out_bytes)
+            ins, outs = [], []
+            for i, r in enumerate(mine):
+                v = pin_in.view(capi.JOBIN_DTYPE, n, i * n * 32)
+                v[:] = tables[r].packed()                 # the step's inputs live in host memory
+                ins.append(v)
+                o = i * out_bytes
+                ev = pin_out.view(lm.EVROW_DTYPE, rows_cap, o); o += 32 * rows_cap
+                qr = pin_out.view(lm.QROW_DTYPE, qrows_cap, o); o += 32 * qrows_cap
+                jb = pin_out.view(lm.JOBRUN_DTYPE, n, o); o += 8 * n
+                od = pin_out.view(np.int32, n, o); o += 4 * n
+                sp = pin_out.view(lm.SPAN_DTYPE, span_max, o)
+                outs.append((ev, qr, jb, od, sp))
                 e.config(i, cluster)
             ph = dict(load=0.0, run=0.0, fetch=0.0)
-            h2d = d2h = chk = ev = 0
+            h2d = d2h = chk = ev_cnt = 0
             for step in range(e2e_steps + 1):            # step 0 = untimed warm-up (allocations)
                 if step == 1:
                     start_evt.wait()                      # all threads + main: timed region starts
                     ph = dict(load=0.0, run=0.0, fetch=0.0)
-                h2d = d2h = ev = 0
+                    h2d = d2h = chk = ev_cnt = 0
                 c0 = time.perf_counter()
-                for i, r in enumerate(mine):
-                    e.load_trace_packed(i, packed[r])
+                for i in range(len(mine)):
+                    e.load_trace_packed(i, ins[i])
                     h2d += n * 32
                 c1 = time.perf_counter(); ph["load"] += c1 - c0
                 run_to_done(e, rows_cap)
                 c2 = time.perf_counter(); ph["run"] += c2 - c1
+                ws = []
                 for i in range(len(mine)):
-                    s = e.stats(i)
-                    rows, recs, order, span_off, spans = e.fetch_all(i, rows_v, jobs_v, ord_v, off_v, sp_v)
-                    chk += int(rows["finished"][-1]) + int(recs["end"][0]) + int(order[-1]) + len(spans)
-                    d2h += s.ticks * 64 + n * 24 + s.finished * 4 + len(spans) * 16 + (n + 1) * 8
-                    ev += s.events
+                    w = e.window(i)
+                    evb, qrb, jb, od, sp = outs[i]
+                    e.fetch_compact_into(i, evb, qrb, jb, None, od, sp)
+                    ws.append(w)
+                e.sync()
+                for i, w in enumerate(ws):
+                    evb, qrb, jb, od, sp = outs[i]
+                    d2h += 32 * (w.ev_rows + w.q_rows) + 8 * w.n + 4 * w.finished + 16 * w.spans_used
+                    chk += int(evb["finished"][w.ev_rows - 1]) + int(jb["start"][0]) + int(od[w.finished - 1]) + int(sp["node"][w.spans_used - 1])
+                    ev_cnt += e.stats(i).events
                 ph["fetch"] += time.perf_counter() - c2
-            results[k] = (ph, h2d, d2h, chk, ev)
-            for pb in pins:
-                pb.free()
+            # the records really are the run: decode one replica of this thread and compare with the value run
+            w = ws[0]
+            rows = lm.expand_rows(outs[0][0][:w.ev_rows], outs[0][1][:w.q_rows], w.row_first, w.ticks, M, G)
+            assert len(rows) == ticks[mine[0]] and int(rows["finished"][-1]) == n and int(rows["now"][-1]) == ticks[mine[0]]
+            results[k] = (ph, h2d // e2e_steps, d2h // e2e_steps, chk, ev_cnt // e2e_steps)
+            pin_in.free(); pin_out.free()
             e.close()
         except Exception as exc:                          # surface worker failures in the main thread
             errors.append(exc)
@@ -335,28 +433,32 @@ def ours(args):
     threads = [threading.Thread(target=worker, args=(k,)) for k in range(K)]
     for t in threads:
         t.start()
+    try:
+        start_evt.wait()                                  # released together with the workers' timed steps
+    except threading.BrokenBarrierError:
+        pass
     barrier_sync()
-    start_evt.wait()                                      # released together with the workers' timed steps
     w0 = time.perf_counter()
     for t in threads:
         t.join()
     if errors:
         raise errors[0]
     barrier_sync()
-    e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / e2e_steps
+    e2e_ms = red.max((time.perf_counter() - w0) * 1e3) / e2e_steps
     h2d = sum(r[1] for r in results); d2h = sum(r[2] for r in results)
     checksum = sum(r[3] for r in results)
     assert sum(r[4] for r in results) == events_rank, "e2e run simulated a different number of events"
     ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "fetch")}
     e2e = {"value": events_all / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(sum_over_ranks(h2d)), "d2h_bytes_per_step": int(sum_over_ranks(d2h)),
-           "steps": e2e_steps, "host_threads": K,
-           "timing": "wall clock between barrier+synchronize, max over ranks",
+           "h2d_bytes_per_step": int(red.sum(h2d)), "d2h_bytes_per_step": int(red.sum(d2h)),
+           "steps": e2e_steps, "host_threads": K, "pinned_buffers_numa_local": bool(numa),
+           "timing": "wall clock between barrier+synchronize around the timed steps of all threads, max over ranks",
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
+           "result_format": "compact records (gs_evrow/gs_qrow/gs_job_run/finish order/spans); one replica per thread is decoded to full rows and checked",
            "checksum": checksum}
 
-    # ---- secondary measurements (rank 0, N=1): the event-driven policies of BASELINE configs 1-3 on
-    # the same cluster (device-timed, 1 warm-up + 1 timed run each) and the stateless scoring kernel
+    # ---- secondary measurements (rank 0, N=1): the event-driven policies of BASELINE configs C2-C4 on the same
+    # cluster (device-timed, 1 warm-up + 1 timed run each, replica 0 checked against the oracle) and the stateless scoring kernel
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
@@ -365,23 +467,10 @@ def ours(args):
             tabs = tables[:rp] if njobs == n else [fast_table(njobs, sd) for sd in gdist.replica_seeds(0, 1, rp, base=BASE_SEED)]
             if name == "gittins":
                 tabs = tabs[:max(1, rp // 2)]
-            save = args.policy
-            args.policy = name
-            pl = [policy_for(t) for t in tabs]
-            args.policy = save
-            with capi.Engine(device=local, nsims=len(tabs)) as pe:
-                for i, t in enumerate(tabs):
-                    pe.config(i, cluster, pl[i])
-                    pe.load_trace_packed(i, t.packed())
-                run_to_done(pe, 0)
-                cap = max(pe.stats(i).ticks for i in range(len(tabs))) + 64
-                pe.reset()
-                run_to_done(pe, cap)
-                ms = pe.stats(0).kernel_ms
-                ev = sum(pe.stats(i).events for i in range(len(tabs)))
-            extras[name] = {"value": ev / (ms / 1e3), "unit": UNIT, "ms": ms, "replicas": len(tabs), "jobs_per_replica": njobs,
-                            "kernel": "gs_dlas_warp_kernel" if name == "dlas-gpu" else "gs_sortpol_warp_kernel",
-                            "parity": "engine == oracle/policy_oracle.c == the reference's loop functions executed under stubs (tests/golden/policy_*)"}
+            try:
+                extras[name] = policy_measure(name, cluster, tabs, local)
+            except Exception as exc:                      # a secondary line never costs the main one
+                extras[name] = {"error": repr(exc)}
         try:
             import contextlib
             import io
@@ -398,7 +487,6 @@ def ours(args):
         # widening row f1 (horus / gandiva / horus+ engine): its own process with a time limit, so that nothing it
         # does can cost the main measurement
         try:
-            import subprocess
             hp = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "horus", "--horus-replicas", "1184"],
                                 capture_output=True, text=True, timeout=240)
             line = [ln for ln in hp.stdout.splitlines() if ln.startswith("{")]
@@ -414,7 +502,7 @@ def ours(args):
         t_cpu, ev_cpu, k = 0.0, 0, 0
         while t_cpu < args.cpu_seconds and k < R:
             c0 = time.perf_counter()
-            ref = oracle.run_fifo(cluster, tables[k], rows_cap=T + 64, want_spans=False)
+            ref = oracle.run_fifo(cluster, tables[k], rows_cap=max(ticks) + 128, want_spans=False)
             t_cpu += time.perf_counter() - c0
             ev_cpu += ref.events
             assert ref.ticks == ticks[k] and ref.events == st[k].events, "engine/oracle disagree"
@@ -422,17 +510,7 @@ def ours(args):
         cpu = {"value": ev_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{k} replica(s) of the {n}-job trace, full runs, oracle/gsched_oracle.c single thread",
                "host_cores": os.cpu_count()}
-        # extra yardstick (not the reference's algorithm): the engine's own O(1)-counter algorithm as
-        # tight single-thread C, oracle/tight_cpu.c -- the strongest CPU competitor we could write
-        tr = oracle.TightRunner(cluster, tables[0])
-        tr.run()
-        c0 = time.perf_counter(); reps = 0; ev_t = 0
-        while time.perf_counter() - c0 < 2.0:
-            tk, ev = tr.run(); reps += 1; ev_t += ev
-        assert tk == ticks[0]
-        cpu_tight = {"value": ev_t / (time.perf_counter() - c0), "unit": UNIT, "cores": 1,
-                     "kind": "tight C restatement of the ENGINE's algorithm (oracle/tight_cpu.c), not reference code",
-                     "sample": f"{reps} runs of one {n}-job replica"}
+        cpu_tight = tight_yardstick(cluster, tables[:1], 1, ticks[0])
 
     if rank == 0:
         out = {
@@ -440,18 +518,43 @@ def ours(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 (+f64 durations)",
             "data": "synthetic",
-            "config": {"workload": f"{n}-job synthetic trace x {R} replicas/GPU (distinct seeds), 4x32x8 cluster, fifo+yarn",
-                       "jobs_per_replica": n, "replicas_per_gpu": R, "cluster": "4x32x8", "policy": "fifo",
-                       "scheme": "yarn", "parallelism": f"replicas x{world} GPUs, no data-path collective",
-                       "l2": "inputs+outputs per step (%.1f GB/GPU) exceed the 126 MB L2" % (alg_bytes / 1e9),
-                       "events_per_step": events_all, "ticks_per_step": ticks_rank * world},
+            "config": config_block(n, R),
+            "run": {"parallelism": f"replicas x{world} GPUs, no data-path collective", "events_per_step": events_all,
+                    "ticks_per_step": red_ticks_all(ticks_rank, world), "step_bytes_per_gpu": written},
             "wall_ms_per_step": wall_ms / args.steps,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_tight": cpu_tight, "secondary": extras,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "single_replica": single,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_tight": cpu_tight,
+            "vs_cpu_tight_one_core": (None if not cpu_tight else {"device_timed": value / cpu_tight["value"], "e2e": e2e["value"] / cpu_tight["value"],
+                                                                   "single_replica": single["value"] / cpu_tight["value"]}),
+            "secondary": extras,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def red_ticks_all(ticks_rank, world):
+    return ticks_rank * world            # every rank simulates the same number of replicas of statistically equal traces
+
+
+def tight_yardstick(cluster, tables, threads, expect_ticks=None, seconds=3.0):
+    """oracle/tight2_cpu.c -- the GPU engine's own event-stepped algorithm as tight single-thread C -- on `threads`
+    host threads, one replica each (ctypes releases the GIL): the strongest CPU competitor we could write."""
+    import concurrent.futures as cf
+    import oracle
+    runners = [oracle.Tight2(cluster, t) for t in tables[:threads]]
+    with cf.ThreadPoolExecutor(threads) as ex:
+        first = list(ex.map(lambda r: r.run(), runners))
+        if expect_ticks is not None:
+            assert first[0][0] == expect_ticks
+        t0 = time.perf_counter(); ev_t = 0; reps = 0
+        while time.perf_counter() - t0 < seconds:
+            ev_t += sum(e for _, e in ex.map(lambda r: r.run(), runners)); reps += 1
+        dt = time.perf_counter() - t0
+    return {"value": ev_t / dt, "unit": UNIT, "cores": threads,
+            "kind": "tight C restatement of the ENGINE's event-stepped algorithm (oracle/tight2_cpu.c), not reference code; "
+                    "writes the same compact records",
+            "sample": f"{reps} rounds of {threads} replica(s) of the {tables[0].n}-job trace, one per thread"}
 
 
 def place_mode(args):
@@ -596,7 +699,9 @@ def horus_mode(args):
 
 
 def reference(args):
-    """The reference arm: the CPU port of the reference's loop on all host cores."""
+    """The reference arm: the CPU port of the reference's loop (oracle/gsched_oracle.c) on ALL the host cores this
+    process may use, one replica per thread.  The Python reference itself (186 events/s at N=10k, O(N^2)) cannot travel
+    to the GPU box and could not finish one 100k-job replica in the time of the whole bench."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -607,25 +712,8 @@ def reference(args):
     n = args.jobs
     cluster = capi.make_cluster(4, 32, 8)
     oracle.lib()
-    threads = max(1, min(cores, args.cpu_threads or cores))
-    if not args.cpu_threads and cores > 4:
-        # "all the host threads it can use": container CPU quotas can make fewer threads faster than
-        # one per visible core, so pick the count with the best throughput on a short probe
-        probe_t = fast_table(min(n, 20000), BASE_SEED)
-        probe_cap = int(probe_t.arrive_tick[-1]) + 2 * int(np.ceil(probe_t.duration.max())) + 4096
-        best = (0.0, 1)
-        k = 1
-        while k <= cores:
-            with cf.ThreadPoolExecutor(k) as ex:
-                t0 = time.perf_counter()
-                ev = sum(ex.map(lambda _: oracle.run_fifo(cluster, probe_t, rows_cap=probe_cap, want_spans=False).events, range(k)))
-                rate = ev / (time.perf_counter() - t0)
-            if rate > best[0]:
-                best = (rate, k)
-            k *= 2
-        threads = best[1]
+    threads = max(1, min(cores, args.cpu_threads or cores))     # default: every core, always (same denominator in every record)
     tables = [fast_table(n, BASE_SEED + r) for r in range(threads)]
-
     caps = [int(t.arrive_tick[-1]) + 2 * int(np.ceil(t.duration.max())) + 4096 for t in tables]
 
     def one(it):
@@ -634,7 +722,7 @@ def reference(args):
 
     with cf.ThreadPoolExecutor(threads) as ex:
         work = list(zip(tables, caps))
-        for _ in range(args.warmup):
+        for _ in range(max(1, min(args.warmup, 2))):
             list(ex.map(one, work))
         t0 = time.perf_counter()
         events = 0
@@ -642,26 +730,18 @@ def reference(args):
             events += sum(ex.map(one, work))
         dt = time.perf_counter() - t0
     value = events / dt
-    runners = [oracle.TightRunner(cluster, t) for t in tables]
-    with cf.ThreadPoolExecutor(threads) as ex:
-        list(ex.map(lambda r: r.run(), runners))
-        t0 = time.perf_counter(); ev_t = 0; reps = 0
-        while time.perf_counter() - t0 < 3.0:
-            ev_t += sum(e for _, e in ex.map(lambda r: r.run(), runners)); reps += 1
-        tight_value = ev_t / (time.perf_counter() - t0)
-    sample = f"{threads} replicas of the {n}-job trace per step (one per thread), full runs"
+    tight = tight_yardstick(cluster, tables, threads)
+    sample = f"{threads} replicas of the {n}-job trace per step (one per thread on {cores} usable cores), full runs"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int32/int64 (+f64 durations)", "data": "synthetic",
-           "config": {"workload": f"{n}-job synthetic trace, 4x32x8 cluster, fifo+yarn", "jobs_per_replica": n,
-                      "cluster": "4x32x8", "policy": "fifo", "scheme": "yarn"},
+           "config": config_block(n, args.replicas),
+           "run": {"replicas_per_step": threads, "host_threads": threads, "usable_cores": cores},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                             "note": "oracle/gsched_oracle.c: C restatement of the reference's Python loop "
                                     "(the Python reference itself: 186 events/s at N=10k, BASELINE.md)"},
-           "cpu_tight": {"value": tight_value, "unit": UNIT, "cores": threads,
-                         "kind": "tight C restatement of the ENGINE's algorithm (oracle/tight_cpu.c), not reference code",
-                         "sample": f"{reps} rounds of {threads} replicas, one per thread"},
+           "cpu_tight": tight,
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -673,8 +753,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--jobs", type=int, default=100000)
-    ap.add_argument("--replicas", type=int, default=3552, help="replicas per GPU (one warp each)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--replicas", type=int, default=4736, help="replicas per GPU (one warp each; 4736 = 148 SMs x 32 warps)")
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=16, help="host threads (one engine handle each) in the e2e run")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
@@ -682,11 +762,10 @@ def main():
     ap.add_argument("--value-only", action="store_true", help="kernel experiments: print the device-timed value and stop")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
     ap.add_argument("--policy-replicas", type=int, default=1024)
-    ap.add_argument("--span-budget", type=float, default=0.0,
-                    help="span-pool records per job (0 = worst case); the trace uses ~1.13")
+    ap.add_argument("--span-budget", type=float, default=1.5,
+                    help="span-pool records per job (0 = worst case); the trace uses ~1.13, overflow is reported, never written")
     ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],
                     help="fifo = the headline (pinned) workload; others = secondary, event-driven policy kernel")
-    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 warp per replica, 2 lane per replica")
     ap.add_argument("--mode", default="sim", choices=["sim", "place", "horus"], help="place = gs_place_batch micro-benchmark; horus = utilisation-aware engine")
     ap.add_argument("--horus-replicas", type=int, default=2368)
     ap.add_argument("--horus-jobs", type=int, default=60)

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .log_manager import JOB_DTYPE, ROW_DTYPE, SPAN_DTYPE
+from .log_manager import EVROW_DTYPE, JOB_DTYPE, JOBRUN_DTYPE, QROW_DTYPE, ROW_DTYPE, SPAN_DTYPE
 
 GS_MAX_QUEUES = 8
 SCHEDULES = {"fifo": 0, "sjf": 1, "dlas": 2, "dlas-gpu": 3, "gittins": 4}
@@ -45,6 +45,11 @@ class GsRunStats(C.Structure):
                 ("started", C.c_int64), ("placement_evals", C.c_int64), ("done", C.c_int32),
                 ("status", C.c_int32), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double)]
+
+
+class GsWindowInfo(C.Structure):
+    _fields_ = [("row_first", C.c_int64), ("ticks", C.c_int64), ("ev_rows", C.c_int64), ("q_rows", C.c_int64),
+                ("spans_used", C.c_int64), ("admitted", C.c_int64), ("finished", C.c_int64), ("n", C.c_int64)]
 
 
 JOBIN_DTYPE = np.dtype([("arrive_tick", "<i4"), ("gpus", "<i4"), ("gpu_per_task", "<i4"), ("ps_count", "<i4"),
@@ -191,13 +196,20 @@ def load_library():
     lib.gs_set_engine.restype = C.c_int
     lib.gs_launch_count.argtypes = [C.c_void_p]
     lib.gs_launch_count.restype = C.c_int64
+    lib.gs_window.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsWindowInfo)]
+    lib.gs_fetch_compact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gs_sync.argtypes = [C.c_void_p]
+    lib.gs_set_async.argtypes = [C.c_void_p, C.c_int]
+    lib.gs_set_queue_rows_cap.argtypes = [C.c_void_p, C.c_int64]
+    for name in ("gs_window", "gs_fetch_compact", "gs_sync", "gs_set_async", "gs_set_queue_rows_cap"):
+        getattr(lib, name).restype = C.c_int
     lib.gs_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.gs_host_free.argtypes = [C.c_void_p]
     for name in ("gs_reset", "gs_host_alloc", "gs_host_free", "gs_create", "gs_config_sim", "gs_load_trace", "gs_run", "gs_stats",
                  "gs_fetch_rows", "gs_fetch_jobs", "gs_fetch_spans", "gs_place_batch",
                  "gs_net_cost"):
         getattr(lib, name).restype = C.c_int
-    if lib.gs_abi_version() != 1:
+    if lib.gs_abi_version() != 2:
         raise GsError("libgsched.so ABI version mismatch")
     declare_horus_prototypes(lib)
     lib.gs_build_tag.restype = C.c_char_p
@@ -384,7 +396,7 @@ class Engine:
             _ptr(ps, C.c_int32)), "gs_load_trace")
 
     def set_engine(self, mode):
-        """0 auto, 1 warp-per-replica, 2 lane-per-replica."""
+        """event-driven policies: 0 / 1 = warp per replica, 2 = thread per replica (the fifo engine has one mapping)"""
         self._check(self.lib.gs_set_engine(self.h, int(mode)), "gs_set_engine")
 
     def load_trace_packed(self, sim, packed, model_mb=None, iterations=None):
@@ -409,6 +421,44 @@ class Engine:
         n = self._n[sim]
         return (rows_out[:int(count)], jobs_out[:n], order_out[:int(st.finished)], off_out[:n + 1],
                 spans_out[:used.value])
+
+    # ---- compact, asynchronous result path (fifo engine)
+    def window(self, sim=0) -> GsWindowInfo:
+        w = GsWindowInfo()
+        self._check(self.lib.gs_window(self.h, sim, C.byref(w)), "gs_window")
+        return w
+
+    def set_async(self, on=True):
+        self._check(self.lib.gs_set_async(self.h, 1 if on else 0), "gs_set_async")
+
+    def set_queue_rows_cap(self, cap):
+        self._check(self.lib.gs_set_queue_rows_cap(self.h, int(cap)), "gs_set_queue_rows_cap")
+
+    def sync(self):
+        self._check(self.lib.gs_sync(self.h), "gs_sync")
+
+    def fetch_compact_into(self, sim, ev=None, qr=None, jobs=None, dur=None, order=None, spans=None):
+        """Enqueue the copies of one replica's compact results into caller buffers (numpy views, ideally of
+        PinnedBuffer memory, each at least as long as window(sim) says); returns at once -- call sync()."""
+        def vp(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.gs_fetch_compact(self.h, sim, vp(ev), vp(qr), vp(jobs), vp(dur), vp(order), vp(spans)),
+                    "gs_fetch_compact")
+
+    def fetch_compact(self, sim=0):
+        """(window info, gs_evrow[], gs_qrow[], gs_job_run[], duration-after-network-cost or None, finish order, span pool)"""
+        w = self.window(sim)
+        n = int(w.n)
+        ev = np.empty(max(int(w.ev_rows), 1), dtype=EVROW_DTYPE)
+        qr = np.empty(max(int(w.q_rows), 1), dtype=QROW_DTYPE)
+        jobs = np.empty(max(n, 1), dtype=JOBRUN_DTYPE)
+        dur = np.full(max(n, 1), np.nan)
+        order = np.empty(max(int(w.finished), 1), dtype=np.int32)
+        spans = np.empty(max(int(w.spans_used), 1), dtype=SPAN_DTYPE)
+        self.fetch_compact_into(sim, ev, qr, jobs, dur, order, spans)
+        self.sync()
+        return (w, ev[:int(w.ev_rows)], qr[:int(w.q_rows)], jobs[:n], (None if n == 0 or np.isnan(dur[0]) else dur[:n]),
+                order[:int(w.finished)], spans[:int(w.spans_used)])
 
     def set_span_budget(self, spans_per_job):
         self._check(self.lib.gs_set_span_budget(self.h, float(spans_per_job)), "gs_set_span_budget")

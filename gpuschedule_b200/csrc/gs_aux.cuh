@@ -1,65 +1,21 @@
 // gs_aux.cuh -- part of libgsched.so (single translation unit, included from gsched.cu).
-// Replica reset, span regrouping, stateless placement scoring, network-cost kernels.
+// Replica reset (event-driven policies), stateless placement scoring, network-cost kernels.
 #pragma once
 
-// One launch (re)initialises every replica flagged need_init: job records (never-started jobs
-// report start=end=-1, jct=preempt=0 and their input duration), empty wheel, idle node table.
+// One launch (re)initialises every event-driven replica flagged need_init: job records (never-started
+// jobs report start=end=-1, jct=preempt=0 and their input duration) and the per-job policy state.
+// (The fifo engine resets its own small tables at the start of gs_tick2_kernel.)
 __global__ void gs_init_kernel(SimDev *sims, int nsims) {
   const int sim = blockIdx.y;
   if (sim >= nsims) return;
   const SimDev &S = sims[sim];
-  if (!S.need_init) return;
+  if (!S.need_init || S.policy == GS_SCHED_FIFO) return;
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int i = t0; i < S.n; i += stride) {
     gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0; r.duration = S.jobs[i].dur;
     S.rec[i] = r;
+    PJob z; memset(&z, 0, sizeof(z)); z.start = -1; S.pj[i] = z;
   }
-  for (int i = t0; i <= S.wheel_mask; i += stride) { S.wheel_head[i] = -1; S.wheel_tail[i] = -1; }
-  for (int i = t0; i < S.M; i += stride) { S.nbusy[i] = 0ull; S.nk[i] = 0; }
-  for (int i = t0; i < S.n; i += stride) S.sref[i] = make_int2(0, 0);
-  if (S.policy != GS_SCHED_FIFO)
-    for (int i = t0; i < S.n; i += stride) { PJob z; memset(&z, 0, sizeof(z)); z.start = -1; S.pj[i] = z; }
-}
-
-// ------------------------------------------------------------------ result regrouping
-// Spans are pooled in START order while the simulation runs; callers want them grouped by
-// job (CSR).  One block scans the per-job span counts, a second kernel gathers.
-__global__ void __launch_bounds__(1024) gs_span_scan_kernel(const gs_job_rec *__restrict__ rec, const int2 *__restrict__ sref,
-                                                            int n, long long *__restrict__ off) {
-  // one block: every thread sums a contiguous chunk, the block scans the 1024 chunk sums,
-  // every thread rewrites its chunk as an exclusive prefix
-  __shared__ long long warp_sum[32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int chunk = (n + 1023) / 1024;
-  const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
-  long long v = 0;
-  for (int j = lo; j < hi; ++j) v += (rec[j].start >= 0) ? sref[j].y : 0;
-  long long incl = v;
-  #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-  if (lane == 31) warp_sum[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    const long long w = warp_sum[lane];
-    long long wi = w;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
-    warp_sum[lane] = wi - w;
-  }
-  __syncthreads();
-  long long run = warp_sum[wid] + incl - v;
-  for (int j = lo; j < hi; ++j) { off[j] = run; run += (rec[j].start >= 0) ? sref[j].y : 0; }
-  if (tid == 1023) off[n] = run;
-}
-
-__global__ void gs_span_gather_kernel(const gs_job_rec *__restrict__ rec, const int2 *__restrict__ sref,
-                                      const gs_span *__restrict__ pool, const long long *__restrict__ off, int n,
-                                      gs_span *__restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n || rec[j].start < 0) return;
-  const int2 sr = sref[j];
-  const long long o = off[j];
-  for (int i = 0; i < sr.y; ++i) out[o + i] = pool[sr.x + i];
 }
 
 // ------------------------------------------------------------------ stateless candidate scoring

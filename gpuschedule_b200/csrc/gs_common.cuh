@@ -3,27 +3,11 @@
 #pragma once
 
 #ifndef GS_TICK_MINBLOCKS
-#define GS_TICK_MINBLOCKS 24
+#define GS_TICK_MINBLOCKS 32
 #endif
 #define FULL 0xffffffffu
-// ballot over the lanes of one replica group, bit 0 = the group's first lane (needs GM, gbase, SUB in scope)
-#define GBALLOT(pred) ((SUB == 32) ? __ballot_sync(GM, (pred)) : ((__ballot_sync(GM, (pred)) >> gbase) & ((1u << SUB) - 1u)))
 
 // ------------------------------------------------------------------ device state
-
-struct __align__(16) JobState {   // 32 B, written at start, read once at completion
-  int next;                  // next job in the same finish-tick bucket (start order)
-  int node0;                 // span_cnt == 1: the node;  span_cnt > 1: first index in the span pool
-  unsigned long long mask0;  // span_cnt == 1: devices held on node0
-  long long memc;            // gpus * min(device capacity, memory_max): the job's share of the memory column
-  int gpus;
-  int cnt_gpc;               // span_cnt (bits 0-23) | gpu_per_task (bits 24-31)
-};
-#define JS_CNT(x) ((x) & 0xffffff)
-#define JS_GPC(x) ((int)((unsigned)(x) >> 24))
-// JobState.gpus: gpus (bits 0-23) | tasks of a single-span job (bits 24-31, <= 64 because gpus <= G <= 64 there)
-#define JS_GPUS(x) ((x) & 0xffffff)
-#define JS_NT0(x) ((int)((unsigned)(x) >> 24))
 
 struct __align__(32) JobIn {   // 32 B = one DRAM sector per job, read once in admission order
   int arrive;       // first tick with normalized_time <= tick
@@ -51,15 +35,19 @@ struct SimDev {
   const JobIn *jobs;
   const double *model_mb, *iters;
   // ---- results / scratch
-  gs_job_rec *rec;
-  JobState *jst;
-  int2 *sref;                 // per job: {first index in the span pool, span count}
-  int *stack, *fin, *wheel_head, *wheel_tail;
-  gs_span *spans;
-  gs_tick_row *rows;
+  gs_job_rec *rec;            // event-driven policies: full 24-byte record per job
+  int2 *rec2;                 // fifo: {start tick, run length} per job (-1, 0 = never started)
+  double *dur2;               // fifo with network costs: job.duration after the cost was added
+  struct JobState2 *jst2;     // fifo: release record of a running job
+  int *stack, *fin, *wheel_head;
+  long long *wheel_mem;       // per finish-tick bucket: memory share of the jobs ending there
+  gs_span *spans;             // start order; bit 31 of ntasks marks the first span of a job
+  gs_tick_row *rows;          // event-driven policies: one row per event
+  gs_evrow *evrows;           // fifo: one record per tick on which a counter changed
+  gs_qrow *qrows;             // fifo: queue statistics beside the records taken with a non-empty queue
   unsigned long long *nbusy;  // persisted node table (between launches)
   int *nk;                    // bit31 = node ever hosted a placement (node.py:93-97, never cleared)
-  long long span_cap, rows_cap;
+  long long span_cap, rows_cap, qrows_cap;
   // ---- event-driven policies (sjf / dlas / dlas-gpu / gittins): scratch + parameters
   struct PJob *pj;            // per-job dynamic state
   int *runnable, *queues, *endj, *tmpl, *cidle, *ckfree;   // queues: num_queue lists of n entries
@@ -70,6 +58,9 @@ struct SimDev {
   int num_queue, git_n, rn, en, end_time, next_job_jump, stale_n, qn[GS_MAX_QUEUES];
   // ---- loop state (persisted)
   int delta, p, top, running, finished, ever, busy_gpus, done, status, need_init;
+  int blocked;                // fifo: the queue head did not fit and nothing has changed since
+  int nev, nq;                // fifo: records / queue records written by the last launch
+  int pad1;
   long long mem_busy, sum_arr, span_used, events, evals, started, ticks, row_first;
 };
 

@@ -1,0 +1,552 @@
+// gs_tick2.cuh -- part of libgsched.so (single translation unit, included from gsched.cu).
+// fifo + yarn tick engine, one warp per replica, event stepped.
+//
+// What the reference does every tick (Scheduler.start, core/scheduling/schedule.py:185-209) is
+// restated here per EVENT tick: a tick on which nothing arrives, nothing can start and nothing
+// finishes changes no counter of the statistics row (schedule.py:95-133) except the ones that are
+// linear in the tick number, so such ticks are jumped over in one step and leave no record.  The
+// device therefore emits
+//   * one 32-byte gs_evrow per tick on which a counter changed (plus the first tick of a launch), and
+//   * one 32-byte gs_qrow beside it while the queue is non-empty (arrival-tick sum, oldest arrival,
+//     the two middle arrivals -- the pending statistics of jobs_manager.py:72-87 are `now - arrival`),
+// from which gs_expand_rows_kernel (or the host) rebuilds every gs_tick_row bit for bit.
+//
+// Per-tick path, in the order of the reference loop:
+//   A  admit arrivals  (jobs_manager.py:228-241; head insert, quirk Q2): a 32-record register window of
+//      the trace; the batch's first job stays in registers as the queue head, the rest go to the stack
+//   B  one attempt on the head  (schedule.py:40-60, algorithm.py:189-202,301-417): ballot first fit /
+//      prefix-sum cross-node fill over the shared-memory node table; a head that did not fit is not
+//      tried again until a completion or a new head could change the answer (the reference re-tries
+//      every tick with the same outcome; the evaluation counter is advanced in closed form)
+//   E  release the jobs whose finish tick is now  (schedule.py:141-162): timing wheel keyed by finish
+//      tick; the next non-empty bucket, its first job and that job's release record are kept in
+//      registers, so the common release has no dependent global load
+//   H  the record(s)
+#pragma once
+
+#define SCACHE 4        // cached top-of-stack entries (power of two)
+
+struct __align__(16) JobState2 {   // 16 B, written at start, read once at completion
+  int next;                  // next job of the same finish-tick bucket (reverse start order)
+  int where;                 // one span:  node (bits 0-19) | (tasks - 1) << 20;   several: bit 31 | first index in the span pool
+  unsigned long long mask0;  // one span:  devices held;                            several: span count | gpus << 32
+};
+
+__device__ __forceinline__ unsigned long long take_lowest(unsigned long long idle, int cnt, int G) {
+  // the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
+  if (cnt == 1) return idle & (~idle + 1ull);
+  if (G <= 32) {
+    unsigned m = (unsigned)idle;
+    if (cnt >= __popc(m)) return idle;
+    for (int i = 0; i < cnt; ++i) m &= m - 1u;
+    return (unsigned long long)((unsigned)idle ^ m);
+  }
+  unsigned long long m = idle;
+  if (cnt >= __popcll(m)) return idle;
+  for (int i = 0; i < cnt; ++i) m &= m - 1ull;
+  return idle ^ m;
+}
+
+__device__ __forceinline__ int meta_cap(unsigned mt, int gpc) {
+  // tasks a node can still take: min(idle devices / gpus per task, free task slots)
+  const int idle = (int)(mt & 0xffu), kfree = (int)(mt >> 16);
+  return min(gpc == 1 ? idle : idle / gpc, kfree);
+}
+
+__device__ __forceinline__ int need_of(double dur) {     // quirk Q11: run length = max(1, ceil(duration)) ticks
+  const double cl = ceil(dur);
+  return cl < 1.0 ? 1 : (cl > 1.0e9 ? 0x7fffffff : (int)cl);
+}
+
+#define GS_INF 0x7fffffff
+
+template <bool NET>
+__global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int sim = blockIdx.x;
+  if (sim >= nsims) return;
+  SimDev &S = sims[sim];
+  if (S.done || S.status != 0 || S.policy != GS_SCHED_FIFO || (S.netcost != 0) != NET) return;
+
+  const int M = S.M, G = S.G, n = S.n;
+  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw);
+  unsigned *kk = reinterpret_cast<unsigned *>(busy + M);     // idle devices (bits 0-7) | ever placed (bit 8) | free task slots << 16
+  int2 *sstk = reinterpret_cast<int2 *>(kk + M + (M & 1));   // 8-byte aligned
+
+  const JobIn *__restrict__ jobs = S.jobs;
+  int2 *rec2 = S.rec2;
+  JobState2 *jst = S.jst2;
+  int2 *stack = reinterpret_cast<int2 *>(S.stack);
+  int *fin = S.fin, *whead = S.wheel_head;
+  long long *wmem = S.wheel_mem;
+  gs_span *spans = S.spans;
+  int4 *rowA = reinterpret_cast<int4 *>(S.evrows), *rowB = reinterpret_cast<int4 *>(S.qrows);
+  // everything a replica owns lives in global memory: let the compiler emit ld/st.global instead of generic accesses
+  __builtin_assume(__isGlobal(jobs)); __builtin_assume(__isGlobal(rec2)); __builtin_assume(__isGlobal(jst));
+  __builtin_assume(__isGlobal(stack)); __builtin_assume(__isGlobal(fin)); __builtin_assume(__isGlobal(whead));
+  __builtin_assume(__isGlobal(wmem)); __builtin_assume(__isGlobal(spans)); __builtin_assume(__isGlobal(rowA));
+  __builtin_assume(__isGlobal(rowB));
+  const int wmask = S.wheel_mask;
+  const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
+  const int span_cap = (int)(S.span_cap > 0x7fffffffLL ? 0x7fffffffLL : S.span_cap);
+  const unsigned long long gmask = (G >= 64) ? ~0ull : ((1ull << G) - 1ull);
+
+  int delta = S.delta, p = S.p, top = S.top, running = S.running, finished = S.finished;
+  int ever = S.ever, busy_gpus = S.busy_gpus, status = 0, blocked = S.blocked;
+  int span_used = (int)S.span_used;
+  long long mem_busy = S.mem_busy, sum_arr = S.sum_arr, evals = S.evals;
+  const int delta0 = delta;
+  const int capA = (int)(S.rows_cap > 0x7fffffffLL ? 0x7fffffffLL : S.rows_cap);
+  const int capB = (int)(S.qrows_cap > 0x7fffffffLL ? 0x7fffffffLL : S.qrows_cap);
+  int na = 0, nb = 0;
+  long long budget_ll = max_ticks > 0 ? max_ticks : 0x7fffffffLL;
+  if (budget_ll > 0x7fffffffLL - delta - 2) budget_ll = 0x7fffffffLL - delta - 2;
+  const int t_end = delta + (int)(budget_ll > 0 ? budget_ll : 0);      // first tick this launch does NOT process
+
+  // ---- stage the node table (a fresh replica starts idle), the wheel and the top of the stack
+  if (S.need_init) {
+    const int K = S.K;
+    for (int i = lane; i < M; i += 32) { busy[i] = 0ull; kk[i] = (unsigned)G | ((unsigned)K << 16); }
+    for (int i = lane; i <= wmask; i += 32) { whead[i] = -1; wmem[i] = 0; }
+  } else {
+    const int K = S.K;
+    for (int i = lane; i < M; i += 32) {
+      const unsigned long long bz = S.nbusy[i];
+      const unsigned kv = (unsigned)S.nk[i];
+      busy[i] = bz;
+      kk[i] = (unsigned)(G - __popcll(bz)) | ((kv & EVER_BIT) ? 0x100u : 0u) | ((unsigned)(K - (int)(kv & ~EVER_BIT)) << 16);
+    }
+  }
+  int scount = top;                              // entries in the stack array; the head may live in registers instead
+  for (int i = max(scount - SCACHE, 0) + lane; i < scount; i += 32) sstk[i & (SCACHE - 1)] = stack[i];
+  int cache_lo = max(scount - SCACHE, 0);        // stack entries [cache_lo, scount) are cached in shared memory
+  int bottom_arr = (top > 0) ? stack[0].y : 0;
+  __syncwarp();
+
+  // ---- trace window: lane l holds record wbase + l, reduced to what the loop needs
+  int wbase = p & ~31;
+  int warr = GS_INF, wpk = 1 | (1 << 24), wneed = 1, wps = 0;
+  long long wmemc = 0;
+  double wdur = 0.0;
+#define LOAD_WINDOW()                                                                         \
+  do {                                                                                        \
+    warr = GS_INF;                                                                            \
+    if (wbase + lane < n) {                                                                   \
+      JobIn r_;                                                                               \
+      {                                                                                       \
+        const int4 *src_ = reinterpret_cast<const int4 *>(&jobs[wbase + lane]);               \
+        const int4 v0_ = __ldcs(src_), v1_ = __ldcs(src_ + 1);      /* streamed once */       \
+        r_.arrive = v0_.x; r_.gpus = v0_.y; r_.gpc = v0_.z; r_.ps = v0_.w;                     \
+        r_.memb = (long long)(((unsigned long long)(unsigned)v1_.y << 32) | (unsigned)v1_.x); \
+        r_.dur = __hiloint2double(v1_.w, v1_.z);                                              \
+      }                                                                                       \
+      warr = r_.arrive; wpk = r_.gpus | (r_.gpc << 24);                                       \
+      wneed = need_of(r_.dur); if (!(r_.memb < fit_limit)) wneed = -wneed;                    \
+      wmemc = (long long)r_.gpus * (r_.memb < cap_bytes ? r_.memb : cap_bytes);               \
+      if (NET) { wdur = r_.dur; wps = r_.ps; }                                                \
+    }                                                                                         \
+  } while (0)
+  LOAD_WINDOW();
+  int next_arr = GS_INF;
+  if (p < n) next_arr = __shfl_sync(FULL, warr, p - wbase);
+
+  // ---- queue head, kept in registers while it waits
+  bool hvalid = false;
+  int hjob = -1, harr = 0, hpk = 1 | (1 << 24), hneed = 1, hps = 0;
+  long long hmemc = 0;
+  double hdur = 0.0;
+#define HEAD_FROM_WINDOW(src_)                                                                \
+  do {                                                                                        \
+    hpk = __shfl_sync(FULL, wpk, (src_)); hneed = __shfl_sync(FULL, wneed, (src_));           \
+    hmemc = __shfl_sync(FULL, wmemc, (src_));                                                 \
+    if (NET) { hdur = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(wdur), (src_))); hps = __shfl_sync(FULL, wps, (src_)); } \
+  } while (0)
+
+  // ---- next completion: tick, first job of that bucket and its release record stay in registers
+  int next_fin = GS_INF, nf_head = -1;
+  JobState2 nf_js; nf_js.next = -1; nf_js.where = 0; nf_js.mask0 = 0ull;
+  if (running > 0) {
+    int base = delta + 1;
+    while (true) {
+      const int ph = whead[(base + lane) & wmask];
+      const unsigned b = __ballot_sync(FULL, ph >= 0);
+      if (b) { const int pos = __ffs(b) - 1; next_fin = base + pos; nf_head = __shfl_sync(FULL, ph, pos); break; }
+      base += 32;
+    }
+    nf_js = jst[nf_head];
+  }
+
+  bool done = (n == 0);
+  bool force = true;                              // the first tick of a launch always leaves a record
+
+  while (!done && status == 0) {
+    if (na >= capA || nb >= capB) break;          // no room for the records of another event tick
+    // ---------------- ticks on which nothing happens: jump
+    if (!force && (top == 0 || blocked)) {
+      const int t_next = min(next_arr, next_fin - 1);
+      if (t_next > delta) {
+        const int t_to = min(t_next, t_end);
+        if (blocked) evals += (long long)(t_to - delta) * M;       // the reference re-tries the head every tick
+        delta = t_to;
+      }
+    }
+    if (delta >= t_end) break;
+    bool changed = force;
+    force = false;
+    // ---------------- A. admit arrivals (gen_jobs + head insert)
+    if (next_arr <= delta) {
+      int cnt = 0, q = p;
+      while (true) {
+        const int idx = wbase + lane;
+        const unsigned b = __ballot_sync(FULL, idx >= q && warr <= delta);
+        const int c = __popc(b);
+        if (c > 0 && cnt == 0) {
+          if (hvalid) {      // the waiting head goes back under the new batch
+            const int2 e = make_int2(hjob, harr);
+            stack[scount] = e; sstk[scount & (SCACHE - 1)] = e;
+            scount += 1;
+          }
+          HEAD_FROM_WINDOW(p - wbase);           // the batch's first job becomes the head (quirk Q2)
+        }
+        cnt += c; q += c;
+        if (q < wbase + 32 || q >= n) break;
+        wbase += 32;
+        LOAD_WINDOW();
+      }
+      if (cnt > 0) {
+        // jobs p+1 .. p+cnt-1 land under the new head, p+1 on top of them
+        const int m = cnt - 1;
+        for (int i = lane; i < m; i += 32) {
+          const int2 e = make_int2(p + cnt - 1 - i, delta);
+          stack[scount + i] = e;
+          if (i >= m - SCACHE) sstk[(scount + i) & (SCACHE - 1)] = e;
+        }
+        scount += m;
+        if (scount - cache_lo > SCACHE) cache_lo = scount - SCACHE;
+        if (top == 0) bottom_arr = delta;
+        hjob = p; harr = delta; hvalid = true;
+        top += cnt; p += cnt;
+        sum_arr += (long long)cnt * delta;
+        blocked = 0; changed = true;
+        __syncwarp();
+      }
+      next_arr = GS_INF;
+      if (p < n) next_arr = __shfl_sync(FULL, warr, p - wbase);
+    }
+    // ---------------- B. one scheduling attempt on the queue head (quirks Q1, Q3)
+    if (top > 0 && blocked) evals += M;           // the reference tries (and fails) on this tick too
+    if (top > 0 && !blocked) {
+      if (!hvalid) {         // the head was started or the launch just resumed: pop the stack
+        int2 e;
+        if (scount - 1 >= cache_lo) e = sstk[(scount - 1) & (SCACHE - 1)];
+        else e = stack[scount - 1];
+        scount -= 1;
+        if (cache_lo > scount) cache_lo = scount;
+        hjob = e.x; harr = e.y; hvalid = true;
+        if (hjob >= wbase && hjob < wbase + 32) {
+          HEAD_FROM_WINDOW(hjob - wbase);
+        } else {
+          const JobIn jr = jobs[hjob];
+          hpk = jr.gpus | (jr.gpc << 24);
+          hneed = need_of(jr.dur); if (!(jr.memb < fit_limit)) hneed = -hneed;
+          hmemc = (long long)jr.gpus * (jr.memb < cap_bytes ? jr.memb : cap_bytes);
+          if (NET) { hdur = jr.dur; hps = jr.ps; }
+        }
+      }
+      const int hg = hpk & 0xffffff, hgpc = (int)((unsigned)hpk >> 24);
+      const int htasks = hgpc == 1 ? hg : hg / hgpc;
+      const bool placeable = hneed > 0;            // Device.can_fit on an empty device
+      bool ok = false;
+      int nspans = 0, where = 0;
+      const int span_first = span_used;
+      unsigned long long mask0 = 0;
+      if (hg <= G) {
+        // try_single_node_alloc_ms: first node (id order) that fits the whole job
+        int found = -1;
+        for (int base = 0; base < M; base += 32) {
+          const int nd = base + lane;
+          bool fit = false;
+          if (nd < M) {
+            const unsigned mt = kk[nd];
+            fit = (int)(mt & 0xffu) >= hg && (int)(mt >> 16) >= htasks;
+          }
+          if (!placeable) {          // quirk Q21: cpu/mem charged for every task, never refunded
+            if (fit) kk[nd] -= (unsigned)htasks << 16;
+            continue;
+          }
+          const unsigned b = __ballot_sync(FULL, fit);
+          if (b) { found = base + __ffs(b) - 1; break; }
+        }
+        if (found >= 0 && span_used + 1 > span_cap) { status = GS_ERR_CAPACITY; found = -1; }
+        if (found >= 0) {
+          ok = true; nspans = 1;
+          const unsigned long long take = take_lowest(~busy[found] & gmask, hg, G);
+          const unsigned kv = kk[found];
+          __syncwarp();
+          if (lane == 0) {
+            busy[found] |= take;
+            kk[found] = (kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u;
+            gs_span sp; sp.node = found; sp.ntasks = htasks | (int)0x80000000; sp.devmask = take;
+            __stcs(reinterpret_cast<int4 *>(&spans[span_first]), *reinterpret_cast<const int4 *>(&sp));
+          }
+          mask0 = take;
+          where = found | ((htasks - 1) << 20);
+          ever += (kv & 0x100u) ? 0 : 1;
+          evals += found + 1;
+        } else {
+          evals += M;
+        }
+      } else {
+        // try_cross_node_alloc_ms: walk nodes in id order, each takes what it can hold
+        int cum = 0, last_base = -1;
+        if (placeable) {
+          for (int base = 0; base < M; base += 32) {
+            const int nd = base + lane;
+            const int c = (nd < M) ? meta_cap(kk[nd], hgpc) : 0;
+            cum += __reduce_add_sync(FULL, c);
+            if (cum >= htasks) { last_base = base; break; }
+          }
+        } else {
+          for (int base = 0; base < M; base += 32) {   // quirk Q21, cross-node flavour: one task charged per node
+            const int nd = base + lane;
+            if (nd < M && meta_cap(kk[nd], hgpc) > 0) kk[nd] -= 1u << 16;
+          }
+        }
+        if (last_base >= 0 && (long long)span_used + min(htasks, M) > (long long)span_cap) { status = GS_ERR_CAPACITY; last_base = -1; }
+        if (last_base >= 0) {
+          // pass 1 proved the job fits: commit (a failed walk is rolled back exactly by the
+          // reference, algorithm.py:378-387, so no state changes in that case)
+          ok = true;
+          int rem = htasks, last_node = 0;
+          for (int base = 0; base <= last_base; base += 32) {
+            const int nd = base + lane;
+            const int c = (nd < M) ? meta_cap(kk[nd], hgpc) : 0;
+            int incl = c;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            const int take = min(c, max(rem - (incl - c), 0));
+            const unsigned tb = __ballot_sync(FULL, take > 0);
+            bool fresh = false;
+            if (take > 0) {
+              const unsigned long long tk = take_lowest(~busy[nd] & gmask, take * hgpc, G);
+              busy[nd] |= tk;
+              const unsigned kv = kk[nd];
+              kk[nd] = (kv - (unsigned)(take * hgpc) - ((unsigned)take << 16)) | 0x100u;
+              fresh = !(kv & 0x100u);
+              const int slot = nspans + __popc(tb & ((1u << lane) - 1u));
+              gs_span sp; sp.node = nd; sp.ntasks = take | (slot == 0 ? (int)0x80000000 : 0); sp.devmask = tk;
+              __stcs(reinterpret_cast<int4 *>(&spans[span_first + slot]), *reinterpret_cast<const int4 *>(&sp));
+            }
+            ever += __popc(__ballot_sync(FULL, fresh));
+            if (tb) last_node = base + 31 - __clz(tb);
+            nspans += __popc(tb);
+            const int tot = __shfl_sync(FULL, incl, 31);
+            rem -= min(rem, tot);
+          }
+          where = (int)0x80000000 | span_first;
+          mask0 = (unsigned long long)(unsigned)nspans | ((unsigned long long)(unsigned)hg << 32);
+          evals += last_node + 1;
+        } else {
+          evals += M;
+        }
+      }
+      __syncwarp();
+      if (ok) {
+        // ---- commit: pop, network cost, start (algorithm.py:198-200, schedule.py:49-54,164-167)
+        const int j = hjob;
+        int need = hneed;
+        if (NET) {
+          double dur2 = hdur;
+          if (hps > 1) {
+            // (model_size/bandwidth + cross*latency) * (iterations*2.0), network_service.py:34-37
+            const double mps = __ddiv_rn(S.model_mb[j], S.bandwidth);
+            const double nis = __dmul_rn((double)nspans, S.latency);
+            const double rt = __dmul_rn(S.iters[j], 2.0);
+            dur2 = __dadd_rn(hdur, __dmul_rn(__dadd_rn(mps, nis), rt));
+          }
+          const double eff = dur2 > hdur ? dur2 : hdur;             // Job.get_duration (job.py:206-210)
+          need = need_of(eff);
+          S.dur2[j] = dur2;
+        }
+        if (need > wmask) { status = GS_ERR_ARG; need = wmask; }
+        const int endt = delta + need;
+        const int bk = endt & wmask;
+        span_used += nspans;
+        JobState2 js; js.where = where; js.mask0 = mask0; js.next = -1;
+        // push on the finish-tick bucket of the timing wheel (released in start order, see E)
+        if (endt < next_fin) { next_fin = endt; nf_head = j; nf_js = js; }
+        else if (endt == next_fin) { js.next = nf_head; nf_head = j; nf_js = js; }
+        else js.next = whead[bk];
+        const long long wm = wmem[bk];
+        if (lane == 0) {
+          whead[bk] = j;
+          wmem[bk] = wm + hmemc;
+          *reinterpret_cast<int4 *>(&jst[j]) = *reinterpret_cast<const int4 *>(&js);
+          __stcs(&rec2[j], make_int2(delta, need));
+        }
+        top -= 1;
+        sum_arr -= harr;
+        running += 1;
+        busy_gpus += hg;
+        mem_busy += hmemc;
+        hvalid = false; changed = true;
+        __syncwarp();
+      } else if (placeable) {
+        blocked = 1;           // nothing can change the outcome before a completion or a new head
+      }
+    }
+    // ---------------- D/E. time advances; release jobs whose finish tick is now
+    const int now = delta + 1;
+    if (next_fin == now) {
+      const int sl = now & wmask;
+      int ph = whead[(now + 1 + lane) & wmask];      // start looking for the following bucket right away
+      const long long wm = wmem[sl];
+      int h = nf_head;
+      JobState2 js = nf_js;
+      const int f0 = finished;
+      int c = 0;
+      while (true) {
+        if (js.where >= 0) {
+          const int nd = js.where & 0xfffff, nt = ((js.where >> 20) & 63) + 1;
+          if (lane == 0) { busy[nd] &= ~js.mask0; kk[nd] += (unsigned)__popcll(js.mask0) + ((unsigned)nt << 16); }
+          busy_gpus -= __popcll(js.mask0);
+        } else {
+          const int first = js.where & 0x7fffffff, scnt = (int)(unsigned)(js.mask0 & 0xffffffffull);
+          for (int i = lane; i < scnt; i += 32) {
+            const gs_span sp = spans[first + i];
+            busy[sp.node] &= ~sp.devmask;
+            kk[sp.node] += (unsigned)__popcll(sp.devmask) + ((unsigned)(sp.ntasks & 0x7fffffff) << 16);
+          }
+          busy_gpus -= (int)(unsigned)(js.mask0 >> 32);
+        }
+        if (lane == 0) fin[f0 + c] = h;
+        c += 1;
+        h = js.next;
+        if (h < 0) break;
+        js = jst[h];
+        __syncwarp();          // the next job may give devices back to the same node from another lane
+      }
+      finished += c; running -= c;
+      mem_busy -= wm;
+      if (lane == 0) { whead[sl] = -1; wmem[sl] = 0; }
+      __syncwarp();
+      if (c >= 2) {          // the bucket was walked newest first; job.csv lists equal finish ticks in start order
+        for (int i = lane; i < (c >> 1); i += 32) { const int a = fin[f0 + i], b2 = fin[f0 + c - 1 - i]; fin[f0 + i] = b2; fin[f0 + c - 1 - i] = a; }
+        __syncwarp();
+      }
+      next_fin = GS_INF; nf_head = -1;
+      if (running > 0) {
+        int base = now + 1;
+        while (true) {
+          const unsigned b = __ballot_sync(FULL, ph >= 0);
+          if (b) { const int pos = __ffs(b) - 1; next_fin = base + pos; nf_head = __shfl_sync(FULL, ph, pos); break; }
+          base += 32;
+          ph = whead[(base + lane) & wmask];
+        }
+        nf_js = jst[nf_head];
+      }
+      blocked = 0; changed = true;
+    }
+    // ---------------- H. statistics record (schedule.py:95-133) from O(1) counters
+    if (changed) {
+      int qidx = -1;
+      if (top > 0) {
+        // the queue is a stack with non-decreasing arrival ticks bottom->top, so the sorted pending
+        // list is the stack read top->bottom: median/max are index look-ups
+        const int ilo = top - 1 - ((top - 1) >> 1), ihi = top - 1 - (top >> 1);
+        int a_lo, a_hi;
+        if (hvalid && ilo == top - 1) a_lo = harr;
+        else a_lo = ilo >= cache_lo ? sstk[ilo & (SCACHE - 1)].y : stack[ilo].y;
+        if (hvalid && ihi == top - 1) a_hi = harr;
+        else a_hi = ihi >= cache_lo ? sstk[ihi & (SCACHE - 1)].y : stack[ihi].y;
+        qidx = nb;
+        if (lane == 0) {
+          __stcs(&rowB[2 * nb], make_int4((int)(sum_arr & 0xffffffffLL), (int)(sum_arr >> 32), bottom_arr, a_lo));
+          __stcs(&rowB[2 * nb + 1], make_int4(a_hi, 0, 0, 0));
+        }
+        nb += 1;
+      }
+      if (lane == 0) {
+        __stcs(&rowA[2 * na], make_int4(now, top, finished, busy_gpus | (running << 16)));
+        __stcs(&rowA[2 * na + 1], make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), ever, qidx));
+      }
+      na += 1;
+    }
+    delta = now;
+    done = (n - p) + running == 0;      // schedule.py:185 -- the queue is NOT counted (quirk Q4)
+  }
+#undef LOAD_WINDOW
+#undef HEAD_FROM_WINDOW
+
+  // ---------------- persist: the head goes back on the stack, node table back to global memory
+  __syncwarp();
+  if (hvalid) { if (lane == 0) stack[scount] = make_int2(hjob, harr); scount += 1; }
+  __syncwarp();
+  // jobs still queued have not started: their result record says so (start = -1), whatever ran before
+  for (int i = lane; i < scount; i += 32) rec2[stack[i].x] = make_int2(-1, 0);
+  {
+    const int K = S.K;
+    for (int i = lane; i < M; i += 32) {
+      const unsigned mt = kk[i];
+      S.nbusy[i] = busy[i];
+      S.nk[i] = (int)((unsigned)(K - (int)(mt >> 16)) | ((mt & 0x100u) ? EVER_BIT : 0u));
+    }
+  }
+  if (lane == 0) {
+    S.delta = delta; S.p = p; S.top = top; S.running = running; S.finished = finished;
+    S.ever = ever; S.busy_gpus = busy_gpus; S.mem_busy = mem_busy; S.sum_arr = sum_arr;
+    S.span_used = span_used; S.started = (long long)finished + running;
+    S.events = (long long)p + finished + running + finished; S.evals = evals;
+    S.ticks = delta; S.row_first = delta0; S.nev = na; S.nq = nb; S.blocked = blocked;
+    S.done = done ? 1 : 0; S.status = status; S.need_init = 0;
+  }
+}
+
+// ------------------------------------------------------------------ record -> row expansion
+// One thread per event record: it writes the gs_tick_row of its own tick and of every jumped tick up to
+// the next record (on those only `now` and the pending statistics move, linearly in the tick number).
+__global__ void gs_expand_rows_kernel(const SimDev *sims, int sim, int M, int G, gs_tick_row *__restrict__ out) {
+  const SimDev &S = sims[sim];
+  const int na = S.nev;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= na) return;
+  const int4 *rowA = reinterpret_cast<const int4 *>(S.evrows), *rowB = reinterpret_cast<const int4 *>(S.qrows);
+  const int4 a0 = rowA[2 * k], a1 = rowA[2 * k + 1];
+  const int t_first = a0.x;                                            // `now` of this record
+  const int t_last = (k + 1 < na) ? rowA[2 * (k + 1)].x - 1 : (int)S.ticks;   // last `now` this record covers
+  const int queued = a0.y, busy_gpus = a0.w & 0xffff, running = (int)((unsigned)a0.w >> 16);
+  long long sum_arr = 0; int bottom = 0, a_lo = 0, a_hi = 0;
+  if (a1.w >= 0) {
+    const int4 b0 = rowB[2 * a1.w], b1 = rowB[2 * a1.w + 1];
+    sum_arr = (long long)(((unsigned long long)(unsigned)b0.y << 32) | (unsigned)b0.x);
+    bottom = b0.z; a_lo = b0.w; a_hi = b1.x;
+  }
+  const long long row0 = S.row_first;                                  // tick index of the window's first row
+  for (int v = t_first; v <= t_last; ++v) {
+    int4 *dst = reinterpret_cast<int4 *>(&out[(long long)v - 1 - row0]);
+    const long long ps = queued > 0 ? (long long)queued * v - sum_arr : 0;
+    dst[0] = make_int4(v, M - a1.z, a1.z, busy_gpus);
+    dst[1] = make_int4(M * G - busy_gpus, running, queued, a0.z);
+    dst[2] = make_int4(a1.x, a1.y, (int)(ps & 0xffffffffLL), (int)(ps >> 32));
+    dst[3] = queued > 0 ? make_int4(v - bottom, v - a_lo, v - a_hi, 0) : make_int4(0, 0, 0, 0);
+  }
+}
+
+// Legacy gs_job_rec view of the compact per-job result {start, run length}: fifo never preempts, so
+// end = start + run length, jct = run length, preempt (migration_count) = 1 (quirk Q12).
+__global__ void gs_expand_jobs_kernel(const SimDev *sims, int sim, gs_job_rec *__restrict__ out) {
+  const SimDev &S = sims[sim];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= S.n) return;
+  gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0;
+  r.duration = S.jobs[j].dur;
+  if (j < S.p) {
+    const int2 v = S.rec2[j];
+    if (v.x >= 0) {
+      r.start = v.x; r.end = v.x + v.y; r.jct = v.y; r.preempt = 1;
+      if (S.netcost) r.duration = S.dur2[j];
+    }
+  }
+  out[j] = r;
+}

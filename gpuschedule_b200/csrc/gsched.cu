@@ -13,10 +13,13 @@
 //     pending-time aging, time_processed stepping) are replaced by closed
 //     forms and O(1) incremental counters; completions come from a timing
 //     wheel keyed by finish tick, appended in start order.
-//   * every tick emits one 64-byte gs_tick_row of integer aggregates; the job
-//     table is streamed once from HBM (arrival-ordered SoA), results are
-//     written once (24-byte gs_job_rec + 16-byte gs_span per (job,node)).
-//   * thousands of replicas run per launch (one warp each, 148 SMs x many
+//   * the loop is event stepped: ticks on which nothing arrives, starts or
+//     finishes are jumped over; every other tick leaves one 32-byte record of
+//     integer aggregates (+ one for the queue while it is non-empty) from which
+//     the 64-byte gs_tick_row of EVERY tick is rebuilt on demand; the job table
+//     is streamed once from HBM, results are written once (8-byte gs_job_run +
+//     16-byte gs_span per (job,node) + finish order).
+//   * thousands of replicas run per launch (one warp each, 148 SMs x 32
 //     warps); a single replica is latency bound by construction.
 //
 // Reference semantics followed (paths relative to the reference root):
@@ -42,8 +45,7 @@
 #include "gsched.h"
 
 #include "gs_common.cuh"
-#include "gs_tick_warp.cuh"
-#include "gs_tick_lane.cuh"
+#include "gs_tick2.cuh"
 #include "gs_policy.cuh"
 #include "gs_aux.cuh"
 
@@ -58,28 +60,29 @@ struct SimHost {
   void *state_slab = nullptr;
   void *git_dev = nullptr;
   size_t trace_bytes = 0, state_bytes = 0;
-  int64_t span_cap = 0, rows_cap = 0, last_arrive = 0;
+  int64_t span_cap = 0, rows_cap = 0, qrows_cap = 0, last_arrive = 0;
   int max_need = 1;
   SimDev dev;
 };
 
 struct gs_engine {
   int device = 0, nsims = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  void *d_scratch2 = nullptr;
-  size_t d_scratch2_bytes = 0;
   std::vector<SimHost> sims;
   SimDev *d_sims = nullptr;
   void *h_stage = nullptr;
   size_t h_stage_bytes = 0;
   void *d_scratch = nullptr;
   size_t d_scratch_bytes = 0;
+  std::vector<SimDev> h_back;   // pinned-size-stable host mirror used by gs_run
   std::string err;
   double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
   long long launches = 0;  // kernels launched by this handle
-  int engine_mode = 0;     // 0 auto, 1 warp-per-replica, 2 lane-per-replica, 3 half-warp-per-replica
+  int engine_mode = 0;     // event-driven policies: 0 warp-cooperative kernels, 2 one thread per replica
   double span_budget = 0;  // > 0: span pool = min(worst case, budget * n + 4096) records per replica
+  int64_t qrows_cap = 0;   // 0: same as rows_cap
+  bool async = false;      // gs_set_async
   bool dirty = true;       // host mirror of SimDev newer than device copy
 };
 
@@ -124,9 +127,8 @@ extern "C" int gs_create(int device, int nsims, gs_handle *out) {
   h->device = device;
   h->nsims = nsims;
   h->sims.resize((size_t)nsims);
+  h->h_back.resize((size_t)nsims);
   cudaError_t e1 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  cudaError_t e1b = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-  (void)e1b;
   cudaError_t e2 = cudaEventCreate(&h->e0);
   cudaError_t e3 = cudaEventCreate(&h->e1);
   cudaError_t e4 = cudaMalloc(&h->d_sims, sizeof(SimDev) * (size_t)nsims);
@@ -141,6 +143,7 @@ extern "C" int gs_create(int device, int nsims, gs_handle *out) {
 extern "C" void gs_destroy(gs_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &s : h->sims) { if (s.trace_slab) cudaFree(s.trace_slab); if (s.state_slab) cudaFree(s.state_slab); if (s.git_dev) cudaFree(s.git_dev); }
   if (h->d_sims) cudaFree(h->d_sims);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -148,8 +151,6 @@ extern "C" void gs_destroy(gs_handle h) {
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   if (h->stream) cudaStreamDestroy(h->stream);
-  if (h->stream2) cudaStreamDestroy(h->stream2);
-  if (h->d_scratch2) cudaFree(h->d_scratch2);
   delete h;
 }
 
@@ -182,6 +183,10 @@ extern "C" int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, co
     return fail(h, GS_ERR_ARG, "gs_config_sim: unknown scheme");
   if (pol.schedule == GS_SCHED_FIFO && pol.scheme != GS_SCHEME_YARN)
     return fail(h, GS_ERR_ARG, "gs_config_sim: fifo runs with the yarn scheme only");
+  if (pol.schedule == GS_SCHED_FIFO &&
+      ((long long)cluster->num_switch * cluster->num_node_p_switch * cluster->num_gpu_p_node > 65535 ||
+       (long long)cluster->num_cpu_p_node / cluster->cpu_per_task > 32767))
+    return fail(h, GS_ERR_ARG, "gs_config_sim: the fifo engine packs its counters for clusters of at most 65535 GPUs");
   if ((pol.schedule == GS_SCHED_DLAS || pol.schedule == GS_SCHED_DLAS_GPU) &&
       (pol.num_queue < 1 || pol.num_queue > GS_MAX_QUEUES))
     return fail(h, GS_ERR_ARG, "gs_config_sim: num_queue must be in 1..8 for dlas");
@@ -202,88 +207,30 @@ extern "C" int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, co
   s.pol = pol;
   s.pol.gittins_data = s.pol.gittins_index = nullptr;   // host pointers are not retained past this call
   s.loaded = false;       // load-time bounds (max_need, span_cap) depend on the cluster: a reconfigured replica needs its trace again
-  h->dirty = true;
   s.configured = true;
+  h->dirty = true;
   return GS_OK;
 }
 
 static int ensure_stage(gs_handle h, size_t bytes) {
   if (h->h_stage_bytes >= bytes) return GS_OK;
-  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_stage) { cudaStreamSynchronize(h->stream); cudaFreeHost(h->h_stage); }
   h->h_stage = nullptr; h->h_stage_bytes = 0;
   CU(cudaMallocHost(&h->h_stage, bytes));
   h->h_stage_bytes = bytes;
   return GS_OK;
 }
 
-// Shared tail of the two loaders: `ji` already holds n validated JobIn records in the pinned
-// staging buffer (plus the optional network columns); bounds are known.
-static int finish_load(gs_handle h, SimHost &s, int64_t n, bool net, size_t off_model, size_t off_iters, size_t total,
-                       int64_t span_cap, double max_need, int64_t last_arrive) {
-  if (max_need > (double)(1 << 26)) return fail(h, GS_ERR_ARG, "gs_load_trace: job duration exceeds 2^26 ticks");
-  unsigned char *st = (unsigned char *)h->h_stage;
-  if (s.trace_slab && s.trace_bytes < total) { cudaFree(s.trace_slab); s.trace_slab = nullptr; }
-  if (!s.trace_slab) { CU(cudaMalloc(&s.trace_slab, total)); s.trace_bytes = total; }
-  CU(cudaEventRecord(h->e0, h->stream));
-  CU(cudaMemcpyAsync(s.trace_slab, st, total, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaEventRecord(h->e1, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
-  h->h2d_ms += ms;
-  unsigned char *d = (unsigned char *)s.trace_slab;
-  SimDev &D = s.dev;
-  memset(&D, 0, sizeof(D));
-  D.jobs = (const JobIn *)d;
-  D.model_mb = net ? (const double *)(d + off_model) : nullptr;
-  D.iters = net ? (const double *)(d + off_iters) : nullptr;
-  if (h->span_budget > 0) {
-    const int64_t lim = (int64_t)(h->span_budget * (double)n) + 4096;
-    if (span_cap > lim) span_cap = lim;
-  }
-  s.n = n; s.span_cap = span_cap > 0 ? span_cap : 1;
-  s.max_need = (int)max_need + 2;
-  s.last_arrive = last_arrive;
-  s.loaded = true;
-  s.prepared = false;      // (re)loading a trace restarts the replica; slabs are reused when big enough
-  h->dirty = true;
-  return GS_OK;
-}
-
-static int load_common(gs_handle h, int sim, int64_t n, const JobIn *packed, const int32_t *arrive_tick,
-                       const int32_t *gpus, const int32_t *gpu_per_task, const double *duration,
-                       const int64_t *mem_bytes, const double *model_mb, const double *iterations,
-                       const int32_t *ps_count) {
-  if (!h) return GS_ERR_ARG;
-  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_load_trace: sim index out of range");
-  SimHost &s = h->sims[(size_t)sim];
-  if (!s.configured) return fail(h, GS_ERR_STATE, "gs_load_trace: call gs_config_sim first");
-  if (n < 0 || n >= (1ll << 31) - 64) return fail(h, GS_ERR_ARG, "gs_load_trace: n out of range");
-  if (n > 0 && !packed && (!arrive_tick || !gpus || !gpu_per_task || !duration || !mem_bytes))
-    return fail(h, GS_ERR_ARG, "gs_load_trace: NULL column");
-  const bool net = model_mb && iterations && (packed || ps_count);
+// Validation + load-time bounds over n packed records (read only).
+static int scan_trace(gs_handle h, const SimHost &s, int64_t n, const JobIn *ji, bool net, const double *model_mb,
+                      const double *iterations, int64_t *span_cap_out, double *max_need_out) {
   const int M = s.cl.num_switch * s.cl.num_node_p_switch;
-  CU(cudaSetDevice(h->device));
-  const size_t N = (size_t)(n > 0 ? n : 1);
-  const size_t off_model = align_up(sizeof(JobIn) * N), off_iters = align_up(off_model + (net ? 8 * N : 0));
-  const size_t total = align_up(off_iters + (net ? 8 * N : 0));
-  int rc = ensure_stage(h, total);
-  if (rc) return rc;
-  unsigned char *st = (unsigned char *)h->h_stage;
-  JobIn *ji = (JobIn *)st;
-  if (packed) memcpy(ji, packed, sizeof(JobIn) * (size_t)n);
-  // one pass: (pack,) validate, bounds
+  const bool netcost = net && s.cl.enable_network_costs;
   int64_t span_cap = 0;
   double max_need = 1.0;
   int prev = 0;
-  const bool netcost = net && s.cl.enable_network_costs;
   for (int64_t j = 0; j < n; ++j) {
-    JobIn r;
-    if (packed) r = ji[j];
-    else {
-      r.arrive = arrive_tick[j]; r.gpus = gpus[j]; r.gpc = gpu_per_task[j]; r.ps = net ? ps_count[j] : 0;
-      r.memb = mem_bytes[j]; r.dur = duration[j];
-      ji[j] = r;
-    }
+    const JobIn r = ji[j];
     if (r.arrive < prev) return fail(h, GS_ERR_ARG, "gs_load_trace: arrive_tick must be non-negative and non-decreasing");
     prev = r.arrive;
     if (r.gpc <= 0 || r.gpus < r.gpc || r.gpus % r.gpc != 0 || r.gpus >= (1 << 24) || r.gpc > 255)
@@ -300,11 +247,88 @@ static int load_common(gs_handle h, int sim, int64_t n, const JobIn *packed, con
     }
     if (d > max_need) max_need = d;
   }
-  if (net && n > 0) {
-    memcpy(st + off_model, model_mb, 8 * (size_t)n);
-    memcpy(st + off_iters, iterations, 8 * (size_t)n);
+  *span_cap_out = span_cap; *max_need_out = max_need;
+  return GS_OK;
+}
+
+static int load_common(gs_handle h, int sim, int64_t n, const JobIn *packed, const int32_t *arrive_tick,
+                       const int32_t *gpus, const int32_t *gpu_per_task, const double *duration,
+                       const int64_t *mem_bytes, const double *model_mb, const double *iterations,
+                       const int32_t *ps_count) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_load_trace: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.configured) return fail(h, GS_ERR_STATE, "gs_load_trace: call gs_config_sim first");
+  if (n < 0 || n >= (1ll << 31) - 64) return fail(h, GS_ERR_ARG, "gs_load_trace: n out of range");
+  if (n > 0 && !packed && (!arrive_tick || !gpus || !gpu_per_task || !duration || !mem_bytes))
+    return fail(h, GS_ERR_ARG, "gs_load_trace: NULL column");
+  const bool net = model_mb && iterations && (packed || ps_count);
+  CU(cudaSetDevice(h->device));
+  const size_t N = (size_t)(n > 0 ? n : 1);
+  const size_t off_model = align_up(sizeof(JobIn) * N), off_iters = align_up(off_model + (net ? 8 * N : 0));
+  const size_t total = align_up(off_iters + (net ? 8 * N : 0));
+  // asynchronous path: packed records in page-locked caller memory go to the device without staging
+  bool direct = false;
+  if (h->async && packed && !net && n > 0) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, packed) == cudaSuccess && at.type == cudaMemoryTypeHost) direct = true;
+    else (void)cudaGetLastError();
   }
-  return finish_load(h, s, n, net, off_model, off_iters, total, span_cap, max_need, n > 0 ? ji[n - 1].arrive : 0);
+  const JobIn *ji = packed;
+  if (!direct) {
+    CU(cudaStreamSynchronize(h->stream));         // the staging buffer may still feed an earlier upload
+    int rc = ensure_stage(h, total);
+    if (rc) return rc;
+    unsigned char *st = (unsigned char *)h->h_stage;
+    JobIn *dst = (JobIn *)st;
+    if (packed) memcpy(dst, packed, sizeof(JobIn) * (size_t)n);
+    else
+      for (int64_t j = 0; j < n; ++j) {
+        JobIn r;
+        r.arrive = arrive_tick[j]; r.gpus = gpus[j]; r.gpc = gpu_per_task[j]; r.ps = net ? ps_count[j] : 0;
+        r.memb = mem_bytes[j]; r.dur = duration[j];
+        dst[j] = r;
+      }
+    if (net && n > 0) {
+      memcpy(st + off_model, model_mb, 8 * (size_t)n);
+      memcpy(st + off_iters, iterations, 8 * (size_t)n);
+    }
+    ji = dst;
+  }
+  int64_t span_cap = 0;
+  double max_need = 1.0;
+  int rc = scan_trace(h, s, n, ji, net, model_mb, iterations, &span_cap, &max_need);
+  if (rc) return rc;
+  if (max_need > (double)(1 << 26)) return fail(h, GS_ERR_ARG, "gs_load_trace: job duration exceeds 2^26 ticks");
+  if (s.trace_slab && s.trace_bytes < total) { CU(cudaStreamSynchronize(h->stream)); cudaFree(s.trace_slab); s.trace_slab = nullptr; }
+  if (!s.trace_slab) { CU(cudaMalloc(&s.trace_slab, total)); s.trace_bytes = total; }
+  if (direct) {
+    CU(cudaMemcpyAsync(s.trace_slab, packed, sizeof(JobIn) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CU(cudaEventRecord(h->e0, h->stream));
+    CU(cudaMemcpyAsync(s.trace_slab, h->h_stage, total, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->e1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+    h->h2d_ms += ms;
+  }
+  unsigned char *d = (unsigned char *)s.trace_slab;
+  SimDev &D = s.dev;
+  memset(&D, 0, sizeof(D));
+  D.jobs = (const JobIn *)d;
+  D.model_mb = net ? (const double *)(d + off_model) : nullptr;
+  D.iters = net ? (const double *)(d + off_iters) : nullptr;
+  if (h->span_budget > 0) {
+    const int64_t lim = (int64_t)(h->span_budget * (double)n) + 4096;
+    if (span_cap > lim) span_cap = lim;
+  }
+  s.n = n; s.span_cap = span_cap > 0 ? span_cap : 1;
+  s.max_need = (int)max_need + 2;
+  s.last_arrive = n > 0 ? ji[n - 1].arrive : 0;
+  s.loaded = true;
+  s.prepared = false;      // (re)loading a trace restarts the replica; slabs are reused when big enough
+  h->dirty = true;
+  return GS_OK;
 }
 
 extern "C" int gs_load_trace(gs_handle h, int sim, int64_t n, const int32_t *arrive_tick, const int32_t *gpus,
@@ -326,43 +350,63 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
   const gs_cluster &c = s.cl;
   const int M = c.num_switch * c.num_node_p_switch;
   const size_t N = (size_t)(s.n > 0 ? s.n : 1);
-  int W = 256; while (W < s.max_need + 1) W <<= 1;    // >= 2x the lane engine's shared-memory window
+  int W = 256; while (W < s.max_need + 1) W <<= 1;
   if (rows_cap <= 0) rows_cap = s.last_arrive + 2ll * s.max_need + 4096;
-  size_t o_rec = 0, o_jst = align_up(o_rec + sizeof(gs_job_rec) * N), o_stack = align_up(o_jst + sizeof(JobState) * N);
-  size_t o_fin = align_up(o_stack + 8 * N), o_sref = align_up(o_fin + 4 * N), o_wh = align_up(o_sref + 8 * N), o_wt = align_up(o_wh + 4 * (size_t)W);
-  size_t o_spans = align_up(o_wt + 4 * (size_t)W), o_rows = align_up(o_spans + sizeof(gs_span) * (size_t)s.span_cap);
-  size_t o_nb = align_up(o_rows + sizeof(gs_tick_row) * (size_t)rows_cap), o_nk = align_up(o_nb + 8 * (size_t)M);
-  size_t total = align_up(o_nk + 4 * (size_t)M);
-  const bool evd = s.pol.schedule != GS_SCHED_FIFO;        // event-driven policy: extra scratch
-  const size_t nql = (size_t)(s.pol.num_queue > 2 ? s.pol.num_queue : 2);
-  size_t o_pj = total, o_run = 0, o_q = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0, o_stale = 0;
+  int64_t qrows_cap = h->qrows_cap > 0 ? h->qrows_cap : rows_cap;
+  const bool evd = s.pol.schedule != GS_SCHED_FIFO;        // event-driven policy: rows + extra scratch
+  const bool net = c.enable_network_costs != 0;
+  size_t total = 0;
+  auto take = [&](size_t bytes) { const size_t o = total; total = align_up(total + bytes); return o; };
+  size_t o_rec = 0, o_rec2 = 0, o_dur2 = 0, o_jst = 0, o_stack = 0, o_wh = 0, o_wm = 0, o_spans = 0, o_rows = 0, o_ev = 0, o_q = 0, o_nb = 0, o_nk = 0;
+  const size_t o_fin = take(4 * N);
   if (evd) {
-    o_run = align_up(o_pj + sizeof(PJob) * N); o_q = align_up(o_run + 4 * N); o_end = align_up(o_q + 4 * N * nql);
-    o_tmp = align_up(o_end + 4 * N); o_ci = align_up(o_tmp + 4 * N); o_ck = align_up(o_ci + 4 * (size_t)M);
-    o_stale = align_up(o_ck + 4 * (size_t)M);
-    total = align_up(o_stale + 4 * N);
+    o_rec = take(sizeof(gs_job_rec) * N);
+    o_rows = take(sizeof(gs_tick_row) * (size_t)rows_cap);
+  } else {
+    o_rec2 = take(8 * N);
+    if (net) o_dur2 = take(8 * N);
+    o_jst = take(sizeof(JobState2) * N);
+    o_stack = take(8 * (N + 1));
+    o_wh = take(4 * (size_t)W); o_wm = take(8 * (size_t)W);
+    o_spans = take(sizeof(gs_span) * (size_t)s.span_cap);
+    o_ev = take(sizeof(gs_evrow) * (size_t)rows_cap);
+    o_q = take(sizeof(gs_qrow) * (size_t)qrows_cap);
+    o_nb = take(8 * (size_t)M); o_nk = take(4 * (size_t)M);
   }
-  if (s.state_slab && s.state_bytes < total) { cudaFree(s.state_slab); s.state_slab = nullptr; }
+  const size_t nql = (size_t)(s.pol.num_queue > 2 ? s.pol.num_queue : 2);
+  size_t o_pj = 0, o_run = 0, o_qs = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0, o_stale = 0;
+  if (evd) {
+    o_pj = take(sizeof(PJob) * N); o_run = take(4 * N); o_qs = take(4 * N * nql); o_end = take(4 * N);
+    o_tmp = take(4 * N); o_ci = take(4 * (size_t)M); o_ck = take(4 * (size_t)M); o_stale = take(4 * N);
+  }
+  if (s.state_slab && s.state_bytes < total) { CU(cudaStreamSynchronize(h->stream)); cudaFree(s.state_slab); s.state_slab = nullptr; }
   if (!s.state_slab) { CU(cudaMalloc(&s.state_slab, total)); s.state_bytes = total; }
   unsigned char *d = (unsigned char *)s.state_slab;
   SimDev &D = s.dev;
   D.M = M; D.G = c.num_gpu_p_node;
   int kc = c.num_cpu_p_node / c.cpu_per_task, km = c.mem_p_node / c.mem_per_task;
   D.K = kc < km ? kc : km;
-  D.netcost = c.enable_network_costs ? 1 : 0;
+  D.netcost = net ? 1 : 0;
   D.n = (int)s.n; D.wheel_mask = W - 1; D.policy = s.pol.schedule;
   D.cap_bytes = (long long)c.gpu_mem_cap_mib << 20;
   D.fit_limit = D.cap_bytes - ((long long)500 << 20);      // cap - mem > 500 MiB  (device.py:75)
   D.bandwidth = c.bandwidth; D.latency = c.internode_latency;
-  D.rec = (gs_job_rec *)(d + o_rec); D.jst = (JobState *)(d + o_jst);
-  D.stack = (int *)(d + o_stack); D.fin = (int *)(d + o_fin); D.sref = (int2 *)(d + o_sref);
-  D.wheel_head = (int *)(d + o_wh); D.wheel_tail = (int *)(d + o_wt);
-  D.spans = (gs_span *)(d + o_spans); D.rows = (gs_tick_row *)(d + o_rows);
-  D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
-  D.span_cap = s.span_cap; D.rows_cap = rows_cap;
-  s.rows_cap = rows_cap;
+  D.fin = (int *)(d + o_fin);
+  D.rec = nullptr; D.rows = nullptr; D.rec2 = nullptr; D.dur2 = nullptr; D.jst2 = nullptr; D.stack = nullptr;
+  D.wheel_head = nullptr; D.wheel_mem = nullptr; D.spans = nullptr; D.evrows = nullptr; D.qrows = nullptr; D.nbusy = nullptr; D.nk = nullptr;
   if (evd) {
-    D.pj = (PJob *)(d + o_pj); D.runnable = (int *)(d + o_run); D.queues = (int *)(d + o_q);
+    D.rec = (gs_job_rec *)(d + o_rec); D.rows = (gs_tick_row *)(d + o_rows);
+  } else {
+    D.rec2 = (int2 *)(d + o_rec2); D.dur2 = net ? (double *)(d + o_dur2) : nullptr;
+    D.jst2 = (JobState2 *)(d + o_jst); D.stack = (int *)(d + o_stack);
+    D.wheel_head = (int *)(d + o_wh); D.wheel_mem = (long long *)(d + o_wm);
+    D.spans = (gs_span *)(d + o_spans); D.evrows = (gs_evrow *)(d + o_ev); D.qrows = (gs_qrow *)(d + o_q);
+    D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
+  }
+  D.span_cap = s.span_cap; D.rows_cap = rows_cap; D.qrows_cap = qrows_cap;
+  s.rows_cap = rows_cap; s.qrows_cap = qrows_cap;
+  if (evd) {
+    D.pj = (PJob *)(d + o_pj); D.runnable = (int *)(d + o_run); D.queues = (int *)(d + o_qs);
     D.endj = (int *)(d + o_end); D.tmpl = (int *)(d + o_tmp); D.cidle = (int *)(d + o_ci); D.ckfree = (int *)(d + o_ck);
     D.stalej = (int *)(d + o_stale); D.stale_n = 0;
     D.num_queue = s.pol.num_queue > 0 ? s.pol.num_queue : 1;
@@ -374,6 +418,7 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
     D.rn = 0; D.en = 0; D.end_time = 0x7fffffff; D.next_job_jump = 0x7fffffff;
   }
   D.delta = D.p = D.top = D.running = D.finished = D.ever = D.busy_gpus = D.done = D.status = 0;
+  D.blocked = D.nev = D.nq = 0;
   D.mem_busy = D.sum_arr = D.span_used = D.events = D.evals = D.started = D.ticks = D.row_first = 0;
   D.need_init = 1;
   s.prepared = true;
@@ -390,42 +435,31 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
     int M = s.cl.num_switch * s.cl.num_node_p_switch;
     if (M > maxM) maxM = M;
   }
-  bool any_init = false;
+  bool any_fifo = false, any_fifo_net = false, any_evd = false, evd_init = false;
+  for (auto &s : h->sims) {
+    if (s.pol.schedule == GS_SCHED_FIFO) { if (s.cl.enable_network_costs) any_fifo_net = true; else any_fifo = true; }
+    else { any_evd = true; evd_init |= s.dev.need_init != 0; }
+  }
   if (h->dirty) {
-    std::vector<SimDev> tmp((size_t)h->nsims);
-    for (int i = 0; i < h->nsims; ++i) { tmp[(size_t)i] = h->sims[(size_t)i].dev; any_init |= tmp[(size_t)i].need_init != 0; }
-    CU(cudaMemcpyAsync(h->d_sims, tmp.data(), sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < h->nsims; ++i) h->h_back[(size_t)i] = h->sims[(size_t)i].dev;
+    CU(cudaMemcpyAsync(h->d_sims, h->h_back.data(), sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->dirty = false;
   }
-  int maxG = 1;
-  bool any_fifo = false, any_evd = false;
-  for (auto &s : h->sims) {
-    if (s.cl.num_gpu_p_node > maxG) maxG = s.cl.num_gpu_p_node;
-    if (s.pol.schedule == GS_SCHED_FIFO) any_fifo = true; else any_evd = true;
-  }
-  const size_t lane_words = (size_t)maxM * (maxG > 32 ? 3 : 2) + LANE_EXTRA_WORDS;
-  int L = 32;
-  while (L > 1 && lane_words * (size_t)L * 4 > 100 * 1024) L >>= 1;
-  const size_t lane_smem = lane_words * (size_t)L * 4;
-  bool use_lane = h->engine_mode == 2;   // auto == warp mapping (measured faster at every replica count that fits HBM)
-  if (use_lane && lane_smem > 200 * 1024) {
-    if (h->engine_mode == 2) return fail(h, GS_ERR_ARG, "gs_run: node table too large for the lane engine");
-    use_lane = false;
-  }
   CU(cudaEventRecord(h->e0, h->stream));
-  if (any_init) {      // state reset is part of the timed engine work
-    gs_init_kernel<<<dim3(16, (unsigned)h->nsims), 256, 0, h->stream>>>(h->d_sims, h->nsims);
-    CU(cudaGetLastError());
-    h->launches += 1;
-  }
   if (any_evd) {
-    // dlas / dlas-gpu: one warp per replica; sjf / gittins (and everything with engine mode 2): one thread per replica
-    const int thread_dlas = h->engine_mode == 2 ? 1 : 0;
-    gs_policy_kernel<<<(unsigned)((h->nsims + 31) / 32), 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, thread_dlas);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    if (!thread_dlas) {
+    if (evd_init) {      // state reset is part of the timed engine work
+      gs_init_kernel<<<dim3(16, (unsigned)h->nsims), 256, 0, h->stream>>>(h->d_sims, h->nsims);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    }
+    // engine mode 2: one thread per replica (first version); default: one warp per replica
+    const int thread_map = h->engine_mode == 2 ? 1 : 0;
+    if (thread_map) {
+      gs_policy_kernel<<<(unsigned)((h->nsims + 31) / 32), 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, 1);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    } else {
       gs_dlas_warp_kernel<<<(unsigned)h->nsims, 32, 0, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks);
       CU(cudaGetLastError());
       const size_t pol_smem = 8 * (size_t)maxM;
@@ -436,47 +470,32 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
       h->launches += 2;
     }
   }
-  if (!any_fifo) {
-    // nothing for the tick kernels
-  } else if (use_lane) {
-    const unsigned grid = (unsigned)((h->nsims + L - 1) / L);
-    if (maxG > 32) {
-      if (lane_smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(gs_lane_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
-      gs_lane_kernel<unsigned long long><<<grid, 32, lane_smem, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, maxM, L);
-    } else {
-      if (lane_smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(gs_lane_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
-      gs_lane_kernel<uint32_t><<<grid, 32, lane_smem, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, maxM, L);
-    }
-  } else {
+  if (any_fifo || any_fifo_net) {
     const int stride = (int)align_up((size_t)maxM * 12 + 8 + SCACHE * 8, 16);
     if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
-    if (2 * stride > 48 * 1024)
-    {
-      CU(cudaFuncSetAttribute(gs_tick_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
-      CU(cudaFuncSetAttribute(gs_tick_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * stride));
+    if (any_fifo) {
+      if (stride > 48 * 1024) CU(cudaFuncSetAttribute(gs_tick2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
+      gs_tick2_kernel<false><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+      CU(cudaGetLastError());
+      h->launches += 1;
     }
-    int sub = 32;
-    if (h->engine_mode == 3) sub = 16;
-    if (sub == 16)
-      gs_tick_kernel<16><<<(unsigned)((h->nsims + 1) / 2), 32, (size_t)stride * 2, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
-    else
-      gs_tick_kernel<32><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+    if (any_fifo_net) {
+      if (stride > 48 * 1024) CU(cudaFuncSetAttribute(gs_tick2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
+      gs_tick2_kernel<true><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    }
   }
-  CU(cudaGetLastError());
-  if (any_fifo) h->launches += 1;
   CU(cudaEventRecord(h->e1, h->stream));
-  std::vector<SimDev> back((size_t)h->nsims);
-  CU(cudaMemcpyAsync(back.data(), h->d_sims, sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->h_back.data(), h->d_sims, sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
   h->kernel_ms += ms;
   int worst = 0;
   for (int i = 0; i < h->nsims; ++i) {
-    back[(size_t)i].need_init = 0;
-    h->sims[(size_t)i].dev = back[(size_t)i];
-    if (back[(size_t)i].status != 0 && worst == 0) worst = back[(size_t)i].status;
+    h->h_back[(size_t)i].need_init = 0;
+    h->sims[(size_t)i].dev = h->h_back[(size_t)i];
+    if (h->h_back[(size_t)i].status != 0 && worst == 0) worst = h->h_back[(size_t)i].status;
   }
   if (worst != 0) return fail(h, worst, "gs_run: a replica stopped with an in-kernel error (see gs_stats.status)");
   return GS_OK;
@@ -490,6 +509,67 @@ extern "C" int gs_stats(gs_handle h, int sim, gs_run_stats *out) {
   out->ticks = D.ticks; out->events = D.events; out->finished = D.finished; out->started = D.started;
   out->placement_evals = D.evals; out->done = D.done; out->status = D.status;
   out->kernel_ms = h->kernel_ms; out->h2d_ms = h->h2d_ms; out->d2h_ms = h->d2h_ms;
+  return GS_OK;
+}
+
+extern "C" int gs_window(gs_handle h, int sim, gs_window_info *out) {
+  if (!h || !out) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_window: sim index out of range");
+  const SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_window: nothing has run yet");
+  const SimDev &D = s.dev;
+  out->row_first = D.row_first; out->ticks = D.ticks;
+  const bool fifo = s.pol.schedule == GS_SCHED_FIFO;
+  out->ev_rows = fifo ? D.nev : 0; out->q_rows = fifo ? D.nq : 0;
+  out->spans_used = D.span_used; out->admitted = D.p; out->finished = D.finished; out->n = s.n;
+  return GS_OK;
+}
+
+extern "C" int gs_sync(gs_handle h) {
+  if (!h) return GS_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return GS_OK;
+}
+
+extern "C" int gs_set_async(gs_handle h, int on) {
+  if (!h) return GS_ERR_ARG;
+  h->async = on != 0;
+  return GS_OK;
+}
+
+extern "C" int gs_set_queue_rows_cap(gs_handle h, int64_t qrows_cap) {
+  if (!h) return GS_ERR_ARG;
+  if (qrows_cap < 0) return fail(h, GS_ERR_ARG, "gs_set_queue_rows_cap: must be >= 0");
+  h->qrows_cap = qrows_cap;
+  return GS_OK;
+}
+
+extern "C" int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_run *jobs_out,
+                                double *duration_out, int32_t *finish_order_out, gs_span *spans_out) {
+  if (!h) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_compact: sim index out of range");
+  SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_compact: nothing has run yet");
+  if (s.pol.schedule != GS_SCHED_FIFO) return fail(h, GS_ERR_ARG, "gs_fetch_compact: the compact records are the fifo engine's output");
+  static_assert(sizeof(gs_evrow) == 32 && sizeof(gs_qrow) == 32 && sizeof(gs_job_run) == 8, "compact record layout");
+  const SimDev &D = s.dev;
+  CU(cudaSetDevice(h->device));
+  if (ev_out && D.nev > 0) CU(cudaMemcpyAsync(ev_out, D.evrows, sizeof(gs_evrow) * (size_t)D.nev, cudaMemcpyDeviceToHost, h->stream));
+  if (q_out && D.nq > 0) CU(cudaMemcpyAsync(q_out, D.qrows, sizeof(gs_qrow) * (size_t)D.nq, cudaMemcpyDeviceToHost, h->stream));
+  if (jobs_out && s.n > 0) CU(cudaMemcpyAsync(jobs_out, D.rec2, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
+  if (duration_out && D.dur2 && s.n > 0) CU(cudaMemcpyAsync(duration_out, D.dur2, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
+  if (finish_order_out && D.finished > 0) CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream));
+  if (spans_out && D.span_used > 0) CU(cudaMemcpyAsync(spans_out, D.spans, sizeof(gs_span) * (size_t)D.span_used, cudaMemcpyDeviceToHost, h->stream));
+  return GS_OK;
+}
+
+static int ensure_scratch(gs_handle h, size_t bytes) {
+  if (h->d_scratch_bytes >= bytes) return GS_OK;
+  if (h->d_scratch) { cudaStreamSynchronize(h->stream); cudaFree(h->d_scratch); }
+  h->d_scratch = nullptr; h->d_scratch_bytes = 0;
+  CU(cudaMalloc(&h->d_scratch, bytes));
+  h->d_scratch_bytes = bytes;
   return GS_OK;
 }
 
@@ -515,7 +595,18 @@ extern "C" int gs_fetch_rows(gs_handle h, int sim, int64_t first, int64_t count,
   if (count == 0) return GS_OK;
   if (!rows_out) return fail(h, GS_ERR_ARG, "gs_fetch_rows: NULL output");
   CU(cudaSetDevice(h->device));
-  return timed_d2h(h, rows_out, D.rows + (first - D.row_first), sizeof(gs_tick_row) * (size_t)count);
+  if (s.pol.schedule != GS_SCHED_FIFO)
+    return timed_d2h(h, rows_out, D.rows + (first - D.row_first), sizeof(gs_tick_row) * (size_t)count);
+  // fifo: rebuild the rows of the whole window from its records on the device, copy the requested slice
+  const int64_t wrows = D.ticks - D.row_first;
+  int rc = ensure_scratch(h, sizeof(gs_tick_row) * (size_t)wrows);
+  if (rc) return rc;
+  if (D.nev > 0) {
+    gs_expand_rows_kernel<<<(unsigned)((D.nev + 127) / 128), 128, 0, h->stream>>>(h->d_sims, sim, D.M, D.G, (gs_tick_row *)h->d_scratch);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
+  return timed_d2h(h, rows_out, (gs_tick_row *)h->d_scratch + (first - D.row_first), sizeof(gs_tick_row) * (size_t)count);
 }
 
 extern "C" int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out, int32_t *finish_order_out) {
@@ -524,11 +615,21 @@ extern "C" int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out, int32_t
   SimHost &s = h->sims[(size_t)sim];
   if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_jobs: nothing has run yet");
   CU(cudaSetDevice(h->device));
+  const SimDev &D = s.dev;
+  const gs_job_rec *src = D.rec;
+  if (jobs_out && s.n > 0 && s.pol.schedule == GS_SCHED_FIFO) {
+    int rc = ensure_scratch(h, sizeof(gs_job_rec) * (size_t)s.n);
+    if (rc) return rc;
+    gs_expand_jobs_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(h->d_sims, sim, (gs_job_rec *)h->d_scratch);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    src = (const gs_job_rec *)h->d_scratch;
+  }
   CU(cudaEventRecord(h->e0, h->stream));
   if (jobs_out && s.n > 0)
-    CU(cudaMemcpyAsync(jobs_out, s.dev.rec, sizeof(gs_job_rec) * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
-  if (finish_order_out && s.dev.finished > 0)
-    CU(cudaMemcpyAsync(finish_order_out, s.dev.fin, 4 * (size_t)s.dev.finished, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(jobs_out, src, sizeof(gs_job_rec) * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
+  if (finish_order_out && D.finished > 0)
+    CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaEventRecord(h->e1, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
@@ -536,15 +637,9 @@ extern "C" int gs_fetch_jobs(gs_handle h, int sim, gs_job_rec *jobs_out, int32_t
   return GS_OK;
 }
 
-static int ensure_scratch(gs_handle h, size_t bytes) {
-  if (h->d_scratch_bytes >= bytes) return GS_OK;
-  if (h->d_scratch) cudaFree(h->d_scratch);
-  h->d_scratch = nullptr; h->d_scratch_bytes = 0;
-  CU(cudaMalloc(&h->d_scratch, bytes));
-  h->d_scratch_bytes = bytes;
-  return GS_OK;
-}
-
+// Spans are pooled in START order while the simulation runs (bit 31 of ntasks marks the first span of a
+// job); this entry point hands them out grouped by job (CSR).  Start ticks are unique (one start per
+// tick), so the k-th marked span belongs to the job with the k-th smallest start tick.
 extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_span *spans_out, int64_t spans_cap,
                               int64_t *spans_used) {
   if (!h) return GS_ERR_ARG;
@@ -552,81 +647,61 @@ extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_sp
   SimHost &s = h->sims[(size_t)sim];
   if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_spans: nothing has run yet");
   CU(cudaSetDevice(h->device));
-  const int64_t used = s.dev.span_used;
+  const SimDev &D = s.dev;
+  const int64_t used = s.pol.schedule == GS_SCHED_FIFO ? D.span_used : 0;
   if (spans_used) *spans_used = used;
   if (!spans_out && !span_off_out) return GS_OK;
   if (spans_out && spans_cap < used) return fail(h, GS_ERR_CAPACITY, "gs_fetch_spans: spans_out too small");
-  const size_t N = (size_t)(s.n > 0 ? s.n : 1);
-  const size_t o_off = 0, o_sp = align_up(8 * (N + 1)), total = align_up(o_sp + sizeof(gs_span) * (size_t)(used > 0 ? used : 1));
-  int rc = ensure_scratch(h, total);
+  const int64_t n = s.n;
+  if (used == 0) {
+    if (span_off_out) for (int64_t j = 0; j <= n; ++j) span_off_out[j] = 0;
+    return GS_OK;
+  }
+  std::vector<gs_span> pool((size_t)used);
+  std::vector<int2> r2((size_t)n);
+  int rc = timed_d2h(h, pool.data(), D.spans, sizeof(gs_span) * (size_t)used);
   if (rc) return rc;
-  unsigned char *d = (unsigned char *)h->d_scratch;
-  long long *d_off = (long long *)(d + o_off);
-  gs_span *d_sp = (gs_span *)(d + o_sp);
-  CU(cudaEventRecord(h->e0, h->stream));
-  gs_span_scan_kernel<<<1, 1024, 0, h->stream>>>(s.dev.rec, s.dev.sref, (int)s.n, d_off);
-  if (s.n > 0 && used > 0 && spans_out)
-    gs_span_gather_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream>>>(s.dev.rec, s.dev.sref, s.dev.spans, d_off,
-                                                                              (int)s.n, d_sp);
-  CU(cudaGetLastError());
-  h->launches += 2;
-  if (span_off_out) CU(cudaMemcpyAsync(span_off_out, d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, h->stream));
-  if (spans_out && used > 0) CU(cudaMemcpyAsync(spans_out, d_sp, sizeof(gs_span) * (size_t)used, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaEventRecord(h->e1, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
-  h->d2h_ms += ms;
+  rc = timed_d2h(h, r2.data(), D.rec2, 8 * (size_t)n);
+  if (rc) return rc;
+  // jobs in start order: bucket by start tick (unique, < ticks)
+  std::vector<int32_t> by_tick((size_t)D.ticks + 1, -1);
+  const int64_t admitted = D.p;
+  for (int64_t j = 0; j < admitted; ++j) if (r2[(size_t)j].x >= 0 && r2[(size_t)j].x <= D.ticks) by_tick[(size_t)r2[(size_t)j].x] = (int32_t)j;
+  std::vector<int32_t> order; order.reserve((size_t)n);
+  for (int64_t t = 0; t <= D.ticks; ++t) if (by_tick[(size_t)t] >= 0) order.push_back(by_tick[(size_t)t]);
+  std::vector<int64_t> first((size_t)n, 0), cnt((size_t)n, 0);
+  int64_t k = -1;
+  for (int64_t i = 0; i < used; ++i) {
+    if ((uint32_t)pool[(size_t)i].ntasks & GS_SPAN_FIRST) { ++k; if (k < (int64_t)order.size()) first[(size_t)order[(size_t)k]] = i; }
+    if (k >= 0 && k < (int64_t)order.size()) cnt[(size_t)order[(size_t)k]] += 1;
+  }
+  if (k + 1 != (int64_t)order.size()) return fail(h, GS_ERR_STATE, "gs_fetch_spans: span pool and start records disagree");
+  int64_t run = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    if (span_off_out) span_off_out[j] = run;
+    if (spans_out)
+      for (int64_t i = 0; i < cnt[(size_t)j]; ++i) {
+        gs_span sp = pool[(size_t)(first[(size_t)j] + i)];
+        sp.ntasks = (int32_t)((uint32_t)sp.ntasks & ~GS_SPAN_FIRST);
+        spans_out[run + i] = sp;
+      }
+    run += cnt[(size_t)j];
+  }
+  if (span_off_out) span_off_out[n] = run;
   return GS_OK;
 }
 
-// Everything a caller needs from one finished (or paused) replica in ONE call: the rows of the last
-// window, job records, finish order and the spans grouped by job.  The big row copy runs on the
-// main stream while the regroup kernels and the small copies run on a second stream.
+// Everything a caller needs from one finished (or paused) replica in ONE call, in the row / record
+// formats of the reference's LogInfo and job.csv (the compact, asynchronous route is gs_fetch_compact).
 extern "C" int gs_fetch_all(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out,
                             gs_job_rec *jobs_out, int32_t *finish_order_out, int64_t *span_off_out,
                             gs_span *spans_out, int64_t spans_cap, int64_t *spans_used) {
   if (!h) return GS_ERR_ARG;
-  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_all: sim index out of range");
-  SimHost &s = h->sims[(size_t)sim];
-  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_all: nothing has run yet");
-  const SimDev &D = s.dev;
-  if (rows_out && (count < 0 || first < D.row_first || first + count > D.ticks))
-    return fail(h, GS_ERR_ARG, "gs_fetch_all: row range is outside the last gs_run window");
-  const int64_t used = D.span_used;
-  if (spans_used) *spans_used = used;
-  if (spans_out && spans_cap < used) return fail(h, GS_ERR_CAPACITY, "gs_fetch_all: spans_out too small");
-  CU(cudaSetDevice(h->device));
-  const size_t N = (size_t)(s.n > 0 ? s.n : 1);
-  const size_t o_sp = align_up(8 * (N + 1)), total = align_up(o_sp + sizeof(gs_span) * (size_t)(used > 0 ? used : 1));
-  if (h->d_scratch2_bytes < total) {
-    if (h->d_scratch2) cudaFree(h->d_scratch2);
-    h->d_scratch2 = nullptr; h->d_scratch2_bytes = 0;
-    CU(cudaMalloc(&h->d_scratch2, total));
-    h->d_scratch2_bytes = total;
-  }
-  unsigned char *d = (unsigned char *)h->d_scratch2;
-  long long *d_off = (long long *)d;
-  gs_span *d_sp = (gs_span *)(d + o_sp);
-  CU(cudaEventRecord(h->e0, h->stream));
-  if (rows_out && count > 0)
-    CU(cudaMemcpyAsync(rows_out, D.rows + (first - D.row_first), sizeof(gs_tick_row) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
-  if (span_off_out || spans_out) {
-    gs_span_scan_kernel<<<1, 1024, 0, h->stream2>>>(D.rec, D.sref, (int)s.n, d_off);
-    if (s.n > 0 && used > 0 && spans_out)
-      gs_span_gather_kernel<<<(unsigned)((s.n + 255) / 256), 256, 0, h->stream2>>>(D.rec, D.sref, D.spans, d_off, (int)s.n, d_sp);
-    CU(cudaGetLastError());
-    h->launches += 2;
-    if (span_off_out) CU(cudaMemcpyAsync(span_off_out, d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, h->stream2));
-    if (spans_out && used > 0) CU(cudaMemcpyAsync(spans_out, d_sp, sizeof(gs_span) * (size_t)used, cudaMemcpyDeviceToHost, h->stream2));
-  }
-  if (jobs_out && s.n > 0) CU(cudaMemcpyAsync(jobs_out, D.rec, sizeof(gs_job_rec) * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream2));
-  if (finish_order_out && D.finished > 0) CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream2));
-  CU(cudaStreamSynchronize(h->stream2));
-  CU(cudaEventRecord(h->e1, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
-  h->d2h_ms += ms;
-  return GS_OK;
+  int rc = GS_OK;
+  if (rows_out) rc = gs_fetch_rows(h, sim, first, count, rows_out);
+  if (rc == GS_OK && (jobs_out || finish_order_out)) rc = gs_fetch_jobs(h, sim, jobs_out, finish_order_out);
+  if (rc == GS_OK) rc = gs_fetch_spans(h, sim, span_off_out, spans_out, spans_cap, spans_used);
+  return rc;
 }
 
 extern "C" int gs_place_batch(gs_handle h, const gs_cluster *cluster, const gs_node *nodes, int32_t m,
@@ -739,10 +814,10 @@ extern "C" int gs_set_span_budget(gs_handle h, double spans_per_job) {
   return GS_OK;
 }
 
-// 0 = auto (lane engine from 32 replicas up), 1 = one warp per replica, 2 = one lane per replica
+// event-driven policies: 0 (or 1) = one warp per replica, 2 = one thread per replica; the fifo engine has one mapping
 extern "C" int gs_set_engine(gs_handle h, int mode) {
   if (!h) return GS_ERR_ARG;
-  if (mode < 0 || mode > 3) return fail(h, GS_ERR_ARG, "gs_set_engine: mode must be 0..3");
+  if (mode < 0 || mode > 2) return fail(h, GS_ERR_ARG, "gs_set_engine: mode must be 0, 1 or 2");
   h->engine_mode = mode;
   return GS_OK;
 }

@@ -33,6 +33,81 @@ JOB_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"),
                       ("preempt", "<i4"), ("duration", "<f8")])
 SPAN_DTYPE = np.dtype([("node", "<i4"), ("ntasks", "<i4"), ("devmask", "<u8")])
 assert ROW_DTYPE.itemsize == 64 and JOB_DTYPE.itemsize == 24 and SPAN_DTYPE.itemsize == 16
+# compact records of the fifo engine: gs_evrow / gs_qrow / gs_job_run
+EVROW_DTYPE = np.dtype([("now", "<i4"), ("queued", "<i4"), ("finished", "<i4"), ("busy_running", "<u4"),
+                        ("mem_busy_bytes", "<i8"), ("busy_nodes", "<i4"), ("qrow", "<i4")])
+QROW_DTYPE = np.dtype([("arrive_sum", "<i8"), ("oldest_arrive", "<i4"), ("med_lo_arrive", "<i4"),
+                       ("med_hi_arrive", "<i4"), ("reserved", "<i4", (3,))])
+JOBRUN_DTYPE = np.dtype([("start", "<i4"), ("run_ticks", "<i4")])
+assert EVROW_DTYPE.itemsize == 32 and QROW_DTYPE.itemsize == 32 and JOBRUN_DTYPE.itemsize == 8
+SPAN_FIRST = 0x80000000
+
+
+def expand_rows(ev, qr, row_first, ticks, n_nodes, gpus_per_node):
+    """gs_tick_row of every tick of a window from its compact records (include/gsched.h: gs_evrow):
+    record k describes the rows `now_k` .. `now_(k+1) - 1`; on those only `delta` and the pending
+    statistics move, linearly with the tick (pending = now - arrival, jobs_manager.py:72-87)."""
+    count = int(ticks - row_first)
+    rows = np.zeros(count, dtype=ROW_DTYPE)
+    if count == 0:
+        return rows
+    now = np.arange(row_first + 1, ticks + 1, dtype=np.int64)
+    starts = ev["now"].astype(np.int64)
+    gaps = np.diff(np.append(starts, ticks + 1))
+    k = np.repeat(np.arange(len(ev)), gaps)
+    e = ev[k]
+    q = e["queued"].astype(np.int64)
+    busy = (e["busy_running"] & 0xffff).astype(np.int32)
+    rows["now"] = now
+    rows["idle_nodes"] = n_nodes - e["busy_nodes"]
+    rows["busy_nodes"] = e["busy_nodes"]
+    rows["busy_gpus"] = busy
+    rows["idle_gpus"] = n_nodes * gpus_per_node - busy
+    rows["running"] = (e["busy_running"] >> 16).astype(np.int32)
+    rows["queued"] = e["queued"]
+    rows["finished"] = e["finished"]
+    rows["mem_busy_bytes"] = e["mem_busy_bytes"]
+    has = e["qrow"] >= 0
+    if has.any():
+        b = qr[e["qrow"][has]]
+        v = now[has]
+        rows["pend_sum"][has] = q[has] * v - b["arrive_sum"]
+        rows["pend_max"][has] = v - b["oldest_arrive"]
+        rows["pend_med_lo"][has] = v - b["med_lo_arrive"]
+        rows["pend_med_hi"][has] = v - b["med_hi_arrive"]
+    return rows
+
+
+def expand_jobs(job_run, admitted, duration_in, duration_out=None):
+    """gs_job_rec view of the compact {start, run_ticks} records (fifo never preempts: end = start + run,
+    jct = run, preempt = migration_count = 1, quirk Q12; never started: -1, -1, 0, 0)."""
+    n = len(job_run)
+    recs = np.zeros(n, dtype=JOB_DTYPE)
+    started = (np.arange(n) < admitted) & (job_run["start"] >= 0)
+    recs["start"] = np.where(started, job_run["start"], -1)
+    recs["end"] = np.where(started, job_run["start"] + job_run["run_ticks"], -1)
+    recs["jct"] = np.where(started, job_run["run_ticks"], 0)
+    recs["preempt"] = started.astype(np.int32)
+    recs["duration"] = duration_in
+    if duration_out is not None:
+        recs["duration"] = np.where(started, duration_out, duration_in)
+    return recs
+
+
+def group_spans(job_run, admitted, pool):
+    """(span_off[n+1], spans grouped by job) from the start-ordered span pool of gs_fetch_compact: the k-th
+    record flagged SPAN_FIRST opens the job with the k-th smallest start tick (start ticks are unique)."""
+    n = len(job_run)
+    started = np.nonzero((np.arange(n) < admitted) & (job_run["start"] >= 0))[0]
+    order = started[np.argsort(job_run["start"][started], kind="stable")]
+    first = (pool["ntasks"].view(np.uint32) & SPAN_FIRST) != 0
+    owner = order[np.cumsum(first) - 1] if len(pool) else np.zeros(0, dtype=np.int64)
+    cnt = np.bincount(owner, minlength=n) if len(pool) else np.zeros(n, dtype=np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cnt, out=off[1:])
+    out = pool[np.argsort(owner, kind="stable")].copy()
+    out["ntasks"] = (out["ntasks"].view(np.uint32) & ~np.uint32(SPAN_FIRST)).astype(np.int32)
+    return off, out
 
 
 class LogInfo:

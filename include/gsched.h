@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 1
+#define GS_ABI_VERSION 2
 #define GS_MAX_QUEUES 8
 #define GS_MAX_GPUS_PER_NODE 64
 
@@ -103,6 +103,50 @@ typedef struct gs_tick_row {
   int32_t reserved;
 } gs_tick_row;
 
+/* Compact form of the same information, as the fifo engine writes it.  On a tick where nothing arrives,
+ * starts or finishes no LogInfo counter changes except `delta` and the pending times, which move linearly
+ * with the tick, so the engine writes one gs_evrow per tick on which a counter DID change (and for the first
+ * tick of every gs_run window) plus, while the queue is non-empty, one gs_qrow; the row of any tick
+ * v in [now_k, now_k+1) follows from record k:
+ *   delta = v, pending sum = queued*v - arrive_sum, max/median pending = v - oldest / middle arrivals
+ * (jobs_manager.py:72-87).  gs_fetch_rows does this expansion on the device; gs_fetch_compact hands out the
+ * records themselves (about a third of the bytes of the rows on the BASELINE trace).  32 bytes each.       */
+typedef struct gs_evrow {
+  int32_t now;              /* 'delta' of the first row this record describes                          */
+  int32_t queued;
+  int32_t finished;
+  uint32_t busy_running;    /* busy_gpus | running << 16  (the engine requires M*G <= 65535)           */
+  int64_t mem_busy_bytes;
+  int32_t busy_nodes;
+  int32_t qrow;             /* index of the gs_qrow of this record in the same window, -1: queue empty */
+} gs_evrow;
+
+typedef struct gs_qrow {
+  int64_t arrive_sum;       /* sum of the arrival ticks of the queued jobs                             */
+  int32_t oldest_arrive;    /* arrival tick of the job that has waited longest                         */
+  int32_t med_lo_arrive;    /* arrival ticks of the two middle jobs of the queue (equal when odd)      */
+  int32_t med_hi_arrive;
+  int32_t reserved[3];
+} gs_qrow;
+
+/* Compact per-job result of the fifo engine: fifo never preempts, so end = start + run_ticks,
+ * jct = run_ticks, preempt = 1 (quirk Q12); start = -1: the job never started.  8 bytes.                */
+typedef struct gs_job_run {
+  int32_t start;
+  int32_t run_ticks;
+} gs_job_run;
+
+/* What the last gs_run window of one replica holds (sizes for gs_fetch_compact).                        */
+typedef struct gs_window_info {
+  int64_t row_first;        /* tick index of the window's first row                                    */
+  int64_t ticks;            /* rows produced so far (the window is [row_first, ticks))                 */
+  int64_t ev_rows, q_rows;  /* records of the window                                                   */
+  int64_t spans_used;       /* (job, node) records so far, start order                                 */
+  int64_t admitted;         /* trace rows consumed so far: gs_job_run is defined for jobs below this   */
+  int64_t finished;
+  int64_t n;
+} gs_window_info;
+
 /* Per-job result, 24 bytes: what LogManager.jcts prints (log_manager.py:143-153). */
 typedef struct gs_job_rec {
   int32_t start;          /* start_time; -1 if the job never started             */
@@ -113,6 +157,7 @@ typedef struct gs_job_rec {
 } gs_job_rec;
 
 /* Where a job's tasks ran: one record per (job, node).  16 bytes.               */
+#define GS_SPAN_FIRST 0x80000000u  /* gs_fetch_compact only: set in ntasks on the first record of every job */
 typedef struct gs_span {
   int32_t node;           /* 0-based node index (reference node_id = node + 1)   */
   int32_t ntasks;
@@ -178,9 +223,13 @@ int gs_load_trace(gs_handle h, int sim, int64_t n,
 int gs_load_trace_packed(gs_handle h, int sim, int64_t n, const gs_jobin *jobs,
                          const double *model_mb, const double *iterations);
 
-/* Advance every replica by at most max_ticks ticks (<=0: until done).  Row
- * storage on the device is sized by rows_cap per replica at the first call.    */
+/* Advance every replica by at most max_ticks ticks (<=0: until done).  Record
+ * storage on the device is sized by rows_cap per replica at the first call (fifo: that many gs_evrow
+ * and gs_qrow records; event-driven policies: that many rows); a launch also ends when it is full,
+ * so any value >= 1 is safe -- drain with the fetch calls and call again.                            */
 int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap);
+/* Separate capacity for the gs_qrow stream of replicas prepared afterwards (0 = same as rows_cap).   */
+int gs_set_queue_rows_cap(gs_handle h, int64_t qrows_cap);
 
 int gs_stats(gs_handle h, int sim, gs_run_stats *out);
 
@@ -188,10 +237,8 @@ int gs_stats(gs_handle h, int sim, gs_run_stats *out);
  * memory (sweeps, benchmarking); also clears the accumulated timers.           */
 int gs_reset(gs_handle h);
 
-/* Kernel mapping: 0 = auto (currently the warp mapping), 1 = one warp per replica
- * (lanes stripe over nodes), 2 = one lane per replica (32 replicas per warp,
- * hot state in shared memory), 3 = half a warp per replica (two replicas share a
- * warp's instruction stream); see DESIGN.md for the measured trade-offs.          */
+/* Kernel mapping of the event-driven policies: 0 = warp-cooperative kernels (default), 2 = one thread
+ * per replica (first version, kept as a cross-check).  The fifo engine has one mapping (a warp per replica). */
 int gs_set_engine(gs_handle h, int mode);
 
 /* Span-pool sizing for traces loaded afterwards: 0 (default) = worst case, never overflows;
@@ -217,6 +264,22 @@ int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out /* n+1 */,
 int gs_fetch_all(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row *rows_out,
                  gs_job_rec *jobs_out, int32_t *finish_order_out, int64_t *span_off_out,
                  gs_span *spans_out, int64_t spans_cap, int64_t *spans_used);
+
+/* ---- compact, asynchronous result path (fifo engine) ------------------------------------------------
+ * gs_window_info: sizes of what the last gs_run left.  gs_fetch_compact enqueues the copies of every
+ * non-NULL output on the handle's stream and returns; gs_sync waits for them.  Buffers from
+ * gs_host_alloc make the copies true DMA.  Sizes: ev_out ev_rows, q_out q_rows, jobs_out n,
+ * duration_out n (only with network costs, else left untouched), finish_order_out finished,
+ * spans_out spans_used (start order, GS_SPAN_FIRST marks job boundaries; jobs in start order =
+ * jobs_out sorted by start, start ticks are unique -- one start per tick, schedule.py:188-190).      */
+int gs_window(gs_handle h, int sim, gs_window_info *out);
+int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_run *jobs_out,
+                     double *duration_out, int32_t *finish_order_out, gs_span *spans_out);
+int gs_sync(gs_handle h);
+/* 1: gs_load_trace_packed from a page-locked buffer enqueues the upload without staging and returns
+ * before it completes -- the caller keeps the buffer unchanged until the next gs_run / gs_sync on
+ * this handle returns.  0 (default): every call copies and completes before returning.              */
+int gs_set_async(gs_handle h, int on);
 
 /* Stateless candidate scoring: evaluate b jobs against ONE cluster state.
  * first_node[i] = node of a single-node first fit, or the first node of a

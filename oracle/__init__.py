@@ -23,7 +23,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(_HERE, "gsched_oracle.c"), os.path.join(_HERE, "policy_oracle.c"),
-            os.path.join(_HERE, "tight_cpu.c"), os.path.join(_HERE, "horus_oracle.c")]
+            os.path.join(_HERE, "tight_cpu.c"), os.path.join(_HERE, "tight2_cpu.c"), os.path.join(_HERE, "horus_oracle.c")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "gsched.h")
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(x) for x in srcs + [hdr])):
@@ -41,6 +41,11 @@ def lib():
         _lib.oracle_run_fifo.restype = C.c_int64
         _lib.oracle_run_policy.restype = C.c_int64
         _lib.tight_run_fifo.restype = C.c_int64
+        _lib.tight2_create.restype = C.c_void_p
+        _lib.tight2_jobs.restype = C.c_void_p
+        _lib.tight2_finish_order.restype = C.c_void_p
+        _lib.tight2_spans.restype = C.c_void_p
+        _lib.tight2_run.restype = C.c_int
         _lib.oracle_run_horus.restype = C.c_int64
         _lib.oracle_place_one.restype = C.c_int
         _lib.oracle_net_cost.restype = C.c_double
@@ -272,3 +277,77 @@ def run_horus(cluster: GsCluster, table, scheme="horus", schedule="horus", num_b
     r.finish_order = order[:nfin.value]
     r.events, r.draws = events.value, draws.value
     return r
+
+
+class Tight2:
+    """oracle/tight2_cpu.c: the event-stepped algorithm of the CUDA fifo engine as single-thread C, producing the same
+    compact records in resumable windows.  run_all() decodes them with the PACKAGE's decoders (log_manager.expand_rows /
+    expand_jobs / group_spans), so a comparison with the pinned oracle checks algorithm and decoders together."""
+
+    def __init__(self, cluster: GsCluster, table, span_cap=0):
+        from gpuschedule_b200.capi import GsWindowInfo
+        from gpuschedule_b200.log_manager import EVROW_DTYPE, JOBRUN_DTYPE, QROW_DTYPE
+        self._w, self._dt = GsWindowInfo, (EVROW_DTYPE, QROW_DTYPE, JOBRUN_DTYPE)
+        self.cluster, self.table, self.n = cluster, table, table.n
+        arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        self.cols = (arr(table.arrive_tick, np.int32), arr(table.gpus, np.int32), arr(table.gpu_per_task, np.int32),
+                     arr(table.duration, np.float64), arr(table.mem_bytes, np.int64))
+        a, g, c, d, mm = self.cols
+        self.h = C.c_void_p(lib().tight2_create(C.byref(cluster), C.c_int64(self.n), _p(a), _p(g), _p(c), _p(d), _p(mm), C.c_int64(span_cap)))
+        worst = int(table.arrive_tick[-1] if self.n else 0) + 2 * int(np.ceil(table.duration.max()) if self.n else 0) + 4096
+        self.cap = worst
+        self.ev = np.zeros(worst, dtype=EVROW_DTYPE)
+        self.qr = np.zeros(worst, dtype=QROW_DTYPE)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().tight2_free(self.h)
+            self.h = None
+
+    def restart(self):
+        lib().tight2_restart(self.h)
+
+    def run_window(self, max_ticks=0, cap_a=None, cap_b=None):
+        """one window -> (status, GsWindowInfo, events, evals, done); records are in self.ev / self.qr"""
+        nev, nq = C.c_int64(0), C.c_int64(0)
+        rc = lib().tight2_run(self.h, C.c_int64(max_ticks), C.c_int64(self.cap if cap_a is None else cap_a),
+                              C.c_int64(self.cap if cap_b is None else cap_b), _p(self.ev), _p(self.qr), C.byref(nev), C.byref(nq))
+        w = self._w()
+        events, evals, done = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        lib().tight2_info(self.h, C.byref(w), nev, nq, C.byref(events), C.byref(evals), C.byref(done))
+        return rc, w, events.value, evals.value, done.value
+
+    def run(self):
+        """bare timing loop body: one full run into the preallocated record buffers -> (ticks, events)"""
+        self.restart()
+        rc, w, events, _, done = self.run_window()
+        if rc != 0 or not done:
+            raise RuntimeError(f"tight2_run failed: {rc}")
+        return int(w.ticks), int(events)
+
+    def run_all(self, max_ticks=0, cap_a=None, cap_b=None):
+        """run to the end in windows; returns an OracleResult in the legacy row / record formats"""
+        from gpuschedule_b200 import log_manager as lm
+        self.restart()
+        m, g = self.cluster.num_switch * self.cluster.num_node_p_switch, self.cluster.num_gpu_p_node
+        parts = []
+        while True:
+            rc, w, events, evals, done = self.run_window(max_ticks, cap_a, cap_b)
+            if rc != 0:
+                raise RuntimeError(f"tight2_run failed: {rc}")
+            parts.append(lm.expand_rows(self.ev[:w.ev_rows], self.qr[:w.q_rows], w.row_first, w.ticks, m, g))
+            if done or self.n == 0:
+                break
+        r = OracleResult()
+        n = self.n
+        jobs = np.ctypeslib.as_array(C.cast(lib().tight2_jobs(self.h), C.POINTER(C.c_int32)), shape=(max(n, 1) * 2,)).view(self._dt[2])[:n].copy()
+        r.ticks = int(w.ticks)
+        r.rows = np.concatenate(parts) if parts else np.zeros(0, dtype=ROW_DTYPE)
+        r.recs = lm.expand_jobs(jobs, int(w.admitted), self.cols[3])
+        nf = int(w.finished)
+        r.finish_order = np.ctypeslib.as_array(C.cast(lib().tight2_finish_order(self.h), C.POINTER(C.c_int32)), shape=(max(nf, 1),))[:nf].copy()
+        ns = int(w.spans_used)
+        pool = np.ctypeslib.as_array(C.cast(lib().tight2_spans(self.h), C.POINTER(C.c_uint8)), shape=(max(ns, 1) * 16,)).view(SPAN_DTYPE)[:ns].copy()
+        r.span_off, r.spans = lm.group_spans(jobs, int(w.admitted), pool)
+        r.events, r.evals, r.job_run, r.pool = events, evals, jobs, pool
+        return r
