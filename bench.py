@@ -236,6 +236,13 @@ def ours(args):
     from gpuschedule_b200 import dist as gdist
     red = gdist.Reducer(world, dev)
 
+    if args.only_sharded:
+        blk = sharded_block(args, rank, world, local, dev)
+        if rank == 0:
+            print(json.dumps(blk), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     R, n = args.replicas, args.jobs
     cluster = capi.make_cluster(4, 32, 8)
     M, G = 128, 8
@@ -512,6 +519,13 @@ def ours(args):
                "host_cores": os.cpu_count()}
         cpu_tight = tight_yardstick(cluster, tables[:1], 1, ticks[0])
 
+    sharded = None
+    if not args.no_sharded:
+        try:
+            sharded = sharded_block(args, rank, world, local, dev)
+        except Exception as exc:                          # the secondary block never costs the main line
+            sharded = {"error": repr(exc)}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -526,11 +540,57 @@ def ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "cpu_tight": cpu_tight,
             "vs_cpu_tight_one_core": (None if not cpu_tight else {"device_timed": value / cpu_tight["value"], "e2e": e2e["value"] / cpu_tight["value"],
                                                                    "single_replica": single["value"] / cpu_tight["value"]}),
-            "secondary": extras,
+            "sharded": sharded, "secondary": extras,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_block(args, rank, world, local, dev):
+    """BASELINE config C4: ONE gittins simulation of the 100k-job trace, on one GPU and sharded over the `world`
+    GPUs of the box (rank evaluation split by chunks of the runnable list, one NVLink peer-store exchange per event
+    inside the persistent kernel; include/gsched.h gs_comm_*).  Every rank runs both and compares the bytes."""
+    from gpuschedule_b200 import capi
+    from gpuschedule_b200 import dist as gdist
+    n = args.sharded_jobs
+    cluster = capi.make_cluster(4, 32, 8)
+    table = fast_table(n, BASE_SEED)
+    pol = make_policy("gittins", table)
+    red = gdist.Reducer(world, dev)
+
+    def timed(eng):
+        eng.config(0, cluster, pol)
+        eng.load_trace_packed(0, table.packed())
+        run_to_done(eng, 0)
+        cap = eng.stats(0).ticks + 64
+        best = None
+        for _ in range(2):
+            eng.reset()
+            red.barrier()
+            run_to_done(eng, cap)
+            ms = eng.stats(0).kernel_ms
+            best = ms if best is None else min(best, ms)
+        rows = eng.fetch_rows(0)
+        recs, order = eng.fetch_jobs(0)
+        return best, eng.stats(0).events, (rows.tobytes(), recs.tobytes(), order.tobytes())
+
+    with capi.Engine(device=local, nsims=1) as e1:
+        ms1, events, single = timed(e1)
+    out = {"policy": "gittins", "jobs": n, "n_gpus": world, "events": int(events),
+           "single_gpu": {"ms": red.max(ms1), "events_per_s": events / (red.max(ms1) / 1e3)}}
+    if world > 1:
+        with capi.Engine(device=local, nsims=1) as e2:
+            handles = gdist.exchange_comm_handles(e2.comm_prepare(n), world, dev)
+            e2.comm_init(rank, handles)
+            msN, eventsN, shard = timed(e2)
+            exchanges, us = e2.comm_stats()
+        same = red.sum(1.0 if (shard == single and eventsN == events) else 0.0)
+        msN = red.max(msN)
+        out["sharded"] = {"ms": msN, "events_per_s": events / (msN / 1e3), "exchanges": exchanges,
+                          "exchange_us_mean": red.max(us), "exchange": "NVLink peer stores + flag words inside the persistent kernel (no NCCL call on the data path)",
+                          "ranks_identical_to_single_gpu": int(same), "speedup_vs_single_gpu": out["single_gpu"]["ms"] / msN}
+    return out
 
 
 def red_ticks_all(ticks_rank, world):
@@ -762,6 +822,9 @@ def main():
     ap.add_argument("--value-only", action="store_true", help="kernel experiments: print the device-timed value and stop")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
     ap.add_argument("--policy-replicas", type=int, default=1024)
+    ap.add_argument("--no-sharded", action="store_true", help="skip the one-simulation-on-N-GPUs block (config C4)")
+    ap.add_argument("--sharded-jobs", type=int, default=100000)
+    ap.add_argument("--only-sharded", action="store_true", help="print the C4 block alone (development)")
     ap.add_argument("--span-budget", type=float, default=1.5,
                     help="span-pool records per job (0 = worst case); the trace uses ~1.13, overflow is reported, never written")
     ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],

@@ -89,7 +89,8 @@ def make_policy(schedule="fifo", scheme="yarn", num_queue=1, queue_limit=(), git
     return p
 
 
-GS_OK, GS_ERR_ARG, GS_ERR_CUDA, GS_ERR_STATE, GS_ERR_CAPACITY = 0, -1, -2, -3, -4      # enum gs_status
+GS_OK, GS_ERR_ARG, GS_ERR_CUDA, GS_ERR_STATE, GS_ERR_CAPACITY, GS_ERR_COMM = 0, -1, -2, -3, -4, -5      # enum gs_status
+GS_MAX_RANKS = 8
 
 
 class GsError(RuntimeError):
@@ -202,6 +203,11 @@ def load_library():
     lib.gs_set_async.argtypes = [C.c_void_p, C.c_int]
     lib.gs_set_queue_rows_cap.argtypes = [C.c_void_p, C.c_int64]
     for name in ("gs_window", "gs_fetch_compact", "gs_sync", "gs_set_async", "gs_set_queue_rows_cap"):
+        getattr(lib, name).restype = C.c_int
+    lib.gs_comm_prepare.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    lib.gs_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.gs_comm_stats.argtypes = [C.c_void_p, i64p, f64p]
+    for name in ("gs_comm_prepare", "gs_comm_init", "gs_comm_stats"):
         getattr(lib, name).restype = C.c_int
     lib.gs_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.gs_host_free.argtypes = [C.c_void_p]
@@ -459,6 +465,26 @@ class Engine:
         self.sync()
         return (w, ev[:int(w.ev_rows)], qr[:int(w.q_rows)], jobs[:n], (None if n == 0 or np.isnan(dur[0]) else dur[:n]),
                 order[:int(w.finished)], spans[:int(w.spans_used)])
+
+    # ---- one simulation on several GPUs of one box (gittins; include/gsched.h: gs_comm_*)
+    def comm_prepare(self, max_jobs) -> bytes:
+        """allocate this handle's exchange buffer; returns its 64-byte IPC handle (send it to every rank)"""
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.gs_comm_prepare(self.h, int(max_jobs), C.cast(buf, C.c_void_p)), "gs_comm_prepare")
+        return bytes(buf)
+
+    def comm_init(self, rank, handles):
+        """handles: the 64-byte IPC handles of ALL ranks, in rank order (own at [rank])"""
+        blob = b"".join(bytes(hb) for hb in handles)
+        assert len(blob) == 64 * len(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.gs_comm_init(self.h, int(rank), len(handles), C.cast(buf, C.c_void_p)), "gs_comm_init")
+
+    def comm_stats(self):
+        """(exchanges of the last run, mean microseconds from publishing to having seen every peer)"""
+        n, us = C.c_int64(0), C.c_double(0.0)
+        self._check(self.lib.gs_comm_stats(self.h, C.byref(n), C.byref(us)), "gs_comm_stats")
+        return int(n.value), float(us.value)
 
     def set_span_budget(self, spans_per_job):
         self._check(self.lib.gs_set_span_budget(self.h, float(spans_per_job)), "gs_set_span_budget")

@@ -56,6 +56,17 @@ struct SimDev {
   double queue_limit[GS_MAX_QUEUES];
   double gittins_delta, next_gittins_unit;
   int num_queue, git_n, rn, en, end_time, next_job_jump, stale_n, qn[GS_MAX_QUEUES];
+  // ---- sharded single simulation (gs_comm_init): the gittins rank evaluation of every event is split over the GPUs
+  // of one box; each rank stores the ranks it computed straight into every peer's receive buffer over NVLink
+  // (peer stores) and publishes an event counter; nothing else crosses the link
+  int comm_rank, comm_n;                     // comm_n <= 1: not sharded
+  long long comm_cap;                        // rank values per receive buffer (>= n)
+  double *comm_rk_in;                        // local receive buffers: 2 x comm_cap doubles, selected by event parity
+  unsigned long long *comm_flags;            // local flags[comm_n]: the event counter last published by each rank
+  double *comm_peer_rk[GS_MAX_RANKS];        // every rank's receive buffers (this rank's own at [comm_rank])
+  unsigned long long *comm_peer_flags[GS_MAX_RANKS];
+  unsigned long long comm_epoch;             // events exchanged so far (continues across launches)
+  long long comm_wait_cycles;                // SM cycles between publishing and seeing every peer's counter, summed
   // ---- loop state (persisted)
   int delta, p, top, running, finished, ever, busy_gpus, done, status, need_init;
   int blocked;                // fifo: the queue head did not fit and nothing has changed since

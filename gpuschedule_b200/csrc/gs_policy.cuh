@@ -561,6 +561,13 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   const long long row_first = ticks;
   long long budget = max_ticks > 0 ? max_ticks : 0x7fffffffffffffffLL;
   bool done = false;
+  // sharded mode (gs_comm_init): rank `me` of `nr` evaluates the gittins index for the chunks c of the runnable list
+  // with c % nr == me and stores the values into every rank's receive buffer; one exchange per event
+  const int nr = (!sjf && S.comm_n > 1) ? S.comm_n : 1, me = S.comm_rank;
+  const long long ccap = S.comm_cap;
+  unsigned long long epoch = S.comm_epoch;
+  long long wait_cycles = 0;
+  int status = 0;
 
   while (budget > 0 && (ticks - row_first) < rows_cap) {
     if (!((n - p) + rn > 0)) { done = true; break; }
@@ -610,6 +617,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         r.status = PST_END; r.q_id = 0; r.last_check = 0; r.total_exec = 0; r.exec = 0; r.pending = 0; r.last_pending = 0; r.start = -1; r.resume = 0;
         if (valid) r = pj[j];
         const bool keep = valid && r.status != PST_END;
+        const bool mine = nr == 1 || ((base >> 5) % nr) == me;     // sharded: whose chunk this is
         double rank = 0.0;
         if (keep) {
           const int dt = event_time - r.last_check;
@@ -617,15 +625,47 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
           if (r.status == PST_RUNNING) { r.total_exec += dt; r.exec += dt; }
           else { r.pending += dt; if (r.exec > 0) r.last_pending += dt; }
           pj[j] = r;
-          if (!sjf) rank = git_lookup(S, r.status == PST_RUNNING ? (double)r.exec * jobs[j].gpus : (double)r.exec);
+          if (!sjf && mine) rank = git_lookup(S, r.status == PST_RUNNING ? (double)r.exec * jobs[j].gpus : (double)r.exec);
         }
         const unsigned kb = __ballot_sync(FULL, keep);
-        if (keep) { const int pos = w + __popc(kb & lt); runnable[pos] = j; if (!sjf) rk[pos] = rank; }
+        if (keep) {
+          const int pos = w + __popc(kb & lt);
+          runnable[pos] = j;
+          if (!sjf) {
+            if (nr == 1) rk[pos] = rank;
+            else if (mine) {
+              const long long at = (long long)(epoch & 1ull) * ccap + pos;
+              for (int q = 0; q < nr; ++q) S.comm_peer_rk[q][at] = rank;      // NVLink peer store (own buffer included)
+            }
+          }
+        }
         w += __popc(kb);
       }
       rn = w;
     }
     __syncwarp();
+    if (nr > 1) {
+      // ---- the exchange: publish "my ranks of event `epoch` are in your buffer" to every rank, wait for theirs
+      __threadfence_system();
+      __syncwarp();
+      const long long t0 = clock64();
+      bool late = false;
+      if (lane < nr) {
+        *reinterpret_cast<volatile unsigned long long *>(&S.comm_peer_flags[lane][me]) = epoch + 1ull;
+        const volatile unsigned long long *mine_f = reinterpret_cast<const volatile unsigned long long *>(&S.comm_flags[lane]);
+        while (*mine_f < epoch + 1ull) {
+          if (clock64() - t0 > 10000000000LL) { late = true; break; }       // ~5 s: a peer is gone
+        }
+      }
+      late = __any_sync(FULL, late);
+      wait_cycles += clock64() - t0;
+      __threadfence_system();
+      if (late) { status = GS_ERR_COMM; break; }
+      const double *rin = S.comm_rk_in + (long long)(epoch & 1ull) * ccap;
+      for (int i = lane; i < rn; i += 32) rk[i] = __ldcg(&rin[i]);
+      epoch += 1ull;
+      __syncwarp();
+    }
     // ---- arrivals (after the survivors, like the list append of the specification)
     int cnt = 0;
     if (has_start) {
@@ -843,6 +883,8 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     S.p = p; S.rn = rn; S.en = en; S.end_time = end_time; S.finished = nfin; S.next_gittins_unit = next_git; S.stale_n = stale_n;
     S.events = events; S.ticks = ticks; S.row_first = row_first;
     S.done = done ? 1 : 0; S.running = 0; S.top = 0; S.started = 0;
+    S.comm_epoch = epoch; S.comm_wait_cycles += wait_cycles;
+    if (status != 0) S.status = status;
   }
 }
 

@@ -83,6 +83,10 @@ struct gs_engine {
   double span_budget = 0;  // > 0: span pool = min(worst case, budget * n + 4096) records per replica
   int64_t qrows_cap = 0;   // 0: same as rows_cap
   bool async = false;      // gs_set_async
+  // sharded single simulation (gs_comm_prepare / gs_comm_init)
+  void *comm_buf = nullptr; int64_t comm_cap = 0; int comm_rank = 0, comm_n = 0;
+  void *comm_peer[GS_MAX_RANKS] = {nullptr}; bool comm_opened[GS_MAX_RANKS] = {false};
+  unsigned long long comm_epoch = 0, comm_epoch0 = 0;   // exchange counter: continues across runs / value at the last prepare
   bool dirty = true;       // host mirror of SimDev newer than device copy
 };
 
@@ -148,6 +152,8 @@ extern "C" void gs_destroy(gs_handle h) {
   if (h->d_sims) cudaFree(h->d_sims);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->d_scratch) cudaFree(h->d_scratch);
+  for (int q = 0; q < GS_MAX_RANKS; ++q) if (h->comm_opened[q] && h->comm_peer[q]) cudaIpcCloseMemHandle(h->comm_peer[q]);
+  if (h->comm_buf) cudaFree(h->comm_buf);
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -417,6 +423,20 @@ static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
     D.git_index = s.git_dev ? (const double *)((unsigned char *)s.git_dev + 8 * (size_t)s.pol.gittins_n) : nullptr;
     D.rn = 0; D.en = 0; D.end_time = 0x7fffffff; D.next_job_jump = 0x7fffffff;
   }
+  D.comm_n = 0; D.comm_rank = 0; D.comm_cap = 0; D.comm_rk_in = nullptr; D.comm_flags = nullptr; D.comm_epoch = 0; D.comm_wait_cycles = 0;
+  if (h->comm_n > 1 && s.pol.schedule == GS_SCHED_GITTINS) {
+    if ((int64_t)s.n > h->comm_cap) return fail(h, GS_ERR_ARG, "gs_run: the trace has more jobs than gs_comm_prepare sized the exchange buffer for");
+    // the event counter never restarts: a new run continues where the last one ended (all ranks execute the same
+    // events, so their counters agree), which needs no reset of the flag words and no extra synchronisation
+    D.comm_epoch = h->comm_epoch; h->comm_epoch0 = h->comm_epoch;
+    D.comm_n = h->comm_n; D.comm_rank = h->comm_rank; D.comm_cap = h->comm_cap;
+    D.comm_flags = (unsigned long long *)h->comm_buf;
+    D.comm_rk_in = (double *)((unsigned char *)h->comm_buf + 256);
+    for (int q = 0; q < h->comm_n; ++q) {
+      D.comm_peer_flags[q] = (unsigned long long *)h->comm_peer[q];
+      D.comm_peer_rk[q] = (double *)((unsigned char *)h->comm_peer[q] + 256);
+    }
+  }
   D.delta = D.p = D.top = D.running = D.finished = D.ever = D.busy_gpus = D.done = D.status = 0;
   D.blocked = D.nev = D.nq = 0;
   D.mem_busy = D.sum_arr = D.span_used = D.events = D.evals = D.started = D.ticks = D.row_first = 0;
@@ -491,6 +511,7 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
   CU(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
   h->kernel_ms += ms;
+  if (h->comm_n > 1 && h->h_back[0].comm_n > 1) h->comm_epoch = h->h_back[0].comm_epoch;
   int worst = 0;
   for (int i = 0; i < h->nsims; ++i) {
     h->h_back[(size_t)i].need_init = 0;
@@ -522,6 +543,59 @@ extern "C" int gs_window(gs_handle h, int sim, gs_window_info *out) {
   const bool fifo = s.pol.schedule == GS_SCHED_FIFO;
   out->ev_rows = fifo ? D.nev : 0; out->q_rows = fifo ? D.nq : 0;
   out->spans_used = D.span_used; out->admitted = D.p; out->finished = D.finished; out->n = s.n;
+  return GS_OK;
+}
+
+extern "C" int gs_comm_prepare(gs_handle h, int64_t max_jobs, gs_comm_handle *out) {
+  if (!h || !out || max_jobs < 1) return fail(h, GS_ERR_ARG, "gs_comm_prepare: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(gs_comm_handle), "IPC handle size");
+  if (h->nsims != 1) return fail(h, GS_ERR_ARG, "gs_comm_prepare: a sharded simulation needs a handle with exactly one replica");
+  if (h->comm_n > 0) return fail(h, GS_ERR_STATE, "gs_comm_prepare: already initialised");
+  CU(cudaSetDevice(h->device));
+  if (h->comm_buf) { cudaFree(h->comm_buf); h->comm_buf = nullptr; }
+  const size_t bytes = 256 + 2 * 8 * (size_t)max_jobs;
+  CU(cudaMalloc(&h->comm_buf, bytes));
+  CU(cudaMemset(h->comm_buf, 0, bytes));
+  h->comm_cap = max_jobs;
+  cudaIpcMemHandle_t ih;
+  CU(cudaIpcGetMemHandle(&ih, h->comm_buf));
+  memset(out, 0, sizeof(*out));
+  memcpy(out->bytes, &ih, sizeof(ih));
+  return GS_OK;
+}
+
+extern "C" int gs_comm_init(gs_handle h, int rank, int nranks, const gs_comm_handle *all) {
+  if (!h || !all || nranks < 1 || nranks > GS_MAX_RANKS || rank < 0 || rank >= nranks)
+    return fail(h, GS_ERR_ARG, "gs_comm_init: bad arguments (1 <= nranks <= 8)");
+  if (!h->comm_buf) return fail(h, GS_ERR_STATE, "gs_comm_init: call gs_comm_prepare first");
+  if (h->comm_n > 0) return fail(h, GS_ERR_STATE, "gs_comm_init: already initialised");
+  CU(cudaSetDevice(h->device));
+  for (int q = 0; q < nranks; ++q) {
+    if (q == rank) { h->comm_peer[q] = h->comm_buf; h->comm_opened[q] = false; continue; }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, all[q].bytes, sizeof(ih));
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int r = 0; r < q; ++r) if (h->comm_opened[r]) { cudaIpcCloseMemHandle(h->comm_peer[r]); h->comm_opened[r] = false; h->comm_peer[r] = nullptr; }
+      return fail(h, GS_ERR_COMM, std::string("gs_comm_init: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    h->comm_peer[q] = ptr; h->comm_opened[q] = true;
+  }
+  h->comm_rank = rank; h->comm_n = nranks;
+  for (auto &s : h->sims) s.prepared = false;
+  h->dirty = true;
+  return GS_OK;
+}
+
+extern "C" int gs_comm_stats(gs_handle h, int64_t *exchanges, double *mean_us) {
+  if (!h) return GS_ERR_ARG;
+  const SimDev &D = h->sims[0].dev;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+  const unsigned long long done = D.comm_n > 1 ? D.comm_epoch - h->comm_epoch0 : 0ull;
+  if (exchanges) *exchanges = (int64_t)done;
+  if (mean_us) *mean_us = (done > 0 && khz > 0) ? (double)D.comm_wait_cycles / (double)done / ((double)khz / 1000.0) : 0.0;
   return GS_OK;
 }
 

@@ -1,11 +1,12 @@
 """Multi-GPU plumbing: one process per GPU, replicas sharded across ranks.
 
-A single simulation does not shard usefully (one shared cluster state, at most one placement
-per simulated tick, every tick ~1 us of work on one GPU versus >= 10 us for any cross-GPU
-exchange), so the multi-GPU axis is REPLICAS: rank r simulates its own slice of the sweep
-and nothing crosses NVLink on the data path.  torch.distributed (nccl on GPUs, gloo in the
-CPU tests) is used only for the start/stop barrier and for reducing the timing / event
-counters to rank 0.
+Two axes.  REPLICAS (throughput): rank r simulates its own slice of the sweep and nothing crosses
+NVLink on the data path; torch.distributed (nccl on GPUs, gloo in the CPU tests) carries only the
+start/stop barrier and the reduction of timers / counters to rank 0.  ONE SIMULATION ON SEVERAL GPUS
+(BASELINE config C4, gittins): the per-event index evaluation is split over the ranks by chunks of
+the runnable list (`chunk_owner`), results travel as peer stores inside the persistent kernel
+(include/gsched.h: gs_comm_*); torch.distributed only distributes the 64-byte IPC handles
+(`exchange_comm_handles`) before the run.
 """
 from __future__ import annotations
 
@@ -61,3 +62,26 @@ class Reducer:
         if self.world > 1:
             import torch.distributed as dist
             dist.barrier()
+
+
+def chunk_owner(chunk: int, world: int) -> int:
+    """Which rank evaluates chunk `chunk` (32 consecutive entries of the runnable list) of a sharded gittins event:
+    round robin, the rule gs_sortpol_warp_kernel applies (gs_policy.cuh: `(base >> 5) % nr == me`)."""
+    if world < 1 or chunk < 0:
+        raise ValueError("bad chunk / world")
+    return chunk % world
+
+
+def exchange_comm_handles(handle: bytes, world: int, device=None):
+    """All-gather of the ranks' 64-byte exchange-buffer handles (Engine.comm_prepare) -> list in rank order.
+    Works with any torch.distributed backend: device tensors for nccl, cpu tensors for gloo."""
+    if len(handle) != 64:
+        raise ValueError("an IPC handle is 64 bytes")
+    if world == 1:
+        return [bytes(handle)]
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=device or "cpu")
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().tolist()) for t in out]

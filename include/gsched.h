@@ -41,6 +41,7 @@ extern "C" {
 #define GS_ABI_VERSION 2
 #define GS_MAX_QUEUES 8
 #define GS_MAX_GPUS_PER_NODE 64
+#define GS_MAX_RANKS 8          /* GPUs of one box that may share one simulation (gs_comm_init) */
 
 typedef enum {
   GS_OK = 0,
@@ -48,7 +49,7 @@ typedef enum {
   GS_ERR_CUDA = -2,     /* CUDA runtime or driver error                      */
   GS_ERR_STATE = -3,    /* call order (e.g. gs_run before gs_load_trace)     */
   GS_ERR_CAPACITY = -4, /* an output buffer is too small                     */
-  GS_ERR_NCCL = -5      /* NCCL error in the sharded multi-GPU path          */
+  GS_ERR_COMM = -5      /* sharded multi-GPU path: a peer did not answer in time / IPC error */
 } gs_status;
 
 /* scheduling policies (run_sim.py:37-49 names) and placement schemes (:25-36) */
@@ -280,6 +281,27 @@ int gs_sync(gs_handle h);
  * before it completes -- the caller keeps the buffer unchanged until the next gs_run / gs_sync on
  * this handle returns.  0 (default): every call copies and completes before returning.              */
 int gs_set_async(gs_handle h, int on);
+
+/* ---- one simulation on several GPUs of one box (BASELINE config C4) ----------------------
+ * The north-star sketches "the trace sharded across the 8 GPUs with one allreduce per tick".  What is worth
+ * sharding in this path is the per-event work that is O(runnable jobs): for the gittins policy that is the index
+ * evaluation (run_sim.py:1040-1078 -> get_gittins_index :949-954, a table search per runnable job per event).
+ * Every rank holds the (small) cluster / queue state and the trace; rank r evaluates the chunks c of the
+ * runnable list with c mod nranks == r and STORES the results straight into every peer's receive buffer over
+ * NVLink (peer memory opened with CUDA IPC), then publishes an event counter in the peers' flag words and waits
+ * for theirs -- one exchange per event, inside the persistent kernel, no host round trip and no NCCL call on the
+ * data path (torch.distributed only carries the 64-byte IPC handles at start-up).  Order, admission and the
+ * statistics are then computed redundantly and identically on every rank: results are bit-identical to one GPU.
+ *
+ *   gs_comm_prepare  allocates this handle's exchange buffer (for traces of up to max_jobs jobs) and returns its IPC handle
+ *   gs_comm_init     receives the handles of ALL ranks (own at [rank]), opens the peers', arms the sharded mode for
+ *                    gittins replicas prepared afterwards; the handle must hold exactly one replica
+ *   gs_comm_stats    exchanges done and their mean cost in microseconds (publish -> all peers seen, incl. skew)
+ * A peer that does not answer within ~5 s ends the run with GS_ERR_COMM on every waiting rank.            */
+typedef struct gs_comm_handle { unsigned char bytes[64]; } gs_comm_handle;
+int gs_comm_prepare(gs_handle h, int64_t max_jobs, gs_comm_handle *out);
+int gs_comm_init(gs_handle h, int rank, int nranks, const gs_comm_handle *all_ranks);
+int gs_comm_stats(gs_handle h, int64_t *exchanges, double *mean_us);
 
 /* Stateless candidate scoring: evaluate b jobs against ONE cluster state.
  * first_node[i] = node of a single-node first fit, or the first node of a

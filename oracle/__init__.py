@@ -23,7 +23,8 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(_HERE, "gsched_oracle.c"), os.path.join(_HERE, "policy_oracle.c"),
-            os.path.join(_HERE, "tight_cpu.c"), os.path.join(_HERE, "tight2_cpu.c"), os.path.join(_HERE, "horus_oracle.c")]
+            os.path.join(_HERE, "tight_cpu.c"), os.path.join(_HERE, "tight2_cpu.c"), os.path.join(_HERE, "horus_oracle.c"),
+            os.path.join(_HERE, "switch_oracle.c")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "gsched.h")
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(x) for x in srcs + [hdr])):
@@ -46,6 +47,9 @@ def lib():
         _lib.tight2_finish_order.restype = C.c_void_p
         _lib.tight2_spans.restype = C.c_void_p
         _lib.tight2_run.restype = C.c_int
+        _lib.switch_round1.restype = C.c_double
+        _lib.switch_round1.argtypes = [C.c_double]
+        _lib.switch_yarn_place.restype = C.c_int
         _lib.oracle_run_horus.restype = C.c_int64
         _lib.oracle_place_one.restype = C.c_int
         _lib.oracle_net_cost.restype = C.c_double
@@ -351,3 +355,30 @@ class Tight2:
         r.span_off, r.spans = lm.group_spans(jobs, int(w.admitted), pool)
         r.events, r.evals, r.job_run, r.pool = events, evals, jobs, pool
         return r
+
+
+SWITCH_MEM = (5.0, 8.0, 0.2)          # worker_mem, ps_mem, p_w_mem (core/models.py:24-26)
+
+
+class SwitchCluster:
+    """Node tables of the legacy switch-local yarn placement (oracle/switch_oracle.c); place() is one
+    _Cluster.ms_yarn_placement call and mutates the tables on success."""
+
+    def __init__(self, S, P, G, free_gpus, free_cpus, free_mem):
+        self.S, self.P, self.G = S, P, G
+        self.free_gpus = np.ascontiguousarray(free_gpus, dtype=np.int32).copy()
+        self.free_cpus = np.ascontiguousarray(free_cpus, dtype=np.int32).copy()
+        self.free_mem = np.ascontiguousarray(free_mem, dtype=np.float64).copy()
+        self.net_in = np.zeros(S * P, dtype=np.float64)
+
+    def place(self, num_gpu, model_size, ps_network):
+        ps = np.ascontiguousarray(ps_network, dtype=np.float64)
+        cap = self.P + 1
+        sw = C.c_int32(-1)
+        node, gpu, cpu = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+        mem, net = np.zeros(cap), np.zeros(cap)
+        k = lib().switch_yarn_place(C.c_int(self.S), C.c_int(self.P), C.c_int(self.G), _p(self.free_gpus), _p(self.free_cpus),
+                                    _p(self.free_mem), _p(self.net_in), C.c_int(int(num_gpu)), C.c_double(float(model_size)),
+                                    _p(ps), C.c_int(len(ps)), C.c_double(SWITCH_MEM[0]), C.c_double(SWITCH_MEM[1]),
+                                    C.c_double(SWITCH_MEM[2]), C.byref(sw), _p(node), _p(gpu), _p(cpu), _p(mem), _p(net))
+        return k, sw.value, node[:k], gpu[:k], cpu[:k], mem[:k], net[:k]

@@ -26,6 +26,9 @@ def _worker(rank, world, port, out):
     total = red.sum(events)
     worst = red.max(ms)
     lo, hi = gd.shard_range(11, rank, world)
+    # sharded single simulation: every rank ends up with every rank's exchange-buffer handle, in rank order
+    handles = gd.exchange_comm_handles(bytes([rank + 1]) * 64, world)
+    assert handles == [bytes([r + 1]) * 64 for r in range(world)]
     out.put((rank, seeds, total, worst, (lo, hi)))
     dist.destroy_process_group()
 
@@ -55,7 +58,7 @@ def test_reference_arm_runs_on_rank0_only(monkeypatch, capsys):
     import bench
     monkeypatch.setenv("RANK", "1")
     monkeypatch.setenv("WORLD_SIZE", "2")
-    args = type("A", (), dict(jobs=200, steps=1, warmup=0, cpu_threads=1))()
+    args = type("A", (), dict(jobs=200, steps=1, warmup=0, cpu_threads=1, replicas=4736))()
     bench.reference(args)                          # non-zero ranks exit without work or output
     assert capsys.readouterr().out == ""
     monkeypatch.setenv("RANK", "0")
@@ -63,6 +66,7 @@ def test_reference_arm_runs_on_rank0_only(monkeypatch, capsys):
     import json
     line = json.loads(capsys.readouterr().out)
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"] == bench.config_block(200, 4736)         # the same `config` the GPU arm prints
 
 
 def test_replica_seed_validation():
@@ -70,3 +74,14 @@ def test_replica_seed_validation():
     with pytest.raises(ValueError):
         gd.replica_seeds(2, 2, 4)
     assert gd.shard_range(10, 0, 3) == (0, 4) and gd.shard_range(10, 2, 3) == (7, 10)
+
+
+def test_chunk_owner_partitions_the_runnable_list():
+    from gpuschedule_b200 import dist as gd
+    for world in (1, 2, 4, 8):
+        owners = [gd.chunk_owner(c, world) for c in range(64)]
+        assert set(owners) == set(range(world))
+        for r in range(world):
+            assert owners.count(r) == 64 // world          # balanced round robin
+    with pytest.raises(ValueError):
+        gd.exchange_comm_handles(b"short", 2)
