@@ -247,8 +247,14 @@ def ours(args):
     cluster = capi.make_cluster(4, 32, 8)
     M, G = 128, 8
     t0 = time.time()
-    tables = [fast_table(n, sd) for sd in gdist.replica_seeds(rank, world, R, base=BASE_SEED)]
-    log(f"[rank {rank}] generated {R} traces of {n} jobs in {time.time() - t0:.1f}s")
+    seeds = gdist.replica_seeds(rank, world, R, base=BASE_SEED)
+    if args.distinct and args.distinct < R:              # development only: fewer distinct traces, reused round robin
+        seeds = [seeds[i % args.distinct] for i in range(R)]
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(min(32, len(os.sched_getaffinity(0)))) as ex:      # numpy releases the GIL in the generators
+        made = dict(zip(sorted(set(seeds)), ex.map(lambda sd: fast_table(n, sd), sorted(set(seeds)))))
+    tables = [made[sd] for sd in seeds]
+    log(f"[rank {rank}] generated {len(made)} traces of {n} jobs in {time.time() - t0:.1f}s")
 
     if args.policy != "fifo":
         # secondary mode: one event-driven policy alone (device-timed value, roofline, oracle check of replica 0)
@@ -369,8 +375,12 @@ def ours(args):
     errors = []
     start_evt = threading.Barrier(K + 1)
     numa = numa_cpus_of_gpu(local)
+    stagger_unit = 0.25 + 0.6 * (dev_ms / args.steps / 1e3)       # rough length of a step's copy phases, seconds
     span_max = max(int(w.spans_used) for w in wins) + 64
     out_bytes = 32 * rows_cap + 32 * qrows_cap + 8 * n + 4 * n + 16 * span_max
+
+    import ctypes as C
+    numa = None if args.no_numa else numa
 
     def worker(k):
         try:
@@ -383,11 +393,12 @@ def ours(args):
             e.set_queue_rows_cap(qrows_cap)
             pin_in = capi.PinnedBuffer(len(mine) * n * 32)
             pin_out = capi.PinnedBuffer(len(mine) * out_bytes)
-            ins, outs = [], []
+            ins, outs, optr = [], [], []
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
             for i, r in enumerate(mine):
                 v = pin_in.view(capi.JOBIN_DTYPE, n, i * n * 32)
                 v[:] = tables[r].packed()                 # the step's inputs live in host memory
-                ins.append(v)
+                ins.append((v, vp(v)))
                 o = i * out_bytes
                 ev = pin_out.view(lm.EVROW_DTYPE, rows_cap, o); o += 32 * rows_cap
                 qr = pin_out.view(lm.QROW_DTYPE, qrows_cap, o); o += 32 * qrows_cap
@@ -395,37 +406,46 @@ def ours(args):
                 od = pin_out.view(np.int32, n, o); o += 4 * n
                 sp = pin_out.view(lm.SPAN_DTYPE, span_max, o)
                 outs.append((ev, qr, jb, od, sp))
+                optr.append((vp(ev), vp(qr), vp(jb), vp(od), vp(sp)))
                 e.config(i, cluster)
-            ph = dict(load=0.0, run=0.0, fetch=0.0)
+            lib, h = e.lib, e.h
+            ph = dict(load=0.0, run=0.0, fetch_enqueue=0.0, fetch_wait=0.0, check=0.0)
             h2d = d2h = chk = ev_cnt = 0
+            win = capi.GsWindowInfo()
             for step in range(e2e_steps + 1):            # step 0 = untimed warm-up (allocations)
                 if step == 1:
                     start_evt.wait()                      # all threads + main: timed region starts
-                    ph = dict(load=0.0, run=0.0, fetch=0.0)
+                    ph = dict(load=0.0, run=0.0, fetch_enqueue=0.0, fetch_wait=0.0, check=0.0)
                     h2d = d2h = chk = ev_cnt = 0
+                    if k % 2 == 1 and args.e2e_stagger > 0:
+                        time.sleep(args.e2e_stagger * stagger_unit)     # odd threads run half a step behind the even ones
                 c0 = time.perf_counter()
                 for i in range(len(mine)):
-                    e.load_trace_packed(i, ins[i])
+                    if lib.gs_load_trace_packed(h, i, n, ins[i][1], None, None) != 0:
+                        raise capi.GsError("gs_load_trace_packed failed")
                     h2d += n * 32
                 c1 = time.perf_counter(); ph["load"] += c1 - c0
                 run_to_done(e, rows_cap)
                 c2 = time.perf_counter(); ph["run"] += c2 - c1
                 ws = []
                 for i in range(len(mine)):
-                    w = e.window(i)
-                    evb, qrb, jb, od, sp = outs[i]
-                    e.fetch_compact_into(i, evb, qrb, jb, None, od, sp)
-                    ws.append(w)
+                    lib.gs_window(h, i, C.byref(win))
+                    p_ev, p_qr, p_jb, p_od, p_sp = optr[i]
+                    if lib.gs_fetch_compact(h, i, p_ev, p_qr, p_jb, None, p_od, p_sp) != 0:
+                        raise capi.GsError("gs_fetch_compact failed")
+                    ws.append((win.ev_rows, win.q_rows, win.finished, win.spans_used, win.ticks, win.row_first))
+                c3 = time.perf_counter(); ph["fetch_enqueue"] += c3 - c2
                 e.sync()
-                for i, w in enumerate(ws):
+                c4 = time.perf_counter(); ph["fetch_wait"] += c4 - c3
+                for i, (ner, nqr, nfin, nsp, _, _) in enumerate(ws):
                     evb, qrb, jb, od, sp = outs[i]
-                    d2h += 32 * (w.ev_rows + w.q_rows) + 8 * w.n + 4 * w.finished + 16 * w.spans_used
-                    chk += int(evb["finished"][w.ev_rows - 1]) + int(jb["start"][0]) + int(od[w.finished - 1]) + int(sp["node"][w.spans_used - 1])
-                    ev_cnt += e.stats(i).events
-                ph["fetch"] += time.perf_counter() - c2
+                    d2h += 32 * (ner + nqr) + 8 * n + 4 * nfin + 16 * nsp
+                    chk += int(evb[ner - 1]["finished"]) + int(jb[0]["start"]) + int(od[nfin - 1]) + int(sp[nsp - 1]["node"])
+                    ev_cnt += n + 2 * nfin               # arrivals + starts + completions of a finished run
+                ph["check"] += time.perf_counter() - c4
             # the records really are the run: decode one replica of this thread and compare with the value run
-            w = ws[0]
-            rows = lm.expand_rows(outs[0][0][:w.ev_rows], outs[0][1][:w.q_rows], w.row_first, w.ticks, M, G)
+            ner, nqr, nfin, nsp, tk, rf = ws[0]
+            rows = lm.expand_rows(outs[0][0][:ner], outs[0][1][:nqr], rf, tk, M, G)
             assert len(rows) == ticks[mine[0]] and int(rows["finished"][-1]) == n and int(rows["now"][-1]) == ticks[mine[0]]
             results[k] = (ph, h2d // e2e_steps, d2h // e2e_steps, chk, ev_cnt // e2e_steps)
             pin_in.free(); pin_out.free()
@@ -455,7 +475,7 @@ def ours(args):
     h2d = sum(r[1] for r in results); d2h = sum(r[2] for r in results)
     checksum = sum(r[3] for r in results)
     assert sum(r[4] for r in results) == events_rank, "e2e run simulated a different number of events"
-    ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "fetch")}
+    ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "fetch_enqueue", "fetch_wait", "check")}
     e2e = {"value": events_all / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(red.sum(h2d)), "d2h_bytes_per_step": int(red.sum(d2h)),
            "steps": e2e_steps, "host_threads": K, "pinned_buffers_numa_local": bool(numa),
@@ -463,6 +483,23 @@ def ours(args):
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
            "result_format": "compact records (gs_evrow/gs_qrow/gs_job_run/finish order/spans); one replica per thread is decoded to full rows and checked",
            "checksum": checksum}
+
+    if args.e2e_only:
+        probe = {}
+        try:                                              # what one stream gets out of the link, for orientation
+            hbuf = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+            dbuf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+            for name, (dst, src) in (("d2h", (hbuf, dbuf)), ("h2d", (dbuf, hbuf))):
+                dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+                t0 = time.perf_counter(); dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+                probe[name + "_gbs_1GiB_one_stream"] = (1 << 30) / (time.perf_counter() - t0) / 1e9
+        except Exception as exc:
+            probe["error"] = repr(exc)
+        if rank == 0:
+            print(json.dumps({"e2e": e2e, "copy_probe": probe, "value": value, "replicas_per_gpu": R}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- secondary measurements (rank 0, N=1): the event-driven policies of BASELINE configs C2-C4 on the same
     # cluster (device-timed, 1 warm-up + 1 timed run each, replica 0 checked against the oracle) and the stateless scoring kernel
@@ -820,6 +857,10 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--value-only", action="store_true", help="kernel experiments: print the device-timed value and stop")
+    ap.add_argument("--e2e-only", action="store_true", help="development: print the end-to-end block (with a copy-bandwidth probe) and stop")
+    ap.add_argument("--e2e-stagger", type=float, default=0.5, help="fraction of a step by which every second host thread starts late, so that uploads, kernels and read-backs of different threads overlap")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the e2e threads to the GPU's NUMA node")
+    ap.add_argument("--distinct", type=int, default=0, help="development: number of distinct traces (0 = one per replica)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
     ap.add_argument("--policy-replicas", type=int, default=1024)
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-simulation-on-N-GPUs block (config C4)")

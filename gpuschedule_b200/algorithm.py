@@ -43,22 +43,48 @@ def ms_yarn_placement(infrastructure, next_job, scheme):
     nodes = {}
     tab = infrastructure.table
     gmask = (1 << infrastructure.num_gpu_p_node) - 1
+    held = getattr(next_job, "held", None)
     for t in range(tasks):
         nd = int(task_node[t])
         idle = ~int(tab["busy_mask"][nd]) & gmask
-        tab["busy_mask"][nd] = int(tab["busy_mask"][nd]) | _lowest_bits(idle, gpc)
+        take = _lowest_bits(idle, gpc)
+        tab["busy_mask"][nd] = int(tab["busy_mask"][nd]) | take
         tab["cpu_used"][nd] += cl.cpu_per_task
         tab["mem_used"][nd] += cl.mem_per_task
+        if held is not None:
+            held.append((nd, take))
         next_job.tasks_running_on["%s_worker%d" % (next_job.job_id, t)] = str(nd + 1)
         nodes[str(nd + 1)] = infrastructure.nodes[str(nd + 1)]
     return nodes, True
 
 
 def schedule_fifo(scheme, placement_algo, infrastructure, jobs_manager, delta, **kwargs):
-    """(algorithm.py:189-202) kept for API shape; the engine runs the fused loop."""
-    raise NotImplementedError("per-call fifo stepping is fused into Scheduler.start() on the device")
+    """-> (nodes or None, job or None, success or None)   (algorithm.py:189-202): one attempt on the queue head; the
+    placement itself is the GPU call behind `placement_algo`.  Scheduler.start() runs the fused loop on the device;
+    this entry point is the same step driven from the host, one call per tick, like the reference drives it."""
+    next_job = jobs_manager.get_next_job(delta)
+    if next_job is None:
+        return None, None, None
+    nodes, success = placement_algo(infrastructure, next_job, scheme)
+    if success:
+        jobs_manager.pop(delta)
+    return nodes, next_job, success
+
+
+def release_job(infrastructure, job):
+    """Node.release_allocated_resources for every task of a finished job (node.py:71-91): devices, cpu and memory of
+    what ms_yarn_placement committed go back to the node table."""
+    cl = infrastructure.gs_cluster()
+    tab = infrastructure.table
+    for nd, take in job.held:
+        tab["busy_mask"][nd] = int(tab["busy_mask"][nd]) & ~take
+        tab["cpu_used"][nd] -= cl.cpu_per_task
+        tab["mem_used"][nd] -= cl.mem_per_task
+    job.held = []
 
 
 placement_algorithms = {"yarn": ms_yarn_placement}
 scheduling_algorithms = {"fifo": schedule_fifo}
+# the reference registers only gandiva's time-slice hook here (algorithm.py:442-444); that policy runs inside the
+# utilisation-aware engine (schedule.py: _start_utilisation_aware), so nothing is hooked per tick on this side
 plugin_algorithms = {}

@@ -47,6 +47,15 @@ class GsRunStats(C.Structure):
                 ("d2h_ms", C.c_double)]
 
 
+SWITCH_CLUSTER_DTYPE = np.dtype([("num_switch", "<i4"), ("num_node_p_switch", "<i4"), ("num_gpu_p_node", "<i4"), ("reserved", "<i4"),
+                                 ("node_off", "<i8"), ("job_off", "<i8"), ("job_cnt", "<i8")])
+SWITCH_NODE_DTYPE = np.dtype([("free_gpus", "<i4"), ("free_cpus", "<i4"), ("free_mem", "<f8"), ("net_in", "<f8")])
+SWITCH_JOB_DTYPE = np.dtype([("num_gpu", "<i4"), ("n_ps", "<i4"), ("ps_off", "<i8"), ("span_off", "<i8"), ("model_size", "<f8")])
+SWITCH_ANS_DTYPE = np.dtype([("n_nodes", "<i4"), ("sw", "<i4")])
+SWITCH_SPAN_DTYPE = np.dtype([("node", "<i4"), ("num_gpu", "<i4"), ("num_cpu", "<i4"), ("reserved", "<i4"), ("mem", "<f8"), ("network", "<f8")])
+SWITCH_MEM = (5.0, 8.0, 0.2)          # worker_mem, ps_mem, p_w_mem: core/models.py:24-26 of the reference
+
+
 class GsWindowInfo(C.Structure):
     _fields_ = [("row_first", C.c_int64), ("ticks", C.c_int64), ("ev_rows", C.c_int64), ("q_rows", C.c_int64),
                 ("spans_used", C.c_int64), ("admitted", C.c_int64), ("finished", C.c_int64), ("n", C.c_int64)]
@@ -204,6 +213,9 @@ def load_library():
     lib.gs_set_queue_rows_cap.argtypes = [C.c_void_p, C.c_int64]
     for name in ("gs_window", "gs_fetch_compact", "gs_sync", "gs_set_async", "gs_set_queue_rows_cap"):
         getattr(lib, name).restype = C.c_int
+    lib.gs_switch_yarn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, f64p, C.c_int64,
+                                   C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.gs_switch_yarn.restype = C.c_int
     lib.gs_comm_prepare.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.gs_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.gs_comm_stats.argtypes = [C.c_void_p, i64p, f64p]
@@ -465,6 +477,41 @@ class Engine:
         self.sync()
         return (w, ev[:int(w.ev_rows)], qr[:int(w.q_rows)], jobs[:n], (None if n == 0 or np.isnan(dur[0]) else dur[:n]),
                 order[:int(w.finished)], spans[:int(w.spans_used)])
+
+    def switch_yarn(self, clusters, mem=SWITCH_MEM):
+        """Legacy switch-local yarn placement with PS traffic (include/gsched.h: gs_switch_yarn).
+        clusters: list of dicts {num_switch, num_node_p_switch, num_gpu_p_node, free_gpus[], free_cpus[], free_mem[],
+        jobs: [(num_gpu, model_size, ps_network list)]}.  Returns per cluster (answers[(n_nodes, switch, spans)], node table)."""
+        ncl = len(clusters)
+        cl = np.zeros(ncl, dtype=SWITCH_CLUSTER_DTYPE)
+        nodes, jobs, ps = [], [], []
+        n_spans = 0
+        for i, c in enumerate(clusters):
+            m = c["num_switch"] * c["num_node_p_switch"]
+            cl[i] = (c["num_switch"], c["num_node_p_switch"], c["num_gpu_p_node"], 0, len(nodes), len(jobs), len(c["jobs"]))
+            for k in range(m):
+                nodes.append((c["free_gpus"][k], c["free_cpus"][k], c["free_mem"][k], 0.0))
+            for g, model, psn in c["jobs"]:
+                jobs.append((g, len(psn), len(ps), n_spans, model))
+                ps.extend(psn)
+                n_spans += g // c["num_gpu_p_node"] + 1
+        nodes = np.array(nodes, dtype=SWITCH_NODE_DTYPE)
+        jobs = np.array(jobs, dtype=SWITCH_JOB_DTYPE) if jobs else np.zeros(0, dtype=SWITCH_JOB_DTYPE)
+        ps = np.ascontiguousarray(ps, dtype=np.float64)
+        ans = np.zeros(max(len(jobs), 1), dtype=SWITCH_ANS_DTYPE)
+        spans = np.zeros(max(n_spans, 1), dtype=SWITCH_SPAN_DTYPE)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.gs_switch_yarn(self.h, ncl, vp(cl), vp(nodes), len(nodes), vp(jobs), len(jobs), _ptr(ps, C.c_double), len(ps),
+                                            mem[0], mem[1], mem[2], vp(ans), vp(spans), n_spans), "gs_switch_yarn")
+        out = []
+        for i in range(ncl):
+            jo, jc, no = int(cl["job_off"][i]), int(cl["job_cnt"][i]), int(cl["node_off"][i])
+            res = []
+            for j in range(jo, jo + jc):
+                k, so = int(ans["n_nodes"][j]), int(jobs["span_off"][j])
+                res.append((k, int(ans["sw"][j]), spans[so:so + k].copy()))
+            out.append((res, nodes[no:no + clusters[i]["num_switch"] * clusters[i]["num_node_p_switch"]].copy()))
+        return out
 
     # ---- one simulation on several GPUs of one box (gittins; include/gsched.h: gs_comm_*)
     def comm_prepare(self, max_jobs) -> bytes:

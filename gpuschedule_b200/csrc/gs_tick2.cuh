@@ -281,12 +281,13 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         if (found >= 0 && span_used + 1 > span_cap) { status = GS_ERR_CAPACITY; found = -1; }
         if (found >= 0) {
           ok = true; nspans = 1;
-          const unsigned long long take = take_lowest(~busy[found] & gmask, hg, G);
+          // warp-uniform update: every lane reads the same words and writes the same values (no lane-0 branch, no sync)
+          const unsigned long long bz = busy[found];
+          const unsigned long long take = take_lowest(~bz & gmask, hg, G);
           const unsigned kv = kk[found];
-          __syncwarp();
-          if (lane == 0) {
-            busy[found] |= take;
-            kk[found] = (kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u;
+          busy[found] = bz | take;
+          kk[found] = (kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u;
+          {
             gs_span sp; sp.node = found; sp.ntasks = htasks | (int)0x80000000; sp.devmask = take;
             __stcs(reinterpret_cast<int4 *>(&spans[span_first]), *reinterpret_cast<const int4 *>(&sp));
           }
@@ -347,11 +348,12 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
           where = (int)0x80000000 | span_first;
           mask0 = (unsigned long long)(unsigned)nspans | ((unsigned long long)(unsigned)hg << 32);
           evals += last_node + 1;
+          __syncwarp();        // lanes updated different nodes
         } else {
           evals += M;
+          __syncwarp();        // (the unplaceable walk charges nodes lane by lane)
         }
       }
-      __syncwarp();
       if (ok) {
         // ---- commit: pop, network cost, start (algorithm.py:198-200, schedule.py:49-54,164-167)
         const int j = hjob;
@@ -379,19 +381,16 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         else if (endt == next_fin) { js.next = nf_head; nf_head = j; nf_js = js; }
         else js.next = whead[bk];
         const long long wm = wmem[bk];
-        if (lane == 0) {
-          whead[bk] = j;
-          wmem[bk] = wm + hmemc;
-          *reinterpret_cast<int4 *>(&jst[j]) = *reinterpret_cast<const int4 *>(&js);
-          __stcs(&rec2[j], make_int2(delta, need));
-        }
+        whead[bk] = j;                                   // warp-uniform stores (same address, same value from every lane)
+        wmem[bk] = wm + hmemc;
+        *reinterpret_cast<int4 *>(&jst[j]) = *reinterpret_cast<const int4 *>(&js);
+        __stcs(&rec2[j], make_int2(delta, need));
         top -= 1;
         sum_arr -= harr;
         running += 1;
         busy_gpus += hg;
         mem_busy += hmemc;
         hvalid = false; changed = true;
-        __syncwarp();
       } else if (placeable) {
         blocked = 1;           // nothing can change the outcome before a completion or a new head
       }
@@ -409,8 +408,12 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
       while (true) {
         if (js.where >= 0) {
           const int nd = js.where & 0xfffff, nt = ((js.where >> 20) & 63) + 1;
-          if (lane == 0) { busy[nd] &= ~js.mask0; kk[nd] += (unsigned)__popcll(js.mask0) + ((unsigned)nt << 16); }
-          busy_gpus -= __popcll(js.mask0);
+          const int gp = __popcll(js.mask0);
+          const unsigned long long bz = busy[nd];        // warp-uniform read-modify-write
+          const unsigned kv = kk[nd];
+          busy[nd] = bz & ~js.mask0;
+          kk[nd] = kv + (unsigned)gp + ((unsigned)nt << 16);
+          busy_gpus -= gp;
         } else {
           const int first = js.where & 0x7fffffff, scnt = (int)(unsigned)(js.mask0 & 0xffffffffull);
           for (int i = lane; i < scnt; i += 32) {
@@ -419,18 +422,17 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
             kk[sp.node] += (unsigned)__popcll(sp.devmask) + ((unsigned)(sp.ntasks & 0x7fffffff) << 16);
           }
           busy_gpus -= (int)(unsigned)(js.mask0 >> 32);
+          __syncwarp();          // lanes updated different nodes
         }
-        if (lane == 0) fin[f0 + c] = h;
+        fin[f0 + c] = h;
         c += 1;
         h = js.next;
         if (h < 0) break;
         js = jst[h];
-        __syncwarp();          // the next job may give devices back to the same node from another lane
       }
       finished += c; running -= c;
       mem_busy -= wm;
-      if (lane == 0) { whead[sl] = -1; wmem[sl] = 0; }
-      __syncwarp();
+      whead[sl] = -1; wmem[sl] = 0;
       if (c >= 2) {          // the bucket was walked newest first; job.csv lists equal finish ticks in start order
         for (int i = lane; i < (c >> 1); i += 32) { const int a = fin[f0 + i], b2 = fin[f0 + c - 1 - i]; fin[f0 + i] = b2; fin[f0 + c - 1 - i] = a; }
         __syncwarp();
@@ -461,16 +463,12 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         if (hvalid && ihi == top - 1) a_hi = harr;
         else a_hi = ihi >= cache_lo ? sstk[ihi & (SCACHE - 1)].y : stack[ihi].y;
         qidx = nb;
-        if (lane == 0) {
-          __stcs(&rowB[2 * nb], make_int4((int)(sum_arr & 0xffffffffLL), (int)(sum_arr >> 32), bottom_arr, a_lo));
-          __stcs(&rowB[2 * nb + 1], make_int4(a_hi, 0, 0, 0));
-        }
+        __stcs(&rowB[2 * nb], make_int4((int)(sum_arr & 0xffffffffLL), (int)(sum_arr >> 32), bottom_arr, a_lo));
+        __stcs(&rowB[2 * nb + 1], make_int4(a_hi, 0, 0, 0));
         nb += 1;
       }
-      if (lane == 0) {
-        __stcs(&rowA[2 * na], make_int4(now, top, finished, busy_gpus | (running << 16)));
-        __stcs(&rowA[2 * na + 1], make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), ever, qidx));
-      }
+      __stcs(&rowA[2 * na], make_int4(now, top, finished, busy_gpus | (running << 16)));
+      __stcs(&rowA[2 * na + 1], make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), ever, qidx));
       na += 1;
     }
     delta = now;

@@ -48,6 +48,7 @@
 #include "gs_tick2.cuh"
 #include "gs_policy.cuh"
 #include "gs_aux.cuh"
+#include "gs_switch.cuh"
 
 // ------------------------------------------------------------------ host side
 
@@ -865,6 +866,60 @@ extern "C" int gs_net_cost(gs_handle h, const gs_cluster *cluster, int64_t b, co
   CU(cudaGetLastError());
   h->launches += 1;
   return timed_d2h(h, extra_out, d + o_out, 8 * (size_t)b);
+}
+
+extern "C" int gs_switch_yarn(gs_handle h, int32_t ncl, const gs_switch_cluster *clusters, gs_switch_node *nodes, int64_t n_nodes,
+                              const gs_switch_job *jobs, int64_t n_jobs, const double *ps_network, int64_t n_ps,
+                              double worker_mem, double ps_mem, double p_w_mem,
+                              gs_switch_ans *ans, gs_switch_span *spans, int64_t n_spans) {
+  if (!h) return GS_ERR_ARG;
+  if (ncl < 0 || n_nodes < 0 || n_jobs < 0 || n_ps < 0 || n_spans < 0 ||
+      (ncl > 0 && (!clusters || !nodes)) || (n_jobs > 0 && (!jobs || !ans || !spans)) || (n_ps > 0 && !ps_network))
+    return fail(h, GS_ERR_ARG, "gs_switch_yarn: bad arguments");
+  static_assert(sizeof(gs_switch_cluster) == 40 && sizeof(gs_switch_node) == 24 && sizeof(gs_switch_job) == 32 &&
+                sizeof(gs_switch_ans) == 8 && sizeof(gs_switch_span) == 32, "switch record layout");
+  for (int32_t c = 0; c < ncl; ++c) {
+    const gs_switch_cluster &cl = clusters[c];
+    const int64_t m = (int64_t)cl.num_switch * cl.num_node_p_switch;
+    if (cl.num_switch <= 0 || cl.num_node_p_switch <= 0 || cl.num_gpu_p_node <= 0 || cl.node_off < 0 || cl.node_off + m > n_nodes ||
+        cl.job_off < 0 || cl.job_cnt < 0 || cl.job_off + cl.job_cnt > n_jobs)
+      return fail(h, GS_ERR_ARG, "gs_switch_yarn: a cluster record points outside the tables");
+    for (int64_t j = cl.job_off; j < cl.job_off + cl.job_cnt; ++j) {
+      const gs_switch_job &jb = jobs[j];
+      const int64_t slots = jb.num_gpu / cl.num_gpu_p_node + 1;
+      if (jb.num_gpu <= 0 || jb.n_ps < 0 || jb.ps_off < 0 || jb.ps_off + jb.n_ps > n_ps || jb.span_off < 0 || jb.span_off + slots > n_spans)
+        return fail(h, GS_ERR_ARG, "gs_switch_yarn: a job record points outside the tables (spans need num_gpu / G + 1 slots)");
+    }
+  }
+  if (ncl == 0 || n_jobs == 0) return GS_OK;
+  CU(cudaSetDevice(h->device));
+  size_t total = 0;
+  auto take = [&](size_t bytes) { const size_t o = total; total = align_up(total + (bytes ? bytes : 1)); return o; };
+  const size_t o_cl = take(sizeof(gs_switch_cluster) * (size_t)ncl), o_nd = take(sizeof(gs_switch_node) * (size_t)n_nodes);
+  const size_t o_jb = take(sizeof(gs_switch_job) * (size_t)n_jobs), o_ps = take(8 * (size_t)n_ps);
+  const size_t o_an = take(sizeof(gs_switch_ans) * (size_t)n_jobs), o_sp = take(sizeof(gs_switch_span) * (size_t)n_spans);
+  int rc = ensure_scratch(h, total);
+  if (rc) return rc;
+  unsigned char *d = (unsigned char *)h->d_scratch;
+  CU(cudaMemcpyAsync(d + o_cl, clusters, sizeof(gs_switch_cluster) * (size_t)ncl, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d + o_nd, nodes, sizeof(gs_switch_node) * (size_t)n_nodes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d + o_jb, jobs, sizeof(gs_switch_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, h->stream));
+  if (n_ps > 0) CU(cudaMemcpyAsync(d + o_ps, ps_network, 8 * (size_t)n_ps, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(d + o_sp, 0, sizeof(gs_switch_span) * (size_t)n_spans, h->stream));
+  CU(cudaEventRecord(h->e0, h->stream));
+  gs_switch_yarn_kernel<<<(unsigned)ncl, 32, 0, h->stream>>>(ncl, (const gs_switch_cluster *)(d + o_cl), (gs_switch_node *)(d + o_nd),
+                                                            (const gs_switch_job *)(d + o_jb), (const double *)(d + o_ps),
+                                                            worker_mem, ps_mem, p_w_mem, (gs_switch_ans *)(d + o_an), (gs_switch_span *)(d + o_sp));
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaEventRecord(h->e1, h->stream));
+  CU(cudaMemcpyAsync(nodes, d + o_nd, sizeof(gs_switch_node) * (size_t)n_nodes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(ans, d + o_an, sizeof(gs_switch_ans) * (size_t)n_jobs, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(spans, d + o_sp, sizeof(gs_switch_span) * (size_t)n_spans, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->kernel_ms += ms;
+  return GS_OK;
 }
 
 // Restart every replica from tick 0 on the traces already resident in HBM.

@@ -31,6 +31,7 @@ class Job:
         self.model_size = model_size
         self.iterations = iterations
         self.tasks_running_on = {}
+        self.held = []                               # [(node index, device mask, tasks)] set by the placement call
         self.start_time = 0
         self.end_time = 0
         self.migration_count = 0
@@ -63,5 +64,38 @@ class JobsManager:
         self.running_jobs = {}
         self.finished_jobs = {}
 
+        self.queue = []                              # queue 0 of the reference, head = index 0
+        self._next_row = 0
+
     def remaining_jobs(self, delta_time=None):
-        return self.table.n
+        return self.table.n - self._next_row
+
+    # ---- per-call surface of the reference's JobsManager (jobs_manager.py:32-37,115-140,228-241), host mirror:
+    # the fused engine never calls these; they exist so that the registry entries of algorithm.py can be driven tick by
+    # tick like the reference drives them (tests/test_gpu_parity.py::test_per_call_registries_step_like_the_fused_loop)
+    def gen_jobs(self, delta_time, scale_factor=0.5):
+        """admit every trace row whose arrival tick is due; the batch lands at the HEAD of the queue (quirk Q2)"""
+        t = self.table
+        batch = []
+        while self._next_row < t.n and t.arrive_tick[self._next_row] <= delta_time:
+            j = self._next_row
+            job = Job(t.label[j] if t.label else j, float(t.duration[j]), int(t.submit[j]), int(t.gpu_per_task[j]),
+                      float(t.mem_bytes[j]) / 1048576.0, int(t.gpus[j]))
+            job.index = j
+            batch.append(job)
+            self._next_row += 1
+        self.insert(batch)
+        return batch
+
+    def insert(self, jobs):
+        jobs = jobs if isinstance(jobs, list) else [jobs]
+        self.queue[0:0] = jobs                       # positions 0..n-1 (jobs_manager.py:52-55,134-135)
+
+    def get_next_job(self, delta_time):
+        return self.queue[0] if self.queue and self.queue[0].submit_time <= delta_time else None
+
+    def pop(self, delta_time):
+        return self.queue.pop(0)
+
+    def queuing_jobs(self, delta_time=None):
+        return len(self.queue)

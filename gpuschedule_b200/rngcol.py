@@ -61,14 +61,17 @@ def busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans, chunk
         cand = cand[last[cand] >= r0]
         rows_n = r1 - r0
         # +(job+1) where a holding starts (or continues into the chunk), -(job+1) on the first row after it;
-        # devices host one job at a time, so a running sum down each column is the owner (+1), 0 = idle
-        marks = np.zeros((rows_n + 1, width), dtype=np.int32)
+        # devices host one job at a time, so a running sum along each device's row is the owner (+1), 0 = idle.
+        # The grid is kept device-major so that the running sum walks contiguous memory, then transposed once.
+        ukeys, kidx = np.unique(hold_key[cand], return_inverse=True)    # only devices that host something in this chunk
+        marks = np.zeros((len(ukeys), rows_n + 1), dtype=np.int32)
         a = np.maximum(first[cand], r0) - r0
         b = np.minimum(last[cand], r1 - 1) - r0 + 1                 # first row after the holding (<= rows_n)
         val = (hold_job[cand] + 1).astype(np.int32)
-        np.add.at(marks, (a, hold_key[cand]), val)
-        np.add.at(marks, (b, hold_key[cand]), -val)
-        filled = np.cumsum(marks[:rows_n], axis=0, dtype=np.int32)
+        np.add.at(marks, (kidx, a), val)
+        np.add.at(marks, (kidx, b), -val)
+        np.cumsum(marks, axis=1, out=marks)
+        filled = np.ascontiguousarray(marks[:, :rows_n].T)            # (rows, devices in id order)
         busy = filled > 0
         active = cand[last[cand] >= r1]
         yield busy.sum(axis=1), filled[busy].astype(np.int64) - 1
@@ -103,13 +106,16 @@ def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, span
         vals = np.where(clipped, 100.0, draw)
         off = np.zeros(len(counts) + 1, dtype=np.int64)
         np.cumsum(counts, out=off[1:])
+        # sequential per-row accumulation (Python float additions, left to right): the draws of a chunk go into a
+        # (rows x widest row) matrix padded with 0.0 -- x + 0.0 == x -- and are added column by column
         acc = np.zeros(len(counts), dtype=np.float64)
-        order = np.argsort(-counts, kind="stable")                  # rows with many busy devices first
-        sorted_counts = counts[order]
-        for k in range(int(sorted_counts[0]) if len(counts) else 0):   # sequential per-row accumulation
-            m = int(np.searchsorted(-sorted_counts, -k, side="left"))  # rows with count > k
-            sel = order[:m]
-            acc[sel] = acc[sel] + vals[off[sel] + k]
+        if len(vals):
+            row_of = np.repeat(np.arange(len(counts)), counts)
+            pos_of = np.arange(len(vals)) - off[row_of]
+            mat = np.zeros((int(counts.max()), len(counts)), dtype=np.float64)
+            mat[pos_of, row_of] = vals
+            for k in range(mat.shape[0]):
+                acc += mat[k]
         csum = np.concatenate([[0], np.cumsum(~clipped)])
         n_arr = csum[off[1:]] - csum[off[:-1]]                      # un-clipped draws per row (numpy arrays)
         frac = acc / total

@@ -312,6 +312,34 @@ int gs_place_batch(gs_handle h, const gs_cluster *cluster, const gs_node *nodes,
                    int32_t *nodes_used, const int64_t *task_off, int32_t *task_node,
                    double *kernel_ms);
 
+/* ---- legacy switch-local yarn placement with parameter-server traffic accounting --------
+ * _Cluster.ms_yarn_placement (infra/cluster.py:888-898) over _Switch.try_cross_node_alloc / try_single_node_alloc
+ * (infra/switch.py:38-167,190-206): all gpus of a job come from ONE switch; a job wider than a node takes
+ * floor(g/G) completely idle nodes plus one node for the remainder, is charged 6 cpus per gpu and
+ * (ps_mem + g*p_w_mem + worker_mem) memory per gpu, and every node's network load grows by
+ *   round(model*k, 1), then per PS shard on the node:  += ps*(g-k);  -= ps*k;  round(., 1)     (switch.py:98-108)
+ * (Python's round, reproduced exactly).  `ncl` independent clusters per call; the jobs of a cluster are placed in
+ * order and change its node table (in/out).  spans: caller-sized, job j writes at span_off (floor(g/G)+1 slots);
+ * network is NaN on the single-node path (the reference records none there).                              */
+typedef struct gs_switch_cluster {
+  int32_t num_switch, num_node_p_switch, num_gpu_p_node, reserved;
+  int64_t node_off;        /* first record of this cluster in `nodes` (num_switch * num_node_p_switch records)   */
+  int64_t job_off, job_cnt;
+} gs_switch_cluster;
+typedef struct gs_switch_node { int32_t free_gpus, free_cpus; double free_mem; double net_in; } gs_switch_node;
+typedef struct gs_switch_job {
+  int32_t num_gpu, n_ps;   /* job['num_gpu'], len(job['ps_network'])                                             */
+  int64_t ps_off;          /* first entry of the job's ps_network in `ps_network`                                */
+  int64_t span_off;        /* where the job's per-node records go in `spans`                                     */
+  double model_size;       /* job['model']['total_size']                                                         */
+} gs_switch_job;
+typedef struct gs_switch_ans { int32_t n_nodes; int32_t sw; } gs_switch_ans;   /* n_nodes == 0: not placed      */
+typedef struct gs_switch_span { int32_t node, num_gpu, num_cpu, reserved; double mem, network; } gs_switch_span;
+int gs_switch_yarn(gs_handle h, int32_t ncl, const gs_switch_cluster *clusters, gs_switch_node *nodes, int64_t n_nodes,
+                   const gs_switch_job *jobs, int64_t n_jobs, const double *ps_network, int64_t n_ps,
+                   double worker_mem, double ps_mem, double p_w_mem,
+                   gs_switch_ans *ans, gs_switch_span *spans, int64_t n_spans);
+
 /* PS<->worker transfer time for a batch of placed jobs.  task_node holds the
  * node of every task (segments given by task_off), is_ps marks PS tasks.        */
 int gs_net_cost(gs_handle h, const gs_cluster *cluster, int64_t b,

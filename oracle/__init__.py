@@ -298,7 +298,8 @@ class Tight2:
                      arr(table.duration, np.float64), arr(table.mem_bytes, np.int64))
         a, g, c, d, mm = self.cols
         self.h = C.c_void_p(lib().tight2_create(C.byref(cluster), C.c_int64(self.n), _p(a), _p(g), _p(c), _p(d), _p(mm), C.c_int64(span_cap)))
-        worst = int(table.arrive_tick[-1] if self.n else 0) + 2 * int(np.ceil(table.duration.max()) if self.n else 0) + 4096
+        # at most one job starts per tick, so a saturated run lasts at least n ticks
+        worst = max(int(table.arrive_tick[-1] if self.n else 0), self.n) + 2 * int(np.ceil(table.duration.max()) if self.n else 0) + 4096
         self.cap = worst
         self.ev = np.zeros(worst, dtype=EVROW_DTYPE)
         self.qr = np.zeros(worst, dtype=QROW_DTYPE)

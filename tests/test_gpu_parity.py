@@ -509,3 +509,45 @@ def test_async_load_and_fetch_from_pinned_buffers():
                 pb.free()
     for pb in pin_in:
         pb.free()
+
+
+def test_per_call_registries_step_like_the_fused_loop():
+    """scheduling_algorithms['fifo'] / placement_algorithms['yarn'] driven from the host one tick at a time, the way the
+    reference's Scheduler.start drives its registries (schedule.py:185-209): same start tick, same nodes and same finish
+    order as the fused device loop -- which is pinned to the reference's bytes."""
+    import math
+    import os
+    from types import SimpleNamespace
+    from conftest import GOLDEN
+    from gpuschedule_b200 import algorithm, capi
+    from gpuschedule_b200.infrastructure import Infrastructure
+    from gpuschedule_b200.jobs import JobQueueManager, JobsManager
+    for case in ("kat0", "n64"):
+        table, cluster, meta, _, _ = load_golden(case)
+        rows, recs, order, span_off, spans, st = _engine_run(cluster, table)[0]
+        flags = SimpleNamespace(num_switch=cluster.num_switch, num_node_p_switch=cluster.num_node_p_switch,
+                                num_gpu_p_node=cluster.num_gpu_p_node, num_cpu_p_node=cluster.num_cpu_p_node, mem_p_node=cluster.mem_p_node,
+                                gpu_memory_capacity=cluster.gpu_mem_cap_mib // 1024, enable_network_costs=False, bandwidth=1250,
+                                internode_latency=0.015, schedule="fifo", scheme="yarn", num_queue=1,
+                                trace_file=os.path.join(GOLDEN, case, "trace.csv"))
+        infra = Infrastructure(flags)
+        jm = JobsManager(flags, JobQueueManager(flags))
+        running, finished, delta = [], [], 0
+        while jm.remaining_jobs() + len(running) > 0:
+            jm.gen_jobs(delta)
+            if jm.queuing_jobs() > 0:
+                nodes, job, ok = algorithm.scheduling_algorithms["fifo"]("yarn", algorithm.placement_algorithms["yarn"], infra, jm, delta)
+                if ok:
+                    job.start_time = delta
+                    job.end_time = delta + max(1, math.ceil(job.duration))
+                    running.append(job)
+                    assert sorted(int(k) - 1 for k in nodes) == sorted(spans["node"][span_off[job.index]:span_off[job.index + 1]].tolist())
+            delta += 1
+            for job in [j for j in running if j.end_time == delta]:
+                algorithm.release_job(infra, job)
+                running.remove(job)
+                finished.append(job)
+        assert delta == st.ticks
+        assert [j.index for j in finished] == order.tolist()
+        for j in finished:
+            assert (j.start_time, j.end_time) == (int(recs["start"][j.index]), int(recs["end"][j.index]))

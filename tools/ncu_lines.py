@@ -33,8 +33,8 @@ def src_line(fname, line):
     return src[line - 1].strip()[:95] if 0 < line <= len(src) else "?"
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+                for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))      # every translation unit's cubin
 off2line, cur, infn = {}, ("", 0), False
 for ln in dis.split("\n"):
     if ln.startswith(".text."):
@@ -66,6 +66,7 @@ for r in rows[hi + 1:]:
     a[0] += int(r[ie]); a[1] += int(r[te]); a[2] += int(r[sm])
 tot = sum(a[0] for a in agg.values()); tots = sum(a[2] for a in agg.values())
 print(f"total warp instructions {tot}, samples {tots}")
-for (fname, line), a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
+key = (lambda kv: -kv[1][0]) if "--by-inst" in sys.argv else (lambda kv: -kv[1][2])
+for (fname, line), a in sorted(agg.items(), key=key)[:top]:
     print("%s:%d: inst %5.1f%%  samples %5.1f%%  thr/inst %5.1f | %s" % (os.path.basename(fname), line, 100 * a[0] / tot,
                                                                   100 * a[2] / max(tots, 1), a[1] / max(a[0], 1), src_line(fname, line)))
