@@ -375,9 +375,8 @@ def ours(args):
     errors = []
     start_evt = threading.Barrier(K + 1)
     numa = numa_cpus_of_gpu(local)
+    span_budget_e2e = (max(int(w.spans_used) for w in wins) + 64) / n
     stagger_unit = 0.25 + 0.6 * (dev_ms / args.steps / 1e3)       # rough length of a step's copy phases, seconds
-    span_max = max(int(w.spans_used) for w in wins) + 64
-    out_bytes = 32 * rows_cap + 32 * qrows_cap + 8 * n + 4 * n + 16 * span_max
 
     import ctypes as C
     numa = None if args.no_numa else numa
@@ -389,65 +388,60 @@ def ours(args):
             mine = slices[k]
             e = capi.Engine(device=local, nsims=len(mine))
             e.set_async(True)
-            e.set_span_budget(args.span_budget)
+            e.set_span_budget(span_budget_e2e)            # capacities sized by the warm-up run: the copied blocks carry little slack
             e.set_queue_rows_cap(qrows_cap)
+            # the step's inputs: every trace of this thread in one page-locked block, trace i at i * n * 32
             pin_in = capi.PinnedBuffer(len(mine) * n * 32)
-            pin_out = capi.PinnedBuffer(len(mine) * out_bytes)
-            ins, outs, optr = [], [], []
-            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            block = pin_in.view(capi.JOBIN_DTYPE, len(mine) * n)
             for i, r in enumerate(mine):
-                v = pin_in.view(capi.JOBIN_DTYPE, n, i * n * 32)
-                v[:] = tables[r].packed()                 # the step's inputs live in host memory
-                ins.append((v, vp(v)))
-                o = i * out_bytes
-                ev = pin_out.view(lm.EVROW_DTYPE, rows_cap, o); o += 32 * rows_cap
-                qr = pin_out.view(lm.QROW_DTYPE, qrows_cap, o); o += 32 * qrows_cap
-                jb = pin_out.view(lm.JOBRUN_DTYPE, n, o); o += 8 * n
-                od = pin_out.view(np.int32, n, o); o += 4 * n
-                sp = pin_out.view(lm.SPAN_DTYPE, span_max, o)
-                outs.append((ev, qr, jb, od, sp))
-                optr.append((vp(ev), vp(qr), vp(jb), vp(od), vp(sp)))
+                block[i * n:(i + 1) * n] = tables[r].packed()
                 e.config(i, cluster)
+            n_each = np.full(len(mine), n, dtype=np.int64)
+            p_in, p_n = block.ctypes.data_as(C.c_void_p), n_each.ctypes.data_as(C.POINTER(C.c_int64))
             lib, h = e.lib, e.h
-            ph = dict(load=0.0, run=0.0, fetch_enqueue=0.0, fetch_wait=0.0, check=0.0)
-            h2d = d2h = chk = ev_cnt = 0
+            pin_out = out = lay = None
+            pitch = 0
+            ph = dict(load=0.0, run=0.0, fetch=0.0, check=0.0)
+            h2d = d2h = d2h_copied = chk = ev_cnt = 0
             win = capi.GsWindowInfo()
             for step in range(e2e_steps + 1):            # step 0 = untimed warm-up (allocations)
                 if step == 1:
                     start_evt.wait()                      # all threads + main: timed region starts
-                    ph = dict(load=0.0, run=0.0, fetch_enqueue=0.0, fetch_wait=0.0, check=0.0)
-                    h2d = d2h = chk = ev_cnt = 0
+                    ph = dict(load=0.0, run=0.0, fetch=0.0, check=0.0)
+                    h2d = d2h = d2h_copied = chk = ev_cnt = 0
                     if k % 2 == 1 and args.e2e_stagger > 0:
                         time.sleep(args.e2e_stagger * stagger_unit)     # odd threads run half a step behind the even ones
                 c0 = time.perf_counter()
-                for i in range(len(mine)):
-                    if lib.gs_load_trace_packed(h, i, n, ins[i][1], None, None) != 0:
-                        raise capi.GsError("gs_load_trace_packed failed")
-                    h2d += n * 32
+                if lib.gs_load_traces_packed(h, p_in, n * 32, p_n) != 0:          # ONE strided upload (asynchronous)
+                    raise capi.GsError("gs_load_traces_packed failed: " + lib.gs_last_error(h).decode())
+                h2d += len(mine) * n * 32
                 c1 = time.perf_counter(); ph["load"] += c1 - c0
                 run_to_done(e, rows_cap)
                 c2 = time.perf_counter(); ph["run"] += c2 - c1
-                ws = []
-                for i in range(len(mine)):
-                    lib.gs_window(h, i, C.byref(win))
-                    p_ev, p_qr, p_jb, p_od, p_sp = optr[i]
-                    if lib.gs_fetch_compact(h, i, p_ev, p_qr, p_jb, None, p_od, p_sp) != 0:
-                        raise capi.GsError("gs_fetch_compact failed")
-                    ws.append((win.ev_rows, win.q_rows, win.finished, win.spans_used, win.ticks, win.row_first))
-                c3 = time.perf_counter(); ph["fetch_enqueue"] += c3 - c2
+                if pin_out is None:                       # first step: the result-block layout is known now
+                    lay = e.result_layout(0)
+                    pitch = (int(lay.block_bytes) + 255) // 256 * 256
+                    pin_out = capi.PinnedBuffer(len(mine) * pitch)
+                    out = pin_out.view(np.uint8, len(mine) * pitch)
+                    p_out = out.ctypes.data_as(C.c_void_p)
+                if lib.gs_fetch_results(h, 0, len(mine), p_out, pitch) != 0:       # ONE strided read-back
+                    raise capi.GsError("gs_fetch_results failed: " + lib.gs_last_error(h).decode())
                 e.sync()
-                c4 = time.perf_counter(); ph["fetch_wait"] += c4 - c3
-                for i, (ner, nqr, nfin, nsp, _, _) in enumerate(ws):
-                    evb, qrb, jb, od, sp = outs[i]
-                    d2h += 32 * (ner + nqr) + 8 * n + 4 * nfin + 16 * nsp
-                    chk += int(evb[ner - 1]["finished"]) + int(jb[0]["start"]) + int(od[nfin - 1]) + int(sp[nsp - 1]["node"])
-                    ev_cnt += n + 2 * nfin               # arrivals + starts + completions of a finished run
-                ph["check"] += time.perf_counter() - c4
+                c3 = time.perf_counter(); ph["fetch"] += c3 - c2
+                d2h_copied += len(mine) * int(lay.block_bytes)
+                for i in range(len(mine)):                # touch every replica's results
+                    lib.gs_window(h, i, C.byref(win))
+                    evb, qrb, jb, od, sp = capi.Engine.result_views(out, pitch, i, lay, win)
+                    d2h += 32 * (win.ev_rows + win.q_rows) + 8 * n + 4 * win.finished + 16 * win.spans_used
+                    chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["node"])
+                    ev_cnt += n + 2 * win.finished        # arrivals + starts + completions of a finished run
+                ph["check"] += time.perf_counter() - c3
             # the records really are the run: decode one replica of this thread and compare with the value run
-            ner, nqr, nfin, nsp, tk, rf = ws[0]
-            rows = lm.expand_rows(outs[0][0][:ner], outs[0][1][:nqr], rf, tk, M, G)
+            lib.gs_window(h, 0, C.byref(win))
+            evb, qrb, jb, od, sp = capi.Engine.result_views(out, pitch, 0, lay, win)
+            rows = lm.expand_rows(evb, qrb, win.row_first, win.ticks, M, G)
             assert len(rows) == ticks[mine[0]] and int(rows["finished"][-1]) == n and int(rows["now"][-1]) == ticks[mine[0]]
-            results[k] = (ph, h2d // e2e_steps, d2h // e2e_steps, chk, ev_cnt // e2e_steps)
+            results[k] = (ph, h2d // e2e_steps, d2h // e2e_steps, chk, ev_cnt // e2e_steps, d2h_copied // e2e_steps)
             pin_in.free(); pin_out.free()
             e.close()
         except Exception as exc:                          # surface worker failures in the main thread
@@ -475,13 +469,16 @@ def ours(args):
     h2d = sum(r[1] for r in results); d2h = sum(r[2] for r in results)
     checksum = sum(r[3] for r in results)
     assert sum(r[4] for r in results) == events_rank, "e2e run simulated a different number of events"
-    ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "fetch_enqueue", "fetch_wait", "check")}
+    ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "fetch", "check")}
+    d2h_copied = sum(r[5] for r in results)
     e2e = {"value": events_all / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(red.sum(h2d)), "d2h_bytes_per_step": int(red.sum(d2h)),
+           "h2d_bytes_per_step": int(red.sum(h2d)), "d2h_bytes_per_step": int(red.sum(d2h_copied)),
+           "d2h_valid_bytes_per_step": int(red.sum(d2h)),
            "steps": e2e_steps, "host_threads": K, "pinned_buffers_numa_local": bool(numa),
            "timing": "wall clock between barrier+synchronize around the timed steps of all threads, max over ranks",
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
-           "result_format": "compact records (gs_evrow/gs_qrow/gs_job_run/finish order/spans); one replica per thread is decoded to full rows and checked",
+           "result_format": "compact records (gs_evrow/gs_qrow/gs_job_run/finish order/spans), one strided copy per handle each way "
+                            "(d2h_bytes counts the copied blocks incl. their unused capacity); one replica per thread is decoded to full rows and checked",
            "checksum": checksum}
 
     if args.e2e_only:

@@ -61,6 +61,12 @@ class GsWindowInfo(C.Structure):
                 ("spans_used", C.c_int64), ("admitted", C.c_int64), ("finished", C.c_int64), ("n", C.c_int64)]
 
 
+class GsResultLayout(C.Structure):
+    _fields_ = [("block_bytes", C.c_int64), ("off_ev", C.c_int64), ("off_q", C.c_int64), ("off_jobs", C.c_int64),
+                ("off_duration", C.c_int64), ("off_finish_order", C.c_int64), ("off_spans", C.c_int64),
+                ("cap_ev", C.c_int64), ("cap_q", C.c_int64), ("cap_spans", C.c_int64), ("n", C.c_int64)]
+
+
 JOBIN_DTYPE = np.dtype([("arrive_tick", "<i4"), ("gpus", "<i4"), ("gpu_per_task", "<i4"), ("ps_count", "<i4"),
                         ("mem_bytes", "<i8"), ("duration", "<f8")])
 NODE_DTYPE = np.dtype([("busy_mask", "<u8"), ("cpu_used", "<i4"), ("mem_used", "<i4")])
@@ -212,6 +218,11 @@ def load_library():
     lib.gs_set_async.argtypes = [C.c_void_p, C.c_int]
     lib.gs_set_queue_rows_cap.argtypes = [C.c_void_p, C.c_int64]
     for name in ("gs_window", "gs_fetch_compact", "gs_sync", "gs_set_async", "gs_set_queue_rows_cap"):
+        getattr(lib, name).restype = C.c_int
+    lib.gs_load_traces_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, i64p]
+    lib.gs_result_layout.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsResultLayout)]
+    lib.gs_fetch_results.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    for name in ("gs_load_traces_packed", "gs_result_layout", "gs_fetch_results"):
         getattr(lib, name).restype = C.c_int
     lib.gs_switch_yarn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, f64p, C.c_int64,
                                    C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
@@ -462,6 +473,37 @@ class Engine:
             return None if a is None else a.ctypes.data_as(C.c_void_p)
         self._check(self.lib.gs_fetch_compact(self.h, sim, vp(ev), vp(qr), vp(jobs), vp(dur), vp(order), vp(spans)),
                     "gs_fetch_compact")
+
+    def load_traces_packed(self, block, pitch_bytes, n_each):
+        """every replica's trace from one host block (numpy uint8 / record view; trace i at i * pitch_bytes): one strided upload"""
+        n_each = np.ascontiguousarray(n_each, dtype=np.int64)
+        assert len(n_each) == self.nsims
+        for i, k in enumerate(n_each.tolist()):
+            self._n[i] = int(k)
+        self._keep_block = (block, n_each)
+        self._check(self.lib.gs_load_traces_packed(self.h, block.ctypes.data_as(C.c_void_p), int(pitch_bytes), _ptr(n_each, C.c_int64)),
+                    "gs_load_traces_packed")
+
+    def result_layout(self, sim=0) -> GsResultLayout:
+        lay = GsResultLayout()
+        self._check(self.lib.gs_result_layout(self.h, sim, C.byref(lay)), "gs_result_layout")
+        return lay
+
+    def fetch_results(self, out, out_pitch, first=0, count=None):
+        """enqueue ONE strided copy of the result blocks of replicas [first, first+count) into `out`; call sync()"""
+        count = self.nsims - first if count is None else count
+        self._check(self.lib.gs_fetch_results(self.h, int(first), int(count), out.ctypes.data_as(C.c_void_p), int(out_pitch)), "gs_fetch_results")
+
+    @staticmethod
+    def result_views(buf, pitch, index, lay: "GsResultLayout", win: "GsWindowInfo"):
+        """numpy views (ev rows, queue rows, job runs, finish order, span pool) of replica `index` inside a fetched block buffer"""
+        base = index * pitch
+        ev = np.frombuffer(buf, dtype=EVROW_DTYPE, count=int(win.ev_rows), offset=base + lay.off_ev)
+        qr = np.frombuffer(buf, dtype=QROW_DTYPE, count=int(win.q_rows), offset=base + lay.off_q)
+        jobs = np.frombuffer(buf, dtype=JOBRUN_DTYPE, count=int(win.n), offset=base + lay.off_jobs)
+        order = np.frombuffer(buf, dtype=np.int32, count=int(win.finished), offset=base + lay.off_finish_order)
+        spans = np.frombuffer(buf, dtype=SPAN_DTYPE, count=int(win.spans_used), offset=base + lay.off_spans)
+        return ev, qr, jobs, order, spans
 
     def fetch_compact(self, sim=0):
         """(window info, gs_evrow[], gs_qrow[], gs_job_run[], duration-after-network-cost or None, finish order, span pool)"""

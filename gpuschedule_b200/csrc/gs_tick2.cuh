@@ -32,18 +32,36 @@ struct __align__(16) JobState2 {   // 16 B, written at start, read once at compl
   unsigned long long mask0;  // one span:  devices held;                            several: span count | gpus << 32
 };
 
-__device__ __forceinline__ unsigned long long take_lowest(unsigned long long idle, int cnt, int G) {
+// Shared memory through 32-bit shared-window addresses held in registers: generic pointers make the compiler rebuild the
+// window base (S2UR CgaCtaId / ULEA ...) at every access once registers are tight (ncu, profiles/r02_tick2_v1_ncu_full.txt)
+__device__ __forceinline__ unsigned lds32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ unsigned long long lds64(unsigned a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts64(unsigned a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v)); }
+__device__ __forceinline__ int2 ldsv2(unsigned a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void stsv2(unsigned a, int2 v) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(v.x), "r"(v.y)); }
+
+// Device masks: 32-bit words when a node has at most 32 GPUs (every BASELINE cluster), 64-bit otherwise
+template <bool G64> struct MaskOps;
+template <> struct MaskOps<true> {
+  typedef unsigned long long T;
+  static __device__ __forceinline__ T ld(unsigned a) { return lds64(a); }
+  static __device__ __forceinline__ void st(unsigned a, T v) { sts64(a, v); }
+  static __device__ __forceinline__ int popc(T v) { return __popcll(v); }
+};
+template <> struct MaskOps<false> {
+  typedef unsigned T;
+  static __device__ __forceinline__ T ld(unsigned a) { return lds32(a); }
+  static __device__ __forceinline__ void st(unsigned a, T v) { sts32(a, v); }
+  static __device__ __forceinline__ int popc(T v) { return __popc(v); }
+};
+
+template <typename T>
+__device__ __forceinline__ T take_lowest(T idle, int cnt) {
   // the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
-  if (cnt == 1) return idle & (~idle + 1ull);
-  if (G <= 32) {
-    unsigned m = (unsigned)idle;
-    if (cnt >= __popc(m)) return idle;
-    for (int i = 0; i < cnt; ++i) m &= m - 1u;
-    return (unsigned long long)((unsigned)idle ^ m);
-  }
-  unsigned long long m = idle;
-  if (cnt >= __popcll(m)) return idle;
-  for (int i = 0; i < cnt; ++i) m &= m - 1ull;
+  if (cnt == 1) return idle & (~idle + (T)1);
+  T m = idle;
+  for (int i = 0; i < cnt && m; ++i) m &= m - (T)1;
   return idle ^ m;
 }
 
@@ -60,19 +78,30 @@ __device__ __forceinline__ int need_of(double dur) {     // quirk Q11: run lengt
 
 #define GS_INF 0x7fffffff
 
-template <bool NET>
+template <bool NET, bool G64>
 __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev *sims, int nsims, long long max_ticks, int smem_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
+  typedef MaskOps<G64> MO;
+  typedef typename MO::T MaskT;
+  unsigned lane_u;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_u));      // read once; the compiler would otherwise re-read the special register
+  const int lane = (int)lane_u;
   const int sim = blockIdx.x;
   if (sim >= nsims) return;
   SimDev &S = sims[sim];
-  if (S.done || S.status != 0 || S.policy != GS_SCHED_FIFO || (S.netcost != 0) != NET) return;
+  if (S.done || S.status != 0 || S.policy != GS_SCHED_FIFO || (S.netcost != 0) != NET || (S.G > 32) != G64) return;
 
   const int M = S.M, G = S.G, n = S.n;
-  unsigned long long *busy = reinterpret_cast<unsigned long long *>(smem_raw);
-  unsigned *kk = reinterpret_cast<unsigned *>(busy + M);     // idle devices (bits 0-7) | ever placed (bit 8) | free task slots << 16
-  int2 *sstk = reinterpret_cast<int2 *>(kk + M + (M & 1));   // 8-byte aligned
+  // shared memory, per warp: busy[M] device masks (8 bytes each) | kk[M] idle devices (bits 0-7), ever placed (bit 8),
+  // free task slots << 16 | sstk[SCACHE] top of the stack
+  unsigned sb_busy = (unsigned)__cvta_generic_to_shared(smem_raw);
+  asm volatile("" : "+r"(sb_busy));
+  unsigned sb_kk = sb_busy + 8u * (unsigned)M;
+  asm volatile("" : "+r"(sb_kk));
+  const unsigned sb_stk = sb_kk + 4u * (unsigned)(M + (M & 1));   // 8-byte aligned
+#define BUSY_A(nd_) (sb_busy + 8u * (unsigned)(nd_))
+#define KK_A(nd_) (sb_kk + 4u * (unsigned)(nd_))
+#define STK_A(i_) (sb_stk + 8u * (unsigned)((i_) & (SCACHE - 1)))
 
   const JobIn *__restrict__ jobs = S.jobs;
   int2 *rec2 = S.rec2;
@@ -90,7 +119,9 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
   const int wmask = S.wheel_mask;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
   const int span_cap = (int)(S.span_cap > 0x7fffffffLL ? 0x7fffffffLL : S.span_cap);
-  const unsigned long long gmask = (G >= 64) ? ~0ull : ((1ull << G) - 1ull);
+  MaskT gmask = (G >= (int)(8 * sizeof(MaskT))) ? ~(MaskT)0 : (((MaskT)1 << G) - (MaskT)1);
+  if constexpr (G64) asm volatile("" : "+l"(gmask));                // keep it in a register instead of rebuilding it at every use
+  else asm volatile("" : "+r"(gmask));
 
   int delta = S.delta, p = S.p, top = S.top, running = S.running, finished = S.finished;
   int ever = S.ever, busy_gpus = S.busy_gpus, status = 0, blocked = S.blocked;
@@ -107,19 +138,19 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
   // ---- stage the node table (a fresh replica starts idle), the wheel and the top of the stack
   if (S.need_init) {
     const int K = S.K;
-    for (int i = lane; i < M; i += 32) { busy[i] = 0ull; kk[i] = (unsigned)G | ((unsigned)K << 16); }
+    for (int i = lane; i < M; i += 32) { sts64(BUSY_A(i), 0ull); sts32(KK_A(i), (unsigned)G | ((unsigned)K << 16)); }
     for (int i = lane; i <= wmask; i += 32) { whead[i] = -1; wmem[i] = 0; }
   } else {
     const int K = S.K;
     for (int i = lane; i < M; i += 32) {
       const unsigned long long bz = S.nbusy[i];
       const unsigned kv = (unsigned)S.nk[i];
-      busy[i] = bz;
-      kk[i] = (unsigned)(G - __popcll(bz)) | ((kv & EVER_BIT) ? 0x100u : 0u) | ((unsigned)(K - (int)(kv & ~EVER_BIT)) << 16);
+      sts64(BUSY_A(i), bz);
+      sts32(KK_A(i), (unsigned)(G - __popcll(bz)) | ((kv & EVER_BIT) ? 0x100u : 0u) | ((unsigned)(K - (int)(kv & ~EVER_BIT)) << 16));
     }
   }
   int scount = top;                              // entries in the stack array; the head may live in registers instead
-  for (int i = max(scount - SCACHE, 0) + lane; i < scount; i += 32) sstk[i & (SCACHE - 1)] = stack[i];
+  for (int i = max(scount - SCACHE, 0) + lane; i < scount; i += 32) stsv2(STK_A(i), stack[i]);
   int cache_lo = max(scount - SCACHE, 0);        // stack entries [cache_lo, scount) are cached in shared memory
   int bottom_arr = (top > 0) ? stack[0].y : 0;
   __syncwarp();
@@ -204,7 +235,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         if (c > 0 && cnt == 0) {
           if (hvalid) {      // the waiting head goes back under the new batch
             const int2 e = make_int2(hjob, harr);
-            stack[scount] = e; sstk[scount & (SCACHE - 1)] = e;
+            stack[scount] = e; stsv2(STK_A(scount), e);
             scount += 1;
           }
           HEAD_FROM_WINDOW(p - wbase);           // the batch's first job becomes the head (quirk Q2)
@@ -220,7 +251,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         for (int i = lane; i < m; i += 32) {
           const int2 e = make_int2(p + cnt - 1 - i, delta);
           stack[scount + i] = e;
-          if (i >= m - SCACHE) sstk[(scount + i) & (SCACHE - 1)] = e;
+          if (i >= m - SCACHE) stsv2(STK_A(scount + i), e);
         }
         scount += m;
         if (scount - cache_lo > SCACHE) cache_lo = scount - SCACHE;
@@ -239,7 +270,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
     if (top > 0 && !blocked) {
       if (!hvalid) {         // the head was started or the launch just resumed: pop the stack
         int2 e;
-        if (scount - 1 >= cache_lo) e = sstk[(scount - 1) & (SCACHE - 1)];
+        if (scount - 1 >= cache_lo) e = ldsv2(STK_A(scount - 1));
         else e = stack[scount - 1];
         scount -= 1;
         if (cache_lo > scount) cache_lo = scount;
@@ -268,11 +299,11 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
           const int nd = base + lane;
           bool fit = false;
           if (nd < M) {
-            const unsigned mt = kk[nd];
+            const unsigned mt = lds32(KK_A(nd));
             fit = (int)(mt & 0xffu) >= hg && (int)(mt >> 16) >= htasks;
           }
           if (!placeable) {          // quirk Q21: cpu/mem charged for every task, never refunded
-            if (fit) kk[nd] -= (unsigned)htasks << 16;
+            if (fit) sts32(KK_A(nd), lds32(KK_A(nd)) - ((unsigned)htasks << 16));
             continue;
           }
           const unsigned b = __ballot_sync(FULL, fit);
@@ -282,11 +313,11 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         if (found >= 0) {
           ok = true; nspans = 1;
           // warp-uniform update: every lane reads the same words and writes the same values (no lane-0 branch, no sync)
-          const unsigned long long bz = busy[found];
-          const unsigned long long take = take_lowest(~bz & gmask, hg, G);
-          const unsigned kv = kk[found];
-          busy[found] = bz | take;
-          kk[found] = (kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u;
+          const MaskT bz = MO::ld(BUSY_A(found));
+          const MaskT take = take_lowest<MaskT>(~bz & gmask, hg);
+          const unsigned kv = lds32(KK_A(found));
+          MO::st(BUSY_A(found), bz | take);
+          sts32(KK_A(found), (kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u);
           {
             gs_span sp; sp.node = found; sp.ntasks = htasks | (int)0x80000000; sp.devmask = take;
             __stcs(reinterpret_cast<int4 *>(&spans[span_first]), *reinterpret_cast<const int4 *>(&sp));
@@ -304,14 +335,14 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         if (placeable) {
           for (int base = 0; base < M; base += 32) {
             const int nd = base + lane;
-            const int c = (nd < M) ? meta_cap(kk[nd], hgpc) : 0;
+            const int c = (nd < M) ? meta_cap(lds32(KK_A(nd)), hgpc) : 0;
             cum += __reduce_add_sync(FULL, c);
             if (cum >= htasks) { last_base = base; break; }
           }
         } else {
           for (int base = 0; base < M; base += 32) {   // quirk Q21, cross-node flavour: one task charged per node
             const int nd = base + lane;
-            if (nd < M && meta_cap(kk[nd], hgpc) > 0) kk[nd] -= 1u << 16;
+            if (nd < M) { const unsigned mt = lds32(KK_A(nd)); if (meta_cap(mt, hgpc) > 0) sts32(KK_A(nd), mt - (1u << 16)); }
           }
         }
         if (last_base >= 0 && (long long)span_used + min(htasks, M) > (long long)span_cap) { status = GS_ERR_CAPACITY; last_base = -1; }
@@ -322,7 +353,8 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
           int rem = htasks, last_node = 0;
           for (int base = 0; base <= last_base; base += 32) {
             const int nd = base + lane;
-            const int c = (nd < M) ? meta_cap(kk[nd], hgpc) : 0;
+            const unsigned kv = (nd < M) ? lds32(KK_A(nd)) : 0u;
+            const int c = meta_cap(kv, hgpc);
             int incl = c;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
@@ -330,10 +362,10 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
             const unsigned tb = __ballot_sync(FULL, take > 0);
             bool fresh = false;
             if (take > 0) {
-              const unsigned long long tk = take_lowest(~busy[nd] & gmask, take * hgpc, G);
-              busy[nd] |= tk;
-              const unsigned kv = kk[nd];
-              kk[nd] = (kv - (unsigned)(take * hgpc) - ((unsigned)take << 16)) | 0x100u;
+              const MaskT bz = MO::ld(BUSY_A(nd));
+              const MaskT tk = take_lowest<MaskT>(~bz & gmask, take * hgpc);
+              MO::st(BUSY_A(nd), bz | tk);
+              sts32(KK_A(nd), (kv - (unsigned)(take * hgpc) - ((unsigned)take << 16)) | 0x100u);
               fresh = !(kv & 0x100u);
               const int slot = nspans + __popc(tb & ((1u << lane) - 1u));
               gs_span sp; sp.node = nd; sp.ntasks = take | (slot == 0 ? (int)0x80000000 : 0); sp.devmask = tk;
@@ -409,17 +441,17 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         if (js.where >= 0) {
           const int nd = js.where & 0xfffff, nt = ((js.where >> 20) & 63) + 1;
           const int gp = __popcll(js.mask0);
-          const unsigned long long bz = busy[nd];        // warp-uniform read-modify-write
-          const unsigned kv = kk[nd];
-          busy[nd] = bz & ~js.mask0;
-          kk[nd] = kv + (unsigned)gp + ((unsigned)nt << 16);
+          const MaskT bz = MO::ld(BUSY_A(nd));           // warp-uniform read-modify-write
+          const unsigned kv = lds32(KK_A(nd));
+          MO::st(BUSY_A(nd), bz & ~(MaskT)js.mask0);
+          sts32(KK_A(nd), kv + (unsigned)gp + ((unsigned)nt << 16));
           busy_gpus -= gp;
         } else {
           const int first = js.where & 0x7fffffff, scnt = (int)(unsigned)(js.mask0 & 0xffffffffull);
           for (int i = lane; i < scnt; i += 32) {
             const gs_span sp = spans[first + i];
-            busy[sp.node] &= ~sp.devmask;
-            kk[sp.node] += (unsigned)__popcll(sp.devmask) + ((unsigned)(sp.ntasks & 0x7fffffff) << 16);
+            MO::st(BUSY_A(sp.node), MO::ld(BUSY_A(sp.node)) & ~(MaskT)sp.devmask);
+            sts32(KK_A(sp.node), lds32(KK_A(sp.node)) + (unsigned)__popcll(sp.devmask) + ((unsigned)(sp.ntasks & 0x7fffffff) << 16));
           }
           busy_gpus -= (int)(unsigned)(js.mask0 >> 32);
           __syncwarp();          // lanes updated different nodes
@@ -459,9 +491,9 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         const int ilo = top - 1 - ((top - 1) >> 1), ihi = top - 1 - (top >> 1);
         int a_lo, a_hi;
         if (hvalid && ilo == top - 1) a_lo = harr;
-        else a_lo = ilo >= cache_lo ? sstk[ilo & (SCACHE - 1)].y : stack[ilo].y;
+        else a_lo = ilo >= cache_lo ? ldsv2(STK_A(ilo)).y : stack[ilo].y;
         if (hvalid && ihi == top - 1) a_hi = harr;
-        else a_hi = ihi >= cache_lo ? sstk[ihi & (SCACHE - 1)].y : stack[ihi].y;
+        else a_hi = ihi >= cache_lo ? ldsv2(STK_A(ihi)).y : stack[ihi].y;
         qidx = nb;
         __stcs(&rowB[2 * nb], make_int4((int)(sum_arr & 0xffffffffLL), (int)(sum_arr >> 32), bottom_arr, a_lo));
         __stcs(&rowB[2 * nb + 1], make_int4(a_hi, 0, 0, 0));
@@ -486,8 +518,8 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
   {
     const int K = S.K;
     for (int i = lane; i < M; i += 32) {
-      const unsigned mt = kk[i];
-      S.nbusy[i] = busy[i];
+      const unsigned mt = lds32(KK_A(i));
+      S.nbusy[i] = (unsigned long long)MO::ld(BUSY_A(i));
       S.nk[i] = (int)((unsigned)(K - (int)(mt >> 16)) | ((mt & 0x100u) ? EVER_BIT : 0u));
     }
   }
@@ -499,6 +531,9 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
     S.ticks = delta; S.row_first = delta0; S.nev = na; S.nq = nb; S.blocked = blocked;
     S.done = done ? 1 : 0; S.status = status; S.need_init = 0;
   }
+#undef BUSY_A
+#undef KK_A
+#undef STK_A
 }
 
 // ------------------------------------------------------------------ record -> row expansion

@@ -39,6 +39,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,18 @@
 
 // ------------------------------------------------------------------ host side
 
+// Per-replica device layout.  The RESULT arrays come first and contiguously (gs_result_layout): statistics records,
+// queue records, per-job results, (durations,) finish order, spans -- so that everything a caller reads back from a
+// replica is ONE copy, and from all replicas of a handle ONE strided copy (the slabs live side by side in an arena).
+struct SimLayout {
+  size_t o_ev = 0, o_q = 0, o_rec2 = 0, o_dur2 = 0, o_fin = 0, o_spans = 0, out_bytes = 0;
+  size_t o_rec = 0, o_rows = 0, o_jst = 0, o_stack = 0, o_wh = 0, o_wm = 0, o_nb = 0, o_nk = 0;
+  size_t o_pj = 0, o_run = 0, o_qs = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0, o_stale = 0;
+  size_t total = 0;
+  int64_t rows_cap = 0, qrows_cap = 0;
+  int W = 256;
+};
+
 struct SimHost {
   gs_cluster cl;
   gs_policy pol;
@@ -63,7 +76,10 @@ struct SimHost {
   size_t trace_bytes = 0, state_bytes = 0;
   int64_t span_cap = 0, rows_cap = 0, qrows_cap = 0, last_arrive = 0;
   int max_need = 1;
+  unsigned char *state_ptr = nullptr;     // the replica's slab: inside the handle's arena or its own allocation (state_slab)
+  bool trace_in_arena = false;
   SimDev dev;
+  SimLayout layout;
 };
 
 struct gs_engine {
@@ -77,6 +93,10 @@ struct gs_engine {
   void *d_scratch = nullptr;
   size_t d_scratch_bytes = 0;
   std::vector<SimDev> h_back;   // pinned-size-stable host mirror used by gs_run
+  // arenas: the replicas' state slabs (result block first) / traces side by side with one stride, so that a whole
+  // handle is read back or uploaded with ONE strided copy (gs_fetch_results / gs_load_traces_packed)
+  void *arena = nullptr; size_t arena_bytes = 0, arena_stride = 0;
+  void *tarena = nullptr; size_t tarena_bytes = 0, tarena_stride = 0;
   std::string err;
   double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
   long long launches = 0;  // kernels launched by this handle
@@ -151,6 +171,8 @@ extern "C" void gs_destroy(gs_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &s : h->sims) { if (s.trace_slab) cudaFree(s.trace_slab); if (s.state_slab) cudaFree(s.state_slab); if (s.git_dev) cudaFree(s.git_dev); }
   if (h->d_sims) cudaFree(h->d_sims);
+  if (h->arena) cudaFree(h->arena);
+  if (h->tarena) cudaFree(h->tarena);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->d_scratch) cudaFree(h->d_scratch);
   for (int q = 0; q < GS_MAX_RANKS; ++q) if (h->comm_opened[q] && h->comm_peer[q]) cudaIpcCloseMemHandle(h->comm_peer[q]);
@@ -333,6 +355,7 @@ static int load_common(gs_handle h, int sim, int64_t n, const JobIn *packed, con
   s.max_need = (int)max_need + 2;
   s.last_arrive = n > 0 ? ji[n - 1].arrive : 0;
   s.loaded = true;
+  s.trace_in_arena = false;
   s.prepared = false;      // (re)loading a trace restarts the replica; slabs are reused when big enough
   h->dirty = true;
   return GS_OK;
@@ -353,42 +376,57 @@ extern "C" int gs_load_trace_packed(gs_handle h, int sim, int64_t n, const gs_jo
                      model_mb, iterations, nullptr);
 }
 
-static int prepare_sim(gs_handle h, SimHost &s, int64_t rows_cap) {
+static SimLayout layout_sim(gs_handle h, const SimHost &s, int64_t rows_cap) {
+  SimLayout L;
   const gs_cluster &c = s.cl;
   const int M = c.num_switch * c.num_node_p_switch;
   const size_t N = (size_t)(s.n > 0 ? s.n : 1);
   int W = 256; while (W < s.max_need + 1) W <<= 1;
+  L.W = W;
   if (rows_cap <= 0) rows_cap = s.last_arrive + 2ll * s.max_need + 4096;
-  int64_t qrows_cap = h->qrows_cap > 0 ? h->qrows_cap : rows_cap;
+  L.rows_cap = rows_cap;
+  L.qrows_cap = h->qrows_cap > 0 ? h->qrows_cap : rows_cap;
   const bool evd = s.pol.schedule != GS_SCHED_FIFO;        // event-driven policy: rows + extra scratch
   const bool net = c.enable_network_costs != 0;
   size_t total = 0;
   auto take = [&](size_t bytes) { const size_t o = total; total = align_up(total + bytes); return o; };
-  size_t o_rec = 0, o_rec2 = 0, o_dur2 = 0, o_jst = 0, o_stack = 0, o_wh = 0, o_wm = 0, o_spans = 0, o_rows = 0, o_ev = 0, o_q = 0, o_nb = 0, o_nk = 0;
-  const size_t o_fin = take(4 * N);
   if (evd) {
-    o_rec = take(sizeof(gs_job_rec) * N);
-    o_rows = take(sizeof(gs_tick_row) * (size_t)rows_cap);
+    L.o_fin = take(4 * N);
+    L.o_rec = take(sizeof(gs_job_rec) * N);
+    L.o_rows = take(sizeof(gs_tick_row) * (size_t)rows_cap);
+    L.out_bytes = total;
+    const size_t nql = (size_t)(s.pol.num_queue > 2 ? s.pol.num_queue : 2);
+    L.o_pj = take(sizeof(PJob) * N); L.o_run = take(4 * N); L.o_qs = take(4 * N * nql); L.o_end = take(4 * N);
+    L.o_tmp = take(4 * N); L.o_ci = take(4 * (size_t)M); L.o_ck = take(4 * (size_t)M); L.o_stale = take(4 * N);
   } else {
-    o_rec2 = take(8 * N);
-    if (net) o_dur2 = take(8 * N);
-    o_jst = take(sizeof(JobState2) * N);
-    o_stack = take(8 * (N + 1));
-    o_wh = take(4 * (size_t)W); o_wm = take(8 * (size_t)W);
-    o_spans = take(sizeof(gs_span) * (size_t)s.span_cap);
-    o_ev = take(sizeof(gs_evrow) * (size_t)rows_cap);
-    o_q = take(sizeof(gs_qrow) * (size_t)qrows_cap);
-    o_nb = take(8 * (size_t)M); o_nk = take(4 * (size_t)M);
+    L.o_ev = take(sizeof(gs_evrow) * (size_t)rows_cap);
+    L.o_q = take(sizeof(gs_qrow) * (size_t)L.qrows_cap);
+    L.o_rec2 = take(8 * N);
+    if (net) L.o_dur2 = take(8 * N);
+    L.o_fin = take(4 * N);
+    L.o_spans = take(sizeof(gs_span) * (size_t)s.span_cap);
+    L.out_bytes = total;
+    L.o_jst = take(sizeof(JobState2) * N);
+    L.o_stack = take(8 * (N + 1));
+    L.o_wh = take(4 * (size_t)W); L.o_wm = take(8 * (size_t)W);
+    L.o_nb = take(8 * (size_t)M); L.o_nk = take(4 * (size_t)M);
   }
-  const size_t nql = (size_t)(s.pol.num_queue > 2 ? s.pol.num_queue : 2);
-  size_t o_pj = 0, o_run = 0, o_qs = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0, o_stale = 0;
-  if (evd) {
-    o_pj = take(sizeof(PJob) * N); o_run = take(4 * N); o_qs = take(4 * N * nql); o_end = take(4 * N);
-    o_tmp = take(4 * N); o_ci = take(4 * (size_t)M); o_ck = take(4 * (size_t)M); o_stale = take(4 * N);
-  }
-  if (s.state_slab && s.state_bytes < total) { CU(cudaStreamSynchronize(h->stream)); cudaFree(s.state_slab); s.state_slab = nullptr; }
-  if (!s.state_slab) { CU(cudaMalloc(&s.state_slab, total)); s.state_bytes = total; }
-  unsigned char *d = (unsigned char *)s.state_slab;
+  L.total = total;
+  return L;
+}
+
+static int bind_sim(gs_handle h, SimHost &s, const SimLayout &L, unsigned char *d) {
+  const gs_cluster &c = s.cl;
+  const int M = c.num_switch * c.num_node_p_switch;
+  const int W = L.W;
+  const int64_t rows_cap = L.rows_cap, qrows_cap = L.qrows_cap;
+  const bool evd = s.pol.schedule != GS_SCHED_FIFO;
+  const bool net = c.enable_network_costs != 0;
+  const size_t o_fin = L.o_fin, o_rec = L.o_rec, o_rows = L.o_rows, o_rec2 = L.o_rec2, o_dur2 = L.o_dur2, o_jst = L.o_jst, o_stack = L.o_stack;
+  const size_t o_wh = L.o_wh, o_wm = L.o_wm, o_spans = L.o_spans, o_ev = L.o_ev, o_q = L.o_q, o_nb = L.o_nb, o_nk = L.o_nk;
+  const size_t o_pj = L.o_pj, o_run = L.o_run, o_qs = L.o_qs, o_end = L.o_end, o_tmp = L.o_tmp, o_ci = L.o_ci, o_ck = L.o_ck, o_stale = L.o_stale;
+  s.layout = L;
+  s.state_ptr = d;
   SimDev &D = s.dev;
   D.M = M; D.G = c.num_gpu_p_node;
   int kc = c.num_cpu_p_node / c.cpu_per_task, km = c.mem_p_node / c.mem_per_task;
@@ -450,15 +488,48 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
   if (!h) return GS_ERR_ARG;
   CU(cudaSetDevice(h->device));
   int maxM = 1;
+  bool none_prepared = true;
   for (auto &s : h->sims) {
     if (!s.loaded) return fail(h, GS_ERR_STATE, "gs_run: every replica needs gs_config_sim + gs_load_trace");
-    if (!s.prepared) { int rc = prepare_sim(h, s, rows_cap); if (rc) return rc; h->dirty = true; }
+    none_prepared &= !s.prepared;
     int M = s.cl.num_switch * s.cl.num_node_p_switch;
     if (M > maxM) maxM = M;
   }
-  bool any_fifo = false, any_fifo_net = false, any_evd = false, evd_init = false;
+  if (none_prepared) {
+    // a fresh start of every replica (the common case): the slabs go side by side into one arena with one stride
+    std::vector<SimLayout> Ls((size_t)h->nsims);
+    size_t stride = 0;
+    for (int i = 0; i < h->nsims; ++i) { Ls[(size_t)i] = layout_sim(h, h->sims[(size_t)i], rows_cap); stride = std::max(stride, Ls[(size_t)i].total); }
+    stride = align_up(stride, 512);
+    const size_t need = stride * (size_t)h->nsims;
+    if (h->arena_bytes < need) {
+      CU(cudaStreamSynchronize(h->stream));
+      if (h->arena) cudaFree(h->arena);
+      h->arena = nullptr; h->arena_bytes = 0;
+      CU(cudaMalloc(&h->arena, need));
+      h->arena_bytes = need;
+    }
+    h->arena_stride = stride;
+    for (int i = 0; i < h->nsims; ++i) {
+      int rc = bind_sim(h, h->sims[(size_t)i], Ls[(size_t)i], (unsigned char *)h->arena + stride * (size_t)i);
+      if (rc) return rc;
+    }
+    h->dirty = true;
+  } else {
+    for (auto &s : h->sims)
+      if (!s.prepared) {   // one replica restarts while others keep running: it gets (or keeps) its own allocation
+        const SimLayout L = layout_sim(h, s, rows_cap);
+        if (s.state_slab && s.state_bytes < L.total) { CU(cudaStreamSynchronize(h->stream)); cudaFree(s.state_slab); s.state_slab = nullptr; }
+        if (!s.state_slab) { CU(cudaMalloc(&s.state_slab, L.total)); s.state_bytes = L.total; }
+        int rc = bind_sim(h, s, L, (unsigned char *)s.state_slab);
+        if (rc) return rc;
+        h->dirty = true;
+      }
+  }
+  bool fifo_kind[4] = {false, false, false, false};   // [network costs][more than 32 GPUs per node]
+  bool any_evd = false, evd_init = false;
   for (auto &s : h->sims) {
-    if (s.pol.schedule == GS_SCHED_FIFO) { if (s.cl.enable_network_costs) any_fifo_net = true; else any_fifo = true; }
+    if (s.pol.schedule == GS_SCHED_FIFO) fifo_kind[(s.cl.enable_network_costs ? 2 : 0) + (s.cl.num_gpu_p_node > 32 ? 1 : 0)] = true;
     else { any_evd = true; evd_init |= s.dev.need_init != 0; }
   }
   if (h->dirty) {
@@ -491,21 +562,22 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
       h->launches += 2;
     }
   }
-  if (any_fifo || any_fifo_net) {
+  if (fifo_kind[0] || fifo_kind[1] || fifo_kind[2] || fifo_kind[3]) {
     const int stride = (int)align_up((size_t)maxM * 12 + 8 + SCACHE * 8, 16);
     if (stride > 200 * 1024) return fail(h, GS_ERR_ARG, "gs_run: node table does not fit shared memory (M too large)");
-    if (any_fifo) {
-      if (stride > 48 * 1024) CU(cudaFuncSetAttribute(gs_tick2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
-      gs_tick2_kernel<false><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
-      CU(cudaGetLastError());
-      h->launches += 1;
-    }
-    if (any_fifo_net) {
-      if (stride > 48 * 1024) CU(cudaFuncSetAttribute(gs_tick2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride));
-      gs_tick2_kernel<true><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride);
-      CU(cudaGetLastError());
-      h->launches += 1;
-    }
+    // one instantiation per (network costs, mask width); each skips the replicas of the other kinds
+#define GS_LAUNCH_TICK2(NET_, G64_)                                                                                              \
+    do {                                                                                                                         \
+      if (stride > 48 * 1024) CU(cudaFuncSetAttribute(gs_tick2_kernel<NET_, G64_>, cudaFuncAttributeMaxDynamicSharedMemorySize, stride)); \
+      gs_tick2_kernel<NET_, G64_><<<(unsigned)h->nsims, 32, (size_t)stride, h->stream>>>(h->d_sims, h->nsims, (long long)max_ticks, stride); \
+      CU(cudaGetLastError());                                                                                                    \
+      h->launches += 1;                                                                                                          \
+    } while (0)
+    if (fifo_kind[0]) GS_LAUNCH_TICK2(false, false);
+    if (fifo_kind[1]) GS_LAUNCH_TICK2(false, true);
+    if (fifo_kind[2]) GS_LAUNCH_TICK2(true, false);
+    if (fifo_kind[3]) GS_LAUNCH_TICK2(true, true);
+#undef GS_LAUNCH_TICK2
   }
   CU(cudaEventRecord(h->e1, h->stream));
   CU(cudaMemcpyAsync(h->h_back.data(), h->d_sims, sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyDeviceToHost, h->stream));
@@ -636,6 +708,123 @@ extern "C" int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow 
   if (duration_out && D.dur2 && s.n > 0) CU(cudaMemcpyAsync(duration_out, D.dur2, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
   if (finish_order_out && D.finished > 0) CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream));
   if (spans_out && D.span_used > 0) CU(cudaMemcpyAsync(spans_out, D.spans, sizeof(gs_span) * (size_t)D.span_used, cudaMemcpyDeviceToHost, h->stream));
+  return GS_OK;
+}
+
+// Every replica of the handle at once, from ONE host block (record i*pitch_bytes is the trace of replica i): the traces
+// go into a device arena with one stride and travel as a single strided copy.  With gs_set_async and a page-locked
+// block nothing is staged and the call returns before the copy completes (keep the block until gs_run / gs_sync).
+extern "C" int gs_load_traces_packed(gs_handle h, const gs_jobin *jobs, size_t pitch_bytes, const int64_t *n_each) {
+  if (!h) return GS_ERR_ARG;
+  if (!jobs || !n_each || pitch_bytes % sizeof(JobIn) != 0) return fail(h, GS_ERR_ARG, "gs_load_traces_packed: bad arguments (pitch must be a multiple of 32)");
+  CU(cudaSetDevice(h->device));
+  int64_t nmax = 1;
+  for (int i = 0; i < h->nsims; ++i) {
+    const SimHost &s = h->sims[(size_t)i];
+    if (!s.configured) return fail(h, GS_ERR_STATE, "gs_load_traces_packed: call gs_config_sim for every replica first");
+    if (s.cl.enable_network_costs) return fail(h, GS_ERR_ARG, "gs_load_traces_packed: traces with network columns go through gs_load_trace");
+    if (n_each[i] < 0 || n_each[i] >= (1ll << 31) - 64 || (size_t)n_each[i] * sizeof(JobIn) > pitch_bytes)
+      return fail(h, GS_ERR_ARG, "gs_load_traces_packed: a trace does not fit the pitch");
+    nmax = std::max(nmax, n_each[i]);
+  }
+  // validate first (read only); nothing changes if a trace is rejected
+  std::vector<int64_t> span_cap((size_t)h->nsims); std::vector<double> max_need((size_t)h->nsims);
+  for (int i = 0; i < h->nsims; ++i) {
+    const JobIn *ji = reinterpret_cast<const JobIn *>(reinterpret_cast<const unsigned char *>(jobs) + pitch_bytes * (size_t)i);
+    int rc = scan_trace(h, h->sims[(size_t)i], n_each[i], ji, false, nullptr, nullptr, &span_cap[(size_t)i], &max_need[(size_t)i]);
+    if (rc) return rc;
+    if (max_need[(size_t)i] > (double)(1 << 26)) return fail(h, GS_ERR_ARG, "gs_load_trace: job duration exceeds 2^26 ticks");
+  }
+  const size_t stride = align_up(sizeof(JobIn) * (size_t)nmax, 512);
+  const size_t need = stride * (size_t)h->nsims;
+  CU(cudaStreamSynchronize(h->stream));                 // earlier work may still read the old traces
+  if (h->tarena_bytes < need) {
+    if (h->tarena) cudaFree(h->tarena);
+    h->tarena = nullptr; h->tarena_bytes = 0;
+    CU(cudaMalloc(&h->tarena, need));
+    h->tarena_bytes = need;
+  }
+  h->tarena_stride = stride;
+  bool direct = false;
+  if (h->async) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, jobs) == cudaSuccess && at.type == cudaMemoryTypeHost) direct = true;
+    else (void)cudaGetLastError();
+  }
+  const void *src = jobs;
+  if (!direct) {
+    int rc = ensure_stage(h, pitch_bytes * (size_t)h->nsims);
+    if (rc) return rc;
+    memcpy(h->h_stage, jobs, pitch_bytes * (size_t)h->nsims);
+    src = h->h_stage;
+  }
+  CU(cudaEventRecord(h->e0, h->stream));
+  CU(cudaMemcpy2DAsync(h->tarena, stride, src, pitch_bytes, sizeof(JobIn) * (size_t)nmax, (size_t)h->nsims, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(h->e1, h->stream));
+  if (!direct) {
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
+    h->h2d_ms += ms;
+  }
+  for (int i = 0; i < h->nsims; ++i) {
+    SimHost &s = h->sims[(size_t)i];
+    const JobIn *ji = reinterpret_cast<const JobIn *>(reinterpret_cast<const unsigned char *>(jobs) + pitch_bytes * (size_t)i);
+    SimDev &D = s.dev;
+    memset(&D, 0, sizeof(D));
+    D.jobs = (const JobIn *)((unsigned char *)h->tarena + stride * (size_t)i);
+    int64_t sc = span_cap[(size_t)i];
+    if (h->span_budget > 0) { const int64_t lim = (int64_t)(h->span_budget * (double)n_each[i]) + 4096; if (sc > lim) sc = lim; }
+    s.n = n_each[i]; s.span_cap = sc > 0 ? sc : 1;
+    s.max_need = (int)max_need[(size_t)i] + 2;
+    s.last_arrive = n_each[i] > 0 ? ji[n_each[i] - 1].arrive : 0;
+    s.loaded = true; s.prepared = false; s.trace_in_arena = true;
+  }
+  h->dirty = true;
+  return GS_OK;
+}
+
+// Where the results of a replica lie inside its result block, and how the blocks of the handle are spaced.
+extern "C" int gs_result_layout(gs_handle h, int sim, gs_result_layout_t *out) {
+  if (!h || !out) return GS_ERR_ARG;
+  if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_result_layout: sim index out of range");
+  const SimHost &s = h->sims[(size_t)sim];
+  if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_result_layout: nothing has run yet");
+  if (s.pol.schedule != GS_SCHED_FIFO) return fail(h, GS_ERR_ARG, "gs_result_layout: the compact records are the fifo engine's output");
+  const SimLayout &L = s.layout;
+  memset(out, 0, sizeof(*out));
+  out->block_bytes = (int64_t)L.out_bytes;
+  out->off_ev = (int64_t)L.o_ev; out->off_q = (int64_t)L.o_q; out->off_jobs = (int64_t)L.o_rec2;
+  out->off_duration = s.cl.enable_network_costs ? (int64_t)L.o_dur2 : -1;
+  out->off_finish_order = (int64_t)L.o_fin; out->off_spans = (int64_t)L.o_spans;
+  out->cap_ev = L.rows_cap; out->cap_q = L.qrows_cap; out->cap_spans = s.span_cap; out->n = s.n;
+  return GS_OK;
+}
+
+// The result blocks of replicas [first, first + count) in one strided copy (asynchronous: gs_sync waits).  Row i of
+// `out` (out_pitch bytes apart) receives the first block_bytes bytes of replica first + i's block.
+extern "C" int gs_fetch_results(gs_handle h, int first, int count, void *out, size_t out_pitch) {
+  if (!h) return GS_ERR_ARG;
+  if (first < 0 || count < 0 || first + count > h->nsims || (count > 0 && !out)) return fail(h, GS_ERR_ARG, "gs_fetch_results: bad arguments");
+  if (count == 0) return GS_OK;
+  CU(cudaSetDevice(h->device));
+  size_t width = 0;
+  bool in_arena = true;
+  for (int i = first; i < first + count; ++i) {
+    const SimHost &s = h->sims[(size_t)i];
+    if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_results: nothing has run yet");
+    if (s.pol.schedule != GS_SCHED_FIFO) return fail(h, GS_ERR_ARG, "gs_fetch_results: the compact records are the fifo engine's output");
+    width = std::max(width, s.layout.out_bytes);
+    in_arena &= s.state_ptr == (unsigned char *)h->arena + h->arena_stride * (size_t)i;
+  }
+  if (width > out_pitch) return fail(h, GS_ERR_CAPACITY, "gs_fetch_results: out_pitch is smaller than a result block");
+  if (in_arena) {
+    CU(cudaMemcpy2DAsync(out, out_pitch, (unsigned char *)h->arena + h->arena_stride * (size_t)first, h->arena_stride, width, (size_t)count,
+                         cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    for (int i = first; i < first + count; ++i)
+      CU(cudaMemcpyAsync((unsigned char *)out + out_pitch * (size_t)(i - first), h->sims[(size_t)i].state_ptr, h->sims[(size_t)i].layout.out_bytes,
+                         cudaMemcpyDeviceToHost, h->stream));
+  }
   return GS_OK;
 }
 

@@ -277,6 +277,22 @@ int gs_window(gs_handle h, int sim, gs_window_info *out);
 int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_run *jobs_out,
                      double *duration_out, int32_t *finish_order_out, gs_span *spans_out);
 int gs_sync(gs_handle h);
+/* The same, for many replicas with ONE copy each way (what bench.py's end-to-end path uses).  The replicas of a
+ * handle keep their results in blocks of one layout, side by side on the device:
+ *   gs_load_traces_packed  all traces of the handle from one host block, trace i at jobs + i * pitch_bytes
+ *                          (n_each[i] records): one strided upload
+ *   gs_result_layout       byte offsets of the arrays inside a replica's result block, their capacities, and
+ *                          block_bytes, the length of the block
+ *   gs_fetch_results       the blocks of replicas [first, first + count) into out + i * out_pitch: one strided
+ *                          copy, asynchronous (gs_sync waits); gs_window tells how many entries of each array are valid */
+typedef struct gs_result_layout_t {
+  int64_t block_bytes;
+  int64_t off_ev, off_q, off_jobs, off_duration /* -1 without network costs */, off_finish_order, off_spans;
+  int64_t cap_ev, cap_q, cap_spans, n;
+} gs_result_layout_t;
+int gs_load_traces_packed(gs_handle h, const gs_jobin *jobs, size_t pitch_bytes, const int64_t *n_each);
+int gs_result_layout(gs_handle h, int sim, gs_result_layout_t *out);
+int gs_fetch_results(gs_handle h, int first, int count, void *out, size_t out_pitch);
 /* 1: gs_load_trace_packed from a page-locked buffer enqueues the upload without staging and returns
  * before it completes -- the caller keeps the buffer unchanged until the next gs_run / gs_sync on
  * this handle returns.  0 (default): every call copies and completes before returning.              */

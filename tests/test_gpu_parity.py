@@ -551,3 +551,45 @@ def test_per_call_registries_step_like_the_fused_loop():
         assert [j.index for j in finished] == order.tolist()
         for j in finished:
             assert (j.start_time, j.end_time) == (int(recs["start"][j.index]), int(recs["end"][j.index]))
+
+
+def test_batch_upload_and_strided_read_back():
+    """gs_load_traces_packed (all traces of a handle, one strided upload) + gs_fetch_results (all result blocks, one strided
+    copy) -- the path bench.py's end-to-end measurement uses -- against the oracle, replica by replica, with traces of
+    different lengths and a second step that reuses the arenas."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    from gpuschedule_b200 import log_manager as lm
+    cluster = capi.make_cluster(num_switch=2, num_node_p_switch=12)
+    tables = [ingest.table_from_columns(tracegen.synth_columns(700 + 37 * i, seed=90 + i, rate=0.6 + 0.2 * (i % 4))) for i in range(9)]
+    refs = [oracle.run_fifo(cluster, t) for t in tables]
+    nmax = max(t.n for t in tables)
+    pin = capi.PinnedBuffer(len(tables) * nmax * 32)
+    block = pin.view(capi.JOBIN_DTYPE, len(tables) * nmax)
+    for i, t in enumerate(tables):
+        block[i * nmax:i * nmax + t.n] = t.packed()
+    for use_async in (False, True):
+        with capi.Engine(device=0, nsims=len(tables)) as eng:
+            eng.set_async(use_async)
+            for i in range(len(tables)):
+                eng.config(i, cluster)
+            for step in range(2):
+                eng.load_traces_packed(block, nmax * 32, [t.n for t in tables])
+                eng.run(0, 0)
+                lay = [eng.result_layout(i) for i in range(len(tables))]
+                pitch = max(int(x.block_bytes) for x in lay)
+                out = np.zeros(len(tables) * pitch, dtype=np.uint8)
+                eng.fetch_results(out, pitch)
+                eng.sync()
+                for i, t in enumerate(tables):
+                    w = eng.window(i)
+                    ev, qr, jobs, order, pool = capi.Engine.result_views(out, pitch, i, lay[i], w)
+                    rows = lm.expand_rows(ev, qr, w.row_first, w.ticks, 24, 8)
+                    assert eng.stats(i).done == 1 and rows.tobytes() == refs[i].rows.tobytes(), (use_async, step, i)
+                    assert lm.expand_jobs(jobs, int(w.admitted), t.duration).tobytes() == refs[i].recs.tobytes()
+                    assert np.array_equal(order, refs[i].finish_order)
+                    off, spans = lm.group_spans(jobs, int(w.admitted), pool)
+                    assert np.array_equal(off, refs[i].span_off) and spans.tobytes() == refs[i].spans.tobytes()
+                    recs2, order2 = eng.fetch_jobs(i)               # the per-replica calls see the same arena
+                    assert recs2.tobytes() == refs[i].recs.tobytes() and np.array_equal(order2, order)
+    pin.free()
