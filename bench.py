@@ -373,7 +373,9 @@ def ours(args):
     e2e_steps = max(1, args.e2e_steps)
     results = [None] * K
     errors = []
+    ready_evt = threading.Barrier(K + 1)                 # every thread has done its warm-up step
     start_evt = threading.Barrier(K + 1)
+    end_evt = threading.Barrier(K + 1)                   # reached after the last timed step, BEFORE buffers are freed
     numa = numa_cpus_of_gpu(local)
     span_budget_e2e = (max(int(w.spans_used) for w in wins) + 64) / n
     stagger_unit = 0.25 + 0.6 * (dev_ms / args.steps / 1e3)       # rough length of a step's copy phases, seconds
@@ -406,7 +408,8 @@ def ours(args):
             win = capi.GsWindowInfo()
             for step in range(e2e_steps + 1):            # step 0 = untimed warm-up (allocations)
                 if step == 1:
-                    start_evt.wait()                      # all threads + main: timed region starts
+                    ready_evt.wait()                      # warm-up done everywhere; main synchronises the ranks ...
+                    start_evt.wait()                      # ... and the timed region starts for all threads + main
                     ph = dict(load=0.0, run=0.0, fetch=0.0, check=0.0)
                     h2d = d2h = d2h_copied = chk = ev_cnt = 0
                     if k % 2 == 1 and args.e2e_stagger > 0:
@@ -436,6 +439,7 @@ def ours(args):
                     chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["node"])
                     ev_cnt += n + 2 * win.finished        # arrivals + starts + completions of a finished run
                 ph["check"] += time.perf_counter() - c3
+            end_evt.wait()                                # the timed region ends when the slowest thread gets here
             # the records really are the run: decode one replica of this thread and compare with the value run
             lib.gs_window(h, 0, C.byref(win))
             evb, qrb, jb, od, sp = capi.Engine.result_views(out, pitch, 0, lay, win)
@@ -446,26 +450,33 @@ def ours(args):
             e.close()
         except Exception as exc:                          # surface worker failures in the main thread
             errors.append(exc)
-            try:
-                start_evt.abort()
-            except Exception:
-                pass
+            for b_ in (ready_evt, start_evt, end_evt):
+                try:
+                    b_.abort()
+                except Exception:
+                    pass
 
     threads = [threading.Thread(target=worker, args=(k,)) for k in range(K)]
     for t in threads:
         t.start()
     try:
+        ready_evt.wait()
+        barrier_sync()                                    # all ranks start their timed region together
         start_evt.wait()                                  # released together with the workers' timed steps
     except threading.BrokenBarrierError:
         pass
-    barrier_sync()
     w0 = time.perf_counter()
+    try:
+        end_evt.wait()                                    # every thread has finished (and synchronised) its last timed step
+    except threading.BrokenBarrierError:
+        pass
+    e2e_wall = time.perf_counter() - w0
     for t in threads:
         t.join()
     if errors:
         raise errors[0]
     barrier_sync()
-    e2e_ms = red.max((time.perf_counter() - w0) * 1e3) / e2e_steps
+    e2e_ms = red.max(e2e_wall * 1e3) / e2e_steps
     h2d = sum(r[1] for r in results); d2h = sum(r[2] for r in results)
     checksum = sum(r[3] for r in results)
     assert sum(r[4] for r in results) == events_rank, "e2e run simulated a different number of events"
@@ -589,7 +600,7 @@ def sharded_block(args, rank, world, local, dev):
     from gpuschedule_b200 import dist as gdist
     n = args.sharded_jobs
     cluster = capi.make_cluster(4, 32, 8)
-    table = fast_table(n, BASE_SEED)
+    table = fast_table(n, BASE_SEED, rate=args.sharded_rate)
     pol = make_policy("gittins", table)
     red = gdist.Reducer(world, dev)
 
@@ -611,7 +622,7 @@ def sharded_block(args, rank, world, local, dev):
 
     with capi.Engine(device=local, nsims=1) as e1:
         ms1, events, single = timed(e1)
-    out = {"policy": "gittins", "jobs": n, "n_gpus": world, "events": int(events),
+    out = {"policy": "gittins", "jobs": n, "arrivals_per_tick": args.sharded_rate, "n_gpus": world, "events": int(events),
            "single_gpu": {"ms": red.max(ms1), "events_per_s": events / (red.max(ms1) / 1e3)}}
     if world > 1:
         with capi.Engine(device=local, nsims=1) as e2:
@@ -847,7 +858,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--jobs", type=int, default=100000)
-    ap.add_argument("--replicas", type=int, default=4736, help="replicas per GPU (one warp each; 4736 = 148 SMs x 32 warps)")
+    ap.add_argument("--replicas", type=int, default=4144, help="replicas per GPU (one warp each; 4144 = 148 SMs x 28 resident warps)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=16, help="host threads (one engine handle each) in the e2e run")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -862,6 +873,7 @@ def main():
     ap.add_argument("--policy-replicas", type=int, default=1024)
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-simulation-on-N-GPUs block (config C4)")
     ap.add_argument("--sharded-jobs", type=int, default=100000)
+    ap.add_argument("--sharded-rate", type=float, default=0.5, help="arrivals per tick of the C4 trace (0.5 = the BASELINE generator; higher rates build a long runnable list)")
     ap.add_argument("--only-sharded", action="store_true", help="print the C4 block alone (development)")
     ap.add_argument("--span-budget", type=float, default=1.5,
                     help="span-pool records per job (0 = worst case); the trace uses ~1.13, overflow is reported, never written")

@@ -3,7 +3,7 @@
 #pragma once
 
 #ifndef GS_TICK_MINBLOCKS
-#define GS_TICK_MINBLOCKS 32
+#define GS_TICK_MINBLOCKS 28     // 72 registers: no spills (64 spill), 28 warps per SM; measured best (profiles/r02_kernel_versions.md)
 #endif
 #define FULL 0xffffffffu
 
