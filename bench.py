@@ -37,6 +37,21 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 METRIC = "simulated events/sec (100k-job trace, 4x32x8 cluster)"
+# --config: c1 = the BASELINE metric's configuration (default); c5 = BASELINE configs[4]: 16x64x8 cluster, 1M-job trace
+# (arrivals 8x faster because the cluster is 8x larger; at most one fifo job starts per tick, so this is the deep-queue regime)
+CONFIGS = {"c1": dict(num_switch=4, num_node_p_switch=32, jobs=100000, rate=0.5, replicas=4144, label="4x32x8",
+                      metric=METRIC),
+           "c5": dict(num_switch=16, num_node_p_switch=64, jobs=1000000, rate=4.0, replicas=296, label="16x64x8",
+                      metric="simulated events/sec (1M-job trace, 16x64x8 cluster)")}
+
+
+def apply_config(args):
+    cfg = CONFIGS[args.config]
+    if args.jobs is None:
+        args.jobs = cfg["jobs"]
+    if args.replicas is None:
+        args.replicas = cfg["replicas"]
+    return cfg
 UNIT = "events/s"
 BASE_SEED = 1
 
@@ -141,10 +156,10 @@ def numa_cpus_of_gpu(index):
         return None
 
 
-def config_block(n, R):
+def config_block(n, R, label="4x32x8"):
     """The `config` both arms print (the reference arm runs a bounded sample of the same workload)."""
-    return {"workload": f"{n}-job synthetic trace x {R} replicas/GPU (distinct seeds), 4x32x8 cluster, fifo+yarn",
-            "jobs_per_replica": n, "replicas_per_gpu": R, "cluster": "4x32x8", "policy": "fifo", "scheme": "yarn",
+    return {"workload": f"{n}-job synthetic trace x {R} replicas/GPU (distinct seeds), {label} cluster, fifo+yarn",
+            "jobs_per_replica": n, "replicas_per_gpu": R, "cluster": label, "policy": "fifo", "scheme": "yarn",
             "l2": "inputs + outputs of a step (GBs per GPU) exceed the 126 MB L2"}
 
 
@@ -243,16 +258,20 @@ def ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    cfg = apply_config(args)
     R, n = args.replicas, args.jobs
-    cluster = capi.make_cluster(4, 32, 8)
-    M, G = 128, 8
+    cluster = capi.make_cluster(cfg["num_switch"], cfg["num_node_p_switch"], 8)
+    M, G = cfg["num_switch"] * cfg["num_node_p_switch"], 8
+    metric = cfg["metric"]
+    if args.config != "c1":
+        args.no_sharded = True                            # the C4 block and the CLI figure belong to the headline configuration
     t0 = time.time()
     seeds = gdist.replica_seeds(rank, world, R, base=BASE_SEED)
     if args.distinct and args.distinct < R:              # development only: fewer distinct traces, reused round robin
         seeds = [seeds[i % args.distinct] for i in range(R)]
     import concurrent.futures as cf
     with cf.ThreadPoolExecutor(min(32, len(os.sched_getaffinity(0)))) as ex:      # numpy releases the GIL in the generators
-        made = dict(zip(sorted(set(seeds)), ex.map(lambda sd: fast_table(n, sd), sorted(set(seeds)))))
+        made = dict(zip(sorted(set(seeds)), ex.map(lambda sd: fast_table(n, sd, rate=cfg["rate"]), sorted(set(seeds)))))
     tables = [made[sd] for sd in seeds]
     log(f"[rank {rank}] generated {len(made)} traces of {n} jobs in {time.time() - t0:.1f}s")
 
@@ -262,7 +281,7 @@ def ours(args):
         ev_all = red.sum(out["value"] * out["ms"] / 1e3)
         ms = red.max(out["ms"])
         if rank == 0:
-            out.update({"metric": METRIC, "value": ev_all / (ms / 1e3), "n_gpus": world, "steps": args.steps,
+            out.update({"metric": metric, "value": ev_all / (ms / 1e3), "n_gpus": world, "steps": args.steps,
                         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                         "vs_baseline": None, "data": "synthetic", "dtype": "int32/int64 (+f64 ranks)",
                         "config": {"workload": f"{n}-job synthetic trace x {R} replicas/GPU, 4x32x8, {args.policy}"}})
@@ -515,8 +534,9 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
         rp = min(R, args.policy_replicas)
-        for name, njobs in (("sjf", min(n, 10000)), ("dlas-gpu", n), ("gittins", n)):
-            tabs = tables[:rp] if njobs == n else [fast_table(njobs, sd) for sd in gdist.replica_seeds(0, 1, rp, base=BASE_SEED)]
+        pn = min(n, 100000)                              # C2: 10k-job sjf; C3 / C4: 100k jobs (c5: the same sizes on 16x64x8)
+        for name, njobs in (("sjf", min(pn, 10000)), ("dlas-gpu", pn), ("gittins", pn)):
+            tabs = tables[:rp] if njobs == n else [fast_table(njobs, sd, rate=cfg["rate"]) for sd in gdist.replica_seeds(0, 1, rp, base=BASE_SEED)]
             if name == "gittins":
                 tabs = tabs[:max(1, rp // 2)]
             try:
@@ -536,6 +556,34 @@ def ours(args):
                                      "achieved_gbs": pj["roofline"]["achieved"]}
         except Exception as exc:
             extras["place_batch"] = {"error": str(exc)}
+        # row f3: the command line end to end on the headline trace (ingest, engine, RNG-column replay, CSV writing)
+        try:
+            if args.config != "c1":
+                raise RuntimeError("measured on the headline configuration only")
+            import glob
+            import shutil
+            import tempfile
+            from gpuschedule_b200 import tracegen
+            tmp = tempfile.mkdtemp(prefix="gs_cli_")
+            tracegen.write_trace(os.path.join(tmp, "t.csv"), n, seed=BASE_SEED, rate=0.5)
+            cmd = [sys.executable, os.path.join(REPO, "run_sim.py"), "--num_switch", "4", "--num_node_p_switch", "32", "--num_gpu_p_node", "8",
+                   "--scheme", "yarn", "--schedule", "fifo", "--trace_file", "t.csv", "--log_path", "cli", "--seed", "7"]
+            best = None
+            for _ in range(2):
+                c0 = time.perf_counter()
+                cp = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=120)
+                dt = time.perf_counter() - c0
+                best = dt if best is None else min(best, dt)
+            runs = sorted(glob.glob(os.path.join(tmp, "log", "cli", "*")))
+            lines = sum(1 for _ in open(os.path.join(runs[-1], "cluster.csv"))) - 1
+            jl = sum(1 for _ in open(os.path.join(runs[-1], "job.csv"))) - 1
+            extras["cli"] = {"seconds": best, "cmd": "python run_sim.py --scheme yarn --schedule fifo (4x32x8) on the %d-job trace, --seed 7" % n,
+                             "cluster_csv_rows": lines, "job_csv_rows": jl, "events_per_s": 3.0 * jl / best, "rc": cp.returncode,
+                             "note": "process start to exit: imports, CUDA context, pandas ingest, engine, host replay of the sampled "
+                                     "utilisation column (numpy's sequential legacy generator), CSV formatting; round 1: 11.4 s"}
+            shutil.rmtree(tmp, ignore_errors=True)
+        except Exception as exc:
+            extras["cli"] = {"error": repr(exc)}
         # widening row f1 (horus / gandiva / horus+ engine): its own process with a time limit, so that nothing it
         # does can cost the main measurement
         try:
@@ -552,16 +600,22 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         t_cpu, ev_cpu, k = 0.0, 0, 0
-        while t_cpu < args.cpu_seconds and k < R:
+        if args.config == "c1":
+            while t_cpu < args.cpu_seconds and k < R:
+                c0 = time.perf_counter()
+                ref = oracle.run_fifo(cluster, tables[k], rows_cap=max(ticks) + 128, want_spans=False)
+                t_cpu += time.perf_counter() - c0
+                ev_cpu += ref.events
+                assert ref.ticks == ticks[k] and ref.events == st[k].events, "engine/oracle disagree"
+                k += 1
+            sample = f"{k} replica(s) of the {n}-job trace, full runs, oracle/gsched_oracle.c single thread"
+        else:       # the literal port re-scans M x G devices per tick: a full 1M-job run takes ~20 minutes, so a bounded sample
+            small = fast_table(20000, BASE_SEED, rate=cfg["rate"])
             c0 = time.perf_counter()
-            ref = oracle.run_fifo(cluster, tables[k], rows_cap=max(ticks) + 128, want_spans=False)
-            t_cpu += time.perf_counter() - c0
-            ev_cpu += ref.events
-            assert ref.ticks == ticks[k] and ref.events == st[k].events, "engine/oracle disagree"
-            k += 1
-        cpu = {"value": ev_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{k} replica(s) of the {n}-job trace, full runs, oracle/gsched_oracle.c single thread",
-               "host_cores": os.cpu_count()}
+            ref = oracle.run_fifo(cluster, small, want_spans=False)
+            t_cpu, ev_cpu, k = time.perf_counter() - c0, ref.events, 1
+            sample = f"one 20000-job trace of the same generator and cluster (bounded sample), oracle/gsched_oracle.c single thread"
+        cpu = {"value": ev_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count()}
         cpu_tight = tight_yardstick(cluster, tables[:1], 1, ticks[0])
 
     sharded = None
@@ -573,11 +627,11 @@ def ours(args):
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 (+f64 durations)",
             "data": "synthetic",
-            "config": config_block(n, R),
+            "config": config_block(n, R, cfg["label"]),
             "run": {"parallelism": f"replicas x{world} GPUs, no data-path collective", "events_per_step": events_all,
                     "ticks_per_step": red_ticks_all(ticks_rank, world), "step_bytes_per_gpu": written},
             "wall_ms_per_step": wall_ms / args.steps,
@@ -593,18 +647,17 @@ def ours(args):
 
 
 def sharded_block(args, rank, world, local, dev):
-    """BASELINE config C4: ONE gittins simulation of the 100k-job trace, on one GPU and sharded over the `world`
-    GPUs of the box (rank evaluation split by chunks of the runnable list, one NVLink peer-store exchange per event
-    inside the persistent kernel; include/gsched.h gs_comm_*).  Every rank runs both and compares the bytes."""
+    """BASELINE config C4: ONE gittins simulation, on one GPU and sharded over the `world` GPUs of the box (rank
+    evaluation split by chunks of the runnable list, one NVLink peer-store exchange per event inside the persistent
+    kernel; include/gsched.h gs_comm_*).  Every rank runs both and compares the bytes.  Two traces: the BASELINE one
+    (100k jobs, 0.5 arrivals per tick: ~20 runnable jobs, one chunk -- nothing to split, the exchange is pure cost) and an
+    overloaded one (30k jobs at 20 per tick: a runnable list of ~20 000)."""
     from gpuschedule_b200 import capi
     from gpuschedule_b200 import dist as gdist
-    n = args.sharded_jobs
     cluster = capi.make_cluster(4, 32, 8)
-    table = fast_table(n, BASE_SEED, rate=args.sharded_rate)
-    pol = make_policy("gittins", table)
     red = gdist.Reducer(world, dev)
 
-    def timed(eng):
+    def timed(eng, table, pol):
         eng.config(0, cluster, pol)
         eng.load_trace_packed(0, table.packed())
         run_to_done(eng, 0)
@@ -620,22 +673,32 @@ def sharded_block(args, rank, world, local, dev):
         recs, order = eng.fetch_jobs(0)
         return best, eng.stats(0).events, (rows.tobytes(), recs.tobytes(), order.tobytes())
 
-    with capi.Engine(device=local, nsims=1) as e1:
-        ms1, events, single = timed(e1)
-    out = {"policy": "gittins", "jobs": n, "arrivals_per_tick": args.sharded_rate, "n_gpus": world, "events": int(events),
-           "single_gpu": {"ms": red.max(ms1), "events_per_s": events / (red.max(ms1) / 1e3)}}
-    if world > 1:
-        with capi.Engine(device=local, nsims=1) as e2:
-            handles = gdist.exchange_comm_handles(e2.comm_prepare(n), world, dev)
-            e2.comm_init(rank, handles)
-            msN, eventsN, shard = timed(e2)
-            exchanges, us = e2.comm_stats()
-        same = red.sum(1.0 if (shard == single and eventsN == events) else 0.0)
-        msN = red.max(msN)
-        out["sharded"] = {"ms": msN, "events_per_s": events / (msN / 1e3), "exchanges": exchanges,
-                          "exchange_us_mean": red.max(us), "exchange": "NVLink peer stores + flag words inside the persistent kernel (no NCCL call on the data path)",
-                          "ranks_identical_to_single_gpu": int(same), "speedup_vs_single_gpu": out["single_gpu"]["ms"] / msN}
-    return out
+    def one(n, rate):
+        table = fast_table(n, BASE_SEED, rate=rate)
+        pol = make_policy("gittins", table)
+        with capi.Engine(device=local, nsims=1) as e1:
+            ms1, events, single = timed(e1, table, pol)
+        ms1 = red.max(ms1)
+        out = {"jobs": n, "arrivals_per_tick": rate, "events": int(events),
+               "single_gpu": {"ms": ms1, "events_per_s": events / (ms1 / 1e3)}}
+        if world > 1:
+            with capi.Engine(device=local, nsims=1) as e2:
+                handles = gdist.exchange_comm_handles(e2.comm_prepare(n), world, dev)
+                e2.comm_init(rank, handles)
+                msN, eventsN, shard = timed(e2, table, pol)
+                exchanges, us = e2.comm_stats()
+            same = red.sum(1.0 if (shard == single and eventsN == events) else 0.0)
+            msN = red.max(msN)
+            out["sharded"] = {"ms": msN, "events_per_s": events / (msN / 1e3), "exchanges": exchanges, "exchange_us_mean": red.max(us),
+                              "ranks_identical_to_single_gpu": int(same), "speedup_vs_single_gpu": ms1 / msN}
+        return out
+
+    blk = {"policy": "gittins", "n_gpus": world,
+           "exchange": "NVLink peer stores + flag words inside the persistent kernel (no NCCL call on the data path)",
+           "baseline_trace": one(args.sharded_jobs, args.sharded_rate)}
+    if not args.sharded_skip_overloaded:
+        blk["overloaded_trace"] = one(30000, 20.0)
+    return blk
 
 
 def red_ticks_all(ticks_rank, world):
@@ -814,11 +877,13 @@ def reference(args):
     import oracle
     from gpuschedule_b200 import capi
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cfg = apply_config(args)
     n = args.jobs
-    cluster = capi.make_cluster(4, 32, 8)
+    cluster = capi.make_cluster(cfg["num_switch"], cfg["num_node_p_switch"], 8)
     oracle.lib()
     threads = max(1, min(cores, args.cpu_threads or cores))     # default: every core, always (same denominator in every record)
-    tables = [fast_table(n, BASE_SEED + r) for r in range(threads)]
+    n_run = n if args.config == "c1" else 20000                 # c5: bounded sample (the literal port needs ~20 min per 1M-job run)
+    tables = [fast_table(n_run, BASE_SEED + r, rate=cfg["rate"]) for r in range(threads)]
     caps = [int(t.arrive_tick[-1]) + 2 * int(np.ceil(t.duration.max())) + 4096 for t in tables]
 
     def one(it):
@@ -836,12 +901,12 @@ def reference(args):
         dt = time.perf_counter() - t0
     value = events / dt
     tight = tight_yardstick(cluster, tables, threads)
-    sample = f"{threads} replicas of the {n}-job trace per step (one per thread on {cores} usable cores), full runs"
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+    sample = f"{threads} replicas of the {n_run}-job trace per step (one per thread on {cores} usable cores), full runs"
+    out = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT,
            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int32/int64 (+f64 durations)", "data": "synthetic",
-           "config": config_block(n, args.replicas),
+           "config": config_block(n, args.replicas, cfg["label"]),
            "run": {"replicas_per_step": threads, "host_threads": threads, "usable_cores": cores},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                             "note": "oracle/gsched_oracle.c: C restatement of the reference's Python loop "
@@ -857,8 +922,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--jobs", type=int, default=100000)
-    ap.add_argument("--replicas", type=int, default=4144, help="replicas per GPU (one warp each; 4144 = 148 SMs x 28 resident warps)")
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS), help="c1 = the BASELINE metric's configuration; c5 = 16x64x8, 1M-job traces")
+    ap.add_argument("--jobs", type=int, default=None, help="jobs per trace (default: the configuration's)")
+    ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU, one warp each (default c1: 4144 = 148 SMs x 28 resident warps)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=16, help="host threads (one engine handle each) in the e2e run")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -875,6 +941,7 @@ def main():
     ap.add_argument("--sharded-jobs", type=int, default=100000)
     ap.add_argument("--sharded-rate", type=float, default=0.5, help="arrivals per tick of the C4 trace (0.5 = the BASELINE generator; higher rates build a long runnable list)")
     ap.add_argument("--only-sharded", action="store_true", help="print the C4 block alone (development)")
+    ap.add_argument("--sharded-skip-overloaded", action="store_true")
     ap.add_argument("--span-budget", type=float, default=1.5,
                     help="span-pool records per job (0 = worst case); the trace uses ~1.13, overflow is reported, never written")
     ap.add_argument("--policy", default="fifo", choices=["fifo", "sjf", "dlas", "dlas-gpu", "gittins"],

@@ -92,14 +92,17 @@ def _format_bracketed(values):
 
 def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, spans, rng=None):
     """Text of the avg_gpu_utilization column for rows 0..n_rows-1."""
-    normal = np.random.normal if rng is None else rng.normal
+    # numpy's legacy normal(loc, scale) is loc + scale * gauss() (legacy-distributions.c: legacy_normal); drawing the
+    # standard values and applying the affine map in numpy is the same two roundings and 3x faster than broadcasting
+    # loc / scale through the generator (bit equality checked on 21 M samples, tests/test_oracle_golden.py pins the bytes)
+    std_normal = np.random.standard_normal if rng is None else rng.standard_normal
     total = n_nodes * gpus_per_node
     out = []
     loc_all = table.util_avg
     scale_all = (table.util_max - table.util_avg) / 2
     for counts, jobs in busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans):
         if len(jobs):
-            draw = normal(loc=loc_all[jobs], scale=scale_all[jobs])
+            draw = loc_all[jobs] + scale_all[jobs] * std_normal(len(jobs))
         else:
             draw = np.zeros(0)
         clipped = draw >= 100.0          # min(100, x) returns the int 100 unless x < 100

@@ -58,7 +58,7 @@ def test_reference_arm_runs_on_rank0_only(monkeypatch, capsys):
     import bench
     monkeypatch.setenv("RANK", "1")
     monkeypatch.setenv("WORLD_SIZE", "2")
-    args = type("A", (), dict(jobs=200, steps=1, warmup=0, cpu_threads=1, replicas=4736))()
+    args = type("A", (), dict(jobs=200, steps=1, warmup=0, cpu_threads=1, replicas=4736, config="c1"))()
     bench.reference(args)                          # non-zero ranks exit without work or output
     assert capsys.readouterr().out == ""
     monkeypatch.setenv("RANK", "0")
