@@ -290,6 +290,8 @@ def ours(args):
             dist.destroy_process_group()
         return
 
+    if args.config != "c1":
+        args.span_budget = 0.0                            # deep queues spread jobs over more nodes: keep the worst-case pool
     eng = capi.Engine(device=local, nsims=R)
     eng.set_span_budget(args.span_budget)
     for r in range(R):
@@ -402,71 +404,114 @@ def ours(args):
     import ctypes as C
     numa = None if args.no_numa else numa
 
+    class Half:
+        """one engine handle over half of a thread's replicas, with its page-locked input block and output blocks"""
+
+        def __init__(self, reps):
+            self.reps = reps
+            self.e = e = capi.Engine(device=local, nsims=len(reps))
+            e.set_async(True)
+            e.set_span_budget(span_budget_e2e)            # capacities sized by the warm-up run: the copied blocks carry little slack
+            e.set_queue_rows_cap(qrows_cap)
+            self.pin_in = capi.PinnedBuffer(len(reps) * n * 32)
+            block = self.pin_in.view(capi.JOBIN_DTYPE, len(reps) * n)
+            for i, r in enumerate(reps):
+                block[i * n:(i + 1) * n] = tables[r].packed()      # the step's inputs live in host memory
+                e.config(i, cluster)
+            self.n_each = np.full(len(reps), n, dtype=np.int64)
+            self.p_in, self.p_n = block.ctypes.data_as(C.c_void_p), self.n_each.ctypes.data_as(C.POINTER(C.c_int64))
+            self.pin_out = self.out = self.lay = self.p_out = None
+            self.pitch = 0
+            self.pending = False                          # a read-back is in flight
+
+        def load(self):                                   # ONE strided upload (asynchronous)
+            if self.e.lib.gs_load_traces_packed(self.e.h, self.p_in, n * 32, self.p_n) != 0:
+                raise capi.GsError("gs_load_traces_packed failed: " + self.e.lib.gs_last_error(self.e.h).decode())
+            return len(self.reps) * n * 32
+
+        def run(self):
+            run_to_done(self.e, rows_cap)
+
+        def fetch(self):                                  # ONE strided read-back (asynchronous)
+            if self.pin_out is None:                      # first step: the result-block layout is known now
+                self.lay = self.e.result_layout(0)
+                self.pitch = (int(self.lay.block_bytes) + 255) // 256 * 256
+                self.pin_out = capi.PinnedBuffer(len(self.reps) * self.pitch)
+                self.out = self.pin_out.view(np.uint8, len(self.reps) * self.pitch)
+                self.p_out = self.out.ctypes.data_as(C.c_void_p)
+            if self.e.lib.gs_fetch_results(self.e.h, 0, len(self.reps), self.p_out, self.pitch) != 0:
+                raise capi.GsError("gs_fetch_results failed: " + self.e.lib.gs_last_error(self.e.h).decode())
+            self.pending = True
+
+        def finish(self, win):
+            """wait for the read-back and touch every replica's results -> (valid bytes, copied bytes, checksum, events)"""
+            self.e.sync()
+            self.pending = False
+            valid = chk = ev = 0
+            for i in range(len(self.reps)):
+                self.e.lib.gs_window(self.e.h, i, C.byref(win))
+                evb, qrb, jb, od, sp = capi.Engine.result_views(self.out, self.pitch, i, self.lay, win)
+                valid += 32 * (win.ev_rows + win.q_rows) + 8 * n + 4 * win.finished + 16 * win.spans_used
+                chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["node"])
+                ev += n + 2 * win.finished                # arrivals + starts + completions of a finished run
+            return valid, len(self.reps) * int(self.lay.block_bytes), chk, ev
+
+        def close(self):
+            self.pin_in.free()
+            if self.pin_out is not None:
+                self.pin_out.free()
+            self.e.close()
+
     def worker(k):
         try:
             if numa:
                 os.sched_setaffinity(0, numa)            # this thread only: its pinned allocations are node-local
             mine = slices[k]
-            e = capi.Engine(device=local, nsims=len(mine))
-            e.set_async(True)
-            e.set_span_budget(span_budget_e2e)            # capacities sized by the warm-up run: the copied blocks carry little slack
-            e.set_queue_rows_cap(qrows_cap)
-            # the step's inputs: every trace of this thread in one page-locked block, trace i at i * n * 32
-            pin_in = capi.PinnedBuffer(len(mine) * n * 32)
-            block = pin_in.view(capi.JOBIN_DTYPE, len(mine) * n)
-            for i, r in enumerate(mine):
-                block[i * n:(i + 1) * n] = tables[r].packed()
-                e.config(i, cluster)
-            n_each = np.full(len(mine), n, dtype=np.int64)
-            p_in, p_n = block.ctypes.data_as(C.c_void_p), n_each.ctypes.data_as(C.POINTER(C.c_int64))
-            lib, h = e.lib, e.h
-            pin_out = out = lay = None
-            pitch = 0
-            ph = dict(load=0.0, run=0.0, fetch=0.0, check=0.0)
+            # two handles per thread: while one half's results travel to the host, the other half uploads and simulates
+            cut = (len(mine) + 1) // 2
+            halves = [Half(mine[:cut])] + ([Half(mine[cut:])] if len(mine) > cut else [])
+            ph = dict(load=0.0, run=0.0, finish=0.0)
             h2d = d2h = d2h_copied = chk = ev_cnt = 0
             win = capi.GsWindowInfo()
             for step in range(e2e_steps + 1):            # step 0 = untimed warm-up (allocations)
                 if step == 1:
+                    for hf in halves:                     # drain the warm-up step completely
+                        if hf.pending:
+                            hf.finish(win)
                     ready_evt.wait()                      # warm-up done everywhere; main synchronises the ranks ...
                     start_evt.wait()                      # ... and the timed region starts for all threads + main
-                    ph = dict(load=0.0, run=0.0, fetch=0.0, check=0.0)
+                    ph = dict(load=0.0, run=0.0, finish=0.0)
                     h2d = d2h = d2h_copied = chk = ev_cnt = 0
                     if k % 2 == 1 and args.e2e_stagger > 0:
-                        time.sleep(args.e2e_stagger * stagger_unit)     # odd threads run half a step behind the even ones
-                c0 = time.perf_counter()
-                if lib.gs_load_traces_packed(h, p_in, n * 32, p_n) != 0:          # ONE strided upload (asynchronous)
-                    raise capi.GsError("gs_load_traces_packed failed: " + lib.gs_last_error(h).decode())
-                h2d += len(mine) * n * 32
-                c1 = time.perf_counter(); ph["load"] += c1 - c0
-                run_to_done(e, rows_cap)
-                c2 = time.perf_counter(); ph["run"] += c2 - c1
-                if pin_out is None:                       # first step: the result-block layout is known now
-                    lay = e.result_layout(0)
-                    pitch = (int(lay.block_bytes) + 255) // 256 * 256
-                    pin_out = capi.PinnedBuffer(len(mine) * pitch)
-                    out = pin_out.view(np.uint8, len(mine) * pitch)
-                    p_out = out.ctypes.data_as(C.c_void_p)
-                if lib.gs_fetch_results(h, 0, len(mine), p_out, pitch) != 0:       # ONE strided read-back
-                    raise capi.GsError("gs_fetch_results failed: " + lib.gs_last_error(h).decode())
-                e.sync()
-                c3 = time.perf_counter(); ph["fetch"] += c3 - c2
-                d2h_copied += len(mine) * int(lay.block_bytes)
-                for i in range(len(mine)):                # touch every replica's results
-                    lib.gs_window(h, i, C.byref(win))
-                    evb, qrb, jb, od, sp = capi.Engine.result_views(out, pitch, i, lay, win)
-                    d2h += 32 * (win.ev_rows + win.q_rows) + 8 * n + 4 * win.finished + 16 * win.spans_used
-                    chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["node"])
-                    ev_cnt += n + 2 * win.finished        # arrivals + starts + completions of a finished run
-                ph["check"] += time.perf_counter() - c3
+                        time.sleep(args.e2e_stagger * stagger_unit)     # odd threads run a fraction of a step behind the even ones
+                for hf in halves:
+                    other = halves[1 - halves.index(hf)] if len(halves) == 2 else None
+                    c0 = time.perf_counter()
+                    if hf.pending:                        # (single-handle case) its own previous read-back first
+                        v, cp, ck, ev = hf.finish(win); d2h += v; d2h_copied += cp; chk += ck; ev_cnt += ev
+                    h2d += hf.load()
+                    c1 = time.perf_counter(); ph["load"] += c1 - c0
+                    hf.run()                              # the other half's read-back proceeds on its own stream meanwhile
+                    c2 = time.perf_counter(); ph["run"] += c2 - c1
+                    hf.fetch()
+                    if other is not None and other.pending:
+                        v, cp, ck, ev = other.finish(win); d2h += v; d2h_copied += cp; chk += ck; ev_cnt += ev
+                    ph["finish"] += time.perf_counter() - c2
+            c2 = time.perf_counter()
+            for hf in halves:                             # the last read-backs belong to the timed region
+                if hf.pending:
+                    v, cp, ck, ev = hf.finish(win); d2h += v; d2h_copied += cp; chk += ck; ev_cnt += ev
+            ph["finish"] += time.perf_counter() - c2
             end_evt.wait()                                # the timed region ends when the slowest thread gets here
             # the records really are the run: decode one replica of this thread and compare with the value run
-            lib.gs_window(h, 0, C.byref(win))
-            evb, qrb, jb, od, sp = capi.Engine.result_views(out, pitch, 0, lay, win)
+            hf = halves[0]
+            hf.e.lib.gs_window(hf.e.h, 0, C.byref(win))
+            evb, qrb, jb, od, sp = capi.Engine.result_views(hf.out, hf.pitch, 0, hf.lay, win)
             rows = lm.expand_rows(evb, qrb, win.row_first, win.ticks, M, G)
             assert len(rows) == ticks[mine[0]] and int(rows["finished"][-1]) == n and int(rows["now"][-1]) == ticks[mine[0]]
             results[k] = (ph, h2d // e2e_steps, d2h // e2e_steps, chk, ev_cnt // e2e_steps, d2h_copied // e2e_steps)
-            pin_in.free(); pin_out.free()
-            e.close()
+            for hf in halves:
+                hf.close()
         except Exception as exc:                          # surface worker failures in the main thread
             errors.append(exc)
             for b_ in (ready_evt, start_evt, end_evt):
@@ -499,7 +544,7 @@ def ours(args):
     h2d = sum(r[1] for r in results); d2h = sum(r[2] for r in results)
     checksum = sum(r[3] for r in results)
     assert sum(r[4] for r in results) == events_rank, "e2e run simulated a different number of events"
-    ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "fetch", "check")}
+    ph = {k: max(r[0][k] for r in results) for k in ("load", "run", "finish")}
     d2h_copied = sum(r[5] for r in results)
     e2e = {"value": events_all / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(red.sum(h2d)), "d2h_bytes_per_step": int(red.sum(d2h_copied)),
@@ -507,6 +552,7 @@ def ours(args):
            "steps": e2e_steps, "host_threads": K, "pinned_buffers_numa_local": bool(numa),
            "timing": "wall clock between barrier+synchronize around the timed steps of all threads, max over ranks",
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
+           "pipeline": "two engine handles per host thread: the strided read-back of one half overlaps the strided upload and the kernel of the other",
            "result_format": "compact records (gs_evrow/gs_qrow/gs_job_run/finish order/spans), one strided copy per handle each way "
                             "(d2h_bytes counts the copied blocks incl. their unused capacity); one replica per thread is decoded to full rows and checked",
            "checksum": checksum}
@@ -651,19 +697,19 @@ def sharded_block(args, rank, world, local, dev):
     evaluation split by chunks of the runnable list, one NVLink peer-store exchange per event inside the persistent
     kernel; include/gsched.h gs_comm_*).  Every rank runs both and compares the bytes.  Two traces: the BASELINE one
     (100k jobs, 0.5 arrivals per tick: ~20 runnable jobs, one chunk -- nothing to split, the exchange is pure cost) and an
-    overloaded one (30k jobs at 20 per tick: a runnable list of ~20 000)."""
+    overloaded one (12k jobs at 20 per tick: a runnable list of several thousand)."""
     from gpuschedule_b200 import capi
     from gpuschedule_b200 import dist as gdist
     cluster = capi.make_cluster(4, 32, 8)
     red = gdist.Reducer(world, dev)
 
-    def timed(eng, table, pol):
+    def timed(eng, table, pol, reps=2):
         eng.config(0, cluster, pol)
         eng.load_trace_packed(0, table.packed())
         run_to_done(eng, 0)
         cap = eng.stats(0).ticks + 64
         best = None
-        for _ in range(2):
+        for _ in range(reps):
             eng.reset()
             red.barrier()
             run_to_done(eng, cap)
@@ -673,31 +719,35 @@ def sharded_block(args, rank, world, local, dev):
         recs, order = eng.fetch_jobs(0)
         return best, eng.stats(0).events, (rows.tobytes(), recs.tobytes(), order.tobytes())
 
-    def one(n, rate):
+    def one(n, rate, reps=2):
         table = fast_table(n, BASE_SEED, rate=rate)
         pol = make_policy("gittins", table)
         with capi.Engine(device=local, nsims=1) as e1:
-            ms1, events, single = timed(e1, table, pol)
+            ms1, events, single = timed(e1, table, pol, reps)
         ms1 = red.max(ms1)
         out = {"jobs": n, "arrivals_per_tick": rate, "events": int(events),
                "single_gpu": {"ms": ms1, "events_per_s": events / (ms1 / 1e3)}}
         if world > 1:
-            with capi.Engine(device=local, nsims=1) as e2:
-                handles = gdist.exchange_comm_handles(e2.comm_prepare(n), world, dev)
-                e2.comm_init(rank, handles)
-                msN, eventsN, shard = timed(e2, table, pol)
-                exchanges, us = e2.comm_stats()
-            same = red.sum(1.0 if (shard == single and eventsN == events) else 0.0)
-            msN = red.max(msN)
-            out["sharded"] = {"ms": msN, "events_per_s": events / (msN / 1e3), "exchanges": exchanges, "exchange_us_mean": red.max(us),
-                              "ranks_identical_to_single_gpu": int(same), "speedup_vs_single_gpu": ms1 / msN}
+            # "always": an exchange on every event (what the north-star sketches); "adaptive" (the default): events whose
+            # runnable list is at most 256 jobs long are evaluated by every rank itself, without sending anything
+            for key, min_rn in (("sharded_always_exchange", 0), ("sharded", 256)):
+                with capi.Engine(device=local, nsims=1) as e2:
+                    handles = gdist.exchange_comm_handles(e2.comm_prepare(n), world, dev)
+                    e2.comm_init(rank, handles)
+                    e2.comm_set_min_runnable(min_rn)
+                    msN, eventsN, shard = timed(e2, table, pol, reps)
+                    exchanges, us = e2.comm_stats()
+                same = red.sum(1.0 if (shard == single and eventsN == events) else 0.0)
+                msN = red.max(msN)
+                out[key] = {"ms": msN, "events_per_s": events / (msN / 1e3), "min_runnable_for_exchange": min_rn, "exchanges": exchanges,
+                            "exchange_us_mean": red.max(us), "ranks_identical_to_single_gpu": int(same), "speedup_vs_single_gpu": ms1 / msN}
         return out
 
     blk = {"policy": "gittins", "n_gpus": world,
            "exchange": "NVLink peer stores + flag words inside the persistent kernel (no NCCL call on the data path)",
            "baseline_trace": one(args.sharded_jobs, args.sharded_rate)}
     if not args.sharded_skip_overloaded:
-        blk["overloaded_trace"] = one(30000, 20.0)
+        blk["overloaded_trace"] = one(12000, 20.0, reps=1)
     return blk
 
 

@@ -230,7 +230,8 @@ def load_library():
     lib.gs_comm_prepare.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.gs_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.gs_comm_stats.argtypes = [C.c_void_p, i64p, f64p]
-    for name in ("gs_comm_prepare", "gs_comm_init", "gs_comm_stats"):
+    lib.gs_comm_set_min_runnable.argtypes = [C.c_void_p, C.c_int]
+    for name in ("gs_comm_prepare", "gs_comm_init", "gs_comm_stats", "gs_comm_set_min_runnable"):
         getattr(lib, name).restype = C.c_int
     lib.gs_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.gs_host_free.argtypes = [C.c_void_p]
@@ -568,6 +569,10 @@ class Engine:
         assert len(blob) == 64 * len(handles)
         buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
         self._check(self.lib.gs_comm_init(self.h, int(rank), len(handles), C.cast(buf, C.c_void_p)), "gs_comm_init")
+
+    def comm_set_min_runnable(self, k):
+        """events with at most k runnable jobs are evaluated locally by every rank (default 256); 0 = always exchange"""
+        self._check(self.lib.gs_comm_set_min_runnable(self.h, int(k)), "gs_comm_set_min_runnable")
 
     def comm_stats(self):
         """(exchanges of the last run, mean microseconds from publishing to having seen every peer)"""

@@ -60,6 +60,7 @@ struct SimDev {
   // of one box; each rank stores the ranks it computed straight into every peer's receive buffer over NVLink
   // (peer stores) and publishes an event counter; nothing else crosses the link
   int comm_rank, comm_n;                     // comm_n <= 1: not sharded
+  int comm_min_runnable, comm_pad;           // events with at most this many runnable jobs are evaluated locally, without an exchange
   long long comm_cap;                        // rank values per receive buffer (>= n)
   double *comm_rk_in;                        // local receive buffers: 2 x comm_cap doubles, selected by event parity
   unsigned long long *comm_flags;            // local flags[comm_n]: the event counter last published by each rank

@@ -563,7 +563,8 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   bool done = false;
   // sharded mode (gs_comm_init): rank `me` of `nr` evaluates the gittins index for the chunks c of the runnable list
   // with c % nr == me and stores the values into every rank's receive buffer; one exchange per event
-  const int nr = (!sjf && S.comm_n > 1) ? S.comm_n : 1, me = S.comm_rank;
+  const int nr_all = (!sjf && S.comm_n > 1) ? S.comm_n : 1, me = S.comm_rank;
+  const int min_rn = S.comm_min_runnable;       // shorter runnable lists are not worth an exchange: every rank evaluates them itself
   const long long ccap = S.comm_cap;
   unsigned long long epoch = S.comm_epoch;
   long long wait_cycles = 0;
@@ -607,6 +608,8 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     }
     __syncwarp();
     // ---- pass 1: drop END, age counters, (gittins) rank of every survivor at its new position
+    // (the list length is the same on every rank, so all of them take the same decision about the exchange)
+    const int nr = (nr_all > 1 && rn > min_rn) ? nr_all : 1;
     {
       int w = 0;
       for (int base = 0; base < rn; base += 32) {

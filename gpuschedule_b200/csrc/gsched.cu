@@ -107,6 +107,7 @@ struct gs_engine {
   // sharded single simulation (gs_comm_prepare / gs_comm_init)
   void *comm_buf = nullptr; int64_t comm_cap = 0; int comm_rank = 0, comm_n = 0;
   void *comm_peer[GS_MAX_RANKS] = {nullptr}; bool comm_opened[GS_MAX_RANKS] = {false};
+  int comm_min_runnable = 256;             // gs_comm_set_min_runnable
   unsigned long long comm_epoch = 0, comm_epoch0 = 0;   // exchange counter: continues across runs / value at the last prepare
   bool dirty = true;       // host mirror of SimDev newer than device copy
 };
@@ -468,7 +469,7 @@ static int bind_sim(gs_handle h, SimHost &s, const SimLayout &L, unsigned char *
     // the event counter never restarts: a new run continues where the last one ended (all ranks execute the same
     // events, so their counters agree), which needs no reset of the flag words and no extra synchronisation
     D.comm_epoch = h->comm_epoch; h->comm_epoch0 = h->comm_epoch;
-    D.comm_n = h->comm_n; D.comm_rank = h->comm_rank; D.comm_cap = h->comm_cap;
+    D.comm_n = h->comm_n; D.comm_rank = h->comm_rank; D.comm_cap = h->comm_cap; D.comm_min_runnable = h->comm_min_runnable;
     D.comm_flags = (unsigned long long *)h->comm_buf;
     D.comm_rk_in = (double *)((unsigned char *)h->comm_buf + 256);
     for (int q = 0; q < h->comm_n; ++q) {
@@ -656,6 +657,18 @@ extern "C" int gs_comm_init(gs_handle h, int rank, int nranks, const gs_comm_han
     h->comm_peer[q] = ptr; h->comm_opened[q] = true;
   }
   h->comm_rank = rank; h->comm_n = nranks;
+  for (auto &s : h->sims) s.prepared = false;
+  h->dirty = true;
+  return GS_OK;
+}
+
+// Events whose runnable list has at most `k` entries are evaluated by every rank itself (identical state, identical
+// result, nothing to send); longer lists are split and exchanged.  k = 0: exchange on every event.  Must be the same on
+// every rank; takes effect for replicas prepared afterwards.
+extern "C" int gs_comm_set_min_runnable(gs_handle h, int k) {
+  if (!h) return GS_ERR_ARG;
+  if (k < 0) return fail(h, GS_ERR_ARG, "gs_comm_set_min_runnable: must be >= 0");
+  h->comm_min_runnable = k;
   for (auto &s : h->sims) s.prepared = false;
   h->dirty = true;
   return GS_OK;

@@ -47,12 +47,18 @@ def _worker(rank, world, port, out, n_jobs):
         with capi.Engine(device=rank, nsims=1) as e2:
             handles = gd.exchange_comm_handles(e2.comm_prepare(table.n), world, torch.device("cuda", rank))
             e2.comm_init(rank, handles)
+            e2.comm_set_min_runnable(0)                  # exchange on EVERY event, however short the runnable list
             sharded = run(e2)
             exchanges, us = e2.comm_stats()
             e2.reset()                                   # a second run continues the exchange counter
             again = run(e2)
+            e2.comm_set_min_runnable(48)                 # adaptive: only events with more than 48 runnable jobs exchange
+            e2.reset()
+            adaptive = run(e2)
+            ex_adaptive, _ = e2.comm_stats()
         ref = oracle.run_policy(cluster, pol, table)
-        ok = (sharded == single and again == single and single[0] == ref.rows.tobytes() and single[1] == ref.recs.tobytes())
+        ok = (sharded == single and again == single and adaptive == single and single[0] == ref.rows.tobytes()
+              and single[1] == ref.recs.tobytes() and 0 < ex_adaptive < exchanges)
         dist.barrier()
         dist.destroy_process_group()
         out.put((rank, ok, exchanges, us, single[3]))
