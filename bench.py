@@ -128,9 +128,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_to_done(eng, rows_cap):
+def run_to_done(eng, rows_cap, totals=None):
+    """run every replica to its end; `totals` (dict) receives per replica the records written over ALL windows"""
     while True:
         eng.run(0, rows_cap)
+        if totals is not None:
+            for s in range(eng.nsims):
+                w = eng.window(s)
+                t = totals.setdefault(s, [0, 0])
+                t[0] += int(w.ev_rows); t[1] += int(w.q_rows)
         if all(eng.stats(s).done for s in range(eng.nsims)):
             return
 
@@ -299,11 +305,12 @@ def ours(args):
         eng.load_trace_packed(r, tables[r].packed())
 
     # ---- warm-up (also sizes the per-replica record windows so that one launch completes a run)
-    run_to_done(eng, 0)
+    totals = {}
+    run_to_done(eng, 0, totals)                           # (a deep-queue run needs several default-sized windows)
     wins = [eng.window(r) for r in range(R)]
     ticks = [int(w.ticks) for w in wins]
-    rows_cap = max(int(w.ev_rows) for w in wins) + 256
-    qrows_cap = max(int(w.q_rows) for w in wins) + 256
+    rows_cap = max(t[0] for t in totals.values()) + 256
+    qrows_cap = max(t[1] for t in totals.values()) + 256
     eng.set_queue_rows_cap(qrows_cap)
     for _ in range(max(args.warmup - 1, 2)):
         eng.reset()
@@ -330,7 +337,7 @@ def ours(args):
     ticks_rank = sum(s.ticks for s in st)
     evals_rank = sum(s.placement_evals for s in st)
     spans_rank = sum(int(w.spans_used) for w in wins)
-    recs_rank = sum(int(w.ev_rows) + int(w.q_rows) for w in wins)
+    recs_rank = sum(int(w.ev_rows) + int(w.q_rows) for w in wins)      # (one window per run once the capacities are sized)
     dev_ms = red.max(dev_ms)
     wall_ms = red.max(wall_ms)
     events_all = red.sum(events_rank)
@@ -633,8 +640,8 @@ def ours(args):
         # widening row f1 (horus / gandiva / horus+ engine): its own process with a time limit, so that nothing it
         # does can cost the main measurement
         try:
-            hp = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "horus", "--horus-replicas", "1184"],
-                                capture_output=True, text=True, timeout=240)
+            hp = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "horus", "--horus-replicas", "9472"],
+                                capture_output=True, text=True, timeout=400)
             line = [ln for ln in hp.stdout.splitlines() if ln.startswith("{")]
             extras["horus"] = json.loads(line[-1]) if line else {"error": (hp.stderr or "no output")[-400:]}
         except Exception as exc:

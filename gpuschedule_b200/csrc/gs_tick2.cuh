@@ -59,7 +59,11 @@ template <> struct MaskOps<false> {
 template <typename T>
 __device__ __forceinline__ T take_lowest(T idle, int cnt) {
   // the `cnt` lowest set bits of `idle` (devices are claimed in index order, node.py:208-216)
-  if (cnt == 1) return idle & (~idle + (T)1);
+  const T low = idle & (~idle + (T)1);              // lowest set bit
+  if (cnt == 1) return low;
+  // idle devices are mostly a contiguous run (claimed lowest first): `cnt` consecutive set bits starting at the lowest one
+  const T run = (cnt >= (int)(8 * sizeof(T))) ? ~(T)0 : (low << cnt) - low;
+  if ((idle & run) == run) return run;
   T m = idle;
   for (int i = 0; i < cnt && m; ++i) m &= m - (T)1;
   return idle ^ m;
@@ -288,6 +292,15 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
       const int hg = hpk & 0xffffff, hgpc = (int)((unsigned)hpk >> 24);
       const int htasks = hgpc == 1 ? hg : hg / hgpc;
       const bool placeable = hneed > 0;            // Device.can_fit on an empty device
+      // the wheel bucket this job would finish in is known before the placement runs (without network costs): issue the
+      // two loads of its current head / memory sum now, so that their L2 latency passes during the node scan
+      int pre_bk = 0, pre_head = -1;
+      long long pre_wm = 0;
+      if (!NET && placeable) {
+        pre_bk = (delta + min(hneed, wmask)) & wmask;
+        pre_head = whead[pre_bk];
+        pre_wm = wmem[pre_bk];
+      }
       bool ok = false;
       int nspans = 0, where = 0;
       const int span_first = span_used;
@@ -411,8 +424,8 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         // push on the finish-tick bucket of the timing wheel (released in start order, see E)
         if (endt < next_fin) { next_fin = endt; nf_head = j; nf_js = js; }
         else if (endt == next_fin) { js.next = nf_head; nf_head = j; nf_js = js; }
-        else js.next = whead[bk];
-        const long long wm = wmem[bk];
+        else js.next = NET ? whead[bk] : pre_head;
+        const long long wm = NET ? wmem[bk] : pre_wm;
         whead[bk] = j;                                   // warp-uniform stores (same address, same value from every lane)
         wmem[bk] = wm + hmemc;
         *reinterpret_cast<int4 *>(&jst[j]) = *reinterpret_cast<const int4 *>(&js);
