@@ -366,7 +366,7 @@ def ours(args):
                 ms1 = e1.stats(0).kernel_ms
                 best = ms1 if best is None else min(best, ms1)
             single = {"value": e1.stats(0).events / (best / 1e3), "unit": UNIT, "ms": best,
-                      "note": "one 100k-job simulation alone on the GPU: one warp, latency bound by construction"}
+                      "note": "one %d-job simulation alone on the GPU: one warp, latency bound by construction" % n}
 
     # ---- roofline of the dominant kernel (gs_tick2_kernel), per launch, this rank's GPU.  Algorithmic bytes are
     # SURVEY 8(d)'s: job table in + job record out (56 B/job), one 16-B span per (job, node), one 64-B statistics
