@@ -372,7 +372,7 @@ def ours(args):
     # SURVEY 8(d)'s: job table in + job record out (56 B/job), one 16-B span per (job, node), one 64-B statistics
     # row per simulated tick -- the information the launch produces, whatever encoding the engine writes it in.
     alg_bytes = R * n * 56 + spans_rank * 16 + ticks_rank * 64
-    written = R * n * (32 + 8 + 4) + spans_rank * 16 + recs_rank * 32
+    written = R * n * (32 + 4 + 4) + spans_rank * 8 + recs_rank * 32
     peak, peak_src = peaks()
     ach = alg_bytes / (dev_ms / args.steps / 1e3) / 1e9
     traffic, traffic_src = None, None
@@ -458,8 +458,8 @@ def ours(args):
             for i in range(len(self.reps)):
                 self.e.lib.gs_window(self.e.h, i, C.byref(win))
                 evb, qrb, jb, od, sp = capi.Engine.result_views(self.out, self.pitch, i, self.lay, win)
-                valid += 32 * (win.ev_rows + win.q_rows) + 8 * n + 4 * win.finished + 16 * win.spans_used
-                chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["node"])
+                valid += 32 * (win.ev_rows + win.q_rows) + 4 * n + 4 * win.finished + int(self.lay.span_bytes) * win.spans_used
+                chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["devmask"])
                 ev += n + 2 * win.finished                # arrivals + starts + completions of a finished run
             return valid, len(self.reps) * int(self.lay.block_bytes), chk, ev
 
@@ -560,7 +560,7 @@ def ours(args):
            "timing": "wall clock between barrier+synchronize around the timed steps of all threads, max over ranks",
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
            "pipeline": "two engine handles per host thread: the strided read-back of one half overlaps the strided upload and the kernel of the other",
-           "result_format": "compact records (gs_evrow/gs_qrow/gs_job_run/finish order/spans), one strided copy per handle each way "
+           "result_format": "compact records (gs_evrow / gs_qrow / start ticks / finish order / gs_cspan), one strided copy per handle each way "
                             "(d2h_bytes counts the copied blocks incl. their unused capacity); one replica per thread is decoded to full rows and checked",
            "checksum": checksum}
 
@@ -849,6 +849,9 @@ def horus_mode(args):
         rows0, util0, flags0, recs0, order0 = eng.fetch(0)
     ref = oracle.run_horus(cluster, tables[0], scheme="horus", schedule="horus", num_buffer=5, seed=0)
     assert rows0.tobytes() == ref.rows.tobytes() and util0.tobytes() == ref.util.tobytes(), "replica 0 differs from the oracle"
+    if args.horus_scalar_only:                              # development: the scalar mapping's time alone
+        print(json.dumps({"value": events / (ms / 1e3), "kernel_ms_by_lanes_per_warp": by_lanes, "replicas": R}), flush=True)
+        return
     # horus+ (credit queues + k-means, raw word stream): a few replicas against the oracle, replica by replica
     plus = None
     try:
@@ -1009,6 +1012,7 @@ def main():
     ap.add_argument("--horus-stream", type=int, default=4000000, help="standard-normal samples loaded per replica")
     ap.add_argument("--horus-rows", type=int, default=8192)
     ap.add_argument("--horus-both-mappings", action="store_true", help="also time 32 simulations per warp")
+    ap.add_argument("--horus-scalar-only", action="store_true", help="development: time the scalar mapping and stop")
     ap.add_argument("--horus-words", type=int, default=6 << 20, help="raw generator words for the horus+ device check")
     ap.add_argument("--place-jobs", type=int, default=64 * 1024 * 1024)
     args = ap.parse_args()

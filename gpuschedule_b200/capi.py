@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .log_manager import EVROW_DTYPE, JOB_DTYPE, JOBRUN_DTYPE, QROW_DTYPE, ROW_DTYPE, SPAN_DTYPE
+from .log_manager import CSPAN_DTYPE, EVROW_DTYPE, JOB_DTYPE, JOBRUN_DTYPE, QROW_DTYPE, ROW_DTYPE, SPAN_DTYPE
 
 GS_MAX_QUEUES = 8
 SCHEDULES = {"fifo": 0, "sjf": 1, "dlas": 2, "dlas-gpu": 3, "gittins": 4}
@@ -64,7 +64,7 @@ class GsWindowInfo(C.Structure):
 class GsResultLayout(C.Structure):
     _fields_ = [("block_bytes", C.c_int64), ("off_ev", C.c_int64), ("off_q", C.c_int64), ("off_jobs", C.c_int64),
                 ("off_duration", C.c_int64), ("off_finish_order", C.c_int64), ("off_spans", C.c_int64),
-                ("cap_ev", C.c_int64), ("cap_q", C.c_int64), ("cap_spans", C.c_int64), ("n", C.c_int64)]
+                ("cap_ev", C.c_int64), ("cap_q", C.c_int64), ("cap_spans", C.c_int64), ("n", C.c_int64), ("span_bytes", C.c_int64)]
 
 
 JOBIN_DTYPE = np.dtype([("arrive_tick", "<i4"), ("gpus", "<i4"), ("gpu_per_task", "<i4"), ("ps_count", "<i4"),
@@ -239,7 +239,7 @@ def load_library():
                  "gs_fetch_rows", "gs_fetch_jobs", "gs_fetch_spans", "gs_place_batch",
                  "gs_net_cost"):
         getattr(lib, name).restype = C.c_int
-    if lib.gs_abi_version() != 2:
+    if lib.gs_abi_version() != 3:
         raise GsError("libgsched.so ABI version mismatch")
     declare_horus_prototypes(lib)
     lib.gs_build_tag.restype = C.c_char_p
@@ -503,11 +503,11 @@ class Engine:
         qr = np.frombuffer(buf, dtype=QROW_DTYPE, count=int(win.q_rows), offset=base + lay.off_q)
         jobs = np.frombuffer(buf, dtype=JOBRUN_DTYPE, count=int(win.n), offset=base + lay.off_jobs)
         order = np.frombuffer(buf, dtype=np.int32, count=int(win.finished), offset=base + lay.off_finish_order)
-        spans = np.frombuffer(buf, dtype=SPAN_DTYPE, count=int(win.spans_used), offset=base + lay.off_spans)
+        spans = np.frombuffer(buf, dtype=CSPAN_DTYPE if lay.span_bytes == 8 else SPAN_DTYPE, count=int(win.spans_used), offset=base + lay.off_spans)
         return ev, qr, jobs, order, spans
 
     def fetch_compact(self, sim=0):
-        """(window info, gs_evrow[], gs_qrow[], gs_job_run[], duration-after-network-cost or None, finish order, span pool)"""
+        """(window info, gs_evrow[], gs_qrow[], gs_job_start[], duration-after-network-cost or None, finish order, span pool)"""
         w = self.window(sim)
         n = int(w.n)
         ev = np.empty(max(int(w.ev_rows), 1), dtype=EVROW_DTYPE)
@@ -515,7 +515,7 @@ class Engine:
         jobs = np.empty(max(n, 1), dtype=JOBRUN_DTYPE)
         dur = np.full(max(n, 1), np.nan)
         order = np.empty(max(int(w.finished), 1), dtype=np.int32)
-        spans = np.empty(max(int(w.spans_used), 1), dtype=SPAN_DTYPE)
+        spans = np.empty(max(int(w.spans_used), 1), dtype=CSPAN_DTYPE if self.result_layout(sim).span_bytes == 8 else SPAN_DTYPE)
         self.fetch_compact_into(sim, ev, qr, jobs, dur, order, spans)
         self.sync()
         return (w, ev[:int(w.ev_rows)], qr[:int(w.q_rows)], jobs[:n], (None if n == 0 or np.isnan(dur[0]) else dur[:n]),

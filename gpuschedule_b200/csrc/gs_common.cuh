@@ -36,12 +36,12 @@ struct SimDev {
   const double *model_mb, *iters;
   // ---- results / scratch
   gs_job_rec *rec;            // event-driven policies: full 24-byte record per job
-  int2 *rec2;                 // fifo: {start tick, run length} per job (-1, 0 = never started)
+  int *jstart;                // fifo: start tick per job (-1 = never started)
   double *dur2;               // fifo with network costs: job.duration after the cost was added
   struct JobState2 *jst2;     // fifo: release record of a running job
   int *stack, *fin, *wheel_head;
   long long *wheel_mem;       // per finish-tick bucket: memory share of the jobs ending there
-  gs_span *spans;             // start order; bit 31 of ntasks marks the first span of a job
+  void *spans;                // start order; gs_cspan (8 B) when G <= 32, else gs_span with bit 31 of ntasks = first span of a job
   gs_tick_row *rows;          // event-driven policies: one row per event
   gs_evrow *evrows;           // fifo: one record per tick on which a counter changed
   gs_qrow *qrows;             // fifo: queue statistics beside the records taken with a non-empty queue

@@ -13,7 +13,10 @@
 #ifdef __CUDACC__
 // lanes = simulations per warp: 32 (every lane drives one) or 1 (lane 0 only: no divergence inside the warp,
 // more warps in flight for the same number of replicas).
-__global__ void __launch_bounds__(32) gs_horus_kernel(HSim *sims, int nsims, long long max_ticks, int lanes) {
+#ifndef GS_HORUS_MINBLOCKS
+#define GS_HORUS_MINBLOCKS 12      // resident warps per SM the register budget is cut for (one active lane each when lanes == 1)
+#endif
+__global__ void __launch_bounds__(32, GS_HORUS_MINBLOCKS) gs_horus_kernel(HSim *sims, int nsims, long long max_ticks, int lanes) {
   const int i = lanes == 32 ? blockIdx.x * 32 + threadIdx.x : (threadIdx.x == 0 ? (int)blockIdx.x : nsims);
   if (i >= nsims) return;
   HSim s = sims[i];                 // pointers + scalars in registers / local memory

@@ -45,12 +45,28 @@ __device__ __forceinline__ void stsv2(unsigned a, int2 v) { asm volatile("st.sha
 template <bool G64> struct MaskOps;
 template <> struct MaskOps<true> {
   typedef unsigned long long T;
+  typedef gs_span Span;                                     // 16-byte span records
+  static __device__ __forceinline__ Span make_span(int node, int ntasks, bool first, T mask) {
+    Span sp; sp.node = node; sp.ntasks = ntasks | (first ? (int)0x80000000 : 0); sp.devmask = mask; return sp;
+  }
+  static __device__ __forceinline__ void st_span(Span *p, const Span &v) { __stcs(reinterpret_cast<int4 *>(p), *reinterpret_cast<const int4 *>(&v)); }
+  static __device__ __forceinline__ int span_node(const Span &v) { return v.node; }
+  static __device__ __forceinline__ int span_ntasks(const Span &v) { return v.ntasks & 0x7fffffff; }
+  static __device__ __forceinline__ T span_mask(const Span &v) { return v.devmask; }
   static __device__ __forceinline__ T ld(unsigned a) { return lds64(a); }
   static __device__ __forceinline__ void st(unsigned a, T v) { sts64(a, v); }
   static __device__ __forceinline__ int popc(T v) { return __popcll(v); }
 };
 template <> struct MaskOps<false> {
   typedef unsigned T;
+  typedef gs_cspan Span;                                    // 8-byte span records
+  static __device__ __forceinline__ Span make_span(int node, int ntasks, bool first, T mask) {
+    Span sp; sp.where = (unsigned)node | ((unsigned)(ntasks - 1) << 20) | (first ? 0x80000000u : 0u); sp.devmask = mask; return sp;
+  }
+  static __device__ __forceinline__ void st_span(Span *p, const Span &v) { __stcs(reinterpret_cast<int2 *>(p), *reinterpret_cast<const int2 *>(&v)); }
+  static __device__ __forceinline__ int span_node(const Span &v) { return (int)(v.where & 0xfffffu); }
+  static __device__ __forceinline__ int span_ntasks(const Span &v) { return (int)((v.where >> 20) & 0x3fu) + 1; }
+  static __device__ __forceinline__ T span_mask(const Span &v) { return v.devmask; }
   static __device__ __forceinline__ T ld(unsigned a) { return lds32(a); }
   static __device__ __forceinline__ void st(unsigned a, T v) { sts32(a, v); }
   static __device__ __forceinline__ int popc(T v) { return __popc(v); }
@@ -108,15 +124,16 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
 #define STK_A(i_) (sb_stk + 8u * (unsigned)((i_) & (SCACHE - 1)))
 
   const JobIn *__restrict__ jobs = S.jobs;
-  int2 *rec2 = S.rec2;
+  int *jstart = S.jstart;
   JobState2 *jst = S.jst2;
   int2 *stack = reinterpret_cast<int2 *>(S.stack);
   int *fin = S.fin, *whead = S.wheel_head;
   long long *wmem = S.wheel_mem;
-  gs_span *spans = S.spans;
+  typedef typename MO::Span SpanT;
+  SpanT *spans = reinterpret_cast<SpanT *>(S.spans);
   int4 *rowA = reinterpret_cast<int4 *>(S.evrows), *rowB = reinterpret_cast<int4 *>(S.qrows);
   // everything a replica owns lives in global memory: let the compiler emit ld/st.global instead of generic accesses
-  __builtin_assume(__isGlobal(jobs)); __builtin_assume(__isGlobal(rec2)); __builtin_assume(__isGlobal(jst));
+  __builtin_assume(__isGlobal(jobs)); __builtin_assume(__isGlobal(jstart)); __builtin_assume(__isGlobal(jst));
   __builtin_assume(__isGlobal(stack)); __builtin_assume(__isGlobal(fin)); __builtin_assume(__isGlobal(whead));
   __builtin_assume(__isGlobal(wmem)); __builtin_assume(__isGlobal(spans)); __builtin_assume(__isGlobal(rowA));
   __builtin_assume(__isGlobal(rowB));
@@ -331,10 +348,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
           const unsigned kv = lds32(KK_A(found));
           MO::st(BUSY_A(found), bz | take);
           sts32(KK_A(found), (kv - (unsigned)hg - ((unsigned)htasks << 16)) | 0x100u);
-          {
-            gs_span sp; sp.node = found; sp.ntasks = htasks | (int)0x80000000; sp.devmask = take;
-            __stcs(reinterpret_cast<int4 *>(&spans[span_first]), *reinterpret_cast<const int4 *>(&sp));
-          }
+          MO::st_span(&spans[span_first], MO::make_span(found, htasks, true, take));
           mask0 = take;
           where = found | ((htasks - 1) << 20);
           ever += (kv & 0x100u) ? 0 : 1;
@@ -381,8 +395,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
               sts32(KK_A(nd), (kv - (unsigned)(take * hgpc) - ((unsigned)take << 16)) | 0x100u);
               fresh = !(kv & 0x100u);
               const int slot = nspans + __popc(tb & ((1u << lane) - 1u));
-              gs_span sp; sp.node = nd; sp.ntasks = take | (slot == 0 ? (int)0x80000000 : 0); sp.devmask = tk;
-              __stcs(reinterpret_cast<int4 *>(&spans[span_first + slot]), *reinterpret_cast<const int4 *>(&sp));
+              MO::st_span(&spans[span_first + slot], MO::make_span(nd, take, slot == 0, tk));
             }
             ever += __popc(__ballot_sync(FULL, fresh));
             if (tb) last_node = base + 31 - __clz(tb);
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         whead[bk] = j;                                   // warp-uniform stores (same address, same value from every lane)
         wmem[bk] = wm + hmemc;
         *reinterpret_cast<int4 *>(&jst[j]) = *reinterpret_cast<const int4 *>(&js);
-        __stcs(&rec2[j], make_int2(delta, need));
+        __stcs(&jstart[j], delta);
         top -= 1;
         sum_arr -= harr;
         running += 1;
@@ -462,9 +475,11 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         } else {
           const int first = js.where & 0x7fffffff, scnt = (int)(unsigned)(js.mask0 & 0xffffffffull);
           for (int i = lane; i < scnt; i += 32) {
-            const gs_span sp = spans[first + i];
-            MO::st(BUSY_A(sp.node), MO::ld(BUSY_A(sp.node)) & ~(MaskT)sp.devmask);
-            sts32(KK_A(sp.node), lds32(KK_A(sp.node)) + (unsigned)__popcll(sp.devmask) + ((unsigned)(sp.ntasks & 0x7fffffff) << 16));
+            const SpanT sp = spans[first + i];
+            const int snd = MO::span_node(sp);
+            const MaskT smk = MO::span_mask(sp);
+            MO::st(BUSY_A(snd), MO::ld(BUSY_A(snd)) & ~smk);
+            sts32(KK_A(snd), lds32(KK_A(snd)) + (unsigned)MO::popc(smk) + ((unsigned)MO::span_ntasks(sp) << 16));
           }
           busy_gpus -= (int)(unsigned)(js.mask0 >> 32);
           __syncwarp();          // lanes updated different nodes
@@ -527,7 +542,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
   if (hvalid) { if (lane == 0) stack[scount] = make_int2(hjob, harr); scount += 1; }
   __syncwarp();
   // jobs still queued have not started: their result record says so (start = -1), whatever ran before
-  for (int i = lane; i < scount; i += 32) rec2[stack[i].x] = make_int2(-1, 0);
+  for (int i = lane; i < scount; i += 32) jstart[stack[i].x] = -1;
   {
     const int K = S.K;
     for (int i = lane; i < M; i += 32) {
@@ -579,8 +594,8 @@ __global__ void gs_expand_rows_kernel(const SimDev *sims, int sim, int M, int G,
   }
 }
 
-// Legacy gs_job_rec view of the compact per-job result {start, run length}: fifo never preempts, so
-// end = start + run length, jct = run length, preempt (migration_count) = 1 (quirk Q12).
+// Legacy gs_job_rec view of the compact per-job result (the start tick): fifo never preempts, so the run length is
+// max(1, ceil(job.duration)) (quirk Q11), end = start + run length, jct = run length, preempt (migration_count) = 1 (Q12).
 __global__ void gs_expand_jobs_kernel(const SimDev *sims, int sim, gs_job_rec *__restrict__ out) {
   const SimDev &S = sims[sim];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -588,10 +603,12 @@ __global__ void gs_expand_jobs_kernel(const SimDev *sims, int sim, gs_job_rec *_
   gs_job_rec r; r.start = -1; r.end = -1; r.jct = 0; r.preempt = 0;
   r.duration = S.jobs[j].dur;
   if (j < S.p) {
-    const int2 v = S.rec2[j];
-    if (v.x >= 0) {
-      r.start = v.x; r.end = v.x + v.y; r.jct = v.y; r.preempt = 1;
+    const int st = S.jstart[j];
+    if (st >= 0) {
+      const double dur_in = r.duration;
       if (S.netcost) r.duration = S.dur2[j];
+      const int need = need_of(r.duration > dur_in ? r.duration : dur_in);      // Job.get_duration (job.py:206-210)
+      r.start = st; r.end = st + need; r.jct = need; r.preempt = 1;
     }
   }
   out[j] = r;

@@ -17,8 +17,8 @@
 //     finishes are jumped over; every other tick leaves one 32-byte record of
 //     integer aggregates (+ one for the queue while it is non-empty) from which
 //     the 64-byte gs_tick_row of EVERY tick is rebuilt on demand; the job table
-//     is streamed once from HBM, results are written once (8-byte gs_job_run +
-//     16-byte gs_span per (job,node) + finish order).
+//     is streamed once from HBM, results are written once (4-byte start tick per job +
+//     8-byte gs_cspan per (job,node) + finish order).
 //   * thousands of replicas run per launch (one warp each, 148 SMs x 32
 //     warps); a single replica is latency bound by construction.
 //
@@ -86,6 +86,7 @@ struct gs_engine {
   int device = 0, nsims = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEvent_t e_wait = nullptr;   // blocking-sync event: in asynchronous mode the driving thread sleeps while it waits
   std::vector<SimHost> sims;
   SimDev *d_sims = nullptr;
   void *h_stage = nullptr;
@@ -127,6 +128,14 @@ static int fail(gs_handle h, int code, const std::string &msg) {
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Wait for the handle's stream.  Asynchronous mode is what many host threads use side by side (one handle each): there the
+// waiting thread sleeps on a blocking-sync event instead of spinning, which leaves the cores to the threads that work.
+static cudaError_t wait_stream(gs_handle h) {
+  if (!h->async) return cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaEventRecord(h->e_wait, h->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(h->e_wait);
+}
+
 extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
 extern "C" const char *gs_build_tag(void) {
 #ifdef __CUDACC__
@@ -158,6 +167,7 @@ extern "C" int gs_create(int device, int nsims, gs_handle *out) {
   cudaError_t e2 = cudaEventCreate(&h->e0);
   cudaError_t e3 = cudaEventCreate(&h->e1);
   cudaError_t e4 = cudaMalloc(&h->d_sims, sizeof(SimDev) * (size_t)nsims);
+  if (cudaEventCreateWithFlags(&h->e_wait, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) e4 = cudaErrorUnknown;
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
     delete h;
     return fail(nullptr, GS_ERR_CUDA, "gs_create: stream/event/alloc failed");
@@ -180,6 +190,7 @@ extern "C" void gs_destroy(gs_handle h) {
   if (h->comm_buf) cudaFree(h->comm_buf);
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
+  if (h->e_wait) cudaEventDestroy(h->e_wait);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -402,10 +413,10 @@ static SimLayout layout_sim(gs_handle h, const SimHost &s, int64_t rows_cap) {
   } else {
     L.o_ev = take(sizeof(gs_evrow) * (size_t)rows_cap);
     L.o_q = take(sizeof(gs_qrow) * (size_t)L.qrows_cap);
-    L.o_rec2 = take(8 * N);
+    L.o_rec2 = take(4 * N);
     if (net) L.o_dur2 = take(8 * N);
     L.o_fin = take(4 * N);
-    L.o_spans = take(sizeof(gs_span) * (size_t)s.span_cap);
+    L.o_spans = take((c.num_gpu_p_node > 32 ? sizeof(gs_span) : sizeof(gs_cspan)) * (size_t)s.span_cap);
     L.out_bytes = total;
     L.o_jst = take(sizeof(JobState2) * N);
     L.o_stack = take(8 * (N + 1));
@@ -438,15 +449,15 @@ static int bind_sim(gs_handle h, SimHost &s, const SimLayout &L, unsigned char *
   D.fit_limit = D.cap_bytes - ((long long)500 << 20);      // cap - mem > 500 MiB  (device.py:75)
   D.bandwidth = c.bandwidth; D.latency = c.internode_latency;
   D.fin = (int *)(d + o_fin);
-  D.rec = nullptr; D.rows = nullptr; D.rec2 = nullptr; D.dur2 = nullptr; D.jst2 = nullptr; D.stack = nullptr;
+  D.rec = nullptr; D.rows = nullptr; D.jstart = nullptr; D.dur2 = nullptr; D.jst2 = nullptr; D.stack = nullptr;
   D.wheel_head = nullptr; D.wheel_mem = nullptr; D.spans = nullptr; D.evrows = nullptr; D.qrows = nullptr; D.nbusy = nullptr; D.nk = nullptr;
   if (evd) {
     D.rec = (gs_job_rec *)(d + o_rec); D.rows = (gs_tick_row *)(d + o_rows);
   } else {
-    D.rec2 = (int2 *)(d + o_rec2); D.dur2 = net ? (double *)(d + o_dur2) : nullptr;
+    D.jstart = (int *)(d + o_rec2); D.dur2 = net ? (double *)(d + o_dur2) : nullptr;
     D.jst2 = (JobState2 *)(d + o_jst); D.stack = (int *)(d + o_stack);
     D.wheel_head = (int *)(d + o_wh); D.wheel_mem = (long long *)(d + o_wm);
-    D.spans = (gs_span *)(d + o_spans); D.evrows = (gs_evrow *)(d + o_ev); D.qrows = (gs_qrow *)(d + o_q);
+    D.spans = (void *)(d + o_spans); D.evrows = (gs_evrow *)(d + o_ev); D.qrows = (gs_qrow *)(d + o_q);
     D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
   }
   D.span_cap = s.span_cap; D.rows_cap = rows_cap; D.qrows_cap = qrows_cap;
@@ -582,7 +593,7 @@ extern "C" int gs_run(gs_handle h, int64_t max_ticks, int64_t rows_cap) {
   }
   CU(cudaEventRecord(h->e1, h->stream));
   CU(cudaMemcpyAsync(h->h_back.data(), h->d_sims, sizeof(SimDev) * (size_t)h->nsims, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  CU(wait_stream(h));
   float ms = 0; cudaEventElapsedTime(&ms, h->e0, h->e1);
   h->kernel_ms += ms;
   if (h->comm_n > 1 && h->h_back[0].comm_n > 1) h->comm_epoch = h->h_back[0].comm_epoch;
@@ -688,7 +699,7 @@ extern "C" int gs_comm_stats(gs_handle h, int64_t *exchanges, double *mean_us) {
 extern "C" int gs_sync(gs_handle h) {
   if (!h) return GS_ERR_ARG;
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));
+  CU(wait_stream(h));
   return GS_OK;
 }
 
@@ -705,22 +716,23 @@ extern "C" int gs_set_queue_rows_cap(gs_handle h, int64_t qrows_cap) {
   return GS_OK;
 }
 
-extern "C" int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_run *jobs_out,
-                                double *duration_out, int32_t *finish_order_out, gs_span *spans_out) {
+extern "C" int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_start *jobs_out,
+                                double *duration_out, int32_t *finish_order_out, void *spans_out) {
   if (!h) return GS_ERR_ARG;
   if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_compact: sim index out of range");
   SimHost &s = h->sims[(size_t)sim];
   if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_compact: nothing has run yet");
   if (s.pol.schedule != GS_SCHED_FIFO) return fail(h, GS_ERR_ARG, "gs_fetch_compact: the compact records are the fifo engine's output");
-  static_assert(sizeof(gs_evrow) == 32 && sizeof(gs_qrow) == 32 && sizeof(gs_job_run) == 8, "compact record layout");
+  static_assert(sizeof(gs_evrow) == 32 && sizeof(gs_qrow) == 32 && sizeof(gs_job_start) == 4 && sizeof(gs_cspan) == 8, "compact record layout");
+  const size_t span_bytes = s.cl.num_gpu_p_node > 32 ? sizeof(gs_span) : sizeof(gs_cspan);
   const SimDev &D = s.dev;
   CU(cudaSetDevice(h->device));
   if (ev_out && D.nev > 0) CU(cudaMemcpyAsync(ev_out, D.evrows, sizeof(gs_evrow) * (size_t)D.nev, cudaMemcpyDeviceToHost, h->stream));
   if (q_out && D.nq > 0) CU(cudaMemcpyAsync(q_out, D.qrows, sizeof(gs_qrow) * (size_t)D.nq, cudaMemcpyDeviceToHost, h->stream));
-  if (jobs_out && s.n > 0) CU(cudaMemcpyAsync(jobs_out, D.rec2, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
+  if (jobs_out && s.n > 0) CU(cudaMemcpyAsync(jobs_out, D.jstart, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
   if (duration_out && D.dur2 && s.n > 0) CU(cudaMemcpyAsync(duration_out, D.dur2, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
   if (finish_order_out && D.finished > 0) CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream));
-  if (spans_out && D.span_used > 0) CU(cudaMemcpyAsync(spans_out, D.spans, sizeof(gs_span) * (size_t)D.span_used, cudaMemcpyDeviceToHost, h->stream));
+  if (spans_out && D.span_used > 0) CU(cudaMemcpyAsync(spans_out, D.spans, span_bytes * (size_t)D.span_used, cudaMemcpyDeviceToHost, h->stream));
   return GS_OK;
 }
 
@@ -750,7 +762,7 @@ extern "C" int gs_load_traces_packed(gs_handle h, const gs_jobin *jobs, size_t p
   }
   const size_t stride = align_up(sizeof(JobIn) * (size_t)nmax, 512);
   const size_t need = stride * (size_t)h->nsims;
-  CU(cudaStreamSynchronize(h->stream));                 // earlier work may still read the old traces
+  CU(wait_stream(h));                                   // earlier work may still read the old traces
   if (h->tarena_bytes < need) {
     if (h->tarena) cudaFree(h->tarena);
     h->tarena = nullptr; h->tarena_bytes = 0;
@@ -810,6 +822,7 @@ extern "C" int gs_result_layout(gs_handle h, int sim, gs_result_layout_t *out) {
   out->off_duration = s.cl.enable_network_costs ? (int64_t)L.o_dur2 : -1;
   out->off_finish_order = (int64_t)L.o_fin; out->off_spans = (int64_t)L.o_spans;
   out->cap_ev = L.rows_cap; out->cap_q = L.qrows_cap; out->cap_spans = s.span_cap; out->n = s.n;
+  out->span_bytes = s.cl.num_gpu_p_node > 32 ? (int64_t)sizeof(gs_span) : (int64_t)sizeof(gs_cspan);
   return GS_OK;
 }
 
@@ -935,15 +948,28 @@ extern "C" int gs_fetch_spans(gs_handle h, int sim, int64_t *span_off_out, gs_sp
     return GS_OK;
   }
   std::vector<gs_span> pool((size_t)used);
-  std::vector<int2> r2((size_t)n);
-  int rc = timed_d2h(h, pool.data(), D.spans, sizeof(gs_span) * (size_t)used);
-  if (rc) return rc;
-  rc = timed_d2h(h, r2.data(), D.rec2, 8 * (size_t)n);
+  std::vector<int32_t> r2((size_t)n);
+  int rc;
+  if (s.cl.num_gpu_p_node > 32) {
+    rc = timed_d2h(h, pool.data(), D.spans, sizeof(gs_span) * (size_t)used);
+    if (rc) return rc;
+  } else {                  // compact 8-byte records on the device: widen them here
+    std::vector<gs_cspan> cp((size_t)used);
+    rc = timed_d2h(h, cp.data(), D.spans, sizeof(gs_cspan) * (size_t)used);
+    if (rc) return rc;
+    for (int64_t i = 0; i < used; ++i) {
+      const uint32_t w = cp[(size_t)i].where;
+      gs_span sp; sp.node = (int32_t)GS_CSPAN_NODE(w); sp.devmask = cp[(size_t)i].devmask;
+      sp.ntasks = (int32_t)(GS_CSPAN_NTASKS(w) | (GS_CSPAN_FIRST(w) ? GS_SPAN_FIRST : 0u));
+      pool[(size_t)i] = sp;
+    }
+  }
+  rc = timed_d2h(h, r2.data(), D.jstart, 4 * (size_t)n);
   if (rc) return rc;
   // jobs in start order: bucket by start tick (unique, < ticks)
   std::vector<int32_t> by_tick((size_t)D.ticks + 1, -1);
   const int64_t admitted = D.p;
-  for (int64_t j = 0; j < admitted; ++j) if (r2[(size_t)j].x >= 0 && r2[(size_t)j].x <= D.ticks) by_tick[(size_t)r2[(size_t)j].x] = (int32_t)j;
+  for (int64_t j = 0; j < admitted; ++j) if (r2[(size_t)j] >= 0 && r2[(size_t)j] <= D.ticks) by_tick[(size_t)r2[(size_t)j]] = (int32_t)j;
   std::vector<int32_t> order; order.reserve((size_t)n);
   for (int64_t t = 0; t <= D.ticks; ++t) if (by_tick[(size_t)t] >= 0) order.push_back(by_tick[(size_t)t]);
   std::vector<int64_t> first((size_t)n, 0), cnt((size_t)n, 0);

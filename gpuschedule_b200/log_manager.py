@@ -33,13 +33,14 @@ JOB_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"),
                       ("preempt", "<i4"), ("duration", "<f8")])
 SPAN_DTYPE = np.dtype([("node", "<i4"), ("ntasks", "<i4"), ("devmask", "<u8")])
 assert ROW_DTYPE.itemsize == 64 and JOB_DTYPE.itemsize == 24 and SPAN_DTYPE.itemsize == 16
-# compact records of the fifo engine: gs_evrow / gs_qrow / gs_job_run
+# compact records of the fifo engine: gs_evrow / gs_qrow / gs_job_start / gs_cspan
 EVROW_DTYPE = np.dtype([("now", "<i4"), ("queued", "<i4"), ("finished", "<i4"), ("busy_running", "<u4"),
                         ("mem_busy_bytes", "<i8"), ("busy_nodes", "<i4"), ("qrow", "<i4")])
 QROW_DTYPE = np.dtype([("arrive_sum", "<i8"), ("oldest_arrive", "<i4"), ("med_lo_arrive", "<i4"),
                        ("med_hi_arrive", "<i4"), ("reserved", "<i4", (3,))])
-JOBRUN_DTYPE = np.dtype([("start", "<i4"), ("run_ticks", "<i4")])
-assert EVROW_DTYPE.itemsize == 32 and QROW_DTYPE.itemsize == 32 and JOBRUN_DTYPE.itemsize == 8
+JOBRUN_DTYPE = np.dtype([("start", "<i4")])                     # gs_job_start: the start tick, -1 = never started
+CSPAN_DTYPE = np.dtype([("where", "<u4"), ("devmask", "<u4")])  # gs_cspan (clusters with at most 32 GPUs per node)
+assert EVROW_DTYPE.itemsize == 32 and QROW_DTYPE.itemsize == 32 and JOBRUN_DTYPE.itemsize == 4 and CSPAN_DTYPE.itemsize == 8
 SPAN_FIRST = 0x80000000
 
 
@@ -79,24 +80,41 @@ def expand_rows(ev, qr, row_first, ticks, n_nodes, gpus_per_node):
 
 
 def expand_jobs(job_run, admitted, duration_in, duration_out=None):
-    """gs_job_rec view of the compact {start, run_ticks} records (fifo never preempts: end = start + run,
-    jct = run, preempt = migration_count = 1, quirk Q12; never started: -1, -1, 0, 0)."""
+    """gs_job_rec view of the compact per-job result (the start tick).  fifo never preempts: the run length is
+    max(1, ceil(Job.get_duration())) ticks (quirk Q11; job.py:206-210), end = start + run, jct = run,
+    preempt = migration_count = 1 (Q12); never started: -1, -1, 0, 0."""
     n = len(job_run)
     recs = np.zeros(n, dtype=JOB_DTYPE)
     started = (np.arange(n) < admitted) & (job_run["start"] >= 0)
-    recs["start"] = np.where(started, job_run["start"], -1)
-    recs["end"] = np.where(started, job_run["start"] + job_run["run_ticks"], -1)
-    recs["jct"] = np.where(started, job_run["run_ticks"], 0)
-    recs["preempt"] = started.astype(np.int32)
-    recs["duration"] = duration_in
+    dur = np.asarray(duration_in, dtype=np.float64)
     if duration_out is not None:
-        recs["duration"] = np.where(started, duration_out, duration_in)
+        dur = np.where(started, duration_out, dur)
+    eff = np.maximum(dur, duration_in)
+    run = np.where(np.ceil(eff) < 1.0, 1, np.minimum(np.ceil(eff), 2147483647.0)).astype(np.int64).astype(np.int32)
+    recs["start"] = np.where(started, job_run["start"], -1)
+    recs["end"] = np.where(started, job_run["start"] + run, -1)
+    recs["jct"] = np.where(started, run, 0)
+    recs["preempt"] = started.astype(np.int32)
+    recs["duration"] = dur
     return recs
+
+
+def widen_spans(pool):
+    """gs_cspan records -> gs_span records (the first-of-job flag moves into bit 31 of ntasks)"""
+    if pool.dtype == SPAN_DTYPE:
+        return pool
+    w = pool["where"]
+    out = np.zeros(len(pool), dtype=SPAN_DTYPE)
+    out["node"] = (w & 0xfffff).astype(np.int32)
+    out["ntasks"] = ((((w >> 20) & 0x3f) + 1) | (w & np.uint32(SPAN_FIRST))).astype(np.uint32).view(np.int32)
+    out["devmask"] = pool["devmask"].astype(np.uint64)
+    return out
 
 
 def group_spans(job_run, admitted, pool):
     """(span_off[n+1], spans grouped by job) from the start-ordered span pool of gs_fetch_compact: the k-th
     record flagged SPAN_FIRST opens the job with the k-th smallest start tick (start ticks are unique)."""
+    pool = widen_spans(pool)
     n = len(job_run)
     started = np.nonzero((np.arange(n) < admitted) & (job_run["start"] >= 0))[0]
     order = started[np.argsort(job_run["start"][started], kind="stable")]

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 2
+#define GS_ABI_VERSION 3
 #define GS_MAX_QUEUES 8
 #define GS_MAX_GPUS_PER_NODE 64
 #define GS_MAX_RANKS 8          /* GPUs of one box that may share one simulation (gs_comm_init) */
@@ -130,12 +130,21 @@ typedef struct gs_qrow {
   int32_t reserved[3];
 } gs_qrow;
 
-/* Compact per-job result of the fifo engine: fifo never preempts, so end = start + run_ticks,
- * jct = run_ticks, preempt = 1 (quirk Q12); start = -1: the job never started.  8 bytes.                */
-typedef struct gs_job_run {
-  int32_t start;
-  int32_t run_ticks;
-} gs_job_run;
+/* Compact per-job result of the fifo engine: the start tick (-1: the job never started).  fifo never preempts,
+ * so the rest of job.csv follows from the trace: run length = max(1, ceil(job.duration)) ticks (quirk Q11; with
+ * network costs job.duration is the value gs_fetch_compact returns in duration_out), end = start + run length,
+ * jct = run length, preempt = 1 (quirk Q12).  4 bytes per job.                                          */
+typedef int32_t gs_job_start;
+
+/* Compact (job, node) record of the fifo engine for clusters with at most 32 GPUs per node (every BASELINE
+ * cluster); wider nodes keep the 16-byte gs_span with GS_SPAN_FIRST in ntasks.  8 bytes.                  */
+typedef struct gs_cspan {
+  uint32_t where;           /* node (bits 0-19) | (ntasks - 1) << 20 | first record of a job << 31           */
+  uint32_t devmask;         /* devices of that node held by the job                                          */
+} gs_cspan;
+#define GS_CSPAN_NODE(w) ((w) & 0xfffffu)
+#define GS_CSPAN_NTASKS(w) ((((w) >> 20) & 0x3fu) + 1u)
+#define GS_CSPAN_FIRST(w) ((w) >> 31)
 
 /* What the last gs_run window of one replica holds (sizes for gs_fetch_compact).                        */
 typedef struct gs_window_info {
@@ -143,7 +152,7 @@ typedef struct gs_window_info {
   int64_t ticks;            /* rows produced so far (the window is [row_first, ticks))                 */
   int64_t ev_rows, q_rows;  /* records of the window                                                   */
   int64_t spans_used;       /* (job, node) records so far, start order                                 */
-  int64_t admitted;         /* trace rows consumed so far: gs_job_run is defined for jobs below this   */
+  int64_t admitted;         /* trace rows consumed so far: gs_job_start is defined for jobs below this  */
   int64_t finished;
   int64_t n;
 } gs_window_info;
@@ -271,11 +280,12 @@ int gs_fetch_all(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row
  * non-NULL output on the handle's stream and returns; gs_sync waits for them.  Buffers from
  * gs_host_alloc make the copies true DMA.  Sizes: ev_out ev_rows, q_out q_rows, jobs_out n,
  * duration_out n (only with network costs, else left untouched), finish_order_out finished,
- * spans_out spans_used (start order, GS_SPAN_FIRST marks job boundaries; jobs in start order =
- * jobs_out sorted by start, start ticks are unique -- one start per tick, schedule.py:188-190).      */
+ * spans_out spans_used records of gs_result_layout's span_bytes each (8: gs_cspan, 16: gs_span; start order,
+ * the first-of-job flag marks job boundaries; jobs in start order = jobs_out sorted by start, start ticks are
+ * unique -- one start per tick, schedule.py:188-190).                                                   */
 int gs_window(gs_handle h, int sim, gs_window_info *out);
-int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_run *jobs_out,
-                     double *duration_out, int32_t *finish_order_out, gs_span *spans_out);
+int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_start *jobs_out,
+                     double *duration_out, int32_t *finish_order_out, void *spans_out /* gs_cspan[] or gs_span[], see gs_result_layout */);
 int gs_sync(gs_handle h);
 /* The same, for many replicas with ONE copy each way (what bench.py's end-to-end path uses).  The replicas of a
  * handle keep their results in blocks of one layout, side by side on the device:
@@ -289,6 +299,7 @@ typedef struct gs_result_layout_t {
   int64_t block_bytes;
   int64_t off_ev, off_q, off_jobs, off_duration /* -1 without network costs */, off_finish_order, off_spans;
   int64_t cap_ev, cap_q, cap_spans, n;
+  int64_t span_bytes;       /* 8: gs_cspan records (at most 32 GPUs per node), 16: gs_span records               */
 } gs_result_layout_t;
 int gs_load_traces_packed(gs_handle h, const gs_jobin *jobs, size_t pitch_bytes, const int64_t *n_each);
 int gs_result_layout(gs_handle h, int sim, gs_result_layout_t *out);

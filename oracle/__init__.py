@@ -345,7 +345,9 @@ class Tight2:
                 break
         r = OracleResult()
         n = self.n
-        jobs = np.ctypeslib.as_array(C.cast(lib().tight2_jobs(self.h), C.POINTER(C.c_int32)), shape=(max(n, 1) * 2,)).view(self._dt[2])[:n].copy()
+        both = np.ctypeslib.as_array(C.cast(lib().tight2_jobs(self.h), C.POINTER(C.c_int32)), shape=(max(n, 1) * 2,)).reshape(-1, 2)[:n]
+        jobs = np.zeros(n, dtype=self._dt[2])                 # the engine's compact per-job result: the start tick only
+        jobs["start"] = both[:, 0]
         r.ticks = int(w.ticks)
         r.rows = np.concatenate(parts) if parts else np.zeros(0, dtype=ROW_DTYPE)
         r.recs = lm.expand_jobs(jobs, int(w.admitted), self.cols[3])
@@ -353,6 +355,13 @@ class Tight2:
         r.finish_order = np.ctypeslib.as_array(C.cast(lib().tight2_finish_order(self.h), C.POINTER(C.c_int32)), shape=(max(nf, 1),))[:nf].copy()
         ns = int(w.spans_used)
         pool = np.ctypeslib.as_array(C.cast(lib().tight2_spans(self.h), C.POINTER(C.c_uint8)), shape=(max(ns, 1) * 16,)).view(SPAN_DTYPE)[:ns].copy()
+        if g <= 32:                                           # the engine's 8-byte records for such clusters
+            from gpuschedule_b200.log_manager import CSPAN_DTYPE, SPAN_FIRST
+            c8 = np.zeros(ns, dtype=CSPAN_DTYPE)
+            nt = pool["ntasks"].view(np.uint32)
+            c8["where"] = pool["node"].astype(np.uint32) | (((nt & 0x7fffffff) - 1) << 20) | (nt & np.uint32(SPAN_FIRST))
+            c8["devmask"] = pool["devmask"].astype(np.uint32)
+            pool = c8
         r.span_off, r.spans = lm.group_spans(jobs, int(w.admitted), pool)
         r.events, r.evals, r.job_run, r.pool = events, evals, jobs, pool
         return r

@@ -6,7 +6,7 @@
  * starts or finishes are jumped over, the queue head waits in registers, the timing wheel is pushed at the
  * front and released newest-first (finish order repaired afterwards), a head that did not fit is not tried
  * again until something could change the answer, and the output is the compact record stream of
- * include/gsched.h (gs_evrow / gs_qrow / gs_job_run / start-ordered spans) in resumable windows.
+ * include/gsched.h (gs_evrow / gs_qrow / start ticks / start-ordered spans) in resumable windows.
  *
  * Two uses: (1) tests/test_tight2_cpu.py checks it -- through the package's own record decoders --
  * against the pinned oracle (oracle/gsched_oracle.c) on the reference fixtures and on random cases, which
@@ -21,6 +21,7 @@
 #include "../include/gsched.h"
 
 #define T2_INF 0x7fffffff
+typedef struct { int32_t start, run_ticks; } t2_job_run;   /* internal; the engine's compact result is the start tick alone */
 
 typedef struct { int32_t next, where; uint64_t mask0; } t2_state;
 
@@ -35,7 +36,7 @@ typedef struct tight2 {
   int32_t *whead; int64_t *wmem;
   t2_state *st;
   int32_t *stack_job, *stack_arr;
-  gs_job_run *rec2;
+  t2_job_run *rec2;
   int32_t *fin;
   gs_span *spans; int64_t span_cap;
   /* loop state */
@@ -99,7 +100,7 @@ tight2 *tight2_create(const gs_cluster *c, int64_t n, const int32_t *arrive, con
   t->whead = (int32_t *)malloc(4 * (size_t)W); t->wmem = (int64_t *)malloc(8 * (size_t)W);
   t->st = (t2_state *)malloc(sizeof(t2_state) * N);
   t->stack_job = (int32_t *)malloc(4 * (N + 1)); t->stack_arr = (int32_t *)malloc(4 * (N + 1));
-  t->rec2 = (gs_job_run *)malloc(sizeof(gs_job_run) * N);
+  t->rec2 = (t2_job_run *)malloc(sizeof(t2_job_run) * N);
   t->fin = (int32_t *)malloc(4 * N);
   t->span_cap = span_cap > 0 ? span_cap : (worst > 0 ? worst : 1);
   t->spans = (gs_span *)malloc(sizeof(gs_span) * (size_t)t->span_cap);
@@ -315,6 +316,6 @@ void tight2_info(const tight2 *t, gs_window_info *w, int64_t nev, int64_t nq, in
   *events = t->p + 2 * (int64_t)t->finished + t->running; *evals = t->evals; *done = t->done;
 }
 
-const gs_job_run *tight2_jobs(const tight2 *t) { return t->rec2; }
+const t2_job_run *tight2_jobs(const tight2 *t) { return t->rec2; }
 const int32_t *tight2_finish_order(const tight2 *t) { return t->fin; }
 const gs_span *tight2_spans(const tight2 *t) { return t->spans; }

@@ -433,7 +433,8 @@ def test_compact_records_decode_to_the_same_rows():
     from gpuschedule_b200 import capi, ingest, tracegen
     from gpuschedule_b200 import log_manager as lm
     for seed, rate, ckw in [(31, 0.5, dict(num_switch=4, num_node_p_switch=32)), (32, 2.5, dict(num_switch=1, num_node_p_switch=6)),
-                            (33, 1.0, dict(num_switch=16, num_node_p_switch=64))]:
+                            (33, 1.0, dict(num_switch=16, num_node_p_switch=64)),
+                            (34, 1.5, dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=48, num_cpu_p_node=800, mem_p_node=4000))]:   # > 32 GPUs per node: 16-byte spans
         cluster = capi.make_cluster(**ckw)
         m, g = cluster.num_switch * cluster.num_node_p_switch, cluster.num_gpu_p_node
         table = ingest.table_from_columns(tracegen.synth_columns(2500, seed=seed, rate=rate))
@@ -470,7 +471,7 @@ def test_async_load_and_fetch_from_pinned_buffers():
     import oracle
     from gpuschedule_b200 import capi, ingest, tracegen
     from gpuschedule_b200 import log_manager as lm
-    from gpuschedule_b200.log_manager import EVROW_DTYPE, JOBRUN_DTYPE, QROW_DTYPE, SPAN_DTYPE
+    from gpuschedule_b200.log_manager import CSPAN_DTYPE, EVROW_DTYPE, JOBRUN_DTYPE, QROW_DTYPE
     cluster = capi.make_cluster(num_switch=2, num_node_p_switch=12)
     tables = [ingest.table_from_columns(tracegen.synth_columns(900 + 10 * i, seed=60 + i, rate=0.8)) for i in range(12)]
     refs = [oracle.run_fifo(cluster, t) for t in tables]
@@ -489,12 +490,13 @@ def test_async_load_and_fetch_from_pinned_buffers():
             wins = [eng.window(i) for i in range(len(tables))]
             outs = []
             for i, w in enumerate(wins):
-                pb = capi.PinnedBuffer(32 * (w.ev_rows + w.q_rows) + 8 * w.n + 4 * w.finished + 16 * w.spans_used + 64)
+                assert eng.result_layout(i).span_bytes == 8          # 8 GPUs per node: the 8-byte span records
+                pb = capi.PinnedBuffer(32 * (w.ev_rows + w.q_rows) + 4 * w.n + 4 * w.finished + 8 * w.spans_used + 64)
                 o = 0
                 ev = pb.view(EVROW_DTYPE, w.ev_rows, o); o += 32 * w.ev_rows
                 qr = pb.view(QROW_DTYPE, w.q_rows, o); o += 32 * w.q_rows
-                jobs = pb.view(JOBRUN_DTYPE, w.n, o); o += 8 * w.n
-                sp = pb.view(SPAN_DTYPE, w.spans_used, o); o += 16 * w.spans_used
+                jobs = pb.view(JOBRUN_DTYPE, w.n, o); o += 4 * w.n
+                sp = pb.view(CSPAN_DTYPE, w.spans_used, o); o += 8 * w.spans_used
                 order = pb.view(np.int32, w.finished, o)
                 eng.fetch_compact_into(i, ev, qr, jobs, None, order, sp)
                 outs.append((pb, ev, qr, jobs, order, sp))
