@@ -985,7 +985,7 @@ def main():
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS), help="c1 = the BASELINE metric's configuration; c5 = 16x64x8, 1M-job traces")
     ap.add_argument("--jobs", type=int, default=None, help="jobs per trace (default: the configuration's)")
     ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU, one warp each (default c1: 4144 = 148 SMs x 28 resident warps)")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--e2e-threads", type=int, default=16, help="host threads (one engine handle each) in the e2e run")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-threads", type=int, default=0)

@@ -9,7 +9,8 @@
 //   * one 32-byte gs_evrow per tick on which a counter changed (plus the first tick of a launch), and
 //   * one 32-byte gs_qrow beside it while the queue is non-empty (arrival-tick sum, oldest arrival,
 //     the two middle arrivals -- the pending statistics of jobs_manager.py:72-87 are `now - arrival`),
-// from which gs_expand_rows_kernel (or the host) rebuilds every gs_tick_row bit for bit.
+// from which gs_expand_rows_kernel (or the host) rebuilds every gs_tick_row bit for bit.  Per job it writes the start
+// tick (4 bytes; the rest of job.csv follows from the trace) and per (job, node) an 8-byte gs_cspan.
 //
 // Per-tick path, in the order of the reference loop:
 //   A  admit arrivals  (jobs_manager.py:228-241; head insert, quirk Q2): a 32-record register window of
