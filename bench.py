@@ -372,7 +372,7 @@ def ours(args):
     # SURVEY 8(d)'s: job table in + job record out (56 B/job), one 16-B span per (job, node), one 64-B statistics
     # row per simulated tick -- the information the launch produces, whatever encoding the engine writes it in.
     alg_bytes = R * n * 56 + spans_rank * 16 + ticks_rank * 64
-    written = R * n * (32 + 4 + 4) + spans_rank * 8 + recs_rank * 32
+    written = R * n * (32 + 4 + 4) + spans_rank * 8 + recs_rank * 24
     peak, peak_src = peaks()
     ach = alg_bytes / (dev_ms / args.steps / 1e3) / 1e9
     traffic, traffic_src = None, None
@@ -457,8 +457,8 @@ def ours(args):
             valid = chk = ev = 0
             for i in range(len(self.reps)):
                 self.e.lib.gs_window(self.e.h, i, C.byref(win))
-                evb, qrb, jb, od, sp = capi.Engine.result_views(self.out, self.pitch, i, self.lay, win)
-                valid += 32 * (win.ev_rows + win.q_rows) + 4 * n + 4 * win.finished + int(self.lay.span_bytes) * win.spans_used
+                evb, qrb, neb, jb, od, sp = capi.Engine.result_views(self.out, self.pitch, i, self.lay, win)
+                valid += 24 * (win.ev_rows + win.q_rows) + 8 * win.node_events + 4 * n + 4 * win.finished + int(self.lay.span_bytes) * win.spans_used
                 chk += int(evb[-1]["finished"]) + int(jb[0]["start"]) + int(od[-1]) + int(sp[-1]["devmask"])
                 ev += n + 2 * win.finished                # arrivals + starts + completions of a finished run
             return valid, len(self.reps) * int(self.lay.block_bytes), chk, ev
@@ -513,8 +513,8 @@ def ours(args):
             # the records really are the run: decode one replica of this thread and compare with the value run
             hf = halves[0]
             hf.e.lib.gs_window(hf.e.h, 0, C.byref(win))
-            evb, qrb, jb, od, sp = capi.Engine.result_views(hf.out, hf.pitch, 0, hf.lay, win)
-            rows = lm.expand_rows(evb, qrb, win.row_first, win.ticks, M, G)
+            evb, qrb, neb, jb, od, sp = capi.Engine.result_views(hf.out, hf.pitch, 0, hf.lay, win)
+            rows = lm.expand_rows(evb, qrb, neb, win.row_first, win.ticks, M, G)
             assert len(rows) == ticks[mine[0]] and int(rows["finished"][-1]) == n and int(rows["now"][-1]) == ticks[mine[0]]
             results[k] = (ph, h2d // e2e_steps, d2h // e2e_steps, chk, ev_cnt // e2e_steps, d2h_copied // e2e_steps)
             for hf in halves:
@@ -560,7 +560,7 @@ def ours(args):
            "timing": "wall clock between barrier+synchronize around the timed steps of all threads, max over ranks",
            "phase_ms_per_step_slowest_thread": {k: v * 1e3 / e2e_steps for k, v in ph.items()},
            "pipeline": "two engine handles per host thread: the strided read-back of one half overlaps the strided upload and the kernel of the other",
-           "result_format": "compact records (gs_evrow / gs_qrow / start ticks / finish order / gs_cspan), one strided copy per handle each way "
+           "result_format": "compact records (24-byte gs_evrow / gs_qrow, gs_nodeev, start ticks, finish order, 8-byte gs_cspan), one strided copy per handle each way "
                             "(d2h_bytes counts the copied blocks incl. their unused capacity); one replica per thread is decoded to full rows and checked",
            "checksum": checksum}
 

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .log_manager import CSPAN_DTYPE, EVROW_DTYPE, JOB_DTYPE, JOBRUN_DTYPE, QROW_DTYPE, ROW_DTYPE, SPAN_DTYPE
+from .log_manager import CSPAN_DTYPE, EVROW_DTYPE, JOB_DTYPE, JOBRUN_DTYPE, NODEEV_DTYPE, QROW_DTYPE, ROW_DTYPE, SPAN_DTYPE
 
 GS_MAX_QUEUES = 8
 SCHEDULES = {"fifo": 0, "sjf": 1, "dlas": 2, "dlas-gpu": 3, "gittins": 4}
@@ -58,13 +58,13 @@ SWITCH_MEM = (5.0, 8.0, 0.2)          # worker_mem, ps_mem, p_w_mem: core/models
 
 class GsWindowInfo(C.Structure):
     _fields_ = [("row_first", C.c_int64), ("ticks", C.c_int64), ("ev_rows", C.c_int64), ("q_rows", C.c_int64),
-                ("spans_used", C.c_int64), ("admitted", C.c_int64), ("finished", C.c_int64), ("n", C.c_int64)]
+                ("node_events", C.c_int64), ("spans_used", C.c_int64), ("admitted", C.c_int64), ("finished", C.c_int64), ("n", C.c_int64)]
 
 
 class GsResultLayout(C.Structure):
-    _fields_ = [("block_bytes", C.c_int64), ("off_ev", C.c_int64), ("off_q", C.c_int64), ("off_jobs", C.c_int64),
+    _fields_ = [("block_bytes", C.c_int64), ("off_ev", C.c_int64), ("off_q", C.c_int64), ("off_nodeev", C.c_int64), ("off_jobs", C.c_int64),
                 ("off_duration", C.c_int64), ("off_finish_order", C.c_int64), ("off_spans", C.c_int64),
-                ("cap_ev", C.c_int64), ("cap_q", C.c_int64), ("cap_spans", C.c_int64), ("n", C.c_int64), ("span_bytes", C.c_int64)]
+                ("cap_ev", C.c_int64), ("cap_q", C.c_int64), ("cap_nodeev", C.c_int64), ("cap_spans", C.c_int64), ("n", C.c_int64), ("span_bytes", C.c_int64)]
 
 
 JOBIN_DTYPE = np.dtype([("arrive_tick", "<i4"), ("gpus", "<i4"), ("gpu_per_task", "<i4"), ("ps_count", "<i4"),
@@ -213,7 +213,7 @@ def load_library():
     lib.gs_launch_count.argtypes = [C.c_void_p]
     lib.gs_launch_count.restype = C.c_int64
     lib.gs_window.argtypes = [C.c_void_p, C.c_int, C.POINTER(GsWindowInfo)]
-    lib.gs_fetch_compact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gs_fetch_compact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gs_sync.argtypes = [C.c_void_p]
     lib.gs_set_async.argtypes = [C.c_void_p, C.c_int]
     lib.gs_set_queue_rows_cap.argtypes = [C.c_void_p, C.c_int64]
@@ -239,7 +239,7 @@ def load_library():
                  "gs_fetch_rows", "gs_fetch_jobs", "gs_fetch_spans", "gs_place_batch",
                  "gs_net_cost"):
         getattr(lib, name).restype = C.c_int
-    if lib.gs_abi_version() != 3:
+    if lib.gs_abi_version() != 4:
         raise GsError("libgsched.so ABI version mismatch")
     declare_horus_prototypes(lib)
     lib.gs_build_tag.restype = C.c_char_p
@@ -467,12 +467,12 @@ class Engine:
     def sync(self):
         self._check(self.lib.gs_sync(self.h), "gs_sync")
 
-    def fetch_compact_into(self, sim, ev=None, qr=None, jobs=None, dur=None, order=None, spans=None):
+    def fetch_compact_into(self, sim, ev=None, qr=None, ne=None, jobs=None, dur=None, order=None, spans=None):
         """Enqueue the copies of one replica's compact results into caller buffers (numpy views, ideally of
         PinnedBuffer memory, each at least as long as window(sim) says); returns at once -- call sync()."""
         def vp(a):
             return None if a is None else a.ctypes.data_as(C.c_void_p)
-        self._check(self.lib.gs_fetch_compact(self.h, sim, vp(ev), vp(qr), vp(jobs), vp(dur), vp(order), vp(spans)),
+        self._check(self.lib.gs_fetch_compact(self.h, sim, vp(ev), vp(qr), vp(ne), vp(jobs), vp(dur), vp(order), vp(spans)),
                     "gs_fetch_compact")
 
     def load_traces_packed(self, block, pitch_bytes, n_each):
@@ -497,28 +497,30 @@ class Engine:
 
     @staticmethod
     def result_views(buf, pitch, index, lay: "GsResultLayout", win: "GsWindowInfo"):
-        """numpy views (ev rows, queue rows, job runs, finish order, span pool) of replica `index` inside a fetched block buffer"""
+        """numpy views (records, queue records, node events, job starts, finish order, span pool) of replica `index` inside a fetched block buffer"""
         base = index * pitch
         ev = np.frombuffer(buf, dtype=EVROW_DTYPE, count=int(win.ev_rows), offset=base + lay.off_ev)
         qr = np.frombuffer(buf, dtype=QROW_DTYPE, count=int(win.q_rows), offset=base + lay.off_q)
+        ne = np.frombuffer(buf, dtype=NODEEV_DTYPE, count=int(win.node_events), offset=base + lay.off_nodeev)
         jobs = np.frombuffer(buf, dtype=JOBRUN_DTYPE, count=int(win.n), offset=base + lay.off_jobs)
         order = np.frombuffer(buf, dtype=np.int32, count=int(win.finished), offset=base + lay.off_finish_order)
         spans = np.frombuffer(buf, dtype=CSPAN_DTYPE if lay.span_bytes == 8 else SPAN_DTYPE, count=int(win.spans_used), offset=base + lay.off_spans)
-        return ev, qr, jobs, order, spans
+        return ev, qr, ne, jobs, order, spans
 
     def fetch_compact(self, sim=0):
-        """(window info, gs_evrow[], gs_qrow[], gs_job_start[], duration-after-network-cost or None, finish order, span pool)"""
+        """(window info, gs_evrow[], gs_qrow[], gs_nodeev[], gs_job_start[], duration-after-network-cost or None, finish order, span pool)"""
         w = self.window(sim)
         n = int(w.n)
         ev = np.empty(max(int(w.ev_rows), 1), dtype=EVROW_DTYPE)
         qr = np.empty(max(int(w.q_rows), 1), dtype=QROW_DTYPE)
+        ne = np.empty(max(int(w.node_events), 1), dtype=NODEEV_DTYPE)
         jobs = np.empty(max(n, 1), dtype=JOBRUN_DTYPE)
         dur = np.full(max(n, 1), np.nan)
         order = np.empty(max(int(w.finished), 1), dtype=np.int32)
         spans = np.empty(max(int(w.spans_used), 1), dtype=CSPAN_DTYPE if self.result_layout(sim).span_bytes == 8 else SPAN_DTYPE)
-        self.fetch_compact_into(sim, ev, qr, jobs, dur, order, spans)
+        self.fetch_compact_into(sim, ev, qr, ne, jobs, dur, order, spans)
         self.sync()
-        return (w, ev[:int(w.ev_rows)], qr[:int(w.q_rows)], jobs[:n], (None if n == 0 or np.isnan(dur[0]) else dur[:n]),
+        return (w, ev[:int(w.ev_rows)], qr[:int(w.q_rows)], ne[:int(w.node_events)], jobs[:n], (None if n == 0 or np.isnan(dur[0]) else dur[:n]),
                 order[:int(w.finished)], spans[:int(w.spans_used)])
 
     def switch_yarn(self, clusters, mem=SWITCH_MEM):

@@ -45,6 +45,7 @@ struct SimDev {
   gs_tick_row *rows;          // event-driven policies: one row per event
   gs_evrow *evrows;           // fifo: one record per tick on which a counter changed
   gs_qrow *qrows;             // fifo: queue statistics beside the records taken with a non-empty queue
+  gs_nodeev *nodeev;          // fifo: (tick, nodes that ever hosted a job) whenever that count grows / at the start of a window
   unsigned long long *nbusy;  // persisted node table (between launches)
   int *nk;                    // bit31 = node ever hosted a placement (node.py:93-97, never cleared)
   long long span_cap, rows_cap, qrows_cap;
@@ -72,7 +73,7 @@ struct SimDev {
   int delta, p, top, running, finished, ever, busy_gpus, done, status, need_init;
   int blocked;                // fifo: the queue head did not fit and nothing has changed since
   int nev, nq;                // fifo: records / queue records written by the last launch
-  int pad1;
+  int nne;                    // fifo: node events written by the last launch
   long long mem_busy, sum_arr, span_used, events, evals, started, ticks, row_first;
 };
 

@@ -6,9 +6,10 @@
 // finishes changes no counter of the statistics row (schedule.py:95-133) except the ones that are
 // linear in the tick number, so such ticks are jumped over in one step and leave no record.  The
 // device therefore emits
-//   * one 32-byte gs_evrow per tick on which a counter changed (plus the first tick of a launch), and
-//   * one 32-byte gs_qrow beside it while the queue is non-empty (arrival-tick sum, oldest arrival,
-//     the two middle arrivals -- the pending statistics of jobs_manager.py:72-87 are `now - arrival`),
+//   * one 24-byte gs_evrow per tick on which a counter changed (plus the first tick of a launch),
+//   * one 24-byte gs_qrow beside it while the queue is non-empty (arrival-tick sum, oldest arrival,
+//     the two middle arrivals -- the pending statistics of jobs_manager.py:72-87 are `now - arrival`), and
+//   * one 8-byte gs_nodeev whenever the count of nodes that ever hosted a job grows (node.py:93-97),
 // from which gs_expand_rows_kernel (or the host) rebuilds every gs_tick_row bit for bit.  Per job it writes the start
 // tick (4 bytes; the rest of job.csv follows from the trace) and per (job, node) an 8-byte gs_cspan.
 //
@@ -132,12 +133,13 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
   long long *wmem = S.wheel_mem;
   typedef typename MO::Span SpanT;
   SpanT *spans = reinterpret_cast<SpanT *>(S.spans);
-  int4 *rowA = reinterpret_cast<int4 *>(S.evrows), *rowB = reinterpret_cast<int4 *>(S.qrows);
+  int2 *rowA = reinterpret_cast<int2 *>(S.evrows), *rowB = reinterpret_cast<int2 *>(S.qrows);   // 24-byte records = 3 x 8 bytes
+  int2 *nodeev = reinterpret_cast<int2 *>(S.nodeev);
   // everything a replica owns lives in global memory: let the compiler emit ld/st.global instead of generic accesses
   __builtin_assume(__isGlobal(jobs)); __builtin_assume(__isGlobal(jstart)); __builtin_assume(__isGlobal(jst));
   __builtin_assume(__isGlobal(stack)); __builtin_assume(__isGlobal(fin)); __builtin_assume(__isGlobal(whead));
   __builtin_assume(__isGlobal(wmem)); __builtin_assume(__isGlobal(spans)); __builtin_assume(__isGlobal(rowA));
-  __builtin_assume(__isGlobal(rowB));
+  __builtin_assume(__isGlobal(rowB)); __builtin_assume(__isGlobal(nodeev));
   const int wmask = S.wheel_mask;
   const long long cap_bytes = S.cap_bytes, fit_limit = S.fit_limit;
   const int span_cap = (int)(S.span_cap > 0x7fffffffLL ? 0x7fffffffLL : S.span_cap);
@@ -152,7 +154,8 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
   const int delta0 = delta;
   const int capA = (int)(S.rows_cap > 0x7fffffffLL ? 0x7fffffffLL : S.rows_cap);
   const int capB = (int)(S.qrows_cap > 0x7fffffffLL ? 0x7fffffffLL : S.qrows_cap);
-  int na = 0, nb = 0;
+  int na = 0, nb = 0, nne = 0;
+  int ever_rec = -1;                              // busy-node count of this launch's last node event (-1: none yet)
   long long budget_ll = max_ticks > 0 ? max_ticks : 0x7fffffffLL;
   if (budget_ll > 0x7fffffffLL - delta - 2) budget_ll = 0x7fffffffLL - delta - 2;
   const int t_end = delta + (int)(budget_ll > 0 ? budget_ll : 0);      // first tick this launch does NOT process
@@ -513,7 +516,6 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
     }
     // ---------------- H. statistics record (schedule.py:95-133) from O(1) counters
     if (changed) {
-      int qidx = -1;
       if (top > 0) {
         // the queue is a stack with non-decreasing arrival ticks bottom->top, so the sorted pending
         // list is the stack read top->bottom: median/max are index look-ups
@@ -523,13 +525,21 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
         else a_lo = ilo >= cache_lo ? ldsv2(STK_A(ilo)).y : stack[ilo].y;
         if (hvalid && ihi == top - 1) a_hi = harr;
         else a_hi = ihi >= cache_lo ? ldsv2(STK_A(ihi)).y : stack[ihi].y;
-        qidx = nb;
-        __stcs(&rowB[2 * nb], make_int4((int)(sum_arr & 0xffffffffLL), (int)(sum_arr >> 32), bottom_arr, a_lo));
-        __stcs(&rowB[2 * nb + 1], make_int4(a_hi, 0, 0, 0));
+        {
+          int2 *qb = rowB + 3 * nb;
+          __stcs(qb, make_int2(now, bottom_arr));
+          __stcs(qb + 1, make_int2(a_lo, a_hi));
+          __stcs(qb + 2, make_int2((int)(sum_arr & 0xffffffffLL), (int)(sum_arr >> 32)));
+        }
         nb += 1;
       }
-      __stcs(&rowA[2 * na], make_int4(now, top, finished, busy_gpus | (running << 16)));
-      __stcs(&rowA[2 * na + 1], make_int4((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32), ever, qidx));
+      if (ever != ever_rec) { __stcs(&nodeev[nne], make_int2(now, ever)); nne += 1; ever_rec = ever; }
+      {
+        int2 *ab = rowA + 3 * na;
+        __stcs(ab, make_int2(now, top));
+        __stcs(ab + 1, make_int2(finished, busy_gpus | (running << 16)));
+        __stcs(ab + 2, make_int2((int)(mem_busy & 0xffffffffLL), (int)(mem_busy >> 32)));
+      }
       na += 1;
     }
     delta = now;
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(32, GS_TICK_MINBLOCKS) gs_tick2_kernel(SimDev 
     S.ever = ever; S.busy_gpus = busy_gpus; S.mem_busy = mem_busy; S.sum_arr = sum_arr;
     S.span_used = span_used; S.started = (long long)finished + running;
     S.events = (long long)p + finished + running + finished; S.evals = evals;
-    S.ticks = delta; S.row_first = delta0; S.nev = na; S.nq = nb; S.blocked = blocked;
+    S.ticks = delta; S.row_first = delta0; S.nev = na; S.nq = nb; S.nne = nne; S.blocked = blocked;
     S.done = done ? 1 : 0; S.status = status; S.need_init = 0;
   }
 #undef BUSY_A
@@ -573,24 +583,30 @@ __global__ void gs_expand_rows_kernel(const SimDev *sims, int sim, int M, int G,
   const int na = S.nev;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= na) return;
-  const int4 *rowA = reinterpret_cast<const int4 *>(S.evrows), *rowB = reinterpret_cast<const int4 *>(S.qrows);
-  const int4 a0 = rowA[2 * k], a1 = rowA[2 * k + 1];
-  const int t_first = a0.x;                                            // `now` of this record
-  const int t_last = (k + 1 < na) ? rowA[2 * (k + 1)].x - 1 : (int)S.ticks;   // last `now` this record covers
-  const int queued = a0.y, busy_gpus = a0.w & 0xffff, running = (int)((unsigned)a0.w >> 16);
+  const gs_evrow a = S.evrows[k];
+  const int t_first = a.now;                                           // `now` of this record
+  const int t_last = (k + 1 < na) ? S.evrows[k + 1].now - 1 : (int)S.ticks;   // last `now` this record covers
+  const int queued = a.queued, busy_gpus = a.busy_gpus, running = a.running;
+  int nodes = 0;
+  {                       // last node event at or before this record (the first record of a window always has one)
+    int lo = 0, hi = S.nne - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S.nodeev[mid].now <= t_first) lo = mid; else hi = mid - 1; }
+    if (S.nne > 0) nodes = S.nodeev[lo].busy_nodes;
+  }
   long long sum_arr = 0; int bottom = 0, a_lo = 0, a_hi = 0;
-  if (a1.w >= 0) {
-    const int4 b0 = rowB[2 * a1.w], b1 = rowB[2 * a1.w + 1];
-    sum_arr = (long long)(((unsigned long long)(unsigned)b0.y << 32) | (unsigned)b0.x);
-    bottom = b0.z; a_lo = b0.w; a_hi = b1.x;
+  if (queued > 0) {       // the queue record taken on the same tick
+    int lo = 0, hi = S.nq - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.qrows[mid].now < t_first) lo = mid + 1; else hi = mid; }
+    const gs_qrow b = S.qrows[lo];
+    sum_arr = b.arrive_sum; bottom = b.oldest_arrive; a_lo = b.med_lo_arrive; a_hi = b.med_hi_arrive;
   }
   const long long row0 = S.row_first;                                  // tick index of the window's first row
   for (int v = t_first; v <= t_last; ++v) {
     int4 *dst = reinterpret_cast<int4 *>(&out[(long long)v - 1 - row0]);
     const long long ps = queued > 0 ? (long long)queued * v - sum_arr : 0;
-    dst[0] = make_int4(v, M - a1.z, a1.z, busy_gpus);
-    dst[1] = make_int4(M * G - busy_gpus, running, queued, a0.z);
-    dst[2] = make_int4(a1.x, a1.y, (int)(ps & 0xffffffffLL), (int)(ps >> 32));
+    dst[0] = make_int4(v, M - nodes, nodes, busy_gpus);
+    dst[1] = make_int4(M * G - busy_gpus, running, queued, a.finished);
+    dst[2] = make_int4((int)(a.mem_busy_bytes & 0xffffffffLL), (int)(a.mem_busy_bytes >> 32), (int)(ps & 0xffffffffLL), (int)(ps >> 32));
     dst[3] = queued > 0 ? make_int4(v - bottom, v - a_lo, v - a_hi, 0) : make_int4(0, 0, 0, 0);
   }
 }

@@ -14,7 +14,7 @@
 //     forms and O(1) incremental counters; completions come from a timing
 //     wheel keyed by finish tick, appended in start order.
 //   * the loop is event stepped: ticks on which nothing arrives, starts or
-//     finishes are jumped over; every other tick leaves one 32-byte record of
+//     finishes are jumped over; every other tick leaves one 24-byte record of
 //     integer aggregates (+ one for the queue while it is non-empty) from which
 //     the 64-byte gs_tick_row of EVERY tick is rebuilt on demand; the job table
 //     is streamed once from HBM, results are written once (4-byte start tick per job +
@@ -57,7 +57,7 @@
 // queue records, per-job results, (durations,) finish order, spans -- so that everything a caller reads back from a
 // replica is ONE copy, and from all replicas of a handle ONE strided copy (the slabs live side by side in an arena).
 struct SimLayout {
-  size_t o_ev = 0, o_q = 0, o_rec2 = 0, o_dur2 = 0, o_fin = 0, o_spans = 0, out_bytes = 0;
+  size_t o_ev = 0, o_q = 0, o_ne = 0, o_rec2 = 0, o_dur2 = 0, o_fin = 0, o_spans = 0, out_bytes = 0;
   size_t o_rec = 0, o_rows = 0, o_jst = 0, o_stack = 0, o_wh = 0, o_wm = 0, o_nb = 0, o_nk = 0;
   size_t o_pj = 0, o_run = 0, o_qs = 0, o_end = 0, o_tmp = 0, o_ci = 0, o_ck = 0, o_stale = 0;
   size_t total = 0;
@@ -413,6 +413,7 @@ static SimLayout layout_sim(gs_handle h, const SimHost &s, int64_t rows_cap) {
   } else {
     L.o_ev = take(sizeof(gs_evrow) * (size_t)rows_cap);
     L.o_q = take(sizeof(gs_qrow) * (size_t)L.qrows_cap);
+    L.o_ne = take(sizeof(gs_nodeev) * (size_t)(M + 2));          // at most one event per node + one per window
     L.o_rec2 = take(4 * N);
     if (net) L.o_dur2 = take(8 * N);
     L.o_fin = take(4 * N);
@@ -450,14 +451,14 @@ static int bind_sim(gs_handle h, SimHost &s, const SimLayout &L, unsigned char *
   D.bandwidth = c.bandwidth; D.latency = c.internode_latency;
   D.fin = (int *)(d + o_fin);
   D.rec = nullptr; D.rows = nullptr; D.jstart = nullptr; D.dur2 = nullptr; D.jst2 = nullptr; D.stack = nullptr;
-  D.wheel_head = nullptr; D.wheel_mem = nullptr; D.spans = nullptr; D.evrows = nullptr; D.qrows = nullptr; D.nbusy = nullptr; D.nk = nullptr;
+  D.wheel_head = nullptr; D.wheel_mem = nullptr; D.spans = nullptr; D.evrows = nullptr; D.qrows = nullptr; D.nodeev = nullptr; D.nbusy = nullptr; D.nk = nullptr;
   if (evd) {
     D.rec = (gs_job_rec *)(d + o_rec); D.rows = (gs_tick_row *)(d + o_rows);
   } else {
     D.jstart = (int *)(d + o_rec2); D.dur2 = net ? (double *)(d + o_dur2) : nullptr;
     D.jst2 = (JobState2 *)(d + o_jst); D.stack = (int *)(d + o_stack);
     D.wheel_head = (int *)(d + o_wh); D.wheel_mem = (long long *)(d + o_wm);
-    D.spans = (void *)(d + o_spans); D.evrows = (gs_evrow *)(d + o_ev); D.qrows = (gs_qrow *)(d + o_q);
+    D.spans = (void *)(d + o_spans); D.evrows = (gs_evrow *)(d + o_ev); D.qrows = (gs_qrow *)(d + o_q); D.nodeev = (gs_nodeev *)(d + L.o_ne);
     D.nbusy = (unsigned long long *)(d + o_nb); D.nk = (int *)(d + o_nk);
   }
   D.span_cap = s.span_cap; D.rows_cap = rows_cap; D.qrows_cap = qrows_cap;
@@ -489,7 +490,7 @@ static int bind_sim(gs_handle h, SimHost &s, const SimLayout &L, unsigned char *
     }
   }
   D.delta = D.p = D.top = D.running = D.finished = D.ever = D.busy_gpus = D.done = D.status = 0;
-  D.blocked = D.nev = D.nq = 0;
+  D.blocked = D.nev = D.nq = D.nne = 0;
   D.mem_busy = D.sum_arr = D.span_used = D.events = D.evals = D.started = D.ticks = D.row_first = 0;
   D.need_init = 1;
   s.prepared = true;
@@ -626,7 +627,7 @@ extern "C" int gs_window(gs_handle h, int sim, gs_window_info *out) {
   const SimDev &D = s.dev;
   out->row_first = D.row_first; out->ticks = D.ticks;
   const bool fifo = s.pol.schedule == GS_SCHED_FIFO;
-  out->ev_rows = fifo ? D.nev : 0; out->q_rows = fifo ? D.nq : 0;
+  out->ev_rows = fifo ? D.nev : 0; out->q_rows = fifo ? D.nq : 0; out->node_events = fifo ? D.nne : 0;
   out->spans_used = D.span_used; out->admitted = D.p; out->finished = D.finished; out->n = s.n;
   return GS_OK;
 }
@@ -716,19 +717,21 @@ extern "C" int gs_set_queue_rows_cap(gs_handle h, int64_t qrows_cap) {
   return GS_OK;
 }
 
-extern "C" int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_start *jobs_out,
+extern "C" int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_nodeev *nodeev_out, gs_job_start *jobs_out,
                                 double *duration_out, int32_t *finish_order_out, void *spans_out) {
   if (!h) return GS_ERR_ARG;
   if (sim < 0 || sim >= h->nsims) return fail(h, GS_ERR_ARG, "gs_fetch_compact: sim index out of range");
   SimHost &s = h->sims[(size_t)sim];
   if (!s.prepared) return fail(h, GS_ERR_STATE, "gs_fetch_compact: nothing has run yet");
   if (s.pol.schedule != GS_SCHED_FIFO) return fail(h, GS_ERR_ARG, "gs_fetch_compact: the compact records are the fifo engine's output");
-  static_assert(sizeof(gs_evrow) == 32 && sizeof(gs_qrow) == 32 && sizeof(gs_job_start) == 4 && sizeof(gs_cspan) == 8, "compact record layout");
+  static_assert(sizeof(gs_evrow) == 24 && sizeof(gs_qrow) == 24 && sizeof(gs_nodeev) == 8 && sizeof(gs_job_start) == 4 && sizeof(gs_cspan) == 8,
+                "compact record layout");
   const size_t span_bytes = s.cl.num_gpu_p_node > 32 ? sizeof(gs_span) : sizeof(gs_cspan);
   const SimDev &D = s.dev;
   CU(cudaSetDevice(h->device));
   if (ev_out && D.nev > 0) CU(cudaMemcpyAsync(ev_out, D.evrows, sizeof(gs_evrow) * (size_t)D.nev, cudaMemcpyDeviceToHost, h->stream));
   if (q_out && D.nq > 0) CU(cudaMemcpyAsync(q_out, D.qrows, sizeof(gs_qrow) * (size_t)D.nq, cudaMemcpyDeviceToHost, h->stream));
+  if (nodeev_out && D.nne > 0) CU(cudaMemcpyAsync(nodeev_out, D.nodeev, sizeof(gs_nodeev) * (size_t)D.nne, cudaMemcpyDeviceToHost, h->stream));
   if (jobs_out && s.n > 0) CU(cudaMemcpyAsync(jobs_out, D.jstart, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
   if (duration_out && D.dur2 && s.n > 0) CU(cudaMemcpyAsync(duration_out, D.dur2, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream));
   if (finish_order_out && D.finished > 0) CU(cudaMemcpyAsync(finish_order_out, D.fin, 4 * (size_t)D.finished, cudaMemcpyDeviceToHost, h->stream));
@@ -818,7 +821,8 @@ extern "C" int gs_result_layout(gs_handle h, int sim, gs_result_layout_t *out) {
   const SimLayout &L = s.layout;
   memset(out, 0, sizeof(*out));
   out->block_bytes = (int64_t)L.out_bytes;
-  out->off_ev = (int64_t)L.o_ev; out->off_q = (int64_t)L.o_q; out->off_jobs = (int64_t)L.o_rec2;
+  out->off_ev = (int64_t)L.o_ev; out->off_q = (int64_t)L.o_q; out->off_nodeev = (int64_t)L.o_ne; out->off_jobs = (int64_t)L.o_rec2;
+  out->cap_nodeev = (int64_t)s.cl.num_switch * s.cl.num_node_p_switch + 2;
   out->off_duration = s.cl.enable_network_costs ? (int64_t)L.o_dur2 : -1;
   out->off_finish_order = (int64_t)L.o_fin; out->off_spans = (int64_t)L.o_spans;
   out->cap_ev = L.rows_cap; out->cap_q = L.qrows_cap; out->cap_spans = s.span_cap; out->n = s.n;

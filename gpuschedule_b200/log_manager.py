@@ -34,18 +34,19 @@ JOB_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("jct", "<i4"),
 SPAN_DTYPE = np.dtype([("node", "<i4"), ("ntasks", "<i4"), ("devmask", "<u8")])
 assert ROW_DTYPE.itemsize == 64 and JOB_DTYPE.itemsize == 24 and SPAN_DTYPE.itemsize == 16
 # compact records of the fifo engine: gs_evrow / gs_qrow / gs_job_start / gs_cspan
-EVROW_DTYPE = np.dtype([("now", "<i4"), ("queued", "<i4"), ("finished", "<i4"), ("busy_running", "<u4"),
-                        ("mem_busy_bytes", "<i8"), ("busy_nodes", "<i4"), ("qrow", "<i4")])
-QROW_DTYPE = np.dtype([("arrive_sum", "<i8"), ("oldest_arrive", "<i4"), ("med_lo_arrive", "<i4"),
-                       ("med_hi_arrive", "<i4"), ("reserved", "<i4", (3,))])
+EVROW_DTYPE = np.dtype([("now", "<i4"), ("queued", "<i4"), ("finished", "<i4"), ("busy_gpus", "<u2"), ("running", "<u2"),
+                        ("mem_busy_bytes", "<i8")])
+QROW_DTYPE = np.dtype([("now", "<i4"), ("oldest_arrive", "<i4"), ("med_lo_arrive", "<i4"), ("med_hi_arrive", "<i4"),
+                       ("arrive_sum", "<i8")])
+NODEEV_DTYPE = np.dtype([("now", "<i4"), ("busy_nodes", "<i4")])
 JOBRUN_DTYPE = np.dtype([("start", "<i4")])                     # gs_job_start: the start tick, -1 = never started
 CSPAN_DTYPE = np.dtype([("where", "<u4"), ("devmask", "<u4")])  # gs_cspan (clusters with at most 32 GPUs per node)
-assert EVROW_DTYPE.itemsize == 32 and QROW_DTYPE.itemsize == 32 and JOBRUN_DTYPE.itemsize == 4 and CSPAN_DTYPE.itemsize == 8
+assert (EVROW_DTYPE.itemsize, QROW_DTYPE.itemsize, NODEEV_DTYPE.itemsize, JOBRUN_DTYPE.itemsize, CSPAN_DTYPE.itemsize) == (24, 24, 8, 4, 8)
 SPAN_FIRST = 0x80000000
 
 
-def expand_rows(ev, qr, row_first, ticks, n_nodes, gpus_per_node):
-    """gs_tick_row of every tick of a window from its compact records (include/gsched.h: gs_evrow):
+def expand_rows(ev, qr, nodeev, row_first, ticks, n_nodes, gpus_per_node):
+    """gs_tick_row of every tick of a window from its compact records (include/gsched.h: gs_evrow / gs_qrow / gs_nodeev):
     record k describes the rows `now_k` .. `now_(k+1) - 1`; on those only `delta` and the pending
     statistics move, linearly with the tick (pending = now - arrival, jobs_manager.py:72-87)."""
     count = int(ticks - row_first)
@@ -58,19 +59,20 @@ def expand_rows(ev, qr, row_first, ticks, n_nodes, gpus_per_node):
     k = np.repeat(np.arange(len(ev)), gaps)
     e = ev[k]
     q = e["queued"].astype(np.int64)
-    busy = (e["busy_running"] & 0xffff).astype(np.int32)
+    busy = e["busy_gpus"].astype(np.int32)
+    nodes = nodeev["busy_nodes"][np.searchsorted(nodeev["now"], ev["now"], side="right") - 1][k]   # last node event at or before the record
     rows["now"] = now
-    rows["idle_nodes"] = n_nodes - e["busy_nodes"]
-    rows["busy_nodes"] = e["busy_nodes"]
+    rows["idle_nodes"] = n_nodes - nodes
+    rows["busy_nodes"] = nodes
     rows["busy_gpus"] = busy
     rows["idle_gpus"] = n_nodes * gpus_per_node - busy
-    rows["running"] = (e["busy_running"] >> 16).astype(np.int32)
+    rows["running"] = e["running"].astype(np.int32)
     rows["queued"] = e["queued"]
     rows["finished"] = e["finished"]
     rows["mem_busy_bytes"] = e["mem_busy_bytes"]
-    has = e["qrow"] >= 0
+    has = q > 0
     if has.any():
-        b = qr[e["qrow"][has]]
+        b = qr[np.searchsorted(qr["now"], e["now"][has])]           # the queue record taken on the same tick
         v = now[has]
         rows["pend_sum"][has] = q[has] * v - b["arrive_sum"]
         rows["pend_max"][has] = v - b["oldest_arrive"]

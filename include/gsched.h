@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 3
+#define GS_ABI_VERSION 4
 #define GS_MAX_QUEUES 8
 #define GS_MAX_GPUS_PER_NODE 64
 #define GS_MAX_RANKS 8          /* GPUs of one box that may share one simulation (gs_comm_init) */
@@ -107,28 +107,35 @@ typedef struct gs_tick_row {
 /* Compact form of the same information, as the fifo engine writes it.  On a tick where nothing arrives,
  * starts or finishes no LogInfo counter changes except `delta` and the pending times, which move linearly
  * with the tick, so the engine writes one gs_evrow per tick on which a counter DID change (and for the first
- * tick of every gs_run window) plus, while the queue is non-empty, one gs_qrow; the row of any tick
+ * tick of every gs_run window), beside it one gs_qrow while the queue is non-empty, and one gs_nodeev whenever
+ * the number of nodes that ever hosted a job grows (and for the first record of a window); the row of any tick
  * v in [now_k, now_k+1) follows from record k:
  *   delta = v, pending sum = queued*v - arrive_sum, max/median pending = v - oldest / middle arrivals
- * (jobs_manager.py:72-87).  gs_fetch_rows does this expansion on the device; gs_fetch_compact hands out the
- * records themselves (about a third of the bytes of the rows on the BASELINE trace).  32 bytes each.       */
+ * (jobs_manager.py:72-87), busy nodes = the last gs_nodeev at or before v, queue statistics = the gs_qrow with
+ * the same `now` (both streams are ordered by `now`).  gs_fetch_rows does this expansion on the device;
+ * gs_fetch_compact / gs_fetch_results hand out the records themselves (about a quarter of the bytes of the rows
+ * on the BASELINE trace).  24 + 24 + 8 bytes.                                                              */
 typedef struct gs_evrow {
   int32_t now;              /* 'delta' of the first row this record describes                          */
   int32_t queued;
   int32_t finished;
-  uint32_t busy_running;    /* busy_gpus | running << 16  (the engine requires M*G <= 65535)           */
+  uint16_t busy_gpus;       /* (the engine requires M*G <= 65535)                                      */
+  uint16_t running;
   int64_t mem_busy_bytes;
-  int32_t busy_nodes;
-  int32_t qrow;             /* index of the gs_qrow of this record in the same window, -1: queue empty */
 } gs_evrow;
 
 typedef struct gs_qrow {
-  int64_t arrive_sum;       /* sum of the arrival ticks of the queued jobs                             */
+  int32_t now;              /* the gs_evrow this record belongs to                                     */
   int32_t oldest_arrive;    /* arrival tick of the job that has waited longest                         */
   int32_t med_lo_arrive;    /* arrival ticks of the two middle jobs of the queue (equal when odd)      */
   int32_t med_hi_arrive;
-  int32_t reserved[3];
+  int64_t arrive_sum;       /* sum of the arrival ticks of the queued jobs                             */
 } gs_qrow;
+
+typedef struct gs_nodeev {
+  int32_t now;              /* from this row on ...                                                    */
+  int32_t busy_nodes;       /* ... this many nodes have hosted a placement (node.py:93-97, never decreases) */
+} gs_nodeev;
 
 /* Compact per-job result of the fifo engine: the start tick (-1: the job never started).  fifo never preempts,
  * so the rest of job.csv follows from the trace: run length = max(1, ceil(job.duration)) ticks (quirk Q11; with
@@ -151,6 +158,7 @@ typedef struct gs_window_info {
   int64_t row_first;        /* tick index of the window's first row                                    */
   int64_t ticks;            /* rows produced so far (the window is [row_first, ticks))                 */
   int64_t ev_rows, q_rows;  /* records of the window                                                   */
+  int64_t node_events;      /* gs_nodeev records of the window (at least 1 once a tick has run)         */
   int64_t spans_used;       /* (job, node) records so far, start order                                 */
   int64_t admitted;         /* trace rows consumed so far: gs_job_start is defined for jobs below this  */
   int64_t finished;
@@ -278,13 +286,13 @@ int gs_fetch_all(gs_handle h, int sim, int64_t first, int64_t count, gs_tick_row
 /* ---- compact, asynchronous result path (fifo engine) ------------------------------------------------
  * gs_window_info: sizes of what the last gs_run left.  gs_fetch_compact enqueues the copies of every
  * non-NULL output on the handle's stream and returns; gs_sync waits for them.  Buffers from
- * gs_host_alloc make the copies true DMA.  Sizes: ev_out ev_rows, q_out q_rows, jobs_out n,
+ * gs_host_alloc make the copies true DMA.  Sizes: ev_out ev_rows, q_out q_rows, nodeev_out node_events, jobs_out n,
  * duration_out n (only with network costs, else left untouched), finish_order_out finished,
  * spans_out spans_used records of gs_result_layout's span_bytes each (8: gs_cspan, 16: gs_span; start order,
  * the first-of-job flag marks job boundaries; jobs in start order = jobs_out sorted by start, start ticks are
  * unique -- one start per tick, schedule.py:188-190).                                                   */
 int gs_window(gs_handle h, int sim, gs_window_info *out);
-int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_job_start *jobs_out,
+int gs_fetch_compact(gs_handle h, int sim, gs_evrow *ev_out, gs_qrow *q_out, gs_nodeev *nodeev_out, gs_job_start *jobs_out,
                      double *duration_out, int32_t *finish_order_out, void *spans_out /* gs_cspan[] or gs_span[], see gs_result_layout */);
 int gs_sync(gs_handle h);
 /* The same, for many replicas with ONE copy each way (what bench.py's end-to-end path uses).  The replicas of a
@@ -297,8 +305,8 @@ int gs_sync(gs_handle h);
  *                          copy, asynchronous (gs_sync waits); gs_window tells how many entries of each array are valid */
 typedef struct gs_result_layout_t {
   int64_t block_bytes;
-  int64_t off_ev, off_q, off_jobs, off_duration /* -1 without network costs */, off_finish_order, off_spans;
-  int64_t cap_ev, cap_q, cap_spans, n;
+  int64_t off_ev, off_q, off_nodeev, off_jobs, off_duration /* -1 without network costs */, off_finish_order, off_spans;
+  int64_t cap_ev, cap_q, cap_nodeev, cap_spans, n;
   int64_t span_bytes;       /* 8: gs_cspan records (at most 32 GPUs per node), 16: gs_span records               */
 } gs_result_layout_t;
 int gs_load_traces_packed(gs_handle h, const gs_jobin *jobs, size_t pitch_bytes, const int64_t *n_each);

@@ -290,7 +290,7 @@ class Tight2:
 
     def __init__(self, cluster: GsCluster, table, span_cap=0):
         from gpuschedule_b200.capi import GsWindowInfo
-        from gpuschedule_b200.log_manager import EVROW_DTYPE, JOBRUN_DTYPE, QROW_DTYPE
+        from gpuschedule_b200.log_manager import EVROW_DTYPE, JOBRUN_DTYPE, NODEEV_DTYPE, QROW_DTYPE
         self._w, self._dt = GsWindowInfo, (EVROW_DTYPE, QROW_DTYPE, JOBRUN_DTYPE)
         self.cluster, self.table, self.n = cluster, table, table.n
         arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
@@ -303,6 +303,7 @@ class Tight2:
         self.cap = worst
         self.ev = np.zeros(worst, dtype=EVROW_DTYPE)
         self.qr = np.zeros(worst, dtype=QROW_DTYPE)
+        self.ne = np.zeros(cluster.num_switch * cluster.num_node_p_switch + 2, dtype=NODEEV_DTYPE)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -314,12 +315,13 @@ class Tight2:
 
     def run_window(self, max_ticks=0, cap_a=None, cap_b=None):
         """one window -> (status, GsWindowInfo, events, evals, done); records are in self.ev / self.qr"""
-        nev, nq = C.c_int64(0), C.c_int64(0)
+        nev, nq, nne = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         rc = lib().tight2_run(self.h, C.c_int64(max_ticks), C.c_int64(self.cap if cap_a is None else cap_a),
-                              C.c_int64(self.cap if cap_b is None else cap_b), _p(self.ev), _p(self.qr), C.byref(nev), C.byref(nq))
+                              C.c_int64(self.cap if cap_b is None else cap_b), _p(self.ev), _p(self.qr), _p(self.ne),
+                              C.byref(nev), C.byref(nq), C.byref(nne))
         w = self._w()
         events, evals, done = C.c_int64(0), C.c_int64(0), C.c_int32(0)
-        lib().tight2_info(self.h, C.byref(w), nev, nq, C.byref(events), C.byref(evals), C.byref(done))
+        lib().tight2_info(self.h, C.byref(w), nev, nq, nne, C.byref(events), C.byref(evals), C.byref(done))
         return rc, w, events.value, evals.value, done.value
 
     def run(self):
@@ -340,7 +342,7 @@ class Tight2:
             rc, w, events, evals, done = self.run_window(max_ticks, cap_a, cap_b)
             if rc != 0:
                 raise RuntimeError(f"tight2_run failed: {rc}")
-            parts.append(lm.expand_rows(self.ev[:w.ev_rows], self.qr[:w.q_rows], w.row_first, w.ticks, m, g))
+            parts.append(lm.expand_rows(self.ev[:w.ev_rows], self.qr[:w.q_rows], self.ne[:w.node_events], w.row_first, w.ticks, m, g))
             if done or self.n == 0:
                 break
         r = OracleResult()

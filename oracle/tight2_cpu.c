@@ -126,11 +126,12 @@ static void probe_next_fin(tight2 *t, int from) {
 }
 
 /* One window: at most max_ticks ticks (<= 0: no limit), at most capA / capB records.  Returns 0 or a gs_status. */
-int tight2_run(tight2 *t, int64_t max_ticks, int64_t capA, int64_t capB, gs_evrow *ev, gs_qrow *qr,
-               int64_t *nev_out, int64_t *nq_out) {
+int tight2_run(tight2 *t, int64_t max_ticks, int64_t capA, int64_t capB, gs_evrow *ev, gs_qrow *qr, gs_nodeev *ne,
+               int64_t *nev_out, int64_t *nq_out, int64_t *nne_out) {
   const int M = t->M, G = t->G;
   const int64_t n = t->n;
-  int64_t na = 0, nb = 0;
+  int64_t na = 0, nb = 0, nne = 0;
+  int ever_rec = -1;                 /* busy-node count of the last node event of this window (-1: none yet) */
   int64_t budget = max_ticks > 0 ? max_ticks : 0x7fffffffLL;
   if (budget > 0x7fffffffLL - t->delta - 2) budget = 0x7fffffffLL - t->delta - 2;
   const int t_end = t->delta + (int)budget;
@@ -284,21 +285,19 @@ int tight2_run(tight2 *t, int64_t max_ticks, int64_t capA, int64_t capB, gs_evro
     }
     /* H */
     if (changed) {
-      int32_t qidx = -1;
       if (t->top > 0) {
         const int top = t->top;
         const int ilo = top - 1 - ((top - 1) >> 1), ihi = top - 1 - (top >> 1);
         gs_qrow *q = &qr[nb];
-        memset(q, 0, sizeof(*q));
-        q->arrive_sum = t->sum_arr; q->oldest_arrive = t->bottom_arr;
+        q->now = now; q->arrive_sum = t->sum_arr; q->oldest_arrive = t->bottom_arr;
         q->med_lo_arrive = q_arrive(t, ilo); q->med_hi_arrive = q_arrive(t, ihi);
-        qidx = (int32_t)nb;
         nb += 1;
       }
+      if (t->ever != ever_rec) { ne[nne].now = now; ne[nne].busy_nodes = t->ever; nne += 1; ever_rec = t->ever; }
       gs_evrow *e = &ev[na];
       e->now = now; e->queued = t->top; e->finished = t->finished;
-      e->busy_running = (uint32_t)t->busy_gpus | ((uint32_t)t->running << 16);
-      e->mem_busy_bytes = t->mem_busy; e->busy_nodes = t->ever; e->qrow = qidx;
+      e->busy_gpus = (uint16_t)t->busy_gpus; e->running = (uint16_t)t->running;
+      e->mem_busy_bytes = t->mem_busy;
       na += 1;
     }
     t->delta = now;
@@ -306,12 +305,12 @@ int tight2_run(tight2 *t, int64_t max_ticks, int64_t capA, int64_t capB, gs_evro
   }
   if (t->hvalid) { t->stack_job[t->scount] = t->hjob; t->stack_arr[t->scount] = t->harr; t->scount += 1; t->hvalid = 0; }
   for (int i = 0; i < t->scount; ++i) { t->rec2[t->stack_job[i]].start = -1; t->rec2[t->stack_job[i]].run_ticks = 0; }
-  *nev_out = na; *nq_out = nb;
+  *nev_out = na; *nq_out = nb; *nne_out = nne;
   return t->status;
 }
 
-void tight2_info(const tight2 *t, gs_window_info *w, int64_t nev, int64_t nq, int64_t *events, int64_t *evals, int32_t *done) {
-  w->row_first = t->row_first; w->ticks = t->delta; w->ev_rows = nev; w->q_rows = nq; w->spans_used = t->span_used;
+void tight2_info(const tight2 *t, gs_window_info *w, int64_t nev, int64_t nq, int64_t nne, int64_t *events, int64_t *evals, int32_t *done) {
+  w->row_first = t->row_first; w->ticks = t->delta; w->ev_rows = nev; w->q_rows = nq; w->node_events = nne; w->spans_used = t->span_used;
   w->admitted = t->p; w->finished = t->finished; w->n = t->n;
   *events = t->p + 2 * (int64_t)t->finished + t->running; *evals = t->evals; *done = t->done;
 }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert "gs_run" in names and "gs_place_batch" in names and "gs_horus_run" in names and len(names) >= 22
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.gs_abi_version() == 3
+    assert lib.gs_abi_version() == 4
 
 
 def test_library_is_built_for_sm_100a():

@@ -448,9 +448,9 @@ def test_compact_records_decode_to_the_same_rows():
                 parts_dev, parts_host = [], []
                 while True:
                     eng.run(0, cap)
-                    w, ev, qr, jobs, dur, order, pool = eng.fetch_compact(0)
-                    assert len(ev) >= 1 and (cap == 0 or (len(ev) <= cap and len(qr) <= qcap))
-                    parts_host.append(lm.expand_rows(ev, qr, w.row_first, w.ticks, m, g))
+                    w, ev, qr, ne, jobs, dur, order, pool = eng.fetch_compact(0)
+                    assert len(ev) >= 1 and len(ne) >= 1 and (cap == 0 or (len(ev) <= cap and len(qr) <= qcap))
+                    parts_host.append(lm.expand_rows(ev, qr, ne, w.row_first, w.ticks, m, g))
                     parts_dev.append(eng.fetch_rows(0, w.row_first, w.ticks - w.row_first))
                     if eng.stats(0).done:
                         break
@@ -471,7 +471,7 @@ def test_async_load_and_fetch_from_pinned_buffers():
     import oracle
     from gpuschedule_b200 import capi, ingest, tracegen
     from gpuschedule_b200 import log_manager as lm
-    from gpuschedule_b200.log_manager import CSPAN_DTYPE, EVROW_DTYPE, JOBRUN_DTYPE, QROW_DTYPE
+    from gpuschedule_b200.log_manager import CSPAN_DTYPE, EVROW_DTYPE, JOBRUN_DTYPE, NODEEV_DTYPE, QROW_DTYPE
     cluster = capi.make_cluster(num_switch=2, num_node_p_switch=12)
     tables = [ingest.table_from_columns(tracegen.synth_columns(900 + 10 * i, seed=60 + i, rate=0.8)) for i in range(12)]
     refs = [oracle.run_fifo(cluster, t) for t in tables]
@@ -491,18 +491,19 @@ def test_async_load_and_fetch_from_pinned_buffers():
             outs = []
             for i, w in enumerate(wins):
                 assert eng.result_layout(i).span_bytes == 8          # 8 GPUs per node: the 8-byte span records
-                pb = capi.PinnedBuffer(32 * (w.ev_rows + w.q_rows) + 4 * w.n + 4 * w.finished + 8 * w.spans_used + 64)
+                pb = capi.PinnedBuffer(24 * (w.ev_rows + w.q_rows) + 8 * w.node_events + 4 * w.n + 4 * w.finished + 8 * w.spans_used + 64)
                 o = 0
-                ev = pb.view(EVROW_DTYPE, w.ev_rows, o); o += 32 * w.ev_rows
-                qr = pb.view(QROW_DTYPE, w.q_rows, o); o += 32 * w.q_rows
+                ev = pb.view(EVROW_DTYPE, w.ev_rows, o); o += 24 * w.ev_rows
+                qr = pb.view(QROW_DTYPE, w.q_rows, o); o += 24 * w.q_rows
+                ne = pb.view(NODEEV_DTYPE, w.node_events, o); o += 8 * w.node_events
                 jobs = pb.view(JOBRUN_DTYPE, w.n, o); o += 4 * w.n
                 sp = pb.view(CSPAN_DTYPE, w.spans_used, o); o += 8 * w.spans_used
                 order = pb.view(np.int32, w.finished, o)
-                eng.fetch_compact_into(i, ev, qr, jobs, None, order, sp)
-                outs.append((pb, ev, qr, jobs, order, sp))
+                eng.fetch_compact_into(i, ev, qr, ne, jobs, None, order, sp)
+                outs.append((pb, ev, qr, ne, jobs, order, sp))
             eng.sync()
-            for i, (w, (pb, ev, qr, jobs, order, sp)) in enumerate(zip(wins, outs)):
-                rows = lm.expand_rows(ev, qr, w.row_first, w.ticks, 24, 8)
+            for i, (w, (pb, ev, qr, ne, jobs, order, sp)) in enumerate(zip(wins, outs)):
+                rows = lm.expand_rows(ev, qr, ne, w.row_first, w.ticks, 24, 8)
                 assert rows.tobytes() == refs[i].rows.tobytes(), (step, i)
                 assert np.array_equal(order, refs[i].finish_order)
                 assert lm.expand_jobs(jobs, int(w.admitted), tables[i].duration).tobytes() == refs[i].recs.tobytes()
@@ -585,8 +586,8 @@ def test_batch_upload_and_strided_read_back():
                 eng.sync()
                 for i, t in enumerate(tables):
                     w = eng.window(i)
-                    ev, qr, jobs, order, pool = capi.Engine.result_views(out, pitch, i, lay[i], w)
-                    rows = lm.expand_rows(ev, qr, w.row_first, w.ticks, 24, 8)
+                    ev, qr, ne, jobs, order, pool = capi.Engine.result_views(out, pitch, i, lay[i], w)
+                    rows = lm.expand_rows(ev, qr, ne, w.row_first, w.ticks, 24, 8)
                     assert eng.stats(i).done == 1 and rows.tobytes() == refs[i].rows.tobytes(), (use_async, step, i)
                     assert lm.expand_jobs(jobs, int(w.admitted), t.duration).tobytes() == refs[i].recs.tobytes()
                     assert np.array_equal(order, refs[i].finish_order)
