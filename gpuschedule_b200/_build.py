@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "gsched.cu")
 SRC_HORUS = os.path.join(HERE, "csrc", "gs_horus.cu")          # utilisation-aware placement engine (gsched_horus.h)
+SRC_LOGCOL = os.path.join(HERE, "csrc", "gs_logcol.cpp")       # host side of the log writer (sampled cluster.csv column)
 OUT = os.path.join(HERE, "libgsched.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-I", os.path.join(REPO, "include")]
@@ -23,12 +24,12 @@ def nvcc_path():
 
 def build(force=False, verbose=False):
     csrc = os.path.dirname(SRC)
-    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
     deps += [os.path.join(REPO, "include", "gsched.h"), os.path.join(REPO, "include", "gsched_horus.h")]
     if (not force and os.path.exists(OUT)
             and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps)):
         return OUT
-    cmd = [nvcc_path()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, SRC_HORUS]
+    cmd = [nvcc_path()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, SRC_HORUS, SRC_LOGCOL]
     subprocess.run(cmd, check=True, cwd=REPO)
     return OUT
 

@@ -233,6 +233,13 @@ def load_library():
     lib.gs_comm_set_min_runnable.argtypes = [C.c_void_p, C.c_int]
     for name in ("gs_comm_prepare", "gs_comm_init", "gs_comm_stats", "gs_comm_set_min_runnable"):
         getattr(lib, name).restype = C.c_int
+    lib.gs_logcol_open.argtypes = [C.c_int64, C.c_int32, C.c_int64, i64p, i64p, i32p, i32p]
+    lib.gs_logcol_open.restype = C.c_void_p
+    lib.gs_logcol_close.argtypes = [C.c_void_p]
+    lib.gs_logcol_close.restype = None
+    lib.gs_logcol_counts.argtypes = [C.c_void_p, i64p]
+    lib.gs_logcol_rows.argtypes = [C.c_void_p, C.c_int64, f64p, f64p, f64p, C.c_int64, f64p, i32p]
+    lib.gs_logcol_counts.restype = lib.gs_logcol_rows.restype = C.c_int
     lib.gs_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.gs_host_free.argtypes = [C.c_void_p]
     for name in ("gs_reset", "gs_host_alloc", "gs_host_free", "gs_create", "gs_config_sim", "gs_load_trace", "gs_run", "gs_stats",
@@ -247,6 +254,63 @@ def load_library():
         raise GsError(f"{path} is not the nvcc sm_100a build (there is no CPU path)")
     _lib = lib
     return lib
+
+
+def warm_device_async(device=0):
+    """Start creating the CUDA context of `device` on a helper thread (the driver call releases the GIL), so that a command
+    line can parse its trace meanwhile.  Nothing is reported from here: the Engine constructor that follows raises whatever
+    is wrong with the device or the library."""
+    import threading
+
+    def work():
+        try:
+            with Engine(device=device, nsims=1):
+                pass
+        except Exception:                                   # noqa: BLE001 - see the docstring
+            pass
+    t = threading.Thread(target=work, name="gs-warm-device", daemon=True)
+    t.start()
+    return t
+
+
+class LogColumn:
+    """Host walk of the sampled cluster.csv column (include/gsched.h gs_logcol_*): holdings in, per-row sums out."""
+
+    def __init__(self, n_rows, width, first, last, key, job):
+        self.lib = load_library()
+        self.n_rows = int(n_rows)
+        self._keep = (first, last, key, job)
+        self.h = self.lib.gs_logcol_open(self.n_rows, int(width), len(first), _ptr(first, C.c_int64), _ptr(last, C.c_int64),
+                                         _ptr(key, C.c_int32), _ptr(job, C.c_int32))
+        if not self.h:
+            raise GsError("gs_logcol_open: holdings must be sorted by first row, with device keys inside the cluster")
+        self.row = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.h:
+            self.lib.gs_logcol_close(self.h)
+            self.h = None
+
+    def counts(self):
+        out = np.zeros(self.n_rows, dtype=np.int64)
+        rc = self.lib.gs_logcol_counts(self.h, _ptr(out, C.c_int64))
+        if rc:
+            raise GsError("gs_logcol_counts", rc)
+        return out
+
+    def rows(self, r_end, loc, scale, z):
+        k = int(r_end) - self.row
+        acc, nun = np.zeros(k, dtype=np.float64), np.zeros(k, dtype=np.int32)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        rc = self.lib.gs_logcol_rows(self.h, int(r_end), _ptr(loc, C.c_double), _ptr(scale, C.c_double), _ptr(z, C.c_double), len(z),
+                                     _ptr(acc, C.c_double), _ptr(nun, C.c_int32))
+        if rc:
+            raise GsError("gs_logcol_rows: the values passed are not the ones these rows consume", rc)
+        self.row = int(r_end)
+        return acc, nun
 
 
 class GsHorusParams(C.Structure):

@@ -111,6 +111,7 @@ def define_simulator_flags():
     DEFINE_boolean("flush_stdout", True, "accepted for CLI compatibility")
     # engine-side additions (absent from the reference; defaults keep its behaviour)
     DEFINE_integer("device", 0, "CUDA device ordinal")
+    DEFINE_string("trace_cache", "log/.trace_cache", "directory for parsed traces (sweeps replay one trace many times); empty: always parse")
     DEFINE_string("queue_limit", "3600,7200,18000", "dlas thresholds, comma separated")
     DEFINE_float("gittins_delta", 3250.0, "gittins service quantum")
     DEFINE_version("0.1")

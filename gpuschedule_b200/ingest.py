@@ -161,6 +161,59 @@ def table_from_frame(df, scale_factor=0.5) -> JobTable:
     return t
 
 
+CACHE_FORMAT = 1
+_ARRAY_FIELDS = ("arrive_tick", "submit", "gpus", "gpu_per_task", "duration", "mem_bytes", "util_avg", "util_max")
+_OPTIONAL_FIELDS = ("model_mb", "iterations", "ps_count")
+
+
+def _cache_path(file_path, scale_factor, cache_dir):
+    """One file per (trace file contents as far as stat() tells, scale factor, pandas / numpy versions: the row order is
+    whatever THOSE versions' sort produces, see the module docstring)."""
+    import hashlib
+    from importlib import metadata
+    st = os.stat(file_path)
+    key = "|".join([os.path.abspath(file_path), str(st.st_size), str(st.st_mtime_ns), repr(float(scale_factor)),
+                    metadata.version("pandas"), metadata.version("numpy"), str(CACHE_FORMAT)])
+    return os.path.join(cache_dir, hashlib.sha1(key.encode()).hexdigest() + ".npz")
+
+
+def load_table(file_path, scale_factor=0.5, cache_dir=None) -> JobTable:
+    """The prepared JobTable of a trace file.  Parsing goes through pandas (JobTraceReader) -- whose import alone costs a
+    second -- so a sweep that replays one trace many times (execute.py) keeps the parsed table under `cache_dir` and
+    later runs read that instead; any change of the file (size, mtime), of the scale factor or of the pandas / numpy
+    versions misses.  cache_dir=None: no cache."""
+    path = None
+    if cache_dir is not None and os.path.exists(file_path):
+        try:
+            path = _cache_path(file_path, scale_factor, cache_dir)
+            if os.path.exists(path):
+                with np.load(path, allow_pickle=False) as z:
+                    t = JobTable(n=int(z["n"]), label=z["label"].tolist(), num_gpu_text=z["num_gpu_text"].tolist(),
+                                 **{k: z[k] for k in _ARRAY_FIELDS})
+                    for k in _OPTIONAL_FIELDS:
+                        if k in z.files:
+                            setattr(t, k, z[k])
+                    if "mem_avg_mib" in z.files:
+                        t.extra["mem_avg_mib"] = z["mem_avg_mib"]
+                return t
+        except Exception as exc:                            # noqa: BLE001 - a bad cache file is a miss, never an error
+            logging.warning("trace cache %s unusable (%s): parsing the trace", path, exc)
+    t = JobTraceReader(file_path).prepare_jobs().table(scale_factor)
+    if path is not None:
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            arrays = {k: getattr(t, k) for k in _ARRAY_FIELDS}
+            arrays.update({k: getattr(t, k) for k in _OPTIONAL_FIELDS if getattr(t, k) is not None})
+            if "mem_avg_mib" in t.extra:
+                arrays["mem_avg_mib"] = t.extra["mem_avg_mib"]
+            tmp = path + ".%d.tmp.npz" % os.getpid()
+            np.savez(tmp, n=np.int64(t.n), label=np.array(t.label, dtype=str), num_gpu_text=np.array(t.num_gpu_text, dtype=str), **arrays)
+            os.replace(tmp, path)
+        except OSError as exc:
+            logging.warning("trace cache not written (%s)", exc)
+    return t
+
+
 def table_from_columns(cols: dict, scale_factor=0.5) -> JobTable:
     """Synthetic columns (tracegen.synth_columns) -> table through the same
     pandas path as a CSV on disk, without touching the filesystem."""

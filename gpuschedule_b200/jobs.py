@@ -57,15 +57,23 @@ class JobsManager:
         if flags.schedule not in SUPPORTED_SCHEDULES:
             # the reference dies at the first insert (jobs_manager.py:62)
             raise NotImplementedError(flags.schedule)
-        self.job_generator = ingest.JobTraceReader(flags.trace_file)
-        self.job_generator.prepare_jobs()
         self.replay_trace = True
-        self.table = self.job_generator.table(scale_factor=0.5)      # schedule.py:187
+        self._reader = None
+        self.table = ingest.load_table(flags.trace_file, 0.5,        # scale factor: schedule.py:187
+                                       getattr(flags, "trace_cache", None) or None)
         self.running_jobs = {}
         self.finished_jobs = {}
 
         self.queue = []                              # queue 0 of the reference, head = index 0
         self._next_row = 0
+
+    @property
+    def job_generator(self):
+        """the reference's reader object (jobs_manager.py:16-18); built on first use -- a run served from the parsed-trace
+        cache never needs the frame"""
+        if self._reader is None:
+            self._reader = ingest.JobTraceReader(self.flags.trace_file).prepare_jobs()
+        return self._reader
 
     def remaining_jobs(self, delta_time=None):
         return self.table.n - self._next_row

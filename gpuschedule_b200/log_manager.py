@@ -185,11 +185,31 @@ def memory_column(rows, total_cap_mib):
     return [repr(v) if b else "0.0" for v, b in zip(vals.tolist(), busy.tolist())]
 
 
-def cluster_lines(rows, util_text, total_cap_mib):
+def int_text(col):
+    """str() of every entry of an integer column.  The statistics columns are counters with a small range, so the text
+    of each distinct value is made once and gathered (numpy's int -> str conversion costs ~10x a gather)."""
+    col = np.asarray(col)
+    if len(col) == 0:
+        return []
+    lo, hi = int(col.min()), int(col.max())
+    if hi - lo > 4 * len(col) + 4096:
+        return col.astype(str).tolist()
+    table = np.array([str(v) for v in range(lo, hi + 1)], dtype=object)
+    return table[col.astype(np.int64) - lo].tolist()
+
+
+def cluster_static_columns(rows, total_cap_mib):
+    """Text of every cluster.csv column but the sampled one: (five leading columns, memory, avg / median / max pending,
+    three trailing columns).  Independent of the utilisation column, so a caller can prepare it meanwhile."""
     avg_t, med_t, max_t = pending_columns(rows)
     mem_t = memory_column(rows, total_cap_mib)
-    cols = [rows[k].astype(str).tolist() for k in ("now", "idle_nodes", "busy_nodes", "busy_gpus", "idle_gpus")]
-    tail = [rows[k].astype(str).tolist() for k in ("running", "queued", "finished")]
+    cols = [int_text(rows[k]) for k in ("now", "idle_nodes", "busy_nodes", "busy_gpus", "idle_gpus")]
+    tail = [int_text(rows[k]) for k in ("running", "queued", "finished")]
+    return cols, mem_t, (avg_t, med_t, max_t), tail
+
+
+def cluster_lines(rows, util_text, total_cap_mib, static=None):
+    cols, mem_t, (avg_t, med_t, max_t), tail = static if static is not None else cluster_static_columns(rows, total_cap_mib)
     return [",".join(t) for t in zip(cols[0], cols[1], cols[2], cols[3], cols[4], util_text, mem_t, avg_t, med_t, max_t,
                                      tail[0], tail[1], tail[2])]
 
@@ -200,10 +220,10 @@ def job_lines(table, recs, finish_order):
     dur = recs["duration"][order]
     actual = np.maximum(table.duration[order], dur)              # Job.get_duration job.py:206-210
     label, gtext = table.label, table.num_gpu_text
-    return [",".join((label[j], gtext[j], str(sb), str(st), str(en), repr(d), repr(a), str(jc), str(pr)))
-            for j, sb, st, en, d, a, jc, pr in zip(order.tolist(), table.submit[order].tolist(), recs["start"][order].tolist(),
-                                                   recs["end"][order].tolist(), dur.tolist(), actual.tolist(),
-                                                   recs["jct"][order].tolist(), recs["preempt"][order].tolist())]
+    return [",".join((label[j], gtext[j], sb, st, en, repr(d), repr(a), jc, pr))
+            for j, sb, st, en, d, a, jc, pr in zip(order.tolist(), int_text(table.submit[order]), int_text(recs["start"][order]),
+                                                   int_text(recs["end"][order]), dur.tolist(), actual.tolist(),
+                                                   int_text(recs["jct"][order]), int_text(recs["preempt"][order]))]
 
 
 def horus_job_lines(table, recs, finish_order):
@@ -267,8 +287,8 @@ class LogManager:
         time.sleep(1)
 
     # ---- batch API (engine)
-    def write_cluster_rows(self, rows, util_text, total_cap_mib):
-        lines = cluster_lines(rows, util_text, total_cap_mib)
+    def write_cluster_rows(self, rows, util_text, total_cap_mib, static=None):
+        lines = cluster_lines(rows, util_text, total_cap_mib, static)
         with open(self.log_cluster, "a", newline="") as f:
             if lines:
                 f.write(EOL.join(lines) + EOL)
@@ -278,9 +298,9 @@ class LogManager:
         with open(self.log_job, "a", newline="") as f:
             f.write(EOL.join(horus_job_lines(table, recs, finish_order)) + EOL)
 
-    def write_job_rows(self, table, recs, finish_order):
+    def write_job_rows(self, table, recs, finish_order, lines=None):
         assert len(finish_order) > 0, ValueError("No finished jobs")
-        lines = job_lines(table, recs, finish_order)
+        lines = job_lines(table, recs, finish_order) if lines is None else lines
         with open(self.log_job, "a", newline="") as f:
             f.write(EOL.join(lines) + EOL)
 

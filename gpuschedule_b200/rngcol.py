@@ -7,13 +7,12 @@ divides by the GPU count (/root/reference/infra/device.py:48-54,
 /root/reference/core/scheduling/schedule.py:103-120).  The draws come from
 numpy's global legacy MT19937 stream, which is sequential by construction, so
 this column stays on the host.  The engine supplies where every
-job ran (gs_span records) and when (start/end); this module rebuilds the
-per-tick ordered device list and replays the stream with ONE vectorised call
-per chunk of rows, which consumes the stream exactly like the per-device
-size=1 calls do.  Everything is vectorised numpy: a (rows x devices) owner grid
-per chunk is a running sum of +owner / -owner marks at interval starts / stops, the
-sequential per-row accumulation runs column-wise, and the text is produced with
-numpy's own dragon4 formatter.
+job ran (gs_span records) and when (start/end); this module turns them into
+(job, device, first row, last row) holdings, draws the standard-normal values
+from numpy with ONE vectorised call per block of rows -- which consumes the
+stream exactly like the per-device size=1 calls do -- and lets the library's
+host helper (include/gsched.h gs_logcol_*) walk the ticks and busy devices in
+the reference's order.  The text is produced with numpy's own dragon4 formatter.
 """
 from __future__ import annotations
 
@@ -33,100 +32,68 @@ def _holdings(recs, span_off, spans, gpus_per_node):
     return span_job[si], spans["node"][si].astype(np.int64) * gpus_per_node + dev.astype(np.int64)
 
 
-def busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans, chunk_rows=2048):
-    """Yield (row_counts, jobs_in_draw_order) per chunk of rows.
+def _intervals(n_rows, gpus_per_node, recs, span_off, spans):
+    """(first row, last row, device key, job) of every (job, device) holding, sorted by first row.
 
     Row r (0-based) is the statistics row written with delta == r + 1; job j is
     counted there iff start_j <= r and (end_j < 0 or end_j > r + 1).
     """
-    width = n_nodes * gpus_per_node
     hold_job, hold_key = _holdings(recs, span_off, spans, gpus_per_node)
     start = recs["start"][hold_job].astype(np.int64)
     end = recs["end"][hold_job]
-    keep = start >= 0
-    hold_job, hold_key, start, end = hold_job[keep], hold_key[keep], start[keep], end[keep]
     first = start                                                   # first row counted
     last = np.where(end < 0, n_rows - 1, end.astype(np.int64) - 2)  # last row counted
-    live = last >= first
-    hold_job, hold_key, first, last = hold_job[live], hold_key[live], first[live], last[live]
+    live = (start >= 0) & (last >= first) & (first < n_rows)
+    hold_job, hold_key, first, last = hold_job[live], hold_key[live], first[live], np.minimum(last[live], n_rows - 1)
     order = np.argsort(first, kind="stable")
-    hold_job, hold_key, first, last = hold_job[order], hold_key[order], first[order], last[order]
-    lo_ptr = 0
-    active = np.zeros(0, dtype=np.int64)                            # holdings still open
-    for r0 in range(0, n_rows, chunk_rows):
-        r1 = min(n_rows, r0 + chunk_rows)
-        hi_ptr = int(np.searchsorted(first, r1, side="left"))
-        cand = np.concatenate([active, np.arange(lo_ptr, hi_ptr, dtype=np.int64)])
-        lo_ptr = hi_ptr
-        cand = cand[last[cand] >= r0]
-        rows_n = r1 - r0
-        # +(job+1) where a holding starts (or continues into the chunk), -(job+1) on the first row after it;
-        # devices host one job at a time, so a running sum along each device's row is the owner (+1), 0 = idle.
-        # The grid is kept device-major so that the running sum walks contiguous memory, then transposed once.
-        ukeys, kidx = np.unique(hold_key[cand], return_inverse=True)    # only devices that host something in this chunk
-        marks = np.zeros((len(ukeys), rows_n + 1), dtype=np.int32)
-        a = np.maximum(first[cand], r0) - r0
-        b = np.minimum(last[cand], r1 - 1) - r0 + 1                 # first row after the holding (<= rows_n)
-        val = (hold_job[cand] + 1).astype(np.int32)
-        np.add.at(marks, (kidx, a), val)
-        np.add.at(marks, (kidx, b), -val)
-        np.cumsum(marks, axis=1, out=marks)
-        filled = np.ascontiguousarray(marks[:, :rows_n].T)            # (rows, devices in id order)
-        busy = filled > 0
-        active = cand[last[cand] >= r1]
-        yield busy.sum(axis=1), filled[busy].astype(np.int64) - 1
+    return (np.ascontiguousarray(first[order]), np.ascontiguousarray(last[order]),
+            np.ascontiguousarray(hold_key[order], dtype=np.int32), np.ascontiguousarray(hold_job[order], dtype=np.int32))
 
 
 def _format_bracketed(values):
     """str(np.array([v])) for every v, fast: numpy prints a 1-element float64 array with the dragon4
-    positional formatter (precision 8, unique, trim '.') unless the value calls for exponent form."""
-    out = []
-    fmt = np.format_float_positional
-    for v in values:
-        if v != 0.0 and (v < 1e-4 or v >= 1e8):
-            out.append(str(np.array([v])))                          # exponent notation: leave it to numpy
-        else:
-            out.append("[" + fmt(v, precision=8, unique=True, fractional=True, trim=".") + "]")
-    return out
+    positional formatter (precision 8, unique, trim '.') unless the value calls for exponent form.  In the positional
+    range that text is the value correctly rounded to 8 decimals with the trailing zeros removed -- what C's "%.8f"
+    prints (both round the exact binary value, ties to even) -- because a shortest representation of 8 decimals or
+    fewer is itself a multiple of 1e-8 within half an ulp of the value (tests/test_abi_and_host.py compares the two
+    on millions of values, ties included)."""
+    return [("[" + ("%.8f" % v).rstrip("0") + "]") if (1e-4 <= v < 1e8 or v == 0.0) else str(np.array([v]))   # exponent notation: leave it to numpy
+            for v in (values.tolist() if isinstance(values, np.ndarray) else values)]
+
+
+DRAWS_PER_CALL = 1 << 19        # standard-normal values drawn at a time: blocks that stay in the cache (fresh 100 MB arrays cost more in page faults than the draw itself)
 
 
 def utilization_text(n_rows, n_nodes, gpus_per_node, table, recs, span_off, spans, rng=None):
     """Text of the avg_gpu_utilization column for rows 0..n_rows-1."""
     # numpy's legacy normal(loc, scale) is loc + scale * gauss() (legacy-distributions.c: legacy_normal); drawing the
-    # standard values and applying the affine map in numpy is the same two roundings and 3x faster than broadcasting
-    # loc / scale through the generator (bit equality checked on 21 M samples, tests/test_oracle_golden.py pins the bytes)
+    # standard values here and applying the affine map in gs_logcol_rows is the same two roundings (bit equality checked
+    # on 21 M samples, tests/test_oracle_golden.py pins the bytes).  ONE vectorised draw per block of rows consumes the
+    # stream exactly like the per-device size=1 calls do; the walk over ticks and busy devices is the library's
+    # (csrc/gs_logcol.cpp), the text is numpy's own dragon4 formatter.
+    from . import capi
     std_normal = np.random.standard_normal if rng is None else rng.standard_normal
     total = n_nodes * gpus_per_node
+    loc = np.ascontiguousarray(table.util_avg, dtype=np.float64)
+    scale = np.ascontiguousarray((table.util_max - table.util_avg) / 2, dtype=np.float64)
+    first, last, key, job = _intervals(n_rows, gpus_per_node, recs, span_off, spans)
     out = []
-    loc_all = table.util_avg
-    scale_all = (table.util_max - table.util_avg) / 2
-    for counts, jobs in busy_job_stream(n_rows, n_nodes, gpus_per_node, recs, span_off, spans):
-        if len(jobs):
-            draw = loc_all[jobs] + scale_all[jobs] * std_normal(len(jobs))
-        else:
-            draw = np.zeros(0)
-        clipped = draw >= 100.0          # min(100, x) returns the int 100 unless x < 100
-        vals = np.where(clipped, 100.0, draw)
-        off = np.zeros(len(counts) + 1, dtype=np.int64)
-        np.cumsum(counts, out=off[1:])
-        # sequential per-row accumulation (Python float additions, left to right): the draws of a chunk go into a
-        # (rows x widest row) matrix padded with 0.0 -- x + 0.0 == x -- and are added column by column
-        acc = np.zeros(len(counts), dtype=np.float64)
-        if len(vals):
-            row_of = np.repeat(np.arange(len(counts)), counts)
-            pos_of = np.arange(len(vals)) - off[row_of]
-            mat = np.zeros((int(counts.max()), len(counts)), dtype=np.float64)
-            mat[pos_of, row_of] = vals
-            for k in range(mat.shape[0]):
-                acc += mat[k]
-        csum = np.concatenate([[0], np.cumsum(~clipped)])
-        n_arr = csum[off[1:]] - csum[off[:-1]]                      # un-clipped draws per row (numpy arrays)
-        frac = acc / total
-        brack = _format_bracketed(frac)
-        # no busy device: 0 / n -> float 0.0;  some un-clipped draw: numpy 1-element array;
-        # every draw clipped at the int 100: plain Python numbers
-        out.extend("0.0" if c == 0 else (bk if na > 0 else repr(float(int(ac) / total)))
-                   for c, na, bk, ac in zip(counts.tolist(), n_arr.tolist(), brack, acc.tolist()))
+    with capi.LogColumn(n_rows, total, first, last, key, job) as col:
+        counts = col.counts()
+        ends = np.cumsum(counts)
+        r0 = 0
+        while r0 < n_rows:
+            base = int(ends[r0 - 1]) if r0 else 0
+            r1 = max(r0 + 1, int(np.searchsorted(ends, base + DRAWS_PER_CALL, side="right")))
+            r1 = min(r1, n_rows)
+            z = std_normal(int(ends[r1 - 1]) - base)
+            acc, n_arr = col.rows(r1, loc, scale, z)
+            brack = _format_bracketed(acc / total)
+            # no busy device: 0 / n -> float 0.0;  some un-clipped draw: numpy 1-element array;
+            # every draw clipped at the int 100: plain Python numbers
+            out.extend("0.0" if c == 0 else (bk if na > 0 else repr(float(int(ac) / total)))
+                       for c, na, bk, ac in zip(counts[r0:r1].tolist(), n_arr.tolist(), brack, acc.tolist()))
+            r0 = r1
     return out
 
 

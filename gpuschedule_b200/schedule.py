@@ -96,9 +96,17 @@ class Scheduler:
             self.stats = eng.stats(0)
         m = cluster.num_switch * cluster.num_node_p_switch
         g = cluster.num_gpu_p_node
-        util = rngcol.utilization_text(len(rows), m, g, table, recs, span_off, spans)
-        self.log_manager.write_cluster_rows(rows, util, m * g * cluster.gpu_mem_cap_mib)
+        # the sampled column spends most of its time inside numpy's generator and the library (both release the GIL):
+        # the text of the other columns and of job.csv is prepared meanwhile
+        from concurrent.futures import ThreadPoolExecutor
+        from . import log_manager as lm
+        cap = m * g * cluster.gpu_mem_cap_mib
+        with ThreadPoolExecutor(1) as pool:
+            static = pool.submit(lm.cluster_static_columns, rows, cap)
+            job_text = pool.submit(lm.job_lines, table, recs, order) if len(order) else None
+            util = rngcol.utilization_text(len(rows), m, g, table, recs, span_off, spans)
+            self.log_manager.write_cluster_rows(rows, util, cap, static.result())
         logging.info("Total Time Taken in seconds: %d" % (time.time() - t0))
-        self.log_manager.write_job_rows(table, recs, order)
+        self.log_manager.write_job_rows(table, recs, order, job_text.result() if job_text else None)
         self.rows, self.recs, self.finish_order = rows, recs, order
         return self.stats

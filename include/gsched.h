@@ -379,6 +379,19 @@ int gs_switch_yarn(gs_handle h, int32_t ncl, const gs_switch_cluster *clusters, 
                    double worker_mem, double ps_mem, double p_w_mem,
                    gs_switch_ans *ans, gs_switch_span *spans, int64_t n_spans);
 
+/* ---- host side of the log writer (no device work): the sampled avg_gpu_utilization column of cluster.csv.
+ * The reference draws one np.random.normal per busy device and tick, nodes in id order, devices 0..G-1
+ * (infra/device.py:48-54, core/scheduling/schedule.py:103-120), from numpy's sequential global stream; the caller draws the
+ * standard-normal values from numpy, these entry points consume them in that order.  A holding = one (job, device)
+ * pair counted on rows first..last; holdings are passed sorted by `first`, key = node * G + device.                */
+typedef struct gs_logcol_s *gs_logcol;
+gs_logcol gs_logcol_open(int64_t n_rows, int32_t width, int64_t n_hold, const int64_t *first, const int64_t *last,
+                         const int32_t *key, const int32_t *job);
+void gs_logcol_close(gs_logcol c);
+int gs_logcol_counts(gs_logcol c, int64_t *counts);                  /* values consumed by each row                  */
+int gs_logcol_rows(gs_logcol c, int64_t r_end, const double *loc, const double *scale, const double *z, int64_t n_z,
+                   double *acc, int32_t *unclipped);                 /* rows [current, r_end): sums in draw order     */
+
 /* PS<->worker transfer time for a batch of placed jobs.  task_node holds the
  * node of every task (segments given by task_off), is_ps marks PS tasks.        */
 int gs_net_cost(gs_handle h, const gs_cluster *cluster, int64_t b,

@@ -25,6 +25,8 @@ def main(log_manager):
     from gpuschedule_b200 import jobs as jobs_mod
     from gpuschedule_b200 import schedule as sche
 
+    from gpuschedule_b200 import capi
+    capi.warm_device_async(FLAGS.device)                   # CUDA context creation overlaps the trace ingest
     infrastructure = cluster.Infrastructure(FLAGS)
     log_manager.init(infrastructure)
     jq_manager = jobs_mod.JobQueueManager(FLAGS, FLAGS.trace_file)

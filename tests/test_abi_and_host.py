@@ -131,3 +131,87 @@ def test_log_manager_headers_and_object_api(tmp_path):
     lm.step_cluster(log_manager.LogInfo(3, 0, 0, 6, 0.0, 0.0, 0.0, float("nan"), 0, 0, 0, 0), 1)
     lines = open(tmp_path / "cluster.csv", newline="").read().split("\r\n")
     assert lines[1] == "1,3,0,0,6,0.0,0.0,0.0,nan,0,0,0,0"
+
+
+def test_bracketed_float_text_is_numpy_array_text():
+    """rngcol._format_bracketed prints with C's %.8f; the reference prints str(np.array([v])) (dragon4, precision 8,
+    unique): same text on random values of every magnitude the column takes, short decimals and binary ties."""
+    from gpuschedule_b200 import rngcol
+    rng = np.random.default_rng(5)
+    vals = [0.0, 2.0 ** -9, 3 * 2.0 ** -9, 5 * 2.0 ** -9, 2.0 ** -13, 0.5, 1.0, 100.0, 12345678.0, 1e-5, 3e-7, 1e8, 2.5e9, 99.99999999, 0.000100001]
+    for scale in (1e-3, 0.05, 1.0, 7.0, 100.0, 1e4, 1e7):
+        vals += (rng.random(20000) * scale).tolist() + np.round(rng.random(5000) * scale, 8).tolist() + np.round(rng.random(5000) * scale, 3).tolist()
+        vals += ((rng.integers(1, 1 << 20, 5000) / 1024.0) * scale).tolist()
+    text = rngcol._format_bracketed(np.array(vals))
+    for v, t in zip(vals, text):
+        assert t == str(np.array([v])), (v, t)
+
+
+def test_logcol_walk_matches_a_direct_numpy_walk():
+    """gs_logcol_* (host helper of the log writer) against the definition: per row, busy devices in key order, one value each"""
+    from gpuschedule_b200 import capi
+    rng = np.random.default_rng(11)
+    n_rows, width, njobs = 300, 96, 40
+    loc, scale = rng.random(njobs) * 90 + 5, rng.random(njobs) * 20
+    # holdings that never overlap on a device: consecutive intervals per device
+    first, last, key, job = [], [], [], []
+    for k in range(width):
+        r = int(rng.integers(0, 50))
+        while r < n_rows + 20:
+            ln = int(rng.integers(1, 60))
+            if rng.random() < 0.7:
+                first.append(r); last.append(r + ln - 1); key.append(k); job.append(int(rng.integers(0, njobs)))
+            r += ln + int(rng.integers(0, 3))
+    order = np.argsort(np.array(first), kind="stable")
+    first, last = np.array(first, dtype=np.int64)[order], np.array(last, dtype=np.int64)[order]
+    key, job = np.array(key, dtype=np.int32)[order], np.array(job, dtype=np.int32)[order]
+    owner = np.full((n_rows, width), -1)
+    for f, l, k, j in zip(first, last, key, job):
+        owner[f:min(l, n_rows - 1) + 1, k] = j
+    with capi.LogColumn(n_rows, width, first, last, key, job) as col:
+        counts = col.counts()
+        assert np.array_equal(counts, (owner >= 0).sum(axis=1))
+        z = rng.standard_normal(int(counts.sum()))
+        half = n_rows // 3
+        a1, u1 = col.rows(half, loc, scale, z[:int(counts[:half].sum())])
+        a2, u2 = col.rows(n_rows, loc, scale, z[int(counts[:half].sum()):])
+    acc, unc = np.concatenate([a1, a2]), np.concatenate([u1, u2])
+    p = 0
+    for r in range(n_rows):
+        a, nu = 0.0, 0
+        for k in range(width):
+            j = owner[r, k]
+            if j < 0:
+                continue
+            x = float(loc[j]) + float(scale[j]) * float(z[p]); p += 1
+            if x >= 100.0:
+                a += 100.0
+            else:
+                a += x; nu += 1
+        assert a == acc[r] and nu == unc[r], r
+    with pytest.raises(capi.GsError):                       # unsorted holdings are refused
+        capi.LogColumn(n_rows, width, first[::-1].copy(), last[::-1].copy(), key, job)
+
+
+def test_parsed_trace_cache_round_trip_and_invalidation(tmp_path):
+    import time as _time
+    from gpuschedule_b200 import ingest, tracegen
+    p = str(tmp_path / "t.csv")
+    cache = str(tmp_path / "cache")
+    tracegen.write_trace(p, 3000, seed=3, rate=0.5)
+    a = ingest.load_table(p, 0.5, cache)
+    assert len(os.listdir(cache)) == 1
+    b = ingest.load_table(p, 0.5, cache)                    # served from the cache
+    plain = ingest.JobTraceReader(p).prepare_jobs().table(0.5)
+    for t in (a, b):
+        for k in ingest._ARRAY_FIELDS:
+            assert getattr(t, k).dtype == getattr(plain, k).dtype and getattr(t, k).tobytes() == getattr(plain, k).tobytes(), k
+        assert t.label == plain.label and t.num_gpu_text == plain.num_gpu_text and t.n == plain.n
+        assert t.extra["mem_avg_mib"].tobytes() == plain.extra["mem_avg_mib"].tobytes()
+    ingest.load_table(p, 1.0, cache)                        # another scale factor: another entry
+    assert len(os.listdir(cache)) == 2
+    _time.sleep(0.01)
+    tracegen.write_trace(p, 3001, seed=4, rate=0.5)         # the file changed: a miss, and the new contents
+    c = ingest.load_table(p, 0.5, cache)
+    assert c.n == ingest.JobTraceReader(p).prepare_jobs().table(0.5).n and len(os.listdir(cache)) == 3
+    assert ingest.load_table(p, 0.5, None).n == c.n         # no cache directory: plain parse
