@@ -163,3 +163,16 @@ def test_host_mirror_and_batched_sweep_through_the_c_abi(engine_cls, tmp_path, m
     _, _, _, job_csv, cluster_csv = load_horus(cases[0])
     assert open(tmp_path / "single" / "job.csv", newline="").read() == job_csv
     assert open(tmp_path / "single" / "cluster.csv", newline="").read() == cluster_csv
+
+
+def test_scheme_schedule_matrix_of_make_horus_params():
+    """the same matrix tests/test_gpu_widen_horus.py asserts on the device (algorithm.py:182-187,292-298): yarn is a served
+    placement under the look-ahead schedulers, fifo has no score function (KeyError at algorithm.py:58), unknown names die"""
+    from gpuschedule_b200 import capi
+    yp = capi.make_horus_params("yarn", "horus", 5)
+    assert (yp.placement, yp.schedule, yp.score) == (1, 1, 0)
+    assert capi.make_horus_params("horus", "gandiva", 5).placement == 0
+    assert capi.make_horus_params("gandiva", "gandiva", 5).score == 1
+    for scheme, schedule in (("yarn", "fifo"), ("random", "horus"), ("horus", "sjf")):
+        with pytest.raises(NotImplementedError):
+            capi.make_horus_params(scheme, schedule, 5)
