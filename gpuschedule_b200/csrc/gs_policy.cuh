@@ -743,59 +743,96 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     if (sjf) {
       for (int nd = lane; nd < M; nd += 32) { nidle[nd] = G; nkfree[nd] = K; }
       __syncwarp();
-      for (int i = 0; i < rn; ++i) {
-        const int j = runnable[i];
-        const JobIn jr = jobs[j];
-        PJob r = pj[j];
-        const int hg = jr.gpus, hc = jr.gpc, tasks = hc == 1 ? hg : hg / hc;
+      // The list is walked 32 entries at a time.  Consecutive entries that ask for the same thing (GPUs, GPUs per task,
+      // fits a device) are placed together: identical jobs fill the nodes in id order -- each goes to the first node
+      // that still holds one (single node) or takes the next tasks of the walk (cross node) -- so a run of r of them
+      // is one prefix sum over the node capacities instead of r first-fit scans, and the first `placed` of the run are
+      // the ones that start.  The list is ordered by GPU count, so runs are long.
+      for (int base = 0; base < rn; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < rn;
+        const int j = valid ? runnable[idx] : 0;
+        int hg = 0, hc = 1;
+        long long memb = 0;
+        PJob r;
+        r.status = PST_NONE; r.start = -1; r.resume = 0;
+        if (valid) { const JobIn jr = jobs[j]; hg = jr.gpus; hc = jr.gpc; memb = jr.memb; r = pj[j]; }
+        const bool fit = valid && memb < fit_limit;
+        const unsigned fb = __ballot_sync(FULL, fit);
+        const int phg = __shfl_up_sync(FULL, hg, 1), phc = __shfl_up_sync(FULL, hc, 1);
+        const bool pfit = lane > 0 && ((fb >> (lane - 1)) & 1u);
+        const bool head = valid && (lane == 0 || hg != phg || hc != phc || fit != pfit);
+        unsigned heads = __ballot_sync(FULL, head);
+        const int nvalid = __popc(__ballot_sync(FULL, valid));
         bool ok = false;
-        if (jr.memb < fit_limit) {
-          if (hg <= G) {
-            int found = -1;
-            for (int base = 0; base < M && found < 0; base += 32) {
-              const int nd = base + lane;
-              const bool fit = nd < M && nidle[nd] >= hg && nkfree[nd] >= tasks;
-              const unsigned b = __ballot_sync(FULL, fit);
-              if (b) found = base + __ffs(b) - 1;
-            }
-            if (found >= 0) { ok = true; if (lane == 0) { nidle[found] -= hg; nkfree[found] -= tasks; } }
-          } else {
-            int cum = 0, last_base = -1;
-            for (int base = 0; base < M; base += 32) {
-              const int nd = base + lane;
-              const int c = nd < M ? max(min(nidle[nd] / hc, nkfree[nd]), 0) : 0;
-              cum += __reduce_add_sync(FULL, c);
-              if (cum >= tasks) { last_base = base; break; }
-            }
-            if (last_base >= 0) {
-              ok = true;
-              int rem = tasks;
-              for (int base = 0; base <= last_base; base += 32) {
-                const int nd = base + lane;
-                const int c = nd < M ? max(min(nidle[nd] / hc, nkfree[nd]), 0) : 0;
+        while (heads) {
+          const int s0 = __ffs(heads) - 1;
+          heads &= heads - 1;
+          const int e0 = heads ? __ffs(heads) - 1 : nvalid;
+          const int rcount = e0 - s0;
+          const int rhg = __shfl_sync(FULL, hg, s0), rhc = __shfl_sync(FULL, hc, s0);
+          int placed = 0;
+          if ((fb >> s0) & 1u) {
+            const int rtasks = rhc == 1 ? rhg : rhg / rhc;
+            if (rhg <= G) {
+              // capacity of a node in such jobs = min(idle / gpus, slots / tasks); divisions by the run's constants as
+              // multiplications by 2^32 / d (exact below 65536; larger tables take the plain division)
+              const bool small = G < 65536 && K < 65536;
+              const unsigned mg = (small && rhg > 1) ? 0xffffffffu / (unsigned)rhg + 1u : 0u;
+              const unsigned mt = (small && rtasks > 1) ? 0xffffffffu / (unsigned)rtasks + 1u : 0u;
+              int left = rcount;
+              for (int nb = 0; nb < M && left > 0; nb += 32) {
+                const int nd = nb + lane;
+                int c = 0, ni = 0, nk = 0;
+                if (nd < M) {
+                  ni = nidle[nd]; nk = nkfree[nd];
+                  const int cg = rhg == 1 ? ni : (mg ? (int)__umulhi((unsigned)max(ni, 0), mg) : max(ni, 0) / rhg);
+                  const int ct = rtasks == 1 ? nk : (mt ? (int)__umulhi((unsigned)max(nk, 0), mt) : max(nk, 0) / rtasks);
+                  c = max(min(cg, ct), 0);
+                }
                 const int incl = warp_incl_scan(c, lane);
-                const int take = min(c, max(rem - (incl - c), 0));
-                if (take > 0) { nidle[nd] -= take * hc; nkfree[nd] -= take; }
-                rem -= min(rem, __shfl_sync(FULL, incl, 31));
+                const int take = min(c, max(left - (incl - c), 0));
+                if (take > 0) { nidle[nd] = ni - take * rhg; nkfree[nd] = nk - take * rtasks; }
+                left -= min(left, __shfl_sync(FULL, incl, 31));
+              }
+              placed = rcount - left;
+            } else {
+              // cross node: a job takes `rtasks` tasks from the nodes in id order, each node giving what it holds
+              const long long want = (long long)rcount * rtasks;
+              long long cap = 0;
+              for (int nb = 0; nb < M && cap < want; nb += 32) {
+                const int nd = nb + lane;
+                const int c = nd < M ? max(min(nidle[nd] / rhc, nkfree[nd]), 0) : 0;
+                cap += __reduce_add_sync(FULL, c);
+              }
+              placed = (int)min((long long)rcount, cap / rtasks);
+              long long todo = (long long)placed * rtasks;
+              for (int nb = 0; nb < M && todo > 0; nb += 32) {
+                const int nd = nb + lane;
+                const int c = nd < M ? max(min(nidle[nd] / rhc, nkfree[nd]), 0) : 0;
+                const int incl = warp_incl_scan(c, lane);
+                const long long before = todo - (long long)(incl - c);
+                const int take = before > 0 ? (int)min((long long)c, before) : 0;
+                if (take > 0) { nidle[nd] -= take * rhc; nkfree[nd] -= take; }
+                const int tot = __shfl_sync(FULL, incl, 31);
+                todo -= min(todo, (long long)tot);
               }
             }
+            __syncwarp();          // lanes updated different nodes
           }
-          __syncwarp();
+          if (lane >= s0 && lane < e0) ok = (lane - s0) < placed;
         }
-        if (ok) {
-          busy += hg;
-          mem_busy += (long long)hg * (jr.memb < cap_bytes ? jr.memb : cap_bytes);
-          if (r.status == PST_PENDING) {
-            r.status = PST_RUNNING; r.resume += 1; if (r.start < 0) r.start = event_time;
-            if (lane == 0) pj[j] = r;
-            events += 1;
-          } else if (r.start < 0) { r.start = event_time; if (lane == 0) pj[j] = r; }
-        } else if (r.status == PST_RUNNING) {
-          r.status = PST_PENDING;
-          if (lane == 0) pj[j] = r;
-          events += 1;
-        }
-        __syncwarp();
+        const bool flip_run = valid && ok && r.status == PST_PENDING;
+        const bool flip_pre = valid && !ok && r.status == PST_RUNNING;
+        if (flip_run) { r.status = PST_RUNNING; r.resume += 1; if (r.start < 0) r.start = event_time; pj[j] = r; }
+        else if (valid && ok && r.start < 0) { r.start = event_time; pj[j] = r; }
+        if (flip_pre) { r.status = PST_PENDING; pj[j] = r; }
+        events += __popc(__ballot_sync(FULL, flip_run)) + __popc(__ballot_sync(FULL, flip_pre));
+        busy += __reduce_add_sync(FULL, ok ? hg : 0);
+        long long mc = ok ? (long long)hg * (memb < cap_bytes ? memb : cap_bytes) : 0;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mc += __shfl_xor_sync(FULL, mc, o);
+        mem_busy += mc;
       }
     } else {
       int free_gpu = total_gpus;

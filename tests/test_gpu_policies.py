@@ -145,3 +145,30 @@ def test_policy_engine_matches_reference_loop_fixtures(case, engine):
     rows, recs, order, st = _run(cluster, pol, table, engine=engine)
     assert st.done == 1
     check_against_expected(table, SimpleNamespace(finish_order=order, recs=recs, rows=rows, ticks=st.ticks, events=st.events), exp)
+
+
+@pytest.mark.parametrize("ckw,rate,seed", [(dict(num_switch=2, num_node_p_switch=20, num_gpu_p_node=8), 6.0, 21),
+                                           (dict(num_switch=1, num_node_p_switch=5, num_gpu_p_node=4), 3.0, 22),
+                                           (dict(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8, num_cpu_p_node=16), 8.0, 23)])
+def test_sjf_long_lists_mixed_tasks_and_oversize_jobs(ckw, rate, seed):
+    """sjf places runs of identical list entries with one walk over the nodes: lists of hundreds of entries (several
+    chunks, runs crossing chunk borders), 1 / 2 / 4 GPUs per task mixed inside one GPU count, jobs too large for a
+    device in the middle of runs, cross-node jobs, a slot-bound cluster (16 cpus per node)"""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, tracegen
+    cluster = capi.make_cluster(**ckw)
+    cols = tracegen.synth_columns(2500, seed=seed, rate=rate, gpu_choices=[1, 2, 4, 8, 16, 32], gpu_probs=[.3, .2, .2, .15, .1, .05],
+                                  max_mem_mib=40000)               # some jobs exceed the 32 GiB device
+    rng = np.random.default_rng(seed)
+    gpc = rng.choice([1, 2, 4], size=2500, p=[.6, .25, .15])
+    cols["gpu_per_container"] = np.minimum(gpc, cols["used_gpus"]).astype(np.int64)
+    table = ingest.table_from_columns(cols)
+    pol = capi.make_policy("sjf")
+    ref = oracle.run_policy(cluster, pol, table)
+    assert int(ref.rows["queued"].max()) > 100                      # several chunks of runnable jobs
+    for engine in (0, 2):
+        rows, recs, order, st = _run(cluster, pol, table, engine=engine)
+        assert rows.tobytes() == ref.rows.tobytes() and recs.tobytes() == ref.recs.tobytes(), engine
+        assert np.array_equal(order, ref.finish_order) and st.events == ref.events, engine
+    rows2, recs2, _, _ = _run(cluster, pol, table, rows_cap=97)
+    assert rows2.tobytes() == ref.rows.tobytes() and recs2.tobytes() == ref.recs.tobytes()
