@@ -1,7 +1,7 @@
 """Host-side policy parameters for the event-driven (Tiresias-style) policies.
 
 `build_gittins_table` restates parse_job_dist / cal_r_gittins_index
-(/root/reference/run_sim.py:1650-1708) with binary searches and prefix sums instead of the
+(/root/reference/run_sim.py:1650-1708) with vectorised binary searches and prefix sums instead of the
 O(n^2) generator scans; the arithmetic (Python round(), association) is kept.  The reference's
 sample file yarn-gput1000.csv is not in the repository, so the sample is the trace's own
 `run length x gpus`.  Pinned: tests/test_policy_golden.py compares the table with the
@@ -9,40 +9,54 @@ output of the reference's parse_job_dist executed verbatim (tests/golden/make_po
 """
 from __future__ import annotations
 
-import bisect
 import sys
 
 import numpy as np
 
 
+def _py_round(x, nd):
+    """Python's round(x, nd) for a float64 array: the value correctly rounded to nd decimals (ties on the EXACT binary
+    value to even), then the nearest double.  rint(x * 10^nd) / 10^nd is that whenever x * 10^nd is not within rounding
+    error of a half-way point -- the quotient of two exactly representable numbers is correctly rounded, like strtod of
+    the decimal string --; the few entries that are go through Python's round()."""
+    scale = 10.0 ** nd
+    y = x * scale
+    out = np.rint(y) / scale
+    frac = np.abs(y - np.floor(y) - 0.5)
+    risky = np.nonzero(~(frac > 8.0 * np.spacing(np.abs(y))))[0]               # x * 10^nd is within 1 ulp; also catches nan / inf
+    for i in risky.tolist():
+        out[i] = round(float(x[i]), nd)
+    return out
+
+
 def build_gittins_table(samples, delta=3250.0):
     """-> (data float64[n+1], index float64[n+1]); data sorted, last entries = (maxsize, 0.0)."""
-    data = sorted(int(x) for x in samples)
+    data = np.sort(np.asarray([int(x) for x in samples] if not isinstance(samples, np.ndarray) else samples, dtype=np.int64))
     num = len(data)
     if num == 0:
         return np.array([float(sys.maxsize)]), np.array([0.0])
-    prefix = [0]
-    for v in data:
-        prefix.append(prefix[-1] + v)
-    last = data[-1]
-
-    def r_index(a):                                    # cal_r_gittins_index(job_data, a)
-        if a > last - 1:
-            return 0.0
-        idx = bisect.bisect_right(data, a)             # first i with data[i] > a
-        next_a = a + delta
-        if next_a > last - 1:
-            idx_delta = num - 1
-        else:
-            idx_delta = bisect.bisect_right(data, next_a)
-        p = round(((idx_delta - idx) * 1.0) / (num - idx), 5)
-        e_sum = (prefix[idx_delta] - prefix[idx]) + (delta * (num - idx_delta))
-        e = round(e_sum / (num - idx), 5)
-        return round(p * 1000000 / e, 4)
-
-    gi = [r_index(int(v - 1)) for v in data]
-    return (np.array([float(v) for v in data] + [float(sys.maxsize)], dtype=np.float64),
-            np.array(gi + [0.0], dtype=np.float64))
+    if int(data[-1]) * num >= 2 ** 53:                  # the sums below are exact in float64 only up to there
+        raise ValueError("gittins sample too large")
+    prefix = np.zeros(num + 1, dtype=np.int64)
+    np.cumsum(data, out=prefix[1:])
+    last = int(data[-1])
+    # cal_r_gittins_index(job_data, a) for a = v - 1 of every sample v, all at once
+    a = data - 1
+    live = ~(a > last - 1)
+    idx = np.searchsorted(data, a, side="right")       # first i with data[i] > a
+    next_a = a + delta                                  # float, like the reference's a + delta
+    idx_delta = np.where(next_a > last - 1, num - 1, np.searchsorted(data, next_a, side="right"))
+    den = np.maximum(num - idx, 1).astype(np.float64)
+    p = _py_round(((idx_delta - idx) * 1.0) / den, 5)
+    e_sum = (prefix[idx_delta] - prefix[idx]).astype(np.float64) + (delta * (num - idx_delta))
+    e = _py_round(e_sum / den, 5)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gi = _py_round(p * 1000000 / e, 4)
+    if np.any(live & ~np.isfinite(gi)):
+        raise ZeroDivisionError("float division by zero")       # what the reference raises for such a sample
+    gi = np.where(live, gi, 0.0)
+    return (np.concatenate([data.astype(np.float64), [float(sys.maxsize)]]),
+            np.concatenate([gi, [0.0]]))
 
 
 def gittins_samples(table):

@@ -61,3 +61,42 @@ def test_gittins_table_matches_reference_parse_job_dist():
     data, gi = policies.build_gittins_table(policies.gittins_samples(table), 3250.0)
     assert data.tolist() == exp["gittins_table"]["data"]
     assert gi.tolist() == exp["gittins_table"]["gittins"]
+
+
+def _gittins_table_scalar(samples, delta):
+    """cal_r_gittins_index (run_sim.py:1650-1708) value by value with Python's round(): what the vectorised builder must equal"""
+    import bisect
+    import sys
+    data = sorted(int(x) for x in samples)
+    num = len(data)
+    prefix = [0]
+    for v in data:
+        prefix.append(prefix[-1] + v)
+    last = data[-1]
+
+    def r_index(a):
+        if a > last - 1:
+            return 0.0
+        idx = bisect.bisect_right(data, a)
+        next_a = a + delta
+        idx_delta = num - 1 if next_a > last - 1 else bisect.bisect_right(data, next_a)
+        p = round(((idx_delta - idx) * 1.0) / (num - idx), 5)
+        e = round(((prefix[idx_delta] - prefix[idx]) + (delta * (num - idx_delta))) / (num - idx), 5)
+        return round(p * 1000000 / e, 4)
+    return (np.array([float(v) for v in data] + [float(sys.maxsize)]), np.array([r_index(int(v - 1)) for v in data] + [0.0]))
+
+
+def test_vectorised_gittins_table_equals_the_scalar_restatement_bit_for_bit():
+    from gpuschedule_b200 import policies, tracegen, ingest
+    rng = np.random.default_rng(3)
+    cases = [policies.gittins_samples(ingest.table_from_columns(tracegen.synth_columns(20000, seed=s))) for s in (1, 2)]
+    cases += [rng.integers(1, 50, 5000), rng.integers(1, 10 ** 7, 20000), np.array([5]), np.array([1, 1, 1, 2]),
+              rng.integers(3000, 3500, 3000), np.arange(1, 4000)]
+    for delta in (3250.0, 10.0, 123.5):
+        for c in cases:
+            a, b = policies.build_gittins_table(c, delta), _gittins_table_scalar(c, delta)
+            assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), (delta, len(c))
+    for nd in (4, 5):                                       # the rounding helper alone, half-way decimals included
+        x = np.concatenate([rng.random(50000) * 10.0 ** rng.integers(-3, 7, 50000), (rng.integers(0, 10 ** 7, 50000) * 10 + 5) / 10.0 ** (nd + 1),
+                            rng.integers(0, 10 ** 6, 20000) / 1024.0, np.array([0.0, 0.5, 1.5, 2.5e-5, 0.000005, 0.000015, 0.000025, 1e-7])])
+        assert policies._py_round(x, nd).tobytes() == np.array([round(float(v), nd) for v in x]).tobytes()
