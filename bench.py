@@ -590,8 +590,6 @@ def ours(args):
         pn = min(n, 100000)                              # C2: 10k-job sjf; C3 / C4: 100k jobs (c5: the same sizes on 16x64x8)
         for name, njobs in (("sjf", min(pn, 10000)), ("dlas-gpu", pn), ("gittins", pn)):
             tabs = tables[:rp] if njobs == n else [fast_table(njobs, sd, rate=cfg["rate"]) for sd in gdist.replica_seeds(0, 1, rp, base=BASE_SEED)]
-            if name == "gittins":
-                tabs = tabs[:max(1, rp // 2)]
             try:
                 extras[name] = policy_measure(name, cluster, tabs, local)
             except Exception as exc:                      # a secondary line never costs the main one
@@ -1008,7 +1006,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the e2e threads to the GPU's NUMA node")
     ap.add_argument("--distinct", type=int, default=0, help="development: number of distinct traces (0 = one per replica)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
-    ap.add_argument("--policy-replicas", type=int, default=2368, help="replicas of the secondary policy runs (gittins: half); they are latency bound per replica: 1024 -> 2368 replicas is 1.7-2x the throughput")
+    ap.add_argument("--policy-replicas", type=int, default=2368, help="replicas of the secondary policy runs; they are latency bound per replica: 1024 -> 2368 replicas is 1.7-2x the throughput")
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-simulation-on-N-GPUs block (config C4)")
     ap.add_argument("--sharded-jobs", type=int, default=100000)
     ap.add_argument("--sharded-rate", type=float, default=0.5, help="arrivals per tick of the C4 trace (0.5 = the BASELINE generator; higher rates build a long runnable list)")

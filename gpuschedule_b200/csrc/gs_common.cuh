@@ -54,6 +54,8 @@ struct SimDev {
   int *runnable, *queues, *endj, *tmpl, *cidle, *ckfree;   // queues: num_queue lists of n entries
   int *stalej;                // end list a start event inherited from a tie it lost to a jump (quirk Q25)
   const double *git_data, *git_index;                      // device copies of the gittins tables
+  const double *git_direct;                                // index value for every integer attained service below git_direct_n (or null)
+  long long git_direct_n;
   double queue_limit[GS_MAX_QUEUES];
   double gittins_delta, next_gittins_unit;
   int num_queue, git_n, rn, en, end_time, next_job_jump, stale_n, qn[GS_MAX_QUEUES];

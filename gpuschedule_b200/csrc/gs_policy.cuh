@@ -10,6 +10,13 @@
 // event re-evaluates all runnable jobs (counter update, ordering, emptied-cluster greedy
 // re-admission), exactly as the specification does.  Lists live in global memory.
 __device__ __forceinline__ double git_lookup(const SimDev &S, double a) {
+  // attained service is a whole number of (GPU) ticks: when the table's range is small enough the host tabulates the
+  // answer for every integer up to the largest sample (gs_config_sim) and the bisection below -- 17 dependent loads into
+  // a 1.6 MB table for a 100k-job trace -- becomes one load
+  if (a >= 0.0 && a < (double)S.git_direct_n) {
+    const int k = (int)a;
+    if ((double)k == a) return S.git_direct[k];
+  }
   const int n = S.git_n;
   if (n < 2 || a > S.git_data[n - 2]) return 0.0;
   int lo = 0, hi = n - 1;
@@ -569,6 +576,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
   unsigned long long epoch = S.comm_epoch;
   long long wait_cycles = 0;
   int status = 0;
+  const double rank_new = sjf ? 0.0 : git_lookup(S, 0.0);        // a new job: executed_time == 0
 
   while (budget > 0 && (ticks - row_first) < rows_cap) {
     if (!((n - p) + rn > 0)) { done = true; break; }
@@ -687,8 +695,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
       }
       events += cnt;
       if (!sjf) {
-        const double r0 = git_lookup(S, 0.0);              // a new job: executed_time == 0
-        for (int i = lane; i < cnt; i += 32) { runnable[rn + i] = p + i; rk[rn + i] = r0; }
+        for (int i = lane; i < cnt; i += 32) { runnable[rn + i] = p + i; rk[rn + i] = rank_new; }
         rn += cnt;
       }
     }
@@ -737,9 +744,32 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
     }
     p += cnt;
     __syncwarp();
-    // ---- greedy re-admission on the emptied cluster, in list order
+    // ---- greedy re-admission on the emptied cluster, in list order; the chunk that has just been decided also feeds
+    // the next completion (ties in list order) and the statistics, while its records are still in registers
     int busy = 0;
     long long mem_busy = 0;
+    end_time = 0x7fffffff; en = 0;
+    int running = 0, queued = 0, pmax = 0;
+    long long psum = 0;
+#define SORTPOL_ACCOUNT(valid_, j_, r_, dur_)                                                         \
+    do {                                                                                              \
+      int e_ = 0x7fffffff, pend_ = 0;                                                                 \
+      const bool isrun_ = (valid_) && (r_).status == PST_RUNNING;                                     \
+      if (isrun_) {                                                                                   \
+        const double cl_ = ceil(dur_);                                                                \
+        const int D_ = cl_ < 1.0 ? 1 : (int)cl_;                                                      \
+        e_ = event_time + (D_ - (r_).total_exec);                                                     \
+      } else if (valid_) pend_ = (r_).pending;                                                        \
+      const int cmin_ = __reduce_min_sync(FULL, e_);                                                  \
+      if (cmin_ < end_time) { end_time = cmin_; en = 0; }                                             \
+      const unsigned eb_ = __ballot_sync(FULL, isrun_ && e_ == end_time);                             \
+      if (isrun_ && e_ == end_time) endj[en + __popc(eb_ & lt)] = (j_);                               \
+      en += __popc(eb_);                                                                              \
+      running += __popc(__ballot_sync(FULL, isrun_));                                                 \
+      queued += __popc(__ballot_sync(FULL, (valid_) && !isrun_));                                     \
+      pmax = max(pmax, __reduce_max_sync(FULL, pend_));                                               \
+      psum += (long long)__reduce_add_sync(FULL, pend_);                                              \
+    } while (0)
     if (sjf) {
       for (int nd = lane; nd < M; nd += 32) { nidle[nd] = G; nkfree[nd] = K; }
       __syncwarp();
@@ -756,7 +786,9 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         long long memb = 0;
         PJob r;
         r.status = PST_NONE; r.start = -1; r.resume = 0;
-        if (valid) { const JobIn jr = jobs[j]; hg = jr.gpus; hc = jr.gpc; memb = jr.memb; r = pj[j]; }
+        double dur = 0.0;
+        r.total_exec = 0; r.pending = 0;
+        if (valid) { const JobIn jr = jobs[j]; hg = jr.gpus; hc = jr.gpc; memb = jr.memb; dur = jr.dur; r = pj[j]; }
         const bool fit = valid && memb < fit_limit;
         const unsigned fb = __ballot_sync(FULL, fit);
         const int phg = __shfl_up_sync(FULL, hg, 1), phc = __shfl_up_sync(FULL, hc, 1);
@@ -833,6 +865,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mc += __shfl_xor_sync(FULL, mc, o);
         mem_busy += mc;
+        SORTPOL_ACCOUNT(valid, j, r, dur);
       }
     } else {
       int free_gpu = total_gpus;
@@ -841,7 +874,7 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         const bool valid = idx < rn;
         const int j = valid ? runnable[idx] : 0;
         PJob r; JobIn jr;
-        r.status = PST_NONE; r.start = -1; r.resume = 0; jr.memb = 0; jr.gpus = 0;
+        r.status = PST_NONE; r.start = -1; r.resume = 0; r.total_exec = 0; r.pending = 0; jr.memb = 0; jr.gpus = 0; jr.dur = 0.0;
         int g = 0;
         if (valid) { r = pj[j]; jr = jobs[j]; g = jr.gpus; }
         bool admitted = false, decided = !valid;
@@ -868,38 +901,12 @@ __global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int n
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mc += __shfl_xor_sync(FULL, mc, o);
         mem_busy += mc;
+        SORTPOL_ACCOUNT(valid, j, r, jr.dur);
       }
     }
+#undef SORTPOL_ACCOUNT
     __syncwarp();
-    // ---- final pass: next completion (ties in list order) and statistics
-    end_time = 0x7fffffff; en = 0;
-    int running = 0, queued = 0, pmax = 0;
-    long long psum = 0;
-    for (int base = 0; base < rn; base += 32) {
-      const int idx = base + lane;
-      const bool valid = idx < rn;
-      const int j = valid ? runnable[idx] : 0;
-      int e = 0x7fffffff, pend = 0;
-      bool isrun = false;
-      if (valid) {
-        const PJob r = pj[j];
-        isrun = r.status == PST_RUNNING;
-        if (isrun) {
-          const double cl = ceil(jobs[j].dur);
-          const int D = cl < 1.0 ? 1 : (int)cl;
-          e = event_time + (D - r.total_exec);
-        } else pend = r.pending;
-      }
-      const int cmin = __reduce_min_sync(FULL, e);
-      if (cmin < end_time) { end_time = cmin; en = 0; }
-      const unsigned eb = __ballot_sync(FULL, valid && isrun && e == end_time);
-      if (valid && isrun && e == end_time) endj[en + __popc(eb & lt)] = j;
-      en += __popc(eb);
-      running += __popc(__ballot_sync(FULL, valid && isrun));
-      queued += __popc(__ballot_sync(FULL, valid && !isrun));
-      pmax = max(pmax, __reduce_max_sync(FULL, pend));
-      psum += (long long)__reduce_add_sync(FULL, pend);
-    }
+    // ---- next completion and statistics were accumulated chunk by chunk above
     if (!sjf) next_git += (double)event_time;
     int busy_nodes = 0;
     if (sjf) for (int base = 0; base < M; base += 32) { const int nd = base + lane; busy_nodes += __popc(__ballot_sync(FULL, nd < M && nidle[nd] < G)); }

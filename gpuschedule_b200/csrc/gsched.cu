@@ -73,6 +73,7 @@ struct SimHost {
   void *trace_slab = nullptr;
   void *state_slab = nullptr;
   void *git_dev = nullptr;
+  long long git_direct_n = 0;       // entries of the direct look-up table behind the two gittins tables in git_dev
   size_t trace_bytes = 0, state_bytes = 0;
   int64_t span_cap = 0, rows_cap = 0, qrows_cap = 0, last_arrive = 0;
   int max_need = 1;
@@ -232,18 +233,36 @@ extern "C" int gs_config_sim(gs_handle h, int sim, const gs_cluster *cluster, co
       (pol.num_queue < 1 || pol.num_queue > GS_MAX_QUEUES))
     return fail(h, GS_ERR_ARG, "gs_config_sim: num_queue must be in 1..8 for dlas");
   void *git_dev = nullptr;
+  long long git_direct_n = 0;
   if (pol.schedule == GS_SCHED_GITTINS) {
     if (pol.gittins_n < 1 || !pol.gittins_data || !pol.gittins_index)
       return fail(h, GS_ERR_ARG, "gs_config_sim: gittins needs the (data, index) tables");
     CU(cudaSetDevice(h->device));
     const size_t bytes = 8 * (size_t)pol.gittins_n;
-    CU(cudaMalloc(&git_dev, 2 * bytes));
+    // direct form of the look-up "index of the first sample above a" for whole-number a (attained service always is one):
+    // one entry per integer up to the largest sample, when that is not out of proportion with the table itself
+    std::vector<double> direct;
+    if (pol.gittins_n >= 2) {
+      const double last = pol.gittins_data[pol.gittins_n - 2];
+      if (last >= 0.0 && last < 8.0 * (double)pol.gittins_n + 65536.0 && last < 67108864.0) {
+        direct.resize((size_t)last + 1);
+        size_t idx = 0;
+        for (size_t k = 0; k < direct.size(); ++k) {
+          while (idx + 1 < (size_t)pol.gittins_n && !(pol.gittins_data[idx] > (double)k)) ++idx;
+          direct[k] = pol.gittins_index[idx];
+        }
+      }
+    }
+    git_direct_n = (long long)direct.size();
+    CU(cudaMalloc(&git_dev, 2 * bytes + 8 * direct.size()));
     cudaError_t e1 = cudaMemcpy(git_dev, pol.gittins_data, bytes, cudaMemcpyHostToDevice);
     cudaError_t e2 = cudaMemcpy((unsigned char *)git_dev + bytes, pol.gittins_index, bytes, cudaMemcpyHostToDevice);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(git_dev); return fail(h, GS_ERR_CUDA, "gs_config_sim: gittins table upload failed"); }
+    cudaError_t e3 = direct.empty() ? cudaSuccess : cudaMemcpy((unsigned char *)git_dev + 2 * bytes, direct.data(), 8 * direct.size(), cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cudaFree(git_dev); return fail(h, GS_ERR_CUDA, "gs_config_sim: gittins table upload failed"); }
   }
   if (s.git_dev) cudaFree(s.git_dev);
   s.git_dev = git_dev;
+  s.git_direct_n = git_direct_n;
   s.cl = *cluster;
   s.pol = pol;
   s.pol.gittins_data = s.pol.gittins_index = nullptr;   // host pointers are not retained past this call
@@ -473,6 +492,8 @@ static int bind_sim(gs_handle h, SimHost &s, const SimLayout &L, unsigned char *
     D.git_n = s.pol.schedule == GS_SCHED_GITTINS ? s.pol.gittins_n : 0;
     D.git_data = (const double *)s.git_dev;
     D.git_index = s.git_dev ? (const double *)((unsigned char *)s.git_dev + 8 * (size_t)s.pol.gittins_n) : nullptr;
+    D.git_direct_n = (s.git_dev && D.git_n > 0) ? s.git_direct_n : 0;
+    D.git_direct = D.git_direct_n > 0 ? (const double *)((unsigned char *)s.git_dev + 16 * (size_t)s.pol.gittins_n) : nullptr;
     D.rn = 0; D.en = 0; D.end_time = 0x7fffffff; D.next_job_jump = 0x7fffffff;
   }
   D.comm_n = 0; D.comm_rank = 0; D.comm_cap = 0; D.comm_rk_in = nullptr; D.comm_flags = nullptr; D.comm_epoch = 0; D.comm_wait_cycles = 0;

@@ -172,3 +172,26 @@ def test_sjf_long_lists_mixed_tasks_and_oversize_jobs(ckw, rate, seed):
         assert np.array_equal(order, ref.finish_order) and st.events == ref.events, engine
     rows2, recs2, _, _ = _run(cluster, pol, table, rows_cap=97)
     assert rows2.tobytes() == ref.rows.tobytes() and recs2.tobytes() == ref.recs.tobytes()
+
+
+@pytest.mark.parametrize("stretch", [1, 40000], ids=["direct-table", "bisection"])
+def test_gittins_lookup_forms_agree_with_the_oracle(stretch):
+    """gs_config_sim tabulates the gittins index per whole unit of attained service when the largest sample allows it and
+    the kernel then reads it with one load; a table whose samples are far apart (here: stretched by 40000) keeps the
+    bisection.  Both against oracle/policy_oracle.c, which always bisects."""
+    import oracle
+    from gpuschedule_b200 import capi, ingest, policies, tracegen
+    cluster = capi.make_cluster(num_switch=1, num_node_p_switch=6)
+    table = ingest.table_from_columns(tracegen.synth_columns(1200, seed=31, rate=1.5, gpu_choices=[1, 2, 4, 8], gpu_probs=[.4, .3, .2, .1]))
+    samples = policies.gittins_samples(table) * stretch
+    data, index = policies.build_gittins_table(samples, 3250.0 * stretch)
+    if stretch > 1:                                         # the same index values at far-apart, partly non-integer sample positions
+        base = np.sort(policies.gittins_samples(table)).astype(np.float64) + 0.25 * (np.arange(len(data) - 1) % 2)
+        data = np.concatenate([np.sort(base) * stretch, data[-1:]])
+    pol = capi.make_policy("gittins", gittins_delta=3250.0, gittins_table=(data, index))
+    ref = oracle.run_policy(cluster, pol, table)
+    for engine in (0, 2):
+        rows, recs, order, st = _run(cluster, pol, table, engine=engine)
+        assert rows.tobytes() == ref.rows.tobytes() and recs.tobytes() == ref.recs.tobytes(), engine
+        assert np.array_equal(order, ref.finish_order) and st.events == ref.events, engine
+    assert st.events > 3 * 1200                             # preemptions happened: ranks were compared, not only read
