@@ -637,7 +637,7 @@ class Engine:
         self._check(self.lib.gs_comm_init(self.h, int(rank), len(handles), C.cast(buf, C.c_void_p)), "gs_comm_init")
 
     def comm_set_min_runnable(self, k):
-        """events with at most k runnable jobs are evaluated locally by every rank (default 256); 0 = always exchange"""
+        """events with at most k runnable jobs are evaluated locally by every rank; 0 = always exchange; default: never exchange (include/gsched.h)"""
         self._check(self.lib.gs_comm_set_min_runnable(self.h, int(k)), "gs_comm_set_min_runnable")
 
     def comm_stats(self):

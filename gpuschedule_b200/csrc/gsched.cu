@@ -109,7 +109,7 @@ struct gs_engine {
   // sharded single simulation (gs_comm_prepare / gs_comm_init)
   void *comm_buf = nullptr; int64_t comm_cap = 0; int comm_rank = 0, comm_n = 0;
   void *comm_peer[GS_MAX_RANKS] = {nullptr}; bool comm_opened[GS_MAX_RANKS] = {false};
-  int comm_min_runnable = 256;             // gs_comm_set_min_runnable
+  int comm_min_runnable = 0x7fffffff;      // gs_comm_set_min_runnable: no exchange unless the caller asks for one (include/gsched.h)
   unsigned long long comm_epoch = 0, comm_epoch0 = 0;   // exchange counter: continues across runs / value at the last prepare
   bool dirty = true;       // host mirror of SimDev newer than device copy
 };

@@ -337,9 +337,11 @@ typedef struct gs_comm_handle { unsigned char bytes[64]; } gs_comm_handle;
 int gs_comm_prepare(gs_handle h, int64_t max_jobs, gs_comm_handle *out);
 int gs_comm_init(gs_handle h, int rank, int nranks, const gs_comm_handle *all_ranks);
 int gs_comm_stats(gs_handle h, int64_t *exchanges, double *mean_us);
-/* An exchange costs a few microseconds; a runnable list of a few dozen jobs is evaluated faster than that by one GPU.
- * Events with at most k runnable jobs (default 256) are therefore evaluated by every rank itself -- the replicated state
- * guarantees identical results without sending anything -- and only longer lists are split.  k = 0: always exchange. */
+/* Events with at most k runnable jobs are evaluated by every rank itself -- the replicated state guarantees identical
+ * results without sending anything -- and only longer lists are split and exchanged.  k = 0: always exchange.
+ * DEFAULT: no list is long enough (k = INT32_MAX).  An exchange costs 2-4 us, and since the index of a job is one table
+ * load (the direct table of gs_config_sim) no list we measured -- up to ~7000 runnable jobs -- is evaluated slower by
+ * one GPU than an exchange takes (DESIGN section 7 has the numbers); the call is how a caller opts in. */
 int gs_comm_set_min_runnable(gs_handle h, int k);
 
 /* Stateless candidate scoring: evaluate b jobs against ONE cluster state.
