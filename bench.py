@@ -1008,7 +1008,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the e2e threads to the GPU's NUMA node")
     ap.add_argument("--distinct", type=int, default=0, help="development: number of distinct traces (0 = one per replica)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary policy / place_batch measurements")
-    ap.add_argument("--policy-replicas", type=int, default=2368, help="replicas of the secondary policy runs; they are latency bound per replica: 1024 -> 2368 replicas is 1.7-2x the throughput")
+    ap.add_argument("--policy-replicas", type=int, default=2960, help="replicas of the secondary policy runs; 148 SMs x the 20 warps the policy kernels keep resident per SM")
     ap.add_argument("--no-sharded", action="store_true", help="skip the one-simulation-on-N-GPUs block (config C4)")
     ap.add_argument("--sharded-jobs", type=int, default=100000)
     ap.add_argument("--sharded-rate", type=float, default=0.5, help="arrivals per tick of the C4 trace (0.5 = the BASELINE generator; higher rates build a long runnable list)")

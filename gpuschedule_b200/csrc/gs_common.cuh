@@ -5,6 +5,10 @@
 #ifndef GS_TICK_MINBLOCKS
 #define GS_TICK_MINBLOCKS 28     // 72 registers: no spills (64 spill), 28 warps per SM; measured best (profiles/r02_kernel_versions.md)
 #endif
+#ifndef GS_POLICY_MINBLOCKS
+#define GS_POLICY_MINBLOCKS 20   // event-driven policy kernels (one warp per replica): resident warps per SM the registers are cut for (96 / 94 registers);
+                                 // measured 16 / 20 / 24: sjf 8.9 / 8.8 / 9.5e8, dlas-gpu 1.23 / 1.32 / 1.31e9, gittins 1.31 / 1.39 / 1.40e9 events/s at 148 x that many replicas
+#endif
 #define FULL 0xffffffffu
 
 // ------------------------------------------------------------------ device state

@@ -267,7 +267,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsims, long long max_ticks) {
+__global__ void __launch_bounds__(32, GS_POLICY_MINBLOCKS) gs_dlas_warp_kernel(SimDev *sims, int nsims, long long max_ticks) {
   const int sim = blockIdx.x;
   const int lane = threadIdx.x;
   if (sim >= nsims) return;
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(32) gs_dlas_warp_kernel(SimDev *sims, int nsim
 // sjf (keys never change), so new arrivals are INSERTED (count of keys <= k, warp-parallel shift);
 // gittins ranks move a little every event, so the list is repaired with stable odd-even
 // transposition rounds (adjacent swaps only when strictly greater == the unique stable order).
-__global__ void __launch_bounds__(32) gs_sortpol_warp_kernel(SimDev *sims, int nsims, long long max_ticks) {
+__global__ void __launch_bounds__(32, GS_POLICY_MINBLOCKS) gs_sortpol_warp_kernel(SimDev *sims, int nsims, long long max_ticks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int sim = blockIdx.x;
   const int lane = threadIdx.x;
