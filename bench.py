@@ -720,27 +720,44 @@ def sharded_block(args, rank, world, local, dev):
     cluster = capi.make_cluster(4, 32, 8)
     red = gdist.Reducer(world, dev)
 
-    def timed(eng, table, pol, reps=2):
-        eng.config(0, cluster, pol)
-        eng.load_trace_packed(0, table.packed())
-        run_to_done(eng, 0)
-        cap = eng.stats(0).ticks + 64
-        best = None
+    # Every rank reaches the same collectives (barriers, reductions, the handle all-gather) whatever fails locally: a
+    # failure is carried as `err` and agreed on afterwards, so a rank with a problem cannot leave its peers in a collective.
+    def timed(eng, table, pol, reps=2, err=None):
+        best, events, blob, cap = None, 0, None, 0
+        if err is None:
+            try:
+                eng.config(0, cluster, pol)
+                eng.load_trace_packed(0, table.packed())
+                run_to_done(eng, 0)                      # (sharded: a peer that never starts ends this with GS_ERR_COMM after ~5 s)
+                cap = eng.stats(0).ticks + 64
+            except Exception as exc:                      # noqa: BLE001
+                err = repr(exc)
         for _ in range(reps):
-            eng.reset()
             red.barrier()
-            run_to_done(eng, cap)
-            ms = eng.stats(0).kernel_ms
-            best = ms if best is None else min(best, ms)
-        rows = eng.fetch_rows(0)
-        recs, order = eng.fetch_jobs(0)
-        return best, eng.stats(0).events, (rows.tobytes(), recs.tobytes(), order.tobytes())
+            if err is None:
+                try:
+                    eng.reset()
+                    run_to_done(eng, cap)
+                    ms = eng.stats(0).kernel_ms
+                    best = ms if best is None else min(best, ms)
+                except Exception as exc:                  # noqa: BLE001
+                    err = repr(exc)
+        if err is None:
+            try:
+                rows = eng.fetch_rows(0)
+                recs, order = eng.fetch_jobs(0)
+                events, blob = eng.stats(0).events, (rows.tobytes(), recs.tobytes(), order.tobytes())
+            except Exception as exc:                      # noqa: BLE001
+                err = repr(exc)
+        return best, events, blob, err
 
     def one(n, rate, reps=2):
         table = fast_table(n, BASE_SEED, rate=rate)
         pol = make_policy("gittins", table)
         with capi.Engine(device=local, nsims=1) as e1:
-            ms1, events, single = timed(e1, table, pol, reps)
+            ms1, events, single, err1 = timed(e1, table, pol, reps)
+        if red.sum(1.0 if err1 else 0.0) > 0:
+            return {"jobs": n, "arrivals_per_tick": rate, "error": err1 or "another rank failed its single-GPU run"}
         ms1 = red.max(ms1)
         out = {"jobs": n, "arrivals_per_tick": rate, "events": int(events),
                "single_gpu": {"ms": ms1, "events_per_s": events / (ms1 / 1e3)}}
@@ -750,12 +767,26 @@ def sharded_block(args, rank, world, local, dev):
             # default after gs_comm_init, which exchanges only when the caller sets a threshold (no measured list pays for one)
             for key, min_rn in (("sharded_always_exchange", 0), ("sharded_above_256", 256), ("sharded", None)):
                 with capi.Engine(device=local, nsims=1) as e2:
-                    handles = gdist.exchange_comm_handles(e2.comm_prepare(n), world, dev)
-                    e2.comm_init(rank, handles)
-                    if min_rn is not None:
-                        e2.comm_set_min_runnable(min_rn)
-                    msN, eventsN, shard = timed(e2, table, pol, reps)
-                    exchanges, us = e2.comm_stats()
+                    err, hnd = None, bytes(64)
+                    try:
+                        hnd = e2.comm_prepare(n)
+                    except Exception as exc:              # noqa: BLE001
+                        err = repr(exc)
+                    handles = gdist.exchange_comm_handles(hnd, world, dev)
+                    if err is None:
+                        try:
+                            e2.comm_init(rank, handles)
+                            if min_rn is not None:
+                                e2.comm_set_min_runnable(min_rn)
+                        except Exception as exc:          # noqa: BLE001
+                            err = repr(exc)
+                    msN, eventsN, shard, err = timed(e2, table, pol, reps, err)
+                    exchanges, us = (0, 0.0)
+                    if err is None:
+                        exchanges, us = e2.comm_stats()
+                if red.sum(1.0 if err else 0.0) > 0:
+                    out[key] = {"error": err or "another rank failed"}
+                    continue
                 same = red.sum(1.0 if (shard == single and eventsN == events) else 0.0)
                 msN = red.max(msN)
                 out[key] = {"ms": msN, "events_per_s": events / (msN / 1e3), "min_runnable_for_exchange": min_rn if min_rn is not None else "library default (never)", "exchanges": exchanges,
