@@ -922,6 +922,23 @@ def horus_mode(args):
     t0 = time.perf_counter()
     cpu_ev = sum(oracle.run_horus(cluster, tables[r], scheme="horus", schedule="horus", num_buffer=5, seed=0).events for r in range(sample))
     cpu_s = time.perf_counter() - t0
+    # the honest CPU yardstick: the ENGINE's own core (gs_horus_core.cuh, with its shortcuts) compiled for the host by the
+    # test harness (tests/emu), one core, same replicas and stream -- what `cpu_tight` is for the fifo engine
+    tight = None
+    try:
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import emu
+        emu.lib()
+        k = min(R, 256)
+        t0 = time.perf_counter()
+        tight_ev = sum(emu.run_horus(cluster, hp, tables[r], stream, args.horus_rows)[6] for r in range(k))
+        tight_s = time.perf_counter() - t0
+        tight = {"value": tight_ev / tight_s, "unit": UNIT, "cores": 1,
+                 "kind": "the engine's own core (gs_horus_core.cuh) built for the host with g++ -O2 (tests/emu), not reference code",
+                 "sample": f"{k} of the {R} replicas, one thread",
+                 "gpu_in_cores_of_it": (events / (ms / 1e3)) / (tight_ev / tight_s)}
+    except Exception as exc:                                # noqa: BLE001
+        tight = {"error": repr(exc)}
     # the warp-cooperative mapping (one simulation per warp, all lanes score together): LAST, in its own handle, so
     # that whatever it does cannot touch the numbers above
     coop = None
@@ -966,7 +983,8 @@ def horus_mode(args):
                       "parity": "replica 0 == oracle/horus_oracle.c == reference (tests/golden/horus_*)",
                       "horus_plus_device_check": plus, "cooperative_warp_mapping": coop,
                       "cpu_baseline": {"value": cpu_ev / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
-                                       "sample": f"{sample} of the {R} replicas, oracle/horus_oracle.c, one thread"}}), flush=True)
+                                       "sample": f"{sample} of the {R} replicas, oracle/horus_oracle.c, one thread"},
+                      "cpu_tight": tight}), flush=True)
 
 
 def reference(args):
