@@ -54,10 +54,12 @@ extern "C" void gs_logcol_close(gs_logcol c) { delete c; }
 // busy devices per row (= values the row consumes), rows 0 .. n_rows-1
 extern "C" int gs_logcol_counts(gs_logcol c, int64_t *counts) {
   if (!c || (!counts && c->n_rows > 0)) return GS_ERR_ARG;
-  std::vector<int64_t> diff((size_t)c->n_rows + 1, 0);
-  for (int64_t i = 0; i < c->n_hold; ++i) { diff[c->first[i]] += 1; diff[c->last[i] + 1] -= 1; }
-  int64_t run = 0;
-  for (int64_t r = 0; r < c->n_rows; ++r) { run += diff[r]; counts[r] = run; }
+  try {
+    std::vector<int64_t> diff((size_t)c->n_rows + 1, 0);
+    for (int64_t i = 0; i < c->n_hold; ++i) { diff[c->first[i]] += 1; diff[c->last[i] + 1] -= 1; }
+    int64_t run = 0;
+    for (int64_t r = 0; r < c->n_rows; ++r) { run += diff[r]; counts[r] = run; }
+  } catch (...) { return GS_ERR_STATE; }      // host allocation failed: nothing may be thrown across the C ABI
   return GS_OK;
 }
 
